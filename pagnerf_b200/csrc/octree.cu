@@ -1,0 +1,402 @@
+// Occupancy-octree query, ray marching ('ray' and 'voxel') and packed-ray bookkeeping.
+//
+// Replaces (behind the same grid.raymarch() surface, reference grids/occtree.py:85-91):
+//   kaolin.ops.spc.unbatched_query, kaolin.render.spc.unbatched_raytrace,
+//   wisp OctreeAS.raymarch (sample_from_depth_intervals / linspace+rand+mask compaction),
+//   kaolin.render.spc.mark_pack_boundaries.
+// Design (B200): one warp per ray for 'ray' mode (lanes = steps, ballot compaction), one thread
+// per ray DFS for 'voxel' mode; both are count -> scan -> emit so that no per-level host sync
+// exists (upstream syncs once per octree level).  The octree bytes + prefix (<= 1.5 MB at
+// level 7) stay L1/L2 resident; outputs are written once, packed.
+// Integer outputs are bit-exact against oracle/spc.py + oracle/raymarch.py.
+#include "common.cuh"
+
+#define PAG_MAX_LEVEL 10
+
+// ---------------------------------------------------------------------------------------------
+// point query
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int octree_query_point(const uint8_t* __restrict__ octree,
+                                                  const int* __restrict__ prefix,
+                                                  float x, float y, float z, int level) {
+    const float res = (float)(1 << level);
+    const float qx = floorf(__fmul_rn(res, __fadd_rn(__fmul_rn(x, 0.5f), 0.5f)));
+    const float qy = floorf(__fmul_rn(res, __fadd_rn(__fmul_rn(y, 0.5f), 0.5f)));
+    const float qz = floorf(__fmul_rn(res, __fadd_rn(__fmul_rn(z, 0.5f), 0.5f)));
+    if (!(qx >= 0.f && qx < res && qy >= 0.f && qy < res && qz >= 0.f && qz < res)) return -1;
+    if (isinf(x) || isinf(y) || isinf(z)) return -1;
+    const int ix = (int)qx, iy = (int)qy, iz = (int)qz;
+    int node = 0;
+    for (int l = 0; l < level; ++l) {
+        const int s = level - 1 - l;
+        const uint32_t j = (((ix >> s) & 1) << 2) | (((iy >> s) & 1) << 1) | ((iz >> s) & 1);
+        const uint32_t byte = __ldg(octree + node);
+        if (!((byte >> j) & 1u)) return -1;
+        node = __ldg(prefix + node) + __popc(byte & ((2u << j) - 1u));
+    }
+    return node;
+}
+
+__global__ void octree_query_kernel(const uint8_t* __restrict__ octree, const int* __restrict__ prefix,
+                                    const float* __restrict__ coords, int64_t P, int level,
+                                    int* __restrict__ pidx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    pidx[i] = octree_query_point(octree, prefix, coords[3 * i], coords[3 * i + 1], coords[3 * i + 2], level);
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-CTA exclusive scan (N <= ~1M per-ray counts); writes total to out[N]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restrict__ in, int64_t N,
+                                                               int64_t* __restrict__ out) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t per = (N + 1023) / 1024;
+    const int64_t lo = min((int64_t)tid * per, N), hi = min(lo + per, N);
+    int64_t s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += in[i];
+    int64_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t w = warp_sums[lane];
+        int64_t wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        warp_sums[lane] = wi - w;  // exclusive warp offsets
+        if (lane == 31) carry_s = wi;
+    }
+    __syncthreads();
+    int64_t run = warp_sums[wid] + incl - s;
+    for (int64_t i = lo; i < hi; ++i) { out[i] = run; run += in[i]; }
+    if (tid == 0) out[N] = carry_s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 'ray' mode
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ray_step_depth(int64_t ray, int i, int S, const float* __restrict__ lin,
+                                                const float* __restrict__ jitter, uint32_t seed,
+                                                float near, float range) {
+    const uint64_t flat = (uint64_t)ray * (uint64_t)S + (uint64_t)i;
+    const float u = jitter ? __ldg(jitter + flat) : pag_jitter(seed, flat);
+    float t = __fadd_rn(__ldg(lin + i), __fdiv_rn(u, (float)S));
+    t = __fmul_rn(t, range);
+    return __fadd_rn(t, near);
+}
+
+__global__ void march_ray_count_kernel(const float* __restrict__ org, const float* __restrict__ dir, int64_t N,
+                                       int S, const float* __restrict__ lin, const float* __restrict__ jitter,
+                                       uint32_t seed, float near, float range,
+                                       const uint8_t* __restrict__ octree, const int* __restrict__ prefix,
+                                       int level, int* __restrict__ pidx_tmp, int* __restrict__ counts) {
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= N) return;
+    const float ox = org[3 * ray], oy = org[3 * ray + 1], oz = org[3 * ray + 2];
+    const float dx = dir[3 * ray], dy = dir[3 * ray + 1], dz = dir[3 * ray + 2];
+    int cnt = 0;
+    for (int base = 0; base < S; base += 32) {
+        const int i = base + lane;
+        int p = -1;
+        if (i < S) {
+            const float t = ray_step_depth(ray, i, S, lin, jitter, seed, near, range);
+            const float x = __fadd_rn(ox, __fmul_rn(dx, t));
+            const float y = __fadd_rn(oy, __fmul_rn(dy, t));
+            const float z = __fadd_rn(oz, __fmul_rn(dz, t));
+            p = octree_query_point(octree, prefix, x, y, z, level);
+            pidx_tmp[ray * S + i] = p;
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, p >= 0));
+    }
+    if (lane == 0) counts[ray] = cnt;
+}
+
+__global__ void march_ray_emit_kernel(const float* __restrict__ org, const float* __restrict__ dir, int64_t N,
+                                      int S, const float* __restrict__ lin, const float* __restrict__ jitter,
+                                      uint32_t seed, float near, float range,
+                                      const int* __restrict__ pidx_tmp, const int64_t* __restrict__ offsets,
+                                      int64_t* __restrict__ ridx, int64_t* __restrict__ pidx,
+                                      float* __restrict__ samples, float* __restrict__ depths,
+                                      float* __restrict__ deltas, uint8_t* __restrict__ boundary) {
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= N) return;
+    const int64_t first = offsets[ray];
+    if (offsets[ray + 1] == first) return;
+    const float ox = org[3 * ray], oy = org[3 * ray + 1], oz = org[3 * ray + 2];
+    const float dx = dir[3 * ray], dy = dir[3 * ray + 1], dz = dir[3 * ray + 2];
+    int64_t off = first;
+    for (int base = 0; base < S; base += 32) {
+        const int i = base + lane;
+        const int p = (i < S) ? pidx_tmp[ray * S + i] : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, p >= 0);
+        if (p >= 0) {
+            const int64_t dst = off + __popc(bal & ((1u << lane) - 1u));
+            const float t = ray_step_depth(ray, i, S, lin, jitter, seed, near, range);
+            const float tp = (i == 0) ? near : ray_step_depth(ray, i - 1, S, lin, jitter, seed, near, range);
+            ridx[dst] = ray;
+            pidx[dst] = p;
+            samples[3 * dst + 0] = __fadd_rn(ox, __fmul_rn(dx, t));
+            samples[3 * dst + 1] = __fadd_rn(oy, __fmul_rn(dy, t));
+            samples[3 * dst + 2] = __fadd_rn(oz, __fmul_rn(dz, t));
+            depths[dst] = t;
+            deltas[dst] = __fsub_rn(t, tp);
+            boundary[dst] = (dst == first) ? 1 : 0;
+        }
+        off += __popc(bal);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 'voxel' mode: per-ray DFS in kaolin's nugget order (children j = code ^ i)
+// ---------------------------------------------------------------------------------------------
+struct RayCtx { float ox, oy, oz, dx, dy, dz, ix, iy, iz, sx, sy, sz; };
+
+__device__ __forceinline__ float ray_aabb(const RayCtx& r, float vcx, float vcy, float vcz, float rad, float* exit_t) {
+    const float ox = __fsub_rn(r.ox, vcx), oy = __fsub_rn(r.oy, vcy), oz = __fsub_rn(r.oz, vcz);
+    const float cmax = fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz));
+    const float d0 = __fmul_rn(__fmaf_rn(rad, r.sx, -ox), r.ix);
+    const float d1 = __fmul_rn(__fmaf_rn(rad, r.sy, -oy), r.iy);
+    const float d2 = __fmul_rn(__fmaf_rn(rad, r.sz, -oz), r.iz);
+    const bool t0 = (d0 >= 0.f) && (fabsf(__fmaf_rn(r.dy, d0, oy)) < rad) && (fabsf(__fmaf_rn(r.dz, d0, oz)) < rad);
+    const bool t1 = (d1 >= 0.f) && (fabsf(__fmaf_rn(r.dx, d1, ox)) < rad) && (fabsf(__fmaf_rn(r.dz, d1, oz)) < rad);
+    const bool t2 = (d2 >= 0.f) && (fabsf(__fmaf_rn(r.dx, d2, ox)) < rad) && (fabsf(__fmaf_rn(r.dy, d2, oy)) < rad);
+    float entry = t0 ? d0 : (t1 ? d1 : (t2 ? d2 : 0.f));
+    if (cmax < rad) entry = -1.f;
+    if (exit_t) {
+        const float e0 = __fmul_rn(__fmaf_rn(-rad, r.sx, -ox), r.ix);
+        const float e1 = __fmul_rn(__fmaf_rn(-rad, r.sy, -oy), r.iy);
+        const float e2 = __fmul_rn(__fmaf_rn(-rad, r.sz, -oz), r.iz);
+        *exit_t = fminf(fminf(e0, e1), e2);
+    }
+    return entry;
+}
+
+template <bool EMIT>
+__global__ void raytrace_kernel(const uint8_t* __restrict__ octree, const int* __restrict__ prefix,
+                                const float* __restrict__ org, const float* __restrict__ dir, int64_t N, int level,
+                                int* __restrict__ counts, const int64_t* __restrict__ offsets,
+                                int64_t* __restrict__ ridx, int64_t* __restrict__ pidx, float* __restrict__ depth) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= N) return;
+    RayCtx r;
+    r.ox = org[3 * ray]; r.oy = org[3 * ray + 1]; r.oz = org[3 * ray + 2];
+    r.dx = dir[3 * ray]; r.dy = dir[3 * ray + 1]; r.dz = dir[3 * ray + 2];
+    r.ix = __fdiv_rn(1.0f, r.dx); r.iy = __fdiv_rn(1.0f, r.dy); r.iz = __fdiv_rn(1.0f, r.dz);
+    r.sx = (__float_as_uint(r.dx) >> 31) ? 1.f : -1.f;
+    r.sy = (__float_as_uint(r.dy) >> 31) ? 1.f : -1.f;
+    r.sz = (__float_as_uint(r.dz) >> 31) ? 1.f : -1.f;
+    const float ax = __fmaf_rn(0.5f, r.ox, 0.5f), ay = __fmaf_rn(0.5f, r.oy, 0.5f), az = __fmaf_rn(0.5f, r.oz, 0.5f);
+
+    int64_t out = EMIT ? offsets[ray] : 0;
+    int n = 0;
+    int node[PAG_MAX_LEVEL + 1], px[PAG_MAX_LEVEL + 1], py[PAG_MAX_LEVEL + 1], pz[PAG_MAX_LEVEL + 1];
+    uint8_t byte[PAG_MAX_LEVEL + 1], code[PAG_MAX_LEVEL + 1], iter[PAG_MAX_LEVEL + 1];
+    int l = -1;
+    {   // root
+        float ex;
+        const float entry = ray_aabb(r, 0.f, 0.f, 0.f, 1.f, &ex);
+        if (level == 0) {
+            if (entry > 0.f) {
+                if (EMIT) { ridx[out] = ray; pidx[out] = 0; depth[2 * out] = entry; depth[2 * out + 1] = ex; ++out; }
+                ++n;
+            }
+        } else if (entry != 0.f) {
+            l = 0; node[0] = 0; px[0] = py[0] = pz[0] = 0; byte[0] = __ldg(octree); iter[0] = 0;
+            code[0] = (uint8_t)(((ax > 0.5f) ? 4 : 0) | ((ay > 0.5f) ? 2 : 0) | ((az > 0.5f) ? 1 : 0));
+        }
+    }
+    while (l >= 0) {
+        if (iter[l] == 8) { --l; continue; }
+        const uint32_t i = iter[l]++;
+        const uint32_t j = code[l] ^ i;
+        const uint32_t b = byte[l];
+        if (!((b >> j) & 1u)) continue;
+        const int child = __ldg(prefix + node[l]) + __popc(b & ((2u << j) - 1u));
+        const int cl = l + 1;
+        const int cx = 2 * px[l] + ((j >> 2) & 1), cy = 2 * py[l] + ((j >> 1) & 1), cz = 2 * pz[l] + (j & 1);
+        const float rad = 1.0f / (float)(1 << cl);
+        const float vcx = __fmaf_rn(rad, (float)(2 * cx + 1), -1.0f);
+        const float vcy = __fmaf_rn(rad, (float)(2 * cy + 1), -1.0f);
+        const float vcz = __fmaf_rn(rad, (float)(2 * cz + 1), -1.0f);
+        if (cl == level) {
+            float ex;
+            const float entry = ray_aabb(r, vcx, vcy, vcz, rad, &ex);
+            if (entry > 0.f) {
+                if (EMIT) { ridx[out] = ray; pidx[out] = child; depth[2 * out] = entry; depth[2 * out + 1] = ex; ++out; }
+                ++n;
+            }
+        } else {
+            const float entry = ray_aabb(r, vcx, vcy, vcz, rad, nullptr);
+            if (entry != 0.f) {
+                l = cl; node[l] = child; px[l] = cx; py[l] = cy; pz[l] = cz;
+                byte[l] = __ldg(octree + child); iter[l] = 0;
+                const float bx = __fmul_rn(rad, (float)cx + 0.5f), by = __fmul_rn(rad, (float)cy + 0.5f),
+                            bz = __fmul_rn(rad, (float)cz + 0.5f);
+                code[l] = (uint8_t)(((__fsub_rn(ax, bx) > 0.f) ? 4 : 0) | ((__fsub_rn(ay, by) > 0.f) ? 2 : 0) |
+                                    ((__fsub_rn(az, bz) > 0.f) ? 1 : 0));
+            }
+        }
+    }
+    if (!EMIT) counts[ray] = n;
+}
+
+__device__ __forceinline__ float voxel_sample_depth(int64_t k, int s, int S, float t0, float t1,
+                                                    const float* __restrict__ jitter, uint32_t seed) {
+    const uint64_t flat = (uint64_t)k * (uint64_t)S + (uint64_t)s;
+    const float u = jitter ? __ldg(jitter + flat) : pag_jitter(seed, flat);
+    const float step = __fdiv_rn(__fadd_rn((float)s, u), (float)S);
+    return __fadd_rn(t0, __fmul_rn(__fsub_rn(t1, t0), step));
+}
+
+__global__ void voxel_samples_kernel(const float* __restrict__ org, const float* __restrict__ dir,
+                                     const int64_t* __restrict__ ridx, const float* __restrict__ depth, int64_t K,
+                                     int S, const float* __restrict__ jitter, uint32_t seed,
+                                     float* __restrict__ samples, float* __restrict__ depths,
+                                     float* __restrict__ deltas, uint8_t* __restrict__ boundary) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= K * S) return;
+    const int64_t k = t / S;
+    const int s = (int)(t - k * S);
+    const int64_t ray = ridx[k];
+    const float t0 = depth[2 * k], t1 = depth[2 * k + 1];
+    const float ds = voxel_sample_depth(k, s, S, t0, t1, jitter, seed);
+    const float prev = (s == 0) ? t0 : voxel_sample_depth(k, s - 1, S, t0, t1, jitter, seed);
+    depths[t] = ds;
+    deltas[t] = __fsub_rn(ds, prev);
+    samples[3 * t + 0] = __fadd_rn(org[3 * ray + 0], __fmul_rn(dir[3 * ray + 0], ds));
+    samples[3 * t + 1] = __fadd_rn(org[3 * ray + 1], __fmul_rn(dir[3 * ray + 1], ds));
+    samples[3 * t + 2] = __fadd_rn(org[3 * ray + 2], __fmul_rn(dir[3 * ray + 2], ds));
+    boundary[t] = (s == 0 && (k == 0 || ridx[k - 1] != ray)) ? 1 : 0;
+}
+
+// max-travel filter (tracers/panoptic_packed_rf_tracer.py:88-99): keep[k] = d0[k] - d0[first nugget of ray] < max_travel
+__global__ void max_travel_mask_kernel(const int64_t* __restrict__ ridx, const float* __restrict__ depths, int64_t K,
+                                       int S, const int64_t* __restrict__ ray_first, float max_travel,
+                                       uint8_t* __restrict__ keep) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int64_t f = ray_first[ridx[k]];
+    keep[k] = (__fsub_rn(depths[k * S], depths[f * S]) < max_travel) ? 1 : 0;
+}
+
+__global__ void mark_pack_boundaries_kernel(const int64_t* __restrict__ ids, int64_t M, uint8_t* __restrict__ b) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    b[i] = (i == 0 || ids[i] != ids[i - 1]) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int pag_octree_query(const uint8_t* octree, const int32_t* prefix, const float* coords, int64_t P, int level,
+                     int32_t* pidx, void* stream) {
+    if (level < 0 || level > PAG_MAX_LEVEL) return PAG_ERR_ARG;
+    if (P == 0) return PAG_OK;
+    octree_query_kernel<<<pag_grid(P, 256), 256, 0, (cudaStream_t)stream>>>(octree, prefix, coords, P, level, pidx);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_exclusive_scan_i32(const int32_t* in, int64_t N, int64_t* out /*[N+1]*/, void* stream) {
+    exclusive_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(in, N, out);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// pass 1: pidx_tmp[N*S], counts[N]; then offsets[N+1] = exclusive scan (offsets[N] = M)
+int pag_march_ray_count(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
+                        const float* jitter, uint32_t seed, float dist_min, float dist_range,
+                        const uint8_t* octree, const int32_t* prefix, int level,
+                        int32_t* pidx_tmp, int32_t* counts, int64_t* offsets, void* stream) {
+    if (level < 0 || level > PAG_MAX_LEVEL || S <= 0) return PAG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 0) {
+        march_ray_count_kernel<<<pag_grid(N * 32, 256), 256, 0, st>>>(origins, dirs, N, S, linspace, jitter, seed,
+                                                                     dist_min, dist_range, octree, prefix, level,
+                                                                     pidx_tmp, counts);
+        PAG_LAUNCH_CHECK();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, offsets);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_march_ray_emit(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
+                       const float* jitter, uint32_t seed, float dist_min, float dist_range,
+                       const int32_t* pidx_tmp, const int64_t* offsets,
+                       int64_t* ridx, int64_t* pidx, float* samples, float* depths, float* deltas,
+                       uint8_t* boundary, void* stream) {
+    if (N == 0) return PAG_OK;
+    march_ray_emit_kernel<<<pag_grid(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        origins, dirs, N, S, linspace, jitter, seed, dist_min, dist_range, pidx_tmp, offsets, ridx, pidx, samples,
+        depths, deltas, boundary);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_raytrace_count(const uint8_t* octree, const int32_t* prefix, const float* origins, const float* dirs,
+                       int64_t N, int level, int32_t* counts, int64_t* offsets, void* stream) {
+    if (level < 0 || level > PAG_MAX_LEVEL) return PAG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 0) {
+        raytrace_kernel<false><<<pag_grid(N, 128), 128, 0, st>>>(octree, prefix, origins, dirs, N, level, counts,
+                                                                nullptr, nullptr, nullptr, nullptr);
+        PAG_LAUNCH_CHECK();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, offsets);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_raytrace_emit(const uint8_t* octree, const int32_t* prefix, const float* origins, const float* dirs,
+                      int64_t N, int level, const int64_t* offsets, int64_t* ridx, int64_t* pidx, float* depth,
+                      void* stream) {
+    if (level < 0 || level > PAG_MAX_LEVEL) return PAG_ERR_ARG;
+    if (N == 0) return PAG_OK;
+    raytrace_kernel<true><<<pag_grid(N, 128), 128, 0, (cudaStream_t)stream>>>(octree, prefix, origins, dirs, N, level,
+                                                                             nullptr, offsets, ridx, pidx, depth);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_voxel_samples(const float* origins, const float* dirs, const int64_t* ridx, const float* depth, int64_t K,
+                      int S, const float* jitter, uint32_t seed, float* samples, float* depths, float* deltas,
+                      uint8_t* boundary, void* stream) {
+    if (S <= 0) return PAG_ERR_ARG;
+    if (K == 0) return PAG_OK;
+    voxel_samples_kernel<<<pag_grid(K * S, 256), 256, 0, (cudaStream_t)stream>>>(origins, dirs, ridx, depth, K, S,
+                                                                                jitter, seed, samples, depths, deltas,
+                                                                                boundary);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_max_travel_mask(const int64_t* ridx, const float* depths, int64_t K, int S, const int64_t* ray_first,
+                        float max_travel, uint8_t* keep, void* stream) {
+    if (K == 0) return PAG_OK;
+    max_travel_mask_kernel<<<pag_grid(K, 256), 256, 0, (cudaStream_t)stream>>>(ridx, depths, K, S, ray_first,
+                                                                              max_travel, keep);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_mark_pack_boundaries(const int64_t* ids, int64_t M, uint8_t* boundary, void* stream) {
+    if (M == 0) return PAG_OK;
+    mark_pack_boundaries_kernel<<<pag_grid(M, 256), 256, 0, (cudaStream_t)stream>>>(ids, M, boundary);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+}  // extern "C"

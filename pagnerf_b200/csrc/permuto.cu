@@ -1,0 +1,236 @@
+// Multi-resolution permutohedral-lattice encoding, forward + backward (values and positions).
+//
+// Replaces permutohedral_encoding.PermutoEncoding as the reference uses it
+// (grids/permuto_grid.py:57-62 build, :71 call; pc_nerf/panoptic_delta_nef.py:170,219):
+// pos_dim 3, F = 2 features per level, L levels, table f32[L, capacity, 2].
+//
+// B200 design: one thread per sample walks ALL levels with the 4L float2 gathers of a sample
+// issued from one thread (unrolled by 4 levels -> 16 independent 8-byte gathers in flight); the
+// whole 50 MB table stays L2 resident (126 MB L2) so the gathers are L2-sector bound, not HBM
+// bound; each thread writes its own contiguous 8L-byte output row.  Backward re-derives the
+// lattice (cheaper than storing 32 B/level/sample) and scatters with red.global.add.v2.f32;
+// the coarse levels, where a warp hits a handful of vertices, are first aggregated inside the
+// warp (match-any leader reduction) so contention at L2 drops by up to 32x.
+// Lattice integers (rem0, rank, key, idx) are bit-exact against oracle/permuto.py.
+#include "common.cuh"
+
+#define PERMUTO_HASH_MUL 2531011u
+
+struct PermutoVertex {
+    uint32_t idx[4];
+    float bary[4];
+    int rank[4];
+};
+
+// one level of the lattice for one point; `cap_mask` != 0 means capacity is a power of two
+__device__ __forceinline__ void permuto_lattice(float p0, float p1, float p2, const float* __restrict__ sf,
+                                                const float* __restrict__ sh, uint32_t cap, uint32_t cap_mask,
+                                                PermutoVertex& v) {
+    const float cf0 = __fmul_rn(__fadd_rn(p0, __ldg(sh + 0)), __ldg(sf + 0));
+    const float cf1 = __fmul_rn(__fadd_rn(p1, __ldg(sh + 1)), __ldg(sf + 1));
+    const float cf2 = __fmul_rn(__fadd_rn(p2, __ldg(sh + 2)), __ldg(sf + 2));
+    float e[4];
+    float sm = 0.f;
+    e[3] = __fmaf_rn(-3.f, cf2, sm); sm = __fadd_rn(sm, cf2);
+    e[2] = __fmaf_rn(-2.f, cf1, sm); sm = __fadd_rn(sm, cf1);
+    e[1] = __fmaf_rn(-1.f, cf0, sm); sm = __fadd_rn(sm, cf0);
+    e[0] = sm;
+    int rem0[4];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float q = e[i] * 0.25f;
+        const float up = ceilf(q) * 4.f, down = floorf(q) * 4.f;
+        rem0[i] = (__fsub_rn(up, e[i]) < __fsub_rn(e[i], down)) ? (int)up : (int)down;
+        sum += rem0[i];
+    }
+    sum /= 4;
+    float dlt[4];
+    int rank[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dlt[i] = __fsub_rn(e[i], (float)rem0[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) {
+            if (dlt[i] < dlt[j]) rank[i]++; else rank[j]++;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rank[i] += sum;
+        if (rank[i] < 0) { rank[i] += 4; rem0[i] += 4; }
+        else if (rank[i] > 3) { rank[i] -= 4; rem0[i] -= 4; }
+    }
+    // barycentric weights: D[k] = delta of the coordinate whose rank is k (ranks are a permutation)
+    float D[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float delta = __fsub_rn(e[i], (float)rem0[i]) * 0.25f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) D[k] = (rank[i] == k) ? delta : D[k];
+        v.rank[i] = rank[i];
+    }
+    v.bary[0] = (D[3] + 1.0f) - D[0];
+    v.bary[1] = D[2] - D[3];
+    v.bary[2] = D[1] - D[2];
+    v.bary[3] = D[0] - D[1];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t k = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int key = rem0[i] + r - ((rank[i] > 3 - r) ? 4 : 0);
+            k += (uint32_t)key;
+            k *= PERMUTO_HASH_MUL;
+        }
+        v.idx[r] = cap_mask ? (k & cap_mask) : (k % cap);
+    }
+}
+
+__global__ void __launch_bounds__(128) permuto_fwd_kernel(
+    const float* __restrict__ pos, int64_t M, const float* __restrict__ table, uint32_t cap, uint32_t cap_mask, int L,
+    const float* __restrict__ sf, const float* __restrict__ sh, const float* __restrict__ anneal,
+    float* __restrict__ out) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float p0 = pos[3 * m], p1 = pos[3 * m + 1], p2 = pos[3 * m + 2];
+    float2* orow = reinterpret_cast<float2*>(out + m * (int64_t)(2 * L));
+#pragma unroll 4
+    for (int l = 0; l < L; ++l) {
+        PermutoVertex v;
+        permuto_lattice(p0, p1, p2, sf + 3 * l, sh + 3 * l, cap, cap_mask, v);
+        const float* tl = table + (size_t)l * cap * 2;
+        const float2 a = ldg2(tl + 2 * (size_t)v.idx[0]);
+        const float2 b = ldg2(tl + 2 * (size_t)v.idx[1]);
+        const float2 c = ldg2(tl + 2 * (size_t)v.idx[2]);
+        const float2 d = ldg2(tl + 2 * (size_t)v.idx[3]);
+        const float w = __ldg(anneal + l);
+        float2 acc;
+        acc.x = (a.x * v.bary[0] + b.x * v.bary[1] + c.x * v.bary[2] + d.x * v.bary[3]) * w;
+        acc.y = (a.y * v.bary[0] + b.y * v.bary[1] + c.y * v.bary[2] + d.y * v.bary[3]) * w;
+        orow[l] = acc;
+    }
+}
+
+// debug / parity: dump lattice integers  idx[L,M,4] u32, rank[L,M,4] i32
+__global__ void permuto_indices_kernel(const float* __restrict__ pos, int64_t M, uint32_t cap, uint32_t cap_mask, int L,
+                                       const float* __restrict__ sf, const float* __restrict__ sh,
+                                       uint32_t* __restrict__ idx, int* __restrict__ rank, float* __restrict__ bary) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float p0 = pos[3 * m], p1 = pos[3 * m + 1], p2 = pos[3 * m + 2];
+    for (int l = 0; l < L; ++l) {
+        PermutoVertex v;
+        permuto_lattice(p0, p1, p2, sf + 3 * l, sh + 3 * l, cap, cap_mask, v);
+        for (int r = 0; r < 4; ++r) {
+            idx[((size_t)l * M + m) * 4 + r] = v.idx[r];
+            rank[((size_t)l * M + m) * 4 + r] = v.rank[r];
+            bary[((size_t)l * M + m) * 4 + r] = v.bary[r];
+        }
+    }
+}
+
+template <bool POS_GRAD>
+__global__ void __launch_bounds__(128) permuto_bwd_kernel(
+    const float* __restrict__ pos, int64_t M, const float* __restrict__ table, uint32_t cap, uint32_t cap_mask, int L,
+    const float* __restrict__ sf, const float* __restrict__ sh, const float* __restrict__ anneal,
+    const float* __restrict__ gout, float* __restrict__ gtable, float* __restrict__ gpos, int n_agg_levels) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = m < M;
+    // aggregated levels need the full warp converged: clamp instead of returning early
+    const int64_t mm = valid ? m : (M - 1);
+    const float p0 = pos[3 * mm], p1 = pos[3 * mm + 1], p2 = pos[3 * mm + 2];
+    const float2* grow = reinterpret_cast<const float2*>(gout + mm * (int64_t)(2 * L));
+    float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
+    for (int l = 0; l < L; ++l) {
+        PermutoVertex v;
+        permuto_lattice(p0, p1, p2, sf + 3 * l, sh + 3 * l, cap, cap_mask, v);
+        const float w = __ldg(anneal + l);
+        float2 g = __ldg(grow + l);
+        g.x = valid ? g.x * w : 0.f;
+        g.y = valid ? g.y * w : 0.f;
+        float* gl = gtable + (size_t)l * cap * 2;
+        if (l < n_agg_levels) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                scatter_aggregated(gl, v.idx[r], g.x * v.bary[r], g.y * v.bary[r], 0xffffffffu);
+        } else if (valid) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) red_add_f32x2(gl + 2 * (size_t)v.idx[r], g.x * v.bary[r], g.y * v.bary[r]);
+        }
+        if (POS_GRAD) {
+            const float* tl = table + (size_t)l * cap * 2;
+            float s[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float2 t = ldg2(tl + 2 * (size_t)v.idx[r]);
+                s[r] = g.x * t.x + g.y * t.y;
+            }
+            // dL/dD[k]; D[k] = delta of the coordinate with rank k
+            const float dD[4] = {s[3] - s[0], s[2] - s[3], s[1] - s[2], s[0] - s[1]};
+            float de[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float t = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t = (v.rank[i] == k) ? dD[k] : t;
+                de[i] = 0.25f * t;
+            }
+            // e0 = c0+c1+c2, e1 = c2+c1-c0, e2 = c2-2c1, e3 = -3c2
+            gp0 += (de[0] - de[1]) * __ldg(sf + 3 * l + 0);
+            gp1 += (de[0] + de[1] - 2.f * de[2]) * __ldg(sf + 3 * l + 1);
+            gp2 += (de[0] + de[1] + de[2] - 3.f * de[3]) * __ldg(sf + 3 * l + 2);
+        }
+    }
+    if (POS_GRAD && valid) { gpos[3 * m] = gp0; gpos[3 * m + 1] = gp1; gpos[3 * m + 2] = gp2; }
+}
+
+extern "C" {
+
+// forward: out[M, 2L] (level-major, feature-minor)
+int pag_permuto_fwd(const float* pos, int64_t M, const float* table, int64_t capacity, int L, int F,
+                    const float* scale_factor, const float* shift, const float* anneal, float* out, void* stream) {
+    if (F != 2) return PAG_ERR_UNSUPPORTED;
+    if (capacity <= 0 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (M == 0) return PAG_OK;
+    const uint32_t cap = (uint32_t)capacity;
+    const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
+    if (cap == 1) return PAG_ERR_ARG;
+    permuto_fwd_kernel<<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(pos, M, table, cap, mask, L, scale_factor,
+                                                                          shift, anneal, out);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// backward: gtable[L,cap,2] is ACCUMULATED into (caller zeroes it); gpos[M,3] written iff non-null.
+int pag_permuto_bwd(const float* pos, int64_t M, const float* table, int64_t capacity, int L, int F,
+                    const float* scale_factor, const float* shift, const float* anneal, const float* grad_out,
+                    float* grad_table, float* grad_pos, int n_agg_levels, void* stream) {
+    if (F != 2) return PAG_ERR_UNSUPPORTED;
+    if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (M == 0) return PAG_OK;
+    const uint32_t cap = (uint32_t)capacity;
+    const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
+    if (grad_pos)
+        permuto_bwd_kernel<true><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels);
+    else
+        permuto_bwd_kernel<false><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_permuto_indices(const float* pos, int64_t M, int64_t capacity, int L, const float* scale_factor,
+                        const float* shift, uint32_t* idx, int32_t* rank, float* bary, void* stream) {
+    if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (M == 0) return PAG_OK;
+    const uint32_t cap = (uint32_t)capacity;
+    const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
+    permuto_indices_kernel<<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(pos, M, cap, mask, L, scale_factor, shift,
+                                                                              idx, rank, bary);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+}  // extern "C"
