@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- PAg-NeRF hot path on B200: rays/s of a training step (march + encode + decode +
+composite + backward), BASELINE.json config[1]:
+  PanopticDeltaNeF + permutohedral grid (L=24, F=2, T=2^18, colour + delta grid), BUP20-shaped 1 MP
+  camera, 16 384 rays / step / GPU, occupancy-octree 'ray' march with 128 steps on a pruned level-7 octree.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS = 16384
+NUM_STEPS = 128
+LEVEL = 7
+L, F, CAP_LOG2 = 24, 2, 18
+C_SEM, C_INST = 6, 200
+RAYS_PER_IMG = 4096
+NEAR, FAR = 0.0, 2.0
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic BUP20-shaped workload: scene, cameras, rays, targets
+# ------------------------------------------------------------------------------------------------
+def make_scene(level=LEVEL, seed=0):
+    """Pruned occupancy: slab |z| < 0.15 plus 200 blobs r = 0.05 (a few % of the level-7 cells)."""
+    rng = np.random.default_rng(seed)
+    n = 1 << level
+    ax = (np.arange(n) + 0.5) / n * 2 - 1
+    occ = np.zeros((n, n, n), dtype=bool)
+    occ[:, :, np.abs(ax) < 0.15] = True
+    ctr = rng.uniform(-0.9, 0.9, (200, 3))
+    r = 0.05
+    for c in ctr:
+        lo = np.clip(((c - r + 1) / 2 * n).astype(int), 0, n - 1)
+        hi = np.clip(((c + r + 1) / 2 * n).astype(int) + 1, 1, n)
+        sub = np.stack(np.meshgrid(ax[lo[0]:hi[0]], ax[lo[1]:hi[1]], ax[lo[2]:hi[2]], indexing="ij"), -1)
+        occ[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] |= np.linalg.norm(sub - c, axis=-1) < r
+    return np.argwhere(occ).astype(np.int16)
+
+
+def make_rays(n_rays, step, seed=0, res=1024):
+    """`n_rays/4096` images x 4096 random pixels; pinhole res x res, focal 0.9*res; cameras on the line
+    x in [-0.8, 0.8] at z = +0.9 looking down -z with 2 degrees of seeded jitter."""
+    rng = np.random.default_rng(seed * 100003 + step)
+    n_img = max(1, n_rays // RAYS_PER_IMG)
+    per = n_rays // n_img
+    os_, ds_ = [], []
+    for _ in range(n_img):
+        cam = np.array([rng.uniform(-0.8, 0.8), rng.uniform(-0.05, 0.05), 0.9])
+        pix = rng.integers(0, res, size=(per, 2)).astype(np.float64) + 0.5
+        d = np.stack([(pix[:, 0] - res / 2) / (0.9 * res), (pix[:, 1] - res / 2) / (0.9 * res), -np.ones(per)], 1)
+        ang = np.deg2rad(rng.normal(0, 2.0, 2))
+        cx, sx, cy, sy = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1])
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        d = d @ (Ry @ Rx).T
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        os_.append(np.tile(cam, (per, 1)))
+        ds_.append(d)
+    return np.concatenate(os_).astype(np.float32), np.concatenate(ds_).astype(np.float32)
+
+
+def make_targets(n_rays, step, seed=0):
+    rng = np.random.default_rng(seed * 7919 + step + 1)
+    return (rng.uniform(0, 1, (n_rays, 3)).astype(np.float32), rng.integers(0, C_SEM, n_rays).astype(np.int64),
+            rng.integers(0, C_INST, n_rays).astype(np.int64))
+
+
+NEF_KW = dict(grid_type="PermutoGrid", interpolation_type='linear', multiscale_type='cat', feature_dim=F, num_lods=L,
+              base_lod=2, hidden_dim=64, num_layers=1, view_multires=4, pos_multires=10, embedder_type='positional',
+              activation_type='relu', layer_type='none', num_classes=C_SEM, num_instances=C_INST,
+              sem_num_layers=1, sem_hidden_dim=64, inst_num_layers=2, inst_hidden_dim=64, sem_softmax=True,
+              inst_softmax=True, sem_detach=True, inst_detach=True, panoptic_features_type='delta', blas_level=LEVEL,
+              coarsest_scale=1.0, finest_scale=1e-4, capacity_log_2=CAP_LOG2, delta_capacity_log_2=CAP_LOG2)
+
+
+def loss_fn(rb_rgb, rb_sem, rb_inst, t_rgb, t_sem, t_inst):
+    """rgb L1 x10 + semantic NLL x0.1 + instance NLL (reference pc_nerf/trainer.py:442-480, log(x + 1e-27) :459)."""
+    l = 10.0 * torch.abs(rb_rgb - t_rgb).mean()
+    l = l + 0.1 * torch.nn.functional.nll_loss(torch.log(rb_sem + 1e-27), t_sem)
+    l = l + 1.0 * torch.nn.functional.nll_loss(torch.log(rb_inst + 1e-27), t_inst)
+    return l
+
+
+class Workload:
+    """The training-step hot path on one GPU through the plugin classes."""
+
+    def __init__(self, device, n_rays=N_RAYS, seed=0, n_batches=4):
+        from pagnerf_b200.pc_nerf import PanopticDeltaNeF
+        from pagnerf_b200.tracers import PanopticPackedRFTracer
+        from pagnerf_b200 import spc
+        torch.manual_seed(seed)
+        self.device, self.n_rays = device, n_rays
+        self.nef = PanopticDeltaNeF(**NEF_KW)
+        pts = torch.from_numpy(make_scene(LEVEL, seed))
+        octree = spc.unbatched_points_to_octree(pts, LEVEL)
+        for g in (self.nef.grid, self.nef.delta_grid):
+            g.init_from_scales()
+            g.blas_init(octree)
+        with torch.no_grad():  # random-init field, but opaque enough that compositing terminates like a trained one
+            self.nef.grid.embedder.lattice_values.mul_(1e3)
+            self.nef.delta_grid.embedder.lattice_values.mul_(1e3)
+        self.nef = self.nef.to(device)
+        self.tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=NUM_STEPS, bg_color='white', ray_max_travel=2.0)
+        self.params = [p for p in self.nef.parameters()]
+        self.channels = ['rgb', 'depth', 'semantics', 'inst_embedding']
+        # pool of host (pinned) batches; step i uses batch i % n_batches
+        self.host = []
+        for b in range(n_batches):
+            o, d = make_rays(n_rays, b, seed)
+            tr, ts, ti = make_targets(n_rays, b, seed)
+            hb = [torch.from_numpy(x) for x in (o, d, tr, ts, ti)]
+            if device.type == 'cuda':
+                hb = [x.pin_memory() for x in hb]
+            self.host.append(hb)
+        self.dev = [[x.to(device) for x in hb] for hb in self.host]
+        self.step_idx = 0
+
+    def h2d_bytes(self):
+        return sum(x.numel() * x.element_size() for x in self.host[0])
+
+    def forward_backward(self, batch=None, from_host=False):
+        from pagnerf_b200.wisp_compat import Rays
+        b = self.step_idx % len(self.host) if batch is None else batch
+        self.step_idx += 1
+        if from_host:
+            o, d, tr, ts, ti = [x.to(self.device, non_blocking=True) for x in self.host[b]]
+        else:
+            o, d, tr, ts, ti = self.dev[b]
+        for p in self.params:
+            p.grad = None
+        rays = Rays(origins=o, dirs=d, dist_min=NEAR, dist_max=FAR)
+        rb = self.tracer(self.nef, channels=self.channels, rays=rays, lod_idx=None, stage='train')
+        loss = loss_fn(rb.rgb, rb.semantics, rb.inst_embedding, tr, ts, ti)
+        loss.backward()
+        return {"rb": rb, "loss": loss, "ridx": getattr(self.tracer, "_last_ridx", torch.zeros(1, device=self.device))}
+
+
+def build_workload(device, n_rays=N_RAYS, seed=0):
+    return Workload(device, n_rays, seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: oracle port of the same path (numpy/torch CPU), bounded sample
+# ------------------------------------------------------------------------------------------------
+class CpuReference:
+    def __init__(self, n_rays, seed=0):
+        from oracle.field import FieldOracle
+        from oracle.permuto import PermutoEncodingOracle
+        from oracle import spc as ospc
+        torch.manual_seed(seed)
+        scales = np.geomspace(1.0, 1e-4, L)
+        grid = PermutoEncodingOracle(2 ** CAP_LOG2, L, F, scales, seed=seed)
+        delta = PermutoEncodingOracle(2 ** CAP_LOG2, L, F, scales, seed=seed + 1)
+        with torch.no_grad():
+            grid.lattice_values.mul_(1e3); delta.lattice_values.mul_(1e3)
+        self.field = FieldOracle(grid, delta, feat_dim=L * F, num_classes=C_SEM, num_instances=C_INST)
+        self.octree = ospc.points_to_octree(make_scene(LEVEL, seed), LEVEL)
+        _, _, self.prefix = ospc.scan_octree(self.octree, LEVEL)
+        self.n_rays, self.seed, self.i = n_rays, seed, 0
+
+    def step(self):
+        from oracle import raymarch as orm
+        from oracle.field import trace_oracle
+        o, d = make_rays(self.n_rays, self.i, self.seed)
+        tr, ts, ti = [torch.from_numpy(x) for x in make_targets(self.n_rays, self.i, self.seed)]
+        self.i += 1
+        ridx, pidx, s, dp, dl, b = orm.raymarch_ray(self.octree, self.prefix, o, d, LEVEL, NUM_STEPS, NEAR, FAR, seed=self.i)
+        for p in self.field.parameters():
+            p.grad = None
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        out = trace_oracle(self.field, t(o), t(d), t(ridx).long(), t(s), t(dp), t(dl), t(b),
+                           ['rgb', 'depth', 'semantics', 'inst_embedding'])
+        loss = loss_fn(out['rgb'], out['semantics'], out['inst_embedding'], tr, ts, ti)
+        loss.backward()
+        return float(loss)
+
+
+def time_cpu_reference(n_rays, steps, warmup):
+    torch.set_num_threads(os.cpu_count())
+    ref = CpuReference(n_rays)
+    for _ in range(warmup):
+        ref.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref.step()
+    dt = (time.perf_counter() - t0) / steps
+    return n_rays / dt, dt
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# main
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes / flops per packed sample (DESIGN.md "Kernels")
+ALGO = {
+    "pag_permuto_fwd": ("hbm", 12 + L * 4 * 8 + L * 2 * 4),
+    "pag_permuto_bwd": ("hbm", 12 + L * 2 * 4 + 2 * L * 4 * 8),
+    "pag_decode_dc_fwd": ("tensor", 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
+    "pag_decode_dc_bwd": ("tensor", 3 * 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
+    "pag_decode_pan_fwd": ("tensor", 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
+    "pag_decode_pan_bwd": ("tensor", 3 * 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
+    "pag_composite_fwd": ("hbm", 4 + 4 + 4 + 12 + 4 * C_SEM + 4 * C_INST + 8),
+    "pag_composite_bwd": ("hbm", 2 * (4 + 4 + 4 + 12 + 4 * C_SEM + 4 * C_INST) + 8),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return j["hbm_gbs"], j.get("bf16_tflops_sustained", j["bf16_tflops"]), "measured (MEASURED_PEAKS.json; bf16 sustained)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=N_RAYS)
+    ap.add_argument("--cpu-sample-rays", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    config = {"workload": "PanopticDeltaNeF + permutohedral grid (L=24,F=2,T=2^18 x2), BUP20-shaped 1MP frame, "
+                          f"{args.rays} rays/step/GPU, occtree 'ray' march {NUM_STEPS} steps, level-7 pruned octree; "
+                          "rgb+depth+semantics(6)+inst(200); fwd+bwd",
+              "rays_per_gpu": args.rays, "parallelism": f"ray-sharded dp{world}" if world > 1 else "single"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+        value, dt = time_cpu_reference(args.cpu_sample_rays, steps, warm)
+        out = {"impl": "reference", "metric": "train rays/s (march+encode+decode+composite+backward)", "value": value,
+               "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": config,
+               "cpu_baseline": {"value": value, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{args.cpu_sample_rays} rays/step of the same workload, oracle (numpy+torch CPU) fwd+bwd"},
+               "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return 0
+
+    import torch.distributed as dist
+    from pagnerf_b200 import _lib, parallel
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    wl = Workload(device, args.rays, seed=rank)
+
+    def step(from_host):
+        out = wl.forward_backward(from_host=from_host)
+        if world > 1:
+            parallel.allreduce_grads(wl.params)
+        return out
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    # ---- device-resident timing (value) ------------------------------------------------------------
+    sync()
+    clocks = ClockSampler(local) if rank == 0 else None
+    _lib.timing_reset(True)
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step(False)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (_lib.launch_count - l0) // args.steps
+    per_kernel = _lib.timing_report()
+    for v in per_kernel.values():
+        v["ms_per_step"] = v["ms_total"] / args.steps
+    _lib.timing_reset(False)
+    # ---- end-to-end timing (host pinned inputs -> H2D -> step -> D2H loss) -------------------------
+    for _ in range(2):
+        step(True)
+    sync()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        o = step(True)
+        _ = float(o["loss"].item())
+    t1.record()
+    sync()
+    ms_e2e = t0.elapsed_time(t1) / args.steps
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    hbm, tf, how = peaks()
+    top = max(per_kernel.items(), key=lambda kv: kv[1]["ms_per_step"]) if per_kernel else None
+    roof = None
+    n_samples = wl.tracer.last_num_samples if hasattr(wl.tracer, "last_num_samples") else None
+    if top and top[0] in ALGO and n_samples:
+        bound, per = ALGO[top[0]]
+        dur = top[1]["ms_per_launch"] * 1e-3
+        if bound == "hbm":
+            ach = per * n_samples / dur / 1e9
+            roof = {"kernel": top[0], "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None}
+        else:
+            ach = per * n_samples / dur / 1e12
+            roof = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "traffic": None,
+                    "note": "fp32 FMA kernel measured against the bf16 tensor peak"}
+        roof["peak_source"] = how
+        roof["share_of_step"] = top[1]["ms_per_step"] / ms
+        roof["samples_per_launch"] = n_samples
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, dt = time_cpu_reference(args.cpu_sample_rays, 3, 1)
+        cpu = {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{args.cpu_sample_rays} rays/step x 3 steps of the same workload, oracle (numpy+torch CPU) fwd+bwd"}
+    total_rays = args.rays * world
+    result = {"metric": "train rays/s (march+encode+decode+composite+backward)", "value": total_rays / (ms * 1e-3),
+              "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": dict(config, l2="no explicit flush: ray batches cycle and the per-step working set (2x50 MB tables + "
+                                        "[M,200] fp32 instance activations and grads) exceeds the 126 MB L2",
+                             packed_samples_per_step=n_samples),
+              "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": wl.h2d_bytes(),
+                      "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+              "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+              "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
+    print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,132 @@
+/* pagnerf_b200 -- C ABI of the B200-native PAg-NeRF per-ray hot path (libpagnerf_b200.so).
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); kernels never allocate/free;
+ *   - sizes are int64_t, small dims int; `stream` is a cudaStream_t passed as void*;
+ *   - return 0 on success, <0 argument/unsupported-shape error (PAG_ERR_*), >0 a cudaError_t;
+ *   - no host synchronisation, no global state, re-entrant per stream;
+ *   - "nullable" arguments may be NULL to skip the corresponding channel.
+ * The reference is pure Python on top of kaolin / kaolin-wisp / permutohedral_encoding / tiny-cuda-nn;
+ * each entry below cites the reference call site (file:line under the reference tree) whose
+ * third-party kernel(s) it replaces.  The Python binding a maintainer adds is in INTEGRATION.md.
+ */
+#ifndef PAGNERF_B200_H
+#define PAGNERF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAG_OK 0
+#define PAG_ERR_ARG (-1)
+#define PAG_ERR_UNSUPPORTED (-2)
+
+/* ---- occupancy octree: grids/occtree.py:85-91 -> wisp OctreeAS.{query,raytrace,raymarch} ------------- */
+
+/* kaolin.ops.spc.unbatched_query: coords f32[P,3] in [-1,1] -> point-hierarchy index (or -1). */
+int pag_octree_query(const uint8_t* octree, const int32_t* prefix, const float* coords, int64_t P, int level,
+                     int32_t* pidx, void* stream);
+
+/* exclusive scan of int32 counts; out has N+1 entries, out[N] = total. */
+int pag_exclusive_scan_i32(const int32_t* in, int64_t N, int64_t* out, void* stream);
+
+/* 'ray' raymarch, pass 1 (tracers/panoptic_packed_rf_tracer.py:85 with raymarch_type='ray'):
+ * S jittered steps per ray, octree lookup per step.  Writes pidx_tmp[N*S], counts[N], offsets[N+1].
+ * jitter f32[N,S] nullable (then the counter RNG with `seed` is used); linspace = torch.linspace(0,1,S). */
+int pag_march_ray_count(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
+                        const float* jitter, uint32_t seed, float dist_min, float dist_range,
+                        const uint8_t* octree, const int32_t* prefix, int level,
+                        int32_t* pidx_tmp, int32_t* counts, int64_t* offsets, void* stream);
+/* pass 2: packed outputs of size M = offsets[N]: ridx/pidx i64[M], samples f32[M,3], depths/deltas f32[M],
+ * boundary u8[M]. */
+int pag_march_ray_emit(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
+                       const float* jitter, uint32_t seed, float dist_min, float dist_range,
+                       const int32_t* pidx_tmp, const int64_t* offsets,
+                       int64_t* ridx, int64_t* pidx, float* samples, float* depths, float* deltas,
+                       uint8_t* boundary, void* stream);
+
+/* kaolin.render.spc.unbatched_raytrace(return_depth, with_exit): count pass then emit pass;
+ * nuggets (ridx,pidx,[entry,exit]) in kaolin's order.  offsets[N+1] doubles as the per-ray first-nugget index. */
+int pag_raytrace_count(const uint8_t* octree, const int32_t* prefix, const float* origins, const float* dirs,
+                       int64_t N, int level, int32_t* counts, int64_t* offsets, void* stream);
+int pag_raytrace_emit(const uint8_t* octree, const int32_t* prefix, const float* origins, const float* dirs,
+                      int64_t N, int level, const int64_t* offsets, int64_t* ridx, int64_t* pidx, float* depth,
+                      void* stream);
+/* 'voxel' raymarch sampling (wisp sample_from_depth_intervals + addcmul + expand_pack_boundary):
+ * samples f32[K,S,3], depths f32[K,S], deltas f32[K*S], boundary u8[K*S]. */
+int pag_voxel_samples(const float* origins, const float* dirs, const int64_t* ridx, const float* depth, int64_t K,
+                      int S, const float* jitter, uint32_t seed, float* samples, float* depths, float* deltas,
+                      uint8_t* boundary, void* stream);
+/* max-travel filter, tracers/panoptic_packed_rf_tracer.py:88-99: keep[k] u8. */
+int pag_max_travel_mask(const int64_t* ridx, const float* depths, int64_t K, int S, const int64_t* ray_first,
+                        float max_travel, uint8_t* keep, void* stream);
+/* kaolin.render.spc.mark_pack_boundaries, tracers/panoptic_packed_rf_tracer.py:114. */
+int pag_mark_pack_boundaries(const int64_t* ids, int64_t M, uint8_t* boundary, void* stream);
+
+/* ---- permutohedral encoding: grids/permuto_grid.py:57-62,71 -> PermutoEncoding fwd / bwd ------------- */
+/* pos f32[M,3]; table f32[L,capacity,F]; scale_factor/shift f32[L,3]; anneal f32[L]; out f32[M,L*F]. F must be 2. */
+int pag_permuto_fwd(const float* pos, int64_t M, const float* table, int64_t capacity, int L, int F,
+                    const float* scale_factor, const float* shift, const float* anneal, float* out, void* stream);
+/* grad_table f32[L,capacity,F] is accumulated into; grad_pos f32[M,3] nullable (delta grid: NULL,
+ * pc_nerf/panoptic_delta_nef.py:215). n_agg_levels = number of coarse levels scattered with warp aggregation. */
+int pag_permuto_bwd(const float* pos, int64_t M, const float* table, int64_t capacity, int L, int F,
+                    const float* scale_factor, const float* shift, const float* anneal, const float* grad_out,
+                    float* grad_table, float* grad_pos, int n_agg_levels, void* stream);
+/* parity probe: lattice vertex hash indices u32[L,M,4], ranks i32[L,M,4], barycentric f32[L,M,4]. */
+int pag_permuto_indices(const float* pos, int64_t M, int64_t capacity, int L, const float* scale_factor,
+                        const float* shift, uint32_t* idx, int32_t* rank, float* bary, void* stream);
+
+/* ---- hash grids: flavour 0 = tiny-cuda-nn (grids/hash_grid_tinycudann.py:24-34,41),
+ *                  flavour 1 = HashNeRF torch grid (grids/hash_grid_torch.py:13-108) ------------------- */
+int pag_hash_fwd(int flavour, const float* pos, int64_t M, const float* table, int L, int F, const float* fparam,
+                 const uint32_t* res, const uint32_t* offset, const uint32_t* size, float* out, int round_half,
+                 void* stream);
+int pag_hash_bwd(int flavour, const float* pos, int64_t M, const float* table, int L, int F, const float* fparam,
+                 const uint32_t* res, const uint32_t* offset, const uint32_t* size, const float* grad_out,
+                 float* grad_table, float* grad_pos, int n_agg_levels, void* stream);
+int pag_hash_indices(int flavour, const float* pos, int64_t M, int L, const float* fparam, const uint32_t* res,
+                     const uint32_t* offset, const uint32_t* size, uint32_t* idx, void* stream);
+
+/* ---- decoders: pc_nerf/panoptic_nef.py:114-164,309-361; pc_nerf/panoptic_delta_nef.py:184-257 -------- */
+/* density IN->64->16 (+relu on ch0) and color [16|PE(-d)]->64->64->3 sigmoid.
+ * weights: Wd1,bd1,Wd2,bd2,Wc1,bc1,Wc2,bc2,Wc3,bc3 (torch Linear [out][in]); sample m uses ray_d[m / S]. */
+int pag_decode_dc_fwd(const float* feats, const float* lodw, const float* ray_d, int S, int64_t M, int IN,
+                      const float* const* weights, int hidden, int view_dim, int want_rgb, float* sigma, float* rgb,
+                      void* stream);
+int pag_decode_dc_bwd(const float* feats, const float* lodw, const float* ray_d, int S, int64_t M, int IN,
+                      const float* const* weights, float* const* grads, int hidden, int view_dim,
+                      const float* g_sigma, const float* g_rgb, float* g_feats, float* g_dir, void* stream);
+/* semantics IN->64->Cs and instance IN->64->64->Ci on panop = (feats + dfeats) * lodw, optional softmax / temperature.
+ * weights: Ws1,bs1,Ws2,bs2,Wi1,bi1,Wi2,bi2,Wi3,bi3. */
+int pag_decode_pan_fwd(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                       const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
+                       float inst_temperature, float* sem, float* inst, void* stream);
+int pag_decode_pan_bwd(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                       const float* const* weights, float* const* grads, int hidden, int Cs, int Ci, int sem_softmax,
+                       int inst_softmax, float inst_temperature, const float* sem, const float* inst,
+                       const float* g_sem, const float* g_inst, float* g_panop, void* stream);
+
+/* ---- packed compositing: tracers/panoptic_packed_rf_tracer.py:134-205 ------------------------------- */
+/* offsets[r] = first packed index with ridx >= r (ridx ascending), offsets[R] = M. */
+int pag_ray_offsets(const int64_t* ridx, int64_t M, int64_t R, int64_t* offsets, void* stream);
+/* fused exponential integration + all channel reductions + alpha-on-top + background, dense [R,*] outputs. */
+int pag_composite_fwd(const float* sigma, const float* deltas, const float* depths, const float* rgb,
+                      const float* sem, int Cs, const float* inst, int Ci, const int64_t* offsets, int64_t R,
+                      int bg_white, float* w, float* T, float* alpha, uint8_t* hit, float* rgb_out, float* rgbsum_out,
+                      float* depth_out, float* sem_out, float* inst_out, void* stream);
+int pag_composite_bwd(const float* sigma, const float* deltas, const float* depths, const float* rgb,
+                      const int64_t* offsets, int64_t R, int bg_white, const float* w, const float* T,
+                      const float* alpha, const float* rgbsum, const float* g_alpha, const float* g_rgb,
+                      const float* g_depth, const float* g_sem, int Cs, const float* g_inst, int Ci, float* g_sigma,
+                      float* g_rgb_s, float* g_sem_s, float* g_inst_s, void* stream);
+/* kaolin.render.spc.sum_reduce / exponential_integration (weights only), packs given by offsets[R+1]. */
+int pag_sum_reduce_fwd(const float* x, int64_t C, const int64_t* offsets, int64_t R, float* out, void* stream);
+int pag_sum_reduce_bwd(const float* g, int64_t C, const int64_t* offsets, int64_t R, float* gx, void* stream);
+int pag_expint_fwd(const float* tau, const int64_t* offsets, int64_t R, float* w, float* T, void* stream);
+int pag_expint_bwd(const float* gw, const float* w, const float* T, const int64_t* offsets, int64_t R, float* gtau,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAGNERF_B200_H */

@@ -5,8 +5,6 @@ the "separately rounded" semantics (CUDA: __fmul_rn / __fadd_rn).  Where the
 upstream CUDA code uses an explicit or compiler-contracted FMA we need a
 correctly rounded single-precision fma on the CPU; `fma32` provides it.
 """
-from fractions import Fraction
-
 import numpy as np
 
 F32 = np.float32
@@ -17,43 +15,32 @@ def f32(x):
 
 
 def fma32(a, b, c):
-    """Correctly rounded float32 fma(a, b, c) for float32 array inputs.
+    """Correctly rounded float32 fma(a, b, c) for float32 array inputs (vectorised, exact).
 
-    a*b is exact in float64 (24+24 <= 53 bits).  The float64 add rounds once
-    and the cast to float32 rounds again; the two roundings can only disagree
-    with a true fma when the float64 sum lies exactly on a float32 rounding
-    boundary (low 29 mantissa bits == 0x10000000).  Those (astronomically rare)
-    elements are recomputed with exact rational arithmetic.
+    p = a*b is exact in float64 (24+24 <= 53 bits).  s = fl64(p + c) may round; TwoSum recovers the
+    exact residual err = (p + c) - s.  Casting s to float32 is a correct single rounding unless s
+    sits exactly on a float32 tie (low 29 mantissa bits == 0x10000000) while err != 0: the true
+    value is then strictly on one side of the tie and the result is the neighbour on that side.
     """
     a = np.asarray(a, dtype=np.float32)
     b = np.asarray(b, dtype=np.float32)
     c = np.asarray(c, dtype=np.float32)
     a, b, c = np.broadcast_arrays(a, b, c)
     with np.errstate(all="ignore"):
-        s = a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)
+        p = a.astype(np.float64) * b.astype(np.float64)
+        c64 = c.astype(np.float64)
+        s = p + c64
+        bb = s - p
+        err = (p - (s - bb)) + (c64 - bb)
         out = s.astype(np.float32)
-    bits = s.view(np.uint64) if s.flags["C_CONTIGUOUS"] else np.ascontiguousarray(s).view(np.uint64)
-    tie = ((bits & np.uint64(0x1FFFFFFF)) == np.uint64(0x10000000)) & np.isfinite(s)
-    if np.any(tie):
-        out = out.copy()
-        idx = np.nonzero(tie)
-        for i in zip(*idx):
-            exact = Fraction(float(a[i])) * Fraction(float(b[i])) + Fraction(float(c[i]))
-            out[i] = _round_fraction_to_f32(exact)
+        bits = np.ascontiguousarray(s).view(np.uint64)
+        tie = ((bits & np.uint64(0x1FFFFFFF)) == np.uint64(0x10000000)) & np.isfinite(s) & (err != 0)
+        if np.any(tie):
+            near = out.astype(np.float64)
+            up = np.where(near > s, out, np.nextafter(out, np.float32(np.inf)))
+            dn = np.where(near > s, np.nextafter(out, np.float32(-np.inf)), out)
+            out = np.where(tie, np.where(err > 0, up, dn), out).astype(np.float32)
     return out
-
-
-def _round_fraction_to_f32(q: Fraction) -> np.float32:
-    # round-to-nearest-even of an exact rational to binary32 via two candidates
-    lo = np.float32(float(q))  # float(q) is correctly rounded to double; cast may double-round
-    cands = [lo, np.nextafter(lo, np.float32(np.inf)), np.nextafter(lo, np.float32(-np.inf))]
-    best = None
-    for cnd in cands:
-        err = abs(Fraction(float(cnd)) - q)
-        key = (err, int(np.float32(cnd).view(np.uint32)) & 1)  # ties -> even mantissa
-        if best is None or key < best[0]:
-            best = (key, cnd)
-    return np.float32(best[1])
 
 
 def lowbias32(x):

@@ -1,0 +1,447 @@
+"""Torch-facing wrappers (allocation + autograd) over the C ABI in include/pagnerf_b200.h.
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd graph; every arithmetic
+step of the hot path is one of our sm_100a kernels.  All functions require CUDA tensors and raise
+otherwise -- there is deliberately no CPU or library fallback.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import call, ptr, ptr_array
+
+
+def _chk(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pagnerf_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _f32(t):
+    if t is None:
+        return None
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# octree / marching
+# ------------------------------------------------------------------------------------------------
+_LINSPACE = {}
+
+
+def _linspace(S, device):
+    key = (S, str(device))
+    if key not in _LINSPACE:
+        _LINSPACE[key] = torch.linspace(0.0, 1.0, S, dtype=torch.float32).to(device)  # CPU arithmetic == oracle
+    return _LINSPACE[key]
+
+
+def octree_query(octree, prefix, coords, level):
+    """kaolin.ops.spc.unbatched_query -> int32 [P] (-1 = empty)."""
+    _chk(octree, prefix, coords)
+    c = _f32(coords).reshape(-1, 3)
+    out = torch.empty(c.shape[0], dtype=torch.int32, device=c.device)
+    call("pag_octree_query", ptr(octree), ptr(prefix), ptr(c), c.shape[0], int(level), ptr(out))
+    return out
+
+
+def raymarch_ray(octree, prefix, origins, dirs, level, num_samples, dist_min, dist_max, jitter=None, seed=0):
+    """'ray' mode.  Returns ridx i64[M], pidx i64[M], samples f32[M,1,3], depths f32[M,1], deltas f32[M,1],
+    boundary bool[M], offsets i64[N+1] (per-ray packed start; offsets[N] = M)."""
+    _chk(octree, prefix, origins, dirs)
+    o, d = _f32(origins), _f32(dirs)
+    N, S, dev = o.shape[0], int(num_samples), o.device
+    lin = _linspace(S, dev)
+    pidx_tmp = torch.empty(max(N * S, 1), dtype=torch.int32, device=dev)
+    counts = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    offsets = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    jit = _f32(jitter) if jitter is not None else None
+    near, rng = float(dist_min), float(torch.tensor(float(dist_max) - float(dist_min), dtype=torch.float32))
+    call("pag_march_ray_count", ptr(o), ptr(d), N, S, ptr(lin), ptr(jit), int(seed), near, rng,
+         ptr(octree), ptr(prefix), int(level), ptr(pidx_tmp), ptr(counts), ptr(offsets))
+    M = int(offsets[-1].item())  # the one host sync the tensor-shaped plugin API needs
+    ridx = torch.empty(M, dtype=torch.int64, device=dev)
+    pidx = torch.empty(M, dtype=torch.int64, device=dev)
+    samples = torch.empty(M, 1, 3, dtype=torch.float32, device=dev)
+    depths = torch.empty(M, 1, dtype=torch.float32, device=dev)
+    deltas = torch.empty(M, 1, dtype=torch.float32, device=dev)
+    boundary = torch.empty(M, dtype=torch.bool, device=dev)
+    if M:
+        call("pag_march_ray_emit", ptr(o), ptr(d), N, S, ptr(lin), ptr(jit), int(seed), near, rng,
+             ptr(pidx_tmp), ptr(offsets), ptr(ridx), ptr(pidx), ptr(samples), ptr(depths), ptr(deltas), ptr(boundary))
+    return ridx, pidx, samples, depths, deltas, boundary, offsets
+
+
+def raytrace(octree, prefix, origins, dirs, level):
+    """kaolin unbatched_raytrace(return_depth=True, with_exit=True) -> ridx i64[K], pidx i64[K], depth f32[K,2], offsets."""
+    _chk(octree, prefix, origins, dirs)
+    o, d = _f32(origins), _f32(dirs)
+    N, dev = o.shape[0], o.device
+    counts = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    offsets = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    call("pag_raytrace_count", ptr(octree), ptr(prefix), ptr(o), ptr(d), N, int(level), ptr(counts), ptr(offsets))
+    K = int(offsets[-1].item())
+    ridx = torch.empty(K, dtype=torch.int64, device=dev)
+    pidx = torch.empty(K, dtype=torch.int64, device=dev)
+    depth = torch.empty(K, 2, dtype=torch.float32, device=dev)
+    if K:
+        call("pag_raytrace_emit", ptr(octree), ptr(prefix), ptr(o), ptr(d), N, int(level), ptr(offsets),
+             ptr(ridx), ptr(pidx), ptr(depth))
+    return ridx, pidx, depth, offsets
+
+
+def raymarch_voxel(octree, prefix, origins, dirs, level, num_samples, jitter=None, seed=0):
+    """'voxel' mode.  Returns ridx i64[K], pidx i64[K], samples f32[K,S,3], depths f32[K,S,1], deltas f32[K*S,1],
+    boundary bool[K*S], offsets i64[N+1] (per-ray first nugget)."""
+    ridx, pidx, depth, offsets = raytrace(octree, prefix, origins, dirs, level)
+    o, d = _f32(origins), _f32(dirs)
+    K, S, dev = ridx.shape[0], int(num_samples), o.device
+    samples = torch.empty(K, S, 3, dtype=torch.float32, device=dev)
+    depths = torch.empty(K, S, 1, dtype=torch.float32, device=dev)
+    deltas = torch.empty(K * S, 1, dtype=torch.float32, device=dev)
+    boundary = torch.empty(K * S, dtype=torch.bool, device=dev)
+    jit = _f32(jitter) if jitter is not None else None
+    if K:
+        call("pag_voxel_samples", ptr(o), ptr(d), ptr(ridx), ptr(depth), K, S, ptr(jit), int(seed),
+             ptr(samples), ptr(depths), ptr(deltas), ptr(boundary))
+    return ridx, pidx, samples, depths, deltas, boundary, offsets
+
+
+def max_travel_mask(ridx, depths, ray_first, max_travel):
+    """tracers/panoptic_packed_rf_tracer.py:88-99 -> bool[K] keep mask over nuggets."""
+    K = ridx.shape[0]
+    S = depths.shape[1] if depths.dim() > 1 else 1
+    keep = torch.empty(K, dtype=torch.bool, device=ridx.device)
+    if K:
+        call("pag_max_travel_mask", ptr(ridx), ptr(depths.contiguous()), K, S, ptr(ray_first), float(max_travel), ptr(keep))
+    return keep
+
+
+def mark_pack_boundaries(ids):
+    _chk(ids)
+    ids64 = ids.to(torch.int64).contiguous()
+    out = torch.empty(ids64.shape[0], dtype=torch.bool, device=ids.device)
+    call("pag_mark_pack_boundaries", ptr(ids64), ids64.shape[0], ptr(out))
+    return out
+
+
+def ray_offsets(ridx, num_rays):
+    """offsets i64[R+1] from an ascending ridx (lower_bound per ray)."""
+    _chk(ridx)
+    r64 = ridx.to(torch.int64).contiguous()
+    off = torch.empty(num_rays + 1, dtype=torch.int64, device=ridx.device)
+    call("pag_ray_offsets", ptr(r64), r64.shape[0], int(num_rays), ptr(off))
+    return off
+
+
+class RaySamplesFn(Function):
+    """Re-attaches the marcher's sample positions to the ray tensors for autograd:
+    samples = o[ridx] + d[ridx] * t   (values come from the marcher kernel, bit-exact)."""
+
+    @staticmethod
+    def forward(ctx, origins, dirs, samples, depths, offsets):
+        ctx.save_for_backward(depths, offsets)
+        ctx.n = origins.shape[0]
+        return samples.clone()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        depths, offsets = ctx.saved_tensors
+        # packs here are rays over *nuggets x samples*: offsets index rows of g.view(-1, 3)
+        g2 = _f32(g).reshape(-1, 3)
+        t = depths.reshape(-1, 1)
+        go = torch.empty(ctx.n, 3, dtype=torch.float32, device=g.device)
+        gd = torch.empty(ctx.n, 3, dtype=torch.float32, device=g.device)
+        gt = (g2 * t).contiguous()
+        call("pag_sum_reduce_fwd", ptr(g2), 3, ptr(offsets), ctx.n, ptr(go))
+        call("pag_sum_reduce_fwd", ptr(gt), 3, ptr(offsets), ctx.n, ptr(gd))
+        return go, gd, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# encoders
+# ------------------------------------------------------------------------------------------------
+class PermutoEncodeFn(Function):
+    @staticmethod
+    def forward(ctx, pos, table, scale_factor, shift, anneal, n_agg_levels):
+        _chk(pos, table, scale_factor, shift, anneal)
+        p = _f32(pos).reshape(-1, 3)
+        L, cap, F = table.shape
+        out = torch.empty(p.shape[0], L * F, dtype=torch.float32, device=p.device)
+        tb = table.detach().contiguous()
+        call("pag_permuto_fwd", ptr(p), p.shape[0], ptr(tb), cap, L, F, ptr(scale_factor), ptr(shift), ptr(anneal), ptr(out))
+        ctx.save_for_backward(p, tb, scale_factor, shift, anneal)
+        ctx.n_agg = int(n_agg_levels)
+        ctx.pos_shape = pos.shape
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        p, tb, sf, sh, an = ctx.saved_tensors
+        L, cap, F = tb.shape
+        g = _f32(g)
+        need_pos, need_tab = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gpos = torch.empty_like(p) if need_pos else None
+        gtab = torch.zeros_like(tb)
+        call("pag_permuto_bwd", ptr(p), p.shape[0], ptr(tb), cap, L, F, ptr(sf), ptr(sh), ptr(an), ptr(g),
+             ptr(gtab), ptr(gpos), ctx.n_agg)
+        return (gpos.reshape(ctx.pos_shape) if need_pos else None), (gtab if need_tab else None), None, None, None, None
+
+
+def permuto_encode(pos, table, scale_factor, shift, anneal, n_agg_levels=0):
+    return PermutoEncodeFn.apply(pos, table, scale_factor, shift, anneal, n_agg_levels)
+
+
+def permuto_indices(pos, capacity, scale_factor, shift):
+    p = _f32(pos).reshape(-1, 3)
+    L, M = scale_factor.shape[0], p.shape[0]
+    idx = torch.empty(L, M, 4, dtype=torch.int32, device=p.device)
+    rank = torch.empty(L, M, 4, dtype=torch.int32, device=p.device)
+    bary = torch.empty(L, M, 4, dtype=torch.float32, device=p.device)
+    call("pag_permuto_indices", ptr(p), M, int(capacity), L, ptr(scale_factor), ptr(shift), ptr(idx), ptr(rank), ptr(bary))
+    return idx, rank, bary
+
+
+class HashEncodeFn(Function):
+    @staticmethod
+    def forward(ctx, pos, table, flavour, fparam, res, offset, size, round_half, n_agg_levels):
+        _chk(pos, table, fparam, offset, size)
+        p = _f32(pos).reshape(-1, 3)
+        L = fparam.shape[0]
+        tb = table.detach().contiguous().view(-1, 2)
+        out = torch.empty(p.shape[0], L * 2, dtype=torch.float32, device=p.device)
+        call("pag_hash_fwd", int(flavour), ptr(p), p.shape[0], ptr(tb), L, 2, ptr(fparam), ptr(res), ptr(offset),
+             ptr(size), ptr(out), int(round_half))
+        ctx.save_for_backward(p, tb, fparam, res, offset, size)
+        ctx.flavour, ctx.n_agg, ctx.pos_shape, ctx.tab_shape = int(flavour), int(n_agg_levels), pos.shape, table.shape
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        p, tb, fparam, res, offset, size = ctx.saved_tensors
+        L = fparam.shape[0]
+        g = _f32(g)
+        need_pos, need_tab = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gpos = torch.empty_like(p) if need_pos else None
+        gtab = torch.zeros_like(tb)
+        call("pag_hash_bwd", ctx.flavour, ptr(p), p.shape[0], ptr(tb), L, 2, ptr(fparam), ptr(res), ptr(offset), ptr(size),
+             ptr(g), ptr(gtab), ptr(gpos), ctx.n_agg)
+        return ((gpos.reshape(ctx.pos_shape) if need_pos else None), (gtab.view(ctx.tab_shape) if need_tab else None),
+                None, None, None, None, None, None, None)
+
+
+def hash_encode(pos, table, flavour, fparam, res, offset, size, round_half=False, n_agg_levels=0):
+    return HashEncodeFn.apply(pos, table, flavour, fparam, res, offset, size, round_half, n_agg_levels)
+
+
+def hash_indices(pos, flavour, fparam, res, offset, size):
+    p = _f32(pos).reshape(-1, 3)
+    L, M = fparam.shape[0], p.shape[0]
+    idx = torch.empty(L, M, 8, dtype=torch.int32, device=p.device)
+    call("pag_hash_indices", int(flavour), ptr(p), M, L, ptr(fparam), ptr(res), ptr(offset), ptr(size), ptr(idx))
+    return idx
+
+
+# ------------------------------------------------------------------------------------------------
+# decoders
+# ------------------------------------------------------------------------------------------------
+HIDDEN = 64
+VIEW_DIM = 27
+
+
+class DecodeDCFn(Function):
+    """density + color decoders.  feats [M,IN], ray_d [M//S, 3] -> sigma [M], rgb [M,3] (or None)."""
+
+    @staticmethod
+    def forward(ctx, feats, lodw, ray_d, S, want_rgb, *weights):
+        _chk(feats, ray_d, *weights)
+        f = _f32(feats)
+        M, IN = f.shape
+        rd = _f32(ray_d)
+        w = [_f32(x) for x in weights]
+        sigma = torch.empty(M, dtype=torch.float32, device=f.device)
+        rgb = torch.empty(M, 3, dtype=torch.float32, device=f.device) if want_rgb else None
+        lw = _f32(lodw)
+        call("pag_decode_dc_fwd", ptr(f), ptr(lw), ptr(rd), int(S), M, IN, ptr_array(w), HIDDEN, VIEW_DIM,
+             int(bool(want_rgb)), ptr(sigma), ptr(rgb))
+        ctx.save_for_backward(f, lw, rd, *w)
+        ctx.S, ctx.want_rgb = int(S), bool(want_rgb)
+        return sigma, rgb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_sigma, g_rgb):
+        f, lw, rd, *w = ctx.saved_tensors
+        M, IN = f.shape
+        gs = _f32(g_sigma) if g_sigma is not None else None
+        gr = _f32(g_rgb) if (g_rgb is not None and ctx.want_rgb) else None
+        grads = [torch.zeros_like(x) for x in w]
+        need_f, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+        gf = torch.empty_like(f) if need_f else None
+        gd = torch.empty(M, 3, dtype=torch.float32, device=f.device) if need_d else None
+        call("pag_decode_dc_bwd", ptr(f), ptr(lw), ptr(rd), ctx.S, M, IN, ptr_array(w), ptr_array(grads), HIDDEN,
+             VIEW_DIM, ptr(gs), ptr(gr), ptr(gf), ptr(gd))
+        if need_d:
+            gd = gd.view(-1, ctx.S, 3).sum(1) if ctx.S > 1 else gd
+        return (gf, None, gd, None, None, *grads)
+
+
+class DecodePanFn(Function):
+    """semantic + instance decoders on panop = (feats + dfeats) * lodw."""
+
+    @staticmethod
+    def forward(ctx, feats, dfeats, lodw, Cs, Ci, sem_softmax, inst_softmax, inst_temperature, *weights):
+        _chk(feats, dfeats, *weights)
+        f = _f32(feats)
+        df = _f32(dfeats)
+        M, IN = f.shape
+        w = [_f32(x) for x in weights]
+        sem = torch.empty(M, Cs, dtype=torch.float32, device=f.device) if Cs else None
+        inst = torch.empty(M, Ci, dtype=torch.float32, device=f.device) if Ci else None
+        lw = _f32(lodw)
+        call("pag_decode_pan_fwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), HIDDEN, int(Cs), int(Ci),
+             int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature), ptr(sem), ptr(inst))
+        ctx.save_for_backward(f, df, lw, sem, inst, *w)
+        ctx.cfg = (int(Cs), int(Ci), int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature))
+        return sem, inst
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_sem, g_inst):
+        f, df, lw, sem, inst, *w = ctx.saved_tensors
+        Cs, Ci, ss, is_, it = ctx.cfg
+        M, IN = f.shape
+        gs = _f32(g_sem) if (g_sem is not None and Cs) else None
+        gi = _f32(g_inst) if (g_inst is not None and Ci) else None
+        grads = [torch.zeros_like(x) for x in w]
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gp = torch.empty_like(f) if need else None
+        call("pag_decode_pan_bwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), ptr_array(grads), HIDDEN, Cs, Ci, ss, is_, it,
+             ptr(sem), ptr(inst), ptr(gs), ptr(gi), ptr(gp))
+        return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
+                None, None, None, None, None, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+class CompositeFn(Function):
+    """Fused PanopticPackedRFTracer integration (tracers/panoptic_packed_rf_tracer.py:134-205).
+    Inputs are packed per sample; `offsets` [R+1] gives each ray's packed range.  Dense [R,*] outputs."""
+
+    @staticmethod
+    def forward(ctx, sigma, deltas, depths, rgb, sem, inst, offsets, bg_white):
+        _chk(sigma, deltas, offsets)
+        sg, dl = _f32(sigma).reshape(-1), _f32(deltas).reshape(-1)
+        dp = _f32(depths).reshape(-1) if depths is not None else None
+        c = _f32(rgb).reshape(-1, 3) if rgb is not None else None
+        se = _f32(sem) if sem is not None else None
+        ins = _f32(inst) if inst is not None else None
+        R, M, dev = offsets.shape[0] - 1, sg.shape[0], sg.device
+        Cs = se.shape[1] if se is not None else 0
+        Ci = ins.shape[1] if ins is not None else 0
+        w = torch.empty(M, dtype=torch.float32, device=dev)
+        T = torch.empty(M, dtype=torch.float32, device=dev)
+        alpha = torch.empty(R, 1, dtype=torch.float32, device=dev)
+        hit = torch.empty(R, dtype=torch.bool, device=dev)
+        rgb_o = torch.empty(R, 3, dtype=torch.float32, device=dev) if c is not None else None
+        rgbsum = torch.empty(R, 3, dtype=torch.float32, device=dev) if c is not None else None
+        dep_o = torch.empty(R, 1, dtype=torch.float32, device=dev) if dp is not None else None
+        sem_o = torch.empty(R, Cs, dtype=torch.float32, device=dev) if se is not None else None
+        inst_o = torch.empty(R, Ci, dtype=torch.float32, device=dev) if ins is not None else None
+        call("pag_composite_fwd", ptr(sg), ptr(dl), ptr(dp), ptr(c), ptr(se), Cs, ptr(ins), Ci, ptr(offsets), R,
+             int(bool(bg_white)), ptr(w), ptr(T), ptr(alpha), ptr(hit), ptr(rgb_o), ptr(rgbsum), ptr(dep_o), ptr(sem_o), ptr(inst_o))
+        ctx.save_for_backward(sg, dl, dp, c, offsets, w, T, alpha, rgbsum)
+        ctx.cfg = (int(bool(bg_white)), Cs, Ci, sigma.shape, None if rgb is None else rgb.shape)
+        ctx.mark_non_differentiable(hit)
+        return alpha, hit, rgb_o, dep_o, sem_o, inst_o
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_alpha, g_hit, g_rgb, g_depth, g_sem, g_inst):
+        sg, dl, dp, c, offsets, w, T, alpha, rgbsum = ctx.saved_tensors
+        bgw, Cs, Ci, sig_shape, rgb_shape = ctx.cfg
+        R, M, dev = offsets.shape[0] - 1, sg.shape[0], sg.device
+        ga = _f32(g_alpha) if g_alpha is not None else None
+        gr = _f32(g_rgb) if (g_rgb is not None and c is not None) else None
+        gd = _f32(g_depth) if (g_depth is not None and dp is not None) else None
+        gs = _f32(g_sem) if (g_sem is not None and Cs) else None
+        gi = _f32(g_inst) if (g_inst is not None and Ci) else None
+        g_sigma = torch.zeros(M, dtype=torch.float32, device=dev)
+        g_rgb_s = torch.empty(M, 3, dtype=torch.float32, device=dev) if gr is not None else None
+        g_sem_s = torch.empty(M, Cs, dtype=torch.float32, device=dev) if gs is not None else None
+        g_inst_s = torch.empty(M, Ci, dtype=torch.float32, device=dev) if gi is not None else None
+        call("pag_composite_bwd", ptr(sg), ptr(dl), ptr(dp), ptr(c), ptr(offsets), R, bgw, ptr(w), ptr(T), ptr(alpha),
+             ptr(rgbsum), ptr(ga), ptr(gr), ptr(gd), ptr(gs), Cs, ptr(gi), Ci, ptr(g_sigma), ptr(g_rgb_s), ptr(g_sem_s), ptr(g_inst_s))
+        return (g_sigma.reshape(sig_shape), None, None,
+                g_rgb_s.reshape(rgb_shape) if g_rgb_s is not None else None, g_sem_s, g_inst_s, None, None)
+
+
+def composite(sigma, deltas, depths, rgb, sem, inst, offsets, bg_white=True):
+    return CompositeFn.apply(sigma, deltas, depths, rgb, sem, inst, offsets, bg_white)
+
+
+# ---- kaolin.render.spc compatible pieces (used by callers that integrate by hand) -----------------
+def _pack_offsets(boundary):
+    b = boundary.to(torch.bool)
+    starts = torch.nonzero(b).flatten()
+    return torch.cat([starts, torch.tensor([b.shape[0]], device=b.device, dtype=torch.int64)]).contiguous()
+
+
+class SumReduceFn(Function):
+    @staticmethod
+    def forward(ctx, x, offsets):
+        x2 = _f32(x)
+        R = offsets.shape[0] - 1
+        out = torch.empty(R, x2.shape[1], dtype=torch.float32, device=x2.device)
+        call("pag_sum_reduce_fwd", ptr(x2), x2.shape[1], ptr(offsets), R, ptr(out))
+        ctx.save_for_backward(offsets)
+        ctx.shape = x2.shape
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (offsets,) = ctx.saved_tensors
+        gx = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        call("pag_sum_reduce_bwd", ptr(_f32(g)), ctx.shape[1], ptr(offsets), offsets.shape[0] - 1, ptr(gx))
+        return gx, None
+
+
+def sum_reduce(x, boundary):
+    """kaolin.render.spc.sum_reduce: [M,C] -> [R,C]."""
+    return SumReduceFn.apply(x, _pack_offsets(boundary))
+
+
+class ExpIntFn(Function):
+    @staticmethod
+    def forward(ctx, tau, offsets):
+        t = _f32(tau).reshape(-1)
+        w = torch.empty_like(t)
+        T = torch.empty_like(t)
+        call("pag_expint_fwd", ptr(t), ptr(offsets), offsets.shape[0] - 1, ptr(w), ptr(T))
+        ctx.save_for_backward(w, T, offsets)
+        ctx.shape = tau.shape
+        return w.reshape(tau.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        w, T, offsets = ctx.saved_tensors
+        gt = torch.zeros_like(w)
+        call("pag_expint_bwd", ptr(_f32(g).reshape(-1)), ptr(w), ptr(T), ptr(offsets), offsets.shape[0] - 1, ptr(gt))
+        return gt.reshape(ctx.shape), None
+
+
+def exponential_integration(feats, tau, boundary, exclusive=True):
+    """kaolin.render.spc.exponential_integration -> (sum_reduce(feats*w) or feats, w)."""
+    assert exclusive, "only the exclusive form is used by the reference (tracers/panoptic_packed_rf_tracer.py:135)"
+    off = _pack_offsets(boundary)
+    w = ExpIntFn.apply(tau, off)
+    if feats is None or feats.numel() == 0:
+        return feats, w
+    return SumReduceFn.apply(feats * w, off), w

@@ -1,0 +1,5 @@
+"""Neural-field plugin classes with the reference's surface (pc_nerf/panoptic_{,delta_}nef.py)."""
+from .panoptic_nef import PanopticNeF
+from .panoptic_delta_nef import PanopticDeltaNeF
+
+__all__ = ["PanopticNeF", "PanopticDeltaNeF"]

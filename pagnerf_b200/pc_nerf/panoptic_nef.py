@@ -1,0 +1,218 @@
+"""PanopticNeF: grid encoder + density / color / semantic / instance decoders.
+
+Drop-in for the reference class (pc_nerf/panoptic_nef.py:20-363): same constructor arguments,
+attributes, parameter names (`grid.*`, `decoder_density.*`, `decoder_color.*`,
+`decoder_semantics.*`, `decoder_inst.*`), channel dispatch and output shapes.  The forward itself
+is two fused kernels (csrc/decoder.cu) on top of the grid's encode kernel instead of 9 GEMMs and
+~15 elementwise launches.
+"""
+import logging as log
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .. import ops, spc
+from ..grids import HashGridTorch, HashGridTinyCudaNN, PermutoGrid
+from ..wisp_compat import (BaseNeuralField, BasicDecoder, PerfTimer, get_activation_class, get_layer_class,
+                           get_positional_embedder)
+
+
+def _decoder_tensors(dec, n_hidden):
+    """[W0,b0,(W1,b1,)Wout,bout] of a BasicDecoder; validates the shapes csrc/decoder.cu is built for."""
+    if len(dec.layers) != n_hidden or any(l.out_features != ops.HIDDEN for l in dec.layers) or not dec.bias or dec.skip:
+        raise NotImplementedError(
+            "csrc/decoder.cu is specialised to the reference configuration (configs/bup20/*.yaml: hidden_dim 64, "
+            "density/semantic decoders with 1 hidden layer, color/instance with 2, bias, no skip)")
+    out = []
+    for l in dec.layers:
+        out += [l.weight, l.bias]
+    return out + [dec.lout.weight, dec.lout.bias]
+
+
+class PanopticNeF(BaseNeuralField):
+    def __init__(self,
+                 num_classes: int = -1, num_instances: int = -1,
+                 sem_activation_type: str = None, sem_num_layers: int = None, sem_hidden_dim: int = None,
+                 sem_normalize: bool = False, sem_softmax: bool = False, sem_sigmoid: bool = False, sem_detach: bool = True,
+                 inst_num_layers: int = None, inst_hidden_dim: int = None, inst_normalize: bool = False,
+                 inst_softmax: bool = False, inst_sigmoid: bool = False, inst_detach: bool = True,
+                 panoptic_features_type: str = None, **kwargs):
+        self.num_classes = num_classes
+        self.num_instances = num_instances
+        self.sem_activation_type = sem_activation_type
+        self.sem_num_layers = sem_num_layers
+        self.sem_hidden_dim = sem_hidden_dim
+        self.sem_normalize = sem_normalize
+        self.sem_softmax = sem_softmax
+        self.sem_sigmoid = sem_sigmoid
+        self.sem_detach = sem_detach
+        self.inst_num_layers = inst_num_layers
+        self.inst_hidden_dim = inst_hidden_dim
+        self.inst_detach = inst_detach
+        self.inst_softmax = inst_softmax
+        self.inst_normalize = inst_normalize
+        self.inst_sigmoid = inst_sigmoid
+        self.panoptic_features_type = panoptic_features_type
+        # the reference never assigns this attribute (latent AttributeError); define it
+        self.inst_direct_pos = bool(kwargs.get('inst_direct_pos', False))
+        super().__init__(**kwargs)
+
+    # ---- construction (mirrors pc_nerf/panoptic_nef.py:72-196) ------------------------------------
+    def init_embedder(self):
+        self.view_embedder, self.view_embed_dim = get_positional_embedder(self.view_multires,
+                                                                          self.embedder_type == "positional")
+        log.info(f"View Embed Dim: {self.view_embed_dim}")
+
+    def _compute_input_dimension(self):
+        if self.position_input:
+            raise NotImplementedError
+        if self.multiscale_type == 'cat':
+            self.effective_feature_dim = self.grid.feature_dim * self.num_lods
+        elif self.multiscale_type == 'sum':
+            self.effective_feature_dim = self.grid.feature_dim
+        else:
+            raise NotImplementedError(f"'{self.multiscale_type}' not supported by this neural field. "
+                                      "supported options ['cat', 'sum']")
+        self.input_dim_density = self.effective_feature_dim
+        if self.panoptic_features_type == 'position':
+            self.input_dim_inst = self.input_dim_sem = 3
+        elif self.panoptic_features_type == 'pos_encoding':
+            self.input_dim_inst = self.input_dim_sem = self.pos_embed_dim
+        else:
+            self.input_dim_inst = self.input_dim_sem = self.effective_feature_dim
+
+    def init_decoder(self):
+        self._compute_input_dimension()
+        act, layer = get_activation_class(self.activation_type), get_layer_class(self.layer_type)
+        self.decoder_density = BasicDecoder(input_dim=self.input_dim_density, output_dim=16, activation=act, bias=True,
+                                            layer=layer, num_layers=self.num_layers, hidden_dim=self.hidden_dim, skip=[])
+        self.decoder_density.lout.bias.data[0] = 1.0
+        self.decoder_color = BasicDecoder(input_dim=16 + self.view_embed_dim, output_dim=3, activation=act, bias=True,
+                                          layer=layer, num_layers=self.num_layers + 1, hidden_dim=self.hidden_dim, skip=[])
+        self.sem_activation_type = self.sem_activation_type if self.sem_activation_type else self.activation_type
+        self.sem_num_layers = self.sem_num_layers if self.sem_num_layers else self.num_layers
+        self.sem_hidden_dim = self.sem_hidden_dim if self.sem_hidden_dim else self.hidden_dim
+        sact = get_activation_class(self.sem_activation_type)
+        self.decoder_semantics = BasicDecoder(input_dim=self.input_dim_sem, output_dim=self.num_classes, activation=sact,
+                                              bias=True, layer=layer, num_layers=self.sem_num_layers,
+                                              hidden_dim=self.sem_hidden_dim, skip=[])
+        assert self.num_instances > 2, f"'num_instances' needs to be >= 2, but {self.num_classes} was given."
+        self.inst_num_layers = self.inst_num_layers if self.inst_num_layers else self.num_layers
+        self.inst_hidden_dim = self.inst_hidden_dim if self.inst_hidden_dim else self.hidden_dim
+        self.decoder_inst = BasicDecoder(input_dim=self.input_dim_inst, output_dim=self.num_instances, activation=sact,
+                                         bias=True, layer=layer, num_layers=self.inst_num_layers,
+                                         hidden_dim=self.inst_hidden_dim, skip=[])
+
+    def _get_grid_class(self):
+        table = {"HashGridTorch": HashGridTorch, "HashGridTinyCudaNN": HashGridTinyCudaNN, "PermutoGrid": PermutoGrid}
+        if self.grid_type not in table:
+            raise NotImplementedError(f"'{self.grid_type}' not supproted")
+        return table[self.grid_type]
+
+    def init_grid(self):
+        self.grid = self._get_grid_class()(self.feature_dim, base_lod=self.base_lod, num_lods=self.num_lods,
+                                           interpolation_type=self.interpolation_type, multiscale_type='cat',
+                                           **self.kwargs)
+        self.lod_weights = torch.ones(self.num_lods * self.grid.feature_dim)
+
+    def get_nef_type(self):
+        return 'panoptic_nef'
+
+    # ---- pruning (pc_nerf/panoptic_nef.py:207-237) ------------------------------------------------
+    def _prune_grids(self):
+        return [self.grid]
+
+    def prune(self):
+        if self.grid is None:
+            return
+        density_decay = 0.6
+        min_density = ((0.01 * 512) / np.sqrt(3))
+        dev = self.device
+        self.grid.occupancy = self.grid.occupancy.to(dev) * density_decay
+        points = self.grid.dense_points.to(dev)
+        res = 2.0 ** self.grid.blas_level
+        samples = torch.rand(points.shape[0], 3, device=dev)
+        samples = (points.float() + samples) / res * 2.0 - 1.0
+        sample_views = F.normalize(torch.randn(samples.shape[0], 3, device=dev), dim=-1)
+        with torch.no_grad():
+            density = self.forward(coords=samples[:, None], ray_d=sample_views, channels="density")
+        self.grid.occupancy = torch.stack([density[:, 0, 0], self.grid.occupancy], -1).max(dim=-1)[0]
+        mask = self.grid.occupancy > min_density
+        _points = points[mask]
+        for grid in self._prune_grids():
+            octree = spc.unbatched_points_to_octree(_points, grid.blas_level, sorted=True)
+            grid.blas_init(octree)
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, channels=None, **kwargs):
+        kwargs['compute_channels'] = channels
+        return super().forward(channels, **kwargs)
+
+    def register_forward_functions(self):
+        self._register_forward_function(self.rgb_semantics, ["density", "rgb", "semantics", "inst_embedding"])
+
+    def _encode(self, grid, coords, lod_idx):
+        feats = grid.interpolate(coords, lod_idx)
+        feats = feats.reshape(-1, feats.shape[-1])
+        if self.multiscale_type == 'sum':
+            raise NotImplementedError("multiscale_type='sum' is not served by the fused decoders "
+                                      "(every reference config uses 'cat', configs/bup20/*.yaml)")
+        return feats
+
+    def _dc(self, feats, ray_d, num_samples, want_rgb):
+        w = _decoder_tensors(self.decoder_density, 1) + _decoder_tensors(self.decoder_color, 2)
+        lodw = self.lod_weights.to(feats.device)
+        return ops.DecodeDCFn.apply(feats, lodw, ray_d, num_samples, want_rgb, *w)
+
+    def _pan(self, feats, dfeats, want_sem, want_inst, inst_temperature=0.0):
+        """semantic / instance heads on (feats + dfeats) * lod_weights; non-default sigmoid / normalize
+        options are composed on the host from the raw logits."""
+        w = _decoder_tensors(self.decoder_semantics, 1) + _decoder_tensors(self.decoder_inst, 2)
+        lodw = self.lod_weights.to(feats.device)
+        sem_plain = not (self.sem_sigmoid or self.sem_normalize)
+        inst_plain = not (self.inst_sigmoid or self.inst_normalize)
+        Cs = self.num_classes if want_sem else 0
+        Ci = self.num_instances if want_inst else 0
+        sem, inst = ops.DecodePanFn.apply(feats, dfeats, lodw, Cs, Ci, bool(self.sem_softmax and sem_plain),
+                                          bool(self.inst_softmax and inst_plain),
+                                          float(inst_temperature if inst_plain else 0.0), *w)
+        if want_sem and not sem_plain:
+            sem = torch.sigmoid(sem) if self.sem_sigmoid else sem
+            sem = F.normalize(sem, dim=-1) if self.sem_normalize else sem
+            sem = F.softmax(sem, dim=-1) if self.sem_softmax else sem
+        if want_inst and not inst_plain:
+            inst = torch.sigmoid(inst) if self.inst_sigmoid else inst
+            inst = F.normalize(inst, dim=-1) if self.inst_normalize else inst
+            inst = inst / inst_temperature if inst_temperature > 0.0 else inst
+            inst = F.softmax(inst, dim=-1) if self.inst_softmax else inst
+        return sem, inst
+
+    def rgb_semantics(self, coords, ray_d, compute_channels, pidx=None, lod_idx=None):
+        """coords [batch, num_samples, 3], ray_d [batch, 3] -> dict with density [batch,S,1], rgb [batch,S,3],
+        semantics [batch*S, C], inst_embedding [batch*S, C] (reference shapes, pc_nerf/panoptic_nef.py:253-363)."""
+        out_dict = {}
+        if not compute_channels:
+            return out_dict
+        if lod_idx is None:
+            lod_idx = len(self.grid.active_lods) - 1
+        batch, num_samples, _ = coords.shape
+        feats = self._encode(self.grid, coords, lod_idx)
+        if any(c in compute_channels for c in ['density', 'rgb']):
+            sigma, rgb = self._dc(feats, ray_d, num_samples, 'rgb' in compute_channels)
+            if 'density' in compute_channels:
+                out_dict['density'] = sigma.reshape(batch, num_samples, 1)
+            if 'rgb' in compute_channels:
+                out_dict['rgb'] = rgb.reshape(batch, num_samples, 3)
+        want_sem, want_inst = 'semantics' in compute_channels, 'inst_embedding' in compute_channels
+        if want_inst and self.inst_direct_pos:
+            raise NotImplementedError("inst_direct_pos is not served by the fused decoders")
+        if want_sem and want_inst and self.sem_detach == self.inst_detach:
+            x = feats.detach() if self.sem_detach else feats
+            out_dict['semantics'], out_dict['inst_embedding'] = self._pan(x, None, True, True)
+        else:
+            if want_sem:
+                out_dict['semantics'], _ = self._pan(feats.detach() if self.sem_detach else feats, None, True, False)
+            if want_inst:
+                _, out_dict['inst_embedding'] = self._pan(feats.detach() if self.inst_detach else feats, None, False, True)
+        return out_dict

@@ -1,0 +1,406 @@
+"""GPU parity: every CUDA kernel (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact for integers (octree cells, packed indices, lattice / hash vertex indices, boundaries) and for the
+marcher's float32 depths/samples (identical op order); 1e-4 relative for features, rendered outputs and
+gradients (north_star).  Honest statement: "bit-exact vs OUR CPU restatement of the upstream algorithms; upstream
+binaries unavailable; the in-tree hash_grid_torch and the tracer/nef glue are matched via the reference-made goldens".
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import (load_golden, build_oracle_field, build_cuda_nef, oracle_march, golden_grads, golden_params,
+                        assert_close, GOLDEN_CFG)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _scene(level, seed=0, frac=0.25):
+    rng = np.random.default_rng(seed)
+    n = 1 << level
+    k = max(8, int(frac * n ** 3))
+    return rng.integers(0, n, size=(k, 3)).astype(np.int16)
+
+
+def _rays(N, seed=0, inside=False):
+    rng = np.random.default_rng(seed)
+    if inside:
+        o = rng.uniform(-0.7, 0.7, (N, 3)).astype(np.float32)
+    else:
+        o = np.stack([rng.uniform(-0.6, 0.6, N), rng.uniform(-0.6, 0.6, N), np.full(N, 1.3)], 1).astype(np.float32)
+    d = rng.normal(size=(N, 3)).astype(np.float32)
+    if not inside:
+        d[:, 2] = -np.abs(d[:, 2]) - 0.3
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[0] = np.array([0.0, 0.0, -1.0], np.float32)      # axis-aligned: zero components -> inf reciprocals
+    d[1] = np.array([0.0, 1.0, 0.0], np.float32)
+    return o, d.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# octree
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("level", [1, 4, 6])
+def test_octree_build_and_query(cuda_lib, level):
+    from oracle import spc as ospc
+    from pagnerf_b200 import spc, ops
+    pts = _scene(level, seed=level)
+    oc_ref = ospc.points_to_octree(pts, level)
+    p_ref, py_ref, pre_ref = ospc.scan_octree(oc_ref, level)
+    oc = spc.unbatched_points_to_octree(torch.from_numpy(pts).to(DEV), level)
+    assert np.array_equal(oc.cpu().numpy(), oc_ref)
+    blas = spc.OctreeAS(DEV)
+    blas.init(oc)
+    assert blas.max_level == level
+    assert np.array_equal(blas.points.cpu().numpy(), p_ref)
+    assert np.array_equal(blas.pyramid.numpy(), py_ref)
+    assert np.array_equal(blas.prefix.cpu().numpy(), pre_ref)
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1.05, 1.05, (20000, 3)).astype(np.float32)
+    x[:8] = np.array([[1, 1, 1], [-1, -1, -1], [0, 0, 0], [1, 0, 0], [np.nan, 0, 0], [np.inf, 0, 0], [0.999999, 0.5, -1], [-1.0000001, 0, 0]], np.float32)
+    got = ops.octree_query(blas.octree, blas.prefix, torch.from_numpy(x).to(DEV), level).cpu().numpy()
+    assert np.array_equal(got, ospc.query(oc_ref, pre_ref, x, level))
+
+
+def test_octree_query_empty_and_dense(cuda_lib):
+    from oracle import spc as ospc
+    from pagnerf_b200 import spc, ops
+    blas = spc.OctreeAS(DEV)
+    blas.init_dense(3)
+    assert np.array_equal(blas.octree.cpu().numpy(), ospc.dense_octree(3))
+    out = ops.octree_query(blas.octree, blas.prefix, torch.zeros(0, 3, device=DEV), 3)
+    assert out.shape == (0,)
+
+
+@pytest.mark.parametrize("level,inside", [(4, False), (6, False), (5, True)])
+def test_raytrace_nuggets_bit_exact(cuda_lib, level, inside):
+    from oracle import spc as ospc
+    from pagnerf_b200 import spc, ops
+    pts = _scene(level, seed=10 + level, frac=0.15)
+    oc = ospc.points_to_octree(pts, level)
+    p, py, pre = ospc.scan_octree(oc, level)
+    o, d = _rays(700, seed=level, inside=inside)
+    r_ref, p_ref, dep_ref = ospc.raytrace(oc, p, py, pre, o, d, level)
+    blas = spc.OctreeAS(DEV); blas.init(torch.from_numpy(oc))
+    ridx, pidx, depth, offsets = ops.raytrace(blas.octree, blas.prefix, torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), level)
+    assert np.array_equal(ridx.cpu().numpy(), r_ref)
+    assert np.array_equal(pidx.cpu().numpy(), p_ref)
+    assert np.array_equal(depth.cpu().numpy().view(np.uint32), dep_ref.view(np.uint32)), "entry/exit depths bit-exact"
+    assert int(offsets[-1]) == r_ref.shape[0]
+
+
+@pytest.mark.parametrize("S", [7, 32, 64, 100])
+def test_raymarch_ray_bit_exact(cuda_lib, S):
+    from oracle import spc as ospc, raymarch as orm
+    from pagnerf_b200 import spc, ops
+    level = 5
+    oc = ospc.points_to_octree(_scene(level, seed=3, frac=0.2), level)
+    p, py, pre = ospc.scan_octree(oc, level)
+    o, d = _rays(300, seed=S)
+    ref = orm.raymarch_ray(oc, pre, o, d, level, S, 0.0, 2.5, seed=5)
+    blas = spc.OctreeAS(DEV); blas.init(torch.from_numpy(oc))
+    got = ops.raymarch_ray(blas.octree, blas.prefix, torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), level, S, 0.0, 2.5, seed=5)
+    names = ["ridx", "pidx", "samples", "depths", "deltas", "boundary"]
+    for n, a, b in zip(names, got[:6], ref):
+        a = a.cpu().numpy()
+        assert a.shape == b.shape, (n, a.shape, b.shape)
+        if a.dtype == np.float32:
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), n
+        else:
+            assert np.array_equal(a, b), n
+    # explicit jitter tensor == counter stream
+    from oracle.f32 import jitter_u01
+    jit = jitter_u01(5, np.arange(300 * S, dtype=np.uint64)).reshape(300, S)
+    got2 = ops.raymarch_ray(blas.octree, blas.prefix, torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), level, S, 0.0, 2.5,
+                            jitter=torch.from_numpy(jit).to(DEV))
+    assert torch.equal(got2[2], got[2]) and torch.equal(got2[0], got[0])
+
+
+def test_raymarch_voxel_bit_exact_and_filter(cuda_lib):
+    from oracle import spc as ospc, raymarch as orm
+    from pagnerf_b200 import spc, ops
+    level, S = 5, 3
+    oc = ospc.points_to_octree(_scene(level, seed=4, frac=0.2), level)
+    p, py, pre = ospc.scan_octree(oc, level)
+    o, d = _rays(400, seed=2)
+    ref = orm.raymarch_voxel(oc, p, py, pre, o, d, level, S, seed=9)
+    blas = spc.OctreeAS(DEV); blas.init(torch.from_numpy(oc))
+    got = ops.raymarch_voxel(blas.octree, blas.prefix, torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), level, S, seed=9)
+    for n, a, b in zip(["ridx", "pidx", "samples", "depths", "deltas", "boundary"], got[:6], ref):
+        a = a.cpu().numpy()
+        assert a.shape == b.shape, (n, a.shape, b.shape)
+        if a.dtype == np.float32:
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), n
+        else:
+            assert np.array_equal(a, b), n
+    keep_ref = orm.max_travel_filter(ref[0], ref[3], 0.4)
+    first = ops.ray_offsets(got[0], 400)
+    keep = ops.max_travel_mask(got[0], got[3], first, 0.4).cpu().numpy()
+    assert np.array_equal(keep, keep_ref) and 0 < keep.sum() < keep.shape[0]
+
+
+def test_raymarch_no_hits(cuda_lib):
+    from pagnerf_b200 import spc, ops
+    blas = spc.OctreeAS(DEV); blas.init_dense(2)
+    o = torch.tensor([[3.0, 3.0, 3.0]] * 5, device=DEV)
+    d = torch.tensor([[0.0, 0.0, 1.0]] * 5, device=DEV)
+    for out in (ops.raymarch_ray(blas.octree, blas.prefix, o, d, 2, 16, 0.0, 1.0), ops.raymarch_voxel(blas.octree, blas.prefix, o, d, 2, 4)):
+        assert out[0].numel() == 0 and out[2].shape[0] == 0 and int(out[6][-1]) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# encoders
+# ------------------------------------------------------------------------------------------------
+def _points(M, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, (M, 3)).astype(np.float32)
+    x[:6] = np.array([[0, 0, 0], [1, 1, 1], [-1, -1, -1], [0.5, -0.25, 0.125], [1e-6, -1e-6, 0], [0.999, -0.999, 0.3]], np.float32)
+    return x
+
+
+@pytest.mark.parametrize("cap,L,finest", [(2 ** 12, 8, 1e-2), (2 ** 18, 24, 1e-4), (1000, 5, 1e-1)])
+def test_permuto_indices_and_forward(cuda_lib, cap, L, finest):
+    from oracle.permuto import PermutoEncodingOracle
+    from pagnerf_b200 import ops
+    enc = PermutoEncodingOracle(cap, L, 2, np.geomspace(1.0, finest, L), seed=1)
+    with torch.no_grad():
+        enc.lattice_values.mul_(1e4)
+    x = torch.from_numpy(_points(3000, seed=L))
+    rem0, rank, idx = enc.indices(x)
+    sf, sh = enc.scale_factor.to(DEV), enc.random_shift_per_level.to(DEV)
+    gi, gr, gb = ops.permuto_indices(x.to(DEV), cap, sf, sh)
+    assert np.array_equal(gi.cpu().numpy().view(np.uint32), idx), "lattice vertex hash indices bit-exact"
+    assert np.array_equal(gr.cpu().numpy(), rank), "simplex ranks bit-exact"
+    ref = enc(x)
+    out = ops.permuto_encode(x.to(DEV), enc.lattice_values.detach().to(DEV), sf, sh, enc.anneal_window.to(DEV))
+    assert_close(out, ref.detach(), msg="permuto features")
+
+
+@pytest.mark.parametrize("n_agg", [0, 3, 8])
+def test_permuto_backward(cuda_lib, n_agg):
+    from oracle.permuto import PermutoEncodingOracle
+    from pagnerf_b200 import ops
+    cap, L = 2 ** 10, 8
+    enc = PermutoEncodingOracle(cap, L, 2, np.geomspace(1.0, 1e-2, L), seed=2)
+    with torch.no_grad():
+        enc.lattice_values.mul_(1e4)
+    x = torch.from_numpy(_points(2053, seed=3)).requires_grad_(True)   # not a multiple of 32: ragged last warp
+    g = torch.randn(2053, 2 * L, generator=torch.Generator().manual_seed(0))
+    (enc(x) * g).sum().backward()
+    xt = x.detach().to(DEV).requires_grad_(True)
+    tb = enc.lattice_values.detach().to(DEV).requires_grad_(True)
+    out = ops.permuto_encode(xt, tb, enc.scale_factor.to(DEV), enc.random_shift_per_level.to(DEV), enc.anneal_window.to(DEV), n_agg)
+    (out * g.to(DEV)).sum().backward()
+    assert_close(tb.grad, enc.lattice_values.grad, msg="grad lattice_values")
+    assert_close(xt.grad, x.grad, msg="grad positions")
+
+
+def test_permuto_empty(cuda_lib):
+    from pagnerf_b200.grids import PermutoGrid
+    g = PermutoGrid(2, blas_level=2, num_lods=4, capacity_log_2=8)
+    g.init_from_scales()
+    g = g.to(DEV)
+    assert g.interpolate(torch.zeros(0, 1, 3, device=DEV)).shape == (0, 1, 8)
+
+
+def test_hashnerf_matches_reference_golden(cuda_lib):
+    """CUDA flavour-1 hash grid vs the reference's own grids/hash_grid_torch.py outputs (golden)."""
+    from pagnerf_b200.grids.hash_grid_torch import HashEmbedder
+    from pagnerf_b200 import ops
+    g = load_golden("hash_torch")
+    L, F, T, base, fin = [int(v) for v in g["cfg"]]
+    emb = HashEmbedder(L, F, T, base, fin)
+    assert np.allclose(emb.level_res.numpy(), g["resolutions"])
+    emb.load_state_dict({f"embeddings.{l}.weight": torch.from_numpy(g["weights"][l]) for l in range(L)})
+    assert sorted(emb.state_dict().keys()) == sorted(f"embeddings.{l}.weight" for l in range(L))
+    emb = emb.to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    idx = ops.hash_indices(x, 1, emb.level_res, None, emb.level_offset, emb.level_size).cpu().numpy()
+    perm = [((k & 1) << 2) | (((k >> 1) & 1) << 1) | ((k >> 2) & 1) for k in range(8)]  # ours (bit d = dim d) -> reference (i,j,k x-major)
+    assert np.array_equal(idx.astype(np.int64), g["idx"][:, :, perm]), "hashed vertex indices bit-exact vs reference"
+    out = emb(x)
+    assert_close(out, g["out"], msg="features")
+    (out * torch.from_numpy(g["gout"]).to(DEV)).sum().backward()
+    assert_close(emb.embeddings_weight.grad, g["grad_weights"], msg="grad table")
+    assert_close(x.grad, g["grad_x"], rtol=1e-3, msg="grad x")
+
+
+@pytest.mark.parametrize("L,log2T,base", [(6, 10, 16), (5, 14, 4), (14, 19, 16)])
+def test_tcnn_hash_indices_forward_backward(cuda_lib, L, log2T, base):
+    from oracle.hashgrid import TcnnHashGridOracle
+    from pagnerf_b200.grids.hash_grid_tinycudann import TcnnEncoding
+    from pagnerf_b200 import ops
+    ref = TcnnHashGridOracle(L, 2, log2T, base, 2.0, seed=4)
+    with torch.no_grad():
+        ref.params.mul_(1e3)
+    enc = TcnnEncoding(3, {"otype": "HashGrid", "n_levels": L, "n_features_per_level": 2, "log2_hashmap_size": log2T,
+                           "base_resolution": base, "per_level_scale": 2})
+    assert enc.params.shape == ref.params.shape
+    assert np.array_equal(enc.level_size.numpy(), ref.sizes.astype(np.int64))
+    enc.load_state_dict({"params": ref.params.detach()})
+    enc.round_half = False
+    enc = enc.to(DEV)
+    x = torch.from_numpy(_points(1500, seed=L)).requires_grad_(True)
+    idx_ref = np.stack(ref.indices(x))
+    xt = x.detach().to(DEV).requires_grad_(True)
+    idx = ops.hash_indices(xt, 0, enc.level_scale, enc.level_res, enc.level_offset, enc.level_size).cpu().numpy()
+    assert np.array_equal(idx.view(np.uint32), idx_ref), "tcnn grid indices bit-exact (incl. dense levels, negative cells)"
+    g = torch.randn(1500, 2 * L, generator=torch.Generator().manual_seed(1))
+    (ref(x) * g).sum().backward()
+    out = enc(xt)
+    assert_close(out, ref(x).detach(), msg="features")
+    (out * g.to(DEV)).sum().backward()
+    assert_close(enc.params.grad, ref.params.grad, msg="grad params")
+    assert_close(xt.grad, x.grad, rtol=1e-3, msg="grad x")
+    enc.round_half = True
+    ref.out_half = True
+    assert_close(enc(xt), ref(x).detach(), rtol=2e-3, atol_scale=2e-3, msg="fp16-rounded features (tol 2e-3)")
+
+
+# ------------------------------------------------------------------------------------------------
+# decoders (through the nef plugin) and compositing (through the tracer plugin)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["trace_delta_permuto_ray", "trace_nef_tcnn_ray"])
+def test_nef_forward_backward_vs_oracle(cuda_lib, name):
+    g = load_golden(name)
+    field = build_oracle_field(g)
+    nef = build_cuda_nef(g, DEV)
+    if "tcnn" in name:
+        nef.grid.embedder.round_half = True
+    gen = torch.Generator().manual_seed(0)
+    M, S = 301, 2
+    coords = (torch.rand(M, S, 3, generator=gen) * 2 - 1).requires_grad_(True)
+    ray_d = torch.nn.functional.normalize(torch.randn(M, 3, generator=gen), dim=-1).requires_grad_(True)
+    chans = {'density', 'rgb', 'semantics', 'inst_embedding'}
+    ref = field(coords, ray_d, chans)
+    ct, dt = coords.detach().to(DEV).requires_grad_(True), ray_d.detach().to(DEV).requires_grad_(True)
+    out = nef(coords=ct, ray_d=dt, channels=chans)
+    tol = dict(rtol=2e-3, atol_scale=2e-3) if "tcnn" in name else {}
+    gws = {}
+    for c in sorted(chans):
+        assert out[c].shape == ref[c].shape, c
+        assert_close(out[c], ref[c].detach(), msg=c, **tol)
+        gws[c] = torch.randn(ref[c].shape, generator=gen)
+    sum((ref[c] * gws[c]).sum() for c in chans).backward()
+    sum((out[c] * gws[c].to(DEV)).sum() for c in chans).backward()
+    if "tcnn" in name:
+        return  # fp16-rounded features: gradients are checked in the permuto case and in the tcnn encoder test
+    named = dict(nef.named_parameters())
+    remap = {"grid.lattice_values": "grid.embedder.lattice_values", "delta_grid.lattice_values": "delta_grid.embedder.lattice_values"}
+    for k, p in field.named_parameters():
+        assert_close(named[remap.get(k, k)].grad, p.grad, rtol=1e-3, msg="grad " + k)
+    assert_close(ct.grad, coords.grad, rtol=1e-3, msg="grad coords")
+    assert_close(dt.grad, ray_d.grad, rtol=1e-3, msg="grad ray_d")
+
+
+def test_nef_channel_dispatch(cuda_lib):
+    g = load_golden("trace_delta_permuto_ray")
+    nef = build_cuda_nef(g, DEV)
+    coords = torch.rand(10, 1, 3, device=DEV) * 2 - 1
+    rd = torch.nn.functional.normalize(torch.randn(10, 3, device=DEV), dim=-1)
+    d = nef(coords=coords, ray_d=rd, channels="density")
+    assert torch.is_tensor(d) and d.shape == (10, 1, 1)
+    lst = nef(coords=coords, ray_d=rd, channels=["rgb", "density"])
+    assert isinstance(lst, list) and lst[0].shape == (10, 1, 3)
+    dct = nef(coords=coords, ray_d=rd, channels={"semantics"})
+    assert set(dct) == {"semantics"} and dct["semantics"].shape == (10, 6)
+    assert torch.allclose(dct["semantics"].sum(-1), torch.ones(10, device=DEV), atol=1e-5)
+
+
+@pytest.mark.parametrize("name,mode", [("trace_delta_permuto_ray", "ray"), ("trace_delta_permuto_voxel", "voxel"),
+                                       ("trace_nef_tcnn_ray", "ray")])
+def test_trace_matches_reference_golden(cuda_lib, name, mode):
+    """Full CUDA path (march -> encode -> decode -> composite, fwd + bwd) through the tracer plugin vs the outputs
+    of the REFERENCE's tracer/nef source (golden).  Marcher integers are compared against the oracle marcher."""
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden(name)
+    nef = build_cuda_nef(g, DEV)
+    tracer = PanopticPackedRFTracer(raymarch_type=mode, num_steps=int(g["num_steps"]),
+                                    bg_color='white' if bool(g["bg_white"]) else 'black',
+                                    ray_max_travel=float(g["ray_max_travel"]))
+    o = torch.from_numpy(g["o"]).to(DEV).requires_grad_(True)
+    d = torch.from_numpy(g["d"]).to(DEV).requires_grad_(True)
+    rays = Rays(origins=o, dirs=d, dist_min=0.0, dist_max=2.0)
+    # marcher integers vs oracle
+    r_ref = oracle_march(g, mode)
+    got = nef.grid.raymarch(rays, level=0, num_samples=int(g["num_steps"]), raymarch_type=mode)
+    if mode == 'ray':
+        assert torch.equal(got[0].cpu(), r_ref[0]) and torch.equal(got[1].cpu(), r_ref[1])
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    rb = tracer(nef, channels=chans, rays=rays, lod_idx=None, stage='train')
+    tol = dict(rtol=2e-3, atol_scale=2e-3) if "tcnn" in name else {}
+    for c in chans + ['alpha']:
+        assert_close(getattr(rb, c), g["out_" + c], msg=c, **tol)
+    assert np.array_equal(rb.hit.cpu().numpy(), g["out_hit"])
+    loss = sum((getattr(rb, c) * torch.from_numpy(g["gw_" + c]).to(DEV)).sum() for c in chans)
+    loss.backward()
+    gtol = dict(rtol=5e-3, atol_scale=5e-3) if "tcnn" in name else dict(rtol=1e-3, atol_scale=2e-4)
+    gg = golden_grads(g)
+    for k, p in nef.named_parameters():
+        if k in gg:
+            assert_close(p.grad if p.grad is not None else torch.zeros_like(p), gg[k], msg="grad " + k, **gtol)
+    assert_close(o.grad, g["grad_o"], msg="grad origins", **gtol)
+    assert_close(d.grad, g["grad_d"], msg="grad dirs", **gtol)
+
+
+def test_composite_empty_rays_and_properties(cuda_lib):
+    from pagnerf_b200 import ops
+    N = 9
+    ridx = torch.tensor([1, 1, 1, 4, 7, 7], device=DEV)
+    off = ops.ray_offsets(ridx, N)
+    assert off.tolist() == [0, 0, 3, 3, 3, 4, 4, 4, 6, 6]
+    sigma = torch.tensor([0.5, 2.0, 30.0, 1.0, 0.0, 0.0], device=DEV)
+    deltas = torch.full((6,), 0.1, device=DEV)
+    rgb = torch.rand(6, 3, device=DEV)
+    alpha, hit, rgb_o, dep, sem, inst = ops.composite(sigma, deltas, None, rgb, None, None, off, True)
+    a = alpha[:, 0].cpu()
+    assert torch.all(a >= 0) and torch.all(a <= 1 + 1e-6)
+    empty = [0, 2, 3, 5, 6, 8]
+    assert torch.all(a[empty] == 0) and not hit[empty].any() and torch.all(rgb_o[empty] == 1.0)
+    assert hit[1] and hit[4] and not hit[7]        # zero density ray: alpha == 0 -> no hit, white
+    assert torch.allclose(rgb_o[7], torch.ones(3, device=DEV))
+
+
+def test_kaolin_compat_ops(cuda_lib):
+    from oracle import spc as ospc
+    from pagnerf_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    ridx = torch.sort(torch.randint(0, 40, (500,), generator=gen))[0]
+    b_ref = ospc.mark_pack_boundaries(ridx)
+    b = ops.mark_pack_boundaries(ridx.to(DEV))
+    assert torch.equal(b.cpu(), b_ref)
+    tau = torch.rand(500, 1, generator=gen).requires_grad_(True)
+    x = torch.randn(500, 5, generator=gen).requires_grad_(True)
+    _, w_ref = ospc.exponential_integration(None, tau, b_ref)
+    s_ref = ospc.sum_reduce(x * w_ref, b_ref)
+    gs = torch.randn(s_ref.shape, generator=gen)
+    (s_ref * gs).sum().backward()
+    tt, xt = tau.detach().to(DEV).requires_grad_(True), x.detach().to(DEV).requires_grad_(True)
+    _, w = ops.exponential_integration(None, tt, b)
+    s = ops.sum_reduce(xt * w, b)
+    assert_close(w, w_ref.detach(), msg="weights")
+    assert_close(s, s_ref.detach(), msg="sum_reduce")
+    (s * gs.to(DEV)).sum().backward()
+    assert_close(tt.grad, tau.grad, rtol=1e-3, msg="grad tau")
+    assert_close(xt.grad, x.grad, msg="grad x")
+
+
+def test_full_size_properties(cuda_lib):
+    """BASELINE-size run (16 384 rays x 128 steps, L=24, T=2^18 x2 grids): size-independent properties."""
+    import bench
+    step = bench.build_workload(torch.device(DEV), n_rays=16384, seed=0)
+    out = step.forward_backward()
+    rb = out["rb"]
+    a = rb.alpha[:, 0]
+    assert torch.isfinite(a).all() and (a >= 0).all() and (a <= 1 + 1e-5).all()
+    assert torch.isfinite(rb.rgb).all() and (rb.rgb >= -1e-5).all() and (rb.rgb <= 1 + 1e-5).all()
+    s = rb.semantics.sum(-1)
+    assert torch.allclose(s, a * a, atol=1e-4), "sum_c of composited softmax probabilities == alpha_p * sum w == alpha^2"
+    assert torch.allclose(rb.inst_embedding.sum(-1), a * a, atol=1e-4)
+    assert (rb.rgb[~rb.hit] == 1.0).all()
+    for n, p in step.nef.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    # packed indices: sorted rays, boundary count == rays with samples
+    assert (out["ridx"][1:] >= out["ridx"][:-1]).all()

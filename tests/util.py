@@ -1,0 +1,115 @@
+"""Shared builders for the parity tests (oracle side + CUDA side from the same golden parameters)."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+GOLDEN_CFG = dict(L=6, F=2, hidden=64, num_classes=6, num_instances=20, view_multires=4,
+                  coarsest_scale=1.0, finest_scale=0.01, capacity_log_2=10, delta_capacity_log_2=9,
+                  codebook_bitwidth=10, base_resolution=16)
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def golden_params(g):
+    return {k[len("param:"):]: torch.from_numpy(v.copy()) for k, v in g.items() if k.startswith("param:")}
+
+
+def golden_grads(g):
+    return {k[len("grad:"):]: torch.from_numpy(v.copy()) for k, v in g.items() if k.startswith("grad:")}
+
+
+def _load_decoder(dec, params, name):
+    sd = {k[len(name) + 1:]: v for k, v in params.items() if k.startswith(name + ".")}
+    dec.load_state_dict(sd)
+
+
+def build_oracle_field(g):
+    """FieldOracle carrying the golden's parameters (permuto+delta or tcnn, decided by the keys present)."""
+    from oracle.field import FieldOracle
+    from oracle.permuto import PermutoEncodingOracle
+    from oracle.hashgrid import TcnnHashGridOracle
+    c = GOLDEN_CFG
+    p = golden_params(g)
+
+    def permuto(prefix):
+        cap = p[prefix + ".embedder.lattice_values"].shape[1]
+        enc = PermutoEncodingOracle(cap, c["L"], c["F"], np.geomspace(c["coarsest_scale"], c["finest_scale"], c["L"]))
+        enc.load_state_dict({k[len(prefix) + 10:]: v for k, v in p.items() if k.startswith(prefix + ".embedder.")})
+        return enc
+
+    if "grid.embedder.lattice_values" in p:
+        grid, delta = permuto("grid"), (permuto("delta_grid") if "delta_grid.embedder.lattice_values" in p else None)
+    else:
+        grid = TcnnHashGridOracle(c["L"], c["F"], c["codebook_bitwidth"], c["base_resolution"], 2.0, out_half=True)
+        grid.load_state_dict({"params": p["grid.embedder.params"]})
+        delta = None
+    f = FieldOracle(grid, delta, feat_dim=c["L"] * c["F"], hidden_dim=c["hidden"], num_classes=c["num_classes"],
+                    num_instances=c["num_instances"], view_multires=c["view_multires"])
+    for name in ("decoder_density", "decoder_color", "decoder_semantics", "decoder_inst"):
+        _load_decoder(getattr(f, name), p, name)
+    return f
+
+
+def oracle_march(g, raymarch_type):
+    """Run the oracle marcher (+ max-travel filter) on the golden's rays; returns torch tensors."""
+    from oracle import spc as ospc, raymarch as orm
+    level, S = int(g["level"]), int(g["num_steps"])
+    pts, pyr, pre = ospc.scan_octree(g["octree"], level)
+    if raymarch_type == 'ray':
+        ridx, pidx, s, dp, dl, b = orm.raymarch_ray(g["octree"], pre, g["o"], g["d"], level, S, 0.0, 2.0, seed=int(g["jitter_seed"]))
+    else:
+        ridx, pidx, s, dp, dl, b = orm.raymarch_voxel(g["octree"], pts, pyr, pre, g["o"], g["d"], level, S, seed=int(g["jitter_seed"]))
+        keep = orm.max_travel_filter(ridx, dp, float(g["ray_max_travel"]))
+        dl = dl.reshape(dp.shape)[keep].reshape(-1, 1)
+        b = b.reshape(dp.shape[:2])[keep].reshape(-1)
+        ridx, pidx, s, dp = ridx[keep], pidx[keep], s[keep], dp[keep]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    return t(ridx).long(), t(pidx).long(), t(s), t(dp), t(dl), t(b)
+
+
+def build_cuda_nef(g, device):
+    """Our plugin classes, loaded from the golden's state_dict (same keys as the reference's nef)."""
+    from pagnerf_b200.pc_nerf import PanopticDeltaNeF, PanopticNeF
+    c = GOLDEN_CFG
+    p = golden_params(g)
+    permuto = "grid.embedder.lattice_values" in p
+    delta = "delta_grid.embedder.lattice_values" in p
+    kw = dict(grid_type="PermutoGrid" if permuto else "HashGridTinyCudaNN", interpolation_type='linear',
+              multiscale_type='cat', feature_dim=c["F"], num_lods=c["L"], base_lod=2, hidden_dim=c["hidden"],
+              num_layers=1, view_multires=c["view_multires"], pos_multires=4, embedder_type='positional',
+              activation_type='relu', layer_type='none', num_classes=c["num_classes"], num_instances=c["num_instances"],
+              sem_num_layers=1, sem_hidden_dim=64, inst_num_layers=2, inst_hidden_dim=64, sem_softmax=True,
+              inst_softmax=True, sem_detach=True, inst_detach=True,
+              panoptic_features_type='delta' if delta else None, blas_level=int(g["level"]),
+              coarsest_scale=c["coarsest_scale"], finest_scale=c["finest_scale"], capacity_log_2=c["capacity_log_2"],
+              delta_capacity_log_2=c["delta_capacity_log_2"], codebook_bitwidth=c["codebook_bitwidth"])
+    nef = (PanopticDeltaNeF if delta else PanopticNeF)(**kw)
+    grids = [nef.grid] + ([nef.delta_grid] if delta else [])
+    for gr in grids:
+        if permuto:
+            gr.init_from_scales()
+        else:
+            gr.init_from_resolutions([c["base_resolution"] * 2 ** i for i in range(c["L"])])
+        gr.blas_init(torch.from_numpy(g["octree"].copy()))
+        gr.blas.fixed_jitter = True
+        gr.blas.jitter_seed = int(g["jitter_seed"])
+    missing, unexpected = nef.load_state_dict(p, strict=False)
+    assert not missing, missing
+    return nef.to(device)
+
+
+def assert_close(a, b, rtol=1e-4, atol_scale=1e-4, msg=""):
+    """|a-b| <= rtol*|b| + atol_scale*max|b|  (north_star: 1e-4 relative in fp32)."""
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    assert a.shape == b.shape, f"{msg}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    tol = rtol * b.abs() + atol_scale * (b.abs().max() if b.numel() else 0.0)
+    bad = (a - b).abs() > tol
+    assert not bad.any(), (f"{msg}: {int(bad.sum())}/{bad.numel()} mismatches, max abs err "
+                           f"{float((a - b).abs().max()):.3e}, ref max {float(b.abs().max()):.3e}")
