@@ -1,0 +1,169 @@
+"""CPU: host-side logic, the C-ABI library's symbol table, state_dict compatibility, multi-process plumbing."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    """The built .so loads and exports every prototype of include/pagnerf_b200.h (no compute call without a GPU)."""
+    from pagnerf_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 26
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = set(re.findall(r"\bT (pag_\w+)", out))
+    assert set(protos) == exported, (set(protos) ^ exported)
+    for name in protos:
+        assert getattr(cuda_lib, name).argtypes is not None
+
+
+def test_ops_refuse_cpu_tensors(cuda_lib):
+    """No CPU fallback: the product path raises on CPU tensors instead of routing anywhere else."""
+    from pagnerf_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.permuto_encode(torch.zeros(4, 3), torch.zeros(2, 8, 2), torch.ones(2, 3), torch.zeros(2, 3), torch.ones(2))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.octree_query(torch.zeros(1, dtype=torch.uint8), torch.zeros(2, dtype=torch.int32), torch.zeros(3, 3), 1)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pagnerf_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+@pytest.mark.parametrize("level", [1, 3, 5])
+def test_spc_build_matches_oracle(level):
+    from oracle import spc as ospc
+    from pagnerf_b200 import spc
+    rng = np.random.default_rng(level)
+    pts = rng.integers(0, 1 << level, size=(max(4, 8 ** level // 5), 3)).astype(np.int16)
+    oc_ref = ospc.points_to_octree(pts, level)
+    oc = spc.unbatched_points_to_octree(torch.from_numpy(pts), level)
+    assert np.array_equal(oc.numpy(), oc_ref)
+    p, py, pre = spc.scan_octree(oc, level)
+    p_ref, py_ref, pre_ref = ospc.scan_octree(oc_ref, level)
+    assert np.array_equal(p.numpy(), p_ref) and np.array_equal(py.numpy(), py_ref) and np.array_equal(pre.numpy(), pre_ref)
+    assert spc.octree_max_level(oc) == level
+    lp = spc.unbatched_get_level_points(p, py, level)
+    assert set(map(tuple, lp.tolist())) == set(map(tuple, pts.tolist()))
+
+
+def test_dense_octree_sizes_level7():
+    """OctreeAS.init_dense(7): 299 593 bytes, 2 396 745 points, 2 097 152 leaves."""
+    from pagnerf_b200 import spc
+    blas = spc.OctreeAS('cpu')
+    blas.init_dense(7)
+    assert blas.octree.shape[0] == 299593 and blas.points.shape[0] == 2396745
+    assert int(blas.pyramid[0, 7]) == 2097152 and tuple(blas.pyramid.shape) == (2, 9)
+
+
+def test_plugin_surface_and_state_dict_keys():
+    """Constructor kwargs, attributes and state_dict keys the reference's trainer / checkpoints rely on."""
+    import bench
+    from pagnerf_b200.pc_nerf import PanopticDeltaNeF
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    kw = dict(bench.NEF_KW, blas_level=3, capacity_log_2=8, delta_capacity_log_2=7, some_unrelated_cli_arg=1)
+    nef = PanopticDeltaNeF(**kw)
+    nef.grid.init_from_scales(); nef.delta_grid.init_from_scales()
+    assert nef.grid.capacity == 256 and nef.delta_grid.capacity == 128
+    keys = set(nef.state_dict().keys())
+    for g in ("grid", "delta_grid"):
+        for k in ("blas_octree", "blas_points", "blas_prefix", "blas_pyramid", "embedder.lattice_values",
+                  "embedder.random_shift_per_level", "embedder.scale_factor", "embedder.anneal_window"):
+            assert f"{g}.{k}" in keys
+    names = [n for n, _ in nef.named_parameters()]
+    # optimiser grouping by substring (pc_nerf/trainer.py:240-258): decoder -> inst -> sem -> delta_grid -> grid
+    assert sum('decoder' in n for n in names) == 20
+    assert [n for n in names if 'decoder' not in n] == ['grid.embedder.lattice_values', 'delta_grid.embedder.lattice_values']
+    assert float(nef.decoder_density.lout.bias[0]) == 1.0
+    assert nef.get_supported_channels() == {"density", "rgb", "semantics", "inst_embedding"}
+    assert nef.grid.num_lods == 24 and nef.grid.active_lods[-1] == 23 and nef.grid.multiscale_type == 'cat'
+    assert nef.lod_weights.shape == (48,)
+    tr = PanopticPackedRFTracer(raymarch_type='ray', num_steps=512, ray_max_travel=2.0, ray_sparcity_reg=0.0, extra=1)
+    assert tr.raymarch_type == 'ray' and tr.num_steps == 512 and tr.get_required_nef_channels() == {'rgb', 'density'}
+    tr.raymarch_type, tr.num_steps = 'voxel', 2   # pc_nerf/trainer.py:364-366 mutates these
+    # pruned accel-struct round-trips through state_dict even though its size changed
+    from pagnerf_b200 import spc
+    oc = spc.unbatched_points_to_octree(torch.tensor([[0, 0, 0], [7, 7, 7], [3, 4, 5]], dtype=torch.int16), 3)
+    nef.grid.blas_init(oc); nef.delta_grid.blas_init(oc)
+    nef2 = PanopticDeltaNeF(**kw)
+    nef2.grid.init_from_scales(); nef2.delta_grid.init_from_scales()
+    nef2.load_state_dict(nef.state_dict())
+    assert torch.equal(nef2.grid.blas.octree.cpu(), oc) and nef2.grid.blas.max_level == 3
+
+
+def test_unsupported_configs_fail_loudly():
+    import bench
+    from pagnerf_b200.pc_nerf import PanopticNeF
+    from pagnerf_b200.pc_nerf.panoptic_nef import _decoder_tensors
+    nef = PanopticNeF(**dict(bench.NEF_KW, blas_level=2, capacity_log_2=6, hidden_dim=128, panoptic_features_type=None,
+                             sem_hidden_dim=128, inst_hidden_dim=128))
+    with pytest.raises(NotImplementedError):
+        _decoder_tensors(nef.decoder_density, 1)
+    with pytest.raises(NotImplementedError):
+        PanopticNeF(**dict(bench.NEF_KW, grid_type="OctreeGrid"))
+
+
+def test_wisp_compat_dispatch_and_renderbuffer():
+    from pagnerf_b200.wisp_compat import RenderBuffer, Rays
+    a = RenderBuffer(rgb=torch.zeros(3, 3), alpha=torch.zeros(3, 1), depth=None, semantics=torch.zeros(3, 6))
+    b = RenderBuffer(rgb=torch.ones(2, 3), alpha=torch.ones(2, 1), semantics=torch.ones(2, 6))
+    c = a + b
+    assert c.rgb.shape == (5, 3) and c.semantics.shape == (5, 6) and c.depth is None
+    assert c.reshape(5, -1).rgb.shape == (5, 3)
+    r = Rays(origins=torch.zeros(10, 3), dirs=torch.ones(10, 3), dist_min=0.0, dist_max=2.0)
+    assert len(r) == 10 and [len(x) for x in r.split(4)] == [4, 4, 2] and r.reshape(2, 5, 3).origins.shape == (2, 5, 3)
+
+
+def test_header_cites_reference_for_each_section():
+    src = open(os.path.join(ROOT, "include", "pagnerf_b200.h")).read()
+    for cite in ("grids/occtree.py:85-91", "grids/permuto_grid.py:57-62,71", "grids/hash_grid_tinycudann.py:24-34,41",
+                 "grids/hash_grid_torch.py:13-108", "pc_nerf/panoptic_nef.py:114-164", "tracers/panoptic_packed_rf_tracer.py:134-205"):
+        assert cite in src, cite
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pagnerf_b200 import parallel
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+torch.manual_seed(0)
+big = torch.nn.Parameter(torch.zeros(1 << 20, 2)); small = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7))]
+params = [big] + small + [torch.nn.Parameter(torch.zeros(2))]      # last one has no grad
+g = torch.Generator().manual_seed(100 + rank)
+big.grad = torch.rand(big.shape, generator=g); small[0].grad = torch.rand(5, 3, generator=g); small[1].grad = torch.rand(7, generator=g)
+local = [p.grad.clone() for p in params[:3]]
+n = parallel.allreduce_grads(params, average=False)
+assert n == 2, n
+other = []
+g2 = torch.Generator().manual_seed(100 + (1 - rank))
+other = [torch.rand(big.shape, generator=g2), torch.rand(5, 3, generator=g2), torch.rand(7, generator=g2)]
+for p, a, b in zip(params[:3], local, other):
+    assert torch.allclose(p.grad, a + b), "allreduce mismatch"
+assert parallel.shard_images(7, rank, 2) == list(range(rank, 7, 2))
+dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_grad_allreduce_world_size_2_gloo(tmp_path):
+    """Ray-sharded DP exchange step (grid tables + flattened decoder bucket) on 2 CPU processes over gloo."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK {r}" in o, o
