@@ -106,6 +106,24 @@ int pag_decode_pan_bwd(const float* feats, const float* dfeats, const float* lod
                        int inst_softmax, float inst_temperature, const float* sem, const float* inst,
                        const float* g_sem, const float* g_inst, float* g_panop, void* stream);
 
+/* tensor-core (tcgen05, fp16 operands / fp32 accumulate) variants of the four decoder entry points: the numerics of
+ * the reference's autocast training step (pc_nerf/trainer.py:429).  grad_scale: device pointer to one power-of-two
+ * float applied to the upstream gradients before the fp16 repack and divided out of every result (NULL = 1). */
+int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray_d, int S, int64_t M, int IN,
+                         const float* const* weights, int hidden, int view_dim, int want_rgb, float* sigma, float* rgb,
+                         void* stream);
+int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray_d, int S, int64_t M, int IN,
+                         const float* const* weights, float* const* grads, int hidden, int view_dim,
+                         const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats, float* g_dir,
+                         void* stream);
+int pag_decode_pan_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                          const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
+                          float inst_temperature, float* sem, float* inst, void* stream);
+int pag_decode_pan_bwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                          const float* const* weights, float* const* grads, int hidden, int Cs, int Ci, int sem_softmax,
+                          int inst_softmax, float inst_temperature, const float* sem, const float* inst,
+                          const float* g_sem, const float* g_inst, const float* grad_scale, float* g_panop, void* stream);
+
 /* ---- packed compositing: tracers/panoptic_packed_rf_tracer.py:134-205 ------------------------------- */
 /* offsets[r] = first packed index with ridx >= r (ridx ascending), offsets[R] = M. */
 int pag_ray_offsets(const int64_t* ridx, int64_t M, int64_t R, int64_t* offsets, void* stream);
@@ -125,6 +143,10 @@ int pag_sum_reduce_bwd(const float* g, int64_t C, const int64_t* offsets, int64_
 int pag_expint_fwd(const float* tau, const int64_t* offsets, int64_t R, float* w, float* T, void* stream);
 int pag_expint_bwd(const float* gw, const float* w, const float* T, const int64_t* offsets, int64_t R, float* gtau,
                    void* stream);
+
+/* ---- tcgen05 building-block probe (tests only): one 128-row tile through the tensor-core operand images ---- */
+int pag_tc_gemm_test(int mode, const float* A, const float* B, float* D, int N, int K, int FA, int reps, void* stream);
+int pag_tc_gemm_test16(int mode, const float* A, const float* B, float* D, int N, int K, int FA, int reps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,25 +13,7 @@
 // activations (cheaper than 1.5 KB/sample of saved state), forms dX with the same row-major
 // weights (no transpose), and accumulates dW with a cooperative register-tiled (4x4) product
 // over the CTA's 128-sample tile straight out of the staging columns.
-#include "common.cuh"
-
-#define H 64        // hidden width (configs/bup20/best.yaml:70)
-#define DOUT 16     // density decoder output width (pc_nerf/panoptic_nef.py:115)
-#define PE_F 4      // view_multires (best.yaml:39) -> 3 + 3*2*4 = 27
-#define PE_DIM 27
-#define CIN 43      // 16 + 27
-#define CINP 44     // padded to a multiple of 4
-
-struct DcParams {   // density + color decoders; torch Linear layout W[out][in] row-major
-    const float *Wd1, *bd1, *Wd2, *bd2, *Wc1, *bc1, *Wc2, *bc2, *Wc3, *bc3;
-    float *gWd1, *gbd1, *gWd2, *gbd2, *gWc1, *gbc1, *gWc2, *gbc2, *gWc3, *gbc3;
-};
-struct PanParams {  // semantic + instance decoders
-    const float *Ws1, *bs1, *Ws2, *bs2, *Wi1, *bi1, *Wi2, *bi2, *Wi3, *bi3;
-    float *gWs1, *gbs1, *gWs2, *gbs2, *gWi1, *gbi1, *gWi2, *gbi2, *gWi3, *gbi3;
-};
-
-__host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
+#include "decoder_common.cuh"
 
 // cooperative copy of W[rows][cols] (global) into smem [pad4(rows)][colsp], zero padded
 __device__ __forceinline__ void stage_weights(float* dst, const float* __restrict__ W, int rows, int cols, int colsp) {
@@ -140,21 +122,6 @@ __device__ void accum_dw(const float* __restrict__ Gs, int RJ, const float* __re
             red_add_f32(db + j, s);
         }
     }
-}
-
-// view-direction positional embedding of v = -d : [v, sin(2^f v), cos(2^f v)], f-major / xyz-minor
-__device__ __forceinline__ void view_embed(float dx, float dy, float dz, float* pe /*27*/) {
-    const float v[3] = {-dx, -dy, -dz};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) pe[c] = v[c];
-#pragma unroll
-    for (int f = 0; f < PE_F; ++f)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float a = v[c] * (float)(1 << f);
-            pe[3 + 3 * f + c] = sinf(a);
-            pe[3 + 3 * PE_F + 3 * f + c] = cosf(a);
-        }
 }
 
 // ---------------------------------------------------------------------------------------------

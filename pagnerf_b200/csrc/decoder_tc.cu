@@ -1,0 +1,923 @@
+// Tensor-core (tcgen05 + TMEM) decoders: the training-mode path of the panoptic field's MLPs.
+//
+// Same math as decoder.cu, but every dense layer is a tcgen05.mma (kind::f16: fp16 operands, fp32
+// accumulation in TMEM) -- the numerics of the reference's own training step, which runs these
+// layers as fp16 GEMMs under torch.cuda.amp.autocast with a GradScaler (pc_nerf/trainer.py:429,582).
+// ncu on the FP32-FMA kernels showed them issue/occupancy bound (profiles/r01_*): 85 GFLOP per
+// 410 k-sample step cost 8.6 ms on the FMA pipe, i.e. the contraction, not memory, bounds the step.
+//
+// Mapping: one CTA = 128 threads = one 128-sample tile; thread t owns sample row t == TMEM lane t.
+//   * activations / gradients live in shared memory as fp16 "tile images" [F/8][128 rows][8 halfs]
+//     (UMMA SWIZZLE_NONE canonical layout; a thread writes its row with conflict-free 16-byte stores);
+//   * weights are staged once per persistent CTA as fp16 images [IN/8][OUT rows][8 halfs];
+//   * ONE image serves every operand role:  Y = X W^T (tile K-major x weight K-major),
+//     dX = G W (tile K-major x the same weight image read MN-major), dW += G^T X (tile MN-major x
+//     tile MN-major, K = the tile's 128 samples);
+//   * the layer epilogue (bias, ReLU / sigmoid / softmax, fp16 repack) is thread-per-row on the
+//     accumulator row read back with tcgen05.ld;
+//   * weight gradients never leave TMEM until the CTA has swept all its tiles (accumulate flag),
+//     bias gradients are warp reduce-scattered in registers; both are flushed once per CTA.
+// Upstream gradients are multiplied by a power-of-two `grad_scale` before the fp16 repack and every
+// result is unscaled in fp32 (the GradScaler trick, applied inside the kernel).
+#include "decoder_common.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+
+#define TCH TC_CHUNK_BYTES
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// features [8c, 8c+8) of row `row` into chunk c of a tile image
+__device__ __forceinline__ void tile_store8(uint8_t* tile, int c, int row, const float* v) {
+    uint4 u;
+    u.x = pack_h2(v[0], v[1]); u.y = pack_h2(v[2], v[3]); u.z = pack_h2(v[4], v[5]); u.w = pack_h2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + c * TCH + row * 16) = u;
+}
+// fp16 image of W[OUT][IN] (global fp32, torch Linear layout): [(in/8)][OUTP][8], zero padded
+__device__ __forceinline__ void stage_w16(__half* img, const float* __restrict__ W, int OUT, int IN, int OUTP, int INP) {
+    const int n = (INP / 8) * OUTP * 8;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int e = i & 7, r = (i >> 3) % OUTP, c = (i >> 3) / OUTP, in = c * 8 + e;
+        img[i] = (r < OUT && in < IN) ? __float2half_rn(__ldg(W + (size_t)r * IN + in)) : __float2half_rn(0.f);
+    }
+}
+__device__ __forceinline__ void stage_b32(float* dst, const float* __restrict__ b, int n, int np) {
+    for (int i = threadIdx.x; i < np; i += blockDim.x) dst[i] = (i < n) ? __ldg(b + i) : 0.f;
+}
+// generic-proxy smem writes + TMEM reads of all threads ordered before the MMAs the elected thread issues next
+__device__ __forceinline__ void sync_to_mma() {
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+}
+struct MmaBar {
+    uint64_t* bar;
+    uint32_t parity;
+    __device__ __forceinline__ void commit() { umma_commit(bar); }
+    __device__ __forceinline__ void wait() { mbar_wait(bar, parity); parity ^= 1; tc_fence_after(); }
+};
+
+// accumulator row (64 columns) -> +bias -> ReLU -> fp16 tile; returns the activity mask
+__device__ __forceinline__ uint64_t epi_relu64(uint32_t taddr, const float* __restrict__ bias, uint8_t* tile, int row) {
+    uint64_t mask = 0;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            v[i] = fmaxf(v[i] + bias[c0 + i], 0.f);
+            mask |= (v[i] > 0.f) ? (1ull << (c0 + i)) : 0ull;
+        }
+        tile_store8(tile, c0 / 8, row, v);
+        tile_store8(tile, c0 / 8 + 1, row, v + 8);
+    }
+    return mask;
+}
+
+// warp reduce-scatter of N per-lane values (N = 64): afterwards v[0], v[1] hold the warp sums of
+// features f0 + {0,1}, f0 = 32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0 of the lane id bits
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane) {
+#pragma unroll
+    for (int o = 16, n = N / 2; o >= 1; o >>= 1, n >>= 1) {
+        const bool hi = lane & o;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = hi ? v[i] : v[i + n];
+            const float keep = hi ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+}
+__device__ __forceinline__ int scatter_base(int lane, int n) {  // first feature owned by `lane` after the scatter of n values
+    int f = 0, h = n / 2;
+    for (int o = 16; o >= 1; o >>= 1, h >>= 1) f += (lane & o) ? h : 0;
+    return f;
+}
+// masked hidden gradient: accumulator row (64 cols) * relu mask -> fp16 tile, bias-grad partial sums
+__device__ __forceinline__ void epi_grad64(uint32_t taddr, uint64_t mask, uint8_t* tile, int row, int lane, float (&dbacc)[2]) {
+    float g[64];
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) g[c0 + i] = ((mask >> (c0 + i)) & 1ull) ? v[i] : 0.f;
+        tile_store8(tile, c0 / 8, row, g + c0);
+        tile_store8(tile, c0 / 8 + 1, row, g + c0 + 8);
+    }
+    warp_reduce_scatter<64>(g, lane);
+    dbacc[0] += g[0]; dbacc[1] += g[1];
+}
+// 16-feature gradient row -> tile (2 chunks) + bias partial (lane keeps 1 value when lane is even after 4 scatter steps)
+__device__ __forceinline__ void grad16_store(float (&g)[16], uint8_t* tile, int row, int lane, float& dbacc) {
+    tile_store8(tile, 0, row, g);
+    tile_store8(tile, 1, row, g + 8);
+#pragma unroll
+    for (int o = 16, n = 8; o >= 2; o >>= 1, n >>= 1) {
+        const bool hi = lane & o;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = hi ? g[i] : g[i + n];
+            const float keep = hi ? g[i + n] : g[i];
+            g[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    dbacc += g[0] + __shfl_xor_sync(0xffffffffu, g[0], 1);  // feature 8*b4 + 4*b3 + 2*b2 + b1 (both lanes of a pair hold it)
+}
+// flush a dW accumulator [rows(lane) x cols] from TMEM to global with atomics
+__device__ __forceinline__ void flush_dw(uint32_t taddr, float* __restrict__ gW, int row, int OUT, int IN, int ncols, float inv_scale) {
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (row < OUT) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < IN) red_add_f32(gW + (size_t)row * IN + c0 + i, v[i] * inv_scale);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// density + color
+// ---------------------------------------------------------------------------------------------
+struct DcTcLayout {  // byte offsets inside dynamic smem
+    int INP, nXc;
+    int oG3, oGy, oX, oCin, oHd, oH1, oH2, oWd1, oWd2, oWc1, oWc2, oWc3, oBias, total;
+};
+__host__ __device__ inline DcTcLayout dc_tc_layout(int IN, bool bwd) {
+    DcTcLayout l;
+    l.INP = (IN + 15) & ~15;
+    l.nXc = l.INP / 8;
+    int o = 0;
+    l.oG3 = o; o += bwd ? 2 * TCH : 0;
+    l.oGy = o; o += bwd ? 2 * TCH : 0;
+    l.oX = o; o += 8 * TCH;            // X (<= 64 feats); forward reuses it for Hc2
+    l.oCin = o; o += bwd ? 6 * TCH : 0;
+    l.oHd = o; o += 8 * TCH;
+    l.oH1 = o; o += bwd ? 8 * TCH : 0;
+    l.oH2 = o; o += bwd ? 8 * TCH : 0;
+    l.oWd1 = o; o += l.nXc * 64 * 16;
+    l.oWd2 = o; o += 8 * 16 * 16;
+    l.oWc1 = o; o += 6 * 64 * 16;
+    l.oWc2 = o; o += 8 * 64 * 16;
+    l.oWc3 = o; o += 8 * 16 * 16;
+    l.oBias = o; o += (64 + 16 + 64 + 64 + 16) * 4;
+    if (bwd && o < l.oH2 + 16 * TCH) o = l.oH2 + 16 * TCH;  // MN-major A operands read 16 chunks from their base
+    l.total = o;
+    return l;
+}
+
+__device__ __forceinline__ void dc_tc_stage(uint8_t* sm, const DcTcLayout& l, const DcParams& p, int IN) {
+    stage_w16(reinterpret_cast<__half*>(sm + l.oWd1), p.Wd1, 64, IN, 64, l.INP);
+    stage_w16(reinterpret_cast<__half*>(sm + l.oWd2), p.Wd2, 16, 64, 16, 64);
+    stage_w16(reinterpret_cast<__half*>(sm + l.oWc1), p.Wc1, 64, CIN, 64, 48);
+    stage_w16(reinterpret_cast<__half*>(sm + l.oWc2), p.Wc2, 64, 64, 64, 64);
+    stage_w16(reinterpret_cast<__half*>(sm + l.oWc3), p.Wc3, 3, 64, 16, 64);
+    float* b = reinterpret_cast<float*>(sm + l.oBias);
+    stage_b32(b, p.bd1, 64, 64); stage_b32(b + 64, p.bd2, 16, 16); stage_b32(b + 80, p.bc1, 64, 64);
+    stage_b32(b + 144, p.bc2, 64, 64); stage_b32(b + 208, p.bc3, 3, 16);
+}
+
+// this thread's feature row -> X tile
+__device__ __forceinline__ void stage_x(uint8_t* tile, int row, const float* __restrict__ a, const float* __restrict__ b,
+                                        const float* __restrict__ lodw, int IN, int nchunks, int64_t m) {
+    for (int c = 0; c < nchunks; ++c) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = c * 8 + e;
+            float x = 0.f;
+            if (k < IN) {
+                x = a[m * IN + k];
+                if (b) x += b[m * IN + k];
+                if (lodw) x *= __ldg(lodw + k);
+            }
+            v[e] = x;
+        }
+        tile_store8(tile, c, row, v);
+    }
+}
+// color-decoder input row [y16 | PE(-d) | 0 pad] -> 6 chunks
+__device__ __forceinline__ void stage_cin(uint8_t* tile, int row, const float (&y)[16], const float* pe) {
+    float v[48];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = y[k];
+#pragma unroll
+    for (int k = 0; k < PE_DIM; ++k) v[16 + k] = pe[k];
+#pragma unroll
+    for (int k = CIN; k < 48; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) tile_store8(tile, c, row, v + 8 * c);
+}
+
+__global__ void __launch_bounds__(128) dc_tc_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
+                                                        const float* __restrict__ ray_d, int S, int64_t M, int IN,
+                                                        DcParams p, int want_rgb, float* __restrict__ sigma,
+                                                        float* __restrict__ rgb) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint64_t bar_s;
+    __shared__ uint32_t tmem_s;
+    const DcTcLayout l = dc_tc_layout(IN, false);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    dc_tc_stage(sm, l, p, IN);
+    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_s, 128);
+    sync_to_mma();
+    tc_fence_after();
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    MmaBar mb{&bar_s, 0};
+    const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
+    uint8_t *T0 = sm + l.oX, *T1 = sm + l.oHd;
+    const uint32_t aT0 = smem_u32(T0), aT1 = smem_u32(T1);
+    const uint32_t wd1 = smem_u32(sm + l.oWd1), wd2 = smem_u32(sm + l.oWd2), wc1 = smem_u32(sm + l.oWc1),
+                   wc2 = smem_u32(sm + l.oWc2), wc3 = smem_u32(sm + l.oWc3);
+    const int64_t ntiles = (M + 127) / 128;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t m = tile * 128 + tid;
+        const bool valid = m < M;
+        const int64_t mm = valid ? m : M - 1;
+        stage_x(T0, tid, feats, nullptr, lodw, IN, l.nXc, mm);
+        sync_to_mma();
+        if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT0, wd1, 64, 64, l.INP, false); mb.commit(); }
+        mb.wait();
+        epi_relu64(tl, bias, T1, tid);
+        sync_to_mma();
+        if (tid == 0) { tc_fence_after(); mma16_fwd(tm + 64, aT1, wd2, 16, 16, 64, false); mb.commit(); }
+        mb.wait();
+        float y[16];
+        tmem_ld16(tl + 64, y);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] += bias[64 + i];
+        if (valid) sigma[m] = fmaxf(y[0], 0.f);
+        if (!want_rgb) { tc_fence_before(); __syncthreads(); continue; }
+        {
+            float pe[PE_DIM];
+            const int64_t r = mm / S;
+            view_embed(ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2], pe);
+            stage_cin(T0, tid, y, pe);
+        }
+        sync_to_mma();
+        if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT0, wc1, 64, 64, 48, false); mb.commit(); }
+        mb.wait();
+        epi_relu64(tl, bias + 80, T1, tid);
+        sync_to_mma();
+        if (tid == 0) { tc_fence_after(); mma16_fwd(tm + 64, aT1, wc2, 64, 64, 64, false); mb.commit(); }
+        mb.wait();
+        epi_relu64(tl + 64, bias + 144, T0, tid);
+        sync_to_mma();
+        if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT0, wc3, 16, 16, 64, false); mb.commit(); }
+        mb.wait();
+        float c[16];
+        tmem_ld16(tl, c);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) rgb[3 * m + j] = 1.f / (1.f + expf(-(c[j] + bias[208 + j])));
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 128);
+}
+
+// TMEM columns of the backward kernel
+#define DCB_S0 0
+#define DCB_S1 64
+#define DCB_DWD1 128   // [64 x <=64]
+#define DCB_DWD2 192   // [16 x 64]
+#define DCB_DWC1 256   // [64 x 48]
+#define DCB_DWC2 304   // [64 x 64]
+#define DCB_DWC3 368   // [3  x 64]  -> 432 columns used
+
+__global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
+                                                        const float* __restrict__ ray_d, int S, int64_t M, int IN,
+                                                        DcParams p, const float* __restrict__ g_sigma,
+                                                        const float* __restrict__ g_rgb, const float* __restrict__ scale_ptr,
+                                                        float* __restrict__ g_feats, float* __restrict__ g_dir) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint64_t bar_s;
+    __shared__ uint32_t tmem_s;
+    const DcTcLayout l = dc_tc_layout(IN, true);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    dc_tc_stage(sm, l, p, IN);
+    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_s, 512);
+    sync_to_mma();
+    tc_fence_after();
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    MmaBar mb{&bar_s, 0};
+    const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
+    uint8_t *G3 = sm + l.oG3, *Gy = sm + l.oGy, *X = sm + l.oX, *Cin = sm + l.oCin, *Hd = sm + l.oHd, *H1 = sm + l.oH1, *H2 = sm + l.oH2;
+    const uint32_t aG3 = smem_u32(G3), aGy = smem_u32(Gy), aX = smem_u32(X), aCin = smem_u32(Cin), aHd = smem_u32(Hd),
+                   aH1 = smem_u32(H1), aH2 = smem_u32(H2);
+    const uint32_t wd1 = smem_u32(sm + l.oWd1), wd2 = smem_u32(sm + l.oWd2), wc1 = smem_u32(sm + l.oWc1),
+                   wc2 = smem_u32(sm + l.oWc2), wc3 = smem_u32(sm + l.oWc3);
+    const float scale = scale_ptr ? __ldg(scale_ptr) : 1.f;
+    const float inv_scale = 1.f / scale;
+    const bool do_rgb = g_rgb != nullptr;
+    float db_d1[2] = {0.f, 0.f}, db_c1[2] = {0.f, 0.f}, db_c2[2] = {0.f, 0.f}, db_d2 = 0.f, db_c3 = 0.f;
+    const int64_t ntiles = (M + 127) / 128;
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
+        const int64_t m = tile * 128 + tid;
+        const bool valid = m < M;
+        const int64_t mm = valid ? m : M - 1;
+        // ---------------- forward recompute ----------------
+        stage_x(X, tid, feats, nullptr, lodw, IN, l.nXc, mm);
+        sync_to_mma();
+        if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aX, wd1, 64, 64, l.INP, false); mb.commit(); }
+        mb.wait();
+        const uint64_t mask_d = epi_relu64(tl + DCB_S0, bias, Hd, tid);
+        sync_to_mma();
+        if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S1, aHd, wd2, 16, 16, 64, false); mb.commit(); }
+        mb.wait();
+        float y[16];
+        tmem_ld16(tl + DCB_S1, y);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] += bias[64 + i];
+        const bool y0pos = y[0] > 0.f;
+        float dy[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dy[i] = 0.f;
+        float vdir[3] = {0.f, 0.f, 0.f};
+        if (do_rgb) {
+            {
+                float pe[PE_DIM];
+                const int64_t r = mm / S;
+                vdir[0] = -ray_d[3 * r]; vdir[1] = -ray_d[3 * r + 1]; vdir[2] = -ray_d[3 * r + 2];
+                view_embed(-vdir[0], -vdir[1], -vdir[2], pe);
+                stage_cin(Cin, tid, y, pe);
+            }
+            sync_to_mma();
+            if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aCin, wc1, 64, 64, 48, false); mb.commit(); }
+            mb.wait();
+            const uint64_t mask_1 = epi_relu64(tl + DCB_S0, bias + 80, H1, tid);
+            sync_to_mma();
+            if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S1, aH1, wc2, 64, 64, 64, false); mb.commit(); }
+            mb.wait();
+            const uint64_t mask_2 = epi_relu64(tl + DCB_S1, bias + 144, H2, tid);
+            sync_to_mma();
+            if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aH2, wc3, 16, 16, 64, false); mb.commit(); }
+            mb.wait();
+            {   // d rgb_pre (sigmoid') -> G3 tile (16 features, 3 valid)
+                float c[16], g[16];
+                tmem_ld16(tl + DCB_S0, c);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) g[j] = 0.f;
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float s = 1.f / (1.f + expf(-(c[j] + bias[208 + j])));
+                        g[j] = g_rgb[3 * m + j] * s * (1.f - s) * scale;
+                    }
+                }
+                grad16_store(g, G3, tid, lane, db_c3);
+            }
+            // ---------------- color backward ----------------
+            sync_to_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                mma16_bwd_weight(tm + DCB_DWC3, aG3, aH2, 64, !first);
+                mma16_bwd_data(tm + DCB_S1, aG3, wc3, 64, 16, 16, false);
+                mb.commit();
+            }
+            mb.wait();
+            epi_grad64(tl + DCB_S1, mask_2, H2, tid, lane, db_c2);          // G2 overwrites H2
+            sync_to_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                mma16_bwd_weight(tm + DCB_DWC2, aH2, aH1, 64, !first);
+                mma16_bwd_data(tm + DCB_S0, aH2, wc2, 64, 64, 64, false);
+                mb.commit();
+            }
+            mb.wait();
+            epi_grad64(tl + DCB_S0, mask_1, H1, tid, lane, db_c1);          // G1 overwrites H1
+            sync_to_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                mma16_bwd_weight(tm + DCB_DWC1, aH1, aCin, 48, !first);
+                mma16_bwd_data(tm + DCB_S1, aH1, wc1, 48, 64, 64, false);
+                mb.commit();
+            }
+            mb.wait();
+            {   // d cin: first 16 -> dy, the rest -> view direction
+                float g[48];
+#pragma unroll
+                for (int c0 = 0; c0 < 48; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(tl + DCB_S1 + c0, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) g[c0 + i] = v[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dy[i] = g[i];
+                if (g_dir && valid) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float gv = g[16 + c];
+#pragma unroll
+                        for (int f = 0; f < PE_F; ++f) {
+                            const float b = (float)(1 << f), a = vdir[c] * b;
+                            gv += b * (cosf(a) * g[16 + 3 + 3 * f + c] - sinf(a) * g[16 + 3 + 3 * PE_F + 3 * f + c]);
+                        }
+                        g_dir[3 * m + c] = -gv * inv_scale;
+                    }
+                }
+            }
+        } else if (g_dir && valid) {
+            g_dir[3 * m] = 0.f; g_dir[3 * m + 1] = 0.f; g_dir[3 * m + 2] = 0.f;
+        }
+        // ---------------- density backward ----------------
+        if (g_sigma && valid && y0pos) dy[0] += g_sigma[m] * scale;
+        if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dy[i] = 0.f;
+        }
+        grad16_store(dy, Gy, tid, lane, db_d2);
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            mma16_bwd_weight(tm + DCB_DWD2, aGy, aHd, 64, !first);
+            mma16_bwd_data(tm + DCB_S0, aGy, wd2, 64, 16, 16, false);
+            mb.commit();
+        }
+        mb.wait();
+        epi_grad64(tl + DCB_S0, mask_d, Hd, tid, lane, db_d1);               // Gd overwrites Hd
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            mma16_bwd_weight(tm + DCB_DWD1, aHd, aX, l.INP, !first);
+            if (g_feats) mma16_bwd_data(tm + DCB_S1, aHd, wd1, l.INP, 64, 64, false);
+            mb.commit();
+        }
+        mb.wait();
+        if (g_feats) {
+            for (int c0 = 0; c0 < l.INP; c0 += 16) {
+                float v[16];
+                tmem_ld16(tl + DCB_S1 + c0, v);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < IN) g_feats[m * IN + c0 + i] = v[i] * inv_scale * (lodw ? __ldg(lodw + c0 + i) : 1.f);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    // ---------------- flush weight / bias gradients (once per CTA) ----------------
+    if (!first) {
+        tc_fence_after();
+        flush_dw(tl + DCB_DWD1, p.gWd1, tid, 64, IN, l.INP, inv_scale);
+        flush_dw(tl + DCB_DWD2, p.gWd2, tid, 16, 64, 64, inv_scale);
+        const int f2 = scatter_base(lane, 64);
+        red_add_f32(p.gbd1 + f2, db_d1[0] * inv_scale); red_add_f32(p.gbd1 + f2 + 1, db_d1[1] * inv_scale);
+        const int f1 = scatter_base(lane, 32) >> 1;   // 16-feature scatter: 8*b4 + 4*b3 + 2*b2 + b1
+        if (!(lane & 1)) red_add_f32(p.gbd2 + f1, db_d2 * inv_scale);
+        if (do_rgb) {
+            flush_dw(tl + DCB_DWC1, p.gWc1, tid, 64, CIN, 48, inv_scale);
+            flush_dw(tl + DCB_DWC2, p.gWc2, tid, 64, 64, 64, inv_scale);
+            flush_dw(tl + DCB_DWC3, p.gWc3, tid, 3, 64, 64, inv_scale);
+            red_add_f32(p.gbc1 + f2, db_c1[0] * inv_scale); red_add_f32(p.gbc1 + f2 + 1, db_c1[1] * inv_scale);
+            red_add_f32(p.gbc2 + f2, db_c2[0] * inv_scale); red_add_f32(p.gbc2 + f2 + 1, db_c2[1] * inv_scale);
+            if (!(lane & 1) && f1 < 3) red_add_f32(p.gbc3 + f1, db_c3 * inv_scale);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// semantics + instance
+// ---------------------------------------------------------------------------------------------
+struct PanTcLayout {
+    int INP, nXc, CsP, CiP, nGi;
+    int oGs, oX, oHs, oH1, oH2, oGi, oWs1, oWs2, oWi1, oWi2, oWi3, oBias, total;
+};
+__host__ __device__ inline PanTcLayout pan_tc_layout(int IN, int Cs, int Ci, bool bwd) {
+    PanTcLayout l;
+    l.INP = (IN + 15) & ~15; l.nXc = l.INP / 8;
+    l.CsP = Cs > 0 ? ((Cs + 15) & ~15) : 16;
+    l.CiP = Ci > 0 ? ((Ci + 15) & ~15) : 16;
+    l.nGi = l.CiP / 8;
+    int o = 0;
+    l.oGs = o; o += bwd ? 2 * TCH : 0;
+    l.oX = o; o += 8 * TCH;
+    l.oHs = o; o += 8 * TCH;
+    l.oH1 = o; o += 8 * TCH;
+    l.oH2 = o; o += bwd ? 8 * TCH : 0;
+    l.oGi = o; o += bwd ? l.nGi * TCH : 0;
+    l.oWs1 = o; o += l.nXc * 64 * 16;
+    l.oWs2 = o; o += 8 * l.CsP * 16;
+    l.oWi1 = o; o += l.nXc * 64 * 16;
+    l.oWi2 = o; o += 8 * 64 * 16;
+    l.oWi3 = o; o += 8 * l.CiP * 16;
+    l.oBias = o; o += (64 + l.CsP + 64 + 64 + l.CiP) * 4;
+    if (bwd) {  // MN-major A operands read 16 chunks from their base (the second dWi3 block starts 16 chunks into Gi)
+        const int need = l.oGi + (l.nGi > 16 ? 32 : 16) * TCH;
+        if (o < need) o = need;
+    }
+    l.total = o;
+    return l;
+}
+__device__ __forceinline__ void pan_tc_stage(uint8_t* sm, const PanTcLayout& l, const PanParams& p, int IN, int Cs, int Ci) {
+    float* b = reinterpret_cast<float*>(sm + l.oBias);
+    if (Cs > 0) {
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWs1), p.Ws1, 64, IN, 64, l.INP);
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWs2), p.Ws2, Cs, 64, l.CsP, 64);
+        stage_b32(b, p.bs1, 64, 64); stage_b32(b + 64, p.bs2, Cs, l.CsP);
+    }
+    if (Ci > 0) {
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWi1), p.Wi1, 64, IN, 64, l.INP);
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWi2), p.Wi2, 64, 64, 64, 64);
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWi3), p.Wi3, Ci, 64, l.CiP, 64);
+        stage_b32(b + 64 + l.CsP, p.bi1, 64, 64); stage_b32(b + 128 + l.CsP, p.bi2, 64, 64);
+        stage_b32(b + 192 + l.CsP, p.bi3, Ci, l.CiP);
+    }
+}
+
+// logits row in TMEM [ncols] (+bias) -> optional softmax with temperature -> global row
+__device__ __forceinline__ void epi_head_out(uint32_t taddr, const float* __restrict__ bias, int C, int CP, bool softmax,
+                                             float inv_temp, float* __restrict__ out, bool valid) {
+    float mx = -INFINITY, sum = 0.f;
+    if (softmax) {
+        for (int c0 = 0; c0 < CP; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < C) {
+                    const float z = (v[i] + bias[c0 + i]) * inv_temp;
+                    const float nm = fmaxf(mx, z);
+                    sum = sum * expf(mx - nm) + expf(z - nm);
+                    mx = nm;
+                }
+        }
+    }
+    const float inv = softmax ? 1.f / sum : 1.f;
+    for (int c0 = 0; c0 < CP; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < C) {
+                    const float z = (v[i] + bias[c0 + i]) * inv_temp;
+                    out[c0 + i] = softmax ? expf(z - mx) * inv : z;
+                }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) pan_tc_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ dfeats,
+                                                         const float* __restrict__ lodw, int64_t M, int IN, PanParams p,
+                                                         int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
+                                                         float* __restrict__ sem, float* __restrict__ inst) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint64_t bar_s;
+    __shared__ uint32_t tmem_s;
+    const PanTcLayout l = pan_tc_layout(IN, Cs, Ci, false);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    pan_tc_stage(sm, l, p, IN, Cs, Ci);
+    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_s, 256);
+    sync_to_mma();
+    tc_fence_after();
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    MmaBar mb{&bar_s, 0};
+    const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
+    const float *bs1 = bias, *bs2 = bias + 64, *bi1 = bias + 64 + l.CsP, *bi2 = bi1 + 64, *bi3 = bi2 + 64;
+    uint8_t *X = sm + l.oX, *T1 = sm + l.oHs, *T2 = sm + l.oH1;
+    const uint32_t aX = smem_u32(X), aT1 = smem_u32(T1), aT2 = smem_u32(T2);
+    const uint32_t ws1 = smem_u32(sm + l.oWs1), ws2 = smem_u32(sm + l.oWs2), wi1 = smem_u32(sm + l.oWi1),
+                   wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
+    const int64_t ntiles = (M + 127) / 128;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t m = tile * 128 + tid;
+        const bool valid = m < M;
+        const int64_t mm = valid ? m : M - 1;
+        stage_x(X, tid, feats, dfeats, lodw, IN, l.nXc, mm);
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (Cs > 0) mma16_fwd(tm, aX, ws1, 64, 64, l.INP, false);
+            if (Ci > 0) mma16_fwd(tm + 64, aX, wi1, 64, 64, l.INP, false);
+            mb.commit();
+        }
+        mb.wait();
+        if (Cs > 0) epi_relu64(tl, bs1, T1, tid);
+        if (Ci > 0) epi_relu64(tl + 64, bi1, T2, tid);
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (Cs > 0) mma16_fwd(tm + 128, aT1, ws2, l.CsP, l.CsP, 64, false);
+            if (Ci > 0) mma16_fwd(tm, aT2, wi2, 64, 64, 64, false);
+            mb.commit();
+        }
+        mb.wait();
+        if (Cs > 0) epi_head_out(tl + 128, bs2, Cs, l.CsP, sem_softmax, 1.f, sem + mm * Cs, valid);
+        if (Ci > 0) {
+            epi_relu64(tl, bi2, T1, tid);
+            sync_to_mma();
+            if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT1, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
+            mb.wait();
+            epi_head_out(tl, bi3, Ci, l.CiP, inst_softmax, inst_inv_temp, inst + mm * Ci, valid);
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 256);
+}
+
+#define PNB_S0 0
+#define PNB_S1 64
+#define PNB_DWS1 128   // [64 x <=64]
+#define PNB_DWS2 192   // [Cs x 64]
+#define PNB_DWI1 256   // [64 x <=64]
+#define PNB_DWI2 320   // [64 x 64]
+#define PNB_DWI3 384   // [Ci(<=256) x 64] as two 128-row blocks -> 512 columns
+
+// d logits of one head from the saved probabilities: g_z = p*(g - <p,g>) / T  (or g / T without softmax)
+__device__ __forceinline__ void head_grad_tile(uint8_t* tile, int row, int lane, const float* __restrict__ prob,
+                                               const float* __restrict__ g, int C, int CP, bool softmax, float inv_temp,
+                                               float scale, bool valid, float* dbacc /* CP/32 rounded up, per lane */) {
+    float dot = 0.f;
+    if (softmax && valid)
+        for (int j = 0; j < C; ++j) dot = fmaf(prob[j], g[j], dot);
+#pragma unroll
+    for (int c0 = 0; c0 < 256; c0 += 32) {   // 32 features per pass (one per lane after the scatter); CP <= 256
+        if (c0 < CP) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int j = c0 + i;
+                float d = 0.f;
+                if (valid && j < C) d = (softmax ? prob[j] * (g[j] - dot) : g[j]) * inv_temp * scale;
+                v[i] = d;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c0 + 8 * c < CP) tile_store8(tile, c0 / 8 + c, row, v + 8 * c);
+            warp_reduce_scatter<32>(v, lane);   // lane keeps feature c0 + lane
+            dbacc[c0 / 32] += v[0];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) pan_tc_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dfeats,
+                                                         const float* __restrict__ lodw, int64_t M, int IN, PanParams p,
+                                                         int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
+                                                         const float* __restrict__ sem, const float* __restrict__ inst,
+                                                         const float* __restrict__ g_sem, const float* __restrict__ g_inst,
+                                                         const float* __restrict__ scale_ptr, float* __restrict__ g_panop) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint64_t bar_s;
+    __shared__ uint32_t tmem_s;
+    const PanTcLayout l = pan_tc_layout(IN, Cs, Ci, true);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pan_tc_stage(sm, l, p, IN, Cs, Ci);
+    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_s, 512);
+    sync_to_mma();
+    tc_fence_after();
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    MmaBar mb{&bar_s, 0};
+    const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
+    const float *bs1 = bias, *bi1 = bias + 64 + l.CsP, *bi2 = bi1 + 64;
+    uint8_t *Gs = sm + l.oGs, *X = sm + l.oX, *Hs = sm + l.oHs, *H1 = sm + l.oH1, *H2 = sm + l.oH2, *Gi = sm + l.oGi;
+    const uint32_t aGs = smem_u32(Gs), aX = smem_u32(X), aHs = smem_u32(Hs), aH1 = smem_u32(H1), aH2 = smem_u32(H2), aGi = smem_u32(Gi);
+    const uint32_t ws1 = smem_u32(sm + l.oWs1), ws2 = smem_u32(sm + l.oWs2), wi1 = smem_u32(sm + l.oWi1),
+                   wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
+    const float scale = scale_ptr ? __ldg(scale_ptr) : 1.f;
+    const float inv_scale = 1.f / scale;
+    const bool do_sem = (Cs > 0) && g_sem, do_inst = (Ci > 0) && g_inst;
+    float db_s1[2] = {0.f, 0.f}, db_i1[2] = {0.f, 0.f}, db_i2[2] = {0.f, 0.f}, db_s2[1] = {0.f}, db_i3[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) db_i3[i] = 0.f;
+    const int64_t ntiles = (M + 127) / 128;
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
+        const int64_t m = tile * 128 + tid;
+        const bool valid = m < M;
+        const int64_t mm = valid ? m : M - 1;
+        // ---------------- forward recompute of the hidden layers ----------------
+        stage_x(X, tid, feats, dfeats, lodw, IN, l.nXc, mm);
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (do_sem) mma16_fwd(tm + PNB_S0, aX, ws1, 64, 64, l.INP, false);
+            if (do_inst) mma16_fwd(tm + PNB_S1, aX, wi1, 64, 64, l.INP, false);
+            mb.commit();
+        }
+        mb.wait();
+        uint64_t mask_s = 0, mask_1 = 0, mask_2 = 0;
+        if (do_sem) mask_s = epi_relu64(tl + PNB_S0, bs1, Hs, tid);
+        if (do_inst) mask_1 = epi_relu64(tl + PNB_S1, bi1, H1, tid);
+        if (do_inst) {
+            sync_to_mma();
+            if (tid == 0) { tc_fence_after(); mma16_fwd(tm + PNB_S0, aH1, wi2, 64, 64, 64, false); mb.commit(); }
+            mb.wait();
+            mask_2 = epi_relu64(tl + PNB_S0, bi2, H2, tid);
+        }
+        // ---------------- head gradients from the saved outputs ----------------
+        if (do_sem) head_grad_tile(Gs, tid, lane, sem + mm * Cs, g_sem + mm * Cs, Cs, l.CsP, sem_softmax, 1.f, scale, valid, db_s2);
+        if (do_inst) head_grad_tile(Gi, tid, lane, inst + mm * Ci, g_inst + mm * Ci, Ci, l.CiP, inst_softmax, inst_inv_temp, scale, valid, db_i3);
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (do_sem) {
+                mma16_bwd_weight(tm + PNB_DWS2, aGs, aHs, 64, !first);
+                mma16_bwd_data(tm + PNB_S0, aGs, ws2, 64, l.CsP, l.CsP, false);
+            }
+            if (do_inst) {
+                mma16_bwd_weight(tm + PNB_DWI3, aGi, aH2, 64, !first);
+                if (l.CiP > 128) mma16_bwd_weight(tm + PNB_DWI3 + 64, aGi + 16 * TCH, aH2, 64, !first);
+                mma16_bwd_data(tm + PNB_S1, aGi, wi3, 64, l.CiP, l.CiP, false);
+            }
+            mb.commit();
+        }
+        mb.wait();
+        if (do_sem) epi_grad64(tl + PNB_S0, mask_s, Hs, tid, lane, db_s1);     // Gs1 overwrites Hs
+        if (do_inst) epi_grad64(tl + PNB_S1, mask_2, H2, tid, lane, db_i2);    // Gi2 overwrites H2
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (do_sem) {
+                mma16_bwd_weight(tm + PNB_DWS1, aHs, aX, l.INP, !first);
+                if (g_panop) mma16_bwd_data(tm + PNB_S0, aHs, ws1, l.INP, 64, 64, false);
+            }
+            if (do_inst) {
+                mma16_bwd_weight(tm + PNB_DWI2, aH2, aH1, 64, !first);
+                mma16_bwd_data(tm + PNB_S1, aH2, wi2, 64, 64, 64, false);
+            }
+            mb.commit();
+        }
+        mb.wait();
+        if (do_inst) {
+            epi_grad64(tl + PNB_S1, mask_1, H1, tid, lane, db_i1);             // Gi1 overwrites H1
+            sync_to_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                mma16_bwd_weight(tm + PNB_DWI1, aH1, aX, l.INP, !first);
+                if (g_panop) mma16_bwd_data(tm + PNB_S0, aH1, wi1, l.INP, 64, 64, do_sem);   // accumulates onto the semantic dX
+                mb.commit();
+            }
+            mb.wait();
+        }
+        if (g_panop) {
+            for (int c0 = 0; c0 < l.INP; c0 += 16) {
+                float v[16];
+                tmem_ld16(tl + PNB_S0 + c0, v);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < IN) g_panop[m * IN + c0 + i] = v[i] * inv_scale * (lodw ? __ldg(lodw + c0 + i) : 1.f);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (!first) {
+        tc_fence_after();
+        const int f2 = scatter_base(lane, 64), f32i = scatter_base(lane, 32);
+        if (do_sem) {
+            flush_dw(tl + PNB_DWS1, p.gWs1, tid, 64, IN, l.INP, inv_scale);
+            flush_dw(tl + PNB_DWS2, p.gWs2, tid, Cs, 64, 64, inv_scale);
+            red_add_f32(p.gbs1 + f2, db_s1[0] * inv_scale); red_add_f32(p.gbs1 + f2 + 1, db_s1[1] * inv_scale);
+            if (f32i < Cs) red_add_f32(p.gbs2 + f32i, db_s2[0] * inv_scale);
+        }
+        if (do_inst) {
+            flush_dw(tl + PNB_DWI1, p.gWi1, tid, 64, IN, l.INP, inv_scale);
+            flush_dw(tl + PNB_DWI2, p.gWi2, tid, 64, 64, 64, inv_scale);
+            flush_dw(tl + PNB_DWI3, p.gWi3, tid, Ci, 64, 64, inv_scale);
+            if (l.CiP > 128) flush_dw(tl + PNB_DWI3 + 64, p.gWi3 + (size_t)128 * 64, tid, Ci - 128, 64, 64, inv_scale);
+            red_add_f32(p.gbi1 + f2, db_i1[0] * inv_scale); red_add_f32(p.gbi1 + f2 + 1, db_i1[1] * inv_scale);
+            red_add_f32(p.gbi2 + f2, db_i2[0] * inv_scale); red_add_f32(p.gbi2 + f2 + 1, db_i2[1] * inv_scale);
+            for (int c = 0; c * 32 < l.CiP; ++c)
+                if (c * 32 + f32i < Ci) red_add_f32(p.gbi3 + c * 32 + f32i, db_i3[c] * inv_scale);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int tc_num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+template <typename K>
+static int tc_set_smem(K kernel, size_t bytes) {
+    if (bytes > 227 * 1024) return PAG_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e == cudaSuccess ? PAG_OK : (int)e;
+}
+static void fill_dc(DcParams& p, const float* const* w, float* const* g) {
+    p.Wd1 = w[0]; p.bd1 = w[1]; p.Wd2 = w[2]; p.bd2 = w[3]; p.Wc1 = w[4]; p.bc1 = w[5]; p.Wc2 = w[6]; p.bc2 = w[7]; p.Wc3 = w[8]; p.bc3 = w[9];
+    if (g) { p.gWd1 = g[0]; p.gbd1 = g[1]; p.gWd2 = g[2]; p.gbd2 = g[3]; p.gWc1 = g[4]; p.gbc1 = g[5]; p.gWc2 = g[6]; p.gbc2 = g[7]; p.gWc3 = g[8]; p.gbc3 = g[9]; }
+}
+static void fill_pan(PanParams& p, const float* const* w, float* const* g) {
+    p.Ws1 = w[0]; p.bs1 = w[1]; p.Ws2 = w[2]; p.bs2 = w[3]; p.Wi1 = w[4]; p.bi1 = w[5]; p.Wi2 = w[6]; p.bi2 = w[7]; p.Wi3 = w[8]; p.bi3 = w[9];
+    if (g) { p.gWs1 = g[0]; p.gbs1 = g[1]; p.gWs2 = g[2]; p.gbs2 = g[3]; p.gWi1 = g[4]; p.gbi1 = g[5]; p.gWi2 = g[6]; p.gbi2 = g[7]; p.gWi3 = g[8]; p.gbi3 = g[9]; }
+}
+
+extern "C" {
+
+int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray_d, int S, int64_t M, int IN,
+                         const float* const* weights, int hidden, int view_dim, int want_rgb, float* sigma, float* rgb,
+                         void* stream) {
+    if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64) return PAG_ERR_UNSUPPORTED;
+    if (M == 0) return PAG_OK;
+    DcParams p{};
+    fill_dc(p, weights, nullptr);
+    const DcTcLayout l = dc_tc_layout(IN, false);
+    int rc = tc_set_smem(dc_tc_fwd_kernel, l.total);
+    if (rc) return rc;
+    const int64_t tiles = (M + 127) / 128;
+    const int64_t cap = 4 * (int64_t)tc_num_sms();
+    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// grad_scale: device pointer to one float (power of two) or NULL (= 1)
+int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray_d, int S, int64_t M, int IN,
+                         const float* const* weights, float* const* grads, int hidden, int view_dim,
+                         const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats, float* g_dir,
+                         void* stream) {
+    if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64) return PAG_ERR_UNSUPPORTED;
+    if (M == 0) return PAG_OK;
+    DcParams p{};
+    fill_dc(p, weights, grads);
+    const DcTcLayout l = dc_tc_layout(IN, true);
+    int rc = tc_set_smem(dc_tc_bwd_kernel, l.total);
+    if (rc) return rc;
+    const int64_t tiles = (M + 127) / 128;
+    const int64_t cap = tc_num_sms();
+    dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
+        feats, lodw, ray_d, S, M, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_decode_pan_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                          const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
+                          float inst_temperature, float* sem, float* inst, void* stream) {
+    if (hidden != H || Cs < 0 || Ci < 0 || Cs > 32 || Ci > 256 || IN < 1 || IN > 64) return PAG_ERR_UNSUPPORTED;
+    if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
+    PanParams p{};
+    fill_pan(p, weights, nullptr);
+    const PanTcLayout l = pan_tc_layout(IN, Cs, Ci, false);
+    int rc = tc_set_smem(pan_tc_fwd_kernel, l.total);
+    if (rc) return rc;
+    const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
+    const int64_t tiles = (M + 127) / 128;
+    const int64_t cap = 2 * (int64_t)tc_num_sms();
+    pan_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, sem, inst);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_decode_pan_bwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                          const float* const* weights, float* const* grads, int hidden, int Cs, int Ci, int sem_softmax,
+                          int inst_softmax, float inst_temperature, const float* sem, const float* inst,
+                          const float* g_sem, const float* g_inst, const float* grad_scale, float* g_panop, void* stream) {
+    if (hidden != H || Cs < 0 || Ci < 0 || Cs > 32 || Ci > 256 || IN < 1 || IN > 64) return PAG_ERR_UNSUPPORTED;
+    if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
+    PanParams p{};
+    fill_pan(p, weights, grads);
+    const PanTcLayout l = pan_tc_layout(IN, Cs, Ci, true);
+    int rc = tc_set_smem(pan_tc_bwd_kernel, l.total);
+    if (rc) return rc;
+    const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
+    const int64_t tiles = (M + 127) / 128;
+    const int64_t cap = tc_num_sms();
+    pan_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, sem, inst, g_sem, g_inst, grad_scale, g_panop);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+}  // extern "C"

@@ -251,13 +251,23 @@ def hash_indices(pos, flavour, fparam, res, offset, size):
 # ------------------------------------------------------------------------------------------------
 HIDDEN = 64
 VIEW_DIM = 27
+GRAD_TARGET = 1024.0   # upstream gradients are rescaled so that their max magnitude sits near 2^10 in fp16
+
+
+def grad_scale(*grads):
+    """Power-of-two loss scale for the fp16 tensor-core backward (device scalar, no host sync):
+    2^floor(log2(GRAD_TARGET / max|g|)).  Plays the role of torch.cuda.amp.GradScaler inside the op."""
+    gs = [g for g in grads if g is not None]
+    amax = torch.stack([g.abs().max() for g in gs]).max().clamp_min(1e-30)
+    s = torch.exp2(torch.floor(torch.log2(GRAD_TARGET / amax))).clamp(2.0 ** -24, 2.0 ** 60)
+    return s.reshape(1).to(torch.float32).contiguous()
 
 
 class DecodeDCFn(Function):
     """density + color decoders.  feats [M,IN], ray_d [M//S, 3] -> sigma [M], rgb [M,3] (or None)."""
 
     @staticmethod
-    def forward(ctx, feats, lodw, ray_d, S, want_rgb, *weights):
+    def forward(ctx, feats, lodw, ray_d, S, want_rgb, use_tc, *weights):
         _chk(feats, ray_d, *weights)
         f = _f32(feats)
         M, IN = f.shape
@@ -266,10 +276,10 @@ class DecodeDCFn(Function):
         sigma = torch.empty(M, dtype=torch.float32, device=f.device)
         rgb = torch.empty(M, 3, dtype=torch.float32, device=f.device) if want_rgb else None
         lw = _f32(lodw)
-        call("pag_decode_dc_fwd", ptr(f), ptr(lw), ptr(rd), int(S), M, IN, ptr_array(w), HIDDEN, VIEW_DIM,
-             int(bool(want_rgb)), ptr(sigma), ptr(rgb))
+        call("pag_decode_dc_fwd_tc" if use_tc else "pag_decode_dc_fwd", ptr(f), ptr(lw), ptr(rd), int(S), M, IN,
+             ptr_array(w), HIDDEN, VIEW_DIM, int(bool(want_rgb)), ptr(sigma), ptr(rgb))
         ctx.save_for_backward(f, lw, rd, *w)
-        ctx.S, ctx.want_rgb = int(S), bool(want_rgb)
+        ctx.S, ctx.want_rgb, ctx.use_tc = int(S), bool(want_rgb), bool(use_tc)
         return sigma, rgb
 
     @staticmethod
@@ -283,18 +293,22 @@ class DecodeDCFn(Function):
         need_f, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
         gf = torch.empty_like(f) if need_f else None
         gd = torch.empty(M, 3, dtype=torch.float32, device=f.device) if need_d else None
-        call("pag_decode_dc_bwd", ptr(f), ptr(lw), ptr(rd), ctx.S, M, IN, ptr_array(w), ptr_array(grads), HIDDEN,
-             VIEW_DIM, ptr(gs), ptr(gr), ptr(gf), ptr(gd))
+        if ctx.use_tc:
+            call("pag_decode_dc_bwd_tc", ptr(f), ptr(lw), ptr(rd), ctx.S, M, IN, ptr_array(w), ptr_array(grads), HIDDEN,
+                 VIEW_DIM, ptr(gs), ptr(gr), ptr(grad_scale(gs, gr)), ptr(gf), ptr(gd))
+        else:
+            call("pag_decode_dc_bwd", ptr(f), ptr(lw), ptr(rd), ctx.S, M, IN, ptr_array(w), ptr_array(grads), HIDDEN,
+                 VIEW_DIM, ptr(gs), ptr(gr), ptr(gf), ptr(gd))
         if need_d:
             gd = gd.view(-1, ctx.S, 3).sum(1) if ctx.S > 1 else gd
-        return (gf, None, gd, None, None, *grads)
+        return (gf, None, gd, None, None, None, *grads)
 
 
 class DecodePanFn(Function):
     """semantic + instance decoders on panop = (feats + dfeats) * lodw."""
 
     @staticmethod
-    def forward(ctx, feats, dfeats, lodw, Cs, Ci, sem_softmax, inst_softmax, inst_temperature, *weights):
+    def forward(ctx, feats, dfeats, lodw, Cs, Ci, sem_softmax, inst_softmax, inst_temperature, use_tc, *weights):
         _chk(feats, dfeats, *weights)
         f = _f32(feats)
         df = _f32(dfeats)
@@ -303,7 +317,8 @@ class DecodePanFn(Function):
         sem = torch.empty(M, Cs, dtype=torch.float32, device=f.device) if Cs else None
         inst = torch.empty(M, Ci, dtype=torch.float32, device=f.device) if Ci else None
         lw = _f32(lodw)
-        call("pag_decode_pan_fwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), HIDDEN, int(Cs), int(Ci),
+        ctx.use_tc = bool(use_tc)
+        call("pag_decode_pan_fwd_tc" if use_tc else "pag_decode_pan_fwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), HIDDEN, int(Cs), int(Ci),
              int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature), ptr(sem), ptr(inst))
         ctx.save_for_backward(f, df, lw, sem, inst, *w)
         ctx.cfg = (int(Cs), int(Ci), int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature))
@@ -320,10 +335,14 @@ class DecodePanFn(Function):
         grads = [torch.zeros_like(x) for x in w]
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         gp = torch.empty_like(f) if need else None
-        call("pag_decode_pan_bwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), ptr_array(grads), HIDDEN, Cs, Ci, ss, is_, it,
-             ptr(sem), ptr(inst), ptr(gs), ptr(gi), ptr(gp))
+        if ctx.use_tc:
+            call("pag_decode_pan_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), ptr_array(grads), HIDDEN, Cs, Ci, ss, is_, it,
+                 ptr(sem), ptr(inst), ptr(gs), ptr(gi), ptr(grad_scale(gs, gi)), ptr(gp))
+        else:
+            call("pag_decode_pan_bwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), ptr_array(grads), HIDDEN, Cs, Ci, ss, is_, it,
+                 ptr(sem), ptr(inst), ptr(gs), ptr(gi), ptr(gp))
         return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
-                None, None, None, None, None, None, *grads)
+                None, None, None, None, None, None, None, *grads)
 
 
 # ------------------------------------------------------------------------------------------------

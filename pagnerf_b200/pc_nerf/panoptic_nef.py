@@ -160,10 +160,20 @@ class PanopticNeF(BaseNeuralField):
                                       "(every reference config uses 'cat', configs/bup20/*.yaml)")
         return feats
 
+    # decoder arithmetic: 'auto' = tensor cores (fp16 operands, fp32 accumulate) under torch autocast -- what the
+    # reference's training step runs (pc_nerf/trainer.py:429) -- and exact fp32 otherwise (validation, :683);
+    # 'fp32' / 'fp16' force one of the two kernels.
+    decoder_precision = 'auto'
+
+    def _use_tc(self):
+        if self.decoder_precision == 'auto':
+            return torch.is_autocast_enabled()
+        return self.decoder_precision == 'fp16'
+
     def _dc(self, feats, ray_d, num_samples, want_rgb):
         w = _decoder_tensors(self.decoder_density, 1) + _decoder_tensors(self.decoder_color, 2)
         lodw = self.lod_weights.to(feats.device)
-        return ops.DecodeDCFn.apply(feats, lodw, ray_d, num_samples, want_rgb, *w)
+        return ops.DecodeDCFn.apply(feats, lodw, ray_d, num_samples, want_rgb, self._use_tc(), *w)
 
     def _pan(self, feats, dfeats, want_sem, want_inst, inst_temperature=0.0):
         """semantic / instance heads on (feats + dfeats) * lod_weights; non-default sigmoid / normalize
@@ -176,7 +186,7 @@ class PanopticNeF(BaseNeuralField):
         Ci = self.num_instances if want_inst else 0
         sem, inst = ops.DecodePanFn.apply(feats, dfeats, lodw, Cs, Ci, bool(self.sem_softmax and sem_plain),
                                           bool(self.inst_softmax and inst_plain),
-                                          float(inst_temperature if inst_plain else 0.0), *w)
+                                          float(inst_temperature if inst_plain else 0.0), self._use_tc(), *w)
         if want_sem and not sem_plain:
             sem = torch.sigmoid(sem) if self.sem_sigmoid else sem
             sem = F.normalize(sem, dim=-1) if self.sem_normalize else sem

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from tests.util import (load_golden, build_oracle_field, build_cuda_nef, oracle_march, golden_grads, golden_params,
-                        assert_close, GOLDEN_CFG)
+                        assert_close, assert_close_norm, GOLDEN_CFG)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -404,3 +404,77 @@ def test_full_size_properties(cuda_lib):
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     # packed indices: sorted rays, boundary count == rays with samples
     assert (out["ridx"][1:] >= out["ridx"][:-1]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) decoders vs the exact fp32 kernels / oracle
+# ------------------------------------------------------------------------------------------------
+def test_tcgen05_building_blocks(cuda_lib):
+    """K-major x K-major, K-major x MN-major and MN-major x MN-major (K = 128 samples) operand images."""
+    from pagnerf_b200._lib import call, ptr
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    cases = [(0, 64, 48, 0), (0, 16, 64, 0), (0, 208, 64, 0), (1, 64, 64, 0), (1, 48, 64, 0), (1, 64, 208, 0), (1, 64, 16, 0),
+             (2, 64, 0, 64), (2, 48, 0, 64), (2, 64, 0, 16), (2, 64, 0, 128)]
+    for mode, N, K, FA in cases:
+        if mode == 0:
+            A, B = torch.randn(128, K, device=DEV, generator=gen), torch.randn(N, K, device=DEV, generator=gen); ref = A @ B.t()
+        elif mode == 1:
+            A, B = torch.randn(128, K, device=DEV, generator=gen), torch.randn(K, N, device=DEV, generator=gen); ref = A @ B
+        else:
+            A, B = torch.randn(128, FA, device=DEV, generator=gen), torch.randn(128, N, device=DEV, generator=gen); ref = A.t() @ B
+        for reps in (1, 2):
+            D = torch.zeros(128, N, device=DEV)
+            call("pag_tc_gemm_test16", mode, ptr(A), ptr(B), ptr(D), N, K, FA, reps)
+            assert_close(D[:ref.shape[0]], ref * reps, rtol=2e-3, atol_scale=2e-3, msg=f"mode {mode} N {N} K {K} FA {FA} reps {reps}")
+
+
+@pytest.mark.parametrize("name", ["trace_delta_permuto_ray", "trace_nef_tcnn_ray"])
+@pytest.mark.parametrize("M", [300, 5000])
+def test_tc_decoders_vs_fp32(cuda_lib, name, M):
+    """fp16-operand tensor-core decoders (training mode) against the exact fp32 kernels: 2e-3 (north_star fp16 tolerance)."""
+    g = load_golden(name)
+    nef = build_cuda_nef(g, DEV)
+    gen = torch.Generator().manual_seed(M)
+    coords = (torch.rand(M, 1, 3, generator=gen) * 2 - 1).to(DEV)
+    ray_d = torch.nn.functional.normalize(torch.randn(M, 3, generator=gen), dim=-1).to(DEV)
+    chans = {'density', 'rgb', 'semantics', 'inst_embedding'}
+    gws = None
+    res = {}
+    for prec in ('fp32', 'fp16'):
+        nef.decoder_precision = prec
+        nef.zero_grad(set_to_none=True)
+        ct, dt = coords.clone().requires_grad_(True), ray_d.clone().requires_grad_(True)
+        out = nef(coords=ct, ray_d=dt, channels=chans)
+        if gws is None:
+            gws = {c: torch.randn(out[c].shape, generator=gen).to(DEV) * 1e-3 for c in chans}
+        sum((out[c] * gws[c]).sum() for c in chans).backward()
+        res[prec] = ({c: out[c].detach() for c in chans}, {k: p.grad.clone() for k, p in nef.named_parameters()}, ct.grad, dt.grad)
+    for c in chans:
+        assert_close(res['fp16'][0][c], res['fp32'][0][c], msg=c, rtol=2e-3, atol_scale=2e-3)
+    for k in res['fp32'][1]:
+        assert_close_norm(res['fp16'][1][k], res['fp32'][1][k], msg="grad " + k)
+    assert_close_norm(res['fp16'][2], res['fp32'][2], msg="grad coords")
+    assert_close_norm(res['fp16'][3], res['fp32'][3], msg="grad ray_d")
+
+
+def test_tc_trace_under_autocast_matches_golden(cuda_lib):
+    """Training-mode numerics (autocast -> fp16 coords rounding is bypassed by feeding fp16-exact rays; tensor-core
+    decoders) through the tracer vs the reference-made golden at the fp16 tolerance."""
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_ray")
+    nef = build_cuda_nef(g, DEV)
+    nef.decoder_precision = 'fp16'
+    tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=int(g["num_steps"]), bg_color='white')
+    o = torch.from_numpy(g["o"]).to(DEV).requires_grad_(True)
+    d = torch.from_numpy(g["d"]).to(DEV).requires_grad_(True)
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    rb = tracer(nef, channels=chans, rays=Rays(origins=o, dirs=d, dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+    for c in chans + ['alpha']:
+        assert_close(getattr(rb, c), g["out_" + c], msg=c, rtol=3e-3, atol_scale=3e-3)
+    loss = sum((getattr(rb, c) * torch.from_numpy(g["gw_" + c]).to(DEV)).sum() for c in chans)
+    loss.backward()
+    gg = golden_grads(g)
+    for k, p in nef.named_parameters():
+        if k in gg:
+            assert_close_norm(p.grad, gg[k], msg="grad " + k)
