@@ -185,23 +185,45 @@ __device__ __forceinline__ void dc_tc_stage(uint8_t* sm, const DcTcLayout& l, co
     stage_b32(b + 144, p.bc2, 64, 64); stage_b32(b + 208, p.bc3, 3, 16);
 }
 
-// this thread's feature row -> X tile
+// this thread's feature row -> X tile (float4 global loads: IN is a multiple of 4 for every supported grid)
 __device__ __forceinline__ void stage_x(uint8_t* tile, int row, const float* __restrict__ a, const float* __restrict__ b,
                                         const float* __restrict__ lodw, int IN, int nchunks, int64_t m) {
+    const float4* a4 = reinterpret_cast<const float4*>(a + m * IN);
+    const float4* b4 = b ? reinterpret_cast<const float4*>(b + m * IN) : nullptr;
+    const float4* w4 = lodw ? reinterpret_cast<const float4*>(lodw) : nullptr;
     for (int c = 0; c < nchunks; ++c) {
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int k = c * 8 + e;
-            float x = 0.f;
-            if (k < IN) {
-                x = a[m * IN + k];
-                if (b) x += b[m * IN + k];
-                if (lodw) x *= __ldg(lodw + k);
+        for (int h = 0; h < 2; ++h) {
+            const int q = 2 * c + h;   // float4 index
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * q < IN) {
+                x = __ldg(a4 + q);
+                if (b4) { const float4 y = __ldg(b4 + q); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+                if (w4) { const float4 w = __ldg(w4 + q); x.x *= w.x; x.y *= w.y; x.z *= w.z; x.w *= w.w; }
             }
-            v[e] = x;
+            v[4 * h] = x.x; v[4 * h + 1] = x.y; v[4 * h + 2] = x.z; v[4 * h + 3] = x.w;
         }
         tile_store8(tile, c, row, v);
+    }
+}
+// dX row (TMEM) -> global, float4 stores
+__device__ __forceinline__ void store_dx(uint32_t taddr, float* __restrict__ dst, const float* __restrict__ lodw, int IN,
+                                         int INP, float inv_scale, bool valid) {
+    for (int c0 = 0; c0 < INP; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (c0 + 4 * q < IN) {
+                    float4 w = lodw ? __ldg(reinterpret_cast<const float4*>(lodw + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    float4 o = make_float4(v[4 * q] * inv_scale * w.x, v[4 * q + 1] * inv_scale * w.y,
+                                           v[4 * q + 2] * inv_scale * w.z, v[4 * q + 3] * inv_scale * w.w);
+                    reinterpret_cast<float4*>(dst + c0)[q] = o;
+                }
+            }
+        }
     }
 }
 // color-decoder input row [y16 | PE(-d) | 0 pad] -> 6 chunks
@@ -459,17 +481,7 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
             mb.commit();
         }
         mb.wait();
-        if (g_feats) {
-            for (int c0 = 0; c0 < l.INP; c0 += 16) {
-                float v[16];
-                tmem_ld16(tl + DCB_S1 + c0, v);
-                if (valid) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < IN) g_feats[m * IN + c0 + i] = v[i] * inv_scale * (lodw ? __ldg(lodw + c0 + i) : 1.f);
-                }
-            }
-        }
+        if (g_feats) store_dx(tl + DCB_S1, g_feats + mm * IN, lodw, IN, l.INP, inv_scale, valid);
         tc_fence_before();
         __syncthreads();
     }
@@ -501,7 +513,7 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 struct PanTcLayout {
     int INP, nXc, CsP, CiP, nGi;
-    int oGs, oX, oHs, oH1, oH2, oGi, oWs1, oWs2, oWi1, oWi2, oWi3, oBias, total;
+    int oGs, oX, oHs, oH1, oH2, oGi, oWs1, oWs2, oWi1, oWi2, oWi3, oBias, oStage, total;
 };
 __host__ __device__ inline PanTcLayout pan_tc_layout(int IN, int Cs, int Ci, bool bwd) {
     PanTcLayout l;
@@ -522,6 +534,8 @@ __host__ __device__ inline PanTcLayout pan_tc_layout(int IN, int Cs, int Ci, boo
     l.oWi2 = o; o += 8 * 64 * 16;
     l.oWi3 = o; o += 8 * l.CiP * 16;
     l.oBias = o; o += (64 + l.CsP + 64 + 64 + l.CiP) * 4;
+    o = (o + 15) & ~15;
+    l.oStage = o; o += bwd ? 4 * 2 * 32 * 33 * 4 : 0;   // per-warp transpose buffers for the coalesced prob / grad loads
     if (bwd) {  // MN-major A operands read 16 chunks from their base (the second dWi3 block starts 16 chunks into Gi)
         const int need = l.oGi + (l.nGi > 16 ? 32 : 16) * TCH;
         if (o < need) o = need;
@@ -545,9 +559,12 @@ __device__ __forceinline__ void pan_tc_stage(uint8_t* sm, const PanTcLayout& l, 
     }
 }
 
-// logits row in TMEM [ncols] (+bias) -> optional softmax with temperature -> global row
+// logits row in TMEM [ncols] (+bias) -> optional softmax with temperature -> global rows.
+// `stage` (per-warp [32][33] floats) transposes 32-column blocks so that every global store instruction
+// writes one full 128-byte row segment (lanes = columns) instead of 32 strided 4-byte words.
 __device__ __forceinline__ void epi_head_out(uint32_t taddr, const float* __restrict__ bias, int C, int CP, bool softmax,
-                                             float inv_temp, float* __restrict__ out, bool valid) {
+                                             float inv_temp, float* __restrict__ out_tile /* row 0 of this warp */,
+                                             int64_t rows_valid /* rows of this warp that exist */, float* stage, int lane) {
     float mx = -INFINITY, sum = 0.f;
     if (softmax) {
         for (int c0 = 0; c0 < CP; c0 += 16) {
@@ -564,17 +581,25 @@ __device__ __forceinline__ void epi_head_out(uint32_t taddr, const float* __rest
         }
     }
     const float inv = softmax ? 1.f / sum : 1.f;
-    for (int c0 = 0; c0 < CP; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        if (valid) {
+    for (int c0 = 0; c0 < CP; c0 += 32) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (c0 + i < C) {
-                    const float z = (v[i] + bias[c0 + i]) * inv_temp;
-                    out[c0 + i] = softmax ? expf(z - mx) * inv : z;
+        for (int h = 0; h < 2; ++h) {
+            if (c0 + 16 * h < CP) {
+                float v[16];
+                tmem_ld16(taddr + c0 + 16 * h, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int j = c0 + 16 * h + i;
+                    const float z = (v[i] + (j < C ? bias[j] : 0.f)) * inv_temp;
+                    stage[lane * 33 + 16 * h + i] = softmax ? expf(z - mx) * inv : z;
                 }
+            }
         }
+        __syncwarp();
+        if (c0 + lane < C) {
+            for (int r = 0; r < 32 && r < rows_valid; ++r) out_tile[(int64_t)r * C + c0 + lane] = stage[r * 33 + lane];
+        }
+        __syncwarp();
     }
 }
 
@@ -600,6 +625,7 @@ __global__ void __launch_bounds__(128) pan_tc_fwd_kernel(const float* __restrict
     const uint32_t aX = smem_u32(X), aT1 = smem_u32(T1), aT2 = smem_u32(T2);
     const uint32_t ws1 = smem_u32(sm + l.oWs1), ws2 = smem_u32(sm + l.oWs2), wi1 = smem_u32(sm + l.oWi1),
                    wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
+    const uint32_t semcol = (Ci > 0) ? (uint32_t)(l.CiP > 64 ? l.CiP : 64) : 128u;   // behind the instance logits and the Hi2 accumulator
     const int64_t ntiles = (M + 127) / 128;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t m = tile * 128 + tid;
@@ -619,18 +645,23 @@ __global__ void __launch_bounds__(128) pan_tc_fwd_kernel(const float* __restrict
         sync_to_mma();
         if (tid == 0) {
             tc_fence_after();
-            if (Cs > 0) mma16_fwd(tm + 128, aT1, ws2, l.CsP, l.CsP, 64, false);
+            if (Cs > 0) mma16_fwd(tm + semcol, aT1, ws2, l.CsP, l.CsP, 64, false);
             if (Ci > 0) mma16_fwd(tm, aT2, wi2, 64, 64, 64, false);
             mb.commit();
         }
         mb.wait();
-        if (Cs > 0) epi_head_out(tl + 128, bs2, Cs, l.CsP, sem_softmax, 1.f, sem + mm * Cs, valid);
+        float* stage = reinterpret_cast<float*>(sm + l.oHs) + warp * (32 * 33);   // T1|T2 (32 KB) are free in the final epilogues
+        const int64_t row0 = tile * 128 + warp * 32;
+        const int64_t rows_valid = M - row0;
         if (Ci > 0) {
             epi_relu64(tl, bi2, T1, tid);
             sync_to_mma();
             if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT1, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
             mb.wait();
-            epi_head_out(tl, bi3, Ci, l.CiP, inst_softmax, inst_inv_temp, inst + mm * Ci, valid);
+            epi_head_out(tl, bi3, Ci, l.CiP, inst_softmax, inst_inv_temp, inst + row0 * Ci, rows_valid, stage, tid & 31);
+        }
+        if (Cs > 0) {   // semantic head last: the transpose buffer is only free after the instance chain consumed T1/T2
+            epi_head_out(tl + semcol, bs2, Cs, l.CsP, sem_softmax, 1.f, sem + row0 * Cs, rows_valid, stage, tid & 31);
         }
         tc_fence_before();
         __syncthreads();
@@ -648,24 +679,47 @@ __global__ void __launch_bounds__(128) pan_tc_fwd_kernel(const float* __restrict
 #define PNB_DWI2 320   // [64 x 64]
 #define PNB_DWI3 384   // [Ci(<=256) x 64] as two 128-row blocks -> 512 columns
 
-// d logits of one head from the saved probabilities: g_z = p*(g - <p,g>) / T  (or g / T without softmax)
-__device__ __forceinline__ void head_grad_tile(uint8_t* tile, int row, int lane, const float* __restrict__ prob,
-                                               const float* __restrict__ g, int C, int CP, bool softmax, float inv_temp,
-                                               float scale, bool valid, float* dbacc /* CP/32 rounded up, per lane */) {
+// d logits of one head from the saved probabilities: g_z = p*(g - <p,g>) / T  (or g / T without softmax).
+// prob / g rows are fetched with coalesced 128-byte row segments (lanes = columns) into a per-warp transpose
+// buffer `stage` (2 x [32][33] floats) and consumed thread-per-row from there.
+__device__ __forceinline__ void head_grad_tile(uint8_t* tile, int row, int lane, const float* __restrict__ prob_w0,
+                                               const float* __restrict__ g_w0, int64_t rows_valid, int C, int CP,
+                                               bool softmax, float inv_temp, float scale, float* stage,
+                                               float* dbacc /* CP/32 rounded up, per lane */) {
+    float* sp = stage;
+    float* sg = stage + 32 * 33;
     float dot = 0.f;
-    if (softmax && valid)
-        for (int j = 0; j < C; ++j) dot = fmaf(prob[j], g[j], dot);
+    if (softmax) {
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const bool cok = c0 + lane < C;
+            for (int r = 0; r < 32; ++r) {
+                const bool ok = cok && r < rows_valid;
+                sp[r * 33 + lane] = ok ? __ldg(prob_w0 + (int64_t)r * C + c0 + lane) : 0.f;
+                sg[r * 33 + lane] = ok ? __ldg(g_w0 + (int64_t)r * C + c0 + lane) : 0.f;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dot = fmaf(sp[lane * 33 + i], sg[lane * 33 + i], dot);
+            __syncwarp();
+        }
+    }
 #pragma unroll
     for (int c0 = 0; c0 < 256; c0 += 32) {   // 32 features per pass (one per lane after the scatter); CP <= 256
         if (c0 < CP) {
+            const bool cok = c0 + lane < C;
+            for (int r = 0; r < 32; ++r) {
+                const bool ok = cok && r < rows_valid;
+                sp[r * 33 + lane] = ok ? __ldg(prob_w0 + (int64_t)r * C + c0 + lane) : 0.f;
+                sg[r * 33 + lane] = ok ? __ldg(g_w0 + (int64_t)r * C + c0 + lane) : 0.f;
+            }
+            __syncwarp();
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const int j = c0 + i;
-                float d = 0.f;
-                if (valid && j < C) d = (softmax ? prob[j] * (g[j] - dot) : g[j]) * inv_temp * scale;
-                v[i] = d;
+                const float pj = sp[lane * 33 + i], gj = sg[lane * 33 + i];
+                v[i] = (softmax ? pj * (gj - dot) : gj) * inv_temp * scale;   // zero for padded columns / rows
             }
+            __syncwarp();
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 if (c0 + 8 * c < CP) tile_store8(tile, c0 / 8 + c, row, v + 8 * c);
@@ -731,8 +785,13 @@ __global__ void __launch_bounds__(128) pan_tc_bwd_kernel(const float* __restrict
             mask_2 = epi_relu64(tl + PNB_S0, bi2, H2, tid);
         }
         // ---------------- head gradients from the saved outputs ----------------
-        if (do_sem) head_grad_tile(Gs, tid, lane, sem + mm * Cs, g_sem + mm * Cs, Cs, l.CsP, sem_softmax, 1.f, scale, valid, db_s2);
-        if (do_inst) head_grad_tile(Gi, tid, lane, inst + mm * Ci, g_inst + mm * Ci, Ci, l.CiP, inst_softmax, inst_inv_temp, scale, valid, db_i3);
+        {
+            float* stage = reinterpret_cast<float*>(sm + l.oStage) + warp * (2 * 32 * 33);
+            const int64_t row0 = tile * 128 + warp * 32;
+            const int64_t rows_valid = M - row0;
+            if (do_sem) head_grad_tile(Gs, tid, lane, sem + row0 * Cs, g_sem + row0 * Cs, rows_valid, Cs, l.CsP, sem_softmax, 1.f, scale, stage, db_s2);
+            if (do_inst) head_grad_tile(Gi, tid, lane, inst + row0 * Ci, g_inst + row0 * Ci, rows_valid, Ci, l.CiP, inst_softmax, inst_inv_temp, scale, stage, db_i3);
+        }
         sync_to_mma();
         if (tid == 0) {
             tc_fence_after();
@@ -775,17 +834,7 @@ __global__ void __launch_bounds__(128) pan_tc_bwd_kernel(const float* __restrict
             }
             mb.wait();
         }
-        if (g_panop) {
-            for (int c0 = 0; c0 < l.INP; c0 += 16) {
-                float v[16];
-                tmem_ld16(tl + PNB_S0 + c0, v);
-                if (valid) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < IN) g_panop[m * IN + c0 + i] = v[i] * inv_scale * (lodw ? __ldg(lodw + c0 + i) : 1.f);
-                }
-            }
-        }
+        if (g_panop) store_dx(tl + PNB_S0, g_panop + mm * IN, lodw, IN, l.INP, inv_scale, valid);
         tc_fence_before();
         __syncthreads();
     }
@@ -847,7 +896,7 @@ extern "C" {
 int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray_d, int S, int64_t M, int IN,
                          const float* const* weights, int hidden, int view_dim, int want_rgb, float* sigma, float* rgb,
                          void* stream) {
-    if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64) return PAG_ERR_UNSUPPORTED;
+    if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
     if (M == 0) return PAG_OK;
     DcParams p{};
     fill_dc(p, weights, nullptr);
@@ -866,7 +915,7 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
                          const float* const* weights, float* const* grads, int hidden, int view_dim,
                          const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats, float* g_dir,
                          void* stream) {
-    if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64) return PAG_ERR_UNSUPPORTED;
+    if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
     if (M == 0) return PAG_OK;
     DcParams p{};
     fill_dc(p, weights, grads);
@@ -884,7 +933,7 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
 int pag_decode_pan_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                           const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
                           float inst_temperature, float* sem, float* inst, void* stream) {
-    if (hidden != H || Cs < 0 || Ci < 0 || Cs > 32 || Ci > 256 || IN < 1 || IN > 64) return PAG_ERR_UNSUPPORTED;
+    if (hidden != H || Cs < 0 || Ci < 0 || Cs > 32 || Ci > 224 || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
     PanParams p{};
     fill_pan(p, weights, nullptr);
