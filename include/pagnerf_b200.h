@@ -124,6 +124,19 @@ int pag_decode_pan_bwd_tc(const float* feats, const float* dfeats, const float* 
                           int inst_softmax, float inst_temperature, const float* sem, const float* inst,
                           const float* g_sem, const float* g_inst, const float* grad_scale, float* g_panop, void* stream);
 
+/* panoptic heads fused with their compositing (training mode): out[ray] = alpha_ray * sum_s w_s * head(panop_s) with
+ * alpha, w detached (tracers/panoptic_packed_rf_tracer.py:148-155,178-205); the [M,C] probabilities never reach HBM.
+ * out_sem[N,Cs] / out_inst[N,Ci] must be zeroed by the caller (accumulated with red.add). ridx i64[M] ascending. */
+int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                             const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
+                             float inst_temperature, const float* w, const float* alpha, const int64_t* ridx,
+                             float* out_sem, float* out_inst, void* stream);
+int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                             const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
+                             int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
+                             const int64_t* ridx, const float* g_sem, const float* g_inst, const float* grad_scale,
+                             float* g_panop, void* stream);
+
 /* ---- packed compositing: tracers/panoptic_packed_rf_tracer.py:134-205 ------------------------------- */
 /* offsets[r] = first packed index with ridx >= r (ridx ascending), offsets[R] = M. */
 int pag_ray_offsets(const int64_t* ridx, int64_t M, int64_t R, int64_t* offsets, void* stream);

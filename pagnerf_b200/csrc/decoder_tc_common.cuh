@@ -1,0 +1,229 @@
+// Helpers shared by the tensor-core decoder kernels (decoder_tc.cu, decoder_tc_fused.cu).
+#pragma once
+#include "decoder_common.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+
+#define TCH TC_CHUNK_BYTES
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// features [8c, 8c+8) of row `row` into chunk c of a tile image
+__device__ __forceinline__ void tile_store8(uint8_t* tile, int c, int row, const float* v) {
+    uint4 u;
+    u.x = pack_h2(v[0], v[1]); u.y = pack_h2(v[2], v[3]); u.z = pack_h2(v[4], v[5]); u.w = pack_h2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + c * TCH + row * 16) = u;
+}
+// fp16 image of W[OUT][IN] (global fp32, torch Linear layout): [(in/8)][OUTP][8], zero padded
+__device__ __forceinline__ void stage_w16(__half* img, const float* __restrict__ W, int OUT, int IN, int OUTP, int INP) {
+    const int n = (INP / 8) * OUTP * 8;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int e = i & 7, r = (i >> 3) % OUTP, c = (i >> 3) / OUTP, in = c * 8 + e;
+        img[i] = (r < OUT && in < IN) ? __float2half_rn(__ldg(W + (size_t)r * IN + in)) : __float2half_rn(0.f);
+    }
+}
+__device__ __forceinline__ void stage_b32(float* dst, const float* __restrict__ b, int n, int np) {
+    for (int i = threadIdx.x; i < np; i += blockDim.x) dst[i] = (i < n) ? __ldg(b + i) : 0.f;
+}
+// generic-proxy smem writes + TMEM reads of all threads ordered before the MMAs the elected thread issues next
+__device__ __forceinline__ void sync_to_mma() {
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+}
+struct MmaBar {
+    uint64_t* bar;
+    uint32_t parity;
+    __device__ __forceinline__ void commit() { umma_commit(bar); }
+    __device__ __forceinline__ void wait() { mbar_wait(bar, parity); parity ^= 1; tc_fence_after(); }
+};
+
+// accumulator row (64 columns) -> +bias -> ReLU -> fp16 tile; returns the activity mask
+__device__ __forceinline__ uint64_t epi_relu64(uint32_t taddr, const float* __restrict__ bias, uint8_t* tile, int row) {
+    uint64_t mask = 0;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            v[i] = fmaxf(v[i] + bias[c0 + i], 0.f);
+            mask |= (v[i] > 0.f) ? (1ull << (c0 + i)) : 0ull;
+        }
+        tile_store8(tile, c0 / 8, row, v);
+        tile_store8(tile, c0 / 8 + 1, row, v + 8);
+    }
+    return mask;
+}
+
+// warp reduce-scatter of N per-lane values (N = 64): afterwards v[0], v[1] hold the warp sums of
+// features f0 + {0,1}, f0 = 32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0 of the lane id bits
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane) {
+#pragma unroll
+    for (int o = 16, n = N / 2; o >= 1; o >>= 1, n >>= 1) {
+        const bool hi = lane & o;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = hi ? v[i] : v[i + n];
+            const float keep = hi ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+}
+__device__ __forceinline__ int scatter_base(int lane, int n) {  // first feature owned by `lane` after the scatter of n values
+    int f = 0, h = n / 2;
+    for (int o = 16; o >= 1; o >>= 1, h >>= 1) f += (lane & o) ? h : 0;
+    return f;
+}
+// masked hidden gradient: accumulator row (64 cols) * relu mask -> fp16 tile, bias-grad partial sums
+__device__ __forceinline__ void epi_grad64(uint32_t taddr, uint64_t mask, uint8_t* tile, int row, int lane, float (&dbacc)[2]) {
+    float g[64];
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) g[c0 + i] = ((mask >> (c0 + i)) & 1ull) ? v[i] : 0.f;
+        tile_store8(tile, c0 / 8, row, g + c0);
+        tile_store8(tile, c0 / 8 + 1, row, g + c0 + 8);
+    }
+    warp_reduce_scatter<64>(g, lane);
+    dbacc[0] += g[0]; dbacc[1] += g[1];
+}
+// 16-feature gradient row -> tile (2 chunks) + bias partial (lane keeps 1 value when lane is even after 4 scatter steps)
+__device__ __forceinline__ void grad16_store(float (&g)[16], uint8_t* tile, int row, int lane, float& dbacc) {
+    tile_store8(tile, 0, row, g);
+    tile_store8(tile, 1, row, g + 8);
+#pragma unroll
+    for (int o = 16, n = 8; o >= 2; o >>= 1, n >>= 1) {
+        const bool hi = lane & o;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = hi ? g[i] : g[i + n];
+            const float keep = hi ? g[i + n] : g[i];
+            g[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    dbacc += g[0] + __shfl_xor_sync(0xffffffffu, g[0], 1);  // feature 8*b4 + 4*b3 + 2*b2 + b1 (both lanes of a pair hold it)
+}
+// flush a dW accumulator [rows(lane) x cols] from TMEM to global with atomics
+__device__ __forceinline__ void flush_dw(uint32_t taddr, float* __restrict__ gW, int row, int OUT, int IN, int ncols, float inv_scale) {
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (row < OUT) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < IN) red_add_f32(gW + (size_t)row * IN + c0 + i, v[i] * inv_scale);
+        }
+    }
+}
+
+// this thread's feature row -> X tile (float4 global loads: IN is a multiple of 4 for every supported grid)
+__device__ __forceinline__ void stage_x(uint8_t* tile, int row, const float* __restrict__ a, const float* __restrict__ b,
+                                        const float* __restrict__ lodw, int IN, int nchunks, int64_t m) {
+    const float4* a4 = reinterpret_cast<const float4*>(a + m * IN);
+    const float4* b4 = b ? reinterpret_cast<const float4*>(b + m * IN) : nullptr;
+    const float4* w4 = lodw ? reinterpret_cast<const float4*>(lodw) : nullptr;
+    for (int c = 0; c < nchunks; ++c) {
+        float v[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int q = 2 * c + h;   // float4 index
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * q < IN) {
+                x = __ldg(a4 + q);
+                if (b4) { const float4 y = __ldg(b4 + q); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+                if (w4) { const float4 w = __ldg(w4 + q); x.x *= w.x; x.y *= w.y; x.z *= w.z; x.w *= w.w; }
+            }
+            v[4 * h] = x.x; v[4 * h + 1] = x.y; v[4 * h + 2] = x.z; v[4 * h + 3] = x.w;
+        }
+        tile_store8(tile, c, row, v);
+    }
+}
+// dX row (TMEM) -> global, float4 stores
+__device__ __forceinline__ void store_dx(uint32_t taddr, float* __restrict__ dst, const float* __restrict__ lodw, int IN,
+                                         int INP, float inv_scale, bool valid) {
+    for (int c0 = 0; c0 < INP; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (c0 + 4 * q < IN) {
+                    float4 w = lodw ? __ldg(reinterpret_cast<const float4*>(lodw + c0) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    float4 o = make_float4(v[4 * q] * inv_scale * w.x, v[4 * q + 1] * inv_scale * w.y,
+                                           v[4 * q + 2] * inv_scale * w.z, v[4 * q + 3] * inv_scale * w.w);
+                    reinterpret_cast<float4*>(dst + c0)[q] = o;
+                }
+            }
+        }
+    }
+}
+// color-decoder input row [y16 | PE(-d) | 0 pad] -> 6 chunks
+__device__ __forceinline__ void stage_cin(uint8_t* tile, int row, const float (&y)[16], const float* pe) {
+    float v[48];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = y[k];
+#pragma unroll
+    for (int k = 0; k < PE_DIM; ++k) v[16 + k] = pe[k];
+#pragma unroll
+    for (int k = CIN; k < 48; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) tile_store8(tile, c, row, v + 8 * c);
+}
+
+struct PanTcLayout {
+    int INP, nXc, CsP, CiP, nGi;
+    int oGs, oX, oHs, oH1, oH2, oGi, oWs1, oWs2, oWi1, oWi2, oWi3, oBias, oStage, total;
+};
+__host__ __device__ inline PanTcLayout pan_tc_layout(int IN, int Cs, int Ci, bool bwd) {
+    PanTcLayout l;
+    l.INP = (IN + 15) & ~15; l.nXc = l.INP / 8;
+    l.CsP = Cs > 0 ? ((Cs + 15) & ~15) : 16;
+    l.CiP = Ci > 0 ? ((Ci + 15) & ~15) : 16;
+    l.nGi = l.CiP / 8;
+    int o = 0;
+    l.oGs = o; o += bwd ? 2 * TCH : 0;
+    l.oX = o; o += 8 * TCH;
+    l.oHs = o; o += 8 * TCH;
+    l.oH1 = o; o += 8 * TCH;
+    l.oH2 = o; o += bwd ? 8 * TCH : 0;
+    l.oGi = o; o += bwd ? l.nGi * TCH : 0;
+    l.oWs1 = o; o += l.nXc * 64 * 16;
+    l.oWs2 = o; o += 8 * l.CsP * 16;
+    l.oWi1 = o; o += l.nXc * 64 * 16;
+    l.oWi2 = o; o += 8 * 64 * 16;
+    l.oWi3 = o; o += 8 * l.CiP * 16;
+    l.oBias = o; o += (64 + l.CsP + 64 + 64 + l.CiP) * 4;
+    o = (o + 15) & ~15;
+    l.oStage = o; o += bwd ? 4 * 2 * 32 * 33 * 4 : 0;   // per-warp transpose buffers for the coalesced prob / grad loads
+    if (bwd) {  // MN-major A operands read 16 chunks from their base (the second dWi3 block starts 16 chunks into Gi)
+        const int need = l.oGi + (l.nGi > 16 ? 32 : 16) * TCH;
+        if (o < need) o = need;
+    }
+    l.total = o;
+    return l;
+}
+__device__ __forceinline__ void pan_tc_stage(uint8_t* sm, const PanTcLayout& l, const PanParams& p, int IN, int Cs, int Ci) {
+    float* b = reinterpret_cast<float*>(sm + l.oBias);
+    if (Cs > 0) {
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWs1), p.Ws1, 64, IN, 64, l.INP);
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWs2), p.Ws2, Cs, 64, l.CsP, 64);
+        stage_b32(b, p.bs1, 64, 64); stage_b32(b + 64, p.bs2, Cs, l.CsP);
+    }
+    if (Ci > 0) {
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWi1), p.Wi1, 64, IN, 64, l.INP);
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWi2), p.Wi2, 64, 64, 64, 64);
+        stage_w16(reinterpret_cast<__half*>(sm + l.oWi3), p.Wi3, Ci, 64, l.CiP, 64);
+        stage_b32(b + 64 + l.CsP, p.bi1, 64, 64); stage_b32(b + 128 + l.CsP, p.bi2, 64, 64);
+        stage_b32(b + 192 + l.CsP, p.bi3, Ci, l.CiP);
+    }
+}
+

@@ -1,0 +1,533 @@
+// Panoptic heads FUSED with their compositing (tensor-core path, training mode).
+//
+// In the reference the semantic / instance decoders materialise softmax probabilities [M,6] / [M,200]
+// (pc_nerf/panoptic_delta_nef.py:238-257) which the tracer multiplies by the detached weights and segment-sums
+// per ray (tracers/panoptic_packed_rf_tracer.py:178-205).  At 380 k samples the [M,200] fp32 tensor alone is
+// 304 MB written + read in forward and twice that in backward -- more traffic than everything else in the step.
+// Here the probabilities never leave the SM:
+//   forward : logits (tcgen05, TMEM) -> softmax (thread per sample) -> per-warp transpose -> lanes = classes walk
+//             the warp's 32 samples, accumulate c_s * p[s][j] (c_s = alpha_ray * w_s, both detached) and flush one
+//             coalesced red.add per ray segment into out[N, C];
+//   backward: logits recomputed (tcgen05), per-ray gradients g_out[N, C] (13 MB, L2 resident) gathered per
+//             sample -- the lanes of a warp mostly share the ray, so the gathers are broadcasts --,
+//             d logits = c_s * p * (g - <p, g>) / T, then the usual dX / dW chain of decoder_tc.cu.
+// Output convention: out[ray] = alpha_p * sum_s w_p[s] * f[s]  (alpha_p, w_p detached): only the decoders and the
+// delta grid receive gradient, exactly as in the reference.
+#include "decoder_tc_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+struct PanCompFwdLayout {
+    int INP, nXc, CsP, CiP;
+    int oX, oT1, oT2, oStage, oCR, oWs1, oWs2, oWi1, oWi2, oWi3, oBias, total;
+};
+__host__ __device__ inline PanCompFwdLayout pan_comp_fwd_layout(int IN, int Cs, int Ci) {
+    PanCompFwdLayout l;
+    l.INP = (IN + 15) & ~15; l.nXc = l.INP / 8;
+    l.CsP = 16; l.CiP = Ci > 0 ? ((Ci + 15) & ~15) : 16;
+    int o = 0;
+    l.oX = o; o += l.nXc * TCH;
+    l.oT1 = o; o += 8 * TCH;
+    l.oT2 = o; o += 8 * TCH;
+    l.oStage = o; o += 4 * 32 * 33 * 4;
+    l.oCR = o; o += 4 * 32 * 8;          // per warp: c[32] floats + ray[32] ints
+    o = (o + 15) & ~15;
+    l.oWs1 = o; o += l.nXc * 64 * 16;
+    l.oWs2 = o; o += 8 * l.CsP * 16;
+    l.oWi1 = o; o += l.nXc * 64 * 16;
+    l.oWi2 = o; o += 8 * 64 * 16;
+    l.oWi3 = o; o += 8 * l.CiP * 16;
+    l.oBias = o; o += (64 + l.CsP + 64 + 64 + l.CiP) * 4;
+    l.total = o;
+    return l;
+}
+
+// softmax of the thread's logits row (TMEM) and weighted segment-sum over the warp's rows into out[N, C]
+__device__ __forceinline__ void epi_head_comp(uint32_t taddr, const float* __restrict__ bias, int C, int CP, bool softmax,
+                                              float inv_temp, float* __restrict__ out, float* stage,
+                                              const float* __restrict__ wc, const int* __restrict__ wr, int nrows, int lane) {
+    float mx = -INFINITY, sum = 0.f;
+    if (softmax) {
+        for (int c0 = 0; c0 < CP; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < C) {
+                    const float z = (v[i] + bias[c0 + i]) * inv_temp;
+                    const float nm = fmaxf(mx, z);
+                    sum = sum * __expf(mx - nm) + __expf(z - nm);
+                    mx = nm;
+                }
+        }
+    }
+    const float inv = softmax ? 1.f / sum : 1.f;
+    for (int c0 = 0; c0 < CP; c0 += 32) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (c0 + 16 * h < CP) {
+                float v[16];
+                tmem_ld16(taddr + c0 + 16 * h, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int j = c0 + 16 * h + i;
+                    const float z = (v[i] + (j < C ? bias[j] : 0.f)) * inv_temp;
+                    stage[lane * 33 + 16 * h + i] = softmax ? __expf(z - mx) * inv : z;
+                }
+            }
+        }
+        __syncwarp();
+        if (c0 + lane < C && nrows > 0) {
+            float acc = 0.f;
+            int cur = wr[0];
+            for (int r = 0; r < nrows; ++r) {
+                const int ray = wr[r];
+                if (ray != cur) {
+                    red_add_f32(out + (int64_t)cur * C + c0 + lane, acc);
+                    acc = 0.f;
+                    cur = ray;
+                }
+                acc = fmaf(wc[r], stage[r * 33 + lane], acc);
+            }
+            red_add_f32(out + (int64_t)cur * C + c0 + lane, acc);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) pan_comp_fwd_kernel(
+    const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw, int64_t M, int IN,
+    PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
+    const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
+    float* __restrict__ out_sem, float* __restrict__ out_inst) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint64_t bar_s;
+    __shared__ uint32_t tmem_s;
+    const PanCompFwdLayout l = pan_comp_fwd_layout(IN, Cs, Ci);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {   // weights (same images as decoder_tc.cu)
+        float* b = reinterpret_cast<float*>(sm + l.oBias);
+        if (Cs > 0) {
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWs1), p.Ws1, 64, IN, 64, l.INP);
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWs2), p.Ws2, Cs, 64, l.CsP, 64);
+            stage_b32(b, p.bs1, 64, 64); stage_b32(b + 64, p.bs2, Cs, l.CsP);
+        }
+        if (Ci > 0) {
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWi1), p.Wi1, 64, IN, 64, l.INP);
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWi2), p.Wi2, 64, 64, 64, 64);
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWi3), p.Wi3, Ci, 64, l.CiP, 64);
+            stage_b32(b + 64 + l.CsP, p.bi1, 64, 64); stage_b32(b + 128 + l.CsP, p.bi2, 64, 64);
+            stage_b32(b + 192 + l.CsP, p.bi3, Ci, l.CiP);
+        }
+    }
+    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_s, 256);
+    sync_to_mma();
+    tc_fence_after();
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    MmaBar mb{&bar_s, 0};
+    const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
+    const float *bs1 = bias, *bs2 = bias + 64, *bi1 = bias + 64 + l.CsP, *bi2 = bi1 + 64, *bi3 = bi2 + 64;
+    uint8_t *X = sm + l.oX, *T1 = sm + l.oT1, *T2 = sm + l.oT2;
+    const uint32_t aX = smem_u32(X), aT1 = smem_u32(T1), aT2 = smem_u32(T2);
+    const uint32_t ws1 = smem_u32(sm + l.oWs1), ws2 = smem_u32(sm + l.oWs2), wi1 = smem_u32(sm + l.oWi1),
+                   wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
+    const uint32_t semcol = (Ci > 0) ? (uint32_t)(l.CiP > 64 ? l.CiP : 64) : 128u;
+    float* stage = reinterpret_cast<float*>(sm + l.oStage) + warp * (32 * 33);
+    float* wc = reinterpret_cast<float*>(sm + l.oCR) + warp * 64;
+    int* wr = reinterpret_cast<int*>(wc + 32);
+    const int64_t ntiles = (M + 127) / 128;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t m = tile * 128 + tid;
+        const bool valid = m < M;
+        const int64_t mm = valid ? m : M - 1;
+        stage_x(X, tid, feats, dfeats, lodw, IN, l.nXc, mm);
+        {   // compositing coefficients of this warp's rows
+            const int64_t ray = ridx[mm];
+            wr[lane] = (int)ray;
+            wc[lane] = valid ? __ldg(alpha + ray) * __ldg(w + mm) : 0.f;
+        }
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (Cs > 0) mma16_fwd(tm, aX, ws1, 64, 64, l.INP, false);
+            if (Ci > 0) mma16_fwd(tm + 64, aX, wi1, 64, 64, l.INP, false);
+            mb.commit();
+        }
+        mb.wait();
+        if (Cs > 0) epi_relu64(tl, bs1, T1, tid);
+        if (Ci > 0) epi_relu64(tl + 64, bi1, T2, tid);
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (Cs > 0) mma16_fwd(tm + semcol, aT1, ws2, l.CsP, l.CsP, 64, false);
+            if (Ci > 0) mma16_fwd(tm, aT2, wi2, 64, 64, 64, false);
+            mb.commit();
+        }
+        mb.wait();
+        const int64_t rows_left = M - (tile * 128 + warp * 32);
+        const int nrows = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
+        if (Ci > 0) {
+            epi_relu64(tl, bi2, T1, tid);
+            sync_to_mma();
+            if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT1, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
+            mb.wait();
+            epi_head_comp(tl, bi3, Ci, l.CiP, inst_softmax, inst_inv_temp, out_inst, stage, wc, wr, nrows, lane);
+        }
+        if (Cs > 0) epi_head_comp(tl + semcol, bs2, Cs, l.CsP, sem_softmax, 1.f, out_sem, stage, wc, wr, nrows, lane);
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+// TMEM columns (512): the instance logits [0,208) alias the scratch accumulators S0 / S1
+#define PCB_S0 0
+#define PCB_S1 64
+#define PCB_SEMLOG 128   // 16 columns, consumed before the instance logits are produced
+#define PCB_DWS1 208     // [64 x <=48]
+#define PCB_DWS2T 256    // [64(h) x 16(classes)]  transposed: 16 columns instead of 64
+#define PCB_DWI1 272     // [64 x <=48]
+#define PCB_DWI2 320     // [64 x 64]
+#define PCB_DWI3 384     // [Ci(<=208) x 64] as two 128-row blocks
+
+struct PanCompBwdLayout {
+    int INP, nXc, CsP, CiP, nGi;
+    int oGs, oX, oHs, oH1, oH2, oGi, oWs1, oWs2, oWi1, oWi2, oWi3, oBias, total;
+};
+__host__ __device__ inline PanCompBwdLayout pan_comp_bwd_layout(int IN, int Cs, int Ci) {
+    PanCompBwdLayout l;
+    l.INP = (IN + 15) & ~15; l.nXc = l.INP / 8;
+    l.CsP = 16; l.CiP = Ci > 0 ? ((Ci + 15) & ~15) : 16; l.nGi = l.CiP / 8;
+    int o = 0;
+    l.oGs = o; o += 2 * TCH;
+    l.oX = o; o += l.nXc * TCH;
+    l.oHs = o; o += 8 * TCH;
+    l.oH1 = o; o += 8 * TCH;
+    l.oH2 = o; o += 8 * TCH;
+    l.oGi = o; o += l.nGi * TCH;
+    l.oWs1 = o; o += l.nXc * 64 * 16;
+    l.oWs2 = o; o += 8 * l.CsP * 16;
+    l.oWi1 = o; o += l.nXc * 64 * 16;
+    l.oWi2 = o; o += 8 * 64 * 16;
+    l.oWi3 = o; o += 8 * l.CiP * 16;
+    l.oBias = o; o += (64 + l.CsP + 64 + 64 + l.CiP) * 4;
+    const int need = l.oGi + (l.nGi > 16 ? 32 : 16) * TCH;   // MN-major A operands read 16 chunks from their base
+    if (o < need) o = need;
+    l.total = o;
+    return l;
+}
+
+// transposed accumulator [lanes = input features k][cols = classes j] -> gW[j][k]
+__device__ __forceinline__ void flush_dw_T(uint32_t taddr, float* __restrict__ gW, int k, int K, int C, float inv_scale) {
+    float v[16];
+    tmem_ld16(taddr, v);
+    if (k < K) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < C) red_add_f32(gW + (size_t)j * K + k, v[j] * inv_scale);
+    }
+}
+
+__global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
+    const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw, int64_t M, int IN,
+    PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
+    const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
+    const float* __restrict__ g_sem, const float* __restrict__ g_inst, const float* __restrict__ scale_ptr,
+    float* __restrict__ g_panop) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint64_t bar_s;
+    __shared__ uint32_t tmem_s;
+    const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool do_sem = (Cs > 0) && g_sem, do_inst = (Ci > 0) && g_inst;
+    {
+        float* b = reinterpret_cast<float*>(sm + l.oBias);
+        if (do_sem) {
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWs1), p.Ws1, 64, IN, 64, l.INP);
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWs2), p.Ws2, Cs, 64, l.CsP, 64);
+            stage_b32(b, p.bs1, 64, 64); stage_b32(b + 64, p.bs2, Cs, l.CsP);
+        }
+        if (do_inst) {
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWi1), p.Wi1, 64, IN, 64, l.INP);
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWi2), p.Wi2, 64, 64, 64, 64);
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWi3), p.Wi3, Ci, 64, l.CiP, 64);
+            stage_b32(b + 64 + l.CsP, p.bi1, 64, 64); stage_b32(b + 128 + l.CsP, p.bi2, 64, 64);
+            stage_b32(b + 192 + l.CsP, p.bi3, Ci, l.CiP);
+        }
+    }
+    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_s, 512);
+    sync_to_mma();
+    tc_fence_after();
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    MmaBar mb{&bar_s, 0};
+    const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
+    const float *bs1 = bias, *bs2 = bias + 64, *bi1 = bias + 64 + l.CsP, *bi2 = bi1 + 64, *bi3 = bi2 + 64;
+    uint8_t *Gs = sm + l.oGs, *X = sm + l.oX, *Hs = sm + l.oHs, *H1 = sm + l.oH1, *H2 = sm + l.oH2, *Gi = sm + l.oGi;
+    const uint32_t aGs = smem_u32(Gs), aX = smem_u32(X), aHs = smem_u32(Hs), aH1 = smem_u32(H1), aH2 = smem_u32(H2), aGi = smem_u32(Gi);
+    const uint32_t ws1 = smem_u32(sm + l.oWs1), ws2 = smem_u32(sm + l.oWs2), wi1 = smem_u32(sm + l.oWi1),
+                   wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
+    const float scale = scale_ptr ? __ldg(scale_ptr) : 1.f;
+    const float inv_scale = 1.f / scale;
+    float db_s1[2] = {0.f, 0.f}, db_i1[2] = {0.f, 0.f}, db_i2[2] = {0.f, 0.f}, db_s2 = 0.f, db_i3[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) db_i3[i] = 0.f;
+    const int64_t ntiles = (M + 127) / 128;
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
+        const int64_t m = tile * 128 + tid;
+        const bool valid = m < M;
+        const int64_t mm = valid ? m : M - 1;
+        const int64_t ray = ridx[mm];
+        const float cs = valid ? __ldg(alpha + ray) * __ldg(w + mm) * scale : 0.f;   // detached compositing weight x loss scale
+        // ---------------- stage 1: first hidden layers ----------------
+        stage_x(X, tid, feats, dfeats, lodw, IN, l.nXc, mm);
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (do_sem) mma16_fwd(tm + PCB_S0, aX, ws1, 64, 64, l.INP, false);
+            if (do_inst) mma16_fwd(tm + PCB_S1, aX, wi1, 64, 64, l.INP, false);
+            mb.commit();
+        }
+        mb.wait();
+        uint64_t mask_s = 0, mask_1 = 0, mask_2 = 0;
+        if (do_sem) mask_s = epi_relu64(tl + PCB_S0, bs1, Hs, tid);
+        if (do_inst) mask_1 = epi_relu64(tl + PCB_S1, bi1, H1, tid);
+        // ---------------- stage 2: second instance layer + semantic logits ----------------
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (do_inst) mma16_fwd(tm + PCB_S0, aH1, wi2, 64, 64, 64, false);
+            if (do_sem) mma16_fwd(tm + PCB_SEMLOG, aHs, ws2, l.CsP, l.CsP, 64, false);
+            mb.commit();
+        }
+        mb.wait();
+        if (do_inst) mask_2 = epi_relu64(tl + PCB_S0, bi2, H2, tid);
+        if (do_sem) {   // semantic head gradient (<= 16 classes, one pass in registers)
+            float z[16], g[16];
+            tmem_ld16(tl + PCB_SEMLOG, z);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { z[j] += bs2[j]; if (j < Cs) mx = fmaxf(mx, z[j]); }
+            float Z = 0.f, E = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float gj = (j < Cs) ? __ldg(g_sem + ray * Cs + j) : 0.f;
+                const float e = (j < Cs) ? (sem_softmax ? __expf(z[j] - mx) : 1.f) : 0.f;
+                g[j] = gj; z[j] = e;
+                Z += e; E = fmaf(e, gj, E);
+            }
+            const float iz = 1.f / Z, dot = E * iz;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = (j < Cs) ? (sem_softmax ? cs * z[j] * iz * (g[j] - dot) : cs * g[j]) : 0.f;
+            grad16_store(g, Gs, tid, lane, db_s2);
+        }
+        // ---------------- stage 3: instance logits + head gradient ----------------
+        if (do_inst) {
+            sync_to_mma();
+            if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aH2, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
+            mb.wait();
+            const float* grow = g_inst + ray * Ci;
+            float mx = -INFINITY, Z = 0.f, E = 0.f;
+            if (inst_softmax) {
+                for (int c0 = 0; c0 < l.CiP; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(tl + c0, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < Ci) {
+                            const float z = (v[i] + bi3[c0 + i]) * inst_inv_temp;
+                            const float gj = __ldg(grow + c0 + i);
+                            const float nm = fmaxf(mx, z);
+                            const float r = __expf(mx - nm), e = __expf(z - nm);
+                            Z = Z * r + e;
+                            E = E * r + e * gj;
+                            mx = nm;
+                        }
+                }
+            }
+            const float iz = inst_softmax ? 1.f / Z : 1.f, dot = E * iz;
+#pragma unroll
+            for (int c0 = 0; c0 < 224; c0 += 32) {
+                if (c0 < l.CiP) {
+                    float v[32];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float t[16];
+                        if (c0 + 16 * h < l.CiP) tmem_ld16(tl + c0 + 16 * h, t);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int j = c0 + 16 * h + i;
+                            float d = 0.f;
+                            if (j < Ci) {
+                                const float gj = __ldg(grow + j);
+                                if (inst_softmax) {
+                                    const float pj = __expf((t[i] + bi3[j]) * inst_inv_temp - mx) * iz;
+                                    d = cs * pj * (gj - dot) * inst_inv_temp;
+                                } else {
+                                    d = cs * gj * inst_inv_temp;
+                                }
+                            }
+                            v[16 * h + i] = d;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c0 + 8 * c < l.CiP) tile_store8(Gi, c0 / 8 + c, tid, v + 8 * c);
+                    warp_reduce_scatter<32>(v, lane);
+                    db_i3[c0 / 32] += v[0];
+                }
+            }
+        }
+        // ---------------- stage 4: last layers backward ----------------
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (do_inst) {
+                mma16_bwd_weight(tm + PCB_DWI3, aGi, aH2, 64, !first);
+                if (l.CiP > 128) mma16_bwd_weight(tm + PCB_DWI3 + 64, aGi + 16 * TCH, aH2, 64, !first);
+                mma16_bwd_data(tm + PCB_S1, aGi, wi3, 64, l.CiP, l.CiP, false);
+            }
+            if (do_sem) {
+                mma16_bwd_weight(tm + PCB_DWS2T, aHs, aGs, 16, !first);      // transposed: [h x classes]
+                mma16_bwd_data(tm + PCB_S0, aGs, ws2, 64, l.CsP, l.CsP, false);
+            }
+            mb.commit();
+        }
+        mb.wait();
+        if (do_inst) epi_grad64(tl + PCB_S1, mask_2, H2, tid, lane, db_i2);    // Gi2 overwrites H2
+        if (do_sem) epi_grad64(tl + PCB_S0, mask_s, Hs, tid, lane, db_s1);     // Gs1 overwrites Hs
+        // ---------------- stage 5 ----------------
+        sync_to_mma();
+        if (tid == 0) {
+            tc_fence_after();
+            if (do_inst) {
+                mma16_bwd_weight(tm + PCB_DWI2, aH2, aH1, 64, !first);
+                mma16_bwd_data(tm + PCB_S1, aH2, wi2, 64, 64, 64, false);
+            }
+            if (do_sem) {
+                mma16_bwd_weight(tm + PCB_DWS1, aHs, aX, l.INP, !first);
+                if (g_panop) mma16_bwd_data(tm + PCB_S0, aHs, ws1, l.INP, 64, 64, false);
+            }
+            mb.commit();
+        }
+        mb.wait();
+        // ---------------- stage 6 ----------------
+        if (do_inst) {
+            epi_grad64(tl + PCB_S1, mask_1, H1, tid, lane, db_i1);             // Gi1 overwrites H1
+            sync_to_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                mma16_bwd_weight(tm + PCB_DWI1, aH1, aX, l.INP, !first);
+                if (g_panop) mma16_bwd_data(tm + PCB_S0, aH1, wi1, l.INP, 64, 64, do_sem);
+                mb.commit();
+            }
+            mb.wait();
+        }
+        if (g_panop) store_dx(tl + PCB_S0, g_panop + mm * IN, lodw, IN, l.INP, inv_scale, valid);
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (!first) {
+        tc_fence_after();
+        const int f2 = scatter_base(lane, 64);
+        if (do_sem) {
+            flush_dw(tl + PCB_DWS1, p.gWs1, tid, 64, IN, l.INP, inv_scale);
+            flush_dw_T(tl + PCB_DWS2T, p.gWs2, tid, 64, Cs, inv_scale);
+            red_add_f32(p.gbs1 + f2, db_s1[0] * inv_scale); red_add_f32(p.gbs1 + f2 + 1, db_s1[1] * inv_scale);
+            const int f1 = scatter_base(lane, 32) >> 1;
+            if (!(lane & 1) && f1 < Cs) red_add_f32(p.gbs2 + f1, db_s2 * inv_scale);
+        }
+        if (do_inst) {
+            flush_dw(tl + PCB_DWI1, p.gWi1, tid, 64, IN, l.INP, inv_scale);
+            flush_dw(tl + PCB_DWI2, p.gWi2, tid, 64, 64, 64, inv_scale);
+            flush_dw(tl + PCB_DWI3, p.gWi3, tid, Ci, 64, 64, inv_scale);
+            if (l.CiP > 128) flush_dw(tl + PCB_DWI3 + 64, p.gWi3 + (size_t)128 * 64, tid, Ci - 128, 64, 64, inv_scale);
+            red_add_f32(p.gbi1 + f2, db_i1[0] * inv_scale); red_add_f32(p.gbi1 + f2 + 1, db_i1[1] * inv_scale);
+            red_add_f32(p.gbi2 + f2, db_i2[0] * inv_scale); red_add_f32(p.gbi2 + f2 + 1, db_i2[1] * inv_scale);
+#pragma unroll
+            for (int c = 0; c < 7; ++c)
+                if (c * 32 < l.CiP && c * 32 + lane < Ci) red_add_f32(p.gbi3 + c * 32 + lane, db_i3[c] * inv_scale);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int fused_num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+static void fill_pan_f(PanParams& p, const float* const* w, float* const* g) {
+    p.Ws1 = w[0]; p.bs1 = w[1]; p.Ws2 = w[2]; p.bs2 = w[3]; p.Wi1 = w[4]; p.bi1 = w[5]; p.Wi2 = w[6]; p.bi2 = w[7]; p.Wi3 = w[8]; p.bi3 = w[9];
+    if (g) { p.gWs1 = g[0]; p.gbs1 = g[1]; p.gWs2 = g[2]; p.gbs2 = g[3]; p.gWi1 = g[4]; p.gbi1 = g[5]; p.gWi2 = g[6]; p.gbi2 = g[7]; p.gWi3 = g[8]; p.gbi3 = g[9]; }
+}
+static bool fused_shape_ok(int IN, int hidden, int Cs, int Ci) {
+    return hidden == H && IN >= 4 && IN <= 48 && !(IN & 3) && Cs >= 0 && Cs <= 16 && Ci >= 0 && Ci <= 208;
+}
+
+extern "C" {
+
+// out_sem[N,Cs] / out_inst[N,Ci] must be zero-initialised by the caller; results are accumulated with red.add.
+int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                             const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
+                             float inst_temperature, const float* w, const float* alpha, const int64_t* ridx,
+                             float* out_sem, float* out_inst, void* stream) {
+    if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
+    if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
+    PanParams p{};
+    fill_pan_f(p, weights, nullptr);
+    const PanCompFwdLayout l = pan_comp_fwd_layout(IN, Cs, Ci);
+    if (l.total > 227 * 1024) return PAG_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(pan_comp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
+    if (e != cudaSuccess) return (int)e;
+    const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
+    const int64_t tiles = (M + 127) / 128;
+    const int64_t cap = 2 * (int64_t)fused_num_sms();
+    pan_comp_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, out_sem, out_inst);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// g_sem[N,Cs] / g_inst[N,Ci]: per-RAY gradients of the composited outputs (nullable); g_panop[M,IN] nullable.
+int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                             const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
+                             int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
+                             const int64_t* ridx, const float* g_sem, const float* g_inst, const float* grad_scale,
+                             float* g_panop, void* stream) {
+    if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
+    if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
+    PanParams p{};
+    fill_pan_f(p, weights, grads);
+    const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci);
+    if (l.total > 227 * 1024) return PAG_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(pan_comp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
+    if (e != cudaSuccess) return (int)e;
+    const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
+    const int64_t tiles = (M + 127) / 128;
+    const int64_t cap = fused_num_sms();
+    pan_comp_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, grad_scale, g_panop);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+}  // extern "C"

@@ -376,12 +376,12 @@ class CompositeFn(Function):
              int(bool(bg_white)), ptr(w), ptr(T), ptr(alpha), ptr(hit), ptr(rgb_o), ptr(rgbsum), ptr(dep_o), ptr(sem_o), ptr(inst_o))
         ctx.save_for_backward(sg, dl, dp, c, offsets, w, T, alpha, rgbsum)
         ctx.cfg = (int(bool(bg_white)), Cs, Ci, sigma.shape, None if rgb is None else rgb.shape)
-        ctx.mark_non_differentiable(hit)
-        return alpha, hit, rgb_o, dep_o, sem_o, inst_o
+        ctx.mark_non_differentiable(hit, w)
+        return alpha, hit, rgb_o, dep_o, sem_o, inst_o, w
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g_alpha, g_hit, g_rgb, g_depth, g_sem, g_inst):
+    def backward(ctx, g_alpha, g_hit, g_rgb, g_depth, g_sem, g_inst, g_w):
         sg, dl, dp, c, offsets, w, T, alpha, rgbsum = ctx.saved_tensors
         bgw, Cs, Ci, sig_shape, rgb_shape = ctx.cfg
         R, M, dev = offsets.shape[0] - 1, sg.shape[0], sg.device
@@ -401,7 +401,49 @@ class CompositeFn(Function):
 
 
 def composite(sigma, deltas, depths, rgb, sem, inst, offsets, bg_white=True):
+    """-> alpha [R,1], hit [R], rgb [R,3], depth [R,1], sem [R,Cs], inst [R,Ci], w [M] (detached weights)."""
     return CompositeFn.apply(sigma, deltas, depths, rgb, sem, inst, offsets, bg_white)
+
+
+class PanCompositeFn(Function):
+    """Semantic + instance heads fused with their (detached-weight) compositing: per-ray outputs [N,Cs], [N,Ci].
+    Tensor-core kernels only (training mode); csrc/decoder_tc_fused.cu."""
+
+    @staticmethod
+    def forward(ctx, feats, dfeats, lodw, w, alpha, ridx, N, Cs, Ci, sem_softmax, inst_softmax, inst_temperature, *weights):
+        _chk(feats, dfeats, w, alpha, ridx, *weights)
+        f, df = _f32(feats), _f32(dfeats)
+        M, IN = f.shape
+        wt = [_f32(x) for x in weights]
+        lw = _f32(lodw)
+        w_, a_ = _f32(w).reshape(-1), _f32(alpha).reshape(-1)
+        r_ = ridx.to(torch.int64).contiguous()
+        sem = torch.zeros(N, Cs, dtype=torch.float32, device=f.device) if Cs else None
+        inst = torch.zeros(N, Ci, dtype=torch.float32, device=f.device) if Ci else None
+        call("pag_pan_composite_fwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), HIDDEN, int(Cs), int(Ci),
+             int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature), ptr(w_), ptr(a_), ptr(r_), ptr(sem), ptr(inst))
+        ctx.save_for_backward(f, df, lw, w_, a_, r_, *wt)
+        ctx.cfg = (int(Cs), int(Ci), int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature))
+        return sem, inst
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_sem, g_inst):
+        f, df, lw, w_, a_, r_, *wt = ctx.saved_tensors
+        Cs, Ci, ss, is_, it = ctx.cfg
+        M, IN = f.shape
+        gs = _f32(g_sem) if (g_sem is not None and Cs) else None
+        gi = _f32(g_inst) if (g_inst is not None and Ci) else None
+        grads = [torch.zeros_like(x) for x in wt]
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gp = torch.empty_like(f) if need else None
+        if gs is not None or gi is not None:
+            call("pag_pan_composite_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), ptr_array(grads), HIDDEN, Cs, Ci,
+                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), ptr(gs), ptr(gi), ptr(grad_scale(gs, gi)), ptr(gp))
+        elif gp is not None:
+            gp.zero_()
+        return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
+                None, None, None, None, None, None, None, None, None, None, *grads)
 
 
 # ---- kaolin.render.spc compatible pieces (used by callers that integrate by hand) -----------------

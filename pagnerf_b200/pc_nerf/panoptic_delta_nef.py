@@ -38,6 +38,20 @@ class PanopticDeltaNeF(PanopticNeF):
     def register_forward_functions(self):
         self._register_forward_function(self.rgb_semantics, ["density", "rgb", "semantics", "inst_embedding"])
 
+    def _panoptic_inputs(self, feats, coords, lod_idx):
+        pft = self.panoptic_features_type
+        feats_detached = feats.detach()          # :214
+        if pft in ['delta', 'separate'] or pft is None:
+            delta_feats = self._encode(self.delta_grid, coords.detach(), lod_idx)   # coords.detach(): :215
+        if pft == 'delta' or pft is None:
+            return feats_detached, delta_feats    # panop = feats.detach() + delta (:226)
+        if pft == 'separate':
+            return delta_feats, None
+        if pft == 'appearance':
+            return feats_detached, None
+        raise NotImplementedError(f'Panoptic feature type "{pft}" is not served by the fused decoders '
+                                  '(pos_encoding / position change the decoder input width)')
+
     def rgb_semantics(self, coords, ray_d, compute_channels, pidx=None, lod_idx=None):
         out_dict = {}
         if not compute_channels:
@@ -56,20 +70,7 @@ class PanopticDeltaNeF(PanopticNeF):
             out_dict['rgb'] = rgb.reshape(batch, num_samples, 3)
         want_sem, want_inst = 'semantics' in compute_channels, 'inst_embedding' in compute_channels
         if want_sem or want_inst:
-            feats_detached = feats.detach()          # :214
-            coords_detached = coords.detach()        # :215
-            pft = self.panoptic_features_type
-            if pft in ['delta', 'separate'] or pft is None:
-                delta_feats = self._encode(self.delta_grid, coords_detached, lod_idx)
-            if pft == 'delta' or pft is None:
-                a, b = feats_detached, delta_feats    # panop = feats.detach() + delta (:226)
-            elif pft == 'separate':
-                a, b = delta_feats, None
-            elif pft == 'appearance':
-                a, b = feats_detached, None
-            else:
-                raise NotImplementedError(f'Panoptic feature type "{pft}" is not served by the fused decoders '
-                                          '(pos_encoding / position change the decoder input width)')
+            a, b = self._panoptic_inputs(feats, coords, lod_idx)
             sem, inst = self._pan(a, b, want_sem, want_inst, self.inst_soft_temperature)
             if want_sem:
                 out_dict['semantics'] = sem

@@ -198,6 +198,52 @@ class PanopticNeF(BaseNeuralField):
             inst = F.softmax(inst, dim=-1) if self.inst_softmax else inst
         return sem, inst
 
+    # ---- fused decode + composite (used by PanopticPackedRFTracer.trace in training mode) --------------------
+    def _panoptic_inputs(self, feats, coords, lod_idx):
+        """(a, b): the panoptic heads read (a + b) * lod_weights.  Base field: the (detached) colour features."""
+        return (feats.detach() if (self.sem_detach and self.inst_detach) else feats), None
+
+    def fused_panoptic_ok(self, channels):
+        """Can the semantic / instance heads be fused with their compositing (csrc/decoder_tc_fused.cu)?"""
+        want = [c for c in ('semantics', 'inst_embedding') if c in channels]
+        if not want or not self._use_tc():
+            return False
+        plain = not (self.sem_sigmoid or self.sem_normalize or self.inst_sigmoid or self.inst_normalize or self.inst_direct_pos)
+        det = self.sem_detach and self.inst_detach
+        shapes = (self.effective_feature_dim <= 48 and self.effective_feature_dim % 4 == 0 and self.num_classes <= 16
+                  and self.num_instances <= 208 and self.multiscale_type == 'cat')
+        return plain and det and shapes and self.panoptic_features_type in (None, 'delta', 'separate', 'appearance')
+
+    def trace_composited(self, coords, ray_d, ridx_rows, deltas, depths, offsets, num_rays, channels, bg_white, lod_idx=None):
+        """Decode + composite in one pass: per-ray dict(alpha, hit, rgb, depth, semantics, inst_embedding).
+        The panoptic probabilities are composited inside the decoder kernel and never materialised."""
+        if lod_idx is None:
+            lod_idx = len(self.grid.active_lods) - 1
+        batch, num_samples, _ = coords.shape
+        feats = self._encode(self.grid, coords, lod_idx)
+        sigma, rgb = self._dc(feats, ray_d, num_samples, 'rgb' in channels)
+        alpha, hit, rgb_o, dep_o, _, _, w = ops.composite(sigma, deltas, depths if 'depth' in channels else None, rgb,
+                                                           None, None, offsets, bg_white)
+        out = {'alpha': alpha, 'hit': hit, 'density': sigma}
+        if 'rgb' in channels:
+            out['rgb'] = rgb_o
+        if 'depth' in channels:
+            out['depth'] = dep_o
+        want_sem, want_inst = 'semantics' in channels, 'inst_embedding' in channels
+        if want_sem or want_inst:
+            a, b = self._panoptic_inputs(feats, coords, lod_idx)
+            wts = _decoder_tensors(self.decoder_semantics, 1) + _decoder_tensors(self.decoder_inst, 2)
+            lodw = self.lod_weights.to(feats.device)
+            sem_o, inst_o = ops.PanCompositeFn.apply(
+                a, b, lodw, w, alpha.detach(), ridx_rows, num_rays, self.num_classes if want_sem else 0,
+                self.num_instances if want_inst else 0, bool(self.sem_softmax), bool(self.inst_softmax),
+                float(getattr(self, 'inst_soft_temperature', 0.0)), *wts)
+            if want_sem:
+                out['semantics'] = sem_o
+            if want_inst:
+                out['inst_embedding'] = inst_o
+        return out
+
     def rgb_semantics(self, coords, ray_d, compute_channels, pidx=None, lod_idx=None):
         """coords [batch, num_samples, 3], ray_d [batch, 3] -> dict with density [batch,S,1], rgb [batch,S,3],
         semantics [batch*S, C], inst_embedding [batch*S, C] (reference shapes, pc_nerf/panoptic_nef.py:253-363)."""

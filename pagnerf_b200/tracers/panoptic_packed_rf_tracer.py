@@ -56,6 +56,16 @@ class PanopticPackedRFTracer(PackedRFTracer):
         hit_ray_d = rays.dirs.index_select(0, ridx)
 
         outputs = {}
+        if (not extra_channels and not (self.ray_sparcity_reg > 0.0 and stage == 'train')
+                and hasattr(nef, 'fused_panoptic_ok') and nef.fused_panoptic_ok(channels)):
+            # training mode: decode + composite fused, the [M,C] panoptic probabilities never reach HBM
+            ridx_rows = ridx if S == 1 else ridx.repeat_interleave(S)
+            out = nef.trace_composited(samples, hit_ray_d, ridx_rows, deltas, depths, offsets, N, channels,
+                                       bg_color == 'white', lod_idx)
+            for c in ('alpha', 'hit', 'rgb', 'depth', 'semantics', 'inst_embedding'):
+                if c in out and (c in channels or c in ('alpha', 'hit')):
+                    outputs[c] = out[c]
+            return RenderBuffer(**outputs)
         sample_channels = set(channels - self.render_channels)
         sample_channels.update(['density'])
         out_feats = nef(coords=samples, ray_d=hit_ray_d, pidx=pidx, lod_idx=lod_idx, channels=sample_channels)
@@ -66,7 +76,7 @@ class PanopticPackedRFTracer(PackedRFTracer):
             ray_wise_loss = torch.scatter_add(torch.zeros_like(rays.origins[:, 0]), 0, ridx, all_rays_loss)
             outputs['ray_sparcity_loss'] = ray_wise_loss.mean() * self.ray_sparcity_reg
 
-        alpha, hit, rgb, depth, sem, inst = ops.composite(
+        alpha, hit, rgb, depth, sem, inst, _w = ops.composite(
             out_feats['density'], deltas,
             depths if 'depth' in channels else None,
             out_feats['rgb'] if 'rgb' in channels else None,

@@ -354,7 +354,7 @@ def test_composite_empty_rays_and_properties(cuda_lib):
     sigma = torch.tensor([0.5, 2.0, 30.0, 1.0, 0.0, 0.0], device=DEV)
     deltas = torch.full((6,), 0.1, device=DEV)
     rgb = torch.rand(6, 3, device=DEV)
-    alpha, hit, rgb_o, dep, sem, inst = ops.composite(sigma, deltas, None, rgb, None, None, off, True)
+    alpha, hit, rgb_o, dep, sem, inst, w = ops.composite(sigma, deltas, None, rgb, None, None, off, True)
     a = alpha[:, 0].cpu()
     assert torch.all(a >= 0) and torch.all(a <= 1 + 1e-6)
     empty = [0, 2, 3, 5, 6, 8]
@@ -478,3 +478,34 @@ def test_tc_trace_under_autocast_matches_golden(cuda_lib):
     for k, p in nef.named_parameters():
         if k in gg:
             assert_close_norm(p.grad, gg[k], msg="grad " + k)
+
+
+@pytest.mark.parametrize("name,mode", [("trace_delta_permuto_ray", "ray"), ("trace_delta_permuto_voxel", "voxel"), ("trace_nef_tcnn_ray", "ray")])
+def test_fused_panoptic_composite_equals_modular(cuda_lib, name, mode):
+    """decoder_tc_fused.cu (heads + compositing in one kernel) vs the modular tensor-core path
+    (pan_tc kernels -> [M,C] probabilities -> composite kernel): same rounding points, so a tight tolerance."""
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden(name)
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    res = []
+    for fused in (True, False):
+        nef = build_cuda_nef(g, DEV)
+        nef.decoder_precision = 'fp16'
+        if not fused:
+            nef.fused_panoptic_ok = lambda channels: False
+        else:
+            assert nef.fused_panoptic_ok(set(chans))
+        tracer = PanopticPackedRFTracer(raymarch_type=mode, num_steps=int(g["num_steps"]),
+                                        bg_color='white' if bool(g["bg_white"]) else 'black', ray_max_travel=float(g["ray_max_travel"]))
+        o = torch.from_numpy(g["o"]).to(DEV).requires_grad_(True)
+        d = torch.from_numpy(g["d"]).to(DEV).requires_grad_(True)
+        rb = tracer(nef, channels=chans, rays=Rays(origins=o, dirs=d, dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+        loss = sum((getattr(rb, c) * torch.from_numpy(g["gw_" + c]).to(DEV)).sum() for c in chans)
+        loss.backward()
+        res.append(({c: getattr(rb, c).detach() for c in chans + ['alpha']}, {k: p.grad.clone() for k, p in nef.named_parameters()}, o.grad, d.grad))
+    for c in chans + ['alpha']:
+        assert_close(res[0][0][c], res[1][0][c], rtol=1e-3, atol_scale=1e-3, msg=c)
+    for k in res[0][1]:
+        assert_close_norm(res[0][1][k], res[1][1][k], rel_l2=5e-3, max_frac=2e-2, msg="grad " + k)
+    assert_close_norm(res[0][2], res[1][2], rel_l2=5e-3, max_frac=2e-2, msg="grad origins")
