@@ -112,6 +112,41 @@ __device__ __forceinline__ void grad16_store(float (&g)[16], uint8_t* tile, int 
     }
     dbacc += g[0] + __shfl_xor_sync(0xffffffffu, g[0], 1);  // feature 8*b4 + 4*b3 + 2*b2 + b1 (both lanes of a pair hold it)
 }
+// ---- column-split epilogues: a row's columns are divided among NCG threads (warps w, w+4, w+8, ... share the
+// TMEM lane quadrant w%4), which multiplies the warps per SM without more TMEM or shared memory ----------------
+// 16 accumulator columns -> +bias -> ReLU -> 2 tile chunks; returns the 16-bit activity mask
+__device__ __forceinline__ uint32_t epi_relu16(uint32_t taddr, const float* __restrict__ bias, uint8_t* tile2, int row) {
+    float v[16];
+    tmem_ld16(taddr, v);
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        v[i] = fmaxf(v[i] + bias[i], 0.f);
+        mask |= (v[i] > 0.f) ? (1u << i) : 0u;
+    }
+    tile_store8(tile2, 0, row, v);
+    tile_store8(tile2, 1, row, v + 8);
+    return mask;
+}
+// 16 masked gradient columns -> 2 tile chunks + bias-gradient partial (feature 8*b4+4*b3+2*b2+b1 of the 16, on every lane pair)
+__device__ __forceinline__ void epi_grad16(uint32_t taddr, uint32_t mask, uint8_t* tile2, int row, int lane, float& dbacc) {
+    float v[16];
+    tmem_ld16(taddr, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
+    grad16_store(v, tile2, row, lane, dbacc);
+}
+// flush columns [c0, c0+16) of a dW accumulator row
+__device__ __forceinline__ void flush_dw16(uint32_t taddr, float* __restrict__ gW, int row, int OUT, int IN, int c0, float inv_scale) {
+    float v[16];
+    tmem_ld16(taddr + c0, v);
+    if (row < OUT) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (c0 + i < IN) red_add_f32(gW + (size_t)row * IN + c0 + i, v[i] * inv_scale);
+    }
+}
+
 // flush a dW accumulator [rows(lane) x cols] from TMEM to global with atomics
 __device__ __forceinline__ void flush_dw(uint32_t taddr, float* __restrict__ gW, int row, int OUT, int IN, int ncols, float inv_scale) {
     for (int c0 = 0; c0 < ncols; c0 += 16) {

@@ -235,7 +235,10 @@ __device__ __forceinline__ void flush_dw_T(uint32_t taddr, float* __restrict__ g
     }
 }
 
-__global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
+#define PCB_THREADS 512
+#define PCB_NCG 4   // column groups per row
+
+__global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw, int64_t M, int IN,
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
     const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
@@ -244,8 +247,11 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
+    __shared__ float part_s[PCB_NCG][128][3];   // per column group: (max, Z, E) of the row's softmax statistics
     const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant, column group
+    const int row = 32 * q + lane;
     const bool do_sem = (Cs > 0) && g_sem, do_inst = (Ci > 0) && g_inst;
     {
         float* b = reinterpret_cast<float*>(sm + l.oBias);
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
     if (warp == 0) tmem_alloc(&tmem_s, 512);
     sync_to_mma();
     tc_fence_after();
-    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(q * 32) << 16);
     MmaBar mb{&bar_s, 0};
     const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
     const float *bs1 = bias, *bs2 = bias + 64, *bi1 = bias + 64 + l.CsP, *bi2 = bi1 + 64, *bi3 = bi2 + 64;
@@ -276,19 +282,37 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
                    wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
     const float scale = scale_ptr ? __ldg(scale_ptr) : 1.f;
     const float inv_scale = 1.f / scale;
-    float db_s1[2] = {0.f, 0.f}, db_i1[2] = {0.f, 0.f}, db_i2[2] = {0.f, 0.f}, db_s2 = 0.f, db_i3[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) db_i3[i] = 0.f;
+    const int c16 = 16 * cg;                       // this thread's 16 hidden columns
+    float db_s1 = 0.f, db_i1 = 0.f, db_i2 = 0.f, db_s2 = 0.f, db_i3[4] = {0.f, 0.f, 0.f, 0.f};
     const int64_t ntiles = (M + 127) / 128;
     bool first = true;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
-        const int64_t m = tile * 128 + tid;
+        const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
         const int64_t ray = ridx[mm];
-        const float cs = valid ? __ldg(alpha + ray) * __ldg(w + mm) * scale : 0.f;   // detached compositing weight x loss scale
-        // ---------------- stage 1: first hidden layers ----------------
-        stage_x(X, tid, feats, dfeats, lodw, IN, l.nXc, mm);
+        const float cs = valid ? __ldg(alpha + ray) * __ldg(w + mm) * scale : 0.f;
+        // ---------------- stage 1 ----------------
+        {   // X tile: chunk c is written by column group c % 4
+            const float4* a4 = reinterpret_cast<const float4*>(feats + mm * IN);
+            const float4* b4 = dfeats ? reinterpret_cast<const float4*>(dfeats + mm * IN) : nullptr;
+            const float4* w4 = lodw ? reinterpret_cast<const float4*>(lodw) : nullptr;
+            for (int c = cg; c < l.nXc; c += PCB_NCG) {
+                float v[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int qi = 2 * c + h;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (4 * qi < IN) {
+                        x = __ldg(a4 + qi);
+                        if (b4) { const float4 y = __ldg(b4 + qi); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+                        if (w4) { const float4 ww = __ldg(w4 + qi); x.x *= ww.x; x.y *= ww.y; x.z *= ww.z; x.w *= ww.w; }
+                    }
+                    v[4 * h] = x.x; v[4 * h + 1] = x.y; v[4 * h + 2] = x.z; v[4 * h + 3] = x.w;
+                }
+                tile_store8(X, c, row, v);
+            }
+        }
         sync_to_mma();
         if (tid == 0) {
             tc_fence_after();
@@ -297,10 +321,10 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
             mb.commit();
         }
         mb.wait();
-        uint64_t mask_s = 0, mask_1 = 0, mask_2 = 0;
-        if (do_sem) mask_s = epi_relu64(tl + PCB_S0, bs1, Hs, tid);
-        if (do_inst) mask_1 = epi_relu64(tl + PCB_S1, bi1, H1, tid);
-        // ---------------- stage 2: second instance layer + semantic logits ----------------
+        uint32_t mask_s = 0, mask_1 = 0, mask_2 = 0;
+        if (do_sem) mask_s = epi_relu16(tl + PCB_S0 + c16, bs1 + c16, Hs + 2 * cg * TCH, row);
+        if (do_inst) mask_1 = epi_relu16(tl + PCB_S1 + c16, bi1 + c16, H1 + 2 * cg * TCH, row);
+        // ---------------- stage 2 ----------------
         sync_to_mma();
         if (tid == 0) {
             tc_fence_after();
@@ -309,8 +333,8 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
             mb.commit();
         }
         mb.wait();
-        if (do_inst) mask_2 = epi_relu64(tl + PCB_S0, bi2, H2, tid);
-        if (do_sem) {   // semantic head gradient (<= 16 classes, one pass in registers)
+        if (do_inst) mask_2 = epi_relu16(tl + PCB_S0 + c16, bi2 + c16, H2 + 2 * cg * TCH, row);
+        if (do_sem && cg == 0) {   // semantic head gradient (<= 16 classes): column group 0 only
             float z[16], g[16];
             tmem_ld16(tl + PCB_SEMLOG, z);
             float mx = -INFINITY;
@@ -327,9 +351,9 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
             const float iz = 1.f / Z, dot = E * iz;
 #pragma unroll
             for (int j = 0; j < 16; ++j) g[j] = (j < Cs) ? (sem_softmax ? cs * z[j] * iz * (g[j] - dot) : cs * g[j]) : 0.f;
-            grad16_store(g, Gs, tid, lane, db_s2);
+            grad16_store(g, Gs, row, lane, db_s2);
         }
-        // ---------------- stage 3: instance logits + head gradient ----------------
+        // ---------------- stage 3: instance logits + head gradient; 16-column block b belongs to group b % 4 ----------------
         if (do_inst) {
             sync_to_mma();
             if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aH2, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
@@ -337,56 +361,67 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
             const float* grow = g_inst + ray * Ci;
             float mx = -INFINITY, Z = 0.f, E = 0.f;
             if (inst_softmax) {
-                for (int c0 = 0; c0 < l.CiP; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(tl + c0, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < Ci) {
-                            const float z = (v[i] + bi3[c0 + i]) * inst_inv_temp;
-                            const float gj = __ldg(grow + c0 + i);
-                            const float nm = fmaxf(mx, z);
-                            const float r = __expf(mx - nm), e = __expf(z - nm);
-                            Z = Z * r + e;
-                            E = E * r + e * gj;
-                            mx = nm;
-                        }
+                for (int k = 0; k < 4; ++k) {
+                    const int c0 = 16 * (cg + PCB_NCG * k);
+                    if (c0 < l.CiP) {
+                        float v[16];
+                        tmem_ld16(tl + c0, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < Ci) {
+                                const float z = (v[i] + bi3[c0 + i]) * inst_inv_temp;
+                                const float gj = __ldg(grow + c0 + i);
+                                const float nm = fmaxf(mx, z);
+                                const float r = __expf(mx - nm), e = __expf(z - nm);
+                                Z = Z * r + e;
+                                E = E * r + e * gj;
+                                mx = nm;
+                            }
+                    }
                 }
+                part_s[cg][row][0] = mx; part_s[cg][row][1] = Z; part_s[cg][row][2] = E;
+                __syncthreads();
+                float gm = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < PCB_NCG; ++k) gm = fmaxf(gm, part_s[k][row][0]);
+                float gZ = 0.f, gE = 0.f;
+#pragma unroll
+                for (int k = 0; k < PCB_NCG; ++k) {
+                    const float pm = part_s[k][row][0];
+                    const float r = (pm == -INFINITY) ? 0.f : __expf(pm - gm);
+                    gZ = fmaf(part_s[k][row][1], r, gZ);
+                    gE = fmaf(part_s[k][row][2], r, gE);
+                }
+                mx = gm; Z = gZ; E = gE;
             }
             const float iz = inst_softmax ? 1.f / Z : 1.f, dot = E * iz;
 #pragma unroll
-            for (int c0 = 0; c0 < 224; c0 += 32) {
+            for (int k = 0; k < 4; ++k) {
+                const int c0 = 16 * (cg + PCB_NCG * k);
                 if (c0 < l.CiP) {
-                    float v[32];
+                    float t[16], v[16];
+                    tmem_ld16(tl + c0, t);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float t[16];
-                        if (c0 + 16 * h < l.CiP) tmem_ld16(tl + c0 + 16 * h, t);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int j = c0 + 16 * h + i;
-                            float d = 0.f;
-                            if (j < Ci) {
-                                const float gj = __ldg(grow + j);
-                                if (inst_softmax) {
-                                    const float pj = __expf((t[i] + bi3[j]) * inst_inv_temp - mx) * iz;
-                                    d = cs * pj * (gj - dot) * inst_inv_temp;
-                                } else {
-                                    d = cs * gj * inst_inv_temp;
-                                }
+                    for (int i = 0; i < 16; ++i) {
+                        const int j = c0 + i;
+                        float d = 0.f;
+                        if (j < Ci) {
+                            const float gj = __ldg(grow + j);
+                            if (inst_softmax) {
+                                const float pj = __expf((t[i] + bi3[j]) * inst_inv_temp - mx) * iz;
+                                d = cs * pj * (gj - dot) * inst_inv_temp;
+                            } else {
+                                d = cs * gj * inst_inv_temp;
                             }
-                            v[16 * h + i] = d;
                         }
+                        v[i] = d;
                     }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (c0 + 8 * c < l.CiP) tile_store8(Gi, c0 / 8 + c, tid, v + 8 * c);
-                    warp_reduce_scatter<32>(v, lane);
-                    db_i3[c0 / 32] += v[0];
+                    grad16_store(v, Gi + (c0 / 8) * TCH, row, lane, db_i3[k]);
                 }
             }
         }
-        // ---------------- stage 4: last layers backward ----------------
+        // ---------------- stage 4 ----------------
         sync_to_mma();
         if (tid == 0) {
             tc_fence_after();
@@ -396,14 +431,14 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
                 mma16_bwd_data(tm + PCB_S1, aGi, wi3, 64, l.CiP, l.CiP, false);
             }
             if (do_sem) {
-                mma16_bwd_weight(tm + PCB_DWS2T, aHs, aGs, 16, !first);      // transposed: [h x classes]
+                mma16_bwd_weight(tm + PCB_DWS2T, aHs, aGs, 16, !first);
                 mma16_bwd_data(tm + PCB_S0, aGs, ws2, 64, l.CsP, l.CsP, false);
             }
             mb.commit();
         }
         mb.wait();
-        if (do_inst) epi_grad64(tl + PCB_S1, mask_2, H2, tid, lane, db_i2);    // Gi2 overwrites H2
-        if (do_sem) epi_grad64(tl + PCB_S0, mask_s, Hs, tid, lane, db_s1);     // Gs1 overwrites Hs
+        if (do_inst) epi_grad16(tl + PCB_S1 + c16, mask_2, H2 + 2 * cg * TCH, row, lane, db_i2);
+        if (do_sem) epi_grad16(tl + PCB_S0 + c16, mask_s, Hs + 2 * cg * TCH, row, lane, db_s1);
         // ---------------- stage 5 ----------------
         sync_to_mma();
         if (tid == 0) {
@@ -421,7 +456,7 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
         mb.wait();
         // ---------------- stage 6 ----------------
         if (do_inst) {
-            epi_grad64(tl + PCB_S1, mask_1, H1, tid, lane, db_i1);             // Gi1 overwrites H1
+            epi_grad16(tl + PCB_S1 + c16, mask_1, H1 + 2 * cg * TCH, row, lane, db_i1);
             sync_to_mma();
             if (tid == 0) {
                 tc_fence_after();
@@ -431,30 +466,45 @@ __global__ void __launch_bounds__(128) pan_comp_bwd_kernel(
             }
             mb.wait();
         }
-        if (g_panop) store_dx(tl + PCB_S0, g_panop + mm * IN, lodw, IN, l.INP, inv_scale, valid);
+        if (g_panop && c16 < l.INP) {
+            float v[16];
+            tmem_ld16(tl + PCB_S0 + c16, v);
+            if (valid) {
+#pragma unroll
+                for (int qi = 0; qi < 4; ++qi) {
+                    if (c16 + 4 * qi < IN) {
+                        const float4 ww = lodw ? __ldg(reinterpret_cast<const float4*>(lodw + c16) + qi) : make_float4(1.f, 1.f, 1.f, 1.f);
+                        reinterpret_cast<float4*>(g_panop + mm * IN + c16)[qi] =
+                            make_float4(v[4 * qi] * inv_scale * ww.x, v[4 * qi + 1] * inv_scale * ww.y,
+                                        v[4 * qi + 2] * inv_scale * ww.z, v[4 * qi + 3] * inv_scale * ww.w);
+                    }
+                }
+            }
+        }
         tc_fence_before();
         __syncthreads();
     }
     if (!first) {
         tc_fence_after();
-        const int f2 = scatter_base(lane, 64);
+        const int f1 = scatter_base(lane, 32) >> 1;     // feature (of 16) owned by this lane pair after grad16_store
+        const bool own = !(lane & 1);
         if (do_sem) {
-            flush_dw(tl + PCB_DWS1, p.gWs1, tid, 64, IN, l.INP, inv_scale);
-            flush_dw_T(tl + PCB_DWS2T, p.gWs2, tid, 64, Cs, inv_scale);
-            red_add_f32(p.gbs1 + f2, db_s1[0] * inv_scale); red_add_f32(p.gbs1 + f2 + 1, db_s1[1] * inv_scale);
-            const int f1 = scatter_base(lane, 32) >> 1;
-            if (!(lane & 1) && f1 < Cs) red_add_f32(p.gbs2 + f1, db_s2 * inv_scale);
+            if (c16 < l.INP) flush_dw16(tl + PCB_DWS1, p.gWs1, row, 64, IN, c16, inv_scale);
+            if (cg == 0) flush_dw_T(tl + PCB_DWS2T, p.gWs2, row, 64, Cs, inv_scale);
+            if (own) red_add_f32(p.gbs1 + c16 + f1, db_s1 * inv_scale);
+            if (own && cg == 0 && f1 < Cs) red_add_f32(p.gbs2 + f1, db_s2 * inv_scale);
         }
         if (do_inst) {
-            flush_dw(tl + PCB_DWI1, p.gWi1, tid, 64, IN, l.INP, inv_scale);
-            flush_dw(tl + PCB_DWI2, p.gWi2, tid, 64, 64, 64, inv_scale);
-            flush_dw(tl + PCB_DWI3, p.gWi3, tid, Ci, 64, 64, inv_scale);
-            if (l.CiP > 128) flush_dw(tl + PCB_DWI3 + 64, p.gWi3 + (size_t)128 * 64, tid, Ci - 128, 64, 64, inv_scale);
-            red_add_f32(p.gbi1 + f2, db_i1[0] * inv_scale); red_add_f32(p.gbi1 + f2 + 1, db_i1[1] * inv_scale);
-            red_add_f32(p.gbi2 + f2, db_i2[0] * inv_scale); red_add_f32(p.gbi2 + f2 + 1, db_i2[1] * inv_scale);
+            if (c16 < l.INP) flush_dw16(tl + PCB_DWI1, p.gWi1, row, 64, IN, c16, inv_scale);
+            flush_dw16(tl + PCB_DWI2, p.gWi2, row, 64, 64, c16, inv_scale);
+            flush_dw16(tl + PCB_DWI3, p.gWi3, row, Ci, 64, c16, inv_scale);
+            if (l.CiP > 128) flush_dw16(tl + PCB_DWI3 + 64, p.gWi3 + (size_t)128 * 64, row, Ci - 128, 64, c16, inv_scale);
+            if (own) { red_add_f32(p.gbi1 + c16 + f1, db_i1 * inv_scale); red_add_f32(p.gbi2 + c16 + f1, db_i2 * inv_scale); }
 #pragma unroll
-            for (int c = 0; c < 7; ++c)
-                if (c * 32 < l.CiP && c * 32 + lane < Ci) red_add_f32(p.gbi3 + c * 32 + lane, db_i3[c] * inv_scale);
+            for (int k = 0; k < 4; ++k) {
+                const int j = 16 * (cg + PCB_NCG * k) + f1;
+                if (own && j < Ci) red_add_f32(p.gbi3 + j, db_i3[k] * inv_scale);
+            }
         }
     }
     tc_fence_before();
@@ -524,7 +574,7 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
     const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = fused_num_sms();
-    pan_comp_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
+    pan_comp_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), PCB_THREADS, l.total, (cudaStream_t)stream>>>(
         feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, grad_scale, g_panop);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
