@@ -248,6 +248,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # algorithmic bytes / flops per packed sample (DESIGN.md "Kernels")
 ALGO = {
+    "pag_permuto_fwd_dyn": ("hbm", 12 + L * 4 * 8 + L * 2 * 4),
+    "pag_permuto_bwd_dyn": ("hbm", 12 + L * 2 * 4 + 2 * L * 4 * 8),
+    "pag_decode_dc_fwd_tc_dyn": ("tensor", 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
+    "pag_decode_dc_bwd_tc_dyn": ("tensor", 3 * 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
+    "pag_pan_composite_fwd_tc": ("tensor", 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
+    "pag_pan_composite_bwd_tc": ("tensor", 4 * 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
     "pag_permuto_fwd": ("hbm", 12 + L * 4 * 8 + L * 2 * 4),
     "pag_permuto_bwd": ("hbm", 12 + L * 2 * 4 + 2 * L * 4 * 8),
     "pag_decode_dc_fwd_tc": ("tensor", 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
@@ -334,8 +340,10 @@ def main():
     l0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         out = step(False)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time to enqueue one step (no sync)
     e1.record()
     sync()
     ms = e0.elapsed_time(e1) / args.steps
@@ -370,6 +378,8 @@ def main():
     top = max(per_kernel.items(), key=lambda kv: kv[1]["ms_per_step"]) if per_kernel else None
     roof = None
     n_samples = wl.tracer.last_num_samples if hasattr(wl.tracer, "last_num_samples") else None
+    if torch.is_tensor(n_samples):
+        n_samples = int(n_samples.item())
     if top and top[0] in ALGO and n_samples:
         bound, per = ALGO[top[0]]
         dur = top[1]["ms_per_launch"] * 1e-3
@@ -399,7 +409,7 @@ def main():
                              packed_samples_per_step=n_samples),
               "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": wl.h2d_bytes(),
                       "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
-              "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+              "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
               "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
     print(json.dumps(result))
     if world > 1:

@@ -72,6 +72,14 @@ int pag_permuto_fwd(const float* pos, int64_t M, const float* table, int64_t cap
 int pag_permuto_bwd(const float* pos, int64_t M, const float* table, int64_t capacity, int L, int F,
                     const float* scale_factor, const float* shift, const float* anneal, const float* grad_out,
                     float* grad_table, float* grad_pos, int n_agg_levels, void* stream);
+/* variants for the sync-free fused trace: the packed-sample count is read on the device (m_dev[0] <= M_max, written by
+ * the marcher's scan), pos_half rounds positions to fp16 first (autocast, grids/permuto_grid.py:65,71). */
+int pag_permuto_fwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
+                        int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
+                        float* out, void* stream);
+int pag_permuto_bwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
+                        int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
+                        const float* grad_out, float* grad_table, float* grad_pos, int n_agg_levels, void* stream);
 /* parity probe: lattice vertex hash indices u32[L,M,4], ranks i32[L,M,4], barycentric f32[L,M,4]. */
 int pag_permuto_indices(const float* pos, int64_t M, int64_t capacity, int L, const float* scale_factor,
                         const float* shift, uint32_t* idx, int32_t* rank, float* bary, void* stream);
@@ -116,6 +124,13 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
                          const float* const* weights, float* const* grads, int hidden, int view_dim,
                          const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats, float* g_dir,
                          void* stream);
+int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
+                             const int64_t* m_dev, int IN, const float* const* weights, int hidden, int view_dim,
+                             int want_rgb, float* sigma, float* rgb, void* stream);
+int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
+                             const int64_t* m_dev, int IN, const float* const* weights, float* const* grads, int hidden,
+                             int view_dim, const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats,
+                             float* g_dir, void* stream);
 int pag_decode_pan_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                           const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
                           float inst_temperature, float* sem, float* inst, void* stream);
@@ -130,12 +145,12 @@ int pag_decode_pan_bwd_tc(const float* feats, const float* dfeats, const float* 
 int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
                              float inst_temperature, const float* w, const float* alpha, const int64_t* ridx,
-                             float* out_sem, float* out_inst, void* stream);
+                             float* out_sem, float* out_inst, const int64_t* m_dev, void* stream);
 int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
                              const int64_t* ridx, const float* g_sem, const float* g_inst, const float* grad_scale,
-                             float* g_panop, void* stream);
+                             float* g_panop, const int64_t* m_dev, void* stream);
 
 /* ---- packed compositing: tracers/panoptic_packed_rf_tracer.py:134-205 ------------------------------- */
 /* offsets[r] = first packed index with ridx >= r (ridx ascending), offsets[R] = M. */
@@ -150,6 +165,9 @@ int pag_composite_bwd(const float* sigma, const float* deltas, const float* dept
                       const float* alpha, const float* rgbsum, const float* g_alpha, const float* g_rgb,
                       const float* g_depth, const float* g_sem, int Cs, const float* g_inst, int Ci, float* g_sigma,
                       float* g_rgb_s, float* g_sem_s, float* g_inst_s, void* stream);
+/* power-of-two loss scale for the fp16 tensor-core backward (the GradScaler of pc_nerf/trainer.py:582, on the device). */
+int pag_grad_scale(const float* a, int64_t na, int wa, const float* b, int64_t nb, int wb, const int64_t* m_dev,
+                   float target, uint32_t* scratch, float* out_scale, void* stream);
 /* kaolin.render.spc.sum_reduce / exponential_integration (weights only), packs given by offsets[R+1]. */
 int pag_sum_reduce_fwd(const float* x, int64_t C, const int64_t* offsets, int64_t R, float* out, void* stream);
 int pag_sum_reduce_bwd(const float* g, int64_t C, const int64_t* offsets, int64_t R, float* gx, void* stream);

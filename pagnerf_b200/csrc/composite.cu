@@ -261,7 +261,47 @@ __global__ void expint_bwd_kernel(const float* __restrict__ gw, const float* __r
     }
 }
 
+// ---- loss-scale for the fp16 tensor-core backward: scale = 2^floor(log2(target / max|g|)) (one launch + finalize) ----
+__global__ void absmax_kernel(const float* __restrict__ a, int64_t na, const float* __restrict__ b, int64_t nb,
+                              const int64_t* __restrict__ m_dev, int wa, int wb, unsigned* __restrict__ scratch) {
+    if (m_dev) { const int64_t mv = __ldg(m_dev); na = min(na, mv * wa); nb = min(nb, mv * wb); }
+    float mx = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = (i < na) ? a[i] : b[i - na];
+        mx = fmaxf(mx, fabsf(v));     // NaN is dropped by fmaxf
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(scratch, __float_as_uint(mx));
+}
+__global__ void scale_finalize_kernel(const unsigned* __restrict__ scratch, float target, float* __restrict__ out) {
+    const float amax = fmaxf(__uint_as_float(*scratch), 1e-30f);
+    float s = exp2f(floorf(log2f(target / amax)));
+    s = fminf(fmaxf(s, 5.9604645e-08f), 1.1529215e18f);   // [2^-24, 2^60]
+    *out = s;
+}
+
 extern "C" {
+
+// out_scale[0] = power-of-two loss scale for the gradients a[na] (and b[nb], nullable); scratch: one uint32 on the device.
+// With m_dev the element counts are min(na, m_dev[0]*wa) / min(nb, m_dev[0]*wb) (packed-sample tensors of width wa / wb).
+int pag_grad_scale(const float* a, int64_t na, int wa, const float* b, int64_t nb, int wb, const int64_t* m_dev,
+                   float target, uint32_t* scratch, float* out_scale, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    if (!b) nb = 0;
+    const int64_t n = na + nb;
+    if (n > 0) {
+        int grid = (int)((n + 1023) / 1024);
+        if (grid > 1184) grid = 1184;
+        absmax_kernel<<<grid, 256, 0, st>>>(a, na, b, nb, m_dev, wa, wb, scratch);
+        PAG_LAUNCH_CHECK();
+    }
+    scale_finalize_kernel<<<1, 1, 0, st>>>(scratch, target, out_scale);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
 
 int pag_ray_offsets(const int64_t* ridx, int64_t M, int64_t R, int64_t* offsets /*[R+1]*/, void* stream) {
     ray_offsets_kernel<<<pag_grid(M + 1, 256), 256, 0, (cudaStream_t)stream>>>(ridx, M, R, offsets);

@@ -65,7 +65,9 @@ __device__ __forceinline__ void dc_tc_stage(uint8_t* sm, const DcTcLayout& l, co
 __global__ void __launch_bounds__(128) dc_tc_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
                                                         const float* __restrict__ ray_d, int S, int64_t M, int IN,
                                                         DcParams p, int want_rgb, float* __restrict__ sigma,
-                                                        float* __restrict__ rgb) {
+                                                        float* __restrict__ rgb, const int64_t* __restrict__ m_dev,
+                                                        const int64_t* __restrict__ ridx) {
+    if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(128) dc_tc_fwd_kernel(const float* __restrict_
         if (!want_rgb) { tc_fence_before(); __syncthreads(); continue; }
         {
             float pe[PE_DIM];
-            const int64_t r = mm / S;
+            const int64_t r = ridx ? ridx[mm] : mm / S;
             view_embed(ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2], pe);
             stage_cin(T0, tid, y, pe);
         }
@@ -146,7 +148,9 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
                                                         const float* __restrict__ ray_d, int S, int64_t M, int IN,
                                                         DcParams p, const float* __restrict__ g_sigma,
                                                         const float* __restrict__ g_rgb, const float* __restrict__ scale_ptr,
-                                                        float* __restrict__ g_feats, float* __restrict__ g_dir) {
+                                                        float* __restrict__ g_feats, float* __restrict__ g_dir,
+                                                        const int64_t* __restrict__ m_dev, const int64_t* __restrict__ ridx) {
+    if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
         if (do_rgb) {
             {
                 float pe[PE_DIM];
-                const int64_t r = mm / S;
+                const int64_t r = ridx ? ridx[mm] : mm / S;
                 vdir[0] = -ray_d[3 * r]; vdir[1] = -ray_d[3 * r + 1]; vdir[2] = -ray_d[3 * r + 2];
                 view_embed(-vdir[0], -vdir[1], -vdir[2], pe);
                 stage_cin(Cin, tid, y, pe);
@@ -680,7 +684,25 @@ int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray
     if (rc) return rc;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = 4 * (int64_t)tc_num_sms();
-    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb);
+    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb, nullptr, nullptr);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// device-side sample count (m_dev[0] <= M_max) and per-sample ray index: sample m uses ray_d[ridx[m]]
+int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
+                             const int64_t* m_dev, int IN, const float* const* weights, int hidden, int view_dim,
+                             int want_rgb, float* sigma, float* rgb, void* stream) {
+    if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
+    if (M_max == 0) return PAG_OK;
+    DcParams p{};
+    fill_dc(p, weights, nullptr);
+    const DcTcLayout l = dc_tc_layout(IN, false);
+    int rc = tc_set_smem(dc_tc_fwd_kernel, l.total);
+    if (rc) return rc;
+    const int64_t tiles = (M_max + 127) / 128;
+    const int64_t cap = 4 * (int64_t)tc_num_sms();
+    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -700,7 +722,26 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = tc_num_sms();
     dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
-        feats, lodw, ray_d, S, M, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir);
+        feats, lodw, ray_d, S, M, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, nullptr, nullptr);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
+                             const int64_t* m_dev, int IN, const float* const* weights, float* const* grads, int hidden,
+                             int view_dim, const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats,
+                             float* g_dir, void* stream) {
+    if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
+    if (M_max == 0) return PAG_OK;
+    DcParams p{};
+    fill_dc(p, weights, grads);
+    const DcTcLayout l = dc_tc_layout(IN, true);
+    int rc = tc_set_smem(dc_tc_bwd_kernel, l.total);
+    if (rc) return rc;
+    const int64_t tiles = (M_max + 127) / 128;
+    const int64_t cap = tc_num_sms();
+    dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
+        feats, lodw, ray_d, 1, M_max, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, m_dev, ridx);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

@@ -30,8 +30,8 @@ __host__ __device__ inline PanCompFwdLayout pan_comp_fwd_layout(int IN, int Cs, 
     l.oX = o; o += l.nXc * TCH;
     l.oT1 = o; o += 8 * TCH;
     l.oT2 = o; o += 8 * TCH;
-    l.oStage = o; o += 4 * 32 * 33 * 4;
-    l.oCR = o; o += 4 * 32 * 8;          // per warp: c[32] floats + ray[32] ints
+    l.oStage = o; o += 16 * 32 * 33 * 4;   // one transpose buffer per warp (16 warps)
+    l.oCR = o; o += 4 * 32 * 8;           // per lane quadrant: c[32] floats + ray[32] ints
     o = (o + 15) & ~15;
     l.oWs1 = o; o += l.nXc * 64 * 16;
     l.oWs2 = o; o += 8 * l.CsP * 16;
@@ -43,69 +43,42 @@ __host__ __device__ inline PanCompFwdLayout pan_comp_fwd_layout(int IN, int Cs, 
     return l;
 }
 
-// softmax of the thread's logits row (TMEM) and weighted segment-sum over the warp's rows into out[N, C]
-__device__ __forceinline__ void epi_head_comp(uint32_t taddr, const float* __restrict__ bias, int C, int CP, bool softmax,
-                                              float inv_temp, float* __restrict__ out, float* stage,
-                                              const float* __restrict__ wc, const int* __restrict__ wr, int nrows, int lane) {
-    float mx = -INFINITY, sum = 0.f;
-    if (softmax) {
-        for (int c0 = 0; c0 < CP; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (c0 + i < C) {
-                    const float z = (v[i] + bias[c0 + i]) * inv_temp;
-                    const float nm = fmaxf(mx, z);
-                    sum = sum * __expf(mx - nm) + __expf(z - nm);
-                    mx = nm;
-                }
-        }
-    }
-    const float inv = softmax ? 1.f / sum : 1.f;
-    for (int c0 = 0; c0 < CP; c0 += 32) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (c0 + 16 * h < CP) {
-                float v[16];
-                tmem_ld16(taddr + c0 + 16 * h, v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int j = c0 + 16 * h + i;
-                    const float z = (v[i] + (j < C ? bias[j] : 0.f)) * inv_temp;
-                    stage[lane * 33 + 16 * h + i] = softmax ? __expf(z - mx) * inv : z;
-                }
+#define PCF_THREADS 512
+#define PCF_NCG 4
+
+// weighted segment-sum of one transposed 32-column block (stage[row][col]) over the warp's rows into out[N, C]
+__device__ __forceinline__ void comp_block(const float* stage, const float* __restrict__ wc, const int* __restrict__ wr, int nrows,
+                                           float* __restrict__ out, int C, int c0, int lane) {
+    if (c0 + lane < C && nrows > 0) {
+        float acc = 0.f;
+        int cur = wr[0];
+        for (int r = 0; r < nrows; ++r) {
+            const int ray = wr[r];
+            if (ray != cur) {
+                red_add_f32(out + (int64_t)cur * C + c0 + lane, acc);
+                acc = 0.f;
+                cur = ray;
             }
+            acc = fmaf(wc[r], stage[r * 33 + lane], acc);
         }
-        __syncwarp();
-        if (c0 + lane < C && nrows > 0) {
-            float acc = 0.f;
-            int cur = wr[0];
-            for (int r = 0; r < nrows; ++r) {
-                const int ray = wr[r];
-                if (ray != cur) {
-                    red_add_f32(out + (int64_t)cur * C + c0 + lane, acc);
-                    acc = 0.f;
-                    cur = ray;
-                }
-                acc = fmaf(wc[r], stage[r * 33 + lane], acc);
-            }
-            red_add_f32(out + (int64_t)cur * C + c0 + lane, acc);
-        }
-        __syncwarp();
+        red_add_f32(out + (int64_t)cur * C + c0 + lane, acc);
     }
 }
 
-__global__ void __launch_bounds__(128) pan_comp_fwd_kernel(
+__global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
     const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw, int64_t M, int IN,
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
     const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
-    float* __restrict__ out_sem, float* __restrict__ out_inst) {
+    float* __restrict__ out_sem, float* __restrict__ out_inst, const int64_t* __restrict__ m_dev) {
+    if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
+    __shared__ float part_s[PCF_NCG][128][2];   // (max, sum) partials of the row softmax per column group
     const PanCompFwdLayout l = pan_comp_fwd_layout(IN, Cs, Ci);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = 32 * q + lane;
     {   // weights (same images as decoder_tc.cu)
         float* b = reinterpret_cast<float*>(sm + l.oBias);
         if (Cs > 0) {
@@ -125,7 +98,7 @@ __global__ void __launch_bounds__(128) pan_comp_fwd_kernel(
     if (warp == 0) tmem_alloc(&tmem_s, 256);
     sync_to_mma();
     tc_fence_after();
-    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(q * 32) << 16);
     MmaBar mb{&bar_s, 0};
     const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
     const float *bs1 = bias, *bs2 = bias + 64, *bi1 = bias + 64 + l.CsP, *bi2 = bi1 + 64, *bi3 = bi2 + 64;
@@ -134,16 +107,36 @@ __global__ void __launch_bounds__(128) pan_comp_fwd_kernel(
     const uint32_t ws1 = smem_u32(sm + l.oWs1), ws2 = smem_u32(sm + l.oWs2), wi1 = smem_u32(sm + l.oWi1),
                    wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
     const uint32_t semcol = (Ci > 0) ? (uint32_t)(l.CiP > 64 ? l.CiP : 64) : 128u;
-    float* stage = reinterpret_cast<float*>(sm + l.oStage) + warp * (32 * 33);
-    float* wc = reinterpret_cast<float*>(sm + l.oCR) + warp * 64;
+    float* stage = reinterpret_cast<float*>(sm + l.oStage) + warp * (32 * 33);     // one transpose buffer per warp
+    float* wc = reinterpret_cast<float*>(sm + l.oCR) + q * 64;                      // shared by the 4 column groups of a quadrant
     int* wr = reinterpret_cast<int*>(wc + 32);
+    const int c16 = 16 * cg;
     const int64_t ntiles = (M + 127) / 128;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t m = tile * 128 + tid;
+        const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
-        stage_x(X, tid, feats, dfeats, lodw, IN, l.nXc, mm);
-        {   // compositing coefficients of this warp's rows
+        {   // X tile: chunk c is written by column group c % 4
+            const float4* a4 = reinterpret_cast<const float4*>(feats + mm * IN);
+            const float4* b4 = dfeats ? reinterpret_cast<const float4*>(dfeats + mm * IN) : nullptr;
+            const float4* w4 = lodw ? reinterpret_cast<const float4*>(lodw) : nullptr;
+            for (int c = cg; c < l.nXc; c += PCF_NCG) {
+                float v[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int qi = 2 * c + h;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (4 * qi < IN) {
+                        x = __ldg(a4 + qi);
+                        if (b4) { const float4 y = __ldg(b4 + qi); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+                        if (w4) { const float4 ww = __ldg(w4 + qi); x.x *= ww.x; x.y *= ww.y; x.z *= ww.z; x.w *= ww.w; }
+                    }
+                    v[4 * h] = x.x; v[4 * h + 1] = x.y; v[4 * h + 2] = x.z; v[4 * h + 3] = x.w;
+                }
+                tile_store8(X, c, row, v);
+            }
+        }
+        if (cg == 0) {   // compositing coefficients of this quadrant's rows
             const int64_t ray = ridx[mm];
             wr[lane] = (int)ray;
             wc[lane] = valid ? __ldg(alpha + ray) * __ldg(w + mm) : 0.f;
@@ -156,8 +149,8 @@ __global__ void __launch_bounds__(128) pan_comp_fwd_kernel(
             mb.commit();
         }
         mb.wait();
-        if (Cs > 0) epi_relu64(tl, bs1, T1, tid);
-        if (Ci > 0) epi_relu64(tl + 64, bi1, T2, tid);
+        if (Cs > 0) epi_relu16(tl + c16, bs1 + c16, T1 + 2 * cg * TCH, row);
+        if (Ci > 0) epi_relu16(tl + 64 + c16, bi1 + c16, T2 + 2 * cg * TCH, row);
         sync_to_mma();
         if (tid == 0) {
             tc_fence_after();
@@ -166,16 +159,81 @@ __global__ void __launch_bounds__(128) pan_comp_fwd_kernel(
             mb.commit();
         }
         mb.wait();
-        const int64_t rows_left = M - (tile * 128 + warp * 32);
+        const int64_t rows_left = M - (tile * 128 + q * 32);
         const int nrows = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
         if (Ci > 0) {
-            epi_relu64(tl, bi2, T1, tid);
+            epi_relu16(tl + c16, bi2 + c16, T1 + 2 * cg * TCH, row);
             sync_to_mma();
             if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT1, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
             mb.wait();
-            epi_head_comp(tl, bi3, Ci, l.CiP, inst_softmax, inst_inv_temp, out_inst, stage, wc, wr, nrows, lane);
+            // softmax statistics: 16-column block b belongs to column group b % 4
+            float mx = -INFINITY, sum = 0.f;
+            if (inst_softmax) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c0 = 16 * (cg + PCF_NCG * k);
+                    if (c0 < l.CiP) {
+                        float v[16];
+                        tmem_ld16(tl + c0, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < Ci) {
+                                const float z = (v[i] + bi3[c0 + i]) * inst_inv_temp;
+                                const float nm = fmaxf(mx, z);
+                                sum = sum * __expf(mx - nm) + __expf(z - nm);
+                                mx = nm;
+                            }
+                    }
+                }
+                part_s[cg][row][0] = mx; part_s[cg][row][1] = sum;
+                __syncthreads();
+                float gm = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < PCF_NCG; ++k) gm = fmaxf(gm, part_s[k][row][0]);
+                float gs = 0.f;
+#pragma unroll
+                for (int k = 0; k < PCF_NCG; ++k) {
+                    const float pm = part_s[k][row][0];
+                    gs = fmaf(part_s[k][row][1], (pm == -INFINITY) ? 0.f : __expf(pm - gm), gs);
+                }
+                mx = gm; sum = gs;
+            }
+            const float inv = inst_softmax ? 1.f / sum : 1.f;
+            // probabilities -> transpose -> weighted segment sums; 32-column block b2 belongs to column group b2 % 4
+            for (int c0 = 32 * cg; c0 < l.CiP; c0 += 32 * PCF_NCG) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (c0 + 16 * h < l.CiP) {
+                        float v[16];
+                        tmem_ld16(tl + c0 + 16 * h, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int j = c0 + 16 * h + i;
+                            const float z = (v[i] + (j < Ci ? bi3[j] : 0.f)) * inst_inv_temp;
+                            stage[lane * 33 + 16 * h + i] = inst_softmax ? __expf(z - mx) * inv : z;
+                        }
+                    }
+                }
+                __syncwarp();
+                comp_block(stage, wc, wr, nrows, out_inst, Ci, c0, lane);
+                __syncwarp();
+            }
         }
-        if (Cs > 0) epi_head_comp(tl + semcol, bs2, Cs, l.CsP, sem_softmax, 1.f, out_sem, stage, wc, wr, nrows, lane);
+        if (Cs > 0 && cg == 0) {   // semantic head: 16 columns, one column group
+            float z[16];
+            tmem_ld16(tl + semcol, z);
+            float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { z[j] += bs2[j]; if (j < Cs) mx = fmaxf(mx, z[j]); }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { z[j] = (j < Cs) ? (sem_softmax ? __expf(z[j] - mx) : z[j]) : 0.f; sum += z[j]; }
+            const float inv = sem_softmax ? 1.f / sum : 1.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) stage[lane * 33 + j] = z[j] * inv;
+            __syncwarp();
+            comp_block(stage, wc, wr, nrows, out_sem, Cs, 0, lane);
+            __syncwarp();
+        }
         tc_fence_before();
         __syncthreads();
     }
@@ -243,7 +301,8 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
     const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
     const float* __restrict__ g_sem, const float* __restrict__ g_inst, const float* __restrict__ scale_ptr,
-    float* __restrict__ g_panop) {
+    float* __restrict__ g_panop, const int64_t* __restrict__ m_dev) {
+    if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
@@ -539,7 +598,7 @@ extern "C" {
 int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
                              float inst_temperature, const float* w, const float* alpha, const int64_t* ridx,
-                             float* out_sem, float* out_inst, void* stream) {
+                             float* out_sem, float* out_inst, const int64_t* m_dev, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
     PanParams p{};
@@ -550,9 +609,9 @@ int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const floa
     if (e != cudaSuccess) return (int)e;
     const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
     const int64_t tiles = (M + 127) / 128;
-    const int64_t cap = 2 * (int64_t)fused_num_sms();
-    pan_comp_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
-        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, out_sem, out_inst);
+    const int64_t cap = (int64_t)fused_num_sms();
+    pan_comp_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), PCF_THREADS, l.total, (cudaStream_t)stream>>>(
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, out_sem, out_inst, m_dev);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -562,7 +621,7 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
                              const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
                              const int64_t* ridx, const float* g_sem, const float* g_inst, const float* grad_scale,
-                             float* g_panop, void* stream) {
+                             float* g_panop, const int64_t* m_dev, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
     PanParams p{};
@@ -575,7 +634,7 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = fused_num_sms();
     pan_comp_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), PCB_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, grad_scale, g_panop);
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, grad_scale, g_panop, m_dev);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

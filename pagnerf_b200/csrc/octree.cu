@@ -144,13 +144,13 @@ __global__ void march_ray_emit_kernel(const float* __restrict__ org, const float
             const float t = ray_step_depth(ray, i, S, lin, jitter, seed, near, range);
             const float tp = (i == 0) ? near : ray_step_depth(ray, i - 1, S, lin, jitter, seed, near, range);
             ridx[dst] = ray;
-            pidx[dst] = p;
+            if (pidx) pidx[dst] = p;
             samples[3 * dst + 0] = __fadd_rn(ox, __fmul_rn(dx, t));
             samples[3 * dst + 1] = __fadd_rn(oy, __fmul_rn(dy, t));
             samples[3 * dst + 2] = __fadd_rn(oz, __fmul_rn(dz, t));
             depths[dst] = t;
             deltas[dst] = __fsub_rn(t, tp);
-            boundary[dst] = (dst == first) ? 1 : 0;
+            if (boundary) boundary[dst] = (dst == first) ? 1 : 0;
         }
         off += __popc(bal);
     }

@@ -13,6 +13,7 @@
 // warp (match-any leader reduction) so contention at L2 drops by up to 32x.
 // Lattice integers (rem0, rank, key, idx) are bit-exact against oracle/permuto.py.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 #define PERMUTO_HASH_MUL 2531011u
 
@@ -90,10 +91,14 @@ __device__ __forceinline__ void permuto_lattice(float p0, float p1, float p2, co
 __global__ void __launch_bounds__(128) permuto_fwd_kernel(
     const float* __restrict__ pos, int64_t M, const float* __restrict__ table, uint32_t cap, uint32_t cap_mask, int L,
     const float* __restrict__ sf, const float* __restrict__ sh, const float* __restrict__ anneal,
-    float* __restrict__ out) {
+    float* __restrict__ out, const int64_t* __restrict__ m_dev, int pos_half) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m_dev) M = min(M, __ldg(m_dev));   // packed-sample count produced on the device by the marcher
     if (m >= M) return;
-    const float p0 = pos[3 * m], p1 = pos[3 * m + 1], p2 = pos[3 * m + 2];
+    float p0 = pos[3 * m], p1 = pos[3 * m + 1], p2 = pos[3 * m + 2];
+    if (pos_half) {   // autocast: custom_fwd(cast_inputs=torch.half) then .float() (grids/permuto_grid.py:65,71)
+        p0 = __half2float(__float2half_rn(p0)); p1 = __half2float(__float2half_rn(p1)); p2 = __half2float(__float2half_rn(p2));
+    }
     float2* orow = reinterpret_cast<float2*>(out + m * (int64_t)(2 * L));
 #pragma unroll 4
     for (int l = 0; l < L; ++l) {
@@ -134,12 +139,18 @@ template <bool POS_GRAD>
 __global__ void __launch_bounds__(128) permuto_bwd_kernel(
     const float* __restrict__ pos, int64_t M, const float* __restrict__ table, uint32_t cap, uint32_t cap_mask, int L,
     const float* __restrict__ sf, const float* __restrict__ sh, const float* __restrict__ anneal,
-    const float* __restrict__ gout, float* __restrict__ gtable, float* __restrict__ gpos, int n_agg_levels) {
+    const float* __restrict__ gout, float* __restrict__ gtable, float* __restrict__ gpos, int n_agg_levels,
+    const int64_t* __restrict__ m_dev, int pos_half) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m_dev) M = min(M, __ldg(m_dev));
+    if (M <= 0 || (m & ~31ll) >= M) return;   // whole warp beyond the packed samples
     const bool valid = m < M;
     // aggregated levels need the full warp converged: clamp instead of returning early
     const int64_t mm = valid ? m : (M - 1);
-    const float p0 = pos[3 * mm], p1 = pos[3 * mm + 1], p2 = pos[3 * mm + 2];
+    float p0 = pos[3 * mm], p1 = pos[3 * mm + 1], p2 = pos[3 * mm + 2];
+    if (pos_half) {
+        p0 = __half2float(__float2half_rn(p0)); p1 = __half2float(__float2half_rn(p1)); p2 = __half2float(__float2half_rn(p2));
+    }
     const float2* grow = reinterpret_cast<const float2*>(gout + mm * (int64_t)(2 * L));
     float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
     for (int l = 0; l < L; ++l) {
@@ -197,7 +208,22 @@ int pag_permuto_fwd(const float* pos, int64_t M, const float* table, int64_t cap
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
     if (cap == 1) return PAG_ERR_ARG;
     permuto_fwd_kernel<<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(pos, M, table, cap, mask, L, scale_factor,
-                                                                          shift, anneal, out);
+                                                                          shift, anneal, out, nullptr, 0);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// same, with the sample count read on the device (m_dev[0] <= M_max, no host sync) and optional fp16 rounding of pos
+int pag_permuto_fwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
+                        int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
+                        float* out, void* stream) {
+    if (F != 2) return PAG_ERR_UNSUPPORTED;
+    if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    const uint32_t cap = (uint32_t)capacity;
+    const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
+    permuto_fwd_kernel<<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(pos, M_max, table, cap, mask, L, scale_factor,
+                                                                              shift, anneal, out, m_dev, pos_half);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -213,10 +239,28 @@ int pag_permuto_bwd(const float* pos, int64_t M, const float* table, int64_t cap
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
     if (grad_pos)
         permuto_bwd_kernel<true><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels);
+            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0);
     else
         permuto_bwd_kernel<false><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels);
+            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+int pag_permuto_bwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
+                        int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
+                        const float* grad_out, float* grad_table, float* grad_pos, int n_agg_levels, void* stream) {
+    if (F != 2) return PAG_ERR_UNSUPPORTED;
+    if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    const uint32_t cap = (uint32_t)capacity;
+    const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
+    if (grad_pos)
+        permuto_bwd_kernel<true><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half);
+    else
+        permuto_bwd_kernel<false><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

@@ -258,9 +258,18 @@ def grad_scale(*grads):
     """Power-of-two loss scale for the fp16 tensor-core backward (device scalar, no host sync):
     2^floor(log2(GRAD_TARGET / max|g|)).  Plays the role of torch.cuda.amp.GradScaler inside the op."""
     gs = [g for g in grads if g is not None]
-    amax = torch.stack([g.abs().max() for g in gs]).max().clamp_min(1e-30)
-    s = torch.exp2(torch.floor(torch.log2(GRAD_TARGET / amax))).clamp(2.0 ** -24, 2.0 ** 60)
-    return s.reshape(1).to(torch.float32).contiguous()
+    assert 1 <= len(gs) <= 2
+    return grad_scale_dyn(gs[0], gs[1] if len(gs) > 1 else None, None)
+
+
+def grad_scale_dyn(a, b, m_dev, wa=1, wb=1):
+    """One-launch device-side loss scale; with m_dev only the first m_dev[0]*w elements of a / b are scanned."""
+    dev = a.device
+    scratch = torch.empty(1, dtype=torch.int32, device=dev)
+    out = torch.empty(1, dtype=torch.float32, device=dev)
+    call("pag_grad_scale", ptr(a), a.numel(), int(wa), ptr(b), b.numel() if b is not None else 0, int(wb), ptr(m_dev),
+         GRAD_TARGET, ptr(scratch), ptr(out))
+    return out
 
 
 class DecodeDCFn(Function):
@@ -421,7 +430,7 @@ class PanCompositeFn(Function):
         sem = torch.zeros(N, Cs, dtype=torch.float32, device=f.device) if Cs else None
         inst = torch.zeros(N, Ci, dtype=torch.float32, device=f.device) if Ci else None
         call("pag_pan_composite_fwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), HIDDEN, int(Cs), int(Ci),
-             int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature), ptr(w_), ptr(a_), ptr(r_), ptr(sem), ptr(inst))
+             int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature), ptr(w_), ptr(a_), ptr(r_), ptr(sem), ptr(inst), None)
         ctx.save_for_backward(f, df, lw, w_, a_, r_, *wt)
         ctx.cfg = (int(Cs), int(Ci), int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature))
         return sem, inst
@@ -439,7 +448,7 @@ class PanCompositeFn(Function):
         gp = torch.empty_like(f) if need else None
         if gs is not None or gi is not None:
             call("pag_pan_composite_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), ptr_array(grads), HIDDEN, Cs, Ci,
-                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), ptr(gs), ptr(gi), ptr(grad_scale(gs, gi)), ptr(gp))
+                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), ptr(gs), ptr(gi), ptr(grad_scale(gs, gi)), ptr(gp), None)
         elif gp is not None:
             gp.zero_()
         return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
@@ -506,3 +515,150 @@ def exponential_integration(feats, tau, boundary, exclusive=True):
     if feats is None or feats.numel() == 0:
         return feats, w
     return SumReduceFn.apply(feats * w, off), w
+
+
+# ------------------------------------------------------------------------------------------------
+# sync-free fused trace (training mode): march -> encode -> decode -> composite in one autograd node
+# ------------------------------------------------------------------------------------------------
+class FusedTraceFn(Function):
+    """PanopticPackedRFTracer.trace for ('ray' marching, permutohedral grids, tensor-core decoders) as ONE autograd
+    node: ~10 kernel launches forward / ~10 backward, no host synchronisation (the packed-sample count stays on the
+    device: every kernel reads it from the marcher's scan), no torch glue between the kernels.  Work buffers are
+    sized for the worst case N*S samples; only the first M rows are ever touched.
+
+    cfg: dict(octree, prefix, level, S, near, far, seed, bg_white, pos_half, lodw,
+              grid=(sf, shift, anneal, cap, L, n_agg), dgrid=(...) | None, pan_src in {'delta','separate','appearance','none'},
+              want_rgb, want_depth, Cs, Ci, sem_softmax, inst_softmax, inst_temperature)
+    """
+
+    @staticmethod
+    def forward(ctx, origins, dirs, cfg, table, dtable, *weights):
+        _chk(origins, dirs, table, *weights)
+        o, d = _f32(origins), _f32(dirs)
+        N, S, dev = o.shape[0], int(cfg['S']), o.device
+        Mmax = max(N * S, 1)
+        lin = _linspace(S, dev)
+        f32, i64 = torch.float32, torch.int64
+        pidx_tmp = torch.empty(Mmax, dtype=torch.int32, device=dev)
+        counts = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+        offsets = torch.empty(N + 1, dtype=i64, device=dev)
+        near = float(cfg['near'])
+        rng = float(torch.tensor(float(cfg['far']) - near, dtype=f32))
+        call("pag_march_ray_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng,
+             ptr(cfg['octree']), ptr(cfg['prefix']), int(cfg['level']), ptr(pidx_tmp), ptr(counts), ptr(offsets))
+        m_dev = offsets[N:]                      # device-side packed-sample count M
+        ridx = torch.empty(Mmax, dtype=i64, device=dev)
+        samples = torch.empty(Mmax, 3, dtype=f32, device=dev)
+        depths = torch.empty(Mmax, dtype=f32, device=dev)
+        deltas = torch.empty(Mmax, dtype=f32, device=dev)
+        call("pag_march_ray_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(pidx_tmp),
+             ptr(offsets), ptr(ridx), None, ptr(samples), ptr(depths), ptr(deltas), None)
+        sf, sh, an, cap, L, n_agg = cfg['grid']
+        IN = L * 2
+        tb = table.detach().contiguous()
+        feats = torch.empty(Mmax, IN, dtype=f32, device=dev)
+        ph = int(bool(cfg['pos_half']))
+        call("pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an), ptr(feats))
+        w = [_f32(x) for x in weights]
+        lodw = _f32(cfg['lodw'])
+        want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
+        sigma = torch.empty(Mmax, dtype=f32, device=dev)
+        rgb = torch.empty(Mmax, 3, dtype=f32, device=dev) if want_rgb else None
+        call("pag_decode_dc_fwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
+             HIDDEN, VIEW_DIM, int(want_rgb), ptr(sigma), ptr(rgb))
+        wgt = torch.empty(Mmax, dtype=f32, device=dev)
+        T = torch.empty(Mmax, dtype=f32, device=dev)
+        alpha = torch.empty(N, 1, dtype=f32, device=dev)
+        hit = torch.empty(N, dtype=torch.bool, device=dev)
+        rgb_o = torch.empty(N, 3, dtype=f32, device=dev) if want_rgb else None
+        rgbsum = torch.empty(N, 3, dtype=f32, device=dev) if want_rgb else None
+        dep_o = torch.empty(N, 1, dtype=f32, device=dev) if want_depth else None
+        bgw = int(bool(cfg['bg_white']))
+        call("pag_composite_fwd", ptr(sigma), ptr(deltas), ptr(depths) if want_depth else None, ptr(rgb), None, 0, None, 0,
+             ptr(offsets), N, bgw, ptr(wgt), ptr(T), ptr(alpha), ptr(hit), ptr(rgb_o), ptr(rgbsum), ptr(dep_o), None, None)
+        Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
+        sem_o = inst_o = dfeats = dtb = None
+        if Cs or Ci:
+            src = cfg['pan_src']
+            if src in ('delta', 'separate'):
+                dsf, dsh, dan, dcap, dL, dn_agg = cfg['dgrid']
+                dtb = dtable.detach().contiguous()
+                dfeats = torch.empty(Mmax, IN, dtype=f32, device=dev)
+                call("pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan), ptr(dfeats))
+            a, b = {'delta': (feats, dfeats), 'separate': (dfeats, None), 'appearance': (feats, None)}[src]
+            sem_o = torch.zeros(N, Cs, dtype=f32, device=dev) if Cs else None
+            inst_o = torch.zeros(N, Ci, dtype=f32, device=dev) if Ci else None
+            call("pag_pan_composite_fwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), HIDDEN, Cs, Ci,
+                 int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
+                 ptr(wgt), ptr(alpha), ptr(ridx), ptr(sem_o), ptr(inst_o), ptr(m_dev))
+        ctx.cfg = cfg
+        ctx.save_for_backward(o, d, offsets, ridx, samples, depths, deltas, feats, dfeats, sigma, rgb, wgt, T, alpha, rgbsum,
+                              tb, dtb, lodw, *w)
+        ctx.mark_non_differentiable(hit)
+        ctx.last_m_dev = m_dev
+        return alpha, hit, rgb_o, dep_o, sem_o, inst_o, m_dev
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_alpha, g_hit, g_rgb, g_depth, g_sem, g_inst, g_m):
+        (o, d, offsets, ridx, samples, depths, deltas, feats, dfeats, sigma, rgb, wgt, T, alpha, rgbsum, tb, dtb, lodw,
+         *w) = ctx.saved_tensors
+        cfg = ctx.cfg
+        N, dev = o.shape[0], o.device
+        Mmax, IN = feats.shape
+        m_dev = offsets[N:]
+        f32 = torch.float32
+        sf, sh, an, cap, L, n_agg = cfg['grid']
+        ph = int(bool(cfg['pos_half']))
+        Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
+        sizes = [x.numel() for x in w]
+        flat = torch.zeros(sum(sizes), dtype=f32, device=dev)          # all 20 decoder gradients: one memset
+        grads = [t.view_as(x) for t, x in zip(flat.split(sizes), w)]
+        g_dtable = None
+        gs = _f32(g_sem) if (g_sem is not None and Cs) else None
+        gi = _f32(g_inst) if (g_inst is not None and Ci) else None
+        g_feats_extra = None
+        if gs is not None or gi is not None:
+            src = cfg['pan_src']
+            a, b = {'delta': (feats, dfeats), 'separate': (dfeats, None), 'appearance': (feats, None)}[src]
+            scale = grad_scale_dyn(gs if gs is not None else gi, gi if gs is not None else None, None)
+            need_gp = src in ('delta', 'separate')          # 'appearance': features are detached -> nothing upstream
+            g_panop = torch.empty(Mmax, IN, dtype=f32, device=dev) if need_gp else None
+            call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), ptr_array(grads[10:]), HIDDEN,
+                 Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
+                 ptr(wgt), ptr(alpha), ptr(ridx), ptr(gs), ptr(gi), ptr(scale), ptr(g_panop), ptr(m_dev))
+            if need_gp:
+                dsf, dsh, dan, dcap, dL, dn_agg = cfg['dgrid']
+                g_dtable = torch.zeros_like(dtb)
+                call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
+                     ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
+        # scalar compositing backward -> per-sample sigma / rgb gradients
+        want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
+        ga = _f32(g_alpha) if g_alpha is not None else None
+        gr = _f32(g_rgb) if (g_rgb is not None and want_rgb) else None
+        gd = _f32(g_depth) if (g_depth is not None and want_depth) else None
+        g_table = torch.zeros_like(tb)
+        need_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        g_o = g_d = None
+        if ga is not None or gr is not None or gd is not None:
+            g_sigma = torch.empty(Mmax, dtype=f32, device=dev)
+            g_rgb_s = torch.empty(Mmax, 3, dtype=f32, device=dev) if gr is not None else None
+            call("pag_composite_bwd", ptr(sigma), ptr(deltas), ptr(depths) if gd is not None else None, ptr(rgb), ptr(offsets), N,
+                 int(bool(cfg['bg_white'])), ptr(wgt), ptr(T), ptr(alpha), ptr(rgbsum), ptr(ga), ptr(gr), ptr(gd), None, 0, None, 0,
+                 ptr(g_sigma), ptr(g_rgb_s), None, None)
+            scale = grad_scale_dyn(g_sigma, g_rgb_s, m_dev, 1, 3)
+            g_feats = torch.empty(Mmax, IN, dtype=f32, device=dev)
+            g_dir = torch.empty(Mmax, 3, dtype=f32, device=dev) if ctx.needs_input_grad[1] else None
+            call("pag_decode_dc_bwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
+                 ptr_array(grads[:10]), HIDDEN, VIEW_DIM, ptr(g_sigma), ptr(g_rgb_s), ptr(scale), ptr(g_feats), ptr(g_dir))
+            g_pos = torch.empty(Mmax, 3, dtype=f32, device=dev) if need_rays else None
+            call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
+                 ptr(g_feats), ptr(g_table), ptr(g_pos), int(n_agg))
+            if need_rays:   # d samples / d (origin, dir): segment sums over each ray's packed range
+                g_o = torch.empty(N, 3, dtype=f32, device=dev)
+                g_d = torch.empty(N, 3, dtype=f32, device=dev)
+                gpt = torch.addcmul(g_dir, g_pos, depths.unsqueeze(1)) if g_dir is not None else (g_pos * depths.unsqueeze(1))
+                call("pag_sum_reduce_fwd", ptr(g_pos), 3, ptr(offsets), N, ptr(g_o))
+                call("pag_sum_reduce_fwd", ptr(gpt.contiguous()), 3, ptr(offsets), N, ptr(g_d))
+        return (g_o if ctx.needs_input_grad[0] else None, g_d if ctx.needs_input_grad[1] else None, None,
+                g_table, g_dtable, *grads)

@@ -214,6 +214,54 @@ class PanopticNeF(BaseNeuralField):
                   and self.num_instances <= 208 and self.multiscale_type == 'cat')
         return plain and det and shapes and self.panoptic_features_type in (None, 'delta', 'separate', 'appearance')
 
+    def _pan_src(self):
+        """Which features feed the panoptic heads in the fused kernels."""
+        if not hasattr(self, 'delta_grid'):
+            return 'appearance'
+        return {None: 'delta', 'delta': 'delta', 'separate': 'separate', 'appearance': 'appearance'}.get(self.panoptic_features_type)
+
+    def fused_trace_cfg(self, channels, rays, num_steps, bg_color):
+        """Configuration for ops.FusedTraceFn (sync-free training trace), or None when this field / request is not
+        covered by it ('ray' marching on PermutoGrid fields with the reference decoder shapes, tensor-core mode)."""
+        from ..grids import PermutoGrid
+        pan = [c for c in ('semantics', 'inst_embedding') if c in channels]
+        if not self._use_tc() or not isinstance(self.grid, PermutoGrid) or not hasattr(self.grid, 'embedder'):
+            return None
+        if pan and not self.fused_panoptic_ok(channels):
+            return None
+        if self.multiscale_type != 'cat' or self.effective_feature_dim > 48 or self.effective_feature_dim % 4:
+            return None
+        src = self._pan_src() if pan else 'none'
+        if src is None:
+            return None
+        dev = rays.origins.device
+        blas = self.grid.blas.to(dev)
+
+        def enc(e):
+            return (e.scale_factor, e.random_shift_per_level, e.anneal_window, e.capacity, e.nr_levels, e.n_agg_levels)
+
+        seed = blas.jitter_seed
+        if not blas.fixed_jitter:
+            blas.jitter_seed = (blas.jitter_seed + 1) & 0x7FFFFFFF
+        dmin = float(rays.dist_min) if not torch.is_tensor(rays.dist_min) else float(rays.dist_min.flatten()[0])
+        dmax = float(rays.dist_max) if not torch.is_tensor(rays.dist_max) else float(rays.dist_max.flatten()[0])
+        return dict(octree=blas.octree, prefix=blas.prefix, level=self.grid.blas_level, S=int(num_steps), near=dmin, far=dmax,
+                    seed=seed, bg_white=(bg_color == 'white'), pos_half=torch.is_autocast_enabled(),
+                    lodw=self.lod_weights.to(dev), grid=enc(self.grid.embedder),
+                    dgrid=enc(self.delta_grid.embedder) if src in ('delta', 'separate') else None, pan_src=src,
+                    want_rgb='rgb' in channels, want_depth='depth' in channels,
+                    Cs=self.num_classes if 'semantics' in channels else 0,
+                    Ci=self.num_instances if 'inst_embedding' in channels else 0,
+                    sem_softmax=bool(self.sem_softmax), inst_softmax=bool(self.inst_softmax),
+                    inst_temperature=float(getattr(self, 'inst_soft_temperature', 0.0)))
+
+    def fused_trace_tensors(self):
+        """(color table, delta table | None, 20 decoder tensors) in the order ops.FusedTraceFn expects."""
+        wts = (_decoder_tensors(self.decoder_density, 1) + _decoder_tensors(self.decoder_color, 2)
+               + _decoder_tensors(self.decoder_semantics, 1) + _decoder_tensors(self.decoder_inst, 2))
+        dt = self.delta_grid.embedder.lattice_values if hasattr(self, 'delta_grid') else None
+        return self.grid.embedder.lattice_values, dt, wts
+
     def trace_composited(self, coords, ray_d, ridx_rows, deltas, depths, offsets, num_rays, channels, bg_white, lod_idx=None):
         """Decode + composite in one pass: per-ray dict(alpha, hit, rgb, depth, semantics, inst_embedding).
         The panoptic probabilities are composited inside the decoder kernel and never materialised."""

@@ -25,6 +25,7 @@ class PanopticPackedRFTracer(PackedRFTracer):
         self.panoptic_channels = {'semantics', 'inst_embedding'}
         self.ray_sparcity_reg = ray_sparcity_reg
         self.ray_max_travel = ray_max_travel
+        self.allow_fused = True     # sync-free fused trace in training mode ('ray' marching, PermutoGrid fields)
 
     def get_supported_channels(self):
         return {'depth', 'hit', 'rgb', 'alpha', 'semantics', 'inst_embedding'}
@@ -39,6 +40,20 @@ class PanopticPackedRFTracer(PackedRFTracer):
         dev = rays.origins.device
         if lod_idx is None:
             lod_idx = nef.grid.num_lods - 1
+
+        plain = not extra_channels and not (self.ray_sparcity_reg > 0.0 and stage == 'train')
+        if plain and raymarch_type == 'ray' and self.allow_fused and hasattr(nef, 'fused_trace_cfg'):
+            cfg = nef.fused_trace_cfg(channels, rays, num_steps, bg_color)
+            if cfg is not None:
+                # training mode, sync-free: march -> encode -> decode -> composite as one autograd node
+                table, dtable, wts = nef.fused_trace_tensors()
+                alpha, hit, rgb, depth, sem, inst, m_dev = ops.FusedTraceFn.apply(rays.origins, rays.dirs, cfg, table, dtable, *wts)
+                self.last_num_samples = m_dev            # device scalar (no host sync here)
+                outputs = {'alpha': alpha, 'hit': hit}
+                for name, val in (('rgb', rgb), ('depth', depth), ('semantics', sem), ('inst_embedding', inst)):
+                    if name in channels:
+                        outputs[name] = val
+                return RenderBuffer(**outputs)
 
         ridx, pidx, samples, depths, deltas, boundary = nef.grid.raymarch(
             rays, level=nef.grid.active_lods[lod_idx], num_samples=num_steps, raymarch_type=raymarch_type)

@@ -509,3 +509,35 @@ def test_fused_panoptic_composite_equals_modular(cuda_lib, name, mode):
     for k in res[0][1]:
         assert_close_norm(res[0][1][k], res[1][1][k], rel_l2=5e-3, max_frac=2e-2, msg="grad " + k)
     assert_close_norm(res[0][2], res[1][2], rel_l2=5e-3, max_frac=2e-2, msg="grad origins")
+
+
+@pytest.mark.parametrize("with_pose_grad", [False, True])
+def test_sync_free_fused_trace_equals_stepwise(cuda_lib, with_pose_grad):
+    """ops.FusedTraceFn (device-side sample count, worst-case buffers, no host sync) vs the step-by-step plugin path."""
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_ray")
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    res = []
+    for fused in (True, False):
+        nef = build_cuda_nef(g, DEV)
+        nef.decoder_precision = 'fp16'
+        tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=int(g["num_steps"]), bg_color='white')
+        tracer.allow_fused = fused
+        o = torch.from_numpy(g["o"]).to(DEV).requires_grad_(with_pose_grad)
+        d = torch.from_numpy(g["d"]).to(DEV).requires_grad_(with_pose_grad)
+        rb = tracer(nef, channels=chans, rays=Rays(origins=o, dirs=d, dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+        if fused:
+            assert torch.is_tensor(tracer.last_num_samples), "fused path keeps the sample count on the device"
+        loss = sum((getattr(rb, c) * torch.from_numpy(g["gw_" + c]).to(DEV)).sum() for c in chans)
+        loss.backward()
+        res.append(({c: getattr(rb, c).detach() for c in chans + ['alpha', 'hit']}, {k: p.grad.clone() for k, p in nef.named_parameters()},
+                    o.grad if with_pose_grad else None, d.grad if with_pose_grad else None))
+    assert torch.equal(res[0][0]['hit'], res[1][0]['hit'])
+    for c in chans + ['alpha']:
+        assert_close(res[0][0][c], res[1][0][c], rtol=1e-3, atol_scale=1e-3, msg=c)
+    for k in res[0][1]:
+        assert_close_norm(res[0][1][k], res[1][1][k], rel_l2=5e-3, max_frac=2e-2, msg="grad " + k)
+    if with_pose_grad:
+        assert_close_norm(res[0][2], res[1][2], rel_l2=5e-3, max_frac=2e-2, msg="grad origins")
+        assert_close_norm(res[0][3], res[1][3], rel_l2=5e-3, max_frac=2e-2, msg="grad dirs")
