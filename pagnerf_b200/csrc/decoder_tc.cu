@@ -62,23 +62,45 @@ __device__ __forceinline__ void dc_tc_stage(uint8_t* sm, const DcTcLayout& l, co
     stage_b32(b + 144, p.bc2, 64, 64); stage_b32(b + 208, p.bc3, 3, 16);
 }
 
-__global__ void __launch_bounds__(128) dc_tc_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
-                                                        const float* __restrict__ ray_d, int S, int64_t M, int IN,
-                                                        DcParams p, int want_rgb, float* __restrict__ sigma,
-                                                        float* __restrict__ rgb, const int64_t* __restrict__ m_dev,
-                                                        const int64_t* __restrict__ ridx) {
+#define DC_THREADS 512
+#define DC_NCG 4   // column groups per sample row: warps w, w+4, w+8, w+12 share TMEM lane quadrant w % 4
+
+// 16 features [16*cg, 16*cg+16) of the color-decoder input row [y16 | PE(-d) 27 | 0 pad 5], cg = 1, 2
+__device__ __forceinline__ void stage_cin_pe(uint8_t* tile, int row, int cg, float dx, float dy, float dz) {
+    float pe[PE_DIM];
+    view_embed(dx, dy, dz, pe);
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        v[i] = 0.f;
+#pragma unroll
+        for (int g = 1; g <= 2; ++g) {
+            const int k = 16 * (g - 1) + i;      // PE index
+            if (g == cg && k < PE_DIM) v[i] = pe[k];
+        }
+    }
+    tile_store8(tile, 2 * cg, row, v);
+    tile_store8(tile, 2 * cg + 1, row, v + 8);
+}
+
+__global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
+                                                               const float* __restrict__ ray_d, int S, int64_t M, int IN,
+                                                               DcParams p, int want_rgb, float* __restrict__ sigma,
+                                                               float* __restrict__ rgb, const int64_t* __restrict__ m_dev,
+                                                               const int64_t* __restrict__ ridx) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
     const DcTcLayout l = dc_tc_layout(IN, false);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane, c16 = 16 * cg;
     dc_tc_stage(sm, l, p, IN);
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 128);
     sync_to_mma();
     tc_fence_after();
-    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(q * 32) << 16);
     MmaBar mb{&bar_s, 0};
     const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
     uint8_t *T0 = sm + l.oX, *T1 = sm + l.oHd;
@@ -87,45 +109,47 @@ __global__ void __launch_bounds__(128) dc_tc_fwd_kernel(const float* __restrict_
                    wc2 = smem_u32(sm + l.oWc2), wc3 = smem_u32(sm + l.oWc3);
     const int64_t ntiles = (M + 127) / 128;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t m = tile * 128 + tid;
+        const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
-        stage_x(T0, tid, feats, nullptr, lodw, IN, l.nXc, mm);
+        stage_x_cg(T0, row, cg, DC_NCG, feats, nullptr, lodw, IN, l.nXc, mm);
         sync_to_mma();
         if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT0, wd1, 64, 64, l.INP, false); mb.commit(); }
         mb.wait();
-        epi_relu64(tl, bias, T1, tid);
+        epi_relu16(tl + c16, bias + c16, T1 + 2 * cg * TCH, row);
         sync_to_mma();
         if (tid == 0) { tc_fence_after(); mma16_fwd(tm + 64, aT1, wd2, 16, 16, 64, false); mb.commit(); }
         mb.wait();
-        float y[16];
-        tmem_ld16(tl + 64, y);
+        if (cg == 0) {
+            float y[16];
+            tmem_ld16(tl + 64, y);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] += bias[64 + i];
-        if (valid) sigma[m] = fmaxf(y[0], 0.f);
-        if (!want_rgb) { tc_fence_before(); __syncthreads(); continue; }
-        {
-            float pe[PE_DIM];
+            for (int i = 0; i < 16; ++i) y[i] += bias[64 + i];
+            if (valid) sigma[m] = fmaxf(y[0], 0.f);
+            if (want_rgb) { tile_store8(T0, 0, row, y); tile_store8(T0, 1, row, y + 8); }
+        } else if (want_rgb && cg <= 2) {
             const int64_t r = ridx ? ridx[mm] : mm / S;
-            view_embed(ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2], pe);
-            stage_cin(T0, tid, y, pe);
+            stage_cin_pe(T0, row, cg, ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2]);
         }
+        if (!want_rgb) { tc_fence_before(); __syncthreads(); continue; }
         sync_to_mma();
         if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT0, wc1, 64, 64, 48, false); mb.commit(); }
         mb.wait();
-        epi_relu64(tl, bias + 80, T1, tid);
+        epi_relu16(tl + c16, bias + 80 + c16, T1 + 2 * cg * TCH, row);
         sync_to_mma();
         if (tid == 0) { tc_fence_after(); mma16_fwd(tm + 64, aT1, wc2, 64, 64, 64, false); mb.commit(); }
         mb.wait();
-        epi_relu64(tl + 64, bias + 144, T0, tid);
+        epi_relu16(tl + 64 + c16, bias + 144 + c16, T0 + 2 * cg * TCH, row);
         sync_to_mma();
         if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT0, wc3, 16, 16, 64, false); mb.commit(); }
         mb.wait();
-        float c[16];
-        tmem_ld16(tl, c);
-        if (valid) {
+        if (cg == 0) {
+            float c[16];
+            tmem_ld16(tl, c);
+            if (valid) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) rgb[3 * m + j] = 1.f / (1.f + expf(-(c[j] + bias[208 + j])));
+                for (int j = 0; j < 3; ++j) rgb[3 * m + j] = 1.f / (1.f + __expf(-(c[j] + bias[208 + j])));
+            }
         }
         tc_fence_before();
         __syncthreads();
@@ -144,24 +168,26 @@ __global__ void __launch_bounds__(128) dc_tc_fwd_kernel(const float* __restrict_
 #define DCB_DWC2 304   // [64 x 64]
 #define DCB_DWC3 368   // [3  x 64]  -> 432 columns used
 
-__global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
-                                                        const float* __restrict__ ray_d, int S, int64_t M, int IN,
-                                                        DcParams p, const float* __restrict__ g_sigma,
-                                                        const float* __restrict__ g_rgb, const float* __restrict__ scale_ptr,
-                                                        float* __restrict__ g_feats, float* __restrict__ g_dir,
-                                                        const int64_t* __restrict__ m_dev, const int64_t* __restrict__ ridx) {
+__global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
+                                                               const float* __restrict__ ray_d, int S, int64_t M, int IN,
+                                                               DcParams p, const float* __restrict__ g_sigma,
+                                                               const float* __restrict__ g_rgb, const float* __restrict__ scale_ptr,
+                                                               float* __restrict__ g_feats, float* __restrict__ g_dir,
+                                                               const int64_t* __restrict__ m_dev, const int64_t* __restrict__ ridx) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
+    __shared__ float gdir_s[2][128][3];   // view-direction gradient partials of column groups 1 and 2
     const DcTcLayout l = dc_tc_layout(IN, true);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane, c16 = 16 * cg;
     dc_tc_stage(sm, l, p, IN);
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 512);
     sync_to_mma();
     tc_fence_after();
-    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tm = tmem_s, tl = tm + ((uint32_t)(q * 32) << 16);
     MmaBar mb{&bar_s, 0};
     const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
     uint8_t *G3 = sm + l.oG3, *Gy = sm + l.oGy, *X = sm + l.oX, *Cin = sm + l.oCin, *Hd = sm + l.oHd, *H1 = sm + l.oH1, *H2 = sm + l.oH2;
@@ -172,51 +198,53 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
     const float scale = scale_ptr ? __ldg(scale_ptr) : 1.f;
     const float inv_scale = 1.f / scale;
     const bool do_rgb = g_rgb != nullptr;
-    float db_d1[2] = {0.f, 0.f}, db_c1[2] = {0.f, 0.f}, db_c2[2] = {0.f, 0.f}, db_d2 = 0.f, db_c3 = 0.f;
+    float db_d1 = 0.f, db_c1 = 0.f, db_c2 = 0.f, db_d2 = 0.f, db_c3 = 0.f;
     const int64_t ntiles = (M + 127) / 128;
     bool first = true;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
-        const int64_t m = tile * 128 + tid;
+        const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
         // ---------------- forward recompute ----------------
-        stage_x(X, tid, feats, nullptr, lodw, IN, l.nXc, mm);
+        stage_x_cg(X, row, cg, DC_NCG, feats, nullptr, lodw, IN, l.nXc, mm);
         sync_to_mma();
         if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aX, wd1, 64, 64, l.INP, false); mb.commit(); }
         mb.wait();
-        const uint64_t mask_d = epi_relu64(tl + DCB_S0, bias, Hd, tid);
+        const uint32_t mask_d = epi_relu16(tl + DCB_S0 + c16, bias + c16, Hd + 2 * cg * TCH, row);
         sync_to_mma();
         if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S1, aHd, wd2, 16, 16, 64, false); mb.commit(); }
         mb.wait();
-        float y[16];
-        tmem_ld16(tl + DCB_S1, y);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] += bias[64 + i];
-        const bool y0pos = y[0] > 0.f;
+        bool y0pos = false;
+        float vdir[3] = {0.f, 0.f, 0.f};
+        uint32_t mask_1 = 0, mask_2 = 0;
         float dy[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) dy[i] = 0.f;
-        float vdir[3] = {0.f, 0.f, 0.f};
+        if (cg == 0) {
+            float y[16];
+            tmem_ld16(tl + DCB_S1, y);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] += bias[64 + i];
+            y0pos = y[0] > 0.f;
+            if (do_rgb) { tile_store8(Cin, 0, row, y); tile_store8(Cin, 1, row, y + 8); }
+        } else if (do_rgb && cg <= 2) {
+            const int64_t r = ridx ? ridx[mm] : mm / S;
+            vdir[0] = -ray_d[3 * r]; vdir[1] = -ray_d[3 * r + 1]; vdir[2] = -ray_d[3 * r + 2];
+            stage_cin_pe(Cin, row, cg, -vdir[0], -vdir[1], -vdir[2]);
+        }
         if (do_rgb) {
-            {
-                float pe[PE_DIM];
-                const int64_t r = ridx ? ridx[mm] : mm / S;
-                vdir[0] = -ray_d[3 * r]; vdir[1] = -ray_d[3 * r + 1]; vdir[2] = -ray_d[3 * r + 2];
-                view_embed(-vdir[0], -vdir[1], -vdir[2], pe);
-                stage_cin(Cin, tid, y, pe);
-            }
             sync_to_mma();
             if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aCin, wc1, 64, 64, 48, false); mb.commit(); }
             mb.wait();
-            const uint64_t mask_1 = epi_relu64(tl + DCB_S0, bias + 80, H1, tid);
+            mask_1 = epi_relu16(tl + DCB_S0 + c16, bias + 80 + c16, H1 + 2 * cg * TCH, row);
             sync_to_mma();
             if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S1, aH1, wc2, 64, 64, 64, false); mb.commit(); }
             mb.wait();
-            const uint64_t mask_2 = epi_relu64(tl + DCB_S1, bias + 144, H2, tid);
+            mask_2 = epi_relu16(tl + DCB_S1 + c16, bias + 144 + c16, H2 + 2 * cg * TCH, row);
             sync_to_mma();
             if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aH2, wc3, 16, 16, 64, false); mb.commit(); }
             mb.wait();
-            {   // d rgb_pre (sigmoid') -> G3 tile (16 features, 3 valid)
+            if (cg == 0) {   // d rgb_pre (sigmoid') -> G3 tile (16 features, 3 valid)
                 float c[16], g[16];
                 tmem_ld16(tl + DCB_S0, c);
 #pragma unroll
@@ -224,11 +252,11 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        const float s = 1.f / (1.f + expf(-(c[j] + bias[208 + j])));
-                        g[j] = g_rgb[3 * m + j] * s * (1.f - s) * scale;
+                        const float sg = 1.f / (1.f + __expf(-(c[j] + bias[208 + j])));
+                        g[j] = g_rgb[3 * m + j] * sg * (1.f - sg) * scale;
                     }
                 }
-                grad16_store(g, G3, tid, lane, db_c3);
+                grad16_store(g, G3, row, lane, db_c3);
             }
             // ---------------- color backward ----------------
             sync_to_mma();
@@ -239,7 +267,7 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
                 mb.commit();
             }
             mb.wait();
-            epi_grad64(tl + DCB_S1, mask_2, H2, tid, lane, db_c2);          // G2 overwrites H2
+            epi_grad16(tl + DCB_S1 + c16, mask_2, H2 + 2 * cg * TCH, row, lane, db_c2);     // G2 overwrites H2
             sync_to_mma();
             if (tid == 0) {
                 tc_fence_after();
@@ -248,7 +276,7 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
                 mb.commit();
             }
             mb.wait();
-            epi_grad64(tl + DCB_S0, mask_1, H1, tid, lane, db_c1);          // G1 overwrites H1
+            epi_grad16(tl + DCB_S0 + c16, mask_1, H1 + 2 * cg * TCH, row, lane, db_c1);     // G1 overwrites H1
             sync_to_mma();
             if (tid == 0) {
                 tc_fence_after();
@@ -257,40 +285,40 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
                 mb.commit();
             }
             mb.wait();
-            {   // d cin: first 16 -> dy, the rest -> view direction
-                float g[48];
+            if (cg == 0) {
+                tmem_ld16(tl + DCB_S1, dy);      // d cin[0:16] = d y16
+            } else if (cg <= 2 && g_dir) {      // d cin[16:43] -> view direction through the positional embedding
+                float g[16];
+                tmem_ld16(tl + DCB_S1 + c16, g);
+                float gv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                for (int c0 = 0; c0 < 48; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(tl + DCB_S1 + c0, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) g[c0 + i] = v[i];
+                for (int i = 0; i < 16; ++i) {
+                    const int k = 16 * (cg - 1) + i;      // PE index of this column (cg is warp-uniform)
+                    if (k < 3) gv[k] += g[i];
+                    else if (k < 3 + 3 * PE_F) { const int f = (k - 3) / 3, c = (k - 3) % 3; const float b = (float)(1 << f); gv[c] += b * cosf(vdir[c] * b) * g[i]; }
+                    else if (k < PE_DIM) { const int f = (k - 3 - 3 * PE_F) / 3, c = (k - 3 - 3 * PE_F) % 3; const float b = (float)(1 << f); gv[c] -= b * sinf(vdir[c] * b) * g[i]; }
                 }
+                gdir_s[cg - 1][row][0] = gv[0]; gdir_s[cg - 1][row][1] = gv[1]; gdir_s[cg - 1][row][2] = gv[2];
+            }
+            if (g_dir) {
+                __syncthreads();
+                if (cg == 0 && valid) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) dy[i] = g[i];
-                if (g_dir && valid) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float gv = g[16 + c];
-#pragma unroll
-                        for (int f = 0; f < PE_F; ++f) {
-                            const float b = (float)(1 << f), a = vdir[c] * b;
-                            gv += b * (cosf(a) * g[16 + 3 + 3 * f + c] - sinf(a) * g[16 + 3 + 3 * PE_F + 3 * f + c]);
-                        }
-                        g_dir[3 * m + c] = -gv * inv_scale;
-                    }
+                    for (int c = 0; c < 3; ++c) g_dir[3 * m + c] = -(gdir_s[0][row][c] + gdir_s[1][row][c]) * inv_scale;
                 }
             }
-        } else if (g_dir && valid) {
+        } else if (g_dir && valid && cg == 0) {
             g_dir[3 * m] = 0.f; g_dir[3 * m + 1] = 0.f; g_dir[3 * m + 2] = 0.f;
         }
         // ---------------- density backward ----------------
-        if (g_sigma && valid && y0pos) dy[0] += g_sigma[m] * scale;
-        if (!valid) {
+        if (cg == 0) {
+            if (g_sigma && valid && y0pos) dy[0] += g_sigma[m] * scale;
+            if (!valid) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dy[i] = 0.f;
+                for (int i = 0; i < 16; ++i) dy[i] = 0.f;
+            }
+            grad16_store(dy, Gy, row, lane, db_d2);
         }
-        grad16_store(dy, Gy, tid, lane, db_d2);
         sync_to_mma();
         if (tid == 0) {
             tc_fence_after();
@@ -299,7 +327,7 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
             mb.commit();
         }
         mb.wait();
-        epi_grad64(tl + DCB_S0, mask_d, Hd, tid, lane, db_d1);               // Gd overwrites Hd
+        epi_grad16(tl + DCB_S0 + c16, mask_d, Hd + 2 * cg * TCH, row, lane, db_d1);           // Gd overwrites Hd
         sync_to_mma();
         if (tid == 0) {
             tc_fence_after();
@@ -308,26 +336,25 @@ __global__ void __launch_bounds__(128) dc_tc_bwd_kernel(const float* __restrict_
             mb.commit();
         }
         mb.wait();
-        if (g_feats) store_dx(tl + DCB_S1, g_feats + mm * IN, lodw, IN, l.INP, inv_scale, valid);
+        if (g_feats && c16 < l.INP) store_dx16(tl + DCB_S1, g_feats + mm * IN, lodw, IN, c16, inv_scale, valid);
         tc_fence_before();
         __syncthreads();
     }
     // ---------------- flush weight / bias gradients (once per CTA) ----------------
     if (!first) {
         tc_fence_after();
-        flush_dw(tl + DCB_DWD1, p.gWd1, tid, 64, IN, l.INP, inv_scale);
-        flush_dw(tl + DCB_DWD2, p.gWd2, tid, 16, 64, 64, inv_scale);
-        const int f2 = scatter_base(lane, 64);
-        red_add_f32(p.gbd1 + f2, db_d1[0] * inv_scale); red_add_f32(p.gbd1 + f2 + 1, db_d1[1] * inv_scale);
-        const int f1 = scatter_base(lane, 32) >> 1;   // 16-feature scatter: 8*b4 + 4*b3 + 2*b2 + b1
-        if (!(lane & 1)) red_add_f32(p.gbd2 + f1, db_d2 * inv_scale);
+        const int f1 = scatter_base(lane, 32) >> 1;   // feature (of 16) owned by this lane pair
+        const bool own = !(lane & 1);
+        if (c16 < l.INP) flush_dw16(tl + DCB_DWD1, p.gWd1, row, 64, IN, c16, inv_scale);
+        flush_dw16(tl + DCB_DWD2, p.gWd2, row, 16, 64, c16, inv_scale);
+        if (own) red_add_f32(p.gbd1 + c16 + f1, db_d1 * inv_scale);
+        if (own && cg == 0) red_add_f32(p.gbd2 + f1, db_d2 * inv_scale);
         if (do_rgb) {
-            flush_dw(tl + DCB_DWC1, p.gWc1, tid, 64, CIN, 48, inv_scale);
-            flush_dw(tl + DCB_DWC2, p.gWc2, tid, 64, 64, 64, inv_scale);
-            flush_dw(tl + DCB_DWC3, p.gWc3, tid, 3, 64, 64, inv_scale);
-            red_add_f32(p.gbc1 + f2, db_c1[0] * inv_scale); red_add_f32(p.gbc1 + f2 + 1, db_c1[1] * inv_scale);
-            red_add_f32(p.gbc2 + f2, db_c2[0] * inv_scale); red_add_f32(p.gbc2 + f2 + 1, db_c2[1] * inv_scale);
-            if (!(lane & 1) && f1 < 3) red_add_f32(p.gbc3 + f1, db_c3 * inv_scale);
+            if (c16 < 48) flush_dw16(tl + DCB_DWC1, p.gWc1, row, 64, CIN, c16, inv_scale);
+            flush_dw16(tl + DCB_DWC2, p.gWc2, row, 64, 64, c16, inv_scale);
+            flush_dw16(tl + DCB_DWC3, p.gWc3, row, 3, 64, c16, inv_scale);
+            if (own) { red_add_f32(p.gbc1 + c16 + f1, db_c1 * inv_scale); red_add_f32(p.gbc2 + c16 + f1, db_c2 * inv_scale); }
+            if (own && cg == 0 && f1 < 3) red_add_f32(p.gbc3 + f1, db_c3 * inv_scale);
         }
     }
     tc_fence_before();
@@ -683,8 +710,8 @@ int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray
     int rc = tc_set_smem(dc_tc_fwd_kernel, l.total);
     if (rc) return rc;
     const int64_t tiles = (M + 127) / 128;
-    const int64_t cap = 4 * (int64_t)tc_num_sms();
-    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb, nullptr, nullptr);
+    const int64_t cap = 2 * (int64_t)tc_num_sms();
+    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb, nullptr, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -701,8 +728,8 @@ int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float*
     int rc = tc_set_smem(dc_tc_fwd_kernel, l.total);
     if (rc) return rc;
     const int64_t tiles = (M_max + 127) / 128;
-    const int64_t cap = 4 * (int64_t)tc_num_sms();
-    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx);
+    const int64_t cap = 2 * (int64_t)tc_num_sms();
+    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -721,7 +748,7 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
     if (rc) return rc;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = tc_num_sms();
-    dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
+    dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(
         feats, lodw, ray_d, S, M, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, nullptr, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
@@ -740,7 +767,7 @@ int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float*
     if (rc) return rc;
     const int64_t tiles = (M_max + 127) / 128;
     const int64_t cap = tc_num_sms();
-    dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), 128, l.total, (cudaStream_t)stream>>>(
+    dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(
         feats, lodw, ray_d, 1, M_max, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, m_dev, ridx);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
