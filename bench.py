@@ -269,6 +269,15 @@ ALGO = {
 }
 
 
+def measured_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture of this same command
+    (profiles/r01_traffic.json: {entry point: {"dram_bytes": .., "samples": ..}}), rescaled to this run's sample count."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -319,12 +328,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     wl = Workload(device, args.rays, seed=rank)
+    if world > 1:
+        from pagnerf_b200 import ops
+        ops.set_grad_sync(True)      # gradient all-reduce (NCCL, AVG) issued from inside the fused backward, overlapped
 
     def step(from_host):
-        out = wl.forward_backward(from_host=from_host)
-        if world > 1:
-            parallel.allreduce_grads(wl.params)
-        return out
+        return wl.forward_backward(from_host=from_host)
 
     def sync():
         if world > 1:
@@ -390,6 +399,10 @@ def main():
             ach = per * n_samples / dur / 1e12
             roof = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "traffic": None,
                     "note": "decoder flops vs the bf16 tensor peak"}
+        tr = measured_traffic(top[0])
+        if tr:
+            roof["traffic"] = tr["dram_bytes"] * n_samples / tr["samples"]
+            roof["traffic_source"] = "ncu --set full dram__bytes_read+write per launch (profiles/r01_ncu_full_top_kernels.md), scaled by packed samples"
         roof["peak_source"] = how
         roof["share_of_step"] = top[1]["ms_per_step"] / ms
         roof["samples_per_launch"] = n_samples

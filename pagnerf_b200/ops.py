@@ -520,6 +520,22 @@ def exponential_integration(feats, tau, boundary, exclusive=True):
 # ------------------------------------------------------------------------------------------------
 # sync-free fused trace (training mode): march -> encode -> decode -> composite in one autograd node
 # ------------------------------------------------------------------------------------------------
+_GRAD_SYNC = {"group": None, "enabled": False}
+
+
+def set_grad_sync(enabled, group=None):
+    """Ray-sharded data parallelism: when enabled, FusedTraceFn.backward all-reduces (AVG) the gradients it
+    produces itself -- the delta-grid table as soon as its scatter kernel is queued, so that the NCCL transfer over
+    NVLink overlaps the remaining colour-branch backward; the colour table and the flattened decoder gradients at the
+    end -- and returns already-reduced gradients.  One process per GPU, torch.distributed initialised by the caller."""
+    _GRAD_SYNC["enabled"], _GRAD_SYNC["group"] = bool(enabled), group
+
+
+def _allreduce_async(t):
+    import torch.distributed as dist
+    return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=_GRAD_SYNC["group"], async_op=True)
+
+
 class FusedTraceFn(Function):
     """PanopticPackedRFTracer.trace for ('ray' marching, permutohedral grids, tensor-core decoders) as ONE autograd
     node: ~10 kernel launches forward / ~10 backward, no host synchronisation (the packed-sample count stays on the
@@ -611,6 +627,7 @@ class FusedTraceFn(Function):
         sf, sh, an, cap, L, n_agg = cfg['grid']
         ph = int(bool(cfg['pos_half']))
         Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
+        sync, works = _GRAD_SYNC["enabled"], []
         sizes = [x.numel() for x in w]
         flat = torch.zeros(sum(sizes), dtype=f32, device=dev)          # all 20 decoder gradients: one memset
         grads = [t.view_as(x) for t, x in zip(flat.split(sizes), w)]
@@ -632,6 +649,8 @@ class FusedTraceFn(Function):
                 g_dtable = torch.zeros_like(dtb)
                 call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
                      ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
+                if sync:
+                    works.append(_allreduce_async(g_dtable))   # overlaps the colour-branch backward below
         # scalar compositing backward -> per-sample sigma / rgb gradients
         want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
         ga = _f32(g_alpha) if g_alpha is not None else None
@@ -660,5 +679,10 @@ class FusedTraceFn(Function):
                 gpt = torch.addcmul(g_dir, g_pos, depths.unsqueeze(1)) if g_dir is not None else (g_pos * depths.unsqueeze(1))
                 call("pag_sum_reduce_fwd", ptr(g_pos), 3, ptr(offsets), N, ptr(g_o))
                 call("pag_sum_reduce_fwd", ptr(gpt.contiguous()), 3, ptr(offsets), N, ptr(g_d))
+        if sync:
+            works.append(_allreduce_async(g_table))
+            works.append(_allreduce_async(flat))
+            for wk in works:
+                wk.wait()
         return (g_o if ctx.needs_input_grad[0] else None, g_d if ctx.needs_input_grad[1] else None, None,
                 g_table, g_dtable, *grads)
