@@ -128,28 +128,41 @@ class Workload:
             self.host.append(hb)
         self.dev = [[x.to(device) for x in hb] for hb in self.host]
         self.step_idx = 0
+        self.keep_rb = True
 
     def h2d_bytes(self):
         return sum(x.numel() * x.element_size() for x in self.host[0])
 
-    def forward_backward(self, batch=None, from_host=False):
+    def loss_of(self, o, d, tr, ts, ti):
+        """forward + loss of one step (what a trainer's step() does between zero_grad and backward)."""
         from pagnerf_b200.wisp_compat import Rays
-        b = self.step_idx % len(self.host) if batch is None else batch
-        self.step_idx += 1
-        if from_host:
-            o, d, tr, ts, ti = [x.to(self.device, non_blocking=True) for x in self.host[b]]
-        else:
-            o, d, tr, ts, ti = self.dev[b]
-        for p in self.params:
-            p.grad = None
         rays = Rays(origins=o, dirs=d, dist_min=NEAR, dist_max=FAR)
         # the reference's training step runs under autocast (pc_nerf/trainer.py:429): fp16-rounded coords,
         # fp16-operand / fp32-accumulate decoders; the loss scaling of its GradScaler happens inside our kernels
         with torch.autocast('cuda', dtype=torch.float16, enabled=self.amp):
             rb = self.tracer(self.nef, channels=self.channels, rays=rays, lod_idx=None, stage='train')
             loss = loss_fn(rb.rgb.float(), rb.semantics.float(), rb.inst_embedding.float(), tr, ts, ti)
+        # NB: keeping `rb` alive keeps its autograd graph -- and the parameters' AccumulateGrad nodes, which remember the
+        # stream they were created on -- alive; CUDA-graph capture needs them re-created on the capture stream.
+        self.last_rb = rb if self.keep_rb else None
+        return loss
+
+    def batch(self, from_host=False):
+        b = self.step_idx % len(self.host)
+        self.step_idx += 1
+        if from_host:
+            return self.host[b]
+        return self.dev[b]
+
+    def forward_backward(self, batch=None, from_host=False):
+        b = self.batch(from_host)
+        if from_host:
+            b = [x.to(self.device, non_blocking=True) for x in b]
+        for p in self.params:
+            p.grad = None
+        loss = self.loss_of(*b)
         loss.backward()
-        return {"rb": rb, "loss": loss, "ridx": getattr(self.tracer, "_last_ridx", torch.zeros(1, device=self.device))}
+        return {"rb": self.last_rb, "loss": loss, "ridx": getattr(self.tracer, "_last_ridx", torch.zeros(1, device=self.device))}
 
 
 def build_workload(device, n_rays=N_RAYS, seed=0):
@@ -289,12 +302,13 @@ def peaks():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--cpu-sample-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -342,37 +356,66 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step(False)
+    sync()
+    # ---- CUDA-graph capture of the whole step (single GPU; the fused path has static launch geometry) --------------
+    graphed, graph_note = None, "eager"
+    if world == 1 and not args.no_graph:
+        try:
+            from pagnerf_b200.graph import GraphedStep
+            wl.keep_rb, wl.last_rb = False, None
+            graphed = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef)
+            graph_note = "whole step (fwd + loss + bwd) replayed as one CUDA graph"
+        except Exception as e:   # keep the eager number rather than fail the bench
+            graphed, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {e})"
+            torch.cuda.synchronize()
+
+    def run(from_host):
+        if graphed is None:
+            return step(from_host)["loss"]
+        return graphed(*wl.batch(from_host))      # host batches are pinned: copy_ into the static buffers is the H2D
+
+    for _ in range(3):
+        run(False)
     # ---- device-resident timing (value) ------------------------------------------------------------
     sync()
     clocks = ClockSampler(local) if rank == 0 else None
-    _lib.timing_reset(True)
-    l0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    t_host0 = time.perf_counter()
     for _ in range(args.steps):
-        out = step(False)
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time to enqueue one step (no sync)
+        run(False)
     e1.record()
     sync()
     ms = e0.elapsed_time(e1) / args.steps
-    launches = (_lib.launch_count - l0) // args.steps
-    per_kernel = _lib.timing_report()
-    for v in per_kernel.values():
-        v["ms_per_step"] = v["ms_total"] / args.steps
-    _lib.timing_reset(False)
+    t_host0 = time.perf_counter()           # CPU time to enqueue a step into an empty stream (GPU-bound when << ms_per_step)
+    for _ in range(3):
+        run(False)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / 3
+    sync()
     # ---- end-to-end timing (host pinned inputs -> H2D -> step -> D2H loss) -------------------------
     for _ in range(2):
-        step(True)
+        run(True)
     sync()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        o = step(True)
-        _ = float(o["loss"].item())
+        _ = float(run(True).item())
     t1.record()
     sync()
     ms_e2e = t0.elapsed_time(t1) / args.steps
+    # ---- per-entry-point CUDA-event timing of the same step, eager (events cannot be read back from a graph) ---------
+    ksteps = min(args.steps, 20)
+    sync()
+    wl.keep_rb = True
+    _lib.timing_reset(True)
+    l0 = _lib.launch_count
+    for _ in range(ksteps):
+        step(False)
+    sync()
+    launches = (_lib.launch_count - l0) // ksteps
+    per_kernel = _lib.timing_report()
+    for v in per_kernel.values():
+        v["ms_per_step"] = v["ms_total"] / ksteps
+    _lib.timing_reset(False)
     clk = clocks.stop() if clocks else None
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
@@ -419,7 +462,8 @@ def main():
               "data": "synthetic",
               "config": dict(config, l2="no explicit flush: ray batches cycle and the per-step working set (2x50 MB tables + "
                                         "[M,200] fp32 instance activations and grads) exceeds the 126 MB L2",
-                             packed_samples_per_step=n_samples),
+                             packed_samples_per_step=n_samples, execution=graph_note,
+                             kernel_breakdown="per-entry-point CUDA events over %d eager steps of the same workload" % ksteps),
               "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": wl.h2d_bytes(),
                       "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
               "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,

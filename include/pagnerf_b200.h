@@ -32,18 +32,19 @@ int pag_exclusive_scan_i32(const int32_t* in, int64_t N, int64_t* out, void* str
 
 /* 'ray' raymarch, pass 1 (tracers/panoptic_packed_rf_tracer.py:85 with raymarch_type='ray'):
  * S jittered steps per ray, octree lookup per step.  Writes pidx_tmp[N*S], counts[N], offsets[N+1].
- * jitter f32[N,S] nullable (then the counter RNG with `seed` is used); linspace = torch.linspace(0,1,S). */
+ * jitter f32[N,S] nullable (then the counter RNG with `seed` is used); linspace = torch.linspace(0,1,S).
+ * seed_dev (nullable): device word overriding `seed`, so that CUDA-graph replays can advance the jitter stream. */
 int pag_march_ray_count(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
                         const float* jitter, uint32_t seed, float dist_min, float dist_range,
                         const uint8_t* octree, const int32_t* prefix, int level,
-                        int32_t* pidx_tmp, int32_t* counts, int64_t* offsets, void* stream);
+                        int32_t* pidx_tmp, int32_t* counts, int64_t* offsets, const uint32_t* seed_dev, void* stream);
 /* pass 2: packed outputs of size M = offsets[N]: ridx/pidx i64[M], samples f32[M,3], depths/deltas f32[M],
  * boundary u8[M]. */
 int pag_march_ray_emit(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
                        const float* jitter, uint32_t seed, float dist_min, float dist_range,
                        const int32_t* pidx_tmp, const int64_t* offsets,
                        int64_t* ridx, int64_t* pidx, float* samples, float* depths, float* deltas,
-                       uint8_t* boundary, void* stream);
+                       uint8_t* boundary, const uint32_t* seed_dev, void* stream);
 
 /* kaolin.render.spc.unbatched_raytrace(return_depth, with_exit): count pass then emit pass;
  * nuggets (ridx,pidx,[entry,exit]) in kaolin's order.  offsets[N+1] doubles as the per-ray first-nugget index. */
@@ -165,6 +166,8 @@ int pag_composite_bwd(const float* sigma, const float* deltas, const float* dept
                       const float* alpha, const float* rgbsum, const float* g_alpha, const float* g_rgb,
                       const float* g_depth, const float* g_sem, int Cs, const float* g_inst, int Ci, float* g_sigma,
                       float* g_rgb_s, float* g_sem_s, float* g_inst_s, void* stream);
+/* debugging aid: cudaStreamCaptureStatus of `stream` (0 none, 1 active, 2 invalidated), negative on error. */
+int pag_capture_status(void* stream);
 /* power-of-two loss scale for the fp16 tensor-core backward (the GradScaler of pc_nerf/trainer.py:582, on the device). */
 int pag_grad_scale(const float* a, int64_t na, int wa, const float* b, int64_t nb, int wb, const int64_t* m_dev,
                    float target, uint32_t* scratch, float* out_scale, void* stream);

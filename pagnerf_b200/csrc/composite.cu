@@ -303,6 +303,14 @@ int pag_grad_scale(const float* a, int64_t na, int wa, const float* b, int64_t n
     return PAG_OK;
 }
 
+// debugging aid: cudaStreamCaptureStatus of `stream` (0 none, 1 active, 2 invalidated), or -(cudaError) on failure
+int pag_capture_status(void* stream) {
+    cudaStreamCaptureStatus st;
+    cudaError_t e = cudaStreamIsCapturing((cudaStream_t)stream, &st);
+    if (e != cudaSuccess) return -(int)e;
+    return (int)st;
+}
+
 int pag_ray_offsets(const int64_t* ridx, int64_t M, int64_t R, int64_t* offsets /*[R+1]*/, void* stream) {
     ray_offsets_kernel<<<pag_grid(M + 1, 256), 256, 0, (cudaStream_t)stream>>>(ridx, M, R, offsets);
     PAG_LAUNCH_CHECK();

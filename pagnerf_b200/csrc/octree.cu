@@ -97,7 +97,9 @@ __global__ void march_ray_count_kernel(const float* __restrict__ org, const floa
                                        int S, const float* __restrict__ lin, const float* __restrict__ jitter,
                                        uint32_t seed, float near, float range,
                                        const uint8_t* __restrict__ octree, const int* __restrict__ prefix,
-                                       int level, int* __restrict__ pidx_tmp, int* __restrict__ counts) {
+                                       int level, int* __restrict__ pidx_tmp, int* __restrict__ counts,
+                                       const uint32_t* __restrict__ seed_dev) {
+    if (seed_dev) seed = __ldg(seed_dev);   // CUDA-graph replays advance the jitter stream through device memory
     const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (ray >= N) return;
@@ -126,7 +128,9 @@ __global__ void march_ray_emit_kernel(const float* __restrict__ org, const float
                                       const int* __restrict__ pidx_tmp, const int64_t* __restrict__ offsets,
                                       int64_t* __restrict__ ridx, int64_t* __restrict__ pidx,
                                       float* __restrict__ samples, float* __restrict__ depths,
-                                      float* __restrict__ deltas, uint8_t* __restrict__ boundary) {
+                                      float* __restrict__ deltas, uint8_t* __restrict__ boundary,
+                                      const uint32_t* __restrict__ seed_dev) {
+    if (seed_dev) seed = __ldg(seed_dev);
     const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (ray >= N) return;
@@ -319,13 +323,13 @@ int pag_exclusive_scan_i32(const int32_t* in, int64_t N, int64_t* out /*[N+1]*/,
 int pag_march_ray_count(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
                         const float* jitter, uint32_t seed, float dist_min, float dist_range,
                         const uint8_t* octree, const int32_t* prefix, int level,
-                        int32_t* pidx_tmp, int32_t* counts, int64_t* offsets, void* stream) {
+                        int32_t* pidx_tmp, int32_t* counts, int64_t* offsets, const uint32_t* seed_dev, void* stream) {
     if (level < 0 || level > PAG_MAX_LEVEL || S <= 0) return PAG_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (N > 0) {
         march_ray_count_kernel<<<pag_grid(N * 32, 256), 256, 0, st>>>(origins, dirs, N, S, linspace, jitter, seed,
                                                                      dist_min, dist_range, octree, prefix, level,
-                                                                     pidx_tmp, counts);
+                                                                     pidx_tmp, counts, seed_dev);
         PAG_LAUNCH_CHECK();
     }
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, offsets);
@@ -337,11 +341,11 @@ int pag_march_ray_emit(const float* origins, const float* dirs, int64_t N, int S
                        const float* jitter, uint32_t seed, float dist_min, float dist_range,
                        const int32_t* pidx_tmp, const int64_t* offsets,
                        int64_t* ridx, int64_t* pidx, float* samples, float* depths, float* deltas,
-                       uint8_t* boundary, void* stream) {
+                       uint8_t* boundary, const uint32_t* seed_dev, void* stream) {
     if (N == 0) return PAG_OK;
     march_ray_emit_kernel<<<pag_grid(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         origins, dirs, N, S, linspace, jitter, seed, dist_min, dist_range, pidx_tmp, offsets, ridx, pidx, samples,
-        depths, deltas, boundary);
+        depths, deltas, boundary, seed_dev);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

@@ -59,7 +59,7 @@ def raymarch_ray(octree, prefix, origins, dirs, level, num_samples, dist_min, di
     jit = _f32(jitter) if jitter is not None else None
     near, rng = float(dist_min), float(torch.tensor(float(dist_max) - float(dist_min), dtype=torch.float32))
     call("pag_march_ray_count", ptr(o), ptr(d), N, S, ptr(lin), ptr(jit), int(seed), near, rng,
-         ptr(octree), ptr(prefix), int(level), ptr(pidx_tmp), ptr(counts), ptr(offsets))
+         ptr(octree), ptr(prefix), int(level), ptr(pidx_tmp), ptr(counts), ptr(offsets), None)
     M = int(offsets[-1].item())  # the one host sync the tensor-shaped plugin API needs
     ridx = torch.empty(M, dtype=torch.int64, device=dev)
     pidx = torch.empty(M, dtype=torch.int64, device=dev)
@@ -69,7 +69,7 @@ def raymarch_ray(octree, prefix, origins, dirs, level, num_samples, dist_min, di
     boundary = torch.empty(M, dtype=torch.bool, device=dev)
     if M:
         call("pag_march_ray_emit", ptr(o), ptr(d), N, S, ptr(lin), ptr(jit), int(seed), near, rng,
-             ptr(pidx_tmp), ptr(offsets), ptr(ridx), ptr(pidx), ptr(samples), ptr(depths), ptr(deltas), ptr(boundary))
+             ptr(pidx_tmp), ptr(offsets), ptr(ridx), ptr(pidx), ptr(samples), ptr(depths), ptr(deltas), ptr(boundary), None)
     return ridx, pidx, samples, depths, deltas, boundary, offsets
 
 
@@ -560,15 +560,18 @@ class FusedTraceFn(Function):
         offsets = torch.empty(N + 1, dtype=i64, device=dev)
         near = float(cfg['near'])
         rng = float(torch.tensor(float(cfg['far']) - near, dtype=f32))
+        seed_dev = cfg.get('seed_dev')
         call("pag_march_ray_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng,
-             ptr(cfg['octree']), ptr(cfg['prefix']), int(cfg['level']), ptr(pidx_tmp), ptr(counts), ptr(offsets))
+             ptr(cfg['octree']), ptr(cfg['prefix']), int(cfg['level']), ptr(pidx_tmp), ptr(counts), ptr(offsets), ptr(seed_dev))
         m_dev = offsets[N:]                      # device-side packed-sample count M
         ridx = torch.empty(Mmax, dtype=i64, device=dev)
         samples = torch.empty(Mmax, 3, dtype=f32, device=dev)
         depths = torch.empty(Mmax, dtype=f32, device=dev)
         deltas = torch.empty(Mmax, dtype=f32, device=dev)
         call("pag_march_ray_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(pidx_tmp),
-             ptr(offsets), ptr(ridx), None, ptr(samples), ptr(depths), ptr(deltas), None)
+             ptr(offsets), ptr(ridx), None, ptr(samples), ptr(depths), ptr(deltas), None, ptr(seed_dev))
+        if seed_dev is not None:
+            seed_dev.add_(1)                     # next replay / step draws the next jitter stream
         sf, sh, an, cap, L, n_agg = cfg['grid']
         IN = L * 2
         tb = table.detach().contiguous()

@@ -165,6 +165,14 @@ class PanopticNeF(BaseNeuralField):
     # 'fp32' / 'fp16' force one of the two kernels.
     decoder_precision = 'auto'
 
+    def _lodw(self, device):
+        """lod_weights on `device`, cached (the attribute is a CPU tensor that LOD annealing may replace / edit)."""
+        t = self.lod_weights
+        key = (id(t), t._version, str(device))
+        if getattr(self, '_lodw_key', None) != key:
+            self._lodw_key, self._lodw_dev = key, t.detach().to(device=device, dtype=torch.float32).contiguous()
+        return self._lodw_dev
+
     def _use_tc(self):
         if self.decoder_precision == 'auto':
             return torch.is_autocast_enabled()
@@ -172,14 +180,14 @@ class PanopticNeF(BaseNeuralField):
 
     def _dc(self, feats, ray_d, num_samples, want_rgb):
         w = _decoder_tensors(self.decoder_density, 1) + _decoder_tensors(self.decoder_color, 2)
-        lodw = self.lod_weights.to(feats.device)
+        lodw = self._lodw(feats.device)
         return ops.DecodeDCFn.apply(feats, lodw, ray_d, num_samples, want_rgb, self._use_tc(), *w)
 
     def _pan(self, feats, dfeats, want_sem, want_inst, inst_temperature=0.0):
         """semantic / instance heads on (feats + dfeats) * lod_weights; non-default sigmoid / normalize
         options are composed on the host from the raw logits."""
         w = _decoder_tensors(self.decoder_semantics, 1) + _decoder_tensors(self.decoder_inst, 2)
-        lodw = self.lod_weights.to(feats.device)
+        lodw = self._lodw(feats.device)
         sem_plain = not (self.sem_sigmoid or self.sem_normalize)
         inst_plain = not (self.inst_sigmoid or self.inst_normalize)
         Cs = self.num_classes if want_sem else 0
@@ -246,8 +254,8 @@ class PanopticNeF(BaseNeuralField):
         dmin = float(rays.dist_min) if not torch.is_tensor(rays.dist_min) else float(rays.dist_min.flatten()[0])
         dmax = float(rays.dist_max) if not torch.is_tensor(rays.dist_max) else float(rays.dist_max.flatten()[0])
         return dict(octree=blas.octree, prefix=blas.prefix, level=self.grid.blas_level, S=int(num_steps), near=dmin, far=dmax,
-                    seed=seed, bg_white=(bg_color == 'white'), pos_half=torch.is_autocast_enabled(),
-                    lodw=self.lod_weights.to(dev), grid=enc(self.grid.embedder),
+                    seed=seed, seed_dev=getattr(blas, 'seed_tensor', None), bg_white=(bg_color == 'white'), pos_half=torch.is_autocast_enabled(),
+                    lodw=self._lodw(dev), grid=enc(self.grid.embedder),
                     dgrid=enc(self.delta_grid.embedder) if src in ('delta', 'separate') else None, pan_src=src,
                     want_rgb='rgb' in channels, want_depth='depth' in channels,
                     Cs=self.num_classes if 'semantics' in channels else 0,
@@ -281,7 +289,7 @@ class PanopticNeF(BaseNeuralField):
         if want_sem or want_inst:
             a, b = self._panoptic_inputs(feats, coords, lod_idx)
             wts = _decoder_tensors(self.decoder_semantics, 1) + _decoder_tensors(self.decoder_inst, 2)
-            lodw = self.lod_weights.to(feats.device)
+            lodw = self._lodw(feats.device)
             sem_o, inst_o = ops.PanCompositeFn.apply(
                 a, b, lodw, w, alpha.detach(), ridx_rows, num_rays, self.num_classes if want_sem else 0,
                 self.num_instances if want_inst else 0, bool(self.sem_softmax), bool(self.inst_softmax),

@@ -541,3 +541,31 @@ def test_sync_free_fused_trace_equals_stepwise(cuda_lib, with_pose_grad):
     if with_pose_grad:
         assert_close_norm(res[0][2], res[1][2], rel_l2=5e-3, max_frac=2e-2, msg="grad origins")
         assert_close_norm(res[0][3], res[1][3], rel_l2=5e-3, max_frac=2e-2, msg="grad dirs")
+
+
+def test_cuda_graph_replay_matches_eager(cuda_lib):
+    """The fused training step is capturable as one CUDA graph (no host sync, device-side sample count and jitter seed):
+    replayed gradients == eager gradients for the same jitter stream, and the stream advances between replays."""
+    import bench
+    from pagnerf_b200.graph import GraphedStep
+    dev = torch.device(DEV)
+    wl = bench.Workload(dev, n_rays=2048, seed=0, n_batches=2)
+    wl.keep_rb = False
+    blas = wl.nef.grid.blas
+    blas.fixed_jitter, blas.jitter_seed = True, 5
+    g = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef)
+    seed_before = int(blas.seed_tensor.item())
+    loss_g = float(g(*wl.dev[1]))
+    grads_g = [p.grad.clone() for p in wl.params]
+    assert int(blas.seed_tensor.item()) == seed_before + 1
+    # eager step with the same batch and the same jitter seed
+    blas.seed_tensor.fill_(seed_before)
+    for p in wl.params:
+        p.grad = None
+    loss_e = wl.loss_of(*wl.dev[1])
+    loss_e.backward()
+    assert abs(loss_g - float(loss_e)) <= 1e-5 * abs(float(loss_e))
+    for a, p in zip(grads_g, wl.params):
+        assert_close_norm(a, p.grad, rel_l2=1e-4, max_frac=1e-3, msg="graph vs eager grad")
+    l2 = float(g(*wl.dev[1]))
+    assert l2 != loss_g, "jitter stream must advance between replays"
