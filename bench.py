@@ -406,6 +406,8 @@ def main():
     ksteps = min(args.steps, 20)
     sync()
     wl.keep_rb = True
+    from pagnerf_b200 import ops as _ops
+    _ops.BRANCH_OVERLAP = False            # serialise the two branch streams so that per-kernel durations are exclusive
     _lib.timing_reset(True)
     l0 = _lib.launch_count
     for _ in range(ksteps):
@@ -416,6 +418,7 @@ def main():
     for v in per_kernel.values():
         v["ms_per_step"] = v["ms_total"] / ksteps
     _lib.timing_reset(False)
+    _ops.BRANCH_OVERLAP = True
     clk = clocks.stop() if clocks else None
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:

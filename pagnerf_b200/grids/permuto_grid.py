@@ -16,7 +16,7 @@ from .base import HashGridBase
 
 class PermutoEncoding(nn.Module):
     def __init__(self, pos_dim, capacity, nr_levels, nr_feat_per_level, scale_per_level,
-                 apply_random_shift_per_level=True, agg_scale_threshold=0.02):
+                 apply_random_shift_per_level=True, agg_scale_threshold=0.05):
         super().__init__()
         if pos_dim != 3 or nr_feat_per_level != 2:
             raise NotImplementedError("csrc/permuto.cu is specialised to pos_dim=3, 2 features per level "
@@ -30,7 +30,8 @@ class PermutoEncoding(nn.Module):
         sf = np.stack([1.0 / np.sqrt((i + 1) * (i + 2)) / scales for i in range(3)], axis=1)
         self.register_buffer('scale_factor', torch.from_numpy(sf.astype(np.float32)))
         self.register_buffer('anneal_window', torch.ones(nr_levels))
-        # coarse levels (lattice spacing >= threshold of the unit cube) use warp-aggregated scatter in backward
+        # coarse levels (lattice spacing >= 5 % of the unit cube) use warp-aggregated scatter in backward; measured on the
+        # bench workload (tests/permuto_tune.py, 410 k samples): 0 levels 1249 us, 4: 445, 8: 193 (best), 10: 215, 14: 357
         self.n_agg_levels = int((scales >= agg_scale_threshold).sum())
 
     def output_dims(self):

@@ -521,6 +521,19 @@ def exponential_integration(feats, tau, boundary, exclusive=True):
 # sync-free fused trace (training mode): march -> encode -> decode -> composite in one autograd node
 # ------------------------------------------------------------------------------------------------
 _GRAD_SYNC = {"group": None, "enabled": False}
+_SIDE_STREAMS = {}
+BRANCH_OVERLAP = True    # run the independent branches of the fused trace on two streams (bench.py disables it for its
+                         # per-kernel CUDA-event pass so that kernel durations do not overlap)
+
+
+def _side_stream(device):
+    """One auxiliary stream per device for the branch-level concurrency inside the fused trace."""
+    if not BRANCH_OVERLAP:
+        return torch.cuda.current_stream()
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 def set_grad_sync(enabled, group=None):
@@ -581,6 +594,21 @@ class FusedTraceFn(Function):
         w = [_f32(x) for x in weights]
         lodw = _f32(cfg['lodw'])
         want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
+        Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
+        src = cfg['pan_src'] if (Cs or Ci) else 'none'
+        dfeats = dtb = None
+        main = torch.cuda.current_stream()
+        side, ev_side = None, None
+        if src in ('delta', 'separate'):
+            # the delta-grid encode only needs the samples: run it on a side stream, concurrently with the colour
+            # decode + scalar compositing (both kernels leave most of the L1 / LSU bandwidth idle)
+            dsf, dsh, dan, dcap, dL, dn_agg = cfg['dgrid']
+            dtb = dtable.detach().contiguous()
+            dfeats = torch.empty(Mmax, IN, dtype=f32, device=dev)
+            side = _side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                call("pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan), ptr(dfeats))
         sigma = torch.empty(Mmax, dtype=f32, device=dev)
         rgb = torch.empty(Mmax, 3, dtype=f32, device=dev) if want_rgb else None
         call("pag_decode_dc_fwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
@@ -595,18 +623,13 @@ class FusedTraceFn(Function):
         bgw = int(bool(cfg['bg_white']))
         call("pag_composite_fwd", ptr(sigma), ptr(deltas), ptr(depths) if want_depth else None, ptr(rgb), None, 0, None, 0,
              ptr(offsets), N, bgw, ptr(wgt), ptr(T), ptr(alpha), ptr(hit), ptr(rgb_o), ptr(rgbsum), ptr(dep_o), None, None)
-        Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
-        sem_o = inst_o = dfeats = dtb = None
+        sem_o = inst_o = None
         if Cs or Ci:
-            src = cfg['pan_src']
-            if src in ('delta', 'separate'):
-                dsf, dsh, dan, dcap, dL, dn_agg = cfg['dgrid']
-                dtb = dtable.detach().contiguous()
-                dfeats = torch.empty(Mmax, IN, dtype=f32, device=dev)
-                call("pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan), ptr(dfeats))
-            a, b = {'delta': (feats, dfeats), 'separate': (dfeats, None), 'appearance': (feats, None)}[src]
             sem_o = torch.zeros(N, Cs, dtype=f32, device=dev) if Cs else None
             inst_o = torch.zeros(N, Ci, dtype=f32, device=dev) if Ci else None
+            if side is not None:
+                main.wait_stream(side)
+            a, b = {'delta': (feats, dfeats), 'separate': (dfeats, None), 'appearance': (feats, None)}[src]
             call("pag_pan_composite_fwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), HIDDEN, Cs, Ci,
                  int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
                  ptr(wgt), ptr(alpha), ptr(ridx), ptr(sem_o), ptr(inst_o), ptr(m_dev))
@@ -637,23 +660,30 @@ class FusedTraceFn(Function):
         g_dtable = None
         gs = _f32(g_sem) if (g_sem is not None and Cs) else None
         gi = _f32(g_inst) if (g_inst is not None and Ci) else None
-        g_feats_extra = None
+        main = torch.cuda.current_stream()
+        side = None
         if gs is not None or gi is not None:
+            # panoptic chain (heads backward -> delta-grid scatter [-> all-reduce]) on a side stream; it shares nothing
+            # with the colour chain below except read-only inputs, and the two sets of kernels overlap on the SMs
             src = cfg['pan_src']
             a, b = {'delta': (feats, dfeats), 'separate': (dfeats, None), 'appearance': (feats, None)}[src]
-            scale = grad_scale_dyn(gs if gs is not None else gi, gi if gs is not None else None, None)
             need_gp = src in ('delta', 'separate')          # 'appearance': features are detached -> nothing upstream
             g_panop = torch.empty(Mmax, IN, dtype=f32, device=dev) if need_gp else None
-            call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), ptr_array(grads[10:]), HIDDEN,
-                 Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
-                 ptr(wgt), ptr(alpha), ptr(ridx), ptr(gs), ptr(gi), ptr(scale), ptr(g_panop), ptr(m_dev))
             if need_gp:
                 dsf, dsh, dan, dcap, dL, dn_agg = cfg['dgrid']
                 g_dtable = torch.zeros_like(dtb)
-                call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
-                     ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
-                if sync:
-                    works.append(_allreduce_async(g_dtable))   # overlaps the colour-branch backward below
+            side = _side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                scale_p = grad_scale_dyn(gs if gs is not None else gi, gi if gs is not None else None, None)
+                call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), ptr_array(grads[10:]), HIDDEN,
+                     Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
+                     ptr(wgt), ptr(alpha), ptr(ridx), ptr(gs), ptr(gi), ptr(scale_p), ptr(g_panop), ptr(m_dev))
+                if need_gp:
+                    call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
+                         ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
+                    if sync:
+                        works.append(_allreduce_async(g_dtable))   # overlaps the colour-branch backward
         # scalar compositing backward -> per-sample sigma / rgb gradients
         want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
         ga = _f32(g_alpha) if g_alpha is not None else None
@@ -682,6 +712,8 @@ class FusedTraceFn(Function):
                 gpt = torch.addcmul(g_dir, g_pos, depths.unsqueeze(1)) if g_dir is not None else (g_pos * depths.unsqueeze(1))
                 call("pag_sum_reduce_fwd", ptr(g_pos), 3, ptr(offsets), N, ptr(g_o))
                 call("pag_sum_reduce_fwd", ptr(gpt.contiguous()), 3, ptr(offsets), N, ptr(g_d))
+        if side is not None:
+            main.wait_stream(side)
         if sync:
             works.append(_allreduce_async(g_table))
             works.append(_allreduce_async(flat))

@@ -569,3 +569,47 @@ def test_cuda_graph_replay_matches_eager(cuda_lib):
         assert_close_norm(a, p.grad, rel_l2=1e-4, max_frac=1e-3, msg="graph vs eager grad")
     l2 = float(g(*wl.dev[1]))
     assert l2 != loss_g, "jitter stream must advance between replays"
+
+
+def test_fused_trace_all_rays_miss(cuda_lib):
+    """Edge case of the sync-free path: the device-side packed-sample count is 0 (every ray misses the octree)."""
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_ray")
+    nef = build_cuda_nef(g, DEV)
+    nef.decoder_precision = 'fp16'
+    tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=16, bg_color='white')
+    N = 37
+    o = torch.full((N, 3), 5.0, device=DEV)
+    d = torch.nn.functional.normalize(torch.ones(N, 3, device=DEV), dim=-1)
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    rb = tracer(nef, channels=chans, rays=Rays(origins=o, dirs=d, dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+    assert int(tracer.last_num_samples.item()) == 0
+    assert torch.all(rb.rgb == 1.0) and torch.all(rb.alpha == 0) and not rb.hit.any()
+    assert torch.all(rb.depth == 0) and torch.all(rb.semantics == 0) and torch.all(rb.inst_embedding == 0)
+    (rb.rgb.sum() + rb.semantics.sum() + rb.inst_embedding.sum() + rb.depth.sum()).backward()
+    for n, p in nef.named_parameters():
+        assert p.grad is not None and torch.all(p.grad == 0), n
+
+
+@pytest.mark.parametrize("N", [1, 31, 1000])
+def test_fused_trace_ragged_sizes_vs_stepwise(cuda_lib, N):
+    """Ragged ray counts (not multiples of the 128-sample tile / 32-lane warp) through both paths."""
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_ray")
+    gen = torch.Generator().manual_seed(N)
+    o = torch.stack([torch.rand(N, generator=gen) * 1.2 - 0.6, torch.rand(N, generator=gen) * 1.2 - 0.6, torch.full((N,), 0.9)], 1)
+    tgt = torch.stack([torch.rand(N, generator=gen) * 1.8 - 0.9, torch.rand(N, generator=gen) * 1.8 - 0.9, -torch.rand(N, generator=gen) * 0.9], 1)
+    d = torch.nn.functional.normalize(tgt - o, dim=-1)
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    outs = []
+    for fused in (True, False):
+        nef = build_cuda_nef(g, DEV)
+        nef.decoder_precision = 'fp16'
+        tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=24, bg_color='black')
+        tracer.allow_fused = fused
+        rb = tracer(nef, channels=chans, rays=Rays(origins=o.to(DEV), dirs=d.to(DEV), dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+        outs.append({c: getattr(rb, c).detach() for c in chans + ['alpha']})
+    for c in chans + ['alpha']:
+        assert_close(outs[0][c], outs[1][c], rtol=1e-3, atol_scale=1e-3, msg=c)
