@@ -30,7 +30,7 @@ __host__ __device__ inline PanCompFwdLayout pan_comp_fwd_layout(int IN, int Cs, 
     l.oX = o; o += l.nXc * TCH;
     l.oT1 = o; o += 8 * TCH;
     l.oT2 = o; o += 8 * TCH;
-    l.oStage = o; o += 16 * 32 * 33 * 4;   // one transpose buffer per warp (16 warps)
+    l.oStage = 0;   // 16 fp16 transpose buffers [32][34] (34 KB) alias X|T1|T2 (>= 36 KB), all dead once the last MMA has completed
     l.oCR = o; o += 4 * 32 * 8;           // per lane quadrant: c[32] floats + ray[32] ints
     o = (o + 15) & ~15;
     l.oWs1 = o; o += l.nXc * 64 * 16;
@@ -46,8 +46,9 @@ __host__ __device__ inline PanCompFwdLayout pan_comp_fwd_layout(int IN, int Cs, 
 #define PCF_THREADS 512
 #define PCF_NCG 4
 
-// weighted segment-sum of one transposed 32-column block (stage[row][col]) over the warp's rows into out[N, C]
-__device__ __forceinline__ void comp_block(const float* stage, const float* __restrict__ wc, const int* __restrict__ wr, int nrows,
+#define STG_LD 34   // halfs per staged row: 17 words -> conflict-free transposed access
+// weighted segment-sum of one transposed 32-column block (stage[row][col], fp16) over the warp's rows into out[N, C]
+__device__ __forceinline__ void comp_block(const __half* stage, const float* __restrict__ wc, const int* __restrict__ wr, int nrows,
                                            float* __restrict__ out, int C, int c0, int lane) {
     if (c0 + lane < C && nrows > 0) {
         float acc = 0.f;
@@ -59,7 +60,7 @@ __device__ __forceinline__ void comp_block(const float* stage, const float* __re
                 acc = 0.f;
                 cur = ray;
             }
-            acc = fmaf(wc[r], stage[r * 33 + lane], acc);
+            acc = fmaf(wc[r], __half2float(stage[r * STG_LD + lane]), acc);
         }
         red_add_f32(out + (int64_t)cur * C + c0 + lane, acc);
     }
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
     const uint32_t ws1 = smem_u32(sm + l.oWs1), ws2 = smem_u32(sm + l.oWs2), wi1 = smem_u32(sm + l.oWi1),
                    wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
     const uint32_t semcol = (Ci > 0) ? (uint32_t)(l.CiP > 64 ? l.CiP : 64) : 128u;
-    float* stage = reinterpret_cast<float*>(sm + l.oStage) + warp * (32 * 33);     // one transpose buffer per warp
+    __half* stage = reinterpret_cast<__half*>(sm + l.oStage) + warp * (32 * STG_LD);  // one transpose buffer per warp
     float* wc = reinterpret_cast<float*>(sm + l.oCR) + q * 64;                      // shared by the 4 column groups of a quadrant
     int* wr = reinterpret_cast<int*>(wc + 32);
     const int c16 = 16 * cg;
@@ -207,10 +208,12 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
                         float v[16];
                         tmem_ld16(tl + c0 + 16 * h, v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
+                        for (int i = 0; i < 16; i += 2) {
                             const int j = c0 + 16 * h + i;
-                            const float z = (v[i] + (j < Ci ? bi3[j] : 0.f)) * inst_inv_temp;
-                            stage[lane * 33 + 16 * h + i] = inst_softmax ? __expf(z - mx) * inv : z;
+                            const float z0 = (v[i] + (j < Ci ? bi3[j] : 0.f)) * inst_inv_temp;
+                            const float z1 = (v[i + 1] + (j + 1 < Ci ? bi3[j + 1] : 0.f)) * inst_inv_temp;
+                            const float p0 = inst_softmax ? __expf(z0 - mx) * inv : z0, p1 = inst_softmax ? __expf(z1 - mx) * inv : z1;
+                            *reinterpret_cast<__half2*>(stage + lane * STG_LD + 16 * h + i) = __floats2half2_rn(p0, p1);
                         }
                     }
                 }
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
             for (int j = 0; j < 16; ++j) { z[j] = (j < Cs) ? (sem_softmax ? __expf(z[j] - mx) : z[j]) : 0.f; sum += z[j]; }
             const float inv = sem_softmax ? 1.f / sum : 1.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) stage[lane * 33 + j] = z[j] * inv;
+            for (int j = 0; j < 16; ++j) stage[lane * STG_LD + j] = __float2half_rn(z[j] * inv);
             __syncwarp();
             comp_block(stage, wc, wr, nrows, out_sem, Cs, 0, lane);
             __syncwarp();
@@ -609,7 +612,7 @@ int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const floa
     if (e != cudaSuccess) return (int)e;
     const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
     const int64_t tiles = (M + 127) / 128;
-    const int64_t cap = (int64_t)fused_num_sms();
+    const int64_t cap = 2 * (int64_t)fused_num_sms();   // 109 KB smem + 256 TMEM columns per CTA: two CTAs per SM
     pan_comp_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), PCF_THREADS, l.total, (cudaStream_t)stream>>>(
         feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, out_sem, out_inst, m_dev);
     PAG_LAUNCH_CHECK();
