@@ -45,6 +45,13 @@ __host__ __device__ inline PanCompFwdLayout pan_comp_fwd_layout(int IN, int Cs, 
 
 #define PCF_THREADS 512
 #define PCF_NCG 4
+#define LOG2E_F 1.4426950408889634f
+
+// instance output bias in the units the softmax works in: b * (log2e / T), -inf on the padded columns (p = 0 there);
+// without softmax: b / T and 0
+__device__ __forceinline__ void stage_bi3_scaled(float* dst, const float* __restrict__ b, int n, int np, float s2, int softmax) {
+    for (int i = threadIdx.x; i < np; i += blockDim.x) dst[i] = (i < n) ? __ldg(b + i) * s2 : (softmax ? -INFINITY : 0.f);
+}
 
 #define STG_LD 34   // halfs per staged row: 17 words -> conflict-free transposed access
 // weighted segment-sum of one transposed 32-column block (stage[row][col], fp16) over the warp's rows into out[N, C]
@@ -70,7 +77,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
     const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw, int64_t M, int IN,
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
     const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
-    float* __restrict__ out_sem, float* __restrict__ out_inst, const int64_t* __restrict__ m_dev) {
+    float* __restrict__ out_sem, float* __restrict__ out_inst, float* __restrict__ inst_lse, const int64_t* __restrict__ m_dev) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
@@ -80,6 +87,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2;
     const int row = 32 * q + lane;
+    const float s2 = inst_softmax ? inst_inv_temp * LOG2E_F : inst_inv_temp;   // logits -> log2-domain scaled logits
     {   // weights (same images as decoder_tc.cu)
         float* b = reinterpret_cast<float*>(sm + l.oBias);
         if (Cs > 0) {
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
             stage_w16(reinterpret_cast<__half*>(sm + l.oWi2), p.Wi2, 64, 64, 64, 64);
             stage_w16(reinterpret_cast<__half*>(sm + l.oWi3), p.Wi3, Ci, 64, l.CiP, 64);
             stage_b32(b + 64 + l.CsP, p.bi1, 64, 64); stage_b32(b + 128 + l.CsP, p.bi2, 64, 64);
-            stage_b32(b + 192 + l.CsP, p.bi3, Ci, l.CiP);
+            stage_bi3_scaled(b + 192 + l.CsP, p.bi3, Ci, l.CiP, s2, inst_softmax);
         }
     }
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
@@ -167,59 +175,76 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
             sync_to_mma();
             if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT1, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
             mb.wait();
-            // softmax statistics: 16-column block b belongs to column group b % 4
-            float mx = -INFINITY, sum = 0.f;
+            // 32-column block b2 belongs to column group b2 % 4 (two blocks per group at most: CiP <= 208).
+            // Pass 1 (softmax only): block-wise online max / sum with ONE exp2 per logit; the exponentials, taken
+            // relative to the running maximum bref[.] of their 16-column block, go back into TMEM over the logits.
+            float bref[4] = {0.f, 0.f, 0.f, 0.f};
+            float inv = 1.f, gm = 0.f;
             if (inst_softmax) {
+                float mx = -INFINITY, sum = 0.f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int c0 = 16 * (cg + PCF_NCG * k);
-                    if (c0 < l.CiP) {
-                        float v[16];
-                        tmem_ld16(tl + c0, v);
+                for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (c0 + i < Ci) {
-                                const float z = (v[i] + bi3[c0 + i]) * inst_inv_temp;
-                                const float nm = fmaxf(mx, z);
-                                sum = sum * __expf(mx - nm) + __expf(z - nm);
-                                mx = nm;
+                    for (int h = 0; h < 2; ++h) {
+                        const int c0 = 32 * cg + 128 * kk + 16 * h;
+                        if (c0 < l.CiP) {
+                            float v[16];
+                            tmem_ld16(tl + c0, v);
+                            float bm = -INFINITY;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(bi3 + c0 + i);   // pre-scaled, -inf on padding
+                                v[i] = fmaf(v[i], s2, b4.x); v[i + 1] = fmaf(v[i + 1], s2, b4.y);
+                                v[i + 2] = fmaf(v[i + 2], s2, b4.z); v[i + 3] = fmaf(v[i + 3], s2, b4.w);
+                                bm = fmaxf(fmaxf(bm, fmaxf(v[i], v[i + 1])), fmaxf(v[i + 2], v[i + 3]));
                             }
+                            const float nm = fmaxf(mx, bm);
+                            sum *= fast_exp2(mx - nm);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { v[i] = fast_exp2(v[i] - nm); sum += v[i]; }
+                            mx = nm; bref[2 * kk + h] = nm;
+                            tmem_st16(tl + c0, v);
+                        }
                     }
                 }
                 part_s[cg][row][0] = mx; part_s[cg][row][1] = sum;
                 __syncthreads();
-                float gm = -INFINITY;
+                gm = -INFINITY;
 #pragma unroll
                 for (int k = 0; k < PCF_NCG; ++k) gm = fmaxf(gm, part_s[k][row][0]);
                 float gs = 0.f;
 #pragma unroll
-                for (int k = 0; k < PCF_NCG; ++k) {
-                    const float pm = part_s[k][row][0];
-                    gs = fmaf(part_s[k][row][1], (pm == -INFINITY) ? 0.f : __expf(pm - gm), gs);
-                }
-                mx = gm; sum = gs;
+                for (int k = 0; k < PCF_NCG; ++k) gs = fmaf(part_s[k][row][1], fast_exp2(part_s[k][row][0] - gm), gs);
+                inv = 1.f / gs;
+                if (cg == 0 && valid && inst_lse) inst_lse[m] = gm + fast_log2(gs);   // log2-domain logsumexp for the backward
             }
-            const float inv = inst_softmax ? 1.f / sum : 1.f;
-            // probabilities -> transpose -> weighted segment sums; 32-column block b2 belongs to column group b2 % 4
-            for (int c0 = 32 * cg; c0 < l.CiP; c0 += 32 * PCF_NCG) {
+            // Pass 2: probabilities -> fp16 transpose buffer -> weighted segment sums
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (c0 + 16 * h < l.CiP) {
-                        float v[16];
-                        tmem_ld16(tl + c0 + 16 * h, v);
+            for (int kk = 0; kk < 2; ++kk) {
+                const int c0 = 32 * cg + 128 * kk;
+                if (c0 < l.CiP) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) {
-                            const int j = c0 + 16 * h + i;
-                            const float z0 = (v[i] + (j < Ci ? bi3[j] : 0.f)) * inst_inv_temp;
-                            const float z1 = (v[i + 1] + (j + 1 < Ci ? bi3[j + 1] : 0.f)) * inst_inv_temp;
-                            const float p0 = inst_softmax ? __expf(z0 - mx) * inv : z0, p1 = inst_softmax ? __expf(z1 - mx) * inv : z1;
-                            *reinterpret_cast<__half2*>(stage + lane * STG_LD + 16 * h + i) = __floats2half2_rn(p0, p1);
+                    for (int h = 0; h < 2; ++h) {
+                        if (c0 + 16 * h < l.CiP) {
+                            float v[16];
+                            tmem_ld16(tl + c0 + 16 * h, v);
+                            if (inst_softmax) {
+                                const float f = fast_exp2(bref[2 * kk + h] - gm) * inv;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] *= f;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], s2, bi3[c0 + 16 * h + i]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2)
+                                *reinterpret_cast<__half2*>(stage + lane * STG_LD + 16 * h + i) = __floats2half2_rn(v[i], v[i + 1]);
                         }
                     }
+                    __syncwarp();
+                    comp_block(stage, wc, wr, nrows, out_inst, Ci, c0, lane);
+                    __syncwarp();
                 }
-                __syncwarp();
-                comp_block(stage, wc, wr, nrows, out_inst, Ci, c0, lane);
-                __syncwarp();
             }
         }
         if (Cs > 0 && cg == 0) {   // semantic head: 16 columns, one column group
@@ -299,22 +324,30 @@ __device__ __forceinline__ void flush_dw_T(uint32_t taddr, float* __restrict__ g
 #define PCB_THREADS 512
 #define PCB_NCG 4   // column groups per row
 
+// four consecutive per-ray output gradients (zeros past the last class)
+__device__ __forceinline__ float4 load_g4(const float* __restrict__ grow, int j, int C, bool vec4) {
+    if (vec4) return (j < C) ? __ldg(reinterpret_cast<const float4*>(grow + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    return make_float4(j < C ? __ldg(grow + j) : 0.f, j + 1 < C ? __ldg(grow + j + 1) : 0.f,
+                       j + 2 < C ? __ldg(grow + j + 2) : 0.f, j + 3 < C ? __ldg(grow + j + 3) : 0.f);
+}
+
 __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw, int64_t M, int IN,
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
     const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
-    const float* __restrict__ g_sem, const float* __restrict__ g_inst, const float* __restrict__ scale_ptr,
-    float* __restrict__ g_panop, const int64_t* __restrict__ m_dev) {
+    const float* __restrict__ g_sem, const float* __restrict__ g_inst, const float* __restrict__ inst_lse,
+    const float* __restrict__ scale_ptr, float* __restrict__ g_panop, const int64_t* __restrict__ m_dev) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
-    __shared__ float part_s[PCB_NCG][128][3];   // per column group: (max, Z, E) of the row's softmax statistics
+    __shared__ float part_s[PCB_NCG][128];      // per column group: partial <p, g> of the row
     const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant, column group
     const int row = 32 * q + lane;
     const bool do_sem = (Cs > 0) && g_sem, do_inst = (Ci > 0) && g_inst;
+    const float s2 = inst_softmax ? inst_inv_temp * LOG2E_F : inst_inv_temp;
     {
         float* b = reinterpret_cast<float*>(sm + l.oBias);
         if (do_sem) {
@@ -327,7 +360,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             stage_w16(reinterpret_cast<__half*>(sm + l.oWi2), p.Wi2, 64, 64, 64, 64);
             stage_w16(reinterpret_cast<__half*>(sm + l.oWi3), p.Wi3, Ci, 64, l.CiP, 64);
             stage_b32(b + 64 + l.CsP, p.bi1, 64, 64); stage_b32(b + 128 + l.CsP, p.bi2, 64, 64);
-            stage_b32(b + 192 + l.CsP, p.bi3, Ci, l.CiP);
+            stage_bi3_scaled(b + 192 + l.CsP, p.bi3, Ci, l.CiP, s2, inst_softmax);
         }
     }
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
@@ -420,9 +453,13 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             sync_to_mma();
             if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aH2, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
             mb.wait();
+            // d logit_j = c * p_j * (g_j - <p, g>) / T with p_j = 2^(z_j - lse) from the forward's log-sum-exp: one
+            // exp2 per logit; the probabilities go back into TMEM over the logits for the second pass.
             const float* grow = g_inst + ray * Ci;
-            float mx = -INFINITY, Z = 0.f, E = 0.f;
+            const bool vec4 = !(Ci & 3);
+            float dot = 0.f;
             if (inst_softmax) {
+                const float nl = -__ldg(inst_lse + mm);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int c0 = 16 * (cg + PCB_NCG * k);
@@ -430,54 +467,37 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                         float v[16];
                         tmem_ld16(tl + c0, v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (c0 + i < Ci) {
-                                const float z = (v[i] + bi3[c0 + i]) * inst_inv_temp;
-                                const float gj = __ldg(grow + c0 + i);
-                                const float nm = fmaxf(mx, z);
-                                const float r = __expf(mx - nm), e = __expf(z - nm);
-                                Z = Z * r + e;
-                                E = E * r + e * gj;
-                                mx = nm;
-                            }
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bi3 + c0 + i);   // pre-scaled, -inf on padding
+                            const float4 g4 = load_g4(grow, c0 + i, Ci, vec4);
+                            v[i] = fast_exp2(fmaf(v[i], s2, b4.x) + nl);         dot = fmaf(v[i], g4.x, dot);
+                            v[i + 1] = fast_exp2(fmaf(v[i + 1], s2, b4.y) + nl); dot = fmaf(v[i + 1], g4.y, dot);
+                            v[i + 2] = fast_exp2(fmaf(v[i + 2], s2, b4.z) + nl); dot = fmaf(v[i + 2], g4.z, dot);
+                            v[i + 3] = fast_exp2(fmaf(v[i + 3], s2, b4.w) + nl); dot = fmaf(v[i + 3], g4.w, dot);
+                        }
+                        tmem_st16(tl + c0, v);
                     }
                 }
-                part_s[cg][row][0] = mx; part_s[cg][row][1] = Z; part_s[cg][row][2] = E;
+                part_s[cg][row] = dot;
                 __syncthreads();
-                float gm = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < PCB_NCG; ++k) gm = fmaxf(gm, part_s[k][row][0]);
-                float gZ = 0.f, gE = 0.f;
-#pragma unroll
-                for (int k = 0; k < PCB_NCG; ++k) {
-                    const float pm = part_s[k][row][0];
-                    const float r = (pm == -INFINITY) ? 0.f : __expf(pm - gm);
-                    gZ = fmaf(part_s[k][row][1], r, gZ);
-                    gE = fmaf(part_s[k][row][2], r, gE);
-                }
-                mx = gm; Z = gZ; E = gE;
+                dot = (part_s[0][row] + part_s[1][row]) + (part_s[2][row] + part_s[3][row]);
             }
-            const float iz = inst_softmax ? 1.f / Z : 1.f, dot = E * iz;
+            const float c2 = cs * inst_inv_temp;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int c0 = 16 * (cg + PCB_NCG * k);
                 if (c0 < l.CiP) {
-                    float t[16], v[16];
-                    tmem_ld16(tl + c0, t);
+                    float v[16];
+                    if (inst_softmax) tmem_ld16(tl + c0, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int j = c0 + i;
-                        float d = 0.f;
-                        if (j < Ci) {
-                            const float gj = __ldg(grow + j);
-                            if (inst_softmax) {
-                                const float pj = __expf((t[i] + bi3[j]) * inst_inv_temp - mx) * iz;
-                                d = cs * pj * (gj - dot) * inst_inv_temp;
-                            } else {
-                                d = cs * gj * inst_inv_temp;
-                            }
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 g4 = load_g4(grow, c0 + i, Ci, vec4);
+                        if (inst_softmax) {
+                            v[i] = c2 * v[i] * (g4.x - dot);         v[i + 1] = c2 * v[i + 1] * (g4.y - dot);
+                            v[i + 2] = c2 * v[i + 2] * (g4.z - dot); v[i + 3] = c2 * v[i + 3] * (g4.w - dot);
+                        } else {
+                            v[i] = c2 * g4.x; v[i + 1] = c2 * g4.y; v[i + 2] = c2 * g4.z; v[i + 3] = c2 * g4.w;
                         }
-                        v[i] = d;
                     }
                     grad16_store(v, Gi + (c0 / 8) * TCH, row, lane, db_i3[k]);
                 }
@@ -601,7 +621,7 @@ extern "C" {
 int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
                              float inst_temperature, const float* w, const float* alpha, const int64_t* ridx,
-                             float* out_sem, float* out_inst, const int64_t* m_dev, void* stream) {
+                             float* out_sem, float* out_inst, float* inst_lse, const int64_t* m_dev, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
     PanParams p{};
@@ -614,7 +634,7 @@ int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const floa
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = 2 * (int64_t)fused_num_sms();   // 109 KB smem + 256 TMEM columns per CTA: two CTAs per SM
     pan_comp_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), PCF_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, out_sem, out_inst, m_dev);
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, out_sem, out_inst, inst_lse, m_dev);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -623,9 +643,10 @@ int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const floa
 int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
-                             const int64_t* ridx, const float* g_sem, const float* g_inst, const float* grad_scale,
-                             float* g_panop, const int64_t* m_dev, void* stream) {
+                             const int64_t* ridx, const float* g_sem, const float* g_inst, const float* inst_lse,
+                             const float* grad_scale, float* g_panop, const int64_t* m_dev, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
+    if (Ci > 0 && g_inst && inst_softmax && !inst_lse) return PAG_ERR_ARG;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
     PanParams p{};
     fill_pan_f(p, weights, grads);
@@ -637,7 +658,7 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = fused_num_sms();
     pan_comp_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), PCB_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, grad_scale, g_panop, m_dev);
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, inst_lse, grad_scale, g_panop, m_dev);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

@@ -429,8 +429,11 @@ class PanCompositeFn(Function):
         r_ = ridx.to(torch.int64).contiguous()
         sem = torch.zeros(N, Cs, dtype=torch.float32, device=f.device) if Cs else None
         inst = torch.zeros(N, Ci, dtype=torch.float32, device=f.device) if Ci else None
+        lse = torch.empty(M, dtype=torch.float32, device=f.device) if (Ci and inst_softmax) else None
         call("pag_pan_composite_fwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), HIDDEN, int(Cs), int(Ci),
-             int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature), ptr(w_), ptr(a_), ptr(r_), ptr(sem), ptr(inst), None)
+             int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature), ptr(w_), ptr(a_), ptr(r_), ptr(sem), ptr(inst),
+             ptr(lse), None)
+        ctx.lse = lse
         ctx.save_for_backward(f, df, lw, w_, a_, r_, *wt)
         ctx.cfg = (int(Cs), int(Ci), int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature))
         return sem, inst
@@ -448,7 +451,7 @@ class PanCompositeFn(Function):
         gp = torch.empty_like(f) if need else None
         if gs is not None or gi is not None:
             call("pag_pan_composite_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), ptr_array(grads), HIDDEN, Cs, Ci,
-                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), ptr(gs), ptr(gi), ptr(grad_scale(gs, gi)), ptr(gp), None)
+                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(grad_scale(gs, gi)), ptr(gp), None)
         elif gp is not None:
             gp.zero_()
         return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
@@ -624,15 +627,18 @@ class FusedTraceFn(Function):
         call("pag_composite_fwd", ptr(sigma), ptr(deltas), ptr(depths) if want_depth else None, ptr(rgb), None, 0, None, 0,
              ptr(offsets), N, bgw, ptr(wgt), ptr(T), ptr(alpha), ptr(hit), ptr(rgb_o), ptr(rgbsum), ptr(dep_o), None, None)
         sem_o = inst_o = None
+        ctx.lse = None
         if Cs or Ci:
             sem_o = torch.zeros(N, Cs, dtype=f32, device=dev) if Cs else None
             inst_o = torch.zeros(N, Ci, dtype=f32, device=dev) if Ci else None
             if side is not None:
                 main.wait_stream(side)
             a, b = {'delta': (feats, dfeats), 'separate': (dfeats, None), 'appearance': (feats, None)}[src]
+            lse = torch.empty(Mmax, dtype=f32, device=dev) if (Ci and cfg['inst_softmax']) else None
             call("pag_pan_composite_fwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), HIDDEN, Cs, Ci,
                  int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
-                 ptr(wgt), ptr(alpha), ptr(ridx), ptr(sem_o), ptr(inst_o), ptr(m_dev))
+                 ptr(wgt), ptr(alpha), ptr(ridx), ptr(sem_o), ptr(inst_o), ptr(lse), ptr(m_dev))
+            ctx.lse = lse
         ctx.cfg = cfg
         ctx.save_for_backward(o, d, offsets, ridx, samples, depths, deltas, feats, dfeats, sigma, rgb, wgt, T, alpha, rgbsum,
                               tb, dtb, lodw, *w)
@@ -678,7 +684,7 @@ class FusedTraceFn(Function):
                 scale_p = grad_scale_dyn(gs if gs is not None else gi, gi if gs is not None else None, None)
                 call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), ptr_array(grads[10:]), HIDDEN,
                      Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
-                     ptr(wgt), ptr(alpha), ptr(ridx), ptr(gs), ptr(gi), ptr(scale_p), ptr(g_panop), ptr(m_dev))
+                     ptr(wgt), ptr(alpha), ptr(ridx), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev))
                 if need_gp:
                     call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
                          ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
