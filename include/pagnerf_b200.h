@@ -184,6 +184,8 @@ int pag_expint_bwd(const float* gw, const float* w, const float* T, const int64_
 /* ---- tcgen05 building-block probe (tests only): one 128-row tile through the tensor-core operand images ---- */
 int pag_tc_gemm_test(int mode, const float* A, const float* B, float* D, int N, int K, int FA, int reps, void* stream);
 int pag_tc_gemm_test16(int mode, const float* A, const float* B, float* D, int N, int K, int FA, int reps, void* stream);
+/* timing probe: mode 0/1/2 = forward / backward-data / backward-weight operand roles; cycles i64[2] = {total, issue} */
+int pag_tc_mma_bench(int mode, int N, int K, int chains, int reps, int64_t* cycles, void* stream);
 
 #ifdef __cplusplus
 }

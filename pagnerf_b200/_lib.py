@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpagnerf_b200.so")
+LIB_PATH = os.environ.get("PAGNERF_B200_LIB") or os.path.join(_HERE, "csrc", "libpagnerf_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pagnerf_b200.h")
 
 _lock = threading.Lock()

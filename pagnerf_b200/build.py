@@ -23,8 +23,11 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), tag=""):
+    """tag / extra_flags: an instrumented variant (e.g. tag='_dbg', extra_flags=['-DPAG_PHASE_TIMING']) built beside the
+    product library as libpagnerf_b200<tag>.so; select it at load time with PAGNERF_B200_LIB=<path>."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    lib = LIB.replace(".so", f"{tag}.so")
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "pagnerf_b200.h"))
     hdrs = [h for h in hdrs if os.path.exists(h)]
@@ -32,10 +35,10 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(CSRC, src.replace(".cu", ".o"))
+        o = os.path.join(CSRC, src.replace(".cu", f"{tag}.o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else [])
+            cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else [])
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
@@ -45,10 +48,13 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or _stale(LIB, objs):
-        subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
-    return LIB
+    if force or procs or _stale(lib, objs):
+        subprocess.check_call([nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--phase-timing" in sys.argv:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=["-DPAG_PHASE_TIMING"], tag="_dbg"))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
     const DcTcLayout l = dc_tc_layout(IN, false);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane, c16 = 16 * cg;
     dc_tc_stage(sm, l, p, IN);
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
@@ -114,11 +114,11 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
         const int64_t mm = valid ? m : M - 1;
         stage_x_cg(T0, row, cg, DC_NCG, feats, nullptr, lodw, IN, l.nXc, mm);
         sync_to_mma();
-        if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT0, wd1, 64, 64, l.INP, false); mb.commit(); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aT0, wd1, 64, 64, l.INP, false); mb.commit(); }
         mb.wait();
         epi_relu16(tl + c16, bias + c16, T1 + 2 * cg * TCH, row);
         sync_to_mma();
-        if (tid == 0) { tc_fence_after(); mma16_fwd(tm + 64, aT1, wd2, 16, 16, 64, false); mb.commit(); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + 64, aT1, wd2, 16, 16, 64, false); mb.commit(); }
         mb.wait();
         if (cg == 0) {
             float y[16];
@@ -133,15 +133,15 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
         }
         if (!want_rgb) { tc_fence_before(); __syncthreads(); continue; }
         sync_to_mma();
-        if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT0, wc1, 64, 64, 48, false); mb.commit(); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aT0, wc1, 64, 64, 48, false); mb.commit(); }
         mb.wait();
         epi_relu16(tl + c16, bias + 80 + c16, T1 + 2 * cg * TCH, row);
         sync_to_mma();
-        if (tid == 0) { tc_fence_after(); mma16_fwd(tm + 64, aT1, wc2, 64, 64, 64, false); mb.commit(); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + 64, aT1, wc2, 64, 64, 64, false); mb.commit(); }
         mb.wait();
         epi_relu16(tl + 64 + c16, bias + 144 + c16, T0 + 2 * cg * TCH, row);
         sync_to_mma();
-        if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT0, wc3, 16, 16, 64, false); mb.commit(); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aT0, wc3, 16, 16, 64, false); mb.commit(); }
         mb.wait();
         if (cg == 0) {
             float c[16];
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
     __shared__ uint32_t tmem_s;
     __shared__ float gdir_s[2][128][3];   // view-direction gradient partials of column groups 1 and 2
     const DcTcLayout l = dc_tc_layout(IN, true);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane, c16 = 16 * cg;
     dc_tc_stage(sm, l, p, IN);
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
@@ -208,11 +208,11 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
         // ---------------- forward recompute ----------------
         stage_x_cg(X, row, cg, DC_NCG, feats, nullptr, lodw, IN, l.nXc, mm);
         sync_to_mma();
-        if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aX, wd1, 64, 64, l.INP, false); mb.commit(); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aX, wd1, 64, 64, l.INP, false); mb.commit(); }
         mb.wait();
         const uint32_t mask_d = epi_relu16(tl + DCB_S0 + c16, bias + c16, Hd + 2 * cg * TCH, row);
         sync_to_mma();
-        if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S1, aHd, wd2, 16, 16, 64, false); mb.commit(); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + DCB_S1, aHd, wd2, 16, 16, 64, false); mb.commit(); }
         mb.wait();
         bool y0pos = false;
         float vdir[3] = {0.f, 0.f, 0.f};
@@ -234,15 +234,15 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
         }
         if (do_rgb) {
             sync_to_mma();
-            if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aCin, wc1, 64, 64, 48, false); mb.commit(); }
+            if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aCin, wc1, 64, 64, 48, false); mb.commit(); }
             mb.wait();
             mask_1 = epi_relu16(tl + DCB_S0 + c16, bias + 80 + c16, H1 + 2 * cg * TCH, row);
             sync_to_mma();
-            if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S1, aH1, wc2, 64, 64, 64, false); mb.commit(); }
+            if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + DCB_S1, aH1, wc2, 64, 64, 64, false); mb.commit(); }
             mb.wait();
             mask_2 = epi_relu16(tl + DCB_S1 + c16, bias + 144 + c16, H2 + 2 * cg * TCH, row);
             sync_to_mma();
-            if (tid == 0) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aH2, wc3, 16, 16, 64, false); mb.commit(); }
+            if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aH2, wc3, 16, 16, 64, false); mb.commit(); }
             mb.wait();
             if (cg == 0) {   // d rgb_pre (sigmoid') -> G3 tile (16 features, 3 valid)
                 float c[16], g[16];
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
             }
             // ---------------- color backward ----------------
             sync_to_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 mma16_bwd_weight(tm + DCB_DWC3, aG3, aH2, 64, !first);
                 mma16_bwd_data(tm + DCB_S1, aG3, wc3, 64, 16, 16, false);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
             mb.wait();
             epi_grad16(tl + DCB_S1 + c16, mask_2, H2 + 2 * cg * TCH, row, lane, db_c2);     // G2 overwrites H2
             sync_to_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 mma16_bwd_weight(tm + DCB_DWC2, aH2, aH1, 64, !first);
                 mma16_bwd_data(tm + DCB_S0, aH2, wc2, 64, 64, 64, false);
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
             mb.wait();
             epi_grad16(tl + DCB_S0 + c16, mask_1, H1 + 2 * cg * TCH, row, lane, db_c1);     // G1 overwrites H1
             sync_to_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 mma16_bwd_weight(tm + DCB_DWC1, aH1, aCin, 48, !first);
                 mma16_bwd_data(tm + DCB_S1, aH1, wc1, 48, 64, 64, false);
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
             grad16_store(dy, Gy, row, lane, db_d2);
         }
         sync_to_mma();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             mma16_bwd_weight(tm + DCB_DWD2, aGy, aHd, 64, !first);
             mma16_bwd_data(tm + DCB_S0, aGy, wd2, 64, 16, 16, false);
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
         mb.wait();
         epi_grad16(tl + DCB_S0 + c16, mask_d, Hd + 2 * cg * TCH, row, lane, db_d1);           // Gd overwrites Hd
         sync_to_mma();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             mma16_bwd_weight(tm + DCB_DWD1, aHd, aX, l.INP, !first);
             if (g_feats) mma16_bwd_data(tm + DCB_S1, aHd, wd1, l.INP, 64, 64, false);
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(128) pan_tc_fwd_kernel(const float* __restrict
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
     const PanTcLayout l = pan_tc_layout(IN, Cs, Ci, false);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = warp_id_uniform();
     pan_tc_stage(sm, l, p, IN, Cs, Ci);
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 256);
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(128) pan_tc_fwd_kernel(const float* __restrict
         const int64_t mm = valid ? m : M - 1;
         stage_x(X, tid, feats, dfeats, lodw, IN, l.nXc, mm);
         sync_to_mma();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (Cs > 0) mma16_fwd(tm, aX, ws1, 64, 64, l.INP, false);
             if (Ci > 0) mma16_fwd(tm + 64, aX, wi1, 64, 64, l.INP, false);
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(128) pan_tc_fwd_kernel(const float* __restrict
         if (Cs > 0) epi_relu64(tl, bs1, T1, tid);
         if (Ci > 0) epi_relu64(tl + 64, bi1, T2, tid);
         sync_to_mma();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (Cs > 0) mma16_fwd(tm + semcol, aT1, ws2, l.CsP, l.CsP, 64, false);
             if (Ci > 0) mma16_fwd(tm, aT2, wi2, 64, 64, 64, false);
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(128) pan_tc_fwd_kernel(const float* __restrict
         if (Ci > 0) {
             epi_relu64(tl, bi2, T1, tid);
             sync_to_mma();
-            if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT1, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
+            if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aT1, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
             mb.wait();
             epi_head_out(tl, bi3, Ci, l.CiP, inst_softmax, inst_inv_temp, inst + row0 * Ci, rows_valid, stage, tid & 31);
         }
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(128) pan_tc_bwd_kernel(const float* __restrict
     __shared__ uint64_t bar_s;
     __shared__ uint32_t tmem_s;
     const PanTcLayout l = pan_tc_layout(IN, Cs, Ci, true);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     pan_tc_stage(sm, l, p, IN, Cs, Ci);
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 512);
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(128) pan_tc_bwd_kernel(const float* __restrict
         // ---------------- forward recompute of the hidden layers ----------------
         stage_x(X, tid, feats, dfeats, lodw, IN, l.nXc, mm);
         sync_to_mma();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (do_sem) mma16_fwd(tm + PNB_S0, aX, ws1, 64, 64, l.INP, false);
             if (do_inst) mma16_fwd(tm + PNB_S1, aX, wi1, 64, 64, l.INP, false);
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(128) pan_tc_bwd_kernel(const float* __restrict
         if (do_inst) mask_1 = epi_relu64(tl + PNB_S1, bi1, H1, tid);
         if (do_inst) {
             sync_to_mma();
-            if (tid == 0) { tc_fence_after(); mma16_fwd(tm + PNB_S0, aH1, wi2, 64, 64, 64, false); mb.commit(); }
+            if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + PNB_S0, aH1, wi2, 64, 64, 64, false); mb.commit(); }
             mb.wait();
             mask_2 = epi_relu64(tl + PNB_S0, bi2, H2, tid);
         }
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(128) pan_tc_bwd_kernel(const float* __restrict
             if (do_inst) head_grad_tile(Gi, tid, lane, inst + row0 * Ci, g_inst + row0 * Ci, rows_valid, Ci, l.CiP, inst_softmax, inst_inv_temp, scale, stage, db_i3);
         }
         sync_to_mma();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (do_sem) {
                 mma16_bwd_weight(tm + PNB_DWS2, aGs, aHs, 64, !first);
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(128) pan_tc_bwd_kernel(const float* __restrict
         if (do_sem) epi_grad64(tl + PNB_S0, mask_s, Hs, tid, lane, db_s1);     // Gs1 overwrites Hs
         if (do_inst) epi_grad64(tl + PNB_S1, mask_2, H2, tid, lane, db_i2);    // Gi2 overwrites H2
         sync_to_mma();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (do_sem) {
                 mma16_bwd_weight(tm + PNB_DWS1, aHs, aX, l.INP, !first);
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(128) pan_tc_bwd_kernel(const float* __restrict
         if (do_inst) {
             epi_grad64(tl + PNB_S1, mask_1, H1, tid, lane, db_i1);             // Gi1 overwrites H1
             sync_to_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 mma16_bwd_weight(tm + PNB_DWI1, aH1, aX, l.INP, !first);
                 if (g_panop) mma16_bwd_data(tm + PNB_S0, aH1, wi1, l.INP, 64, 64, do_sem);   // accumulates onto the semantic dX

@@ -6,6 +6,35 @@
 
 #define TCH TC_CHUNK_BYTES
 
+// Phase timeline instrumentation (python -m pagnerf_b200.build --phase-timing -> libpagnerf_b200_dbg.so): thread 0 of
+// block 0 accumulates the clock64 ticks between consecutive PAG_PHASE marks; read with pag_debug_phase_read.
+#ifdef PAG_PHASE_TIMING
+static __device__ unsigned long long pag_phase_clk[64];   // one copy per translation unit
+#define PAG_PHASE_READER(name)                                                                        \
+    extern "C" int name(unsigned long long* host64, int reset) {                                      \
+        cudaError_t e = cudaMemcpyFromSymbol(host64, pag_phase_clk, sizeof(unsigned long long) * 64); \
+        if (e != cudaSuccess) return (int)e;                                                          \
+        if (reset) {                                                                                  \
+            unsigned long long z[64] = {0};                                                           \
+            e = cudaMemcpyToSymbol(pag_phase_clk, z, sizeof(z));                                      \
+        }                                                                                             \
+        return (int)e;                                                                                \
+    }
+#define PAG_PHASE_INIT() unsigned long long _ph_t = clock64()
+#define PAG_PHASE(i)                                                                   \
+    do {                                                                               \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                                     \
+            const unsigned long long _t = clock64();                                   \
+            pag_phase_clk[i] += _t - _ph_t;                                            \
+            _ph_t = _t;                                                                \
+        }                                                                              \
+    } while (0)
+#else
+#define PAG_PHASE_INIT()
+#define PAG_PHASE(i)
+#define PAG_PHASE_READER(name)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
@@ -141,9 +170,16 @@ __device__ __forceinline__ void flush_dw16(uint32_t taddr, float* __restrict__ g
     float v[16];
     tmem_ld16(taddr + c0, v);
     if (row < OUT) {
+        float* dst = gW + (size_t)row * IN + c0;
+        if (!(IN & 3) && !(reinterpret_cast<uintptr_t>(gW) & 15)) {   // 16-byte vector reductions: 4x fewer L2 atomics
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (c0 + i < IN) red_add_f32(gW + (size_t)row * IN + c0 + i, v[i] * inv_scale);
+            for (int i = 0; i < 16; i += 4)
+                if (c0 + i < IN) red_add_f32x4(dst + i, v[i] * inv_scale, v[i + 1] * inv_scale, v[i + 2] * inv_scale, v[i + 3] * inv_scale);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < IN) red_add_f32(dst + i, v[i] * inv_scale);
+        }
     }
 }
 
@@ -204,6 +240,64 @@ __device__ __forceinline__ void stage_x_cg(uint8_t* tile, int row, int cg, int n
         tile_store8(tile, c, row, v);
     }
 }
+// L2 prefetch of the chunks stage_x_cg will read for row m of a later tile (kernels without spare shared memory)
+__device__ __forceinline__ void prefetch_x_l2(const float* __restrict__ a, const float* __restrict__ b, int IN, int nchunks, int64_t m,
+                                              int cg, int ncg) {
+    for (int c = cg; c < nchunks; c += ncg) {
+        if (8 * c < IN) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a + m * IN + 8 * c));
+            if (b) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + m * IN + 8 * c));
+        }
+    }
+}
+
+// ---- asynchronous X-tile prefetch (column-split kernels) ------------------------------------------------------------
+// Thread (row, cg) converts the float4 quads q = cg, cg + NCG, ... of its row.  The quads of the NEXT tile are copied
+// with cp.async into private 16-byte slots slots[(2k + {0:a, 1:b}) * nthreads + tid] while the current tile is being
+// processed -- no registers are held and no other thread touches the slots, so the only synchronisation is the
+// thread's own cp.async.wait_all.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NCG, int MAXK>
+__device__ __forceinline__ void xpf_issue(float4* slots, const float* __restrict__ a, const float* __restrict__ b, int IN, int64_t m, int cg) {
+    const int nt = blockDim.x, tid = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) {
+        const int q = cg + NCG * k;
+        if (4 * q < IN) {
+            cp_async16(slots + (2 * k) * nt + tid, a + m * IN + 4 * q);
+            if (b) cp_async16(slots + (2 * k + 1) * nt + tid, b + m * IN + 4 * q);
+        }
+    }
+    cp_async_commit();
+}
+// (a + b) * lodw of the prefetched quads -> fp16 tile image; quads past IN (image padding up to INP) are zero-filled
+template <int NCG, int MAXK>
+__device__ __forceinline__ void xpf_consume(const float4* slots, bool has_b, const float* __restrict__ lodw, int IN, int INP,
+                                            uint8_t* tile, int row, int cg) {
+    const int nt = blockDim.x, tid = threadIdx.x;
+    cp_async_wait_all();
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) {
+        const int q = cg + NCG * k;
+        if (4 * q < INP) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * q < IN) {
+                x = slots[(2 * k) * nt + tid];
+                if (has_b) { const float4 y = slots[(2 * k + 1) * nt + tid]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+                if (lodw) { const float4 w = __ldg(reinterpret_cast<const float4*>(lodw) + q); x.x *= w.x; x.y *= w.y; x.z *= w.z; x.w *= w.w; }
+            }
+            uint2 u;
+            u.x = pack_h2(x.x, x.y); u.y = pack_h2(x.z, x.w);
+            *reinterpret_cast<uint2*>(tile + (q >> 1) * TCH + row * 16 + (q & 1) * 8) = u;
+        }
+    }
+}
+
 // 16 dX columns [c16, c16+16) of this thread's row -> global (float4 stores)
 __device__ __forceinline__ void store_dx16(uint32_t taddr, float* __restrict__ dst, const float* __restrict__ lodw, int IN,
                                            int c16, float inv_scale, bool valid) {

@@ -54,22 +54,39 @@ __device__ __forceinline__ void stage_bi3_scaled(float* dst, const float* __rest
 }
 
 #define STG_LD 34   // halfs per staged row: 17 words -> conflict-free transposed access
-// weighted segment-sum of one transposed 32-column block (stage[row][col], fp16) over the warp's rows into out[N, C]
-__device__ __forceinline__ void comp_block(const __half* stage, const float* __restrict__ wc, const int* __restrict__ wr, int nrows,
-                                           float* __restrict__ out, int C, int c0, int lane) {
+// weighted segment-sum of one transposed 32-column block (stage[row][col], fp16) over the warp's rows into out[N, C].
+// bmask bit r = row r starts a new ray (bit 0 never set); rows are walked four at a time, the common group without an
+// interior ray boundary costs one LDS.128 of coefficients + 4 x (LDS, cvt, FFMA).
+__device__ __forceinline__ void comp_block(const __half* stage, const float* __restrict__ wc, const int* __restrict__ wr, uint32_t bmask,
+                                           int nrows, float* __restrict__ out, int C, int c0, int lane) {
     if (c0 + lane < C && nrows > 0) {
         float acc = 0.f;
-        int cur = wr[0];
-        for (int r = 0; r < nrows; ++r) {
-            const int ray = wr[r];
-            if (ray != cur) {
-                red_add_f32(out + (int64_t)cur * C + c0 + lane, acc);
-                acc = 0.f;
-                cur = ray;
+        float* o = out + c0 + lane;
+        const __half* st = stage + lane;
+        int r = 0;
+        for (; r + 4 <= nrows; r += 4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(wc + r);
+            const float s0 = __half2float(st[r * STG_LD]), s1 = __half2float(st[(r + 1) * STG_LD]),
+                        s2 = __half2float(st[(r + 2) * STG_LD]), s3 = __half2float(st[(r + 3) * STG_LD]);
+            const uint32_t b = (bmask >> r) & 0xFu;
+            if (b) {
+                if (b & 1u) { red_add_f32(o + (int64_t)wr[r - 1] * C, acc); acc = 0.f; }
+                acc = fmaf(c4.x, s0, acc);
+                if (b & 2u) { red_add_f32(o + (int64_t)wr[r] * C, acc); acc = 0.f; }
+                acc = fmaf(c4.y, s1, acc);
+                if (b & 4u) { red_add_f32(o + (int64_t)wr[r + 1] * C, acc); acc = 0.f; }
+                acc = fmaf(c4.z, s2, acc);
+                if (b & 8u) { red_add_f32(o + (int64_t)wr[r + 2] * C, acc); acc = 0.f; }
+                acc = fmaf(c4.w, s3, acc);
+            } else {
+                acc = fmaf(c4.x, s0, acc); acc = fmaf(c4.y, s1, acc); acc = fmaf(c4.z, s2, acc); acc = fmaf(c4.w, s3, acc);
             }
-            acc = fmaf(wc[r], __half2float(stage[r * STG_LD + lane]), acc);
         }
-        red_add_f32(out + (int64_t)cur * C + c0 + lane, acc);
+        for (; r < nrows; ++r) {
+            if ((bmask >> r) & 1u) { red_add_f32(o + (int64_t)wr[r - 1] * C, acc); acc = 0.f; }
+            acc = fmaf(wc[r], __half2float(st[r * STG_LD]), acc);
+        }
+        red_add_f32(o + (int64_t)wr[nrows - 1] * C, acc);
     }
 }
 
@@ -84,7 +101,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
     __shared__ uint32_t tmem_s;
     __shared__ float part_s[PCF_NCG][128][2];   // (max, sum) partials of the row softmax per column group
     const PanCompFwdLayout l = pan_comp_fwd_layout(IN, Cs, Ci);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2;
     const int row = 32 * q + lane;
     const float s2 = inst_softmax ? inst_inv_temp * LOG2E_F : inst_inv_temp;   // logits -> log2-domain scaled logits
@@ -145,13 +162,15 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
                 tile_store8(X, c, row, v);
             }
         }
+        if (tile + gridDim.x < ntiles)
+            prefetch_x_l2(feats, dfeats, IN, l.nXc, min((tile + gridDim.x) * 128 + row, M - 1), cg, PCF_NCG);
         if (cg == 0) {   // compositing coefficients of this quadrant's rows
             const int64_t ray = ridx[mm];
             wr[lane] = (int)ray;
             wc[lane] = valid ? __ldg(alpha + ray) * __ldg(w + mm) : 0.f;
         }
         sync_to_mma();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (Cs > 0) mma16_fwd(tm, aX, ws1, 64, 64, l.INP, false);
             if (Ci > 0) mma16_fwd(tm + 64, aX, wi1, 64, 64, l.INP, false);
@@ -161,7 +180,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
         if (Cs > 0) epi_relu16(tl + c16, bs1 + c16, T1 + 2 * cg * TCH, row);
         if (Ci > 0) epi_relu16(tl + 64 + c16, bi1 + c16, T2 + 2 * cg * TCH, row);
         sync_to_mma();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (Cs > 0) mma16_fwd(tm + semcol, aT1, ws2, l.CsP, l.CsP, 64, false);
             if (Ci > 0) mma16_fwd(tm, aT2, wi2, 64, 64, 64, false);
@@ -170,10 +189,15 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
         mb.wait();
         const int64_t rows_left = M - (tile * 128 + q * 32);
         const int nrows = rows_left >= 32 ? 32 : (rows_left > 0 ? (int)rows_left : 0);
+        uint32_t bmask;
+        {   // ray boundaries inside this quadrant's 32 rows
+            const int rv = wr[lane], pv = __shfl_up_sync(0xffffffffu, rv, 1);
+            bmask = __ballot_sync(0xffffffffu, lane > 0 && rv != pv);
+        }
         if (Ci > 0) {
             epi_relu16(tl + c16, bi2 + c16, T1 + 2 * cg * TCH, row);
             sync_to_mma();
-            if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aT1, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
+            if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aT1, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
             mb.wait();
             // 32-column block b2 belongs to column group b2 % 4 (two blocks per group at most: CiP <= 208).
             // Pass 1 (softmax only): block-wise online max / sum with ONE exp2 per logit; the exponentials, taken
@@ -242,7 +266,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
                         }
                     }
                     __syncwarp();
-                    comp_block(stage, wc, wr, nrows, out_inst, Ci, c0, lane);
+                    comp_block(stage, wc, wr, bmask, nrows, out_inst, Ci, c0, lane);
                     __syncwarp();
                 }
             }
@@ -259,7 +283,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
 #pragma unroll
             for (int j = 0; j < 16; ++j) stage[lane * STG_LD + j] = __float2half_rn(z[j] * inv);
             __syncwarp();
-            comp_block(stage, wc, wr, nrows, out_sem, Cs, 0, lane);
+            comp_block(stage, wc, wr, bmask, nrows, out_sem, Cs, 0, lane);
             __syncwarp();
         }
         tc_fence_before();
@@ -283,9 +307,13 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
 #define PCB_DWI2 320     // [64 x 64]
 #define PCB_DWI3 384     // [Ci(<=208) x 64] as two 128-row blocks
 
+#define PCB_THREADS 512
+#define PCB_NCG 4    // column groups per row
+#define PCB_MAXK 3   // input quads (float4) per thread: IN <= 48
+
 struct PanCompBwdLayout {
     int INP, nXc, CsP, CiP, nGi;
-    int oGs, oX, oHs, oH1, oH2, oGi, oWs1, oWs2, oWi1, oWi2, oWi3, oBias, total;
+    int oGs, oX, oHs, oH1, oH2, oGi, oWs1, oWs2, oWi1, oWi2, oWi3, oBias, oPF, total;
 };
 __host__ __device__ inline PanCompBwdLayout pan_comp_bwd_layout(int IN, int Cs, int Ci) {
     PanCompBwdLayout l;
@@ -306,6 +334,8 @@ __host__ __device__ inline PanCompBwdLayout pan_comp_bwd_layout(int IN, int Cs, 
     l.oBias = o; o += (64 + l.CsP + 64 + 64 + l.CiP) * 4;
     const int need = l.oGi + (l.nGi > 16 ? 32 : 16) * TCH;   // MN-major A operands read 16 chunks from their base
     if (o < need) o = need;
+    o = (o + 15) & ~15;
+    l.oPF = o; o += 2 * PCB_MAXK * PCB_THREADS * 16;          // cp.async slots of the next tile's inputs (48 KB)
     l.total = o;
     return l;
 }
@@ -321,8 +351,6 @@ __device__ __forceinline__ void flush_dw_T(uint32_t taddr, float* __restrict__ g
     }
 }
 
-#define PCB_THREADS 512
-#define PCB_NCG 4   // column groups per row
 
 // four consecutive per-ray output gradients (zeros past the last class)
 __device__ __forceinline__ float4 load_g4(const float* __restrict__ grow, int j, int C, bool vec4) {
@@ -343,7 +371,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     __shared__ uint32_t tmem_s;
     __shared__ float part_s[PCB_NCG][128];      // per column group: partial <p, g> of the row
     const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant, column group
     const int row = 32 * q + lane;
     const bool do_sem = (Cs > 0) && g_sem, do_inst = (Ci > 0) && g_inst;
@@ -380,54 +408,59 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     const int c16 = 16 * cg;                       // this thread's 16 hidden columns
     float db_s1 = 0.f, db_i1 = 0.f, db_i2 = 0.f, db_s2 = 0.f, db_i3[4] = {0.f, 0.f, 0.f, 0.f};
     const int64_t ntiles = (M + 127) / 128;
+    float4* pf = reinterpret_cast<float4*>(sm + l.oPF);
+    int64_t n_ray = 0;
+    float n_w = 0.f, n_lse = 0.f;
+    if ((int64_t)blockIdx.x < ntiles) {
+        const int64_t m0 = min((int64_t)blockIdx.x * 128 + row, M - 1);
+        xpf_issue<PCB_NCG, PCB_MAXK>(pf, feats, dfeats, IN, m0, cg);
+        n_ray = ridx[m0]; n_w = __ldg(w + m0);
+        if (inst_lse) n_lse = __ldg(inst_lse + m0);
+    }
     bool first = true;
+    PAG_PHASE_INIT();
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
         const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
-        const int64_t ray = ridx[mm];
-        const float cs = valid ? __ldg(alpha + ray) * __ldg(w + mm) * scale : 0.f;
+        // per-row scalars were loaded one tile ahead; the dependent alpha[ray] load has the whole MLP forward to land
+        const int64_t ray = n_ray;
+        const float w_row = n_w, lse_row = n_lse;
+        const float a_row = __ldg(alpha + ray);
         // ---------------- stage 1 ----------------
-        {   // X tile: chunk c is written by column group c % 4
-            const float4* a4 = reinterpret_cast<const float4*>(feats + mm * IN);
-            const float4* b4 = dfeats ? reinterpret_cast<const float4*>(dfeats + mm * IN) : nullptr;
-            const float4* w4 = lodw ? reinterpret_cast<const float4*>(lodw) : nullptr;
-            for (int c = cg; c < l.nXc; c += PCB_NCG) {
-                float v[8];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int qi = 2 * c + h;
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (4 * qi < IN) {
-                        x = __ldg(a4 + qi);
-                        if (b4) { const float4 y = __ldg(b4 + qi); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-                        if (w4) { const float4 ww = __ldg(w4 + qi); x.x *= ww.x; x.y *= ww.y; x.z *= ww.z; x.w *= ww.w; }
-                    }
-                    v[4 * h] = x.x; v[4 * h + 1] = x.y; v[4 * h + 2] = x.z; v[4 * h + 3] = x.w;
-                }
-                tile_store8(X, c, row, v);
+        PAG_PHASE(0);
+        xpf_consume<PCB_NCG, PCB_MAXK>(pf, dfeats != nullptr, lodw, IN, l.INP, X, row, cg);
+        PAG_PHASE(1);
+        {   // next tile: inputs by cp.async, row scalars into registers
+            const int64_t tn = tile + gridDim.x;
+            if (tn < ntiles) {
+                const int64_t mn = min(tn * 128 + row, M - 1);
+                xpf_issue<PCB_NCG, PCB_MAXK>(pf, feats, dfeats, IN, mn, cg);
+                n_ray = ridx[mn]; n_w = __ldg(w + mn);
+                if (inst_lse) n_lse = __ldg(inst_lse + mn);
             }
         }
-        sync_to_mma();
-        if (tid == 0) {
+        sync_to_mma(); PAG_PHASE(2);
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (do_sem) mma16_fwd(tm + PCB_S0, aX, ws1, 64, 64, l.INP, false);
             if (do_inst) mma16_fwd(tm + PCB_S1, aX, wi1, 64, 64, l.INP, false);
             mb.commit();
         }
-        mb.wait();
+        mb.wait(); PAG_PHASE(3);
+        const float cs = valid ? a_row * w_row * scale : 0.f;
         uint32_t mask_s = 0, mask_1 = 0, mask_2 = 0;
         if (do_sem) mask_s = epi_relu16(tl + PCB_S0 + c16, bs1 + c16, Hs + 2 * cg * TCH, row);
         if (do_inst) mask_1 = epi_relu16(tl + PCB_S1 + c16, bi1 + c16, H1 + 2 * cg * TCH, row);
         // ---------------- stage 2 ----------------
-        sync_to_mma();
-        if (tid == 0) {
+        sync_to_mma(); PAG_PHASE(4);
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (do_inst) mma16_fwd(tm + PCB_S0, aH1, wi2, 64, 64, 64, false);
             if (do_sem) mma16_fwd(tm + PCB_SEMLOG, aHs, ws2, l.CsP, l.CsP, 64, false);
             mb.commit();
         }
-        mb.wait();
+        mb.wait(); PAG_PHASE(5);
         if (do_inst) mask_2 = epi_relu16(tl + PCB_S0 + c16, bi2 + c16, H2 + 2 * cg * TCH, row);
         if (do_sem && cg == 0) {   // semantic head gradient (<= 16 classes): column group 0 only
             float z[16], g[16];
@@ -450,16 +483,16 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         }
         // ---------------- stage 3: instance logits + head gradient; 16-column block b belongs to group b % 4 ----------------
         if (do_inst) {
-            sync_to_mma();
-            if (tid == 0) { tc_fence_after(); mma16_fwd(tm, aH2, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
-            mb.wait();
+            sync_to_mma(); PAG_PHASE(6);
+            if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aH2, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
+            mb.wait(); PAG_PHASE(7);
             // d logit_j = c * p_j * (g_j - <p, g>) / T with p_j = 2^(z_j - lse) from the forward's log-sum-exp: one
             // exp2 per logit; the probabilities go back into TMEM over the logits for the second pass.
             const float* grow = g_inst + ray * Ci;
             const bool vec4 = !(Ci & 3);
             float dot = 0.f;
             if (inst_softmax) {
-                const float nl = -__ldg(inst_lse + mm);
+                const float nl = -lse_row;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int c0 = 16 * (cg + PCB_NCG * k);
@@ -479,7 +512,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                     }
                 }
                 part_s[cg][row] = dot;
-                __syncthreads();
+                __syncthreads(); PAG_PHASE(8);
                 dot = (part_s[0][row] + part_s[1][row]) + (part_s[2][row] + part_s[3][row]);
             }
             const float c2 = cs * inst_inv_temp;
@@ -504,8 +537,8 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             }
         }
         // ---------------- stage 4 ----------------
-        sync_to_mma();
-        if (tid == 0) {
+        sync_to_mma(); PAG_PHASE(9);
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (do_inst) {
                 mma16_bwd_weight(tm + PCB_DWI3, aGi, aH2, 64, !first);
@@ -518,12 +551,12 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             }
             mb.commit();
         }
-        mb.wait();
+        mb.wait(); PAG_PHASE(10);
         if (do_inst) epi_grad16(tl + PCB_S1 + c16, mask_2, H2 + 2 * cg * TCH, row, lane, db_i2);
         if (do_sem) epi_grad16(tl + PCB_S0 + c16, mask_s, Hs + 2 * cg * TCH, row, lane, db_s1);
         // ---------------- stage 5 ----------------
-        sync_to_mma();
-        if (tid == 0) {
+        sync_to_mma(); PAG_PHASE(11);
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (do_inst) {
                 mma16_bwd_weight(tm + PCB_DWI2, aH2, aH1, 64, !first);
@@ -535,18 +568,18 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             }
             mb.commit();
         }
-        mb.wait();
+        mb.wait(); PAG_PHASE(12);
         // ---------------- stage 6 ----------------
         if (do_inst) {
             epi_grad16(tl + PCB_S1 + c16, mask_1, H1 + 2 * cg * TCH, row, lane, db_i1);
-            sync_to_mma();
-            if (tid == 0) {
+            sync_to_mma(); PAG_PHASE(13);
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 mma16_bwd_weight(tm + PCB_DWI1, aH1, aX, l.INP, !first);
                 if (g_panop) mma16_bwd_data(tm + PCB_S0, aH1, wi1, l.INP, 64, 64, do_sem);
                 mb.commit();
             }
-            mb.wait();
+            mb.wait(); PAG_PHASE(14);
         }
         if (g_panop && c16 < l.INP) {
             float v[16];
@@ -564,7 +597,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             }
         }
         tc_fence_before();
-        __syncthreads();
+        __syncthreads(); PAG_PHASE(15);
     }
     if (!first) {
         tc_fence_after();
@@ -591,6 +624,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     }
     tc_fence_before();
     __syncthreads();
+    PAG_PHASE(40);
     if (warp == 0) tmem_dealloc(tm, 512);
 }
 
@@ -614,6 +648,8 @@ static void fill_pan_f(PanParams& p, const float* const* w, float* const* g) {
 static bool fused_shape_ok(int IN, int hidden, int Cs, int Ci) {
     return hidden == H && IN >= 4 && IN <= 48 && !(IN & 3) && Cs >= 0 && Cs <= 16 && Ci >= 0 && Ci <= 208;
 }
+
+PAG_PHASE_READER(pag_debug_phase_read)
 
 extern "C" {
 

@@ -35,6 +35,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// ---- single-lane election in warp-uniform control flow ------------------------------------------------------------
+// tcgen05.mma / commit live on the uniform datapath.  Issued under a divergent `if (threadIdx.x == 0)` the compiler wraps
+// every one of them in a per-lane waterfall loop (~100 cycles per MMA, measured with tools/mma_bench.py); issued under
+// `warp_id_uniform() == w && elect_one()` they are straight-line uniform instructions.
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- proxies / fences -----------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

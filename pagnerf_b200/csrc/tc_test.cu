@@ -108,6 +108,57 @@ __global__ void __launch_bounds__(128) tc_gemm_test16_kernel(int mode, const flo
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+// MMA issue / completion timing probe: thread 0 issues `chains` operand chains (K/16 MMAs each) back to back, commits and
+// waits, `reps` times; cycles[0] = total clock64 ticks, cycles[1] = ticks spent issuing.
+__global__ void __launch_bounds__(128) tc_mma_bench_kernel(int mode, int N, int K, int chains, int reps, long long* __restrict__ cycles) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = warp_id_uniform();
+    for (int i = tid; i < 32 * 512 * 2; i += 128) reinterpret_cast<float*>(smem_raw)[i] = 0.f;
+    __syncthreads();
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base, 256);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base, a = smem_u32(smem_raw), b = smem_u32(smem_raw + 32 * TC_CHUNK_BYTES);
+    const int KP = (K + 7) & ~7, NP = (N + 7) & ~7;
+    uint32_t parity = 0;
+    long long t_issue = 0;
+    const long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
+        if (warp == 0 && elect_one()) {
+            const long long ti = clock64();
+            for (int c = 0; c < chains; ++c) {
+                if (mode == 0) mma16_fwd(tmem, a, b, N, NP, K, true);
+                else if (mode == 1) mma16_bwd_data(tmem, a, b, N, KP, K, true);
+                else mma16_bwd_weight(tmem, a, b, N, true);
+            }
+            umma_commit(&bar);
+            t_issue += clock64() - ti;
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        tc_fence_after();
+    }
+    const long long t1 = clock64();
+    if (tid == 0) { cycles[0] = t1 - t0; cycles[1] = t_issue; }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+extern "C" int pag_tc_mma_bench(int mode, int N, int K, int chains, int reps, int64_t* cycles, void* stream) {
+    if (N % 16 || N > 256 || N < 16 || K % 16 || K > 256) return PAG_ERR_ARG;
+    const size_t bytes = 64 * TC_CHUNK_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    tc_mma_bench_kernel<<<1, 128, bytes, (cudaStream_t)stream>>>(mode, N, K, chains, reps, reinterpret_cast<long long*>(cycles));
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
 extern "C" int pag_tc_gemm_test16(int mode, const float* A, const float* B, float* D, int N, int K, int FA, int reps, void* stream) {
     if (N % 16 || N > 256 || N < 16) return PAG_ERR_ARG;
     const size_t bytes = 64 * TC_CHUNK_BYTES;
