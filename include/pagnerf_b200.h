@@ -143,7 +143,7 @@ int pag_decode_pan_bwd_tc(const float* feats, const float* dfeats, const float* 
 /* panoptic heads fused with their compositing (training mode): out[ray] = alpha_ray * sum_s w_s * head(panop_s) with
  * alpha, w detached (tracers/panoptic_packed_rf_tracer.py:148-155,178-205); the [M,C] probabilities never reach HBM.
  * out_sem[N,Cs] / out_inst[N,Ci] must be zeroed by the caller (accumulated with red.add). ridx i64[M] ascending.
- * inst_lse f32[M] (nullable in forward): per-sample log2-domain log-sum-exp of the instance logits / T, written by
+ * R = number of rays (rows of g_sem / g_inst). inst_lse f32[M] (nullable in forward): per-sample log2-domain log-sum-exp of the instance logits / T, written by
  * the forward and required by the backward when inst_softmax is set (the backward recomputes the logits with the same
  * tensor-core instructions and turns them into probabilities with one exp2 each). */
 int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
@@ -153,7 +153,7 @@ int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const floa
 int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
-                             const int64_t* ridx, const float* g_sem, const float* g_inst, const float* inst_lse,
+                             const int64_t* ridx, int64_t R, const float* g_sem, const float* g_inst, const float* inst_lse,
                              const float* grad_scale, float* g_panop, const int64_t* m_dev, void* stream);
 
 /* ---- packed compositing: tracers/panoptic_packed_rf_tracer.py:134-205 ------------------------------- */

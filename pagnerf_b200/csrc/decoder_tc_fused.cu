@@ -297,23 +297,27 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-// TMEM columns (512): the instance logits [0,208) alias the scratch accumulators S0 / S1
+// TMEM columns (512).  The instance logits / probabilities [0,208) alias the scratch accumulators S0 / S1 / SEMLOG.
+// Bias gradients of the wide layers come out of the tensor core: a constant "ones" tile is the B operand of an extra
+// N=16 chain (DB3) and an extra 16 columns of the layer-2 weight-gradient chain (DWI2), so the per-tile warp
+// reduce-scatter is only left on the two first-layer gradients.
 #define PCB_S0 0
 #define PCB_S1 64
 #define PCB_SEMLOG 128   // 16 columns, consumed before the instance logits are produced
-#define PCB_DWS1 208     // [64 x <=48]
-#define PCB_DWS2T 256    // [64(h) x 16(classes)]  transposed: 16 columns instead of 64
-#define PCB_DWI1 272     // [64 x <=48]
-#define PCB_DWI2 320     // [64 x 64]
-#define PCB_DWI3 384     // [Ci(<=208) x 64] as two 128-row blocks
+#define PCB_DW1J 208     // [128 = (sem L1 | inst L1) x <=48]: both first-layer weight gradients from ONE chain
+#define PCB_DWS2T 256    // [64(h) x 16(classes)] transposed
+#define PCB_DWI2 272     // [64 x (64 + 16)]: column 64 = bias gradient (ones trick)
+#define PCB_DWI3 352     // [Ci(<=208) x 64] as two 128-row blocks
+#define PCB_DB3 480      // [Ci x 16] x 2 blocks: column 0 = bias gradient (ones trick)
 
 #define PCB_THREADS 512
 #define PCB_NCG 4    // column groups per row
 #define PCB_MAXK 3   // input quads (float4) per thread: IN <= 48
+#define PCB_NGC 16   // rays whose output gradients are cached (fp16, pre-scaled) per tile
 
 struct PanCompBwdLayout {
     int INP, nXc, CsP, CiP, nGi;
-    int oGs, oX, oHs, oH1, oH2, oGi, oWs1, oWs2, oWi1, oWi2, oWi3, oBias, oPF, total;
+    int oGs, oX, oHs, oH1, oOnes, oH2, oGi, oW1, oWs2, oWi2, oWi3, oBias, oGC, oPF, total;
 };
 __host__ __device__ inline PanCompBwdLayout pan_comp_bwd_layout(int IN, int Cs, int Ci) {
     PanCompBwdLayout l;
@@ -322,22 +326,33 @@ __host__ __device__ inline PanCompBwdLayout pan_comp_bwd_layout(int IN, int Cs, 
     int o = 0;
     l.oGs = o; o += 2 * TCH;
     l.oX = o; o += l.nXc * TCH;
-    l.oHs = o; o += 8 * TCH;
+    l.oHs = o; o += 8 * TCH;        // Hs | H1 adjacent: one MN-major A operand covers both first-layer gradients
     l.oH1 = o; o += 8 * TCH;
+    l.oOnes = o; o += 2 * TCH;      // H1 | ones: B operand of the layer-2 weight gradient (N = 80)
     l.oH2 = o; o += 8 * TCH;
     l.oGi = o; o += l.nGi * TCH;
-    l.oWs1 = o; o += l.nXc * 64 * 16;
+    l.oW1 = o; o += l.nXc * 128 * 16;   // joint [Ws1; Wi1] image, 128 output rows
     l.oWs2 = o; o += 8 * l.CsP * 16;
-    l.oWi1 = o; o += l.nXc * 64 * 16;
     l.oWi2 = o; o += 8 * 64 * 16;
     l.oWi3 = o; o += 8 * l.CiP * 16;
     l.oBias = o; o += (64 + l.CsP + 64 + 64 + l.CiP) * 4;
     const int need = l.oGi + (l.nGi > 16 ? 32 : 16) * TCH;   // MN-major A operands read 16 chunks from their base
     if (o < need) o = need;
     o = (o + 15) & ~15;
+    l.oGC = o; o += PCB_NGC * l.CiP * 2;                       // fp16 cache of g_inst rows (6.5 KB)
+    o = (o + 15) & ~15;
     l.oPF = o; o += 2 * PCB_MAXK * PCB_THREADS * 16;          // cp.async slots of the next tile's inputs (48 KB)
     l.total = o;
     return l;
+}
+
+// rows [row0, row0 + rows) of a joint weight image with OUTP output rows; W == nullptr stages zeros
+__device__ __forceinline__ void stage_w16_part(__half* img, const float* __restrict__ W, int OUT, int IN, int rows, int row0, int OUTP, int INP) {
+    const int n = (INP / 8) * rows * 8;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int e = i & 7, r = (i >> 3) % rows, c = (i >> 3) / rows, in = c * 8 + e;
+        img[((size_t)c * OUTP + row0 + r) * 8 + e] = (W && r < OUT && in < IN) ? __float2half_rn(__ldg(W + (size_t)r * IN + in)) : __float2half_rn(0.f);
+    }
 }
 
 // transposed accumulator [lanes = input features k][cols = classes j] -> gW[j][k]
@@ -350,20 +365,45 @@ __device__ __forceinline__ void flush_dw_T(uint32_t taddr, float* __restrict__ g
             if (j < C) red_add_f32(gW + (size_t)j * K + k, v[j] * inv_scale);
     }
 }
+// 16 masked gradient columns -> 2 tile chunks (bias gradient taken elsewhere)
+__device__ __forceinline__ void epi_grad16_nb(uint32_t taddr, uint32_t mask, uint8_t* tile2, int row) {
+    float v[16];
+    tmem_ld16(taddr, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
+    tile_store8(tile2, 0, row, v);
+    tile_store8(tile2, 1, row, v + 8);
+}
 
-
-// four consecutive per-ray output gradients (zeros past the last class)
-__device__ __forceinline__ float4 load_g4(const float* __restrict__ grow, int j, int C, bool vec4) {
-    if (vec4) return (j < C) ? __ldg(reinterpret_cast<const float4*>(grow + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    return make_float4(j < C ? __ldg(grow + j) : 0.f, j + 1 < C ? __ldg(grow + j + 1) : 0.f,
-                       j + 2 < C ? __ldg(grow + j + 2) : 0.f, j + 3 < C ? __ldg(grow + j + 3) : 0.f);
+// 16 consecutive (pre-scaled) per-ray output gradients: from the tile's fp16 cache when the ray is one of the first
+// PCB_NGC of the tile, else straight from global memory
+__device__ __forceinline__ void load_g16(const __half* __restrict__ gc_row, const float* __restrict__ grow, int c0, int C, bool vec4,
+                                         float scale, float (&g)[16]) {
+    if (gc_row) {
+        const uint4 a = *reinterpret_cast<const uint4*>(gc_row + c0), b = *reinterpret_cast<const uint4*>(gc_row + c0 + 8);
+        const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+            g[2 * i] = f.x; g[2 * i + 1] = f.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            float4 t;
+            if (vec4) t = (c0 + i < C) ? __ldg(reinterpret_cast<const float4*>(grow + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else t = make_float4(c0 + i < C ? __ldg(grow + c0 + i) : 0.f, c0 + i + 1 < C ? __ldg(grow + c0 + i + 1) : 0.f,
+                                 c0 + i + 2 < C ? __ldg(grow + c0 + i + 2) : 0.f, c0 + i + 3 < C ? __ldg(grow + c0 + i + 3) : 0.f);
+            g[i] = t.x * scale; g[i + 1] = t.y * scale; g[i + 2] = t.z * scale; g[i + 3] = t.w * scale;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw, int64_t M, int IN,
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
     const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
-    const float* __restrict__ g_sem, const float* __restrict__ g_inst, const float* __restrict__ inst_lse,
+    const float* __restrict__ g_sem, const float* __restrict__ g_inst, int64_t R, const float* __restrict__ inst_lse,
     const float* __restrict__ scale_ptr, float* __restrict__ g_panop, const int64_t* __restrict__ m_dev) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
@@ -376,20 +416,32 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     const int row = 32 * q + lane;
     const bool do_sem = (Cs > 0) && g_sem, do_inst = (Ci > 0) && g_inst;
     const float s2 = inst_softmax ? inst_inv_temp * LOG2E_F : inst_inv_temp;
+    uint8_t *Gs = sm + l.oGs, *X = sm + l.oX, *Hs = sm + l.oHs, *H1 = sm + l.oH1, *H2 = sm + l.oH2, *Gi = sm + l.oGi;
     {
         float* b = reinterpret_cast<float*>(sm + l.oBias);
+        __half* w1 = reinterpret_cast<__half*>(sm + l.oW1);
+        stage_w16_part(w1, do_sem ? p.Ws1 : nullptr, 64, IN, 64, 0, 128, l.INP);
+        stage_w16_part(w1, do_inst ? p.Wi1 : nullptr, 64, IN, 64, 64, 128, l.INP);
         if (do_sem) {
-            stage_w16(reinterpret_cast<__half*>(sm + l.oWs1), p.Ws1, 64, IN, 64, l.INP);
             stage_w16(reinterpret_cast<__half*>(sm + l.oWs2), p.Ws2, Cs, 64, l.CsP, 64);
             stage_b32(b, p.bs1, 64, 64); stage_b32(b + 64, p.bs2, Cs, l.CsP);
         }
         if (do_inst) {
-            stage_w16(reinterpret_cast<__half*>(sm + l.oWi1), p.Wi1, 64, IN, 64, l.INP);
             stage_w16(reinterpret_cast<__half*>(sm + l.oWi2), p.Wi2, 64, 64, 64, 64);
             stage_w16(reinterpret_cast<__half*>(sm + l.oWi3), p.Wi3, Ci, 64, l.CiP, 64);
             stage_b32(b + 64 + l.CsP, p.bi1, 64, 64); stage_b32(b + 128 + l.CsP, p.bi2, 64, 64);
             stage_bi3_scaled(b + 192 + l.CsP, p.bi3, Ci, l.CiP, s2, inst_softmax);
         }
+        // constant tiles: ones column (feature 0 of a 16-feature tile); the gradient tile of a disabled head stays zero
+        for (int i = tid; i < 2 * TCH / 16; i += PCB_THREADS) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (i < TCH / 16) u.x = 0x00003C00u;   // half(1.0) in element 0 of chunk 0
+            reinterpret_cast<uint4*>(sm + l.oOnes)[i] = u;
+        }
+        for (int i = tid; i < PCB_NGC * l.CiP / 8; i += PCB_THREADS)      // the padded classes of the gradient cache stay zero
+            reinterpret_cast<uint4*>(sm + l.oGC)[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (!do_sem) for (int i = tid; i < 8 * TCH / 16; i += PCB_THREADS) reinterpret_cast<uint4*>(Hs)[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (!do_inst) for (int i = tid; i < 8 * TCH / 16; i += PCB_THREADS) reinterpret_cast<uint4*>(H1)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 512);
@@ -399,24 +451,27 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     MmaBar mb{&bar_s, 0};
     const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
     const float *bs1 = bias, *bs2 = bias + 64, *bi1 = bias + 64 + l.CsP, *bi2 = bi1 + 64, *bi3 = bi2 + 64;
-    uint8_t *Gs = sm + l.oGs, *X = sm + l.oX, *Hs = sm + l.oHs, *H1 = sm + l.oH1, *H2 = sm + l.oH2, *Gi = sm + l.oGi;
-    const uint32_t aGs = smem_u32(Gs), aX = smem_u32(X), aHs = smem_u32(Hs), aH1 = smem_u32(H1), aH2 = smem_u32(H2), aGi = smem_u32(Gi);
-    const uint32_t ws1 = smem_u32(sm + l.oWs1), ws2 = smem_u32(sm + l.oWs2), wi1 = smem_u32(sm + l.oWi1),
-                   wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
+    const uint32_t aGs = smem_u32(Gs), aX = smem_u32(X), aHs = smem_u32(Hs), aH1 = smem_u32(H1), aH2 = smem_u32(H2), aGi = smem_u32(Gi),
+                   aOnes = smem_u32(sm + l.oOnes);
+    const uint32_t w1j = smem_u32(sm + l.oW1), ws2 = smem_u32(sm + l.oWs2), wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
+    __half* gcache = reinterpret_cast<__half*>(sm + l.oGC);
     const float scale = scale_ptr ? __ldg(scale_ptr) : 1.f;
     const float inv_scale = 1.f / scale;
     const int c16 = 16 * cg;                       // this thread's 16 hidden columns
-    float db_s1 = 0.f, db_i1 = 0.f, db_i2 = 0.f, db_s2 = 0.f, db_i3[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool vec4 = !(Ci & 3);
+    float db_s1 = 0.f, db_i1 = 0.f, db_s2 = 0.f;
     const int64_t ntiles = (M + 127) / 128;
     float4* pf = reinterpret_cast<float4*>(sm + l.oPF);
-    int64_t n_ray = 0;
+    int64_t n_ray = 0, n_ray0 = 0;
     float n_w = 0.f, n_lse = 0.f;
     if ((int64_t)blockIdx.x < ntiles) {
         const int64_t m0 = min((int64_t)blockIdx.x * 128 + row, M - 1);
         xpf_issue<PCB_NCG, PCB_MAXK>(pf, feats, dfeats, IN, m0, cg);
-        n_ray = ridx[m0]; n_w = __ldg(w + m0);
+        n_ray = ridx[m0]; n_w = __ldg(w + m0); n_ray0 = ridx[(int64_t)blockIdx.x * 128];
         if (inst_lse) n_lse = __ldg(inst_lse + m0);
     }
+    const int ci1 = Ci > 0 ? Ci : 1;
+    const int gc_r0 = tid / ci1, gc_c0 = tid % ci1, gc_dr = PCB_THREADS / ci1, gc_dc = PCB_THREADS % ci1;
     bool first = true;
     PAG_PHASE_INIT();
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
@@ -424,11 +479,11 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
         // per-row scalars were loaded one tile ahead; the dependent alpha[ray] load has the whole MLP forward to land
-        const int64_t ray = n_ray;
+        const int64_t ray = n_ray, ray0 = n_ray0;
         const float w_row = n_w, lse_row = n_lse;
         const float a_row = __ldg(alpha + ray);
-        // ---------------- stage 1 ----------------
         PAG_PHASE(0);
+        // ---------------- stage 1 ----------------
         xpf_consume<PCB_NCG, PCB_MAXK>(pf, dfeats != nullptr, lodw, IN, l.INP, X, row, cg);
         PAG_PHASE(1);
         {   // next tile: inputs by cp.async, row scalars into registers
@@ -436,22 +491,41 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             if (tn < ntiles) {
                 const int64_t mn = min(tn * 128 + row, M - 1);
                 xpf_issue<PCB_NCG, PCB_MAXK>(pf, feats, dfeats, IN, mn, cg);
-                n_ray = ridx[mn]; n_w = __ldg(w + mn);
+                n_ray = ridx[mn]; n_w = __ldg(w + mn); n_ray0 = ridx[tn * 128];
                 if (inst_lse) n_lse = __ldg(inst_lse + mn);
             }
         }
         sync_to_mma(); PAG_PHASE(2);
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            if (do_sem) mma16_fwd(tm + PCB_S0, aX, ws1, 64, 64, l.INP, false);
-            if (do_inst) mma16_fwd(tm + PCB_S1, aX, wi1, 64, 64, l.INP, false);
+            mma16_fwd(tm + PCB_S0, aX, w1j, 128, 128, l.INP, false);     // sem | inst first layers in one chain
             mb.commit();
         }
+        // while the MMAs run: the tile's per-ray output gradients (first PCB_NGC rays) -> registers, coalesced
+        float gpre[7];
+        const int ngc_elems = PCB_NGC * Ci;
+        if (do_inst) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int e = tid + PCB_THREADS * k;
+                const int64_t src = ray0 * Ci + e;
+                gpre[k] = (e < ngc_elems && src < R * Ci) ? __ldg(g_inst + src) : 0.f;
+            }
+        }
         mb.wait(); PAG_PHASE(3);
-        const float cs = valid ? a_row * w_row * scale : 0.f;
+        const float cs = valid ? a_row * w_row : 0.f;     // the loss scale rides on the cached gradients
         uint32_t mask_s = 0, mask_1 = 0, mask_2 = 0;
         if (do_sem) mask_s = epi_relu16(tl + PCB_S0 + c16, bs1 + c16, Hs + 2 * cg * TCH, row);
-        if (do_inst) mask_1 = epi_relu16(tl + PCB_S1 + c16, bi1 + c16, H1 + 2 * cg * TCH, row);
+        if (do_inst) {
+            mask_1 = epi_relu16(tl + PCB_S1 + c16, bi1 + c16, H1 + 2 * cg * TCH, row);
+            int gr = gc_r0, gc = gc_c0;      // (ray slot, class) of element tid + 512 k, advanced without divisions
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                if (gr < PCB_NGC) gcache[gr * l.CiP + gc] = __float2half_rn(gpre[k] * scale);
+                gr += gc_dr; gc += gc_dc;
+                if (gc >= Ci) { gc -= Ci; ++gr; }
+            }
+        }
         // ---------------- stage 2 ----------------
         sync_to_mma(); PAG_PHASE(4);
         if (warp == 0 && elect_one()) {
@@ -476,9 +550,9 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                 g[j] = gj; z[j] = e;
                 Z += e; E = fmaf(e, gj, E);
             }
-            const float iz = 1.f / Z, dot = E * iz;
+            const float iz = 1.f / Z, dot = E * iz, css = cs * scale;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = (j < Cs) ? (sem_softmax ? cs * z[j] * iz * (g[j] - dot) : cs * g[j]) : 0.f;
+            for (int j = 0; j < 16; ++j) g[j] = (j < Cs) ? (sem_softmax ? css * z[j] * iz * (g[j] - dot) : css * g[j]) : 0.f;
             grad16_store(g, Gs, row, lane, db_s2);
         }
         // ---------------- stage 3: instance logits + head gradient; 16-column block b belongs to group b % 4 ----------------
@@ -489,7 +563,8 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             // d logit_j = c * p_j * (g_j - <p, g>) / T with p_j = 2^(z_j - lse) from the forward's log-sum-exp: one
             // exp2 per logit; the probabilities go back into TMEM over the logits for the second pass.
             const float* grow = g_inst + ray * Ci;
-            const bool vec4 = !(Ci & 3);
+            const int64_t slot = ray - ray0;
+            const __half* gc_row = (slot < PCB_NGC) ? gcache + slot * l.CiP : nullptr;
             float dot = 0.f;
             if (inst_softmax) {
                 const float nl = -lse_row;
@@ -497,20 +572,21 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                 for (int k = 0; k < 4; ++k) {
                     const int c0 = 16 * (cg + PCB_NCG * k);
                     if (c0 < l.CiP) {
-                        float v[16];
+                        float v[16], g[16];
+                        load_g16(gc_row, grow, c0, Ci, vec4, scale, g);
                         tmem_ld16(tl + c0, v);
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
                             const float4 b4 = *reinterpret_cast<const float4*>(bi3 + c0 + i);   // pre-scaled, -inf on padding
-                            const float4 g4 = load_g4(grow, c0 + i, Ci, vec4);
-                            v[i] = fast_exp2(fmaf(v[i], s2, b4.x) + nl);         dot = fmaf(v[i], g4.x, dot);
-                            v[i + 1] = fast_exp2(fmaf(v[i + 1], s2, b4.y) + nl); dot = fmaf(v[i + 1], g4.y, dot);
-                            v[i + 2] = fast_exp2(fmaf(v[i + 2], s2, b4.z) + nl); dot = fmaf(v[i + 2], g4.z, dot);
-                            v[i + 3] = fast_exp2(fmaf(v[i + 3], s2, b4.w) + nl); dot = fmaf(v[i + 3], g4.w, dot);
+                            v[i] = fast_exp2(fmaf(v[i], s2, b4.x) + nl);         dot = fmaf(v[i], g[i], dot);
+                            v[i + 1] = fast_exp2(fmaf(v[i + 1], s2, b4.y) + nl); dot = fmaf(v[i + 1], g[i + 1], dot);
+                            v[i + 2] = fast_exp2(fmaf(v[i + 2], s2, b4.z) + nl); dot = fmaf(v[i + 2], g[i + 2], dot);
+                            v[i + 3] = fast_exp2(fmaf(v[i + 3], s2, b4.w) + nl); dot = fmaf(v[i + 3], g[i + 3], dot);
                         }
-                        tmem_st16(tl + c0, v);
+                        tmem_st16_nowait(tl + c0, v);
                     }
                 }
+                tmem_wait_st();
                 part_s[cg][row] = dot;
                 __syncthreads(); PAG_PHASE(8);
                 dot = (part_s[0][row] + part_s[1][row]) + (part_s[2][row] + part_s[3][row]);
@@ -520,19 +596,18 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             for (int k = 0; k < 4; ++k) {
                 const int c0 = 16 * (cg + PCB_NCG * k);
                 if (c0 < l.CiP) {
-                    float v[16];
-                    if (inst_softmax) tmem_ld16(tl + c0, v);
+                    float v[16], g[16];
+                    load_g16(gc_row, grow, c0, Ci, vec4, scale, g);
+                    if (inst_softmax) {
+                        tmem_ld16(tl + c0, v);
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 g4 = load_g4(grow, c0 + i, Ci, vec4);
-                        if (inst_softmax) {
-                            v[i] = c2 * v[i] * (g4.x - dot);         v[i + 1] = c2 * v[i + 1] * (g4.y - dot);
-                            v[i + 2] = c2 * v[i + 2] * (g4.z - dot); v[i + 3] = c2 * v[i + 3] * (g4.w - dot);
-                        } else {
-                            v[i] = c2 * g4.x; v[i + 1] = c2 * g4.y; v[i + 2] = c2 * g4.z; v[i + 3] = c2 * g4.w;
-                        }
+                        for (int i = 0; i < 16; ++i) v[i] = c2 * v[i] * (g[i] - dot);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = c2 * g[i];
                     }
-                    grad16_store(v, Gi + (c0 / 8) * TCH, row, lane, db_i3[k]);
+                    tile_store8(Gi + (c0 / 8) * TCH, 0, row, v);
+                    tile_store8(Gi + (c0 / 8) * TCH, 1, row, v + 8);
                 }
             }
         }
@@ -542,7 +617,11 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             tc_fence_after();
             if (do_inst) {
                 mma16_bwd_weight(tm + PCB_DWI3, aGi, aH2, 64, !first);
-                if (l.CiP > 128) mma16_bwd_weight(tm + PCB_DWI3 + 64, aGi + 16 * TCH, aH2, 64, !first);
+                mma16_bwd_weight(tm + PCB_DB3, aGi, aOnes, 16, !first);
+                if (l.CiP > 128) {
+                    mma16_bwd_weight(tm + PCB_DWI3 + 64, aGi + 16 * TCH, aH2, 64, !first);
+                    mma16_bwd_weight(tm + PCB_DB3 + 16, aGi + 16 * TCH, aOnes, 16, !first);
+                }
                 mma16_bwd_data(tm + PCB_S1, aGi, wi3, 64, l.CiP, l.CiP, false);
             }
             if (do_sem) {
@@ -552,35 +631,29 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             mb.commit();
         }
         mb.wait(); PAG_PHASE(10);
-        if (do_inst) epi_grad16(tl + PCB_S1 + c16, mask_2, H2 + 2 * cg * TCH, row, lane, db_i2);
-        if (do_sem) epi_grad16(tl + PCB_S0 + c16, mask_s, Hs + 2 * cg * TCH, row, lane, db_s1);
+        if (do_inst) epi_grad16_nb(tl + PCB_S1 + c16, mask_2, H2 + 2 * cg * TCH, row);           // G2 overwrites H2
+        if (do_sem) epi_grad16(tl + PCB_S0 + c16, mask_s, Hs + 2 * cg * TCH, row, lane, db_s1);  // Gs1 overwrites Hs
         // ---------------- stage 5 ----------------
-        sync_to_mma(); PAG_PHASE(11);
-        if (warp == 0 && elect_one()) {
-            tc_fence_after();
-            if (do_inst) {
-                mma16_bwd_weight(tm + PCB_DWI2, aH2, aH1, 64, !first);
-                mma16_bwd_data(tm + PCB_S1, aH2, wi2, 64, 64, 64, false);
-            }
-            if (do_sem) {
-                mma16_bwd_weight(tm + PCB_DWS1, aHs, aX, l.INP, !first);
-                if (g_panop) mma16_bwd_data(tm + PCB_S0, aHs, ws1, l.INP, 64, 64, false);
-            }
-            mb.commit();
-        }
-        mb.wait(); PAG_PHASE(12);
-        // ---------------- stage 6 ----------------
         if (do_inst) {
-            epi_grad16(tl + PCB_S1 + c16, mask_1, H1 + 2 * cg * TCH, row, lane, db_i1);
-            sync_to_mma(); PAG_PHASE(13);
+            sync_to_mma(); PAG_PHASE(11);
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
-                mma16_bwd_weight(tm + PCB_DWI1, aH1, aX, l.INP, !first);
-                if (g_panop) mma16_bwd_data(tm + PCB_S0, aH1, wi1, l.INP, 64, 64, do_sem);
+                mma16_bwd_weight(tm + PCB_DWI2, aH2, aH1, 80, !first);      // B = H1 | ones: column 64 = bias gradient
+                mma16_bwd_data(tm + PCB_S1, aH2, wi2, 64, 64, 64, false);
                 mb.commit();
             }
-            mb.wait(); PAG_PHASE(14);
+            mb.wait(); PAG_PHASE(12);
+            epi_grad16(tl + PCB_S1 + c16, mask_1, H1 + 2 * cg * TCH, row, lane, db_i1);           // G1 overwrites H1
         }
+        // ---------------- stage 6: both first layers at once ----------------
+        sync_to_mma(); PAG_PHASE(13);
+        if (warp == 0 && elect_one()) {
+            tc_fence_after();
+            mma16_bwd_weight(tm + PCB_DW1J, aHs, aX, l.INP, !first);                              // A = Gs1 | G1
+            if (g_panop) mma16_bwd_data(tm + PCB_S0, aHs, w1j, l.INP, 128, 128, false);           // K = 128
+            mb.commit();
+        }
+        mb.wait(); PAG_PHASE(14);
         if (g_panop && c16 < l.INP) {
             float v[16];
             tmem_ld16(tl + PCB_S0 + c16, v);
@@ -603,22 +676,30 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         tc_fence_after();
         const int f1 = scatter_base(lane, 32) >> 1;     // feature (of 16) owned by this lane pair after grad16_store
         const bool own = !(lane & 1);
+        if (c16 < l.INP) {      // joint first-layer gradient: lanes 0..63 semantic, 64..127 instance
+            if (row < 64) { if (do_sem) flush_dw16(tl + PCB_DW1J, p.gWs1, row, 64, IN, c16, inv_scale); }
+            else if (do_inst) flush_dw16(tl + PCB_DW1J, p.gWi1, row - 64, 64, IN, c16, inv_scale);
+        }
         if (do_sem) {
-            if (c16 < l.INP) flush_dw16(tl + PCB_DWS1, p.gWs1, row, 64, IN, c16, inv_scale);
             if (cg == 0) flush_dw_T(tl + PCB_DWS2T, p.gWs2, row, 64, Cs, inv_scale);
             if (own) red_add_f32(p.gbs1 + c16 + f1, db_s1 * inv_scale);
             if (own && cg == 0 && f1 < Cs) red_add_f32(p.gbs2 + f1, db_s2 * inv_scale);
         }
         if (do_inst) {
-            if (c16 < l.INP) flush_dw16(tl + PCB_DWI1, p.gWi1, row, 64, IN, c16, inv_scale);
             flush_dw16(tl + PCB_DWI2, p.gWi2, row, 64, 64, c16, inv_scale);
             flush_dw16(tl + PCB_DWI3, p.gWi3, row, Ci, 64, c16, inv_scale);
             if (l.CiP > 128) flush_dw16(tl + PCB_DWI3 + 64, p.gWi3 + (size_t)128 * 64, row, Ci - 128, 64, c16, inv_scale);
-            if (own) { red_add_f32(p.gbi1 + c16 + f1, db_i1 * inv_scale); red_add_f32(p.gbi2 + c16 + f1, db_i2 * inv_scale); }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = 16 * (cg + PCB_NCG * k) + f1;
-                if (own && j < Ci) red_add_f32(p.gbi3 + j, db_i3[k] * inv_scale);
+            if (own) red_add_f32(p.gbi1 + c16 + f1, db_i1 * inv_scale);
+            if (cg == 0) {      // ones-trick bias gradients: column 0 of the extra accumulators
+                float v[16];
+                tmem_ld16(tl + PCB_DWI2 + 64, v);
+                if (row < 64) red_add_f32(p.gbi2 + row, v[0] * inv_scale);
+                tmem_ld16(tl + PCB_DB3, v);
+                if (row < Ci) red_add_f32(p.gbi3 + row, v[0] * inv_scale);
+                if (l.CiP > 128) {
+                    tmem_ld16(tl + PCB_DB3 + 16, v);
+                    if (128 + row < Ci) red_add_f32(p.gbi3 + 128 + row, v[0] * inv_scale);
+                }
             }
         }
     }
@@ -679,7 +760,7 @@ int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const floa
 int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
-                             const int64_t* ridx, const float* g_sem, const float* g_inst, const float* inst_lse,
+                             const int64_t* ridx, int64_t R, const float* g_sem, const float* g_inst, const float* inst_lse,
                              const float* grad_scale, float* g_panop, const int64_t* m_dev, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
     if (Ci > 0 && g_inst && inst_softmax && !inst_lse) return PAG_ERR_ARG;
@@ -694,7 +775,7 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = fused_num_sms();
     pan_comp_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), PCB_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, inst_lse, grad_scale, g_panop, m_dev);
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

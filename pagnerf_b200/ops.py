@@ -451,7 +451,7 @@ class PanCompositeFn(Function):
         gp = torch.empty_like(f) if need else None
         if gs is not None or gi is not None:
             call("pag_pan_composite_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), ptr_array(grads), HIDDEN, Cs, Ci,
-                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(grad_scale(gs, gi)), ptr(gp), None)
+                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), int(a_.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(grad_scale(gs, gi)), ptr(gp), None)
         elif gp is not None:
             gp.zero_()
         return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
@@ -684,7 +684,7 @@ class FusedTraceFn(Function):
                 scale_p = grad_scale_dyn(gs if gs is not None else gi, gi if gs is not None else None, None)
                 call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), ptr_array(grads[10:]), HIDDEN,
                      Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
-                     ptr(wgt), ptr(alpha), ptr(ridx), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev))
+                     ptr(wgt), ptr(alpha), ptr(ridx), int(alpha.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev))
                 if need_gp:
                     call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
                          ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
