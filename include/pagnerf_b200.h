@@ -154,7 +154,11 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
                              const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
                              const int64_t* ridx, int64_t R, const float* g_sem, const float* g_inst, const float* inst_lse,
-                             const float* grad_scale, float* g_panop, const int64_t* m_dev, void* stream);
+                             const float* grad_scale, float* g_panop, const int64_t* m_dev, float* workspace,
+                             int64_t workspace_bytes, void* stream);
+/* workspace (nullable, device): *bytes of pag_pan_composite_bwd_workspace(M, IN, Cs, Ci, &bytes), 16-byte aligned.  With it every CTA stores its
+ * partial weight gradients privately and a second kernel sums them; without it they are accumulated with red.add. */
+int pag_pan_composite_bwd_workspace(int64_t M, int IN, int Cs, int Ci, int64_t* bytes /* host */);
 
 /* ---- packed compositing: tracers/panoptic_packed_rf_tracer.py:134-205 ------------------------------- */
 /* offsets[r] = first packed index with ridx >= r (ridx ascending), offsets[R] = M. */

@@ -20,7 +20,7 @@ _protos = None
 
 # kernels launched per entry point (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {
-    "pag_march_ray_count": 2, "pag_raytrace_count": 2, "pag_grad_scale": 2,
+    "pag_march_ray_count": 2, "pag_raytrace_count": 2, "pag_grad_scale": 2, "pag_pan_composite_bwd_tc": 2,
 }
 launch_count = 0
 
@@ -73,6 +73,15 @@ def load():
 def exported_symbols():
     load()
     return sorted(_protos.keys())
+
+
+def query_i64(name, *args):
+    """Host-side size query `int name(args..., int64_t* out)` (no stream, no launch) -> int."""
+    out = ctypes.c_int64(0)
+    rc = getattr(load(), name)(*args, ctypes.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"pagnerf_b200: {name} -> {rc}")
+    return int(out.value)
 
 
 def ptr(t):

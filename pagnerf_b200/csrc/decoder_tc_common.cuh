@@ -49,11 +49,16 @@ __device__ __forceinline__ void tile_store8(uint8_t* tile, int c, int row, const
     *reinterpret_cast<uint4*>(tile + c * TCH + row * 16) = u;
 }
 // fp16 image of W[OUT][IN] (global fp32, torch Linear layout): [(in/8)][OUTP][8], zero padded
-__device__ __forceinline__ void stage_w16(__half* img, const float* __restrict__ W, int OUT, int IN, int OUTP, int INP) {
+// colscale (nullable, [IN]): per-input-feature factor folded into the weights, W' = W diag(colscale) -- the LOD weights
+// of the feature vector never touch the per-sample path (Y = (x*s) W^T = x W'^T, dX = (G W) * s = G W')
+__device__ __forceinline__ void stage_w16(__half* img, const float* __restrict__ W, int OUT, int IN, int OUTP, int INP,
+                                          const float* __restrict__ colscale = nullptr) {
     const int n = (INP / 8) * OUTP * 8;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int e = i & 7, r = (i >> 3) % OUTP, c = (i >> 3) / OUTP, in = c * 8 + e;
-        img[i] = (r < OUT && in < IN) ? __float2half_rn(__ldg(W + (size_t)r * IN + in)) : __float2half_rn(0.f);
+        float v = 0.f;
+        if (r < OUT && in < IN) { v = __ldg(W + (size_t)r * IN + in); if (colscale) v *= __ldg(colscale + in); }
+        img[i] = __float2half_rn(v);
     }
 }
 __device__ __forceinline__ void stage_b32(float* dst, const float* __restrict__ b, int n, int np) {
@@ -165,20 +170,28 @@ __device__ __forceinline__ void epi_grad16(uint32_t taddr, uint32_t mask, uint8_
     for (int i = 0; i < 16; ++i) v[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
     grad16_store(v, tile2, row, lane, dbacc);
 }
-// flush columns [c0, c0+16) of a dW accumulator row
-__device__ __forceinline__ void flush_dw16(uint32_t taddr, float* __restrict__ gW, int row, int OUT, int IN, int c0, float inv_scale) {
+// flush columns [c0, c0+16) of a dW accumulator row.  plain: the destination is this CTA's private partial buffer
+// (ordinary 16-byte stores, summed over CTAs by a reduce kernel) instead of the shared gradient (red.add).
+__device__ __forceinline__ void flush_dw16(uint32_t taddr, float* __restrict__ gW, int row, int OUT, int IN, int c0, float inv_scale,
+                                           bool plain = false) {
     float v[16];
     tmem_ld16(taddr + c0, v);
     if (row < OUT) {
         float* dst = gW + (size_t)row * IN + c0;
-        if (!(IN & 3) && !(reinterpret_cast<uintptr_t>(gW) & 15)) {   // 16-byte vector reductions: 4x fewer L2 atomics
+        if (!(IN & 3) && !(reinterpret_cast<uintptr_t>(gW) & 15)) {   // 16-byte vector accesses
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
-                if (c0 + i < IN) red_add_f32x4(dst + i, v[i] * inv_scale, v[i + 1] * inv_scale, v[i + 2] * inv_scale, v[i + 3] * inv_scale);
+                if (c0 + i < IN) {
+                    if (plain) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] * inv_scale, v[i + 1] * inv_scale, v[i + 2] * inv_scale, v[i + 3] * inv_scale);
+                    else red_add_f32x4(dst + i, v[i] * inv_scale, v[i + 1] * inv_scale, v[i + 2] * inv_scale, v[i + 3] * inv_scale);
+                }
         } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                if (c0 + i < IN) red_add_f32(dst + i, v[i] * inv_scale);
+                if (c0 + i < IN) {
+                    if (plain) dst[i] = v[i] * inv_scale;
+                    else red_add_f32(dst + i, v[i] * inv_scale);
+                }
         }
     }
 }

@@ -108,12 +108,12 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
     {   // weights (same images as decoder_tc.cu)
         float* b = reinterpret_cast<float*>(sm + l.oBias);
         if (Cs > 0) {
-            stage_w16(reinterpret_cast<__half*>(sm + l.oWs1), p.Ws1, 64, IN, 64, l.INP);
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWs1), p.Ws1, 64, IN, 64, l.INP, lodw);
             stage_w16(reinterpret_cast<__half*>(sm + l.oWs2), p.Ws2, Cs, 64, l.CsP, 64);
             stage_b32(b, p.bs1, 64, 64); stage_b32(b + 64, p.bs2, Cs, l.CsP);
         }
         if (Ci > 0) {
-            stage_w16(reinterpret_cast<__half*>(sm + l.oWi1), p.Wi1, 64, IN, 64, l.INP);
+            stage_w16(reinterpret_cast<__half*>(sm + l.oWi1), p.Wi1, 64, IN, 64, l.INP, lodw);
             stage_w16(reinterpret_cast<__half*>(sm + l.oWi2), p.Wi2, 64, 64, 64, 64);
             stage_w16(reinterpret_cast<__half*>(sm + l.oWi3), p.Wi3, Ci, 64, l.CiP, 64);
             stage_b32(b + 64 + l.CsP, p.bi1, 64, 64); stage_b32(b + 128 + l.CsP, p.bi2, 64, 64);
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
         {   // X tile: chunk c is written by column group c % 4
             const float4* a4 = reinterpret_cast<const float4*>(feats + mm * IN);
             const float4* b4 = dfeats ? reinterpret_cast<const float4*>(dfeats + mm * IN) : nullptr;
-            const float4* w4 = lodw ? reinterpret_cast<const float4*>(lodw) : nullptr;
+            const float4* w4 = nullptr;   // LOD weights are folded into the first-layer weights
             for (int c = cg; c < l.nXc; c += PCF_NCG) {
                 float v[8];
 #pragma unroll
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
 // ---------------------------------------------------------------------------------------------
 // TMEM columns (512).  The instance logits / probabilities [0,208) alias the scratch accumulators S0 / S1 / SEMLOG.
 // Bias gradients of the wide layers come out of the tensor core: a constant "ones" tile is the B operand of an extra
-// N=16 chain (DB3) and an extra 16 columns of the layer-2 weight-gradient chain (DWI2), so the per-tile warp
+// 16 columns of the layer-2 / layer-3 weight-gradient chains (B = H1 | ones, ones | H2), so the per-tile warp
 // reduce-scatter is only left on the two first-layer gradients.
 #define PCB_S0 0
 #define PCB_S1 64
@@ -307,8 +307,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
 #define PCB_DW1J 208     // [128 = (sem L1 | inst L1) x <=48]: both first-layer weight gradients from ONE chain
 #define PCB_DWS2T 256    // [64(h) x 16(classes)] transposed
 #define PCB_DWI2 272     // [64 x (64 + 16)]: column 64 = bias gradient (ones trick)
-#define PCB_DWI3 352     // [Ci(<=208) x 64] as two 128-row blocks
-#define PCB_DB3 480      // [Ci x 16] x 2 blocks: column 0 = bias gradient (ones trick)
+#define PCB_DWI3 352     // [Ci(<=208) x (16 + 64)] as two 128-row blocks: column 0 = bias gradient (ones trick), 16.. = weights
 
 #define PCB_THREADS 512
 #define PCB_NCG 4    // column groups per row
@@ -346,12 +345,54 @@ __host__ __device__ inline PanCompBwdLayout pan_comp_bwd_layout(int IN, int Cs, 
     return l;
 }
 
+// per-CTA partial weight gradients (floats): [Ws1 64xIN | Ws2 Csx64 | Wi1 64xIN | Wi2 64x64 | Wi3 Cix64], 16-byte aligned segments
+struct PanWsLayout { int oWs1, oWs2, oWi1, oWi2, oWi3, total; };
+__host__ __device__ inline PanWsLayout pan_ws_layout(int IN, int Cs, int Ci) {
+    PanWsLayout w;
+    int o = 0;
+    w.oWs1 = o; o += 64 * IN;
+    w.oWs2 = o; o += (Cs * 64 + 3) & ~3;
+    w.oWi1 = o; o += 64 * IN;
+    w.oWi2 = o; o += 64 * 64;
+    w.oWi3 = o; o += (Ci * 64 + 3) & ~3;
+    w.total = o;
+    return w;
+}
+// gW += sum over the CTAs that had at least one tile of their partial slices
+__global__ void __launch_bounds__(256) pan_ws_reduce_kernel(const float* __restrict__ ws, int nblocks, int64_t M, const int64_t* __restrict__ m_dev,
+                                                            int IN, int Cs, int Ci, PanParams p, int do_sem, int do_inst) {
+    if (m_dev) M = min(M, __ldg(m_dev));
+    const int64_t ntiles = (M + 127) / 128;
+    const int nact = (int)(ntiles < nblocks ? ntiles : nblocks);
+    const PanWsLayout wl = pan_ws_layout(IN, Cs, Ci);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wl.total) return;
+    float* dst;
+    if (i < wl.oWs2) dst = do_sem ? p.gWs1 + i : nullptr;
+    else if (i < wl.oWi1) dst = (do_sem && i - wl.oWs2 < Cs * 64) ? p.gWs2 + (i - wl.oWs2) : nullptr;
+    else if (i < wl.oWi2) dst = do_inst ? p.gWi1 + (i - wl.oWi1) : nullptr;
+    else if (i < wl.oWi3) dst = do_inst ? p.gWi2 + (i - wl.oWi2) : nullptr;
+    else dst = (do_inst && i - wl.oWi3 < Ci * 64) ? p.gWi3 + (i - wl.oWi3) : nullptr;
+    if (!dst) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = 0;
+    for (; b + 4 <= nact; b += 4) {
+        a0 += ws[(size_t)b * wl.total + i]; a1 += ws[(size_t)(b + 1) * wl.total + i];
+        a2 += ws[(size_t)(b + 2) * wl.total + i]; a3 += ws[(size_t)(b + 3) * wl.total + i];
+    }
+    for (; b < nact; ++b) a0 += ws[(size_t)b * wl.total + i];
+    *dst += (a0 + a1) + (a2 + a3);
+}
+
 // rows [row0, row0 + rows) of a joint weight image with OUTP output rows; W == nullptr stages zeros
-__device__ __forceinline__ void stage_w16_part(__half* img, const float* __restrict__ W, int OUT, int IN, int rows, int row0, int OUTP, int INP) {
+__device__ __forceinline__ void stage_w16_part(__half* img, const float* __restrict__ W, int OUT, int IN, int rows, int row0, int OUTP, int INP,
+                                               const float* __restrict__ colscale) {
     const int n = (INP / 8) * rows * 8;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int e = i & 7, r = (i >> 3) % rows, c = (i >> 3) / rows, in = c * 8 + e;
-        img[((size_t)c * OUTP + row0 + r) * 8 + e] = (W && r < OUT && in < IN) ? __float2half_rn(__ldg(W + (size_t)r * IN + in)) : __float2half_rn(0.f);
+        float v = 0.f;
+        if (W && r < OUT && in < IN) { v = __ldg(W + (size_t)r * IN + in); if (colscale) v *= __ldg(colscale + in); }
+        img[((size_t)c * OUTP + row0 + r) * 8 + e] = __float2half_rn(v);
     }
 }
 
@@ -404,7 +445,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
     const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
     const float* __restrict__ g_sem, const float* __restrict__ g_inst, int64_t R, const float* __restrict__ inst_lse,
-    const float* __restrict__ scale_ptr, float* __restrict__ g_panop, const int64_t* __restrict__ m_dev) {
+    const float* __restrict__ scale_ptr, float* __restrict__ g_panop, const int64_t* __restrict__ m_dev, float* __restrict__ ws) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
@@ -420,8 +461,8 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     {
         float* b = reinterpret_cast<float*>(sm + l.oBias);
         __half* w1 = reinterpret_cast<__half*>(sm + l.oW1);
-        stage_w16_part(w1, do_sem ? p.Ws1 : nullptr, 64, IN, 64, 0, 128, l.INP);
-        stage_w16_part(w1, do_inst ? p.Wi1 : nullptr, 64, IN, 64, 64, 128, l.INP);
+        stage_w16_part(w1, do_sem ? p.Ws1 : nullptr, 64, IN, 64, 0, 128, l.INP, lodw);
+        stage_w16_part(w1, do_inst ? p.Wi1 : nullptr, 64, IN, 64, 64, 128, l.INP, lodw);
         if (do_sem) {
             stage_w16(reinterpret_cast<__half*>(sm + l.oWs2), p.Ws2, Cs, 64, l.CsP, 64);
             stage_b32(b, p.bs1, 64, 64); stage_b32(b + 64, p.bs2, Cs, l.CsP);
@@ -484,7 +525,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         const float a_row = __ldg(alpha + ray);
         PAG_PHASE(0);
         // ---------------- stage 1 ----------------
-        xpf_consume<PCB_NCG, PCB_MAXK>(pf, dfeats != nullptr, lodw, IN, l.INP, X, row, cg);
+        xpf_consume<PCB_NCG, PCB_MAXK>(pf, dfeats != nullptr, nullptr, IN, l.INP, X, row, cg);   // LOD weights live in W1
         PAG_PHASE(1);
         {   // next tile: inputs by cp.async, row scalars into registers
             const int64_t tn = tile + gridDim.x;
@@ -536,29 +577,32 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         }
         mb.wait(); PAG_PHASE(5);
         if (do_inst) mask_2 = epi_relu16(tl + PCB_S0 + c16, bi2 + c16, H2 + 2 * cg * TCH, row);
-        if (do_sem && cg == 0) {   // semantic head gradient (<= 16 classes): column group 0 only
-            float z[16], g[16];
-            tmem_ld16(tl + PCB_SEMLOG, z);
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { z[j] += bs2[j]; if (j < Cs) mx = fmaxf(mx, z[j]); }
-            float Z = 0.f, E = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float gj = (j < Cs) ? __ldg(g_sem + ray * Cs + j) : 0.f;
-                const float e = (j < Cs) ? (sem_softmax ? __expf(z[j] - mx) : 1.f) : 0.f;
-                g[j] = gj; z[j] = e;
-                Z += e; E = fmaf(e, gj, E);
-            }
-            const float iz = 1.f / Z, dot = E * iz, css = cs * scale;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = (j < Cs) ? (sem_softmax ? css * z[j] * iz * (g[j] - dot) : css * g[j]) : 0.f;
-            grad16_store(g, Gs, row, lane, db_s2);
-        }
+        float zs[16];
+        if (do_sem && cg == 0) tmem_ld16(tl + PCB_SEMLOG, zs);     // before the instance logits overwrite the column range
         // ---------------- stage 3: instance logits + head gradient; 16-column block b belongs to group b % 4 ----------------
         if (do_inst) {
             sync_to_mma(); PAG_PHASE(6);
             if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aH2, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
+        }
+        if (do_sem && cg == 0) {   // semantic head gradient (<= 16 classes): column group 0, while the logits MMA runs
+            float g[16];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { zs[j] += bs2[j]; if (j < Cs) mx = fmaxf(mx, zs[j]); }
+            float Z = 0.f, E = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float gj = (j < Cs) ? __ldg(g_sem + ray * Cs + j) : 0.f;
+                const float e = (j < Cs) ? (sem_softmax ? __expf(zs[j] - mx) : 1.f) : 0.f;
+                g[j] = gj; zs[j] = e;
+                Z += e; E = fmaf(e, gj, E);
+            }
+            const float iz = 1.f / Z, dot = E * iz, css = cs * scale;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = (j < Cs) ? (sem_softmax ? css * zs[j] * iz * (g[j] - dot) : css * g[j]) : 0.f;
+            grad16_store(g, Gs, row, lane, db_s2);
+        }
+        if (do_inst) {
             mb.wait(); PAG_PHASE(7);
             // d logit_j = c * p_j * (g_j - <p, g>) / T with p_j = 2^(z_j - lse) from the forward's log-sum-exp: one
             // exp2 per logit; the probabilities go back into TMEM over the logits for the second pass.
@@ -616,12 +660,8 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         if (warp == 0 && elect_one()) {
             tc_fence_after();
             if (do_inst) {
-                mma16_bwd_weight(tm + PCB_DWI3, aGi, aH2, 64, !first);
-                mma16_bwd_weight(tm + PCB_DB3, aGi, aOnes, 16, !first);
-                if (l.CiP > 128) {
-                    mma16_bwd_weight(tm + PCB_DWI3 + 64, aGi + 16 * TCH, aH2, 64, !first);
-                    mma16_bwd_weight(tm + PCB_DB3 + 16, aGi + 16 * TCH, aOnes, 16, !first);
-                }
+                mma16_bwd_weight(tm + PCB_DWI3, aGi, aOnes, 80, !first);      // B = ones | H2: column 0 = bias gradient
+                if (l.CiP > 128) mma16_bwd_weight(tm + PCB_DWI3 + 80, aGi + 16 * TCH, aOnes, 80, !first);
                 mma16_bwd_data(tm + PCB_S1, aGi, wi3, 64, l.CiP, l.CiP, false);
             }
             if (do_sem) {
@@ -660,12 +700,9 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             if (valid) {
 #pragma unroll
                 for (int qi = 0; qi < 4; ++qi) {
-                    if (c16 + 4 * qi < IN) {
-                        const float4 ww = lodw ? __ldg(reinterpret_cast<const float4*>(lodw + c16) + qi) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (c16 + 4 * qi < IN)
                         reinterpret_cast<float4*>(g_panop + mm * IN + c16)[qi] =
-                            make_float4(v[4 * qi] * inv_scale * ww.x, v[4 * qi + 1] * inv_scale * ww.y,
-                                        v[4 * qi + 2] * inv_scale * ww.z, v[4 * qi + 3] * inv_scale * ww.w);
-                    }
+                            make_float4(v[4 * qi] * inv_scale, v[4 * qi + 1] * inv_scale, v[4 * qi + 2] * inv_scale, v[4 * qi + 3] * inv_scale);
                 }
             }
         }
@@ -676,28 +713,53 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         tc_fence_after();
         const int f1 = scatter_base(lane, 32) >> 1;     // feature (of 16) owned by this lane pair after grad16_store
         const bool own = !(lane & 1);
+        // weight gradients: into this CTA's slice of the partial workspace when one is given (plain stores; 148 CTAs
+        // hammering the same 94 KB with red.add serialise in the L2 atomic units), else straight into the gradients
+        const bool plain = ws != nullptr;
+        const PanWsLayout wl = pan_ws_layout(IN, Cs, Ci);
+        float* wsb = plain ? ws + (size_t)blockIdx.x * wl.total : nullptr;
+        float *dWs1 = plain ? wsb + wl.oWs1 : p.gWs1, *dWs2 = plain ? wsb + wl.oWs2 : p.gWs2, *dWi1 = plain ? wsb + wl.oWi1 : p.gWi1,
+              *dWi2 = plain ? wsb + wl.oWi2 : p.gWi2, *dWi3 = plain ? wsb + wl.oWi3 : p.gWi3;
         if (c16 < l.INP) {      // joint first-layer gradient: lanes 0..63 semantic, 64..127 instance
-            if (row < 64) { if (do_sem) flush_dw16(tl + PCB_DW1J, p.gWs1, row, 64, IN, c16, inv_scale); }
-            else if (do_inst) flush_dw16(tl + PCB_DW1J, p.gWi1, row - 64, 64, IN, c16, inv_scale);
+            float* gW1 = (row < 64) ? (do_sem ? dWs1 : nullptr) : (do_inst ? dWi1 : nullptr);
+            float v[16];
+            tmem_ld16(tl + PCB_DW1J + c16, v);      // G^T X with X unweighted: the LOD weight of each input column applies here
+            if (gW1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c16 + i < IN) {
+                        const float x = v[i] * inv_scale * (lodw ? __ldg(lodw + c16 + i) : 1.f);
+                        float* d = gW1 + (size_t)(row & 63) * IN + c16 + i;
+                        if (plain) *d = x; else red_add_f32(d, x);
+                    }
+            }
         }
         if (do_sem) {
-            if (cg == 0) flush_dw_T(tl + PCB_DWS2T, p.gWs2, row, 64, Cs, inv_scale);
+            if (cg == 0) {
+                float v[16];
+                tmem_ld16(tl + PCB_DWS2T, v);      // transposed accumulator [lanes = hidden k][cols = classes j] -> gW[j][k]
+                if (row < 64) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < Cs) { if (plain) dWs2[(size_t)j * 64 + row] = v[j] * inv_scale; else red_add_f32(dWs2 + (size_t)j * 64 + row, v[j] * inv_scale); }
+                }
+            }
             if (own) red_add_f32(p.gbs1 + c16 + f1, db_s1 * inv_scale);
             if (own && cg == 0 && f1 < Cs) red_add_f32(p.gbs2 + f1, db_s2 * inv_scale);
         }
         if (do_inst) {
-            flush_dw16(tl + PCB_DWI2, p.gWi2, row, 64, 64, c16, inv_scale);
-            flush_dw16(tl + PCB_DWI3, p.gWi3, row, Ci, 64, c16, inv_scale);
-            if (l.CiP > 128) flush_dw16(tl + PCB_DWI3 + 64, p.gWi3 + (size_t)128 * 64, row, Ci - 128, 64, c16, inv_scale);
+            flush_dw16(tl + PCB_DWI2, dWi2, row, 64, 64, c16, inv_scale, plain);
+            flush_dw16(tl + PCB_DWI3 + 16, dWi3, row, Ci, 64, c16, inv_scale, plain);
+            if (l.CiP > 128) flush_dw16(tl + PCB_DWI3 + 96, dWi3 + (size_t)128 * 64, row, Ci - 128, 64, c16, inv_scale, plain);
             if (own) red_add_f32(p.gbi1 + c16 + f1, db_i1 * inv_scale);
             if (cg == 0) {      // ones-trick bias gradients: column 0 of the extra accumulators
                 float v[16];
                 tmem_ld16(tl + PCB_DWI2 + 64, v);
                 if (row < 64) red_add_f32(p.gbi2 + row, v[0] * inv_scale);
-                tmem_ld16(tl + PCB_DB3, v);
+                tmem_ld16(tl + PCB_DWI3, v);
                 if (row < Ci) red_add_f32(p.gbi3 + row, v[0] * inv_scale);
                 if (l.CiP > 128) {
-                    tmem_ld16(tl + PCB_DB3 + 16, v);
+                    tmem_ld16(tl + PCB_DWI3 + 80, v);
                     if (128 + row < Ci) red_add_f32(p.gbi3 + 128 + row, v[0] * inv_scale);
                 }
             }
@@ -761,7 +823,8 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
                              const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
                              const int64_t* ridx, int64_t R, const float* g_sem, const float* g_inst, const float* inst_lse,
-                             const float* grad_scale, float* g_panop, const int64_t* m_dev, void* stream) {
+                             const float* grad_scale, float* g_panop, const int64_t* m_dev, float* workspace,
+                             int64_t workspace_bytes, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
     if (Ci > 0 && g_inst && inst_softmax && !inst_lse) return PAG_ERR_ARG;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
@@ -774,9 +837,25 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
     const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = fused_num_sms();
-    pan_comp_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), PCB_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev);
+    const int nblocks = (int)(tiles < cap ? tiles : cap);
+    const PanWsLayout wl = pan_ws_layout(IN, Cs, Ci);
+    float* ws = (workspace && workspace_bytes >= (int64_t)nblocks * wl.total * 4 && !(reinterpret_cast<uintptr_t>(workspace) & 15)) ? workspace : nullptr;
+    pan_comp_bwd_kernel<<<nblocks, PCB_THREADS, l.total, (cudaStream_t)stream>>>(
+        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev, ws);
     PAG_LAUNCH_CHECK();
+    if (ws) {
+        pan_ws_reduce_kernel<<<(wl.total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, nblocks, M, m_dev, IN, Cs, Ci, p,
+                                                                                         (Cs > 0 && g_sem) ? 1 : 0, (Ci > 0 && g_inst) ? 1 : 0);
+        PAG_LAUNCH_CHECK();
+    }
+    return PAG_OK;
+}
+
+// bytes of partial-gradient workspace pag_pan_composite_bwd_tc can use for M samples (0 rows -> 0)
+int pag_pan_composite_bwd_workspace(int64_t M, int IN, int Cs, int Ci, int64_t* bytes) {
+    if (!bytes) return PAG_ERR_ARG;
+    const int64_t tiles = (M + 127) / 128, cap = fused_num_sms();
+    *bytes = (tiles < cap ? tiles : cap) * (int64_t)pan_ws_layout(IN, Cs, Ci).total * 4;
     return PAG_OK;
 }
 

@@ -9,7 +9,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from ._lib import call, ptr, ptr_array
+from ._lib import call, ptr, ptr_array, query_i64
 
 
 def _chk(*tensors):
@@ -414,6 +414,15 @@ def composite(sigma, deltas, depths, rgb, sem, inst, offsets, bg_white=True):
     return CompositeFn.apply(sigma, deltas, depths, rgb, sem, inst, offsets, bg_white)
 
 
+def _pan_bwd_workspace(M, IN, Cs, Ci, device):
+    """(pointer, bytes) of the partial weight-gradient workspace of pag_pan_composite_bwd_tc (torch-allocated: graph safe)."""
+    nbytes = query_i64("pag_pan_composite_bwd_workspace", int(M), int(IN), int(Cs), int(Ci))
+    if nbytes == 0:
+        return None, 0
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=device)   # the caching allocator is stream ordered: safe to drop after enqueue
+    return ptr(ws), nbytes
+
+
 class PanCompositeFn(Function):
     """Semantic + instance heads fused with their (detached-weight) compositing: per-ray outputs [N,Cs], [N,Ci].
     Tensor-core kernels only (training mode); csrc/decoder_tc_fused.cu."""
@@ -451,7 +460,8 @@ class PanCompositeFn(Function):
         gp = torch.empty_like(f) if need else None
         if gs is not None or gi is not None:
             call("pag_pan_composite_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), ptr_array(grads), HIDDEN, Cs, Ci,
-                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), int(a_.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(grad_scale(gs, gi)), ptr(gp), None)
+                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), int(a_.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(grad_scale(gs, gi)), ptr(gp), None,
+                 *_pan_bwd_workspace(M, IN, Cs, Ci, f.device))
         elif gp is not None:
             gp.zero_()
         return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
@@ -684,7 +694,8 @@ class FusedTraceFn(Function):
                 scale_p = grad_scale_dyn(gs if gs is not None else gi, gi if gs is not None else None, None)
                 call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), ptr_array(grads[10:]), HIDDEN,
                      Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
-                     ptr(wgt), ptr(alpha), ptr(ridx), int(alpha.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev))
+                     ptr(wgt), ptr(alpha), ptr(ridx), int(alpha.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev),
+                     *_pan_bwd_workspace(Mmax, IN, Cs, Ci, dev))
                 if need_gp:
                     call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
                          ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
