@@ -20,18 +20,30 @@ static __device__ unsigned long long pag_phase_clk[64];   // one copy per transl
         }                                                                                             \
         return (int)e;                                                                                \
     }
-#define PAG_PHASE_INIT() unsigned long long _ph_t = clock64()
-#define PAG_PHASE(i)                                                                   \
-    do {                                                                               \
-        if (blockIdx.x == 0 && threadIdx.x == 0) {                                     \
-            const unsigned long long _t = clock64();                                   \
-            pag_phase_clk[i] += _t - _ph_t;                                            \
-            _ph_t = _t;                                                                \
-        }                                                                              \
+// accumulate in shared memory (a global read-modify-write per mark would stall thread 0 for an L2 round trip and
+// distort the very timeline being measured); PAG_PHASE_FLUSH adds the block-0 totals to the global counters
+#define PAG_PHASE_INIT()                                                     \
+    __shared__ unsigned long long _ph_s[64];                                 \
+    if (threadIdx.x < 64) _ph_s[threadIdx.x] = 0ull;                         \
+    __syncthreads();                                                         \
+    unsigned long long _ph_t = clock64()
+#define PAG_PHASE(i)                                                         \
+    do {                                                                     \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                           \
+            const unsigned long long _t = clock64();                         \
+            _ph_s[i] += _t - _ph_t;                                          \
+            _ph_t = _t;                                                      \
+        }                                                                    \
+    } while (0)
+#define PAG_PHASE_FLUSH()                                                    \
+    do {                                                                     \
+        __syncthreads();                                                     \
+        if (blockIdx.x == 0 && threadIdx.x < 64) pag_phase_clk[threadIdx.x] += _ph_s[threadIdx.x]; \
     } while (0)
 #else
 #define PAG_PHASE_INIT()
 #define PAG_PHASE(i)
+#define PAG_PHASE_FLUSH()
 #define PAG_PHASE_READER(name)
 #endif
 
@@ -275,39 +287,61 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int NCG, int MAXK>
-__device__ __forceinline__ void xpf_issue(float4* slots, const float* __restrict__ a, const float* __restrict__ b, int IN, int64_t m, int cg) {
-    const int nt = blockDim.x, tid = threadIdx.x;
+// Coalesced variant.  A lane-per-row float4 access touches 32 different 128-byte lines per warp instruction and costs 32 LSU
+// cycles (measured: 3.4 k cycles per 128 x 48 tile pair); here consecutive threads copy consecutive quads of the tile's
+// contiguous [128][IN] block, 4 lines per instruction, into slots[q * 128 + row] (array b: + 128 * IN/4 slots), and thread
+// (row, cg) later reads slots[q * 128 + row], q = cg + NCG k, conflict free.  The consumer reads slots written by other
+// threads: call cp_async_wait_all() before the block barrier that precedes xpfc_consume.
+template <int MAXK>
+__device__ __forceinline__ void xpfc_issue(float4* slots, const float* __restrict__ a, const float* __restrict__ b, int IN, int64_t row0,
+                                           int64_t M) {
+    const int nt = blockDim.x, tid = threadIdx.x, nq = IN >> 2, total = 128 * nq;
 #pragma unroll
     for (int k = 0; k < MAXK; ++k) {
-        const int q = cg + NCG * k;
-        if (4 * q < IN) {
-            cp_async16(slots + (2 * k) * nt + tid, a + m * IN + 4 * q);
-            if (b) cp_async16(slots + (2 * k + 1) * nt + tid, b + m * IN + 4 * q);
+        const int g = tid + nt * k;
+        if (g < total) {
+            const int r = g / nq, q = g - r * nq;
+            const int64_t rs = min(row0 + r, M - 1);
+            cp_async16(slots + q * 128 + r, a + rs * IN + 4 * q);
+            if (b) cp_async16(slots + total + q * 128 + r, b + rs * IN + 4 * q);
         }
     }
     cp_async_commit();
 }
-// (a + b) * lodw of the prefetched quads -> fp16 tile image; quads past IN (image padding up to INP) are zero-filled
 template <int NCG, int MAXK>
-__device__ __forceinline__ void xpf_consume(const float4* slots, bool has_b, const float* __restrict__ lodw, int IN, int INP,
-                                            uint8_t* tile, int row, int cg) {
-    const int nt = blockDim.x, tid = threadIdx.x;
-    cp_async_wait_all();
+__device__ __forceinline__ void xpfc_consume(const float4* slots, bool has_b, int IN, int INP, uint8_t* tile, int row, int cg) {
+    const int total = 128 * (IN >> 2);
 #pragma unroll
     for (int k = 0; k < MAXK; ++k) {
         const int q = cg + NCG * k;
         if (4 * q < INP) {
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (4 * q < IN) {
-                x = slots[(2 * k) * nt + tid];
-                if (has_b) { const float4 y = slots[(2 * k + 1) * nt + tid]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-                if (lodw) { const float4 w = __ldg(reinterpret_cast<const float4*>(lodw) + q); x.x *= w.x; x.y *= w.y; x.z *= w.z; x.w *= w.w; }
+                x = slots[q * 128 + row];
+                if (has_b) { const float4 y = slots[total + q * 128 + row]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
             }
             uint2 u;
             u.x = pack_h2(x.x, x.y); u.y = pack_h2(x.z, x.w);
             *reinterpret_cast<uint2*>(tile + (q >> 1) * TCH + row * 16 + (q & 1) * 8) = u;
         }
+    }
+}
+// direct (register) variant of the same coalesced mapping for kernels without spare shared memory: thread t loads quads
+// t, t + nthreads, ... of the tile block and writes them into the fp16 image itself
+__device__ __forceinline__ void stage_x_coalesced(uint8_t* tile, const float* __restrict__ a, const float* __restrict__ b, int IN, int INP,
+                                                  int64_t row0, int64_t M) {
+    const int nt = blockDim.x, nq = IN >> 2, nqp = INP >> 2;
+    for (int g = threadIdx.x; g < 128 * nqp; g += nt) {
+        const int r = g / nqp, q = g - r * nqp;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < nq) {
+            const int64_t rs = min(row0 + r, M - 1);
+            x = __ldg(reinterpret_cast<const float4*>(a + rs * IN) + q);
+            if (b) { const float4 y = __ldg(reinterpret_cast<const float4*>(b + rs * IN) + q); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+        }
+        uint2 u;
+        u.x = pack_h2(x.x, x.y); u.y = pack_h2(x.z, x.w);
+        *reinterpret_cast<uint2*>(tile + (q >> 1) * TCH + r * 16 + (q & 1) * 8) = u;
     }
 }
 

@@ -142,26 +142,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
         const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
-        {   // X tile: chunk c is written by column group c % 4
-            const float4* a4 = reinterpret_cast<const float4*>(feats + mm * IN);
-            const float4* b4 = dfeats ? reinterpret_cast<const float4*>(dfeats + mm * IN) : nullptr;
-            const float4* w4 = nullptr;   // LOD weights are folded into the first-layer weights
-            for (int c = cg; c < l.nXc; c += PCF_NCG) {
-                float v[8];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int qi = 2 * c + h;
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (4 * qi < IN) {
-                        x = __ldg(a4 + qi);
-                        if (b4) { const float4 y = __ldg(b4 + qi); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-                        if (w4) { const float4 ww = __ldg(w4 + qi); x.x *= ww.x; x.y *= ww.y; x.z *= ww.z; x.w *= ww.w; }
-                    }
-                    v[4 * h] = x.x; v[4 * h + 1] = x.y; v[4 * h + 2] = x.z; v[4 * h + 3] = x.w;
-                }
-                tile_store8(X, c, row, v);
-            }
-        }
+        stage_x_coalesced(X, feats, dfeats, IN, l.INP, tile * 128, M);   // LOD weights are folded into the first-layer weights
         if (tile + gridDim.x < ntiles)
             prefetch_x_l2(feats, dfeats, IN, l.nXc, min((tile + gridDim.x) * 128 + row, M - 1), cg, PCF_NCG);
         if (cg == 0) {   // compositing coefficients of this quadrant's rows
@@ -507,7 +488,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     float n_w = 0.f, n_lse = 0.f;
     if ((int64_t)blockIdx.x < ntiles) {
         const int64_t m0 = min((int64_t)blockIdx.x * 128 + row, M - 1);
-        xpf_issue<PCB_NCG, PCB_MAXK>(pf, feats, dfeats, IN, m0, cg);
+        xpfc_issue<PCB_MAXK>(pf, feats, dfeats, IN, (int64_t)blockIdx.x * 128, M);
         n_ray = ridx[m0]; n_w = __ldg(w + m0); n_ray0 = ridx[(int64_t)blockIdx.x * 128];
         if (inst_lse) n_lse = __ldg(inst_lse + m0);
     }
@@ -515,6 +496,8 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     const int gc_r0 = tid / ci1, gc_c0 = tid % ci1, gc_dr = PCB_THREADS / ci1, gc_dc = PCB_THREADS % ci1;
     bool first = true;
     PAG_PHASE_INIT();
+    cp_async_wait_all();
+    __syncthreads();
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
         const int64_t m = tile * 128 + row;
         const bool valid = m < M;
@@ -525,13 +508,12 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         const float a_row = __ldg(alpha + ray);
         PAG_PHASE(0);
         // ---------------- stage 1 ----------------
-        xpf_consume<PCB_NCG, PCB_MAXK>(pf, dfeats != nullptr, nullptr, IN, l.INP, X, row, cg);   // LOD weights live in W1
+        xpfc_consume<PCB_NCG, PCB_MAXK>(pf, dfeats != nullptr, IN, l.INP, X, row, cg);   // LOD weights live in W1
         PAG_PHASE(1);
-        {   // next tile: inputs by cp.async, row scalars into registers
+        {   // row scalars of the next tile into registers
             const int64_t tn = tile + gridDim.x;
             if (tn < ntiles) {
                 const int64_t mn = min(tn * 128 + row, M - 1);
-                xpf_issue<PCB_NCG, PCB_MAXK>(pf, feats, dfeats, IN, mn, cg);
                 n_ray = ridx[mn]; n_w = __ldg(w + mn); n_ray0 = ridx[tn * 128];
                 if (inst_lse) n_lse = __ldg(inst_lse + mn);
             }
@@ -542,6 +524,8 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             mma16_fwd(tm + PCB_S0, aX, w1j, 128, 128, l.INP, false);     // sem | inst first layers in one chain
             mb.commit();
         }
+        if (tile + gridDim.x < ntiles)     // every thread is past its slot reads: the next tile's inputs stream in from here
+            xpfc_issue<PCB_MAXK>(pf, feats, dfeats, IN, (tile + gridDim.x) * 128, M);
         // while the MMAs run: the tile's per-ray output gradients (first PCB_NGC rays) -> registers, coalesced
         float gpre[7];
         const int ngc_elems = PCB_NGC * Ci;
@@ -706,6 +690,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                 }
             }
         }
+        cp_async_wait_all();      // own copies landed; the barrier publishes everybody's
         tc_fence_before();
         __syncthreads(); PAG_PHASE(15);
     }
@@ -768,6 +753,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     tc_fence_before();
     __syncthreads();
     PAG_PHASE(40);
+    PAG_PHASE_FLUSH();
     if (warp == 0) tmem_dealloc(tm, 512);
 }
 
