@@ -127,11 +127,15 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
                          void* stream);
 int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, int hidden, int view_dim,
-                             int want_rgb, float* sigma, float* rgb, void* stream);
+                             int want_rgb, float* sigma, float* rgb, const void* view_pe16, void* stream);
 int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, float* const* grads, int hidden,
                              int view_dim, const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats,
-                             float* g_dir, void* stream);
+                             float* g_dir, const void* view_pe16, float* workspace, int64_t workspace_bytes, void* stream);
+/* view_pe16 (nullable): per-ray fp16 view embedding [R][32] from pag_view_pe16 -- the decoders copy it instead of evaluating
+ * the positional embedding per sample.  workspace (nullable, device, 16-byte aligned): see pag_pan_composite_bwd_tc. */
+int pag_view_pe16(const float* ray_d, int64_t R, void* pe16, void* stream);
+int pag_decode_dc_bwd_workspace(int64_t M_max, int IN, int64_t* bytes /* host */);
 int pag_decode_pan_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                           const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
                           float inst_temperature, float* sem, float* inst, void* stream);

@@ -24,10 +24,17 @@
 // ---------------------------------------------------------------------------------------------
 // density + color
 // ---------------------------------------------------------------------------------------------
+#define DC_THREADS 512
+#define DC_NCG 4     // column groups per sample row: warps w, w+4, w+8, w+12 share TMEM lane quadrant w % 4
+#define DC_MAXK 4    // input quads per thread in the coalesced prefetch: 128 * (IN <= 64) / 4 / 512
+
 struct DcTcLayout {  // byte offsets inside dynamic smem
     int INP, nXc;
-    int oG3, oGy, oX, oCin, oHd, oH1, oH2, oWd1, oWd2, oWc1, oWc2, oWc3, oBias, total;
+    int oG3, oGy, oOnesA, oX, oHd, oOnesB, oCin, oH1, oOnesC, oH2, oWd1, oWd2, oWc1, oWc2, oWc3, oBias, oPF, total;
 };
+// Backward tile order: G3 Gy | onesA X | Hd onesB Cin | H1 onesC H2.  Each constant "ones" tile (feature 0 = 1) sits next
+// to the B operands of two weight-gradient chains, which therefore also produce the bias gradients:
+//   dWd1 = Gd^T [onesA | X]   dWd2 = Gy^T [Hd | onesB]   dWc1 = G1^T [onesB | Cin]   dWc2 = G2^T [H1 | onesC]   dWc3 = G3^T [onesC | H2]
 __host__ __device__ inline DcTcLayout dc_tc_layout(int IN, bool bwd) {
     DcTcLayout l;
     l.INP = (IN + 15) & ~15;
@@ -35,10 +42,13 @@ __host__ __device__ inline DcTcLayout dc_tc_layout(int IN, bool bwd) {
     int o = 0;
     l.oG3 = o; o += bwd ? 2 * TCH : 0;
     l.oGy = o; o += bwd ? 2 * TCH : 0;
+    l.oOnesA = o; o += bwd ? 2 * TCH : 0;
     l.oX = o; o += 8 * TCH;            // X (<= 64 feats); forward reuses it for Hc2
-    l.oCin = o; o += bwd ? 6 * TCH : 0;
     l.oHd = o; o += 8 * TCH;
+    l.oOnesB = o; o += bwd ? 2 * TCH : 0;
+    l.oCin = o; o += bwd ? 6 * TCH : 0;
     l.oH1 = o; o += bwd ? 8 * TCH : 0;
+    l.oOnesC = o; o += bwd ? 2 * TCH : 0;
     l.oH2 = o; o += bwd ? 8 * TCH : 0;
     l.oWd1 = o; o += l.nXc * 64 * 16;
     l.oWd2 = o; o += 8 * 16 * 16;
@@ -47,12 +57,15 @@ __host__ __device__ inline DcTcLayout dc_tc_layout(int IN, bool bwd) {
     l.oWc3 = o; o += 8 * 16 * 16;
     l.oBias = o; o += (64 + 16 + 64 + 64 + 16) * 4;
     if (bwd && o < l.oH2 + 16 * TCH) o = l.oH2 + 16 * TCH;  // MN-major A operands read 16 chunks from their base
+    o = (o + 15) & ~15;
+    l.oPF = o; o += bwd ? 128 * (IN >> 2) * 16 : 0;          // cp.async slots of the next tile's inputs
     l.total = o;
     return l;
 }
 
-__device__ __forceinline__ void dc_tc_stage(uint8_t* sm, const DcTcLayout& l, const DcParams& p, int IN) {
-    stage_w16(reinterpret_cast<__half*>(sm + l.oWd1), p.Wd1, 64, IN, 64, l.INP);
+// lodw (nullable): per-feature LOD weights, folded into the first density layer (see stage_w16)
+__device__ __forceinline__ void dc_tc_stage(uint8_t* sm, const DcTcLayout& l, const DcParams& p, int IN, const float* __restrict__ lodw) {
+    stage_w16(reinterpret_cast<__half*>(sm + l.oWd1), p.Wd1, 64, IN, 64, l.INP, lodw);
     stage_w16(reinterpret_cast<__half*>(sm + l.oWd2), p.Wd2, 16, 64, 16, 64);
     stage_w16(reinterpret_cast<__half*>(sm + l.oWc1), p.Wc1, 64, CIN, 64, 48);
     stage_w16(reinterpret_cast<__half*>(sm + l.oWc2), p.Wc2, 64, 64, 64, 64);
@@ -61,9 +74,6 @@ __device__ __forceinline__ void dc_tc_stage(uint8_t* sm, const DcTcLayout& l, co
     stage_b32(b, p.bd1, 64, 64); stage_b32(b + 64, p.bd2, 16, 16); stage_b32(b + 80, p.bc1, 64, 64);
     stage_b32(b + 144, p.bc2, 64, 64); stage_b32(b + 208, p.bc3, 3, 16);
 }
-
-#define DC_THREADS 512
-#define DC_NCG 4   // column groups per sample row: warps w, w+4, w+8, w+12 share TMEM lane quadrant w % 4
 
 // 16 features [16*cg, 16*cg+16) of the color-decoder input row [y16 | PE(-d) 27 | 0 pad 5], cg = 1, 2
 __device__ __forceinline__ void stage_cin_pe(uint8_t* tile, int row, int cg, float dx, float dy, float dz) {
@@ -82,12 +92,35 @@ __device__ __forceinline__ void stage_cin_pe(uint8_t* tile, int row, int cg, flo
     tile_store8(tile, 2 * cg, row, v);
     tile_store8(tile, 2 * cg + 1, row, v + 8);
 }
+// the same from the per-ray fp16 embedding image pe16[ray][32 halfs] (pag_view_pe16): two 16-byte copies
+__device__ __forceinline__ void stage_cin_pe16(uint8_t* tile, int row, int cg, uint4 a, uint4 b) {
+    *reinterpret_cast<uint4*>(tile + (2 * cg) * TCH + row * 16) = a;
+    *reinterpret_cast<uint4*>(tile + (2 * cg + 1) * TCH + row * 16) = b;
+}
+
+// per-ray view embedding, fp16, padded to 32: the decoders copy it instead of evaluating 24 sin/cos per SAMPLE
+__global__ void view_pe16_kernel(const float* __restrict__ ray_d, int64_t R, __half* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float pe[32];
+    view_embed(ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2], pe);
+#pragma unroll
+    for (int i = PE_DIM; i < 32; ++i) pe[i] = 0.f;
+    uint4* o = reinterpret_cast<uint4*>(out + r * 32);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint4 u;
+        u.x = pack_h2(pe[8 * c], pe[8 * c + 1]); u.y = pack_h2(pe[8 * c + 2], pe[8 * c + 3]);
+        u.z = pack_h2(pe[8 * c + 4], pe[8 * c + 5]); u.w = pack_h2(pe[8 * c + 6], pe[8 * c + 7]);
+        o[c] = u;
+    }
+}
 
 __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
                                                                const float* __restrict__ ray_d, int S, int64_t M, int IN,
                                                                DcParams p, int want_rgb, float* __restrict__ sigma,
                                                                float* __restrict__ rgb, const int64_t* __restrict__ m_dev,
-                                                               const int64_t* __restrict__ ridx) {
+                                                               const int64_t* __restrict__ ridx, const uint4* __restrict__ pe16) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
@@ -95,7 +128,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
     const DcTcLayout l = dc_tc_layout(IN, false);
     const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane, c16 = 16 * cg;
-    dc_tc_stage(sm, l, p, IN);
+    dc_tc_stage(sm, l, p, IN, lodw);
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 128);
     sync_to_mma();
@@ -112,9 +145,17 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
         const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
-        stage_x_cg(T0, row, cg, DC_NCG, feats, nullptr, lodw, IN, l.nXc, mm);
+        stage_x_coalesced(T0, feats, nullptr, IN, l.INP, tile * 128, M);
+        // view embedding of this row's ray: issued now, consumed two MMA phases later
+        uint4 pa = make_uint4(0u, 0u, 0u, 0u), pb = pa;
+        int64_t r = 0;
+        if (want_rgb && (cg == 1 || cg == 2)) {
+            r = ridx ? ridx[mm] : mm / S;
+            if (pe16) { pa = __ldg(pe16 + r * 4 + 2 * (cg - 1)); pb = __ldg(pe16 + r * 4 + 2 * (cg - 1) + 1); }
+        }
         sync_to_mma();
         if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aT0, wd1, 64, 64, l.INP, false); mb.commit(); }
+        if (tile + gridDim.x < ntiles) prefetch_x_l2(feats, nullptr, IN, l.nXc, min((tile + gridDim.x) * 128 + row, M - 1), cg, DC_NCG);
         mb.wait();
         epi_relu16(tl + c16, bias + c16, T1 + 2 * cg * TCH, row);
         sync_to_mma();
@@ -128,8 +169,8 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
             if (valid) sigma[m] = fmaxf(y[0], 0.f);
             if (want_rgb) { tile_store8(T0, 0, row, y); tile_store8(T0, 1, row, y + 8); }
         } else if (want_rgb && cg <= 2) {
-            const int64_t r = ridx ? ridx[mm] : mm / S;
-            stage_cin_pe(T0, row, cg, ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2]);
+            if (pe16) stage_cin_pe16(T0, row, cg, pa, pb);
+            else stage_cin_pe(T0, row, cg, ray_d[3 * r], ray_d[3 * r + 1], ray_d[3 * r + 2]);
         }
         if (!want_rgb) { tc_fence_before(); __syncthreads(); continue; }
         sync_to_mma();
@@ -159,21 +200,37 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
     if (warp == 0) tmem_dealloc(tm, 128);
 }
 
-// TMEM columns of the backward kernel
+// TMEM columns of the backward kernel (512): two scratch accumulators + five weight-gradient accumulators, each with 16
+// extra columns (from the ones tile next to its B operand) whose first column is the bias gradient
 #define DCB_S0 0
 #define DCB_S1 64
-#define DCB_DWD1 128   // [64 x <=64]
-#define DCB_DWD2 192   // [16 x 64]
-#define DCB_DWC1 256   // [64 x 48]
-#define DCB_DWC2 304   // [64 x 64]
-#define DCB_DWC3 368   // [3  x 64]  -> 432 columns used
+#define DCB_DWD1 128   // [64 x (16 + INP<=64)]   bias col 0,  weights col 16..
+#define DCB_DWD2 208   // [16 x (64 + 16)]        weights col 0.., bias col 64
+#define DCB_DWC1 288   // [64 x (16 + 48)]        bias col 0,  weights col 16..
+#define DCB_DWC2 352   // [64 x (64 + 16)]        weights col 0.., bias col 64
+#define DCB_DWC3 432   // [3  x (16 + 64)]        bias col 0,  weights col 16..   -> 512
+
+// per-CTA partial weight gradients (floats): [Wd1 64xIN | Wd2 16x64 | Wc1 64x43 (+pad) | Wc2 64x64 | Wc3 3x64]
+struct DcWsLayout { int oWd1, oWd2, oWc1, oWc2, oWc3, total; };
+__host__ __device__ inline DcWsLayout dc_ws_layout(int IN) {
+    DcWsLayout w;
+    int o = 0;
+    w.oWd1 = o; o += 64 * IN;
+    w.oWd2 = o; o += 16 * 64;
+    w.oWc1 = o; o += (64 * CIN + 3) & ~3;
+    w.oWc2 = o; o += 64 * 64;
+    w.oWc3 = o; o += 3 * 64;
+    w.total = o;
+    return w;
+}
 
 __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
                                                                const float* __restrict__ ray_d, int S, int64_t M, int IN,
                                                                DcParams p, const float* __restrict__ g_sigma,
                                                                const float* __restrict__ g_rgb, const float* __restrict__ scale_ptr,
                                                                float* __restrict__ g_feats, float* __restrict__ g_dir,
-                                                               const int64_t* __restrict__ m_dev, const int64_t* __restrict__ ridx) {
+                                                               const int64_t* __restrict__ m_dev, const int64_t* __restrict__ ridx,
+                                                               const uint4* __restrict__ pe16, float* __restrict__ ws) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
@@ -182,7 +239,13 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
     const DcTcLayout l = dc_tc_layout(IN, true);
     const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane, c16 = 16 * cg;
-    dc_tc_stage(sm, l, p, IN);
+    dc_tc_stage(sm, l, p, IN, lodw);
+    for (int i = tid; i < 3 * 2 * TCH / 16; i += DC_THREADS) {      // the three ones tiles: half(1.0) in feature 0 of every row
+        const int t = i / (2 * TCH / 16), j = i - t * (2 * TCH / 16);
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (j < TCH / 16) u.x = 0x00003C00u;
+        reinterpret_cast<uint4*>(sm + (t == 0 ? l.oOnesA : (t == 1 ? l.oOnesB : l.oOnesC)))[j] = u;
+    }
     if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 512);
     sync_to_mma();
@@ -192,23 +255,40 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
     const float* bias = reinterpret_cast<const float*>(sm + l.oBias);
     uint8_t *G3 = sm + l.oG3, *Gy = sm + l.oGy, *X = sm + l.oX, *Cin = sm + l.oCin, *Hd = sm + l.oHd, *H1 = sm + l.oH1, *H2 = sm + l.oH2;
     const uint32_t aG3 = smem_u32(G3), aGy = smem_u32(Gy), aX = smem_u32(X), aCin = smem_u32(Cin), aHd = smem_u32(Hd),
-                   aH1 = smem_u32(H1), aH2 = smem_u32(H2);
+                   aH1 = smem_u32(H1), aH2 = smem_u32(H2), aOnesA = smem_u32(sm + l.oOnesA), aOnesB = smem_u32(sm + l.oOnesB),
+                   aOnesC = smem_u32(sm + l.oOnesC);
     const uint32_t wd1 = smem_u32(sm + l.oWd1), wd2 = smem_u32(sm + l.oWd2), wc1 = smem_u32(sm + l.oWc1),
                    wc2 = smem_u32(sm + l.oWc2), wc3 = smem_u32(sm + l.oWc3);
+    float4* pf = reinterpret_cast<float4*>(sm + l.oPF);
     const float scale = scale_ptr ? __ldg(scale_ptr) : 1.f;
     const float inv_scale = 1.f / scale;
     const bool do_rgb = g_rgb != nullptr;
-    float db_d1 = 0.f, db_c1 = 0.f, db_c2 = 0.f, db_d2 = 0.f, db_c3 = 0.f;
     const int64_t ntiles = (M + 127) / 128;
+    if ((int64_t)blockIdx.x < ntiles) xpfc_issue<DC_MAXK>(pf, feats, nullptr, IN, (int64_t)blockIdx.x * 128, M);
+    cp_async_wait_all();
+    __syncthreads();
     bool first = true;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
         const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
         // ---------------- forward recompute ----------------
-        stage_x_cg(X, row, cg, DC_NCG, feats, nullptr, lodw, IN, l.nXc, mm);
+        xpfc_consume<DC_NCG, DC_MAXK>(pf, false, IN, l.INP, X, row, cg);
+        // this row's upstream gradients / view embedding: issued now, consumed several MMA phases later
+        float gs_row = 0.f, gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
+        uint4 pa = make_uint4(0u, 0u, 0u, 0u), pb = pa;
+        int64_t r = 0;
+        if (cg == 0) {
+            if (g_sigma && valid) gs_row = __ldg(g_sigma + m);
+            if (do_rgb && valid) { gr0 = __ldg(g_rgb + 3 * m); gr1 = __ldg(g_rgb + 3 * m + 1); gr2 = __ldg(g_rgb + 3 * m + 2); }
+        } else if (do_rgb && cg <= 2) {
+            r = ridx ? ridx[mm] : mm / S;
+            if (pe16) { pa = __ldg(pe16 + r * 4 + 2 * (cg - 1)); pb = __ldg(pe16 + r * 4 + 2 * (cg - 1) + 1); }
+        }
         sync_to_mma();
         if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aX, wd1, 64, 64, l.INP, false); mb.commit(); }
+        if (tile + gridDim.x < ntiles)      // every thread is past its slot reads: the next tile's inputs stream in from here
+            xpfc_issue<DC_MAXK>(pf, feats, nullptr, IN, (tile + gridDim.x) * 128, M);
         mb.wait();
         const uint32_t mask_d = epi_relu16(tl + DCB_S0 + c16, bias + c16, Hd + 2 * cg * TCH, row);
         sync_to_mma();
@@ -228,9 +308,11 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
             y0pos = y[0] > 0.f;
             if (do_rgb) { tile_store8(Cin, 0, row, y); tile_store8(Cin, 1, row, y + 8); }
         } else if (do_rgb && cg <= 2) {
-            const int64_t r = ridx ? ridx[mm] : mm / S;
-            vdir[0] = -ray_d[3 * r]; vdir[1] = -ray_d[3 * r + 1]; vdir[2] = -ray_d[3 * r + 2];
-            stage_cin_pe(Cin, row, cg, -vdir[0], -vdir[1], -vdir[2]);
+            if (pe16 && !g_dir) stage_cin_pe16(Cin, row, cg, pa, pb);
+            else {
+                vdir[0] = -ray_d[3 * r]; vdir[1] = -ray_d[3 * r + 1]; vdir[2] = -ray_d[3 * r + 2];
+                stage_cin_pe(Cin, row, cg, -vdir[0], -vdir[1], -vdir[2]);
+            }
         }
         if (do_rgb) {
             sync_to_mma();
@@ -250,37 +332,38 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
 #pragma unroll
                 for (int j = 0; j < 16; ++j) g[j] = 0.f;
                 if (valid) {
+                    const float gr[3] = {gr0, gr1, gr2};
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         const float sg = 1.f / (1.f + __expf(-(c[j] + bias[208 + j])));
-                        g[j] = g_rgb[3 * m + j] * sg * (1.f - sg) * scale;
+                        g[j] = gr[j] * sg * (1.f - sg) * scale;
                     }
                 }
-                grad16_store(g, G3, row, lane, db_c3);
+                tile_store8(G3, 0, row, g); tile_store8(G3, 1, row, g + 8);
             }
             // ---------------- color backward ----------------
             sync_to_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
-                mma16_bwd_weight(tm + DCB_DWC3, aG3, aH2, 64, !first);
+                mma16_bwd_weight(tm + DCB_DWC3, aG3, aOnesC, 80, !first);      // B = ones | H2
                 mma16_bwd_data(tm + DCB_S1, aG3, wc3, 64, 16, 16, false);
                 mb.commit();
             }
             mb.wait();
-            epi_grad16(tl + DCB_S1 + c16, mask_2, H2 + 2 * cg * TCH, row, lane, db_c2);     // G2 overwrites H2
+            epi_grad16_nb(tl + DCB_S1 + c16, mask_2, H2 + 2 * cg * TCH, row);     // G2 overwrites H2
             sync_to_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
-                mma16_bwd_weight(tm + DCB_DWC2, aH2, aH1, 64, !first);
+                mma16_bwd_weight(tm + DCB_DWC2, aH2, aH1, 80, !first);         // B = H1 | ones
                 mma16_bwd_data(tm + DCB_S0, aH2, wc2, 64, 64, 64, false);
                 mb.commit();
             }
             mb.wait();
-            epi_grad16(tl + DCB_S0 + c16, mask_1, H1 + 2 * cg * TCH, row, lane, db_c1);     // G1 overwrites H1
+            epi_grad16_nb(tl + DCB_S0 + c16, mask_1, H1 + 2 * cg * TCH, row);     // G1 overwrites H1
             sync_to_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
-                mma16_bwd_weight(tm + DCB_DWC1, aH1, aCin, 48, !first);
+                mma16_bwd_weight(tm + DCB_DWC1, aH1, aOnesB, 64, !first);      // B = ones | Cin
                 mma16_bwd_data(tm + DCB_S1, aH1, wc1, 48, 64, 64, false);
                 mb.commit();
             }
@@ -312,49 +395,76 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __re
         }
         // ---------------- density backward ----------------
         if (cg == 0) {
-            if (g_sigma && valid && y0pos) dy[0] += g_sigma[m] * scale;
+            if (y0pos) dy[0] += gs_row * scale;
             if (!valid) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) dy[i] = 0.f;
             }
-            grad16_store(dy, Gy, row, lane, db_d2);
+            tile_store8(Gy, 0, row, dy); tile_store8(Gy, 1, row, dy + 8);
         }
         sync_to_mma();
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            mma16_bwd_weight(tm + DCB_DWD2, aGy, aHd, 64, !first);
+            mma16_bwd_weight(tm + DCB_DWD2, aGy, aHd, 80, !first);             // B = Hd | ones
             mma16_bwd_data(tm + DCB_S0, aGy, wd2, 64, 16, 16, false);
             mb.commit();
         }
         mb.wait();
-        epi_grad16(tl + DCB_S0 + c16, mask_d, Hd + 2 * cg * TCH, row, lane, db_d1);           // Gd overwrites Hd
+        epi_grad16_nb(tl + DCB_S0 + c16, mask_d, Hd + 2 * cg * TCH, row);         // Gd overwrites Hd
         sync_to_mma();
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            mma16_bwd_weight(tm + DCB_DWD1, aHd, aX, l.INP, !first);
+            mma16_bwd_weight(tm + DCB_DWD1, aHd, aOnesA, 16 + l.INP, !first);   // B = ones | X
             if (g_feats) mma16_bwd_data(tm + DCB_S1, aHd, wd1, l.INP, 64, 64, false);
             mb.commit();
         }
         mb.wait();
-        if (g_feats && c16 < l.INP) store_dx16(tl + DCB_S1, g_feats + mm * IN, lodw, IN, c16, inv_scale, valid);
+        if (g_feats && c16 < l.INP) store_dx16(tl + DCB_S1, g_feats + mm * IN, nullptr, IN, c16, inv_scale, valid);   // W1 carries the LOD weights
+        cp_async_wait_all();      // own copies landed; the barrier publishes everybody's
         tc_fence_before();
         __syncthreads();
     }
     // ---------------- flush weight / bias gradients (once per CTA) ----------------
     if (!first) {
         tc_fence_after();
-        const int f1 = scatter_base(lane, 32) >> 1;   // feature (of 16) owned by this lane pair
-        const bool own = !(lane & 1);
-        if (c16 < l.INP) flush_dw16(tl + DCB_DWD1, p.gWd1, row, 64, IN, c16, inv_scale);
-        flush_dw16(tl + DCB_DWD2, p.gWd2, row, 16, 64, c16, inv_scale);
-        if (own) red_add_f32(p.gbd1 + c16 + f1, db_d1 * inv_scale);
-        if (own && cg == 0) red_add_f32(p.gbd2 + f1, db_d2 * inv_scale);
+        const bool plain = ws != nullptr;      // private partial slice + reduce kernel instead of contended atomics
+        const DcWsLayout wl = dc_ws_layout(IN);
+        float* wsb = plain ? ws + (size_t)blockIdx.x * wl.total : nullptr;
+        float *dWd1 = plain ? wsb + wl.oWd1 : p.gWd1, *dWd2 = plain ? wsb + wl.oWd2 : p.gWd2, *dWc1 = plain ? wsb + wl.oWc1 : p.gWc1,
+              *dWc2 = plain ? wsb + wl.oWc2 : p.gWc2, *dWc3 = plain ? wsb + wl.oWc3 : p.gWc3;
+        if (c16 < l.INP) {      // G^T X with X unweighted: the LOD weight of each input column applies here
+            float v[16];
+            tmem_ld16(tl + DCB_DWD1 + 16 + c16, v);
+            if (row < 64) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c16 + i < IN) {
+                        const float x = v[i] * inv_scale * (lodw ? __ldg(lodw + c16 + i) : 1.f);
+                        float* d = dWd1 + (size_t)row * IN + c16 + i;
+                        if (plain) *d = x; else red_add_f32(d, x);
+                    }
+            }
+        }
+        flush_dw16(tl + DCB_DWD2, dWd2, row, 16, 64, c16, inv_scale, plain);
         if (do_rgb) {
-            if (c16 < 48) flush_dw16(tl + DCB_DWC1, p.gWc1, row, 64, CIN, c16, inv_scale);
-            flush_dw16(tl + DCB_DWC2, p.gWc2, row, 64, 64, c16, inv_scale);
-            flush_dw16(tl + DCB_DWC3, p.gWc3, row, 3, 64, c16, inv_scale);
-            if (own) { red_add_f32(p.gbc1 + c16 + f1, db_c1 * inv_scale); red_add_f32(p.gbc2 + c16 + f1, db_c2 * inv_scale); }
-            if (own && cg == 0 && f1 < 3) red_add_f32(p.gbc3 + f1, db_c3 * inv_scale);
+            if (c16 < 48) flush_dw16(tl + DCB_DWC1 + 16, dWc1, row, 64, CIN, c16, inv_scale, plain);
+            flush_dw16(tl + DCB_DWC2, dWc2, row, 64, 64, c16, inv_scale, plain);
+            flush_dw16(tl + DCB_DWC3 + 16, dWc3, row, 3, 64, c16, inv_scale, plain);
+        }
+        if (cg == 0) {      // bias gradients: the ones-tile column of each accumulator
+            float v[16];
+            tmem_ld16(tl + DCB_DWD1, v);
+            if (row < 64) red_add_f32(p.gbd1 + row, v[0] * inv_scale);
+            tmem_ld16(tl + DCB_DWD2 + 64, v);
+            if (row < 16) red_add_f32(p.gbd2 + row, v[0] * inv_scale);
+            if (do_rgb) {
+                tmem_ld16(tl + DCB_DWC1, v);
+                if (row < 64) red_add_f32(p.gbc1 + row, v[0] * inv_scale);
+                tmem_ld16(tl + DCB_DWC2 + 64, v);
+                if (row < 64) red_add_f32(p.gbc2 + row, v[0] * inv_scale);
+                tmem_ld16(tl + DCB_DWC3, v);
+                if (row < 3) red_add_f32(p.gbc3 + row, v[0] * inv_scale);
+            }
         }
     }
     tc_fence_before();
@@ -711,7 +821,7 @@ int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray
     if (rc) return rc;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = 2 * (int64_t)tc_num_sms();
-    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb, nullptr, nullptr);
+    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb, nullptr, nullptr, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -719,7 +829,7 @@ int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray
 // device-side sample count (m_dev[0] <= M_max) and per-sample ray index: sample m uses ray_d[ridx[m]]
 int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, int hidden, int view_dim,
-                             int want_rgb, float* sigma, float* rgb, void* stream) {
+                             int want_rgb, float* sigma, float* rgb, const void* view_pe16, void* stream) {
     if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     DcParams p{};
@@ -729,7 +839,7 @@ int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float*
     if (rc) return rc;
     const int64_t tiles = (M_max + 127) / 128;
     const int64_t cap = 2 * (int64_t)tc_num_sms();
-    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx);
+    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx, reinterpret_cast<const uint4*>(view_pe16));
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -749,7 +859,7 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = tc_num_sms();
     dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, lodw, ray_d, S, M, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, nullptr, nullptr);
+        feats, lodw, ray_d, S, M, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, nullptr, nullptr, nullptr, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -757,7 +867,7 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
 int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, float* const* grads, int hidden,
                              int view_dim, const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats,
-                             float* g_dir, void* stream) {
+                             float* g_dir, const void* view_pe16, float* workspace, int64_t workspace_bytes, void* stream) {
     if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     DcParams p{};
@@ -767,8 +877,34 @@ int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float*
     if (rc) return rc;
     const int64_t tiles = (M_max + 127) / 128;
     const int64_t cap = tc_num_sms();
-    dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, lodw, ray_d, 1, M_max, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, m_dev, ridx);
+    const int nblocks = (int)(tiles < cap ? tiles : cap);
+    const DcWsLayout wl = dc_ws_layout(IN);
+    float* ws = (workspace && workspace_bytes >= (int64_t)nblocks * wl.total * 4 && !(reinterpret_cast<uintptr_t>(workspace) & 15)) ? workspace : nullptr;
+    dc_tc_bwd_kernel<<<nblocks, DC_THREADS, l.total, (cudaStream_t)stream>>>(
+        feats, lodw, ray_d, 1, M_max, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, m_dev, ridx, reinterpret_cast<const uint4*>(view_pe16), ws);
+    PAG_LAUNCH_CHECK();
+    if (ws) {
+        const bool rgb = g_rgb != nullptr;
+        WsSegs sg{5, {wl.oWd1, wl.oWd2, wl.oWc1, wl.oWc2, wl.oWc3}, {64 * IN, 16 * 64, 64 * CIN, 64 * 64, 3 * 64},
+                  {p.gWd1, p.gWd2, rgb ? p.gWc1 : nullptr, rgb ? p.gWc2 : nullptr, rgb ? p.gWc3 : nullptr}};
+        ws_reduce_kernel<<<(wl.total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, nblocks, M_max, m_dev, wl.total, sg);
+        PAG_LAUNCH_CHECK();
+    }
+    return PAG_OK;
+}
+
+// bytes of partial-gradient workspace pag_decode_dc_bwd_tc_dyn can use for M_max samples
+int pag_decode_dc_bwd_workspace(int64_t M_max, int IN, int64_t* bytes) {
+    if (!bytes) return PAG_ERR_ARG;
+    const int64_t tiles = (M_max + 127) / 128, cap = tc_num_sms();
+    *bytes = (tiles < cap ? tiles : cap) * (int64_t)dc_ws_layout(IN).total * 4;
+    return PAG_OK;
+}
+
+// per-ray view embedding image pe16[R][32] (fp16: 27 values of PE(-d), 5 zeros) for the *_dyn decoders
+int pag_view_pe16(const float* ray_d, int64_t R, void* pe16, void* stream) {
+    if (R == 0) return PAG_OK;
+    view_pe16_kernel<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ray_d, R, reinterpret_cast<__half*>(pe16));
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

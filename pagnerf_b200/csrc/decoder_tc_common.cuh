@@ -182,6 +182,42 @@ __device__ __forceinline__ void epi_grad16(uint32_t taddr, uint32_t mask, uint8_
     for (int i = 0; i < 16; ++i) v[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
     grad16_store(v, tile2, row, lane, dbacc);
 }
+// 16 masked gradient columns -> 2 tile chunks (bias gradient taken by the tensor core, see the ones tiles)
+__device__ __forceinline__ void epi_grad16_nb(uint32_t taddr, uint32_t mask, uint8_t* tile2, int row) {
+    float v[16];
+    tmem_ld16(taddr, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
+    tile_store8(tile2, 0, row, v);
+    tile_store8(tile2, 1, row, v + 8);
+}
+// ---- per-CTA partial weight gradients -> gradients -------------------------------------------------------------------
+// 148 CTAs accumulating the same ~100 KB of weight gradients with red.add serialise in the L2 atomic units (measured: 8 % of
+// the fused backward).  With a workspace every CTA stores its partial sums privately and this kernel adds the slices of the
+// CTAs that had at least one tile to the gradient tensors.
+struct WsSegs { int n; int off[6]; int len[6]; float* dst[6]; };
+static __global__ void __launch_bounds__(256) ws_reduce_kernel(const float* __restrict__ ws, int nblocks, int64_t M, const int64_t* __restrict__ m_dev,
+                                                               int total, WsSegs segs) {
+    if (m_dev) M = min(M, __ldg(m_dev));
+    const int64_t ntiles = (M + 127) / 128;
+    const int nact = (int)(ntiles < nblocks ? ntiles : nblocks);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float* dst = nullptr;
+#pragma unroll
+    for (int s = 0; s < 6; ++s)
+        if (s < segs.n && i >= segs.off[s] && i < segs.off[s] + segs.len[s] && segs.dst[s]) dst = segs.dst[s] + (i - segs.off[s]);
+    if (!dst) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = 0;
+    for (; b + 4 <= nact; b += 4) {
+        a0 += ws[(size_t)b * total + i]; a1 += ws[(size_t)(b + 1) * total + i];
+        a2 += ws[(size_t)(b + 2) * total + i]; a3 += ws[(size_t)(b + 3) * total + i];
+    }
+    for (; b < nact; ++b) a0 += ws[(size_t)b * total + i];
+    *dst += (a0 + a1) + (a2 + a3);
+}
+
 // flush columns [c0, c0+16) of a dW accumulator row.  plain: the destination is this CTA's private partial buffer
 // (ordinary 16-byte stores, summed over CTAs by a reduce kernel) instead of the shared gradient (red.add).
 __device__ __forceinline__ void flush_dw16(uint32_t taddr, float* __restrict__ gW, int row, int OUT, int IN, int c0, float inv_scale,

@@ -339,32 +339,6 @@ __host__ __device__ inline PanWsLayout pan_ws_layout(int IN, int Cs, int Ci) {
     w.total = o;
     return w;
 }
-// gW += sum over the CTAs that had at least one tile of their partial slices
-__global__ void __launch_bounds__(256) pan_ws_reduce_kernel(const float* __restrict__ ws, int nblocks, int64_t M, const int64_t* __restrict__ m_dev,
-                                                            int IN, int Cs, int Ci, PanParams p, int do_sem, int do_inst) {
-    if (m_dev) M = min(M, __ldg(m_dev));
-    const int64_t ntiles = (M + 127) / 128;
-    const int nact = (int)(ntiles < nblocks ? ntiles : nblocks);
-    const PanWsLayout wl = pan_ws_layout(IN, Cs, Ci);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= wl.total) return;
-    float* dst;
-    if (i < wl.oWs2) dst = do_sem ? p.gWs1 + i : nullptr;
-    else if (i < wl.oWi1) dst = (do_sem && i - wl.oWs2 < Cs * 64) ? p.gWs2 + (i - wl.oWs2) : nullptr;
-    else if (i < wl.oWi2) dst = do_inst ? p.gWi1 + (i - wl.oWi1) : nullptr;
-    else if (i < wl.oWi3) dst = do_inst ? p.gWi2 + (i - wl.oWi2) : nullptr;
-    else dst = (do_inst && i - wl.oWi3 < Ci * 64) ? p.gWi3 + (i - wl.oWi3) : nullptr;
-    if (!dst) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int b = 0;
-    for (; b + 4 <= nact; b += 4) {
-        a0 += ws[(size_t)b * wl.total + i]; a1 += ws[(size_t)(b + 1) * wl.total + i];
-        a2 += ws[(size_t)(b + 2) * wl.total + i]; a3 += ws[(size_t)(b + 3) * wl.total + i];
-    }
-    for (; b < nact; ++b) a0 += ws[(size_t)b * wl.total + i];
-    *dst += (a0 + a1) + (a2 + a3);
-}
-
 // rows [row0, row0 + rows) of a joint weight image with OUTP output rows; W == nullptr stages zeros
 __device__ __forceinline__ void stage_w16_part(__half* img, const float* __restrict__ W, int OUT, int IN, int rows, int row0, int OUTP, int INP,
                                                const float* __restrict__ colscale) {
@@ -387,16 +361,6 @@ __device__ __forceinline__ void flush_dw_T(uint32_t taddr, float* __restrict__ g
             if (j < C) red_add_f32(gW + (size_t)j * K + k, v[j] * inv_scale);
     }
 }
-// 16 masked gradient columns -> 2 tile chunks (bias gradient taken elsewhere)
-__device__ __forceinline__ void epi_grad16_nb(uint32_t taddr, uint32_t mask, uint8_t* tile2, int row) {
-    float v[16];
-    tmem_ld16(taddr, v);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = ((mask >> i) & 1u) ? v[i] : 0.f;
-    tile_store8(tile2, 0, row, v);
-    tile_store8(tile2, 1, row, v + 8);
-}
-
 // 16 consecutive (pre-scaled) per-ray output gradients: from the tile's fp16 cache when the ray is one of the first
 // PCB_NGC of the tile, else straight from global memory
 __device__ __forceinline__ void load_g16(const __half* __restrict__ gc_row, const float* __restrict__ grow, int c0, int C, bool vec4,
@@ -830,8 +794,10 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
         feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev, ws);
     PAG_LAUNCH_CHECK();
     if (ws) {
-        pan_ws_reduce_kernel<<<(wl.total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, nblocks, M, m_dev, IN, Cs, Ci, p,
-                                                                                         (Cs > 0 && g_sem) ? 1 : 0, (Ci > 0 && g_inst) ? 1 : 0);
+        const bool ds = Cs > 0 && g_sem, di = Ci > 0 && g_inst;
+        WsSegs sg{5, {wl.oWs1, wl.oWs2, wl.oWi1, wl.oWi2, wl.oWi3}, {64 * IN, Cs * 64, 64 * IN, 64 * 64, Ci * 64},
+                  {ds ? p.gWs1 : nullptr, ds ? p.gWs2 : nullptr, di ? p.gWi1 : nullptr, di ? p.gWi2 : nullptr, di ? p.gWi3 : nullptr}};
+        ws_reduce_kernel<<<(wl.total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, nblocks, M, m_dev, wl.total, sg);
         PAG_LAUNCH_CHECK();
     }
     return PAG_OK;

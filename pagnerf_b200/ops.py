@@ -415,8 +415,12 @@ def composite(sigma, deltas, depths, rgb, sem, inst, offsets, bg_white=True):
 
 
 def _pan_bwd_workspace(M, IN, Cs, Ci, device):
-    """(pointer, bytes) of the partial weight-gradient workspace of pag_pan_composite_bwd_tc (torch-allocated: graph safe)."""
-    nbytes = query_i64("pag_pan_composite_bwd_workspace", int(M), int(IN), int(Cs), int(Ci))
+    return _ws("pag_pan_composite_bwd_workspace", device, M, IN, Cs, Ci)
+
+
+def _ws(query, device, *args):
+    """(pointer, bytes) of the partial weight-gradient workspace a backward entry point can use (torch-allocated: graph safe)."""
+    nbytes = query_i64(query, *[int(a) for a in args])
     if nbytes == 0:
         return None, 0
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=device)   # the caching allocator is stream ordered: safe to drop after enqueue
@@ -624,8 +628,13 @@ class FusedTraceFn(Function):
                 call("pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan), ptr(dfeats))
         sigma = torch.empty(Mmax, dtype=f32, device=dev)
         rgb = torch.empty(Mmax, 3, dtype=f32, device=dev) if want_rgb else None
+        pe16 = None
+        if want_rgb:      # per-ray fp16 view embedding: the decoders copy it instead of 24 sin/cos per sample
+            pe16 = torch.empty(N, 32, dtype=torch.float16, device=dev)
+            call("pag_view_pe16", ptr(d), N, ptr(pe16))
+        ctx.pe16 = pe16
         call("pag_decode_dc_fwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
-             HIDDEN, VIEW_DIM, int(want_rgb), ptr(sigma), ptr(rgb))
+             HIDDEN, VIEW_DIM, int(want_rgb), ptr(sigma), ptr(rgb), ptr(pe16))
         wgt = torch.empty(Mmax, dtype=f32, device=dev)
         T = torch.empty(Mmax, dtype=f32, device=dev)
         alpha = torch.empty(N, 1, dtype=f32, device=dev)
@@ -719,7 +728,8 @@ class FusedTraceFn(Function):
             g_feats = torch.empty(Mmax, IN, dtype=f32, device=dev)
             g_dir = torch.empty(Mmax, 3, dtype=f32, device=dev) if ctx.needs_input_grad[1] else None
             call("pag_decode_dc_bwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
-                 ptr_array(grads[:10]), HIDDEN, VIEW_DIM, ptr(g_sigma), ptr(g_rgb_s), ptr(scale), ptr(g_feats), ptr(g_dir))
+                 ptr_array(grads[:10]), HIDDEN, VIEW_DIM, ptr(g_sigma), ptr(g_rgb_s), ptr(scale), ptr(g_feats), ptr(g_dir),
+                 ptr(ctx.pe16), *_ws("pag_decode_dc_bwd_workspace", dev, Mmax, IN))
             g_pos = torch.empty(Mmax, 3, dtype=f32, device=dev) if need_rays else None
             call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
                  ptr(g_feats), ptr(g_table), ptr(g_pos), int(n_agg))
