@@ -45,9 +45,10 @@ __device__ __forceinline__ void red_add_f32(float* addr, float a) {
 }
 
 // warp-aggregated scatter of (gx,gy) into tl[idx]: lanes with equal idx are summed, the leader issues one red
+// todo0: lanes that have something to add (lanes with an exactly-zero gradient take part in the shuffles only)
 __device__ __forceinline__ void scatter_aggregated(float* __restrict__ tl, uint32_t idx, float gx, float gy,
-                                                   unsigned active) {
-    unsigned todo = active;
+                                                   unsigned active, unsigned todo0) {
+    unsigned todo = todo0;
     const int lane = threadIdx.x & 31;
     while (todo) {
         const int leader = __ffs(todo) - 1;

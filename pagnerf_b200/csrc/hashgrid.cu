@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) hash_bwd_kernel(const float* __restrict__
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float w = corner_weight(c, k);
-                scatter_aggregated(gl, c.idx[k], g.x * w, g.y * w, 0xffffffffu);
+                scatter_aggregated(gl, c.idx[k], g.x * w, g.y * w, 0xffffffffu, 0xffffffffu);
             }
         } else if (valid) {
 #pragma unroll

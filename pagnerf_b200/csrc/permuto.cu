@@ -152,6 +152,17 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
         p0 = __half2float(__float2half_rn(p0)); p1 = __half2float(__float2half_rn(p1)); p2 = __half2float(__float2half_rn(p2));
     }
     const float2* grow = reinterpret_cast<const float2*>(gout + mm * (int64_t)(2 * L));
+    // Samples the integrator gave zero weight (sigma clamped to 0, or behind an opaque surface with an underflowed
+    // transmittance) arrive with an exactly-zero gradient row: adding zeros is skipped -- a whole warp of them costs one
+    // pass over its rows, a single one costs no atomics.
+    bool rownz = false;
+    if (valid) {
+        for (int l = 0; l < L; ++l) { const float2 g = __ldg(grow + l); rownz |= (g.x != 0.f) | (g.y != 0.f); }
+    }
+    if (!__any_sync(0xffffffffu, rownz)) {
+        if (POS_GRAD && valid) { gpos[3 * m] = 0.f; gpos[3 * m + 1] = 0.f; gpos[3 * m + 2] = 0.f; }
+        return;
+    }
     float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
     for (int l = 0; l < L; ++l) {
         PermutoVertex v;
@@ -160,12 +171,14 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
         float2 g = __ldg(grow + l);
         g.x = valid ? g.x * w : 0.f;
         g.y = valid ? g.y * w : 0.f;
+        const bool nz = rownz && ((g.x != 0.f) | (g.y != 0.f));
         float* gl = gtable + (size_t)l * cap * 2;
         if (l < n_agg_levels) {
+            const unsigned todo0 = __ballot_sync(0xffffffffu, nz);
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                scatter_aggregated(gl, v.idx[r], g.x * v.bary[r], g.y * v.bary[r], 0xffffffffu);
-        } else if (valid) {
+                scatter_aggregated(gl, v.idx[r], g.x * v.bary[r], g.y * v.bary[r], 0xffffffffu, todo0);
+        } else if (nz) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) red_add_f32x2(gl + 2 * (size_t)v.idx[r], g.x * v.bary[r], g.y * v.bary[r]);
         }
