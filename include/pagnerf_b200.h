@@ -29,6 +29,15 @@ int pag_octree_query(const uint8_t* octree, const int32_t* prefix, const float* 
 
 /* exclusive scan of int32 counts; out has N+1 entries, out[N] = total. */
 int pag_exclusive_scan_i32(const int32_t* in, int64_t N, int64_t* out, void* stream);
+/* ---- live-sample compaction (training hot path; no reference counterpart: the reference decodes every packed sample) ----
+ * Samples with density exactly 0 have integration weight 0 and receive gradient 0, so removing them from the packed list
+ * before the remaining decoders / the delta-grid encode / the backward is exact.  offsets i64[N+1] describes the packed list
+ * (ray r owns [offsets[r], offsets[r+1])); pag_compact_count writes counts i32[N] and the compacted offsets_c i64[N+1]
+ * (offsets_c[N] = number of live samples, stays on the device); pag_compact_emit copies the survivors in order. */
+int pag_compact_count(const float* sigma, const int64_t* offsets, int64_t N, int32_t* counts, int64_t* offsets_c, void* stream);
+int pag_compact_emit(const float* sigma, const int64_t* offsets, const int64_t* offsets_c, int64_t N, const float* samples,
+                     const float* depths, const float* deltas, const float* feats, int F, int64_t* ridx_c, float* samples_c,
+                     float* depths_c, float* deltas_c, float* feats_c, void* stream);
 
 /* 'ray' raymarch, pass 1 (tracers/panoptic_packed_rf_tracer.py:85 with raymarch_type='ray'):
  * S jittered steps per ray, octree lookup per step.  Writes pidx_tmp[N*S], counts[N], offsets[N+1].

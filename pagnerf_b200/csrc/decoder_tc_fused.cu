@@ -380,7 +380,9 @@ __device__ __forceinline__ void load_g16(const __half* __restrict__ gc_row, cons
             if (vec4) t = (c0 + i < C) ? __ldg(reinterpret_cast<const float4*>(grow + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
             else t = make_float4(c0 + i < C ? __ldg(grow + c0 + i) : 0.f, c0 + i + 1 < C ? __ldg(grow + c0 + i + 1) : 0.f,
                                  c0 + i + 2 < C ? __ldg(grow + c0 + i + 2) : 0.f, c0 + i + 3 < C ? __ldg(grow + c0 + i + 3) : 0.f);
-            g[i] = t.x * scale; g[i + 1] = t.y * scale; g[i + 2] = t.z * scale; g[i + 3] = t.w * scale;
+            // same fp16 rounding as the cached rows: the result must not depend on which rays of a tile were cached
+            g[i] = __half2float(__float2half_rn(t.x * scale)); g[i + 1] = __half2float(__float2half_rn(t.y * scale));
+            g[i + 2] = __half2float(__float2half_rn(t.z * scale)); g[i + 3] = __half2float(__float2half_rn(t.w * scale));
         }
     }
 }

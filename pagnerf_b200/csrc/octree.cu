@@ -81,6 +81,79 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// live-sample compaction of a packed sample list (training hot path)
+// A sample whose density came out exactly 0 (ReLU-clamped) has integration weight T * (1 - exp(-0 * delta)) = 0 and
+// leaves the transmittance unchanged: it contributes an exact 0 to every composited output and receives an exact 0
+// gradient (ReLU' = 0, everything else is scaled by the weight).  Dropping those samples from the packed list before
+// the colour / panoptic decoders, the delta-grid encode and the whole backward changes no result bit.
+// Per ray (one warp): count the live samples, scan the counts over rays, then copy the survivors in order.
+// ---------------------------------------------------------------------------------------------
+__global__ void compact_count_kernel(const float* __restrict__ sigma, const int64_t* __restrict__ offsets, int64_t N,
+                                     int32_t* __restrict__ counts) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= N) return;
+    const int64_t lo = offsets[r], hi = offsets[r + 1];
+    int cnt = 0;
+    for (int64_t s0 = lo; s0 < hi; s0 += 32) {
+        const int64_t s = s0 + lane;
+        const bool live = s < hi && __ldg(sigma + s) > 0.f;
+        cnt += __popc(__ballot_sync(0xffffffffu, live));
+    }
+    if (lane == 0) counts[r] = cnt;
+}
+__global__ void compact_emit_kernel(const float* __restrict__ sigma, const int64_t* __restrict__ offsets,
+                                    const int64_t* __restrict__ offsets_c, int64_t N, const float* __restrict__ samples,
+                                    const float* __restrict__ depths, const float* __restrict__ deltas,
+                                    const float* __restrict__ feats, int F, int64_t* __restrict__ ridx_c,
+                                    float* __restrict__ samples_c, float* __restrict__ depths_c, float* __restrict__ deltas_c,
+                                    float* __restrict__ feats_c) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= N) return;
+    const int64_t lo = offsets[r], hi = offsets[r + 1];
+    int64_t base = offsets_c[r];
+    const int nq = F >> 2;                       // float4 quads per feature row (F % 4 == 0)
+    for (int64_t s0 = lo; s0 < hi; s0 += 32) {
+        const int64_t s = s0 + lane;
+        const bool live = s < hi && __ldg(sigma + s) > 0.f;
+        const unsigned b = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const int64_t dst = base + __popc(b & ((1u << lane) - 1u));
+            ridx_c[dst] = r;
+            samples_c[3 * dst] = samples[3 * s]; samples_c[3 * dst + 1] = samples[3 * s + 1]; samples_c[3 * dst + 2] = samples[3 * s + 2];
+            depths_c[dst] = depths[s];
+            deltas_c[dst] = deltas[s];
+        }
+        // feature rows: the warp copies one surviving row per step (two when a row needs <= 16 lanes), coalesced
+        unsigned todo = b;
+        int k = 0;
+        if (nq <= 16) {
+            const int half = lane >> 4, ql = lane & 15;
+            while (todo) {
+                const int b0 = __ffs(todo) - 1;
+                todo &= todo - 1;
+                int b1 = -1;
+                if (todo) { b1 = __ffs(todo) - 1; todo &= todo - 1; }
+                const int bit = half ? b1 : b0;
+                if (bit >= 0 && ql < nq)
+                    reinterpret_cast<float4*>(feats_c + (base + k + half) * F)[ql] = __ldg(reinterpret_cast<const float4*>(feats + (s0 + bit) * F) + ql);
+                k += 2;
+            }
+        } else {
+            while (todo) {
+                const int bit = __ffs(todo) - 1;
+                todo &= todo - 1;
+                for (int ql = lane; ql < nq; ql += 32)
+                    reinterpret_cast<float4*>(feats_c + (base + k) * F)[ql] = __ldg(reinterpret_cast<const float4*>(feats + (s0 + bit) * F) + ql);
+                ++k;
+            }
+        }
+        base += __popc(b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 'ray' mode
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ray_step_depth(int64_t ray, int i, int S, const float* __restrict__ lin,
@@ -309,6 +382,28 @@ int pag_octree_query(const uint8_t* octree, const int32_t* prefix, const float* 
     if (level < 0 || level > PAG_MAX_LEVEL) return PAG_ERR_ARG;
     if (P == 0) return PAG_OK;
     octree_query_kernel<<<pag_grid(P, 256), 256, 0, (cudaStream_t)stream>>>(octree, prefix, coords, P, level, pidx);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// offsets i64[N+1] of the packed list (offsets[N] = M); offsets_c i64[N+1] receives the compacted list's (offsets_c[N] = live count)
+int pag_compact_count(const float* sigma, const int64_t* offsets, int64_t N, int32_t* counts, int64_t* offsets_c, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 0) {
+        compact_count_kernel<<<pag_grid(N * 32, 256), 256, 0, st>>>(sigma, offsets, N, counts);
+        PAG_LAUNCH_CHECK();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, offsets_c);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_compact_emit(const float* sigma, const int64_t* offsets, const int64_t* offsets_c, int64_t N, const float* samples,
+                     const float* depths, const float* deltas, const float* feats, int F, int64_t* ridx_c, float* samples_c,
+                     float* depths_c, float* deltas_c, float* feats_c, void* stream) {
+    if (F <= 0 || (F & 3)) return PAG_ERR_ARG;
+    if (N == 0) return PAG_OK;
+    compact_emit_kernel<<<pag_grid(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(sigma, offsets, offsets_c, N, samples, depths, deltas,
+                                                                                feats, F, ridx_c, samples_c, depths_c, deltas_c, feats_c);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

@@ -566,6 +566,13 @@ def _allreduce_async(t):
     return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=_GRAD_SYNC["group"], async_op=True)
 
 
+# FusedTraceFn can drop zero-density samples after a density-only pass (exact; see pag_compact_count).  It pays when a
+# sizeable share of the packed samples is empty space (ReLU-clamped sigma == 0) -- typical of a trained scene; on a
+# freshly initialised field (bench.py's synthetic weights: every sample has sigma > 0) the extra pass is pure overhead
+# (+0.12 ms on 392 k samples), so it is opt-in: cfg['compact'] / ops.COMPACT_LIVE.
+COMPACT_LIVE = False
+
+
 class FusedTraceFn(Function):
     """PanopticPackedRFTracer.trace for ('ray' marching, permutohedral grids, tensor-core decoders) as ONE autograd
     node: ~10 kernel launches forward / ~10 backward, no host synchronisation (the packed-sample count stays on the
@@ -613,6 +620,26 @@ class FusedTraceFn(Function):
         want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
         Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
         src = cfg['pan_src'] if (Cs or Ci) else 'none'
+        m_all = m_dev
+        if cfg.get('compact', COMPACT_LIVE):
+            # density-only pass over every packed sample, then drop the ones with sigma == 0 (weight 0, gradient 0: exact)
+            # from the list; everything below -- colour / panoptic decoders, delta-grid encode, the whole backward -- runs on
+            # the survivors.  The list stays ray-sorted; offsets_c / its last entry replace offsets / the sample count.
+            sigma0 = torch.empty(Mmax, dtype=f32, device=dev)
+            call("pag_decode_dc_fwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
+                 HIDDEN, VIEW_DIM, 0, ptr(sigma0), None, None)
+            offsets_c = torch.empty(N + 1, dtype=i64, device=dev)
+            call("pag_compact_count", ptr(sigma0), ptr(offsets), N, ptr(counts), ptr(offsets_c))
+            ridx_c = torch.empty(Mmax, dtype=i64, device=dev)
+            samples_c = torch.empty(Mmax, 3, dtype=f32, device=dev)
+            depths_c = torch.empty(Mmax, dtype=f32, device=dev)
+            deltas_c = torch.empty(Mmax, dtype=f32, device=dev)
+            feats_c = torch.empty(Mmax, IN, dtype=f32, device=dev)
+            call("pag_compact_emit", ptr(sigma0), ptr(offsets), ptr(offsets_c), N, ptr(samples), ptr(depths), ptr(deltas), ptr(feats), IN,
+                 ptr(ridx_c), ptr(samples_c), ptr(depths_c), ptr(deltas_c), ptr(feats_c))
+            offsets, ridx, samples, depths, deltas, feats = offsets_c, ridx_c, samples_c, depths_c, deltas_c, feats_c
+            m_dev = offsets[N:]
+        FusedTraceFn.last_live_dev = m_dev
         dfeats = dtb = None
         main = torch.cuda.current_stream()
         side, ev_side = None, None
@@ -662,8 +689,8 @@ class FusedTraceFn(Function):
         ctx.save_for_backward(o, d, offsets, ridx, samples, depths, deltas, feats, dfeats, sigma, rgb, wgt, T, alpha, rgbsum,
                               tb, dtb, lodw, *w)
         ctx.mark_non_differentiable(hit)
-        ctx.last_m_dev = m_dev
-        return alpha, hit, rgb_o, dep_o, sem_o, inst_o, m_dev
+        ctx.last_m_dev = m_all
+        return alpha, hit, rgb_o, dep_o, sem_o, inst_o, m_all
 
     @staticmethod
     @once_differentiable

@@ -613,3 +613,51 @@ def test_fused_trace_ragged_sizes_vs_stepwise(cuda_lib, N):
         outs.append({c: getattr(rb, c).detach() for c in chans + ['alpha']})
     for c in chans + ['alpha']:
         assert_close(outs[0][c], outs[1][c], rtol=1e-3, atol_scale=1e-3, msg=c)
+
+
+def test_fused_trace_live_compaction_is_exact(cuda_lib):
+    """Dropping the zero-density samples after the density pass (ops.COMPACT_LIVE) must not change outputs or gradients."""
+    from pagnerf_b200 import ops
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_ray")
+    N = 300
+    gen = torch.Generator().manual_seed(7)
+    o = torch.stack([torch.rand(N, generator=gen) * 1.2 - 0.6, torch.rand(N, generator=gen) * 1.2 - 0.6, torch.full((N,), 0.9)], 1)
+    tgt = torch.stack([torch.rand(N, generator=gen) * 1.8 - 0.9, torch.rand(N, generator=gen) * 1.8 - 0.9, -torch.rand(N, generator=gen) * 0.9], 1)
+    d = torch.nn.functional.normalize(tgt - o, dim=-1)
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+
+    def run(compact, shift):
+        ops.COMPACT_LIVE = compact
+        nef = build_cuda_nef(g, DEV)
+        nef.decoder_precision = 'fp16'
+        with torch.no_grad():      # density pre-activation without its +1 bias: a share of the samples is clamped to 0
+            nef.decoder_density.lout.bias[0] = shift
+            nef.decoder_density.lout.weight[0] *= 8.0
+        tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=24, bg_color='black')
+        rb = tracer(nef, channels=chans, rays=Rays(origins=o.to(DEV), dirs=d.to(DEV), dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+        loss = sum((getattr(rb, c).float() ** 2).sum() for c in chans) + rb.alpha.sum()
+        loss.backward()
+        return ({c: getattr(rb, c).detach() for c in chans + ['alpha']},
+                {n: p.grad.detach().clone() for n, p in nef.named_parameters() if p.grad is not None},
+                int(ops.FusedTraceFn.last_live_dev.item()))
+
+    try:
+        shift, m1 = None, None
+        for cand in (0.0, 0.05, -0.05, 0.2, -0.2, 0.5, -0.5):
+            _, _, total = run(False, cand)
+            o1, g1, m1 = run(True, cand)
+            if 0.15 * total < m1 < 0.85 * total:
+                shift = cand
+                break
+        assert shift is not None, "no density-bias shift gave a mix of live and dead samples"
+        o0, g0, m0 = run(False, shift)
+    finally:
+        ops.COMPACT_LIVE = False
+    assert 0 < m1 < m0
+    for c in chans + ['alpha']:
+        assert_close(o1[c], o0[c], rtol=1e-5, atol_scale=1e-6, msg=c)
+    assert set(g0) == set(g1)
+    for n in g0:
+        assert_close(g1[n], g0[n], rtol=1e-4, atol_scale=2e-5, msg=n)   # summation order (atomics, tile grouping) differs
