@@ -224,7 +224,7 @@ __host__ __device__ inline DcWsLayout dc_ws_layout(int IN) {
     return w;
 }
 
-__global__ void __launch_bounds__(DC_THREADS) dc_tc_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
+__global__ void __maxnreg__(96) dc_tc_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
                                                                const float* __restrict__ ray_d, int S, int64_t M, int IN,
                                                                DcParams p, const float* __restrict__ g_sigma,
                                                                const float* __restrict__ g_rgb, const float* __restrict__ scale_ptr,
