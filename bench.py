@@ -462,6 +462,30 @@ def main():
         roof["peak_source"] = how
         roof["share_of_step"] = top[1]["ms_per_step"] / ms
         roof["samples_per_launch"] = n_samples
+    # ---- encoder vs the memory system (BASELINE metric "encoder GB/s vs peak") -------------------------------
+    encoder = None
+    enc = per_kernel.get("pag_permuto_fwd_dyn")
+    if enc and n_all:
+        table = wl.nef.grid.embedder.lattice_values.detach()
+        entries = table.numel() // 2
+        sink = torch.empty(n_all, device=device)
+        for _ in range(3):
+            _lib.call("pag_gather_probe", _lib.ptr(table), entries, n_all, 96, _lib.ptr(sink))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(10):
+            _lib.call("pag_gather_probe", _lib.ptr(table), entries, n_all, 96, _lib.ptr(sink))
+        g1.record()
+        sync()
+        probe_gbs = n_all * 96 * 8 / (g0.elapsed_time(g1) / 10 * 1e-3) / 1e9
+        t_enc = enc["ms_per_launch"] * 1e-3
+        n_enc = (n_all + n_live) / 2          # two launches per step: colour grid (all samples) and delta grid (live samples)
+        encoder = {"kernel": "pag_permuto_fwd_dyn", "ms_per_launch": round(enc["ms_per_launch"], 4), "samples_per_launch": n_enc,
+                   "algorithmic_GBps": 972 * n_enc / t_enc / 1e9, "hbm_peak_GBps": hbm, "frac_of_hbm_peak": 972 * n_enc / t_enc / 1e9 / hbm,
+                   "vertex_gather_GBps": 768 * n_enc / t_enc / 1e9, "achievable_gather_GBps": probe_gbs,
+                   "frac_of_achievable_gather": 768 * n_enc / t_enc / 1e9 / probe_gbs,
+                   "note": "972 B/sample algorithmic (12 pos + 768 vertex reads + 192 out); achievable = pag_gather_probe: uniformly "
+                           "random 8-byte loads, 4 in flight per thread, from the same 50 MB table (32-byte sectors: 4x the bytes move)"}
     cpu = None
     if not args.no_cpu_baseline:
         v, dt = time_cpu_reference(args.cpu_sample_rays, 3, 1)
@@ -482,7 +506,7 @@ def main():
                              kernel_breakdown="per-entry-point CUDA events over %d eager steps of the same workload" % ksteps),
               "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": wl.h2d_bytes(),
                       "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
-              "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+              "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roof, "encoder": encoder, "cpu_baseline": cpu,
               "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
     print(json.dumps(result))
     if world > 1:

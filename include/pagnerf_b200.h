@@ -198,6 +198,10 @@ int pag_expint_fwd(const float* tau, const int64_t* offsets, int64_t R, float* w
 int pag_expint_bwd(const float* gw, const float* w, const float* T, const int64_t* offsets, int64_t R, float* gtau,
                    void* stream);
 
+/* ---- achievable-gather-bandwidth probe (bench.py: denominator of the encoder's roofline fraction) ----
+ * threads x loads_per_thread (multiple of 4) uniformly random 8-byte loads from table[entries] float2; sink f32[threads]. */
+int pag_gather_probe(const float* table, int64_t entries, int64_t threads, int loads_per_thread, float* sink, void* stream);
+
 /* ---- tcgen05 building-block probe (tests only): one 128-row tile through the tensor-core operand images ---- */
 int pag_tc_gemm_test(int mode, const float* A, const float* B, float* D, int N, int K, int FA, int reps, void* stream);
 int pag_tc_gemm_test16(int mode, const float* A, const float* B, float* D, int N, int K, int FA, int reps, void* stream);

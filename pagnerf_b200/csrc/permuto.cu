@@ -209,6 +209,24 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
     if (POS_GRAD && valid) { gpos[3 * m] = gp0; gpos[3 * m + 1] = gp1; gpos[3 * m + 2] = gp2; }
 }
 
+// uniformly random 8-byte gathers (see pag_gather_probe)
+__global__ void __launch_bounds__(128) gather_probe_kernel(const float* __restrict__ table, uint32_t entries, int64_t threads,
+                                                           int loads_per_thread, float* __restrict__ sink) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= threads) return;
+    uint32_t state = (uint32_t)t * 2654435761u + 12345u;
+    float acc = 0.f;
+    for (int i = 0; i < loads_per_thread; i += 4) {
+        const uint32_t i0 = pag_lowbias32(state) % entries, i1 = pag_lowbias32(state + 1) % entries,
+                       i2 = pag_lowbias32(state + 2) % entries, i3 = pag_lowbias32(state + 3) % entries;
+        state += 4;
+        const float2 a = ldg2(table + 2 * (size_t)i0), b = ldg2(table + 2 * (size_t)i1), c = ldg2(table + 2 * (size_t)i2),
+                     d = ldg2(table + 2 * (size_t)i3);
+        acc += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+    }
+    sink[t] = acc;
+}
+
 extern "C" {
 
 // forward: out[M, 2L] (level-major, feature-minor)
@@ -286,6 +304,17 @@ int pag_permuto_indices(const float* pos, int64_t M, int64_t capacity, int L, co
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
     permuto_indices_kernel<<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(pos, M, cap, mask, L, scale_factor, shift,
                                                                               idx, rank, bary);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// ---- achievable-gather-bandwidth probe (the denominator of the encoder's roofline fraction) ----------------
+// `threads` threads each issue `loads_per_thread` uniformly random 8-byte loads (4 independent loads in flight per
+// iteration, like the 4 simplex vertices of one lattice level) from a table of `entries` float2 -- the same access shape as
+// the encoder's vertex reads without any of its arithmetic.  sink receives one float per thread so the loads stay live.
+int pag_gather_probe(const float* table, int64_t entries, int64_t threads, int loads_per_thread, float* sink, void* stream) {
+    if (entries <= 0 || entries > 0xFFFFFFFFll || threads <= 0 || loads_per_thread <= 0 || (loads_per_thread & 3)) return PAG_ERR_ARG;
+    gather_probe_kernel<<<pag_grid(threads, 128), 128, 0, (cudaStream_t)stream>>>(table, (uint32_t)entries, threads, loads_per_thread, sink);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
