@@ -30,7 +30,7 @@
 
 struct DcTcLayout {  // byte offsets inside dynamic smem
     int INP, nXc;
-    int oG3, oGy, oOnesA, oX, oHd, oOnesB, oCin, oH1, oOnesC, oH2, oWd1, oWd2, oWc1, oWc2, oWc3, oBias, oPF, total;
+    int oG3, oGy, oOnesA, oX, oHd, oOnesB, oCin, oH1, oOnesC, oH2, oWd1, oWd2, oWc1, oWc2, oWc3, oBias, oPF, oDX, total;
 };
 // Backward tile order: G3 Gy | onesA X | Hd onesB Cin | H1 onesC H2.  Each constant "ones" tile (feature 0 = 1) sits next
 // to the B operands of two weight-gradient chains, which therefore also produce the bias gradients:
@@ -59,6 +59,7 @@ __host__ __device__ inline DcTcLayout dc_tc_layout(int IN, bool bwd) {
     if (bwd && o < l.oH2 + 16 * TCH) o = l.oH2 + 16 * TCH;  // MN-major A operands read 16 chunks from their base
     o = (o + 15) & ~15;
     l.oPF = o; o += bwd ? 128 * (IN >> 2) * 16 : 0;          // cp.async slots of the next tile's inputs
+    l.oDX = o; o += bwd ? 128 * (IN + 4) * 4 : 0;            // dX tile staging (see dx_stage16)
     l.total = o;
     return l;
 }
@@ -268,10 +269,13 @@ __global__ void __maxnreg__(96) dc_tc_bwd_kernel(const float* __restrict__ feats
     cp_async_wait_all();
     __syncthreads();
     bool first = true;
+    float* dxs = reinterpret_cast<float*>(sm + l.oDX);
+    int64_t dx_tile = -1;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
         const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
+        if (g_feats && dx_tile >= 0) dx_copy_out(dxs, g_feats, IN, dx_tile * 128, M);      // previous tile's dX
         // ---------------- forward recompute ----------------
         xpfc_consume<DC_NCG, DC_MAXK>(pf, false, IN, l.INP, X, row, cg);
         // this row's upstream gradients / view embedding: issued now, consumed several MMA phases later
@@ -419,11 +423,13 @@ __global__ void __maxnreg__(96) dc_tc_bwd_kernel(const float* __restrict__ feats
             mb.commit();
         }
         mb.wait();
-        if (g_feats && c16 < l.INP) store_dx16(tl + DCB_S1, g_feats + mm * IN, nullptr, IN, c16, inv_scale, valid);   // W1 carries the LOD weights
+        if (g_feats && c16 < l.INP) dx_stage16(tl + DCB_S1, dxs, row, IN, c16, inv_scale);   // W1 carries the LOD weights; written out next tile
+        dx_tile = tile;
         cp_async_wait_all();      // own copies landed; the barrier publishes everybody's
         tc_fence_before();
         __syncthreads();
     }
+    if (g_feats && dx_tile >= 0) dx_copy_out(dxs, g_feats, IN, dx_tile * 128, M);
     // ---------------- flush weight / bias gradients (once per CTA) ----------------
     if (!first) {
         tc_fence_after();

@@ -325,9 +325,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Coalesced variant.  A lane-per-row float4 access touches 32 different 128-byte lines per warp instruction and costs 32 LSU
 // cycles (measured: 3.4 k cycles per 128 x 48 tile pair); here consecutive threads copy consecutive quads of the tile's
-// contiguous [128][IN] block, 4 lines per instruction, into slots[q * 128 + row] (array b: + 128 * IN/4 slots), and thread
-// (row, cg) later reads slots[q * 128 + row], q = cg + NCG k, conflict free.  The consumer reads slots written by other
-// threads: call cp_async_wait_all() before the block barrier that precedes xpfc_consume.
+// contiguous [128][IN] block, 4 lines per instruction, into slots[xpfc_slot(row, q)] (array b: + 128 * IN/4 slots), and
+// thread (row, cg) later reads its quads q = cg + NCG k from there.  The slot order is the block's own (row-major) with the
+// quads of row r rotated by r & 7: at most 2-way bank conflicts for the lane-per-quad writes of cp.async AND the lane-per-row
+// reads (measured: a quad-major layout made every cp.async a 12-way conflict, 4 k cycles per tile).  The consumer reads slots
+// written by other threads: call cp_async_wait_all() before the block barrier that precedes xpfc_consume.
+__device__ __forceinline__ int xpfc_slot(int r, int q, int nq) {
+    int t = q + (r & 7);
+    while (t >= nq) t -= nq;
+    return r * nq + t;
+}
 template <int MAXK>
 __device__ __forceinline__ void xpfc_issue(float4* slots, const float* __restrict__ a, const float* __restrict__ b, int IN, int64_t row0,
                                            int64_t M) {
@@ -338,23 +345,25 @@ __device__ __forceinline__ void xpfc_issue(float4* slots, const float* __restric
         if (g < total) {
             const int r = g / nq, q = g - r * nq;
             const int64_t rs = min(row0 + r, M - 1);
-            cp_async16(slots + q * 128 + r, a + rs * IN + 4 * q);
-            if (b) cp_async16(slots + total + q * 128 + r, b + rs * IN + 4 * q);
+            const int sl = xpfc_slot(r, q, nq);
+            cp_async16(slots + sl, a + rs * IN + 4 * q);
+            if (b) cp_async16(slots + total + sl, b + rs * IN + 4 * q);
         }
     }
     cp_async_commit();
 }
 template <int NCG, int MAXK>
 __device__ __forceinline__ void xpfc_consume(const float4* slots, bool has_b, int IN, int INP, uint8_t* tile, int row, int cg) {
-    const int total = 128 * (IN >> 2);
+    const int nq = IN >> 2, total = 128 * nq;
 #pragma unroll
     for (int k = 0; k < MAXK; ++k) {
         const int q = cg + NCG * k;
         if (4 * q < INP) {
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (4 * q < IN) {
-                x = slots[q * 128 + row];
-                if (has_b) { const float4 y = slots[total + q * 128 + row]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+                const int sl = xpfc_slot(row, q, nq);
+                x = slots[sl];
+                if (has_b) { const float4 y = slots[total + sl]; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
             }
             uint2 u;
             u.x = pack_h2(x.x, x.y); u.y = pack_h2(x.z, x.w);
@@ -378,6 +387,30 @@ __device__ __forceinline__ void stage_x_coalesced(uint8_t* tile, const float* __
         uint2 u;
         u.x = pack_h2(x.x, x.y); u.y = pack_h2(x.z, x.w);
         *reinterpret_cast<uint2*>(tile + (q >> 1) * TCH + r * 16 + (q & 1) * 8) = u;
+    }
+}
+
+// ---- dX tile -> global through shared memory ------------------------------------------------------------------------
+// A lane-per-row float4 store touches 32 lines per warp instruction: the 48 store instructions of a 128 x 48 dX tile keep
+// the LSU busy for ~1.5 k cycles and everything queued behind them (the next tile's shared-memory traffic) waits.  The tile
+// is staged in shared memory instead (row stride IN + 4 floats: conflict free for the lane-per-row writes) and written out
+// by all threads with consecutive threads on consecutive 16-byte quads of the [128][IN] block (4 lines per instruction).
+__device__ __forceinline__ int dx_ld(int IN) { return IN + 4; }
+__device__ __forceinline__ void dx_stage16(uint32_t taddr, float* __restrict__ stage, int row, int IN, int c16, float inv_scale) {
+    float v[16];
+    tmem_ld16(taddr + c16, v);
+    float* d = stage + row * dx_ld(IN) + c16;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (c16 + 4 * q < IN)
+            reinterpret_cast<float4*>(d)[q] = make_float4(v[4 * q] * inv_scale, v[4 * q + 1] * inv_scale, v[4 * q + 2] * inv_scale, v[4 * q + 3] * inv_scale);
+}
+__device__ __forceinline__ void dx_copy_out(const float* __restrict__ stage, float* __restrict__ dst, int IN, int64_t row0, int64_t M) {
+    const unsigned nq = (unsigned)IN >> 2, total = 128u * nq;
+    for (unsigned g = threadIdx.x; g < total; g += blockDim.x) {
+        const unsigned r = g / nq, q = g - r * nq;
+        if (row0 + r < M)
+            reinterpret_cast<float4*>(dst + (row0 + r) * IN)[q] = *reinterpret_cast<const float4*>(stage + r * dx_ld(IN) + 4 * q);
     }
 }
 

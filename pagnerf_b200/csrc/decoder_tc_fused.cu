@@ -461,6 +461,10 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     const int ci1 = Ci > 0 ? Ci : 1;
     const int gc_r0 = tid / ci1, gc_c0 = tid % ci1, gc_dr = PCB_THREADS / ci1, gc_dc = PCB_THREADS % ci1;
     bool first = true;
+    // dX staging [128][IN + 4] f32 (<= 26 KB) aliases Hs | H1 (32 KB): both are dead once the stage-6 MMAs have completed and are
+    // first rewritten after the next tile's stage-1 barrier, i.e. after every thread has finished the copy-out
+    float* dxs = reinterpret_cast<float*>(Hs);
+    int64_t dx_tile = -1;
     PAG_PHASE_INIT();
     cp_async_wait_all();
     __syncthreads();
@@ -472,6 +476,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         const int64_t ray = n_ray, ray0 = n_ray0;
         const float w_row = n_w, lse_row = n_lse;
         const float a_row = __ldg(alpha + ray);
+        if (g_panop && dx_tile >= 0) dx_copy_out(dxs, g_panop, IN, dx_tile * 128, M);      // previous tile's dX
         PAG_PHASE(0);
         // ---------------- stage 1 ----------------
         xpfc_consume<PCB_NCG, PCB_MAXK>(pf, dfeats != nullptr, IN, l.INP, X, row, cg);   // LOD weights live in W1
@@ -490,8 +495,10 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             mma16_fwd(tm + PCB_S0, aX, w1j, 128, 128, l.INP, false);     // sem | inst first layers in one chain
             mb.commit();
         }
+        PAG_PHASE(17);
         if (tile + gridDim.x < ntiles)     // every thread is past its slot reads: the next tile's inputs stream in from here
             xpfc_issue<PCB_MAXK>(pf, feats, dfeats, IN, (tile + gridDim.x) * 128, M);
+        PAG_PHASE(18);
         // while the MMAs run: the tile's per-ray output gradients (first PCB_NGC rays) -> registers, coalesced
         float gpre[7];
         const int ngc_elems = PCB_NGC * Ci;
@@ -503,6 +510,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                 gpre[k] = (e < ngc_elems && src < R * Ci) ? __ldg(g_inst + src) : 0.f;
             }
         }
+        PAG_PHASE(19);
         mb.wait(); PAG_PHASE(3);
         const float cs = valid ? a_row * w_row : 0.f;     // the loss scale rides on the cached gradients
         uint32_t mask_s = 0, mask_1 = 0, mask_2 = 0;
@@ -644,22 +652,13 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             mb.commit();
         }
         mb.wait(); PAG_PHASE(14);
-        if (g_panop && c16 < l.INP) {
-            float v[16];
-            tmem_ld16(tl + PCB_S0 + c16, v);
-            if (valid) {
-#pragma unroll
-                for (int qi = 0; qi < 4; ++qi) {
-                    if (c16 + 4 * qi < IN)
-                        reinterpret_cast<float4*>(g_panop + mm * IN + c16)[qi] =
-                            make_float4(v[4 * qi] * inv_scale, v[4 * qi + 1] * inv_scale, v[4 * qi + 2] * inv_scale, v[4 * qi + 3] * inv_scale);
-                }
-            }
-        }
+        if (g_panop && c16 < l.INP) dx_stage16(tl + PCB_S0, dxs, row, IN, c16, inv_scale);   // written out at the top of the next tile
+        dx_tile = tile;
         cp_async_wait_all();      // own copies landed; the barrier publishes everybody's
         tc_fence_before();
         __syncthreads(); PAG_PHASE(15);
     }
+    if (g_panop && dx_tile >= 0) dx_copy_out(dxs, g_panop, IN, dx_tile * 128, M);
     if (!first) {
         tc_fence_after();
         const int f1 = scatter_base(lane, 32) >> 1;     // feature (of 16) owned by this lane pair after grad16_store
