@@ -55,6 +55,19 @@ int pag_march_ray_emit(const float* origins, const float* dirs, int64_t N, int S
                        int64_t* ridx, int64_t* pidx, float* samples, float* depths, float* deltas,
                        uint8_t* boundary, const uint32_t* seed_dev, void* stream);
 
+/* 'ray' raymarch against an occupancy BIT FIELD of the marching level, without point indices (the fused training trace
+ * never reads pidx).  pag_octree_level_bits derives bits u32[8^level / 32] (bit (ix*res + iy)*res + iz) from the octree once
+ * per octree change; the count pass leaves step masks u32[N * ceil(S/32)] for the emit pass.  Same kept set, same
+ * ridx / samples / depths / deltas as pag_march_ray_{count,emit}. */
+int pag_octree_level_bits(const uint8_t* octree, const int32_t* prefix, int level, uint32_t* bits, void* stream);
+int pag_march_ray_bits_count(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
+                             const float* jitter, uint32_t seed, float dist_min, float dist_range, const uint32_t* bits, int level,
+                             uint32_t* masks, int32_t* counts, int64_t* offsets, const uint32_t* seed_dev, void* stream);
+int pag_march_ray_bits_emit(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
+                            const float* jitter, uint32_t seed, float dist_min, float dist_range, const uint32_t* masks,
+                            const int64_t* offsets, int64_t* ridx, float* samples, float* depths, float* deltas,
+                            const uint32_t* seed_dev, void* stream);
+
 /* kaolin.render.spc.unbatched_raytrace(return_depth, with_exit): count pass then emit pass;
  * nuggets (ridx,pidx,[entry,exit]) in kaolin's order.  offsets[N+1] doubles as the per-ray first-nugget index. */
 int pag_raytrace_count(const uint8_t* octree, const int32_t* prefix, const float* origins, const float* dirs,

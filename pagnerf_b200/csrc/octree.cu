@@ -234,6 +234,104 @@ __global__ void march_ray_emit_kernel(const float* __restrict__ org, const float
 }
 
 // ---------------------------------------------------------------------------------------------
+// 'ray' mode without point indices (training hot path): occupancy bit field of the marching level
+// The fused trace never uses pidx; it only needs to know WHICH of the S steps of a ray fall into an occupied cell.  The
+// level-7 occupancy is 2 M cells = 256 KB as a bit field (cell (ix,iy,iz) -> bit (ix*res + iy)*res + iz): one cached word
+// per step instead of a 7-level descent through octree bytes + prefix sums, and the count pass hands 128-bit step masks
+// (16 B per ray) to the emit pass instead of N*S point indices (8 MB each way).  The kept set is the same by construction:
+// a cell's bit is the result of octree_query_point on that cell, and the step -> cell arithmetic is shared.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t cell_of_point(float x, float y, float z, int level) {
+    const float res = (float)(1 << level);
+    const float qx = floorf(__fmul_rn(res, __fadd_rn(__fmul_rn(x, 0.5f), 0.5f)));
+    const float qy = floorf(__fmul_rn(res, __fadd_rn(__fmul_rn(y, 0.5f), 0.5f)));
+    const float qz = floorf(__fmul_rn(res, __fadd_rn(__fmul_rn(z, 0.5f), 0.5f)));
+    if (!(qx >= 0.f && qx < res && qy >= 0.f && qy < res && qz >= 0.f && qz < res)) return -1;
+    if (isinf(x) || isinf(y) || isinf(z)) return -1;
+    return (((int64_t)qx << level) | (int64_t)qy) << level | (int64_t)qz;
+}
+__global__ void octree_level_bits_kernel(const uint8_t* __restrict__ octree, const int* __restrict__ prefix, int level,
+                                         int64_t ncells, uint32_t* __restrict__ bits) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // ncells is a multiple of 32 for level >= 2
+    bool occ = false;
+    if (c < ncells) {
+        const int m = (1 << level) - 1;
+        const int ix = (int)(c >> (2 * level)) & m, iy = (int)(c >> level) & m, iz = (int)c & m;
+        int node = 0;
+        occ = true;
+        for (int l = 0; l < level && occ; ++l) {
+            const int sft = level - 1 - l;
+            const uint32_t j = (((ix >> sft) & 1) << 2) | (((iy >> sft) & 1) << 1) | ((iz >> sft) & 1);
+            const uint32_t byte = __ldg(octree + node);
+            if (!((byte >> j) & 1u)) occ = false;
+            else node = __ldg(prefix + node) + __popc(byte & ((2u << j) - 1u));
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, occ);
+    if ((threadIdx.x & 31) == 0 && c < ncells) bits[c >> 5] = b;
+}
+__global__ void march_ray_bits_count_kernel(const float* __restrict__ org, const float* __restrict__ dir, int64_t N, int S,
+                                            const float* __restrict__ lin, const float* __restrict__ jitter, uint32_t seed,
+                                            float near, float range, const uint32_t* __restrict__ bits, int level,
+                                            uint32_t* __restrict__ masks, int* __restrict__ counts,
+                                            const uint32_t* __restrict__ seed_dev) {
+    if (seed_dev) seed = __ldg(seed_dev);
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= N) return;
+    const float ox = org[3 * ray], oy = org[3 * ray + 1], oz = org[3 * ray + 2];
+    const float dx = dir[3 * ray], dy = dir[3 * ray + 1], dz = dir[3 * ray + 2];
+    const int nw = (S + 31) >> 5;
+    int cnt = 0;
+    for (int wi = 0; wi < nw; ++wi) {
+        const int i = 32 * wi + lane;
+        bool keep = false;
+        if (i < S) {
+            const float t = ray_step_depth(ray, i, S, lin, jitter, seed, near, range);
+            const int64_t c = cell_of_point(__fadd_rn(ox, __fmul_rn(dx, t)), __fadd_rn(oy, __fmul_rn(dy, t)),
+                                            __fadd_rn(oz, __fmul_rn(dz, t)), level);
+            keep = c >= 0 && ((__ldg(bits + (c >> 5)) >> (c & 31)) & 1u);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) masks[ray * nw + wi] = b;
+        cnt += __popc(b);
+    }
+    if (lane == 0) counts[ray] = cnt;
+}
+__global__ void march_ray_bits_emit_kernel(const float* __restrict__ org, const float* __restrict__ dir, int64_t N, int S,
+                                           const float* __restrict__ lin, const float* __restrict__ jitter, uint32_t seed,
+                                           float near, float range, const uint32_t* __restrict__ masks,
+                                           const int64_t* __restrict__ offsets, int64_t* __restrict__ ridx,
+                                           float* __restrict__ samples, float* __restrict__ depths, float* __restrict__ deltas,
+                                           const uint32_t* __restrict__ seed_dev) {
+    if (seed_dev) seed = __ldg(seed_dev);
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= N) return;
+    int64_t off = offsets[ray];
+    if (offsets[ray + 1] == off) return;
+    const float ox = org[3 * ray], oy = org[3 * ray + 1], oz = org[3 * ray + 2];
+    const float dx = dir[3 * ray], dy = dir[3 * ray + 1], dz = dir[3 * ray + 2];
+    const int nw = (S + 31) >> 5;
+    for (int wi = 0; wi < nw; ++wi) {
+        const unsigned b = __ldg(masks + ray * nw + wi);
+        if ((b >> lane) & 1u) {
+            const int i = 32 * wi + lane;
+            const int64_t dst = off + __popc(b & ((1u << lane) - 1u));
+            const float t = ray_step_depth(ray, i, S, lin, jitter, seed, near, range);
+            const float tp = (i == 0) ? near : ray_step_depth(ray, i - 1, S, lin, jitter, seed, near, range);
+            ridx[dst] = ray;
+            samples[3 * dst + 0] = __fadd_rn(ox, __fmul_rn(dx, t));
+            samples[3 * dst + 1] = __fadd_rn(oy, __fmul_rn(dy, t));
+            samples[3 * dst + 2] = __fadd_rn(oz, __fmul_rn(dz, t));
+            depths[dst] = t;
+            deltas[dst] = __fsub_rn(t, tp);
+        }
+        off += __popc(b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 'voxel' mode: per-ray DFS in kaolin's nugget order (children j = code ^ i)
 // ---------------------------------------------------------------------------------------------
 struct RayCtx { float ox, oy, oz, dx, dy, dz, ix, iy, iz, sx, sy, sz; };
@@ -441,6 +539,40 @@ int pag_march_ray_emit(const float* origins, const float* dirs, int64_t N, int S
     march_ray_emit_kernel<<<pag_grid(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         origins, dirs, N, S, linspace, jitter, seed, dist_min, dist_range, pidx_tmp, offsets, ridx, pidx, samples,
         depths, deltas, boundary, seed_dev);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// occupancy bit field of `level`: bits u32[8^level / 32], bit (ix*res + iy)*res + iz of the word array
+int pag_octree_level_bits(const uint8_t* octree, const int32_t* prefix, int level, uint32_t* bits, void* stream) {
+    if (level < 2 || level > PAG_MAX_LEVEL) return PAG_ERR_ARG;
+    const int64_t ncells = (int64_t)1 << (3 * level);
+    octree_level_bits_kernel<<<pag_grid(ncells, 256), 256, 0, (cudaStream_t)stream>>>(octree, prefix, level, ncells, bits);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+// 'ray' march against the bit field, no point indices: masks u32[N * ceil(S/32)], counts i32[N], offsets i64[N+1]
+int pag_march_ray_bits_count(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
+                             const float* jitter, uint32_t seed, float dist_min, float dist_range, const uint32_t* bits, int level,
+                             uint32_t* masks, int32_t* counts, int64_t* offsets, const uint32_t* seed_dev, void* stream) {
+    if (level < 2 || level > PAG_MAX_LEVEL || S <= 0) return PAG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 0) {
+        march_ray_bits_count_kernel<<<pag_grid(N * 32, 256), 256, 0, st>>>(origins, dirs, N, S, linspace, jitter, seed, dist_min,
+                                                                          dist_range, bits, level, masks, counts, seed_dev);
+        PAG_LAUNCH_CHECK();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, offsets);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_march_ray_bits_emit(const float* origins, const float* dirs, int64_t N, int S, const float* linspace,
+                            const float* jitter, uint32_t seed, float dist_min, float dist_range, const uint32_t* masks,
+                            const int64_t* offsets, int64_t* ridx, float* samples, float* depths, float* deltas,
+                            const uint32_t* seed_dev, void* stream) {
+    if (N == 0) return PAG_OK;
+    march_ray_bits_emit_kernel<<<pag_grid(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        origins, dirs, N, S, linspace, jitter, seed, dist_min, dist_range, masks, offsets, ridx, samples, depths, deltas, seed_dev);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

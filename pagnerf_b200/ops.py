@@ -592,21 +592,30 @@ class FusedTraceFn(Function):
         Mmax = max(N * S, 1)
         lin = _linspace(S, dev)
         f32, i64 = torch.float32, torch.int64
-        pidx_tmp = torch.empty(Mmax, dtype=torch.int32, device=dev)
         counts = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
         offsets = torch.empty(N + 1, dtype=i64, device=dev)
         near = float(cfg['near'])
         rng = float(torch.tensor(float(cfg['far']) - near, dtype=f32))
         seed_dev = cfg.get('seed_dev')
-        call("pag_march_ray_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng,
-             ptr(cfg['octree']), ptr(cfg['prefix']), int(cfg['level']), ptr(pidx_tmp), ptr(counts), ptr(offsets), ptr(seed_dev))
-        m_dev = offsets[N:]                      # device-side packed-sample count M
         ridx = torch.empty(Mmax, dtype=i64, device=dev)
         samples = torch.empty(Mmax, 3, dtype=f32, device=dev)
         depths = torch.empty(Mmax, dtype=f32, device=dev)
         deltas = torch.empty(Mmax, dtype=f32, device=dev)
-        call("pag_march_ray_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(pidx_tmp),
-             ptr(offsets), ptr(ridx), None, ptr(samples), ptr(depths), ptr(deltas), None, ptr(seed_dev))
+        bits = cfg.get('bits')
+        if bits is not None:
+            # occupancy bit field instead of the octree descent, 128-bit step masks instead of N*S point indices
+            masks = torch.empty(max(N, 1) * ((S + 31) // 32), dtype=torch.int32, device=dev)
+            call("pag_march_ray_bits_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(bits),
+                 int(cfg['level']), ptr(masks), ptr(counts), ptr(offsets), ptr(seed_dev))
+            call("pag_march_ray_bits_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(masks),
+                 ptr(offsets), ptr(ridx), ptr(samples), ptr(depths), ptr(deltas), ptr(seed_dev))
+        else:
+            pidx_tmp = torch.empty(Mmax, dtype=torch.int32, device=dev)
+            call("pag_march_ray_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng,
+                 ptr(cfg['octree']), ptr(cfg['prefix']), int(cfg['level']), ptr(pidx_tmp), ptr(counts), ptr(offsets), ptr(seed_dev))
+            call("pag_march_ray_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(pidx_tmp),
+                 ptr(offsets), ptr(ridx), None, ptr(samples), ptr(depths), ptr(deltas), None, ptr(seed_dev))
+        m_dev = offsets[N:]                      # device-side packed-sample count M
         if seed_dev is not None:
             seed_dev.add_(1)                     # next replay / step draws the next jitter stream
         sf, sh, an, cap, L, n_agg = cfg['grid']

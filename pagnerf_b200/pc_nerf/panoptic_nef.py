@@ -254,6 +254,7 @@ class PanopticNeF(BaseNeuralField):
         dmin = float(rays.dist_min) if not torch.is_tensor(rays.dist_min) else float(rays.dist_min.flatten()[0])
         dmax = float(rays.dist_max) if not torch.is_tensor(rays.dist_max) else float(rays.dist_max.flatten()[0])
         return dict(octree=blas.octree, prefix=blas.prefix, level=self.grid.blas_level, S=int(num_steps), near=dmin, far=dmax,
+                    bits=blas.level_bits(self.grid.blas_level) if self.grid.blas_level >= 2 else None,
                     seed=seed, seed_dev=getattr(blas, 'seed_tensor', None), bg_white=(bg_color == 'white'), pos_half=torch.is_autocast_enabled(),
                     lodw=self._lodw(dev), grid=enc(self.grid.embedder),
                     dgrid=enc(self.delta_grid.embedder) if src in ('delta', 'separate') else None, pan_src=src,

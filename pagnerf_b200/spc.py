@@ -109,6 +109,7 @@ class OctreeAS:
         self.max_level = None
         self.jitter_seed = 0       # seed of the counter-based jitter stream; bumped per raymarch call
         self.fixed_jitter = False  # tests pin the stream
+        self._bits = {}            # level -> occupancy bit field (see level_bits)
 
     def init(self, octree):
         octree = octree.to(self.device).to(torch.uint8).contiguous()
@@ -118,6 +119,7 @@ class OctreeAS:
         self.prefix = self.prefix.contiguous()
         self.octree = octree
         self.max_level = level
+        self._bits = {}
 
     def init_dense(self, level):
         n_nodes = (8 ** level - 1) // 7
@@ -131,6 +133,17 @@ class OctreeAS:
             self.prefix = self.prefix.to(device)
         self.device = device
         return self
+
+    def level_bits(self, level):
+        """Occupancy bit field of `level` (int32 words, bit (ix*res + iy)*res + iz), derived from the octree on first use and
+        cached until the octree changes; the fused training trace marches against it (csrc/octree.cu)."""
+        level = int(level)
+        b = self._bits.get(level)
+        if b is None or b.device != self.octree.device:
+            b = torch.empty((8 ** level) // 32, dtype=torch.int32, device=self.octree.device)
+            ops.call("pag_octree_level_bits", ops.ptr(self.octree), ops.ptr(self.prefix), level, ops.ptr(b))
+            self._bits[level] = b
+        return b
 
     def query(self, coords, level=None):
         lvl = self.max_level if level is None else level
