@@ -893,7 +893,7 @@ int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float*
         const bool rgb = g_rgb != nullptr;
         WsSegs sg{5, {wl.oWd1, wl.oWd2, wl.oWc1, wl.oWc2, wl.oWc3}, {64 * IN, 16 * 64, 64 * CIN, 64 * 64, 3 * 64},
                   {p.gWd1, p.gWd2, rgb ? p.gWc1 : nullptr, rgb ? p.gWc2 : nullptr, rgb ? p.gWc3 : nullptr}};
-        ws_reduce_kernel<<<(wl.total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, nblocks, M_max, m_dev, wl.total, sg);
+        ws_reduce_kernel<<<dim3((wl.total + 255) / 256, WS_GROUPS), 256, 0, (cudaStream_t)stream>>>(ws, nblocks, M_max, m_dev, wl.total, sg);
         PAG_LAUNCH_CHECK();
     }
     return PAG_OK;

