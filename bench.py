@@ -461,7 +461,7 @@ def main():
         tr = measured_traffic(top[0])
         if tr:
             roof["traffic"] = tr["dram_bytes"] * n_samples / tr["samples"]
-            roof["traffic_source"] = "ncu --set full dram__bytes_read+write per launch (profiles/r01_ncu_full_top_kernels.md), scaled by packed samples"
+            roof["traffic_source"] = "ncu --set full dram__bytes_read+write per launch (profiles/r01_ncu_full_final.md), scaled by packed samples"
         roof["peak_source"] = how
         roof["share_of_step"] = top[1]["ms_per_step"] / ms
         roof["samples_per_launch"] = n_samples
