@@ -338,13 +338,20 @@ def main():
 
     import torch.distributed as dist
     from pagnerf_b200 import _lib, parallel
+
+    def trace(msg):      # BENCH_TRACE=1: progress marks on stderr (debugging multi-rank runs)
+        if os.environ.get("BENCH_TRACE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        trace("process group up")
     wl = Workload(device, args.rays, seed=rank)
+    trace("workload built")
     if world > 1:
         from pagnerf_b200 import ops
         ops.set_grad_sync(True)      # gradient all-reduce (NCCL, AVG) issued from inside the fused backward, overlapped
@@ -357,9 +364,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
         step(False)
+        trace(f"warm-up step {i} enqueued")
     sync()
+    trace("warm-up done")
     # ---- CUDA-graph capture of the whole step (single GPU; the fused path has static launch geometry) --------------
     graphed, graph_note = None, "eager"
     if world == 1 and not args.no_graph:
@@ -389,6 +398,7 @@ def main():
     e1.record()
     sync()
     ms = e0.elapsed_time(e1) / args.steps
+    trace(f"timed region done: {ms:.3f} ms/step")
     t_host0 = time.perf_counter()           # CPU time to enqueue a step into an empty stream (GPU-bound when << ms_per_step)
     for _ in range(3):
         run(False)
@@ -479,7 +489,7 @@ def main():
         for _ in range(10):
             _lib.call("pag_gather_probe", _lib.ptr(table), entries, n_all, 96, _lib.ptr(sink))
         g1.record()
-        sync()
+        torch.cuda.synchronize()      # rank 0 only from here on: no barrier
         probe_gbs = n_all * 96 * 8 / (g0.elapsed_time(g1) / 10 * 1e-3) / 1e9
         t_enc = enc["ms_per_launch"] * 1e-3
         n_enc = (n_all + n_live) / 2          # two launches per step: colour grid (all samples) and delta grid (live samples)
