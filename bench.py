@@ -302,6 +302,17 @@ def peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def _leave(world):
+    """Multi-rank exit.  No collective follows the max-over-ranks all-reduce, so every rank may leave on its own; the NCCL
+    communicator teardown (destroy_process_group with captured graphs still holding NCCL kernels) can block on a peer that has
+    already gone, so flush and exit the process directly."""
+    if world > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -371,12 +382,14 @@ def main():
     trace("warm-up done")
     # ---- CUDA-graph capture of the whole step (single GPU; the fused path has static launch geometry) --------------
     graphed, graph_note = None, "eager"
-    if world == 1 and not args.no_graph:
+    # multi-rank: NCCL all-reduces issued inside the backward are captured with the step (every rank captures the same sequence)
+    if (world == 1 or os.environ.get("BENCH_GRAPH_MULTI", "1") == "1") and not args.no_graph:
         try:
             from pagnerf_b200.graph import GraphedStep
             wl.keep_rb, wl.last_rb = False, None
             graphed = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef)
-            graph_note = "whole step (fwd + loss + bwd) replayed as one CUDA graph"
+            graph_note = "whole step (fwd + loss + bwd%s) replayed as one CUDA graph" % (" + NCCL gradient all-reduce" if world > 1 else "")
+            trace("graph captured")
         except Exception as e:   # keep the eager number rather than fail the bench
             graphed, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {e})"
             torch.cuda.synchronize()
@@ -438,8 +451,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(world)
         return 0
 
     hbm, tf, how = peaks()
@@ -522,8 +534,7 @@ def main():
               "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roof, "encoder": encoder, "cpu_baseline": cpu,
               "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
     print(json.dumps(result))
-    if world > 1:
-        dist.destroy_process_group()
+    _leave(world)
     return 0
 
 
