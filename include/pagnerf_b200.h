@@ -136,6 +136,13 @@ int pag_decode_pan_bwd(const float* feats, const float* dfeats, const float* lod
                        const float* const* weights, float* const* grads, int hidden, int Cs, int Ci, int sem_softmax,
                        int inst_softmax, float inst_temperature, const float* sem, const float* inst,
                        const float* g_sem, const float* g_inst, float* g_panop, void* stream);
+/* linear scalar head y[m] = b + sum_k (feats + dfeats)[m,k] * lodw[k] * w[k]: PanopticDDensityNeF's delta-density decoder
+ * (pc_nerf/panoptic_dd_nef.py:41-58, BasicDecoder with activation 'none' = one linear map, collapsed on the host).
+ * dfeats / lodw / g_x nullable; g_w f32[IN] and g_b f32[1] accumulate (caller zeroes). */
+int pag_linear_head_fwd(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN, const float* w,
+                        const float* b, float* y, void* stream);
+int pag_linear_head_bwd(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN, const float* w,
+                        const float* g, float* g_x, float* g_w, float* g_b, void* stream);
 
 /* tensor-core (tcgen05, fp16 operands / fp32 accumulate) variants of the four decoder entry points: the numerics of
  * the reference's autocast training step (pc_nerf/trainer.py:429).  grad_scale: device pointer to one power-of-two

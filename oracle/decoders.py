@@ -9,10 +9,12 @@ from torch import nn
 
 
 class BasicDecoderOracle(nn.Module):
-    """num_layers hidden Linear+ReLU (first in->hidden), then `lout` Linear(hidden,out) w/o activation."""
+    """num_layers hidden Linear+activation (first in->hidden; ReLU, or none for wisp's 'none' = Identity), then `lout`
+    Linear(hidden,out) w/o activation."""
 
-    def __init__(self, input_dim, output_dim, num_layers=1, hidden_dim=64, bias=True):
+    def __init__(self, input_dim, output_dim, num_layers=1, hidden_dim=64, bias=True, activation='relu'):
         super().__init__()
+        self.activation = activation
         dims = [input_dim] + [hidden_dim] * num_layers
         self.layers = nn.ModuleList([nn.Linear(dims[i], dims[i + 1], bias=bias) for i in range(num_layers)])
         self.lout = nn.Linear(hidden_dim, output_dim, bias=bias)
@@ -20,7 +22,8 @@ class BasicDecoderOracle(nn.Module):
     def forward(self, x):
         h = x
         for l in self.layers:
-            h = torch.relu(l(h))
+            h = l(h)
+            h = torch.relu(h) if self.activation == 'relu' else h
         return self.lout(h)
 
 

@@ -21,7 +21,7 @@ class FieldOracle(nn.Module):
 
     def __init__(self, grid, delta_grid=None, feat_dim=48, hidden_dim=64, num_classes=6, num_instances=200,
                  view_multires=4, num_layers=1, sem_num_layers=1, inst_num_layers=2,
-                 sem_softmax=True, inst_softmax=True, inst_soft_temperature=0.0, seed=0):
+                 sem_softmax=True, inst_softmax=True, inst_soft_temperature=0.0, seed=0, delta_density=False):
         super().__init__()
         torch.manual_seed(seed)
         self.grid, self.delta_grid = grid, delta_grid
@@ -31,6 +31,8 @@ class FieldOracle(nn.Module):
         self.decoder_color = BasicDecoderOracle(16 + self.view_embedder.out_dim, 3, num_layers + 1, hidden_dim)
         self.decoder_semantics = BasicDecoderOracle(feat_dim, num_classes, sem_num_layers, hidden_dim)
         self.decoder_inst = BasicDecoderOracle(feat_dim, num_instances, inst_num_layers, hidden_dim)
+        # PanopticDDensityNeF (pc_nerf/panoptic_dd_nef.py:41-58): activation-free 1-hidden-layer head feat -> 64 -> 1
+        self.decoder_delta_density = BasicDecoderOracle(feat_dim, 1, 1, hidden_dim, activation='none') if delta_density else None
         self.lod_weights = torch.ones(feat_dim)
         self.sem_softmax, self.inst_softmax = sem_softmax, inst_softmax
         self.inst_soft_temperature = inst_soft_temperature
@@ -48,12 +50,18 @@ class FieldOracle(nn.Module):
         if 'rgb' in channels:
             ve = self.view_embedder(-ray_d)[:, None].repeat(1, S, 1).view(-1, self.view_embedder.out_dim)
             out['rgb'] = torch.sigmoid(self.decoder_color(torch.cat([density_feats, ve], -1))).reshape(batch, S, 3)
-        if 'semantics' in channels or 'inst_embedding' in channels:
+        if any(c in channels for c in ('semantics', 'inst_embedding', 'delta_density', 'panoptic_density')):
             if self.delta_grid is not None:
                 dfe = self.delta_grid(coords.detach().reshape(-1, 3)) * self.lod_weights.to(coords.dtype)
                 panop = feats.detach() + dfe
             else:  # PanopticNeF with sem_detach / inst_detach = True (defaults)
                 panop = feats.detach()
+        if 'delta_density' in channels or 'panoptic_density' in channels:      # pc_nerf/panoptic_dd_nef.py:236-247
+            dd = self.decoder_delta_density(panop).reshape(batch, S, 1)
+            if 'delta_density' in channels:
+                out['delta_density'] = dd
+            if 'panoptic_density' in channels:
+                out['panoptic_density'] = torch.relu(density_feats[..., 0:1].reshape(batch, S, 1).detach() + dd)
         if 'semantics' in channels:
             s = self.decoder_semantics(panop)
             out['semantics'] = F.softmax(s, -1) if self.sem_softmax else s
@@ -66,7 +74,7 @@ class FieldOracle(nn.Module):
 
 
 def trace_oracle(field, origins, dirs, ridx, samples, depths, deltas, boundary, channels,
-                 bg_color='white'):
+                 bg_color='white', dd=False):
     """PanopticPackedRFTracer.trace after the marcher (tracers/...:113-195).
 
     ridx int64 [M], samples [M,S,3], depths [M,S,1] or [M,1], deltas [M*S,1], boundary bool [M*S].
@@ -79,6 +87,9 @@ def trace_oracle(field, origins, dirs, ridx, samples, depths, deltas, boundary, 
     ridx_hit = ridx[spc.mark_pack_boundaries(ridx.int())]
     hit_ray_d = dirs.index_select(0, ridx)
     sample_channels = set(channels) - {'depth', 'alpha', 'hit'} | {'density'}
+    pan = [c for c in ('semantics', 'inst_embedding') if c in channels]
+    if dd and pan:      # tracers/panoptic_dd_packed_rf_tracer.py:102-103
+        sample_channels |= {'panoptic_density'}
     feats = field(samples, hit_ray_d, sample_channels)
     tau = feats['density'].reshape(-1, 1) * deltas
     _, w = spc.exponential_integration(None, tau, boundary, exclusive=True)
@@ -99,9 +110,11 @@ def trace_oracle(field, origins, dirs, ridx, samples, depths, deltas, boundary, 
         rd = spc.sum_reduce(depths.reshape(-1, 1) * w, boundary)
         depth = torch.zeros(N, 1, dtype=dt); depth[ridx_hit] = rd
         out['depth'] = depth
-    pan = [c for c in ('semantics', 'inst_embedding') if c in channels]
     if pan:
-        _, pw = spc.exponential_integration(None, tau.detach(), boundary, exclusive=True)
+        # PanopticPackedRFTracer: second integration of the DETACHED colour density (:149-155);
+        # PanopticDDensityPackedRFTracer: integration of the panoptic density, gradients flowing (:128-137)
+        ptau = feats['panoptic_density'].reshape(-1, 1) * deltas.detach() if dd else tau.detach()
+        _, pw = spc.exponential_integration(None, ptau, boundary, exclusive=True)
         palpha = spc.sum_reduce(pw, boundary)
         for c in pan:
             f = feats[c]

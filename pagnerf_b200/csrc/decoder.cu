@@ -678,6 +678,54 @@ static int pan_bwd_launch(const float* feats, const float* dfeats, const float* 
     return PAG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// linear scalar head: y[m] = b + sum_k (feats[m,k] + dfeats[m,k]) * lodw[k] * w[k]
+// PanopticDDensityNeF's delta-density decoder (pc_nerf/panoptic_dd_nef.py:41-58) is a BasicDecoder with activation 'none'
+// (Identity): feat -> 64 -> 1 without a nonlinearity is ONE linear map, w = W2 W1, b = W2 b1 + b2 (collapsed on the host,
+// where autograd carries the gradient back to W1 / b1 / W2 / b2).  Thread per sample, float4 rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void linear_head_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ dfeats,
+                                       const float* __restrict__ lodw, int64_t M, int IN, const float* __restrict__ w,
+                                       const float* __restrict__ b, float* __restrict__ y) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float acc = __ldg(b);
+    for (int k = 0; k < IN; ++k) {
+        float x = feats[m * IN + k];
+        if (dfeats) x += dfeats[m * IN + k];
+        if (lodw) x *= __ldg(lodw + k);
+        acc = fmaf(x, __ldg(w + k), acc);
+    }
+    y[m] = acc;
+}
+// g_x[m,k] = g[m] * lodw[k] * w[k] (same for feats and dfeats); g_w[k] += sum_m g[m] * x[m,k]; g_b += sum_m g[m]
+__global__ void __launch_bounds__(256) linear_head_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dfeats,
+                                                              const float* __restrict__ lodw, int64_t M, int IN,
+                                                              const float* __restrict__ w, const float* __restrict__ g,
+                                                              float* __restrict__ g_x, float* __restrict__ g_w, float* __restrict__ g_b) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = m < M;
+    const float gm = valid ? g[m] : 0.f;
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < IN; ++k) {
+        const float lw = lodw ? __ldg(lodw + k) : 1.f;
+        float x = 0.f;
+        if (valid) {
+            x = feats[m * IN + k];
+            if (dfeats) x += dfeats[m * IN + k];
+            if (g_x) g_x[m * IN + k] = gm * lw * __ldg(w + k);
+        }
+        float s = gm * x * lw;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && s != 0.f) red_add_f32(g_w + k, s);
+    }
+    float sb = gm;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    if (lane == 0 && sb != 0.f) red_add_f32(g_b, sb);
+}
+
 extern "C" {
 
 // weights: 10 pointers in the order Wd1,bd1,Wd2,bd2,Wc1,bc1,Wc2,bc2,Wc3,bc3 (torch Linear [out][in])
@@ -760,6 +808,24 @@ int pag_decode_pan_bwd(const float* feats, const float* dfeats, const float* lod
         case 48: return pan_bwd_launch<48>(feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, sem, inst, g_sem, g_inst, g_panop, st);
         default: return PAG_ERR_UNSUPPORTED;
     }
+}
+
+// linear scalar head on (feats + dfeats) * lodw: y f32[M]; w f32[IN], b f32[1].  g_x nullable; g_w / g_b accumulate (zeroed by the caller).
+int pag_linear_head_fwd(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN, const float* w,
+                        const float* b, float* y, void* stream) {
+    if (IN <= 0) return PAG_ERR_ARG;
+    if (M == 0) return PAG_OK;
+    linear_head_fwd_kernel<<<pag_grid(M, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M, IN, w, b, y);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_linear_head_bwd(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN, const float* w,
+                        const float* g, float* g_x, float* g_w, float* g_b, void* stream) {
+    if (IN <= 0) return PAG_ERR_ARG;
+    if (M == 0) return PAG_OK;
+    linear_head_bwd_kernel<<<pag_grid(M, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M, IN, w, g, g_x, g_w, g_b);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
 }
 
 }  // extern "C"

@@ -313,6 +313,37 @@ class DecodeDCFn(Function):
         return (gf, None, gd, None, None, None, *grads)
 
 
+class LinearHeadFn(Function):
+    """y[m] = b + sum_k (feats + dfeats)[m,k] * lodw[k] * w[k]  (csrc/decoder.cu linear_head_*): the activation-free
+    delta-density head of PanopticDDensityNeF after collapsing its two Linear layers on the host."""
+
+    @staticmethod
+    def forward(ctx, feats, dfeats, lodw, w, b):
+        _chk(feats, dfeats, w, b)
+        f, df = _f32(feats), _f32(dfeats)
+        M, IN = f.shape
+        lw, w_, b_ = _f32(lodw), _f32(w).reshape(-1), _f32(b).reshape(-1)
+        y = torch.empty(M, dtype=torch.float32, device=f.device)
+        call("pag_linear_head_fwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr(w_), ptr(b_), ptr(y))
+        ctx.save_for_backward(f, df, lw, w_)
+        ctx.shapes = (w.shape, b.shape)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        f, df, lw, w_ = ctx.saved_tensors
+        M, IN = f.shape
+        g_ = _f32(g).reshape(-1)
+        need_x = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        gx = torch.empty_like(f) if need_x else None
+        gw = torch.zeros(IN, dtype=torch.float32, device=f.device)
+        gb = torch.zeros(1, dtype=torch.float32, device=f.device)
+        call("pag_linear_head_bwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr(w_), ptr(g_), ptr(gx), ptr(gw), ptr(gb))
+        return (gx if ctx.needs_input_grad[0] else None, gx if (ctx.needs_input_grad[1] and df is not None) else None, None,
+                gw.reshape(ctx.shapes[0]), gb.reshape(ctx.shapes[1]))
+
+
 class DecodePanFn(Function):
     """semantic + instance decoders on panop = (feats + dfeats) * lodw."""
 

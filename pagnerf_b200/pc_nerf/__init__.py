@@ -1,5 +1,6 @@
-"""Neural-field plugin classes with the reference's surface (pc_nerf/panoptic_{,delta_}nef.py)."""
+"""Neural-field plugin classes with the reference's surface (pc_nerf/panoptic_{,delta_,dd_}nef.py)."""
 from .panoptic_nef import PanopticNeF
 from .panoptic_delta_nef import PanopticDeltaNeF
+from .panoptic_dd_nef import PanopticDDensityNeF
 
-__all__ = ["PanopticNeF", "PanopticDeltaNeF"]
+__all__ = ["PanopticNeF", "PanopticDeltaNeF", "PanopticDDensityNeF"]

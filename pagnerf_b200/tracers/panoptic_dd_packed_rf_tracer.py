@@ -1,0 +1,71 @@
+"""PanopticDDensityPackedRFTracer: PanopticPackedRFTracer whose panoptic channels are integrated with the field's
+`panoptic_density` -- weights NOT detached, so the panoptic losses also train the delta-density head
+(reference tracers/panoptic_dd_packed_rf_tracer.py:52-177; second tau stream :128-137, integration :158-162).
+
+SURVEY 8(f) rank 2.  Step-by-step path: marcher and colour compositing are the kernels of the base tracer; the panoptic
+integration is composed from the kaolin-compatible autograd ops (exponential_integration, sum_reduce)."""
+import torch
+
+from .. import ops
+from ..wisp_compat import RenderBuffer
+from .panoptic_packed_rf_tracer import PanopticPackedRFTracer, sigma_sparsity_loss
+
+
+class PanopticDDensityPackedRFTracer(PanopticPackedRFTracer):
+    allow_fused = False      # the fused trace composites with the detached colour density
+
+    def trace(self, nef, channels, extra_channels, rays, lod_idx=None, raymarch_type='voxel', num_steps=64, step_size=1.0,
+              bg_color='white', stage=None):
+        assert nef.grid is not None and "this tracer requires a grid"
+        N = rays.origins.shape[0]
+        if "depth" in channels:
+            depth = torch.zeros(N, 1, device=rays.origins.device)
+        else:
+            depth = None
+        if lod_idx is None:
+            lod_idx = nef.grid.num_lods - 1
+        raymarch_results = nef.grid.raymarch(rays, level=nef.grid.active_lods[lod_idx], num_samples=num_steps,
+                                             raymarch_type=raymarch_type)
+        ridx, pidx, samples, depths, deltas = raymarch_results[:5]
+        S = samples.shape[1]
+        if raymarch_type == 'voxel' and depths.numel() != 0:          # :88-108
+            first = ops.ray_offsets(ridx, N)
+            valid_mask = ops.max_travel_mask(ridx, depths, first, self.ray_max_travel)
+            deltas = deltas.reshape(depths.shape)[valid_mask].reshape(-1, 1)
+            ridx, pidx, samples, depths = ridx[valid_mask], pidx[valid_mask], samples[valid_mask], depths[valid_mask]
+        offsets = ops.ray_offsets(ridx, N) * S
+        self.last_num_samples, self._last_ridx = int(ridx.shape[0]) * S, ridx
+        hit_ray_d = rays.dirs.index_select(0, ridx)
+
+        outputs = {}
+        sample_channels = set(channels - self.render_channels)
+        sample_channels.update(['density'])
+        pan = [c for c in channels if c in self.panoptic_channels]
+        if pan:
+            sample_channels.update(['panoptic_density'])               # :102-103
+        out_feats = nef(coords=samples, ray_d=hit_ray_d, pidx=pidx, lod_idx=lod_idx, channels=sample_channels)
+        if self.ray_sparcity_reg > 0.0 and stage == 'train':
+            all_rays_loss = sigma_sparsity_loss(out_feats['density'].reshape(ridx.shape[0], -1).sum(-1) if S > 1
+                                                else out_feats['density'].squeeze())
+            ray_wise_loss = torch.scatter_add(torch.zeros_like(rays.origins[:, 0]), 0, ridx, all_rays_loss)
+            outputs['ray_sparcity_loss'] = ray_wise_loss.mean() * self.ray_sparcity_reg
+
+        alpha, hit, rgb, depth_o, _, _, w = ops.composite(
+            out_feats['density'], deltas, depths if 'depth' in channels else None,
+            out_feats['rgb'] if 'rgb' in channels else None, None, None, offsets, bg_white=(bg_color == 'white'))
+        outputs['alpha'], outputs['hit'] = alpha, hit
+        if 'rgb' in channels:
+            outputs['rgb'] = rgb
+        if 'depth' in channels:
+            outputs['depth'] = depth_o
+        if pan:
+            ptau = out_feats['panoptic_density'].reshape(-1, 1) * deltas.detach().reshape(-1, 1)
+            pw = ops.ExpIntFn.apply(ptau, offsets)        # exclusive transmittance * (1 - exp(-tau)) per packed ray, with autograd
+            palpha = ops.SumReduceFn.apply(pw.reshape(-1, 1), offsets)
+            for c in pan:
+                outputs[c] = self._integrate_features(out_feats[c], palpha, pw, offsets, N)
+        extra_outputs = {}
+        for channel in extra_channels:
+            feats = nef(coords=samples, ray_d=hit_ray_d, pidx=pidx, lod_idx=lod_idx, channels=channel)
+            extra_outputs[channel] = self._integrate_features(feats, alpha, w, offsets, N)
+        return RenderBuffer(**outputs, **extra_outputs)

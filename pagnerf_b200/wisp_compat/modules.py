@@ -70,7 +70,13 @@ def get_positional_embedder(frequencies, active, input_dim=3):
     return enc, enc.out_dim
 
 
+def _identity(x):
+    return x
+
+
 def get_activation_class(activation_type):
+    if activation_type == 'none':      # wisp: Identity() -- PanopticDDensityNeF's delta-density head (pc_nerf/panoptic_dd_nef.py:52)
+        return _identity
     if activation_type == 'relu':
         return torch.relu
     if activation_type == 'sin':

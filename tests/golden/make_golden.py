@@ -93,6 +93,9 @@ def golden_trace(name, nef_type, grid_type, raymarch_type, num_steps, level=4, N
     from pc_nerf.panoptic_nef import PanopticNeF
     from pc_nerf.panoptic_delta_nef import PanopticDeltaNeF
     from tracers.panoptic_packed_rf_tracer import PanopticPackedRFTracer
+    if nef_type == 'PanopticDDensityNeF':
+        from pc_nerf.panoptic_dd_nef import PanopticDDensityNeF
+        from tracers.panoptic_dd_packed_rf_tracer import PanopticDDensityPackedRFTracer
     from wisp.core import Rays
     import kaolin.ops.spc as spc_ops
 
@@ -103,11 +106,13 @@ def golden_trace(name, nef_type, grid_type, raymarch_type, num_steps, level=4, N
               activation_type='relu', layer_type='none', num_classes=6, num_instances=20,
               sem_num_layers=1, sem_hidden_dim=64, inst_num_layers=2, inst_hidden_dim=64,
               sem_softmax=True, inst_softmax=True, sem_detach=True, inst_detach=True,
-              panoptic_features_type='delta' if nef_type == 'PanopticDeltaNeF' else None,
+              panoptic_features_type='delta' if nef_type != 'PanopticNeF' else None,
               blas_level=level, coarsest_scale=1.0, finest_scale=0.01, capacity_log_2=10, delta_capacity_log_2=9,
               codebook_bitwidth=10, inst_direct_pos=False)
-    cls = PanopticDeltaNeF if nef_type == 'PanopticDeltaNeF' else PanopticNeF
+    cls = {'PanopticDeltaNeF': PanopticDeltaNeF, 'PanopticNeF': PanopticNeF}.get(nef_type) or PanopticDDensityNeF
     nef = cls(**kw)
+    if nef_type == 'PanopticDDensityNeF':
+        nef.inst_direct_pos = False  # same latent attribute as the base class; the DD override never reads it
     if nef_type == 'PanopticNeF':
         nef.inst_direct_pos = False  # never assigned by the reference ctor
     grids = [nef.grid] + ([nef.delta_grid] if hasattr(nef, 'delta_grid') else [])
@@ -129,8 +134,8 @@ def golden_trace(name, nef_type, grid_type, raymarch_type, num_steps, level=4, N
             g.blas.init(octree)
     with torch.no_grad():  # make the field reasonably opaque so that alpha is not ~0
         nef.decoder_density.lout.bias[0] = 6.0
-    tracer = PanopticPackedRFTracer(raymarch_type=raymarch_type, num_steps=num_steps, bg_color=bg_color,
-                                    ray_max_travel=ray_max_travel)
+    tcls = PanopticDDensityPackedRFTracer if nef_type == 'PanopticDDensityNeF' else PanopticPackedRFTracer
+    tracer = tcls(raymarch_type=raymarch_type, num_steps=num_steps, bg_color=bg_color, ray_max_travel=ray_max_travel)
     o, d = _rays(N)
     o_t = torch.from_numpy(o).requires_grad_(True)
     d_t = torch.from_numpy(d).requires_grad_(True)
@@ -163,3 +168,4 @@ if __name__ == "__main__":
     golden_trace("trace_delta_permuto_ray", "PanopticDeltaNeF", "PermutoGrid", "ray", 48)
     golden_trace("trace_delta_permuto_voxel", "PanopticDeltaNeF", "PermutoGrid", "voxel", 3, bg_color='black')
     golden_trace("trace_nef_tcnn_ray", "PanopticNeF", "HashGridTinyCudaNN", "ray", 32)
+    golden_trace("trace_dd_permuto_ray", "PanopticDDensityNeF", "PermutoGrid", "ray", 40)

@@ -309,7 +309,7 @@ def test_nef_channel_dispatch(cuda_lib):
 
 
 @pytest.mark.parametrize("name,mode", [("trace_delta_permuto_ray", "ray"), ("trace_delta_permuto_voxel", "voxel"),
-                                       ("trace_nef_tcnn_ray", "ray")])
+                                       ("trace_nef_tcnn_ray", "ray"), ("trace_dd_permuto_ray", "ray")])
 def test_trace_matches_reference_golden(cuda_lib, name, mode):
     """Full CUDA path (march -> encode -> decode -> composite, fwd + bwd) through the tracer plugin vs the outputs
     of the REFERENCE's tracer/nef source (golden).  Marcher integers are compared against the oracle marcher."""
@@ -317,6 +317,8 @@ def test_trace_matches_reference_golden(cuda_lib, name, mode):
     from pagnerf_b200.wisp_compat import Rays
     g = load_golden(name)
     nef = build_cuda_nef(g, DEV)
+    if name.startswith("trace_dd"):      # PanopticDDensityNeF + its tracer (own panoptic density stream)
+        from pagnerf_b200.tracers import PanopticDDensityPackedRFTracer as PanopticPackedRFTracer
     tracer = PanopticPackedRFTracer(raymarch_type=mode, num_steps=int(g["num_steps"]),
                                     bg_color='white' if bool(g["bg_white"]) else 'black',
                                     ray_max_travel=float(g["ray_max_travel"]))

@@ -27,7 +27,7 @@ def test_hashnerf_oracle_matches_reference_file():
 
 
 @pytest.mark.parametrize("name,mode", [("trace_delta_permuto_ray", "ray"), ("trace_delta_permuto_voxel", "voxel"),
-                                       ("trace_nef_tcnn_ray", "ray")])
+                                       ("trace_nef_tcnn_ray", "ray"), ("trace_dd_permuto_ray", "ray")])
 def test_trace_oracle_matches_reference_glue(name, mode):
     """oracle.field.trace_oracle == the reference's tracer + nef source run on the oracle-backed stubs."""
     from oracle.field import trace_oracle
@@ -41,7 +41,7 @@ def test_trace_oracle_matches_reference_glue(name, mode):
     samples = samples + (s_attached - s_attached.detach())
     chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
     out = trace_oracle(field, o, d, ridx, samples, depths, deltas, boundary, chans,
-                       bg_color='white' if bool(g["bg_white"]) else 'black')
+                       bg_color='white' if bool(g["bg_white"]) else 'black', dd=name.startswith("trace_dd"))
     for c in chans + ['alpha']:
         assert_close(out[c], g["out_" + c], rtol=1e-5, atol_scale=1e-6, msg=c)
     assert np.array_equal(out['hit'].numpy(), g["out_hit"])

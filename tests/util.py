@@ -49,9 +49,10 @@ def build_oracle_field(g):
         grid = TcnnHashGridOracle(c["L"], c["F"], c["codebook_bitwidth"], c["base_resolution"], 2.0, out_half=True)
         grid.load_state_dict({"params": p["grid.embedder.params"]})
         delta = None
+    dd = any(k.startswith("decoder_delta_density.") for k in p)
     f = FieldOracle(grid, delta, feat_dim=c["L"] * c["F"], hidden_dim=c["hidden"], num_classes=c["num_classes"],
-                    num_instances=c["num_instances"], view_multires=c["view_multires"])
-    for name in ("decoder_density", "decoder_color", "decoder_semantics", "decoder_inst"):
+                    num_instances=c["num_instances"], view_multires=c["view_multires"], delta_density=dd)
+    for name in ("decoder_density", "decoder_color", "decoder_semantics", "decoder_inst") + (("decoder_delta_density",) if dd else ()):
         _load_decoder(getattr(f, name), p, name)
     return f
 
@@ -75,11 +76,12 @@ def oracle_march(g, raymarch_type):
 
 def build_cuda_nef(g, device):
     """Our plugin classes, loaded from the golden's state_dict (same keys as the reference's nef)."""
-    from pagnerf_b200.pc_nerf import PanopticDeltaNeF, PanopticNeF
+    from pagnerf_b200.pc_nerf import PanopticDeltaNeF, PanopticNeF, PanopticDDensityNeF
     c = GOLDEN_CFG
     p = golden_params(g)
     permuto = "grid.embedder.lattice_values" in p
     delta = "delta_grid.embedder.lattice_values" in p
+    dd = any(k.startswith("decoder_delta_density.") for k in p)
     kw = dict(grid_type="PermutoGrid" if permuto else "HashGridTinyCudaNN", interpolation_type='linear',
               multiscale_type='cat', feature_dim=c["F"], num_lods=c["L"], base_lod=2, hidden_dim=c["hidden"],
               num_layers=1, view_multires=c["view_multires"], pos_multires=4, embedder_type='positional',
@@ -89,7 +91,7 @@ def build_cuda_nef(g, device):
               panoptic_features_type='delta' if delta else None, blas_level=int(g["level"]),
               coarsest_scale=c["coarsest_scale"], finest_scale=c["finest_scale"], capacity_log_2=c["capacity_log_2"],
               delta_capacity_log_2=c["delta_capacity_log_2"], codebook_bitwidth=c["codebook_bitwidth"])
-    nef = (PanopticDeltaNeF if delta else PanopticNeF)(**kw)
+    nef = (PanopticDDensityNeF if dd else (PanopticDeltaNeF if delta else PanopticNeF))(**kw)
     grids = [nef.grid] + ([nef.delta_grid] if delta else [])
     for gr in grids:
         if permuto:
