@@ -103,6 +103,17 @@ int pag_permuto_fwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, i
 int pag_permuto_bwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
                         int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
                         const float* grad_out, float* grad_table, float* grad_pos, int n_agg_levels, void* stream);
+/* fp16 operand-image interchange with the tensor-core decoders (fused trace): features / feature gradients as tiles of 128
+ * samples, each [2L/8 chunks][128 rows][8 halfs] (the UMMA operand image, 12 KB for L = 24) -- one bulk copy per tile on the
+ * decoder side, coalesced 16-byte accesses on the encoder side, half the bytes.  img16 holds ceil(M_max/128) tiles; rows past the
+ * sample count in the last tile are zero-filled.  grad_img16 is still multiplied by the decoders' loss scale *img_scale. L % 4 == 0. */
+int pag_permuto_fwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
+                              int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
+                              void* img16, void* stream);
+int pag_permuto_bwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
+                              int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
+                              const void* grad_img16, const float* img_scale, float* grad_table, float* grad_pos, int n_agg_levels,
+                              void* stream);
 /* parity probe: lattice vertex hash indices u32[L,M,4], ranks i32[L,M,4], barycentric f32[L,M,4]. */
 int pag_permuto_indices(const float* pos, int64_t M, int64_t capacity, int L, const float* scale_factor,
                         const float* shift, uint32_t* idx, int32_t* rank, float* bary, void* stream);
@@ -156,11 +167,13 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
                          void* stream);
 int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, int hidden, int view_dim,
-                             int want_rgb, float* sigma, float* rgb, const void* view_pe16, void* stream);
+                             int want_rgb, float* sigma, float* rgb, const void* view_pe16, int feats_img16, void* stream);
 int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, float* const* grads, int hidden,
                              int view_dim, const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats,
-                             float* g_dir, const void* view_pe16, float* workspace, int64_t workspace_bytes, void* stream);
+                             float* g_dir, const void* view_pe16, float* workspace, int64_t workspace_bytes, int img16, void* stream);
+/* feats_img16 / img16 != 0: `feats` (and `g_feats`, then still multiplied by *grad_scale) are fp16 operand images, see
+ * pag_permuto_fwd_img16_dyn; IN % 8 == 0. */
 /* view_pe16 (nullable): per-ray fp16 view embedding [R][32] from pag_view_pe16 -- the decoders copy it instead of evaluating
  * the positional embedding per sample.  workspace (nullable, device, 16-byte aligned): see pag_pan_composite_bwd_tc. */
 int pag_view_pe16(const float* ray_d, int64_t R, void* pe16, void* stream);
@@ -182,13 +195,15 @@ int pag_decode_pan_bwd_tc(const float* feats, const float* dfeats, const float* 
 int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
                              float inst_temperature, const float* w, const float* alpha, const int64_t* ridx,
-                             float* out_sem, float* out_inst, float* inst_lse, const int64_t* m_dev, void* stream);
+                             float* out_sem, float* out_inst, float* inst_lse, const int64_t* m_dev, int x_img16, void* stream);
 int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, float* const* grads, int hidden, int Cs, int Ci,
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
                              const int64_t* ridx, int64_t R, const float* g_sem, const float* g_inst, const float* inst_lse,
                              const float* grad_scale, float* g_panop, const int64_t* m_dev, float* workspace,
-                             int64_t workspace_bytes, void* stream);
+                             int64_t workspace_bytes, int x_img16, void* stream);
+/* x_img16 != 0: feats / dfeats (and g_panop, then still multiplied by *grad_scale) are fp16 operand images, see
+ * pag_permuto_fwd_img16_dyn; IN % 8 == 0. */
 /* workspace (nullable, device): *bytes of pag_pan_composite_bwd_workspace(M, IN, Cs, Ci, &bytes), 16-byte aligned.  With it every CTA stores its
  * partial weight gradients privately and a second kernel sums them; without it they are accumulated with red.add. */
 int pag_pan_composite_bwd_workspace(int64_t M, int IN, int Cs, int Ci, int64_t* bytes /* host */);

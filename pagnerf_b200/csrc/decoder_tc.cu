@@ -30,12 +30,12 @@
 
 struct DcTcLayout {  // byte offsets inside dynamic smem
     int INP, nXc;
-    int oG3, oGy, oOnesA, oX, oHd, oOnesB, oCin, oH1, oOnesC, oH2, oWd1, oWd2, oWc1, oWc2, oWc3, oBias, oPF, oDX, total;
+    int oG3, oGy, oOnesA, oX, oHd, oOnesB, oCin, oH1, oOnesC, oH2, oWd1, oWd2, oWc1, oWc2, oWc3, oBias, oPF, oDX, oXI, total;
 };
 // Backward tile order: G3 Gy | onesA X | Hd onesB Cin | H1 onesC H2.  Each constant "ones" tile (feature 0 = 1) sits next
 // to the B operands of two weight-gradient chains, which therefore also produce the bias gradients:
 //   dWd1 = Gd^T [onesA | X]   dWd2 = Gy^T [Hd | onesB]   dWc1 = G1^T [onesB | Cin]   dWc2 = G2^T [H1 | onesC]   dWc3 = G3^T [onesC | H2]
-__host__ __device__ inline DcTcLayout dc_tc_layout(int IN, bool bwd) {
+__host__ __device__ inline DcTcLayout dc_tc_layout(int IN, bool bwd, bool img = false) {
     DcTcLayout l;
     l.INP = (IN + 15) & ~15;
     l.nXc = l.INP / 8;
@@ -58,8 +58,12 @@ __host__ __device__ inline DcTcLayout dc_tc_layout(int IN, bool bwd) {
     l.oBias = o; o += (64 + 16 + 64 + 64 + 16) * 4;
     if (bwd && o < l.oH2 + 16 * TCH) o = l.oH2 + 16 * TCH;  // MN-major A operands read 16 chunks from their base
     o = (o + 15) & ~15;
-    l.oPF = o; o += bwd ? 128 * (IN >> 2) * 16 : 0;          // cp.async slots of the next tile's inputs
-    l.oDX = o; o += bwd ? 128 * (IN + 4) * 4 : 0;            // dX tile staging (see dx_stage16)
+    l.oPF = o; o += (bwd && !img) ? 128 * (IN >> 2) * 16 : 0;   // cp.async slots of the next tile's inputs (f32 rows)
+    l.oDX = o; o += bwd ? (img ? l.nXc * TCH : 128 * (IN + 4) * 4) : 0;   // dX tile staging: fp16 image tile / padded f32 rows
+    // image mode: the input tile arrives by bulk copy straight into operand layout; two buffers (tile t+1 lands while tile t is
+    // processed), each preceded by its own ones tile in the backward (B operand of dWd1 = [ones | X])
+    o = (o + 127) & ~127;
+    l.oXI = o; o += img ? 2 * ((bwd ? 2 : 0) + l.nXc) * TCH : 0;
     l.total = o;
     return l;
 }
@@ -117,6 +121,9 @@ __global__ void view_pe16_kernel(const float* __restrict__ ray_d, int64_t R, __h
     }
 }
 
+// IMG: feats is the encoder's fp16 operand image (pag_permuto_fwd_img16_dyn): the input tile of a step is one 12 KB bulk copy
+// into a ping-pong buffer, issued a tile ahead by one elected thread, and consumed by the tensor core as it is.
+template <bool IMG>
 __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
                                                                const float* __restrict__ ray_d, int S, int64_t M, int IN,
                                                                DcParams p, int want_rgb, float* __restrict__ sigma,
@@ -125,12 +132,13 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
+    __shared__ uint64_t xbar_s[2];
     __shared__ uint32_t tmem_s;
-    const DcTcLayout l = dc_tc_layout(IN, false);
+    const DcTcLayout l = dc_tc_layout(IN, false, IMG);
     const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane, c16 = 16 * cg;
     dc_tc_stage(sm, l, p, IN, lodw);
-    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bar_s, 1); mbar_init(&xbar_s[0], 1); mbar_init(&xbar_s[1], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 128);
     sync_to_mma();
     tc_fence_after();
@@ -142,11 +150,19 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
     const uint32_t wd1 = smem_u32(sm + l.oWd1), wd2 = smem_u32(sm + l.oWd2), wc1 = smem_u32(sm + l.oWc1),
                    wc2 = smem_u32(sm + l.oWc2), wc3 = smem_u32(sm + l.oWc3);
     const int64_t ntiles = (M + 127) / 128;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t xbytes = (uint32_t)l.nXc * TCH;
+    const uint8_t* fimg = reinterpret_cast<const uint8_t*>(feats);
+    uint32_t xpar = 0;      // bit b = phase parity of xbar_s[b]
+    int xb = 0;
+    if (IMG && (int64_t)blockIdx.x < ntiles && warp == 0 && elect_one()) {
+        mbar_expect_tx(&xbar_s[0], xbytes);
+        bulk_g2s(sm + l.oXI, fimg + (size_t)blockIdx.x * xbytes, xbytes, &xbar_s[0]);
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, xb ^= 1) {
         const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
-        stage_x_coalesced(T0, feats, nullptr, IN, l.INP, tile * 128, M);
+        if (!IMG) stage_x_coalesced(T0, feats, nullptr, IN, l.INP, tile * 128, M);
         // view embedding of this row's ray: issued now, consumed two MMA phases later
         uint4 pa = make_uint4(0u, 0u, 0u, 0u), pb = pa;
         int64_t r = 0;
@@ -154,9 +170,22 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
             r = ridx ? ridx[mm] : mm / S;
             if (pe16) { pa = __ldg(pe16 + r * 4 + 2 * (cg - 1)); pb = __ldg(pe16 + r * 4 + 2 * (cg - 1) + 1); }
         }
+        if (IMG) {
+            // the other buffer was last read by the first MMA of the previous tile (completed): the next tile may land there
+            if (tile + gridDim.x < ntiles && warp == 0 && elect_one()) {
+                mbar_expect_tx(&xbar_s[xb ^ 1], xbytes);
+                bulk_g2s(sm + l.oXI + (xb ^ 1) * xbytes, fimg + (size_t)(tile + gridDim.x) * xbytes, xbytes, &xbar_s[xb ^ 1]);
+            }
+            mbar_wait(&xbar_s[xb], (xpar >> xb) & 1u);
+            xpar ^= 1u << xb;
+        }
         sync_to_mma();
-        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aT0, wd1, 64, 64, l.INP, false); mb.commit(); }
-        if (tile + gridDim.x < ntiles) prefetch_x_l2(feats, nullptr, IN, l.nXc, min((tile + gridDim.x) * 128 + row, M - 1), cg, DC_NCG);
+        if (warp == 0 && elect_one()) {
+            tc_fence_after();
+            mma16_fwd(tm, IMG ? smem_u32(sm + l.oXI + xb * xbytes) : aT0, wd1, 64, 64, l.INP, false);
+            mb.commit();
+        }
+        if (!IMG && tile + gridDim.x < ntiles) prefetch_x_l2(feats, nullptr, IN, l.nXc, min((tile + gridDim.x) * 128 + row, M - 1), cg, DC_NCG);
         mb.wait();
         epi_relu16(tl + c16, bias + c16, T1 + 2 * cg * TCH, row);
         sync_to_mma();
@@ -225,6 +254,7 @@ __host__ __device__ inline DcWsLayout dc_ws_layout(int IN) {
     return w;
 }
 
+template <bool IMG>
 __global__ void __maxnreg__(96) dc_tc_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ lodw,
                                                                const float* __restrict__ ray_d, int S, int64_t M, int IN,
                                                                DcParams p, const float* __restrict__ g_sigma,
@@ -235,9 +265,10 @@ __global__ void __maxnreg__(96) dc_tc_bwd_kernel(const float* __restrict__ feats
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
+    __shared__ uint64_t xbar_s[2];
     __shared__ uint32_t tmem_s;
     __shared__ float gdir_s[2][128][3];   // view-direction gradient partials of column groups 1 and 2
-    const DcTcLayout l = dc_tc_layout(IN, true);
+    const DcTcLayout l = dc_tc_layout(IN, true, IMG);
     const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2, row = 32 * q + lane, c16 = 16 * cg;
     dc_tc_stage(sm, l, p, IN, lodw);
@@ -246,8 +277,9 @@ __global__ void __maxnreg__(96) dc_tc_bwd_kernel(const float* __restrict__ feats
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
         if (j < TCH / 16) u.x = 0x00003C00u;
         reinterpret_cast<uint4*>(sm + (t == 0 ? l.oOnesA : (t == 1 ? l.oOnesB : l.oOnesC)))[j] = u;
+        if (IMG && t < 2) reinterpret_cast<uint4*>(sm + l.oXI + t * (2 + l.nXc) * TCH)[j] = u;    // ones tile in front of each input buffer
     }
-    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bar_s, 1); mbar_init(&xbar_s[0], 1); mbar_init(&xbar_s[1], 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 512);
     sync_to_mma();
     tc_fence_after();
@@ -265,19 +297,42 @@ __global__ void __maxnreg__(96) dc_tc_bwd_kernel(const float* __restrict__ feats
     const float inv_scale = 1.f / scale;
     const bool do_rgb = g_rgb != nullptr;
     const int64_t ntiles = (M + 127) / 128;
-    if ((int64_t)blockIdx.x < ntiles) xpfc_issue<DC_MAXK>(pf, feats, nullptr, IN, (int64_t)blockIdx.x * 128, M);
-    cp_async_wait_all();
+    const uint32_t xbytes = (uint32_t)l.nXc * TCH, xstride = (uint32_t)(2 + l.nXc) * TCH;
+    const uint8_t* fimg = reinterpret_cast<const uint8_t*>(feats);
+    uint32_t xpar = 0;
+    int xb = 0;
+    if (IMG) {
+        if ((int64_t)blockIdx.x < ntiles && warp == 0 && elect_one()) {
+            mbar_expect_tx(&xbar_s[0], xbytes);
+            bulk_g2s(sm + l.oXI + 2 * TCH, fimg + (size_t)blockIdx.x * xbytes, xbytes, &xbar_s[0]);
+        }
+    } else {
+        if ((int64_t)blockIdx.x < ntiles) xpfc_issue<DC_MAXK>(pf, feats, nullptr, IN, (int64_t)blockIdx.x * 128, M);
+        cp_async_wait_all();
+    }
     __syncthreads();
     bool first = true;
     float* dxs = reinterpret_cast<float*>(sm + l.oDX);
     int64_t dx_tile = -1;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false, xb ^= 1) {
         const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
-        if (g_feats && dx_tile >= 0) dx_copy_out(dxs, g_feats, IN, dx_tile * 128, M);      // previous tile's dX
-        // ---------------- forward recompute ----------------
-        xpfc_consume<DC_NCG, DC_MAXK>(pf, false, IN, l.INP, X, row, cg);
+        const uint32_t aXt = IMG ? smem_u32(sm + l.oXI + xb * xstride + 2 * TCH) : aX;      // this tile's input operand
+        const uint32_t aOnesXt = IMG ? smem_u32(sm + l.oXI + xb * xstride) : aOnesA;        // ... and the ones tile in front of it
+        if (IMG) {
+            if (g_feats && dx_tile >= 0 && warp == 0 && elect_one()) bulk_wait_read_all();   // staging tile free again (stored last tile)
+            if (tile + gridDim.x < ntiles && warp == 0 && elect_one()) {      // the other buffer's MMAs (previous tile) have completed
+                mbar_expect_tx(&xbar_s[xb ^ 1], xbytes);
+                bulk_g2s(sm + l.oXI + (xb ^ 1) * xstride + 2 * TCH, fimg + (size_t)(tile + gridDim.x) * xbytes, xbytes, &xbar_s[xb ^ 1]);
+            }
+            mbar_wait(&xbar_s[xb], (xpar >> xb) & 1u);
+            xpar ^= 1u << xb;
+        } else {
+            if (g_feats && dx_tile >= 0) dx_copy_out(dxs, g_feats, IN, dx_tile * 128, M);      // previous tile's dX
+            // ---------------- forward recompute ----------------
+            xpfc_consume<DC_NCG, DC_MAXK>(pf, false, IN, l.INP, X, row, cg);
+        }
         // this row's upstream gradients / view embedding: issued now, consumed several MMA phases later
         float gs_row = 0.f, gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
         uint4 pa = make_uint4(0u, 0u, 0u, 0u), pb = pa;
@@ -290,8 +345,8 @@ __global__ void __maxnreg__(96) dc_tc_bwd_kernel(const float* __restrict__ feats
             if (pe16) { pa = __ldg(pe16 + r * 4 + 2 * (cg - 1)); pb = __ldg(pe16 + r * 4 + 2 * (cg - 1) + 1); }
         }
         sync_to_mma();
-        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aX, wd1, 64, 64, l.INP, false); mb.commit(); }
-        if (tile + gridDim.x < ntiles)      // every thread is past its slot reads: the next tile's inputs stream in from here
+        if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm + DCB_S0, aXt, wd1, 64, 64, l.INP, false); mb.commit(); }
+        if (!IMG && tile + gridDim.x < ntiles)      // every thread is past its slot reads: the next tile's inputs stream in from here
             xpfc_issue<DC_MAXK>(pf, feats, nullptr, IN, (tile + gridDim.x) * 128, M);
         mb.wait();
         const uint32_t mask_d = epi_relu16(tl + DCB_S0 + c16, bias + c16, Hd + 2 * cg * TCH, row);
@@ -418,18 +473,36 @@ __global__ void __maxnreg__(96) dc_tc_bwd_kernel(const float* __restrict__ feats
         sync_to_mma();
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            mma16_bwd_weight(tm + DCB_DWD1, aHd, aOnesA, 16 + l.INP, !first);   // B = ones | X
+            mma16_bwd_weight(tm + DCB_DWD1, aHd, aOnesXt, 16 + l.INP, !first);  // B = ones | X
             if (g_feats) mma16_bwd_data(tm + DCB_S1, aHd, wd1, l.INP, 64, 64, false);
             mb.commit();
         }
         mb.wait();
-        if (g_feats && c16 < l.INP) dx_stage16(tl + DCB_S1, dxs, row, IN, c16, inv_scale);   // W1 carries the LOD weights; written out next tile
-        dx_tile = tile;
-        cp_async_wait_all();      // own copies landed; the barrier publishes everybody's
-        tc_fence_before();
-        __syncthreads();
+        if (IMG) {
+            // dX leaves as an fp16 operand-image tile, still multiplied by the loss scale (the encoder backward unscales): staged
+            // in shared memory in image order, then ONE bulk store of the 12 KB tile by an elected thread
+            if (g_feats && c16 < l.INP) {
+                float v[16];
+                tmem_ld16(tl + DCB_S1 + c16, v);
+                tile_store8(sm + l.oDX, 2 * cg, row, v);
+                tile_store8(sm + l.oDX, 2 * cg + 1, row, v + 8);
+                fence_async_smem();
+            }
+            dx_tile = tile;
+            tc_fence_before();
+            __syncthreads();
+            if (g_feats && warp == 0 && elect_one()) bulk_s2g(reinterpret_cast<uint8_t*>(g_feats) + (size_t)tile * xbytes, sm + l.oDX, xbytes);
+        } else {
+            if (g_feats && c16 < l.INP) dx_stage16(tl + DCB_S1, dxs, row, IN, c16, inv_scale);   // W1 carries the LOD weights; written out next tile
+            dx_tile = tile;
+            cp_async_wait_all();      // own copies landed; the barrier publishes everybody's
+            tc_fence_before();
+            __syncthreads();
+        }
     }
-    if (g_feats && dx_tile >= 0) dx_copy_out(dxs, g_feats, IN, dx_tile * 128, M);
+    if (IMG) {
+        if (g_feats && dx_tile >= 0 && warp == 0 && elect_one()) bulk_wait_read_all();
+    } else if (g_feats && dx_tile >= 0) dx_copy_out(dxs, g_feats, IN, dx_tile * 128, M);
     // ---------------- flush weight / bias gradients (once per CTA) ----------------
     if (!first) {
         tc_fence_after();
@@ -823,11 +896,11 @@ int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray
     DcParams p{};
     fill_dc(p, weights, nullptr);
     const DcTcLayout l = dc_tc_layout(IN, false);
-    int rc = tc_set_smem(dc_tc_fwd_kernel, l.total);
+    int rc = tc_set_smem(dc_tc_fwd_kernel<false>, l.total);
     if (rc) return rc;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = 2 * (int64_t)tc_num_sms();
-    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb, nullptr, nullptr, nullptr);
+    dc_tc_fwd_kernel<false><<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb, nullptr, nullptr, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -835,17 +908,26 @@ int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray
 // device-side sample count (m_dev[0] <= M_max) and per-sample ray index: sample m uses ray_d[ridx[m]]
 int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, int hidden, int view_dim,
-                             int want_rgb, float* sigma, float* rgb, const void* view_pe16, void* stream) {
+                             int want_rgb, float* sigma, float* rgb, const void* view_pe16, int feats_img16, void* stream) {
     if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
+    if (feats_img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     DcParams p{};
     fill_dc(p, weights, nullptr);
-    const DcTcLayout l = dc_tc_layout(IN, false);
-    int rc = tc_set_smem(dc_tc_fwd_kernel, l.total);
-    if (rc) return rc;
+    const DcTcLayout l = dc_tc_layout(IN, false, feats_img16 != 0);
     const int64_t tiles = (M_max + 127) / 128;
     const int64_t cap = 2 * (int64_t)tc_num_sms();
-    dc_tc_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx, reinterpret_cast<const uint4*>(view_pe16));
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    const uint4* pe = reinterpret_cast<const uint4*>(view_pe16);
+    if (feats_img16) {
+        int rc = tc_set_smem(dc_tc_fwd_kernel<true>, l.total);
+        if (rc) return rc;
+        dc_tc_fwd_kernel<true><<<grid, DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx, pe);
+    } else {
+        int rc = tc_set_smem(dc_tc_fwd_kernel<false>, l.total);
+        if (rc) return rc;
+        dc_tc_fwd_kernel<false><<<grid, DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx, pe);
+    }
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -860,11 +942,11 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
     DcParams p{};
     fill_dc(p, weights, grads);
     const DcTcLayout l = dc_tc_layout(IN, true);
-    int rc = tc_set_smem(dc_tc_bwd_kernel, l.total);
+    int rc = tc_set_smem(dc_tc_bwd_kernel<false>, l.total);
     if (rc) return rc;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = tc_num_sms();
-    dc_tc_bwd_kernel<<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(
+    dc_tc_bwd_kernel<false><<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(
         feats, lodw, ray_d, S, M, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, nullptr, nullptr, nullptr, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
@@ -873,21 +955,31 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
 int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, float* const* grads, int hidden,
                              int view_dim, const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats,
-                             float* g_dir, const void* view_pe16, float* workspace, int64_t workspace_bytes, void* stream) {
+                             float* g_dir, const void* view_pe16, float* workspace, int64_t workspace_bytes, int img16,
+                             void* stream) {
     if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
+    if (img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     DcParams p{};
     fill_dc(p, weights, grads);
-    const DcTcLayout l = dc_tc_layout(IN, true);
-    int rc = tc_set_smem(dc_tc_bwd_kernel, l.total);
-    if (rc) return rc;
+    const DcTcLayout l = dc_tc_layout(IN, true, img16 != 0);
     const int64_t tiles = (M_max + 127) / 128;
     const int64_t cap = tc_num_sms();
     const int nblocks = (int)(tiles < cap ? tiles : cap);
     const DcWsLayout wl = dc_ws_layout(IN);
     float* ws = (workspace && workspace_bytes >= (int64_t)nblocks * wl.total * 4 && !(reinterpret_cast<uintptr_t>(workspace) & 15)) ? workspace : nullptr;
-    dc_tc_bwd_kernel<<<nblocks, DC_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, lodw, ray_d, 1, M_max, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, m_dev, ridx, reinterpret_cast<const uint4*>(view_pe16), ws);
+    const uint4* pe = reinterpret_cast<const uint4*>(view_pe16);
+    if (img16) {
+        int rc = tc_set_smem(dc_tc_bwd_kernel<true>, l.total);
+        if (rc) return rc;
+        dc_tc_bwd_kernel<true><<<nblocks, DC_THREADS, l.total, (cudaStream_t)stream>>>(
+            feats, lodw, ray_d, 1, M_max, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, m_dev, ridx, pe, ws);
+    } else {
+        int rc = tc_set_smem(dc_tc_bwd_kernel<false>, l.total);
+        if (rc) return rc;
+        dc_tc_bwd_kernel<false><<<nblocks, DC_THREADS, l.total, (cudaStream_t)stream>>>(
+            feats, lodw, ray_d, 1, M_max, IN, p, g_sigma, g_rgb, grad_scale, g_feats, g_dir, m_dev, ridx, pe, ws);
+    }
     PAG_LAUNCH_CHECK();
     if (ws) {
         const bool rgb = g_rgb != nullptr;

@@ -388,6 +388,22 @@ __device__ __forceinline__ void stage_x_coalesced(uint8_t* tile, const float* __
     }
 }
 
+// X (fp16 operand image tile, `bytes` long) += D, or X = A + D when A is given: the panoptic heads read feats + delta feats
+// (pc_nerf/panoptic_delta_nef.py:226, a half-precision add under the reference's autocast as well)
+__device__ __forceinline__ void tile_add16(uint8_t* X, const uint8_t* A, const uint8_t* D, int bytes) {
+    for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) {
+        uint4 a = reinterpret_cast<const uint4*>(A ? A : X)[i];
+        if (D) {
+            const uint4 d = reinterpret_cast<const uint4*>(D)[i];
+            __half2* ah = reinterpret_cast<__half2*>(&a);
+            const __half2* dh = reinterpret_cast<const __half2*>(&d);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ah[k] = __hadd2(ah[k], dh[k]);
+        }
+        reinterpret_cast<uint4*>(X)[i] = a;
+    }
+}
+
 // ---- dX tile -> global through shared memory ------------------------------------------------------------------------
 // A lane-per-row float4 store touches 32 lines per warp instruction: the 48 store instructions of a 128 x 48 dX tile keep
 // the LSU busy for ~1.5 k cycles and everything queued behind them (the next tile's shared-memory traffic) waits.  The tile

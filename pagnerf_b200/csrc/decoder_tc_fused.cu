@@ -90,6 +90,8 @@ __device__ __forceinline__ void comp_block(const __half* stage, const float* __r
     }
 }
 
+// IMG: feats / dfeats are the encoders' fp16 operand images (one 12 KB bulk copy per tile each), see pag_permuto_fwd_img16_dyn
+template <bool IMG>
 __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
     const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw, int64_t M, int IN,
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
+    __shared__ uint64_t xbar_s;
     __shared__ uint32_t tmem_s;
     __shared__ float part_s[PCF_NCG][128][2];   // (max, sum) partials of the row softmax per column group
     const PanCompFwdLayout l = pan_comp_fwd_layout(IN, Cs, Ci);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
             stage_bi3_scaled(b + 192 + l.CsP, p.bi3, Ci, l.CiP, s2, inst_softmax);
         }
     }
-    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bar_s, 1); mbar_init(&xbar_s, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 256);
     sync_to_mma();
     tc_fence_after();
@@ -138,13 +141,27 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
     int* wr = reinterpret_cast<int*>(wc + 32);
     const int c16 = 16 * cg;
     const int64_t ntiles = (M + 127) / 128;
+    uint32_t xpar = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t m = tile * 128 + row;
         const bool valid = m < M;
         const int64_t mm = valid ? m : M - 1;
-        stage_x_coalesced(X, feats, dfeats, IN, l.INP, tile * 128, M);   // LOD weights are folded into the first-layer weights
-        if (tile + gridDim.x < ntiles)
-            prefetch_x_l2(feats, dfeats, IN, l.nXc, min((tile + gridDim.x) * 128 + row, M - 1), cg, PCF_NCG);
+        if (IMG) {
+            // feats tile -> X, delta tile -> T1 (idle until the first epilogue), then X += delta in place
+            const uint32_t xbytes = (uint32_t)l.nXc * TCH;
+            if (warp == 0 && elect_one()) {
+                mbar_expect_tx(&xbar_s, dfeats ? 2 * xbytes : xbytes);
+                bulk_g2s(X, reinterpret_cast<const uint8_t*>(feats) + (size_t)tile * xbytes, xbytes, &xbar_s);
+                if (dfeats) bulk_g2s(T1, reinterpret_cast<const uint8_t*>(dfeats) + (size_t)tile * xbytes, xbytes, &xbar_s);
+            }
+            mbar_wait(&xbar_s, xpar);
+            xpar ^= 1u;
+            if (dfeats) tile_add16(X, nullptr, T1, (int)xbytes);
+        } else {
+            stage_x_coalesced(X, feats, dfeats, IN, l.INP, tile * 128, M);   // LOD weights are folded into the first-layer weights
+            if (tile + gridDim.x < ntiles)
+                prefetch_x_l2(feats, dfeats, IN, l.nXc, min((tile + gridDim.x) * 128 + row, M - 1), cg, PCF_NCG);
+        }
         if (cg == 0) {   // compositing coefficients of this quadrant's rows
             const int64_t ray = ridx[mm];
             wr[lane] = (int)ray;
@@ -387,6 +404,7 @@ __device__ __forceinline__ void load_g16(const __half* __restrict__ gc_row, cons
     }
 }
 
+template <bool IMG>
 __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw, int64_t M, int IN,
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
@@ -396,6 +414,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
+    __shared__ uint64_t xbar_s;
     __shared__ uint32_t tmem_s;
     __shared__ float part_s[PCB_NCG][128];      // per column group: partial <p, g> of the row
     const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci);
@@ -431,7 +450,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         if (!do_sem) for (int i = tid; i < 8 * TCH / 16; i += PCB_THREADS) reinterpret_cast<uint4*>(Hs)[i] = make_uint4(0u, 0u, 0u, 0u);
         if (!do_inst) for (int i = tid; i < 8 * TCH / 16; i += PCB_THREADS) reinterpret_cast<uint4*>(H1)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (tid == 0) { mbar_init(&bar_s, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bar_s, 1); mbar_init(&xbar_s, 1); fence_mbar_init(); }
     if (warp == 0) tmem_alloc(&tmem_s, 512);
     sync_to_mma();
     tc_fence_after();
@@ -452,9 +471,22 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     float4* pf = reinterpret_cast<float4*>(sm + l.oPF);
     int64_t n_ray = 0, n_ray0 = 0;
     float n_w = 0.f, n_lse = 0.f;
+    // image mode: the landing buffers of the bulk copies (feats tile, delta tile) live where the cp.async slots are
+    const uint32_t xbytes = (uint32_t)l.nXc * TCH;
+    uint8_t *XL = sm + l.oPF, *DL = sm + l.oPF + xbytes;
+    const uint8_t *fimg = reinterpret_cast<const uint8_t*>(feats), *dimg = reinterpret_cast<const uint8_t*>(dfeats);
+    uint32_t xpar = 0;
     if ((int64_t)blockIdx.x < ntiles) {
         const int64_t m0 = min((int64_t)blockIdx.x * 128 + row, M - 1);
-        xpfc_issue<PCB_MAXK>(pf, feats, dfeats, IN, (int64_t)blockIdx.x * 128, M);
+        if (IMG) {
+            if (warp == 0 && elect_one()) {
+                mbar_expect_tx(&xbar_s, dimg ? 2 * xbytes : xbytes);
+                bulk_g2s(XL, fimg + (size_t)blockIdx.x * xbytes, xbytes, &xbar_s);
+                if (dimg) bulk_g2s(DL, dimg + (size_t)blockIdx.x * xbytes, xbytes, &xbar_s);
+            }
+        } else {
+            xpfc_issue<PCB_MAXK>(pf, feats, dfeats, IN, (int64_t)blockIdx.x * 128, M);
+        }
         n_ray = ridx[m0]; n_w = __ldg(w + m0); n_ray0 = ridx[(int64_t)blockIdx.x * 128];
         if (inst_lse) n_lse = __ldg(inst_lse + m0);
     }
@@ -466,7 +498,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     float* dxs = reinterpret_cast<float*>(Hs);
     int64_t dx_tile = -1;
     PAG_PHASE_INIT();
-    cp_async_wait_all();
+    if (!IMG) cp_async_wait_all();
     __syncthreads();
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
         const int64_t m = tile * 128 + row;
@@ -476,10 +508,18 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         const int64_t ray = n_ray, ray0 = n_ray0;
         const float w_row = n_w, lse_row = n_lse;
         const float a_row = __ldg(alpha + ray);
-        if (g_panop && dx_tile >= 0) dx_copy_out(dxs, g_panop, IN, dx_tile * 128, M);      // previous tile's dX
-        PAG_PHASE(0);
-        // ---------------- stage 1 ----------------
-        xpfc_consume<PCB_NCG, PCB_MAXK>(pf, dfeats != nullptr, IN, l.INP, X, row, cg);   // LOD weights live in W1
+        if (IMG) {
+            if (g_panop && dx_tile >= 0 && warp == 0 && elect_one()) bulk_wait_read_all();    // dX staging (Hs) stored: free again
+            PAG_PHASE(0);
+            mbar_wait(&xbar_s, xpar);
+            xpar ^= 1u;
+            tile_add16(X, XL, dimg ? DL : nullptr, (int)xbytes);       // X = feats + delta (fp16), LOD weights live in W1
+        } else {
+            if (g_panop && dx_tile >= 0) dx_copy_out(dxs, g_panop, IN, dx_tile * 128, M);      // previous tile's dX
+            PAG_PHASE(0);
+            // ---------------- stage 1 ----------------
+            xpfc_consume<PCB_NCG, PCB_MAXK>(pf, dfeats != nullptr, IN, l.INP, X, row, cg);   // LOD weights live in W1
+        }
         PAG_PHASE(1);
         {   // row scalars of the next tile into registers
             const int64_t tn = tile + gridDim.x;
@@ -496,8 +536,17 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             mb.commit();
         }
         PAG_PHASE(17);
-        if (tile + gridDim.x < ntiles)     // every thread is past its slot reads: the next tile's inputs stream in from here
-            xpfc_issue<PCB_MAXK>(pf, feats, dfeats, IN, (tile + gridDim.x) * 128, M);
+        if (tile + gridDim.x < ntiles) {     // every thread is past its slot / landing-buffer reads: the next tile streams in from here
+            if (IMG) {
+                if (warp == 0 && elect_one()) {
+                    mbar_expect_tx(&xbar_s, dimg ? 2 * xbytes : xbytes);
+                    bulk_g2s(XL, fimg + (size_t)(tile + gridDim.x) * xbytes, xbytes, &xbar_s);
+                    if (dimg) bulk_g2s(DL, dimg + (size_t)(tile + gridDim.x) * xbytes, xbytes, &xbar_s);
+                }
+            } else {
+                xpfc_issue<PCB_MAXK>(pf, feats, dfeats, IN, (tile + gridDim.x) * 128, M);
+            }
+        }
         PAG_PHASE(18);
         // while the MMAs run: the tile's per-ray output gradients (first PCB_NGC rays) -> registers, coalesced
         float gpre[7];
@@ -652,13 +701,30 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
             mb.commit();
         }
         mb.wait(); PAG_PHASE(14);
-        if (g_panop && c16 < l.INP) dx_stage16(tl + PCB_S0, dxs, row, IN, c16, inv_scale);   // written out at the top of the next tile
-        dx_tile = tile;
-        cp_async_wait_all();      // own copies landed; the barrier publishes everybody's
-        tc_fence_before();
-        __syncthreads(); PAG_PHASE(15);
+        if (IMG) {
+            // dX as an fp16 operand-image tile (still carrying the loss scale), staged over Hs, stored with one bulk copy
+            if (g_panop && c16 < l.INP) {
+                float v[16];
+                tmem_ld16(tl + PCB_S0 + c16, v);
+                tile_store8(Hs, 2 * cg, row, v);
+                tile_store8(Hs, 2 * cg + 1, row, v + 8);
+                fence_async_smem();
+            }
+            dx_tile = tile;
+            tc_fence_before();
+            __syncthreads(); PAG_PHASE(15);
+            if (g_panop && warp == 0 && elect_one()) bulk_s2g(reinterpret_cast<uint8_t*>(g_panop) + (size_t)tile * xbytes, Hs, xbytes);
+        } else {
+            if (g_panop && c16 < l.INP) dx_stage16(tl + PCB_S0, dxs, row, IN, c16, inv_scale);   // written out at the top of the next tile
+            dx_tile = tile;
+            cp_async_wait_all();      // own copies landed; the barrier publishes everybody's
+            tc_fence_before();
+            __syncthreads(); PAG_PHASE(15);
+        }
     }
-    if (g_panop && dx_tile >= 0) dx_copy_out(dxs, g_panop, IN, dx_tile * 128, M);
+    if (IMG) {
+        if (g_panop && dx_tile >= 0 && warp == 0 && elect_one()) bulk_wait_read_all();
+    } else if (g_panop && dx_tile >= 0) dx_copy_out(dxs, g_panop, IN, dx_tile * 128, M);
     if (!first) {
         tc_fence_after();
         const int f1 = scatter_base(lane, 32) >> 1;     // feature (of 16) owned by this lane pair after grad16_store
@@ -751,20 +817,29 @@ extern "C" {
 int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
                              const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
                              float inst_temperature, const float* w, const float* alpha, const int64_t* ridx,
-                             float* out_sem, float* out_inst, float* inst_lse, const int64_t* m_dev, void* stream) {
+                             float* out_sem, float* out_inst, float* inst_lse, const int64_t* m_dev, int x_img16, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
+    if (x_img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
     PanParams p{};
     fill_pan_f(p, weights, nullptr);
     const PanCompFwdLayout l = pan_comp_fwd_layout(IN, Cs, Ci);
     if (l.total > 227 * 1024) return PAG_ERR_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(pan_comp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
-    if (e != cudaSuccess) return (int)e;
     const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
     const int64_t tiles = (M + 127) / 128;
-    const int64_t cap = 2 * (int64_t)fused_num_sms();   // 109 KB smem + 256 TMEM columns per CTA: two CTAs per SM
-    pan_comp_fwd_kernel<<<(int)(tiles < cap ? tiles : cap), PCF_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, out_sem, out_inst, inst_lse, m_dev);
+    const int64_t cap = 2 * (int64_t)fused_num_sms();   // 97 KB smem + 256 TMEM columns per CTA: two CTAs per SM
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    if (x_img16) {
+        cudaError_t e = cudaFuncSetAttribute(pan_comp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
+        if (e != cudaSuccess) return (int)e;
+        pan_comp_fwd_kernel<true><<<grid, PCF_THREADS, l.total, (cudaStream_t)stream>>>(
+            feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, out_sem, out_inst, inst_lse, m_dev);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(pan_comp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
+        if (e != cudaSuccess) return (int)e;
+        pan_comp_fwd_kernel<false><<<grid, PCF_THREADS, l.total, (cudaStream_t)stream>>>(
+            feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, out_sem, out_inst, inst_lse, m_dev);
+    }
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -775,7 +850,7 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
                              const int64_t* ridx, int64_t R, const float* g_sem, const float* g_inst, const float* inst_lse,
                              const float* grad_scale, float* g_panop, const int64_t* m_dev, float* workspace,
-                             int64_t workspace_bytes, void* stream) {
+                             int64_t workspace_bytes, int x_img16, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
     if (Ci > 0 && g_inst && inst_softmax && !inst_lse) return PAG_ERR_ARG;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
@@ -783,16 +858,24 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
     fill_pan_f(p, weights, grads);
     const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci);
     if (l.total > 227 * 1024) return PAG_ERR_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(pan_comp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
-    if (e != cudaSuccess) return (int)e;
+    if (x_img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
     const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = fused_num_sms();
     const int nblocks = (int)(tiles < cap ? tiles : cap);
     const PanWsLayout wl = pan_ws_layout(IN, Cs, Ci);
     float* ws = (workspace && workspace_bytes >= (int64_t)nblocks * wl.total * 4 && !(reinterpret_cast<uintptr_t>(workspace) & 15)) ? workspace : nullptr;
-    pan_comp_bwd_kernel<<<nblocks, PCB_THREADS, l.total, (cudaStream_t)stream>>>(
-        feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev, ws);
+    if (x_img16) {
+        cudaError_t e2 = cudaFuncSetAttribute(pan_comp_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
+        if (e2 != cudaSuccess) return (int)e2;
+        pan_comp_bwd_kernel<true><<<nblocks, PCB_THREADS, l.total, (cudaStream_t)stream>>>(
+            feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev, ws);
+    } else {
+        cudaError_t e2 = cudaFuncSetAttribute(pan_comp_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
+        if (e2 != cudaSuccess) return (int)e2;
+        pan_comp_bwd_kernel<false><<<nblocks, PCB_THREADS, l.total, (cudaStream_t)stream>>>(
+            feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev, ws);
+    }
     PAG_LAUNCH_CHECK();
     if (ws) {
         const bool ds = Cs > 0 && g_sem, di = Ci > 0 && g_inst;

@@ -88,18 +88,35 @@ __device__ __forceinline__ void permuto_lattice(float p0, float p1, float p2, co
     }
 }
 
+// IMG16: features go out as the decoders' fp16 operand image instead of f32[M, 2L]: tile t = m / 128 holds
+// [2L/8 chunks][128 rows][8 halfs] (12 KB for L = 24), so that a decoder CTA fetches its whole input tile with one bulk copy
+// and feeds it to tcgen05.mma unchanged.  Four levels (8 features) are packed per 16-byte store and consecutive lanes write
+// consecutive rows: fully coalesced (the f32 row-major layout makes every float2 store its own sector).  Rows between M and
+// the end of the last tile are zero-filled (the tensor core reads whole tiles).  Matches the reference's autocast, where the
+// encoder output is half (grids/permuto_grid.py:65 custom_fwd(cast_inputs=torch.half)).
+template <bool IMG16>
 __global__ void __launch_bounds__(128) permuto_fwd_kernel(
     const float* __restrict__ pos, int64_t M, const float* __restrict__ table, uint32_t cap, uint32_t cap_mask, int L,
     const float* __restrict__ sf, const float* __restrict__ sh, const float* __restrict__ anneal,
     float* __restrict__ out, const int64_t* __restrict__ m_dev, int pos_half) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m_dev) M = min(M, __ldg(m_dev));   // packed-sample count produced on the device by the marcher
-    if (m >= M) return;
+    uint4* img = nullptr;
+    if (IMG16) {
+        const int64_t Mpad = (M + 127) & ~(int64_t)127;
+        if (m >= Mpad) return;
+        img = reinterpret_cast<uint4*>(out) + ((m >> 7) * (L >> 2)) * 128 + (m & 127);    // chunk c at img[c * 128]
+        if (m >= M) {
+            for (int c = 0; c < (L >> 2); ++c) img[c * 128] = make_uint4(0u, 0u, 0u, 0u);
+            return;
+        }
+    } else if (m >= M) return;
     float p0 = pos[3 * m], p1 = pos[3 * m + 1], p2 = pos[3 * m + 2];
     if (pos_half) {   // autocast: custom_fwd(cast_inputs=torch.half) then .float() (grids/permuto_grid.py:65,71)
         p0 = __half2float(__float2half_rn(p0)); p1 = __half2float(__float2half_rn(p1)); p2 = __half2float(__float2half_rn(p2));
     }
     float2* orow = reinterpret_cast<float2*>(out + m * (int64_t)(2 * L));
+    uint32_t pk[4];
 #pragma unroll 4
     for (int l = 0; l < L; ++l) {
         PermutoVertex v;
@@ -113,7 +130,13 @@ __global__ void __launch_bounds__(128) permuto_fwd_kernel(
         float2 acc;
         acc.x = (a.x * v.bary[0] + b.x * v.bary[1] + c.x * v.bary[2] + d.x * v.bary[3]) * w;
         acc.y = (a.y * v.bary[0] + b.y * v.bary[1] + c.y * v.bary[2] + d.y * v.bary[3]) * w;
-        orow[l] = acc;
+        if (IMG16) {
+            const __half2 h = __floats2half2_rn(acc.x, acc.y);
+            pk[l & 3] = *reinterpret_cast<const uint32_t*>(&h);
+            if ((l & 3) == 3) img[(l >> 2) * 128] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else {
+            orow[l] = acc;
+        }
     }
 }
 
@@ -135,12 +158,14 @@ __global__ void permuto_indices_kernel(const float* __restrict__ pos, int64_t M,
     }
 }
 
-template <bool POS_GRAD>
+// GIMG: the upstream gradient arrives as the decoders' fp16 tile image (see permuto_fwd_kernel), still multiplied by the
+// power-of-two loss scale the tensor-core backward used; *img_scale is that scale (coalesced 16-byte reads, half the bytes).
+template <bool POS_GRAD, bool GIMG>
 __global__ void __launch_bounds__(128) permuto_bwd_kernel(
     const float* __restrict__ pos, int64_t M, const float* __restrict__ table, uint32_t cap, uint32_t cap_mask, int L,
     const float* __restrict__ sf, const float* __restrict__ sh, const float* __restrict__ anneal,
     const float* __restrict__ gout, float* __restrict__ gtable, float* __restrict__ gpos, int n_agg_levels,
-    const int64_t* __restrict__ m_dev, int pos_half) {
+    const int64_t* __restrict__ m_dev, int pos_half, const float* __restrict__ img_scale) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m_dev) M = min(M, __ldg(m_dev));
     if (M <= 0 || (m & ~31ll) >= M) return;   // whole warp beyond the packed samples
@@ -152,23 +177,38 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
         p0 = __half2float(__float2half_rn(p0)); p1 = __half2float(__float2half_rn(p1)); p2 = __half2float(__float2half_rn(p2));
     }
     const float2* grow = reinterpret_cast<const float2*>(gout + mm * (int64_t)(2 * L));
+    const uint4* gimg = reinterpret_cast<const uint4*>(gout) + ((mm >> 7) * (L >> 2)) * 128 + (mm & 127);   // chunk c at gimg[c * 128]
+    const float inv_scale = (GIMG && img_scale) ? 1.f / __ldg(img_scale) : 1.f;
     // Samples the integrator gave zero weight (sigma clamped to 0, or behind an opaque surface with an underflowed
     // transmittance) arrive with an exactly-zero gradient row: adding zeros is skipped -- a whole warp of them costs one
     // pass over its rows, a single one costs no atomics.
     bool rownz = false;
     if (valid) {
-        for (int l = 0; l < L; ++l) { const float2 g = __ldg(grow + l); rownz |= (g.x != 0.f) | (g.y != 0.f); }
+        if (GIMG) {
+            for (int c = 0; c < (L >> 2); ++c) { const uint4 u = __ldg(gimg + c * 128); rownz |= ((u.x | u.y | u.z | u.w) & 0x7fff7fffu) != 0u; }
+        } else {
+            for (int l = 0; l < L; ++l) { const float2 g = __ldg(grow + l); rownz |= (g.x != 0.f) | (g.y != 0.f); }
+        }
     }
     if (!__any_sync(0xffffffffu, rownz)) {
         if (POS_GRAD && valid) { gpos[3 * m] = 0.f; gpos[3 * m + 1] = 0.f; gpos[3 * m + 2] = 0.f; }
         return;
     }
     float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
+    uint4 gq = make_uint4(0u, 0u, 0u, 0u);
     for (int l = 0; l < L; ++l) {
         PermutoVertex v;
         permuto_lattice(p0, p1, p2, sf + 3 * l, sh + 3 * l, cap, cap_mask, v);
         const float w = __ldg(anneal + l);
-        float2 g = __ldg(grow + l);
+        float2 g;
+        if (GIMG) {
+            if ((l & 3) == 0) gq = __ldg(gimg + (l >> 2) * 128);
+            const uint32_t u = (l & 3) == 0 ? gq.x : ((l & 3) == 1 ? gq.y : ((l & 3) == 2 ? gq.z : gq.w));
+            g = __half22float2(*reinterpret_cast<const __half2*>(&u));
+            g.x *= inv_scale; g.y *= inv_scale;
+        } else {
+            g = __ldg(grow + l);
+        }
         g.x = valid ? g.x * w : 0.f;
         g.y = valid ? g.y * w : 0.f;
         const bool nz = rownz && ((g.x != 0.f) | (g.y != 0.f));
@@ -238,7 +278,7 @@ int pag_permuto_fwd(const float* pos, int64_t M, const float* table, int64_t cap
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
     if (cap == 1) return PAG_ERR_ARG;
-    permuto_fwd_kernel<<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(pos, M, table, cap, mask, L, scale_factor,
+    permuto_fwd_kernel<false><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(pos, M, table, cap, mask, L, scale_factor,
                                                                           shift, anneal, out, nullptr, 0);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
@@ -253,8 +293,24 @@ int pag_permuto_fwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, i
     if (M_max == 0) return PAG_OK;
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
-    permuto_fwd_kernel<<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(pos, M_max, table, cap, mask, L, scale_factor,
-                                                                              shift, anneal, out, m_dev, pos_half);
+    permuto_fwd_kernel<false><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(pos, M_max, table, cap, mask, L, scale_factor,
+                                                                                     shift, anneal, out, m_dev, pos_half);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// fp16 operand-image output (see permuto_fwd_kernel<true>): img16 holds ceil(M_max / 128) tiles of 2L/8 * 2048 bytes; L % 4 == 0
+int pag_permuto_fwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
+                              int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
+                              void* img16, void* stream) {
+    if (F != 2 || (L & 3)) return PAG_ERR_UNSUPPORTED;
+    if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    const uint32_t cap = (uint32_t)capacity;
+    const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
+    const int64_t Mpad = (M_max + 127) & ~(int64_t)127;
+    permuto_fwd_kernel<true><<<pag_grid(Mpad, 128), 128, 0, (cudaStream_t)stream>>>(
+        pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, reinterpret_cast<float*>(img16), m_dev, pos_half);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -269,11 +325,11 @@ int pag_permuto_bwd(const float* pos, int64_t M, const float* table, int64_t cap
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
     if (grad_pos)
-        permuto_bwd_kernel<true><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0);
+        permuto_bwd_kernel<true, false><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0, nullptr);
     else
-        permuto_bwd_kernel<false><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0);
+        permuto_bwd_kernel<false, false><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -287,11 +343,32 @@ int pag_permuto_bwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, i
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
     if (grad_pos)
-        permuto_bwd_kernel<true><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half);
+        permuto_bwd_kernel<true, false><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, nullptr);
     else
-        permuto_bwd_kernel<false><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half);
+        permuto_bwd_kernel<false, false><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, nullptr);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// upstream gradient as the decoders' fp16 tile image, scaled by *img_scale (device float, nullable = 1): see permuto_bwd_kernel
+int pag_permuto_bwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
+                              int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
+                              const void* grad_img16, const float* img_scale, float* grad_table, float* grad_pos, int n_agg_levels,
+                              void* stream) {
+    if (F != 2 || (L & 3)) return PAG_ERR_UNSUPPORTED;
+    if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    const uint32_t cap = (uint32_t)capacity;
+    const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
+    const float* g = reinterpret_cast<const float*>(grad_img16);
+    if (grad_pos)
+        permuto_bwd_kernel<true, true><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, g, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, img_scale);
+    else
+        permuto_bwd_kernel<false, true><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, g, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, img_scale);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

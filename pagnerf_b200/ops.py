@@ -476,7 +476,7 @@ class PanCompositeFn(Function):
         lse = torch.empty(M, dtype=torch.float32, device=f.device) if (Ci and inst_softmax) else None
         call("pag_pan_composite_fwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), HIDDEN, int(Cs), int(Ci),
              int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature), ptr(w_), ptr(a_), ptr(r_), ptr(sem), ptr(inst),
-             ptr(lse), None)
+             ptr(lse), None, 0)
         ctx.lse = lse
         ctx.save_for_backward(f, df, lw, w_, a_, r_, *wt)
         ctx.cfg = (int(Cs), int(Ci), int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature))
@@ -496,7 +496,7 @@ class PanCompositeFn(Function):
         if gs is not None or gi is not None:
             call("pag_pan_composite_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), ptr_array(grads), HIDDEN, Cs, Ci,
                  ss, is_, it, ptr(w_), ptr(a_), ptr(r_), int(a_.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(grad_scale(gs, gi)), ptr(gp), None,
-                 *_pan_bwd_workspace(M, IN, Cs, Ci, f.device))
+                 *_pan_bwd_workspace(M, IN, Cs, Ci, f.device), 0)
         elif gp is not None:
             gp.zero_()
         return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
@@ -602,6 +602,7 @@ def _allreduce_async(t):
 # freshly initialised field (bench.py's synthetic weights: every sample has sigma > 0) the extra pass is pure overhead
 # (+0.12 ms on 392 k samples), so it is opt-in: cfg['compact'] / ops.COMPACT_LIVE.
 COMPACT_LIVE = False
+IMG16 = True   # fp16 operand-image interchange between encoders and tensor-core decoders inside FusedTraceFn
 
 
 class FusedTraceFn(Function):
@@ -652,9 +653,19 @@ class FusedTraceFn(Function):
         sf, sh, an, cap, L, n_agg = cfg['grid']
         IN = L * 2
         tb = table.detach().contiguous()
-        feats = torch.empty(Mmax, IN, dtype=f32, device=dev)
         ph = int(bool(cfg['pos_half']))
-        call("pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an), ptr(feats))
+        # fp16 operand-image interchange between the encoders and the tensor-core decoders (one bulk copy per 128-sample tile
+        # on the decoder side, coalesced 16-byte accesses on the encoder side); the f32 [M, 2L] layout stays for compaction
+        img = bool(cfg.get('img16', IMG16)) and not cfg.get('compact', COMPACT_LIVE) and IN % 8 == 0
+        Tmax = (Mmax + 127) // 128
+
+        def feat_buffer():
+            return (torch.empty(Tmax, IN // 8, 128, 8, dtype=torch.float16, device=dev) if img
+                    else torch.empty(Mmax, IN, dtype=f32, device=dev))
+
+        feats = feat_buffer()
+        call("pag_permuto_fwd_img16_dyn" if img else "pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2,
+             ptr(sf), ptr(sh), ptr(an), ptr(feats))
         w = [_f32(x) for x in weights]
         lodw = _f32(cfg['lodw'])
         want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
@@ -667,7 +678,7 @@ class FusedTraceFn(Function):
             # the survivors.  The list stays ray-sorted; offsets_c / its last entry replace offsets / the sample count.
             sigma0 = torch.empty(Mmax, dtype=f32, device=dev)
             call("pag_decode_dc_fwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
-                 HIDDEN, VIEW_DIM, 0, ptr(sigma0), None, None)
+                 HIDDEN, VIEW_DIM, 0, ptr(sigma0), None, None, 0)
             offsets_c = torch.empty(N + 1, dtype=i64, device=dev)
             call("pag_compact_count", ptr(sigma0), ptr(offsets), N, ptr(counts), ptr(offsets_c))
             ridx_c = torch.empty(Mmax, dtype=i64, device=dev)
@@ -688,11 +699,12 @@ class FusedTraceFn(Function):
             # decode + scalar compositing (both kernels leave most of the L1 / LSU bandwidth idle)
             dsf, dsh, dan, dcap, dL, dn_agg = cfg['dgrid']
             dtb = dtable.detach().contiguous()
-            dfeats = torch.empty(Mmax, IN, dtype=f32, device=dev)
+            dfeats = feat_buffer()
             side = _side_stream(dev)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                call("pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan), ptr(dfeats))
+                call("pag_permuto_fwd_img16_dyn" if img else "pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2,
+                     ptr(dsf), ptr(dsh), ptr(dan), ptr(dfeats))
         sigma = torch.empty(Mmax, dtype=f32, device=dev)
         rgb = torch.empty(Mmax, 3, dtype=f32, device=dev) if want_rgb else None
         pe16 = None
@@ -701,7 +713,7 @@ class FusedTraceFn(Function):
             call("pag_view_pe16", ptr(d), N, ptr(pe16))
         ctx.pe16 = pe16
         call("pag_decode_dc_fwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
-             HIDDEN, VIEW_DIM, int(want_rgb), ptr(sigma), ptr(rgb), ptr(pe16))
+             HIDDEN, VIEW_DIM, int(want_rgb), ptr(sigma), ptr(rgb), ptr(pe16), int(img))
         wgt = torch.empty(Mmax, dtype=f32, device=dev)
         T = torch.empty(Mmax, dtype=f32, device=dev)
         alpha = torch.empty(N, 1, dtype=f32, device=dev)
@@ -723,9 +735,9 @@ class FusedTraceFn(Function):
             lse = torch.empty(Mmax, dtype=f32, device=dev) if (Ci and cfg['inst_softmax']) else None
             call("pag_pan_composite_fwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), HIDDEN, Cs, Ci,
                  int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
-                 ptr(wgt), ptr(alpha), ptr(ridx), ptr(sem_o), ptr(inst_o), ptr(lse), ptr(m_dev))
+                 ptr(wgt), ptr(alpha), ptr(ridx), ptr(sem_o), ptr(inst_o), ptr(lse), ptr(m_dev), int(img))
             ctx.lse = lse
-        ctx.cfg = cfg
+        ctx.cfg, ctx.img, ctx.IN = cfg, img, IN
         ctx.save_for_backward(o, d, offsets, ridx, samples, depths, deltas, feats, dfeats, sigma, rgb, wgt, T, alpha, rgbsum,
                               tb, dtb, lodw, *w)
         ctx.mark_non_differentiable(hit)
@@ -739,8 +751,15 @@ class FusedTraceFn(Function):
          *w) = ctx.saved_tensors
         cfg = ctx.cfg
         N, dev = o.shape[0], o.device
-        Mmax, IN = feats.shape
+        img, IN = ctx.img, ctx.IN
+        Mmax = samples.shape[0]
+        Tmax = (Mmax + 127) // 128
         m_dev = offsets[N:]
+
+        def grad_buffer():      # feature gradients: fp16 operand images (still carrying the loss scale) or f32 rows
+            return (torch.empty(Tmax, IN // 8, 128, 8, dtype=torch.float16, device=dev) if img
+                    else torch.empty(Mmax, IN, dtype=torch.float32, device=dev))
+
         f32 = torch.float32
         sf, sh, an, cap, L, n_agg = cfg['grid']
         ph = int(bool(cfg['pos_half']))
@@ -760,7 +779,7 @@ class FusedTraceFn(Function):
             src = cfg['pan_src']
             a, b = {'delta': (feats, dfeats), 'separate': (dfeats, None), 'appearance': (feats, None)}[src]
             need_gp = src in ('delta', 'separate')          # 'appearance': features are detached -> nothing upstream
-            g_panop = torch.empty(Mmax, IN, dtype=f32, device=dev) if need_gp else None
+            g_panop = grad_buffer() if need_gp else None
             if need_gp:
                 dsf, dsh, dan, dcap, dL, dn_agg = cfg['dgrid']
                 g_dtable = torch.zeros_like(dtb)
@@ -771,8 +790,11 @@ class FusedTraceFn(Function):
                 call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), ptr_array(grads[10:]), HIDDEN,
                      Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
                      ptr(wgt), ptr(alpha), ptr(ridx), int(alpha.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev),
-                     *_pan_bwd_workspace(Mmax, IN, Cs, Ci, dev))
-                if need_gp:
+                     *_pan_bwd_workspace(Mmax, IN, Cs, Ci, dev), int(img))
+                if need_gp and img:
+                    call("pag_permuto_bwd_img16_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
+                         ptr(g_panop), ptr(scale_p), ptr(g_dtable), None, int(dn_agg))
+                elif need_gp:
                     call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
                          ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
                     if sync:
@@ -792,14 +814,18 @@ class FusedTraceFn(Function):
                  int(bool(cfg['bg_white'])), ptr(wgt), ptr(T), ptr(alpha), ptr(rgbsum), ptr(ga), ptr(gr), ptr(gd), None, 0, None, 0,
                  ptr(g_sigma), ptr(g_rgb_s), None, None)
             scale = grad_scale_dyn(g_sigma, g_rgb_s, m_dev, 1, 3)
-            g_feats = torch.empty(Mmax, IN, dtype=f32, device=dev)
+            g_feats = grad_buffer()
             g_dir = torch.empty(Mmax, 3, dtype=f32, device=dev) if ctx.needs_input_grad[1] else None
             call("pag_decode_dc_bwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
                  ptr_array(grads[:10]), HIDDEN, VIEW_DIM, ptr(g_sigma), ptr(g_rgb_s), ptr(scale), ptr(g_feats), ptr(g_dir),
-                 ptr(ctx.pe16), *_ws("pag_decode_dc_bwd_workspace", dev, Mmax, IN))
+                 ptr(ctx.pe16), *_ws("pag_decode_dc_bwd_workspace", dev, Mmax, IN), int(img))
             g_pos = torch.empty(Mmax, 3, dtype=f32, device=dev) if need_rays else None
-            call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
-                 ptr(g_feats), ptr(g_table), ptr(g_pos), int(n_agg))
+            if img:
+                call("pag_permuto_bwd_img16_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
+                     ptr(g_feats), ptr(scale), ptr(g_table), ptr(g_pos), int(n_agg))
+            else:
+                call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
+                     ptr(g_feats), ptr(g_table), ptr(g_pos), int(n_agg))
             if need_rays:   # d samples / d (origin, dir): segment sums over each ray's packed range
                 g_o = torch.empty(N, 3, dtype=f32, device=dev)
                 g_d = torch.empty(N, 3, dtype=f32, device=dev)
