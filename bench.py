@@ -266,6 +266,9 @@ class ClockSampler:
 ALGO = {
     "pag_permuto_fwd_dyn": ("hbm", 12 + L * 4 * 8 + L * 2 * 4),
     "pag_permuto_bwd_dyn": ("hbm", 12 + L * 2 * 4 + 2 * L * 4 * 8),
+    # fp16 operand-image interchange: features / feature gradients move as halfs (SURVEY 8d figures minus 2 B per feature)
+    "pag_permuto_fwd_img16_dyn": ("hbm", 12 + L * 4 * 8 + L * 2 * 2),
+    "pag_permuto_bwd_img16_dyn": ("hbm", 12 + L * 2 * 2 + 2 * L * 4 * 8),
     "pag_decode_dc_fwd_tc_dyn": ("tensor", 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
     "pag_decode_dc_bwd_tc_dyn": ("tensor", 3 * 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
     "pag_pan_composite_fwd_tc": ("tensor", 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
@@ -466,9 +469,10 @@ def main():
     n_live = int(live.item()) if torch.is_tensor(live) else n_samples
     n_all = n_samples
     if top and n_samples:
-        if top[0] in ("pag_pan_composite_fwd_tc", "pag_pan_composite_bwd_tc", "pag_decode_dc_bwd_tc_dyn", "pag_permuto_bwd_dyn"):
+        if top[0] in ("pag_pan_composite_fwd_tc", "pag_pan_composite_bwd_tc", "pag_decode_dc_bwd_tc_dyn", "pag_permuto_bwd_dyn",
+                      "pag_permuto_bwd_img16_dyn"):
             n_samples = n_live
-        elif top[0] in ("pag_permuto_fwd_dyn", "pag_decode_dc_fwd_tc_dyn"):
+        elif top[0] in ("pag_permuto_fwd_dyn", "pag_permuto_fwd_img16_dyn", "pag_decode_dc_fwd_tc_dyn"):
             n_samples = (n_all + n_live) // 2
     if top and top[0] in ALGO and n_samples:
         bound, per = ALGO[top[0]]
@@ -489,7 +493,9 @@ def main():
         roof["samples_per_launch"] = n_samples
     # ---- encoder vs the memory system (BASELINE metric "encoder GB/s vs peak") -------------------------------
     encoder = None
-    enc = per_kernel.get("pag_permuto_fwd_dyn")
+    enc_name = "pag_permuto_fwd_img16_dyn" if "pag_permuto_fwd_img16_dyn" in per_kernel else "pag_permuto_fwd_dyn"
+    enc = per_kernel.get(enc_name)
+    enc_bytes = ALGO[enc_name][1]
     if enc and n_all:
         table = wl.nef.grid.embedder.lattice_values.detach()
         entries = table.numel() // 2
@@ -505,12 +511,13 @@ def main():
         probe_gbs = n_all * 96 * 8 / (g0.elapsed_time(g1) / 10 * 1e-3) / 1e9
         t_enc = enc["ms_per_launch"] * 1e-3
         n_enc = (n_all + n_live) / 2          # two launches per step: colour grid (all samples) and delta grid (live samples)
-        encoder = {"kernel": "pag_permuto_fwd_dyn", "ms_per_launch": round(enc["ms_per_launch"], 4), "samples_per_launch": n_enc,
-                   "algorithmic_GBps": 972 * n_enc / t_enc / 1e9, "hbm_peak_GBps": hbm, "frac_of_hbm_peak": 972 * n_enc / t_enc / 1e9 / hbm,
+        encoder = {"kernel": enc_name, "ms_per_launch": round(enc["ms_per_launch"], 4), "samples_per_launch": n_enc,
+                   "algorithmic_bytes_per_sample": enc_bytes,
+                   "algorithmic_GBps": enc_bytes * n_enc / t_enc / 1e9, "hbm_peak_GBps": hbm, "frac_of_hbm_peak": enc_bytes * n_enc / t_enc / 1e9 / hbm,
                    "vertex_gather_GBps": 768 * n_enc / t_enc / 1e9, "achievable_gather_GBps": probe_gbs,
                    "frac_of_achievable_gather": 768 * n_enc / t_enc / 1e9 / probe_gbs,
-                   "note": "972 B/sample algorithmic (12 pos + 768 vertex reads + 192 out); achievable = pag_gather_probe: uniformly "
-                           "random 8-byte loads, 4 in flight per thread, from the same 50 MB table (32-byte sectors: 4x the bytes move)"}
+                   "note": "algorithmic bytes = 12 pos + 768 vertex reads + features out (192 f32 / 96 fp16 image); achievable = pag_gather_probe: uniformly "
+                           "random 8-byte loads, 16 in flight per thread, from the same 50 MB table (32-byte sectors: 4x the bytes move)"}
     cpu = None
     if not args.no_cpu_baseline:
         v, dt = time_cpu_reference(args.cpu_sample_rays, 3, 1)

@@ -234,7 +234,7 @@ int pag_expint_bwd(const float* gw, const float* w, const float* T, const int64_
                    void* stream);
 
 /* ---- achievable-gather-bandwidth probe (bench.py: denominator of the encoder's roofline fraction) ----
- * threads x loads_per_thread (multiple of 4) uniformly random 8-byte loads from table[entries] float2; sink f32[threads]. */
+ * threads x loads_per_thread (multiple of 16, 16 in flight per thread) uniformly random 8-byte loads from table[entries] float2; sink f32[threads]. */
 int pag_gather_probe(const float* table, int64_t entries, int64_t threads, int loads_per_thread, float* sink, void* stream);
 
 /* ---- tcgen05 building-block probe (tests only): one 128-row tile through the tensor-core operand images ---- */

@@ -249,20 +249,26 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
     if (POS_GRAD && valid) { gpos[3 * m] = gp0; gpos[3 * m + 1] = gp1; gpos[3 * m + 2] = gp2; }
 }
 
-// uniformly random 8-byte gathers (see pag_gather_probe)
+// uniformly random 8-byte gathers (see pag_gather_probe): 16 independent loads in flight per thread per iteration -- what the
+// encoder keeps in flight with four lattice levels unrolled
 __global__ void __launch_bounds__(128) gather_probe_kernel(const float* __restrict__ table, uint32_t entries, int64_t threads,
                                                            int loads_per_thread, float* __restrict__ sink) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= threads) return;
     uint32_t state = (uint32_t)t * 2654435761u + 12345u;
+    const bool pow2 = (entries & (entries - 1)) == 0;
     float acc = 0.f;
-    for (int i = 0; i < loads_per_thread; i += 4) {
-        const uint32_t i0 = pag_lowbias32(state) % entries, i1 = pag_lowbias32(state + 1) % entries,
-                       i2 = pag_lowbias32(state + 2) % entries, i3 = pag_lowbias32(state + 3) % entries;
-        state += 4;
-        const float2 a = ldg2(table + 2 * (size_t)i0), b = ldg2(table + 2 * (size_t)i1), c = ldg2(table + 2 * (size_t)i2),
-                     d = ldg2(table + 2 * (size_t)i3);
-        acc += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+    for (int i = 0; i < loads_per_thread; i += 16) {
+        float2 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t h = pag_lowbias32(state + k);
+            const uint32_t idx = pow2 ? (h & (entries - 1)) : (h % entries);
+            v[k] = ldg2(table + 2 * (size_t)idx);
+        }
+        state += 16;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += v[k].x + v[k].y;
     }
     sink[t] = acc;
 }
@@ -386,11 +392,11 @@ int pag_permuto_indices(const float* pos, int64_t M, int64_t capacity, int L, co
 }
 
 // ---- achievable-gather-bandwidth probe (the denominator of the encoder's roofline fraction) ----------------
-// `threads` threads each issue `loads_per_thread` uniformly random 8-byte loads (4 independent loads in flight per
-// iteration, like the 4 simplex vertices of one lattice level) from a table of `entries` float2 -- the same access shape as
+// `threads` threads each issue `loads_per_thread` (multiple of 16) uniformly random 8-byte loads (16 independent loads in
+// flight per iteration, like the 4 simplex vertices of four unrolled lattice levels) from a table of `entries` float2 -- the same access shape as
 // the encoder's vertex reads without any of its arithmetic.  sink receives one float per thread so the loads stay live.
 int pag_gather_probe(const float* table, int64_t entries, int64_t threads, int loads_per_thread, float* sink, void* stream) {
-    if (entries <= 0 || entries > 0xFFFFFFFFll || threads <= 0 || loads_per_thread <= 0 || (loads_per_thread & 3)) return PAG_ERR_ARG;
+    if (entries <= 0 || entries > 0xFFFFFFFFll || threads <= 0 || loads_per_thread <= 0 || (loads_per_thread & 15)) return PAG_ERR_ARG;
     gather_probe_kernel<<<pag_grid(threads, 128), 128, 0, (cudaStream_t)stream>>>(table, (uint32_t)entries, threads, loads_per_thread, sink);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
