@@ -311,12 +311,15 @@ __global__ void __launch_bounds__(PCF_THREADS) pan_comp_fwd_kernel(
 #define PCB_NCG 4    // column groups per row
 #define PCB_MAXK 3   // input quads (float4) per thread: IN <= 48
 #define PCB_NGC 16   // rays whose output gradients are cached (fp16, pre-scaled) per tile
+// The semantic head (one 16-column block per row, ~250 dependent instructions = ~1.5 k cycles for a warp running alone on its
+// scheduler) belongs to the column group that owns the FEWEST instance-logit blocks (13 blocks: group 0 has 4, groups 1-3 have 3)
+#define PCB_SEM_CG 3
 
 struct PanCompBwdLayout {
     int INP, nXc, CsP, CiP, nGi;
-    int oGs, oX, oHs, oH1, oOnes, oH2, oGi, oW1, oWs2, oWi2, oWi3, oBias, oGC, oPF, total;
+    int oGs, oX, oHs, oH1, oOnes, oH2, oGi, oW1, oWs2, oWi2, oWi3, oBias, oGC, oGSC, oPF, total;
 };
-__host__ __device__ inline PanCompBwdLayout pan_comp_bwd_layout(int IN, int Cs, int Ci) {
+__host__ __device__ inline PanCompBwdLayout pan_comp_bwd_layout(int IN, int Cs, int Ci, bool img = false) {
     PanCompBwdLayout l;
     l.INP = (IN + 15) & ~15; l.nXc = l.INP / 8;
     l.CsP = 16; l.CiP = Ci > 0 ? ((Ci + 15) & ~15) : 16; l.nGi = l.CiP / 8;
@@ -338,7 +341,11 @@ __host__ __device__ inline PanCompBwdLayout pan_comp_bwd_layout(int IN, int Cs, 
     o = (o + 15) & ~15;
     l.oGC = o; o += PCB_NGC * l.CiP * 2;                       // fp16 cache of g_inst rows (6.5 KB)
     o = (o + 15) & ~15;
-    l.oPF = o; o += 2 * PCB_MAXK * PCB_THREADS * 16;          // cp.async slots of the next tile's inputs (48 KB)
+    l.oGSC = o; o += img ? PCB_NGC * 16 * 4 : 0;                // f32 cache of g_sem rows (1 KB; image mode only: the f32-row
+                                                                // variant has no shared memory left)
+    o = (o + 127) & ~127;
+    // next tile's inputs: cp.async slots (48 KB, f32 rows) or the two bulk-copy landing tiles (fp16 images, 24 KB)
+    l.oPF = o; o += img ? 2 * l.nXc * TCH : 2 * PCB_MAXK * PCB_THREADS * 16;
     l.total = o;
     return l;
 }
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     __shared__ uint64_t xbar_s;
     __shared__ uint32_t tmem_s;
     __shared__ float part_s[PCB_NCG][128];      // per column group: partial <p, g> of the row
-    const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci);
+    const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci, IMG);
     const int tid = threadIdx.x, warp = warp_id_uniform(), lane = tid & 31;
     const int q = warp & 3, cg = warp >> 2;       // TMEM lane quadrant, column group
     const int row = 32 * q + lane;
@@ -462,6 +469,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                    aOnes = smem_u32(sm + l.oOnes);
     const uint32_t w1j = smem_u32(sm + l.oW1), ws2 = smem_u32(sm + l.oWs2), wi2 = smem_u32(sm + l.oWi2), wi3 = smem_u32(sm + l.oWi3);
     __half* gcache = reinterpret_cast<__half*>(sm + l.oGC);
+    float* gsc = reinterpret_cast<float*>(sm + l.oGSC);
     const float scale = scale_ptr ? __ldg(scale_ptr) : 1.f;
     const float inv_scale = 1.f / scale;
     const int c16 = 16 * cg;                       // this thread's 16 hidden columns
@@ -549,8 +557,12 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         }
         PAG_PHASE(18);
         // while the MMAs run: the tile's per-ray output gradients (first PCB_NGC rays) -> registers, coalesced
-        float gpre[7];
+        float gpre[7], gspre = 0.f;
         const int ngc_elems = PCB_NGC * Ci;
+        if (IMG && do_sem && tid < PCB_NGC * Cs) {      // g_sem rows of the same rays: PCB_NGC * Cs <= 256 values
+            const int64_t src = ray0 * Cs + tid;
+            gspre = (src < R * Cs) ? __ldg(g_sem + src) : 0.f;
+        }
         if (do_inst) {
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
@@ -563,7 +575,10 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         mb.wait(); PAG_PHASE(3);
         const float cs = valid ? a_row * w_row : 0.f;     // the loss scale rides on the cached gradients
         uint32_t mask_s = 0, mask_1 = 0, mask_2 = 0;
-        if (do_sem) mask_s = epi_relu16(tl + PCB_S0 + c16, bs1 + c16, Hs + 2 * cg * TCH, row);
+        if (do_sem) {
+            mask_s = epi_relu16(tl + PCB_S0 + c16, bs1 + c16, Hs + 2 * cg * TCH, row);
+            if (IMG && tid < PCB_NGC * Cs) gsc[(tid / Cs) * 16 + (tid % Cs)] = gspre;
+        }
         if (do_inst) {
             mask_1 = epi_relu16(tl + PCB_S1 + c16, bi1 + c16, H1 + 2 * cg * TCH, row);
             int gr = gc_r0, gc = gc_c0;      // (ray slot, class) of element tid + 512 k, advanced without divisions
@@ -585,29 +600,41 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
         mb.wait(); PAG_PHASE(5);
         if (do_inst) mask_2 = epi_relu16(tl + PCB_S0 + c16, bi2 + c16, H2 + 2 * cg * TCH, row);
         float zs[16];
-        if (do_sem && cg == 0) tmem_ld16(tl + PCB_SEMLOG, zs);     // before the instance logits overwrite the column range
+        if (do_sem && cg == PCB_SEM_CG) tmem_ld16(tl + PCB_SEMLOG, zs);     // before the instance logits overwrite the column range
         // ---------------- stage 3: instance logits + head gradient; 16-column block b belongs to group b % 4 ----------------
         if (do_inst) {
             sync_to_mma(); PAG_PHASE(6);
             if (warp == 0 && elect_one()) { tc_fence_after(); mma16_fwd(tm, aH2, wi3, l.CiP, l.CiP, 64, false); mb.commit(); }
+            PAG_PHASE(20);
         }
-        if (do_sem && cg == 0) {   // semantic head gradient (<= 16 classes): column group 0, while the logits MMA runs
+        if (do_sem && cg == PCB_SEM_CG) {   // semantic head gradient (<= 16 classes), while the logits MMA runs
             float g[16];
             float mx = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 16; ++j) { zs[j] += bs2[j]; if (j < Cs) mx = fmaxf(mx, zs[j]); }
+            const int64_t sslot = ray - ray0;
+            if (IMG && sslot < PCB_NGC) {      // this ray's output gradient is in the tile's cache (filled while the first MMA ran)
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(gsc + sslot * 16 + j);
+                    g[j] = t.x; g[j + 1] = t.y; g[j + 2] = t.z; g[j + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) g[j] = (j < Cs) ? __ldg(g_sem + ray * Cs + j) : 0.f;
+            }
             float Z = 0.f, E = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float gj = (j < Cs) ? __ldg(g_sem + ray * Cs + j) : 0.f;
-                const float e = (j < Cs) ? (sem_softmax ? __expf(zs[j] - mx) : 1.f) : 0.f;
-                g[j] = gj; zs[j] = e;
-                Z += e; E = fmaf(e, gj, E);
+                const float e = (j < Cs) ? (sem_softmax ? fast_exp2((zs[j] - mx) * LOG2E_F) : 1.f) : 0.f;
+                zs[j] = e;
+                Z += e; E = fmaf(e, (j < Cs) ? g[j] : 0.f, E);
             }
             const float iz = 1.f / Z, dot = E * iz, css = cs * scale;
 #pragma unroll
             for (int j = 0; j < 16; ++j) g[j] = (j < Cs) ? (sem_softmax ? css * zs[j] * iz * (g[j] - dot) : css * g[j]) : 0.f;
             grad16_store(g, Gs, row, lane, db_s2);
+            PAG_PHASE(21);
         }
         if (do_inst) {
             mb.wait(); PAG_PHASE(7);
@@ -761,7 +788,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                 }
             }
             if (own) red_add_f32(p.gbs1 + c16 + f1, db_s1 * inv_scale);
-            if (own && cg == 0 && f1 < Cs) red_add_f32(p.gbs2 + f1, db_s2 * inv_scale);
+            if (own && cg == PCB_SEM_CG && f1 < Cs) red_add_f32(p.gbs2 + f1, db_s2 * inv_scale);
         }
         if (do_inst) {
             flush_dw16(tl + PCB_DWI2, dWi2, row, 64, 64, c16, inv_scale, plain);
@@ -856,9 +883,9 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
     PanParams p{};
     fill_pan_f(p, weights, grads);
-    const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci);
-    if (l.total > 227 * 1024) return PAG_ERR_UNSUPPORTED;
     if (x_img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
+    const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci, x_img16 != 0);
+    if (l.total > 227 * 1024) return PAG_ERR_UNSUPPORTED;
     const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = fused_num_sms();
