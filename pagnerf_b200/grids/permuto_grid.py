@@ -31,7 +31,7 @@ class PermutoEncoding(nn.Module):
         self.register_buffer('scale_factor', torch.from_numpy(sf.astype(np.float32)))
         self.register_buffer('anneal_window', torch.ones(nr_levels))
         # coarse levels (lattice spacing >= 5 % of the unit cube) use warp-aggregated scatter in backward; measured on the
-        # bench workload (tests/permuto_tune.py, 410 k samples): 0 levels 1249 us, 4: 445, 8: 193 (best), 10: 215, 14: 357
+        # bench workload (tools/permuto_tune.py, 410 k samples): 0 levels 1249 us, 4: 445, 8: 193 (best), 10: 215, 14: 357
         self.n_agg_levels = int((scales >= agg_scale_threshold).sum())
 
     def output_dims(self):
