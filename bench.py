@@ -368,7 +368,8 @@ def main():
     trace("workload built")
     if world > 1:
         from pagnerf_b200 import ops
-        ops.set_grad_sync(True)      # gradient all-reduce (NCCL, AVG) issued from inside the fused backward, overlapped
+        # gradient all-reduce (NCCL, AVG) issued from inside the fused backward (reserving SMs for NCCL measured slower: 0)
+        ops.set_grad_sync(True, reserved_sms=int(os.environ.get("BENCH_RESERVED_SMS", 0)))
 
     def step(from_host):
         return wl.forward_backward(from_host=from_host)

@@ -113,7 +113,10 @@ int pag_permuto_fwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_
 int pag_permuto_bwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
                               int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
                               const void* grad_img16, const float* img_scale, float* grad_table, float* grad_pos, int n_agg_levels,
-                              void* stream);
+                              int level_begin, int level_end, void* stream);
+/* [level_begin, level_end): the levels this launch scatters (0, L for all).  Splitting the table into level ranges lets the
+ * all-reduce of a finished range overlap the scatter of the next; grad_pos is written by the range starting at 0 and
+ * accumulated by the others. */
 /* parity probe: lattice vertex hash indices u32[L,M,4], ranks i32[L,M,4], barycentric f32[L,M,4]. */
 int pag_permuto_indices(const float* pos, int64_t M, int64_t capacity, int L, const float* scale_factor,
                         const float* shift, uint32_t* idx, int32_t* rank, float* bary, void* stream);
@@ -232,6 +235,11 @@ int pag_sum_reduce_bwd(const float* g, int64_t C, const int64_t* offsets, int64_
 int pag_expint_fwd(const float* tau, const int64_t* offsets, int64_t R, float* w, float* T, void* stream);
 int pag_expint_bwd(const float* gw, const float* w, const float* T, const int64_t* offsets, int64_t R, float* gtau,
                    void* stream);
+
+/* The persistent tensor-core decoder kernels normally occupy every SM (one CTA per SM holding nearly all of its shared memory
+ * and registers); reserve n SMs so that concurrently running kernels of other libraries -- the NCCL all-reduce that overlaps
+ * the backward in multi-GPU training -- can make progress.  previous (host, nullable) receives the old value. */
+int pag_set_reserved_sms(int n, int* previous /* host */);
 
 /* ---- achievable-gather-bandwidth probe (bench.py: denominator of the encoder's roofline fraction) ----
  * threads x loads_per_thread (multiple of 16, 16 in flight per thread) uniformly random 8-byte loads from table[entries] float2; sink f32[threads]. */

@@ -818,6 +818,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+extern int pag_reserved_sms;      // decoder_tc.cu, pag_set_reserved_sms
 static int fused_num_sms() {
     static int n = 0;
     if (!n) {
@@ -826,7 +827,8 @@ static int fused_num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
-    return n;
+    const int m = n - pag_reserved_sms;
+    return m > 8 ? m : 8;
 }
 static void fill_pan_f(PanParams& p, const float* const* w, float* const* g) {
     p.Ws1 = w[0]; p.bs1 = w[1]; p.Ws2 = w[2]; p.bs2 = w[3]; p.Wi1 = w[4]; p.bi1 = w[5]; p.Wi2 = w[6]; p.bi2 = w[7]; p.Wi3 = w[8]; p.bi3 = w[9];

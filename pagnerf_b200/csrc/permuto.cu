@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
     const float* __restrict__ pos, int64_t M, const float* __restrict__ table, uint32_t cap, uint32_t cap_mask, int L,
     const float* __restrict__ sf, const float* __restrict__ sh, const float* __restrict__ anneal,
     const float* __restrict__ gout, float* __restrict__ gtable, float* __restrict__ gpos, int n_agg_levels,
-    const int64_t* __restrict__ m_dev, int pos_half, const float* __restrict__ img_scale) {
+    const int64_t* __restrict__ m_dev, int pos_half, const float* __restrict__ img_scale, int l0, int l1) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m_dev) M = min(M, __ldg(m_dev));
     if (M <= 0 || (m & ~31ll) >= M) return;   // whole warp beyond the packed samples
@@ -190,19 +190,21 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
             for (int l = 0; l < L; ++l) { const float2 g = __ldg(grow + l); rownz |= (g.x != 0.f) | (g.y != 0.f); }
         }
     }
+    // [l0, l1): the levels of this launch (the caller may split the table into level ranges to pipeline the scatter with
+    // the all-reduce of the finished ranges); position gradients accumulate over the ranges (first range writes)
     if (!__any_sync(0xffffffffu, rownz)) {
-        if (POS_GRAD && valid) { gpos[3 * m] = 0.f; gpos[3 * m + 1] = 0.f; gpos[3 * m + 2] = 0.f; }
+        if (POS_GRAD && valid && l0 == 0) { gpos[3 * m] = 0.f; gpos[3 * m + 1] = 0.f; gpos[3 * m + 2] = 0.f; }
         return;
     }
     float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f;
     uint4 gq = make_uint4(0u, 0u, 0u, 0u);
-    for (int l = 0; l < L; ++l) {
+    for (int l = l0; l < l1; ++l) {
         PermutoVertex v;
         permuto_lattice(p0, p1, p2, sf + 3 * l, sh + 3 * l, cap, cap_mask, v);
         const float w = __ldg(anneal + l);
         float2 g;
         if (GIMG) {
-            if ((l & 3) == 0) gq = __ldg(gimg + (l >> 2) * 128);
+            if ((l & 3) == 0 || l == l0) gq = __ldg(gimg + (l >> 2) * 128);
             const uint32_t u = (l & 3) == 0 ? gq.x : ((l & 3) == 1 ? gq.y : ((l & 3) == 2 ? gq.z : gq.w));
             g = __half22float2(*reinterpret_cast<const __half2*>(&u));
             g.x *= inv_scale; g.y *= inv_scale;
@@ -246,7 +248,10 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
             gp2 += (de[0] + de[1] + de[2] - 3.f * de[3]) * __ldg(sf + 3 * l + 2);
         }
     }
-    if (POS_GRAD && valid) { gpos[3 * m] = gp0; gpos[3 * m + 1] = gp1; gpos[3 * m + 2] = gp2; }
+    if (POS_GRAD && valid) {
+        if (l0 == 0) { gpos[3 * m] = gp0; gpos[3 * m + 1] = gp1; gpos[3 * m + 2] = gp2; }
+        else { gpos[3 * m] += gp0; gpos[3 * m + 1] += gp1; gpos[3 * m + 2] += gp2; }
+    }
 }
 
 // uniformly random 8-byte gathers (see pag_gather_probe): 16 independent loads in flight per thread per iteration -- what the
@@ -332,10 +337,10 @@ int pag_permuto_bwd(const float* pos, int64_t M, const float* table, int64_t cap
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
     if (grad_pos)
         permuto_bwd_kernel<true, false><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0, nullptr);
+            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0, nullptr, 0, L);
     else
         permuto_bwd_kernel<false, false><<<pag_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0, nullptr);
+            pos, M, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, nullptr, 0, nullptr, 0, L);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -350,10 +355,10 @@ int pag_permuto_bwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, i
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
     if (grad_pos)
         permuto_bwd_kernel<true, false><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, nullptr);
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, nullptr, 0, L);
     else
         permuto_bwd_kernel<false, false><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, nullptr);
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, grad_out, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, nullptr, 0, L);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -362,8 +367,9 @@ int pag_permuto_bwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, i
 int pag_permuto_bwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table,
                               int64_t capacity, int L, int F, const float* scale_factor, const float* shift, const float* anneal,
                               const void* grad_img16, const float* img_scale, float* grad_table, float* grad_pos, int n_agg_levels,
-                              void* stream) {
+                              int level_begin, int level_end, void* stream) {
     if (F != 2 || (L & 3)) return PAG_ERR_UNSUPPORTED;
+    if (level_begin < 0 || level_end > L || level_begin >= level_end) return PAG_ERR_ARG;
     if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
     if (M_max == 0) return PAG_OK;
     const uint32_t cap = (uint32_t)capacity;
@@ -371,10 +377,10 @@ int pag_permuto_bwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_
     const float* g = reinterpret_cast<const float*>(grad_img16);
     if (grad_pos)
         permuto_bwd_kernel<true, true><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, g, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, img_scale);
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, g, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, img_scale, level_begin, level_end);
     else
         permuto_bwd_kernel<false, true><<<pag_grid(M_max, 128), 128, 0, (cudaStream_t)stream>>>(
-            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, g, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, img_scale);
+            pos, M_max, table, cap, mask, L, scale_factor, shift, anneal, g, grad_table, grad_pos, n_agg_levels, m_dev, pos_half, img_scale, level_begin, level_end);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

@@ -584,12 +584,15 @@ def _side_stream(device):
     return _SIDE_STREAMS[key]
 
 
-def set_grad_sync(enabled, group=None):
+def set_grad_sync(enabled, group=None, reserved_sms=0):
     """Ray-sharded data parallelism: when enabled, FusedTraceFn.backward all-reduces (AVG) the gradients it
     produces itself -- the delta-grid table as soon as its scatter kernel is queued, so that the NCCL transfer over
     NVLink overlaps the remaining colour-branch backward; the colour table and the flattened decoder gradients at the
     end -- and returns already-reduced gradients.  One process per GPU, torch.distributed initialised by the caller."""
     _GRAD_SYNC["enabled"], _GRAD_SYNC["group"] = bool(enabled), group
+    # leave a few SMs to the NCCL kernels: the persistent decoder kernels would otherwise hold every SM until they finish
+    # and the "overlapped" all-reduce would start only then
+    _lib.load().pag_set_reserved_sms(int(reserved_sms) if enabled else 0, None)
 
 
 def _allreduce_async(t):
@@ -602,6 +605,7 @@ def _allreduce_async(t):
 # freshly initialised field (bench.py's synthetic weights: every sample has sigma > 0) the extra pass is pure overhead
 # (+0.12 ms on 392 k samples), so it is opt-in: cfg['compact'] / ops.COMPACT_LIVE.
 COMPACT_LIVE = False
+GRAD_SYNC_CHUNKS = int(__import__('os').environ.get('PAGNERF_GRAD_SYNC_CHUNKS', '1'))   # level ranges the colour-table scatter is split into when its all-reduce is pipelined (multi-GPU)
 IMG16 = True   # fp16 operand-image interchange between encoders and tensor-core decoders inside FusedTraceFn
 
 
@@ -773,6 +777,7 @@ class FusedTraceFn(Function):
         gi = _f32(g_inst) if (g_inst is not None and Ci) else None
         main = torch.cuda.current_stream()
         side = None
+        table_reduced = False
         if gs is not None or gi is not None:
             # panoptic chain (heads backward -> delta-grid scatter [-> all-reduce]) on a side stream; it shares nothing
             # with the colour chain below except read-only inputs, and the two sets of kernels overlap on the SMs
@@ -793,7 +798,7 @@ class FusedTraceFn(Function):
                      *_pan_bwd_workspace(Mmax, IN, Cs, Ci, dev), int(img))
                 if need_gp and img:
                     call("pag_permuto_bwd_img16_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
-                         ptr(g_panop), ptr(scale_p), ptr(g_dtable), None, int(dn_agg))
+                         ptr(g_panop), ptr(scale_p), ptr(g_dtable), None, int(dn_agg), 0, int(dL))
                 elif need_gp:
                     call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
                          ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
@@ -821,8 +826,16 @@ class FusedTraceFn(Function):
                  ptr(ctx.pe16), *_ws("pag_decode_dc_bwd_workspace", dev, Mmax, IN), int(img))
             g_pos = torch.empty(Mmax, 3, dtype=f32, device=dev) if need_rays else None
             if img:
-                call("pag_permuto_bwd_img16_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
-                     ptr(g_feats), ptr(scale), ptr(g_table), ptr(g_pos), int(n_agg))
+                # multi-GPU: the colour table is the LAST gradient produced, so its all-reduce cannot hide behind other work --
+                # scatter it in level ranges and all-reduce every finished range while the next one is being scattered
+                nchunk = GRAD_SYNC_CHUNKS if (sync and L % GRAD_SYNC_CHUNKS == 0) else 1
+                step_l = L // nchunk
+                for c in range(nchunk):
+                    call("pag_permuto_bwd_img16_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
+                         ptr(g_feats), ptr(scale), ptr(g_table), ptr(g_pos), int(n_agg), c * step_l, (c + 1) * step_l)
+                    if sync and nchunk > 1:
+                        works.append(_allreduce_async(g_table[c * step_l:(c + 1) * step_l]))
+                table_reduced = sync and nchunk > 1
             else:
                 call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
                      ptr(g_feats), ptr(g_table), ptr(g_pos), int(n_agg))
@@ -835,7 +848,8 @@ class FusedTraceFn(Function):
         if side is not None:
             main.wait_stream(side)
         if sync:
-            works.append(_allreduce_async(g_table))
+            if not table_reduced:
+                works.append(_allreduce_async(g_table))
             works.append(_allreduce_async(flat))
             for wk in works:
                 wk.wait()
