@@ -665,3 +665,36 @@ def test_fused_trace_live_compaction_is_exact(cuda_lib):
     assert set(g0) == set(g1)
     for n in g0:
         assert_close(g1[n], g0[n], rtol=1e-4, atol_scale=2e-5, msg=n)   # summation order (atomics, tile grouping) differs
+
+
+def test_fused_trace_img16_interchange_equals_f32_rows(cuda_lib):
+    """fp16 operand-image interchange between encoders and tensor-core decoders (ops.IMG16: coalesced encoder stores, bulk
+    tile copies, fp16 dX images) vs the f32 [M, 2L] row interchange, on the bench field (L = 24, 200 instances): same
+    step, same jitter -> outputs at the fp16 tolerance, gradients norm-wise."""
+    import bench
+    from pagnerf_b200 import ops
+    dev = torch.device(DEV)
+    res = []
+    try:
+        for img in (True, False):
+            ops.IMG16 = img
+            wl = bench.Workload(dev, n_rays=2048, seed=0, n_batches=2)
+            wl.keep_rb = True
+            blas = wl.nef.grid.blas
+            blas.fixed_jitter, blas.jitter_seed = True, 11
+            for p in wl.params:
+                p.grad = None
+            loss = wl.loss_of(*wl.dev[0])
+            loss.backward()
+            rb = wl.last_rb
+            res.append((float(loss), {c: getattr(rb, c).detach().clone() for c in ('rgb', 'depth', 'alpha', 'semantics', 'inst_embedding')},
+                        [p.grad.clone() for p in wl.params]))
+    finally:
+        ops.IMG16 = True
+    (l1, o1, g1), (l0, o0, g0) = res
+    assert abs(l1 - l0) <= 2e-3 * abs(l0)
+    for c in o0:
+        assert_close(o1[c], o0[c], rtol=5e-3, atol_scale=5e-3, msg=c)
+    for a, b in zip(g1, g0):
+        assert torch.isfinite(a).all()
+        assert_close_norm(a, b, rel_l2=5e-2, max_frac=0.3, msg="img16 vs f32-row grad")
