@@ -129,6 +129,13 @@ int pag_hash_fwd(int flavour, const float* pos, int64_t M, const float* table, i
 int pag_hash_bwd(int flavour, const float* pos, int64_t M, const float* table, int L, int F, const float* fparam,
                  const uint32_t* res, const uint32_t* offset, const uint32_t* size, const float* grad_out,
                  float* grad_table, float* grad_pos, int n_agg_levels, void* stream);
+/* variants for the sync-free fused trace (device-side sample count, optional fp16 rounding of the positions) */
+int pag_hash_fwd_dyn(int flavour, const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table, int L,
+                     int F, const float* fparam, const uint32_t* res, const uint32_t* offset, const uint32_t* size, float* out,
+                     int round_half, void* stream);
+int pag_hash_bwd_dyn(int flavour, const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table, int L,
+                     int F, const float* fparam, const uint32_t* res, const uint32_t* offset, const uint32_t* size,
+                     const float* grad_out, float* grad_table, float* grad_pos, int n_agg_levels, void* stream);
 int pag_hash_indices(int flavour, const float* pos, int64_t M, int L, const float* fparam, const uint32_t* res,
                      const uint32_t* offset, const uint32_t* size, uint32_t* idx, void* stream);
 

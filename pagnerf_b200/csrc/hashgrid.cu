@@ -89,10 +89,15 @@ __device__ __forceinline__ void make_cell(float x, float y, float z, const Level
 template <int FLAVOUR>
 __global__ void __launch_bounds__(128) hash_fwd_kernel(const float* __restrict__ pos, int64_t M,
                                                        const float* __restrict__ table, int L, LevelDesc d,
-                                                       float* __restrict__ out, int round_half) {
+                                                       float* __restrict__ out, int round_half,
+                                                       const int64_t* __restrict__ m_dev, int pos_half) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m_dev) M = min(M, __ldg(m_dev));   // packed-sample count produced on the device by the marcher (fused trace)
     if (m >= M) return;
-    const float x = pos[3 * m], y = pos[3 * m + 1], z = pos[3 * m + 2];
+    float x = pos[3 * m], y = pos[3 * m + 1], z = pos[3 * m + 2];
+    if (pos_half) {   // autocast: custom_fwd(cast_inputs=torch.half), grids/hash_grid_tinycudann.py:36
+        x = __half2float(__float2half_rn(x)); y = __half2float(__float2half_rn(y)); z = __half2float(__float2half_rn(z));
+    }
     float2* orow = reinterpret_cast<float2*>(out + m * (int64_t)(2 * L));
 #pragma unroll 2
     for (int l = 0; l < L; ++l) {
@@ -134,11 +139,17 @@ template <int FLAVOUR, bool POS_GRAD>
 __global__ void __launch_bounds__(128) hash_bwd_kernel(const float* __restrict__ pos, int64_t M,
                                                        const float* __restrict__ table, int L, LevelDesc d,
                                                        const float* __restrict__ gout, float* __restrict__ gtable,
-                                                       float* __restrict__ gpos, int n_agg_levels) {
+                                                       float* __restrict__ gpos, int n_agg_levels,
+                                                       const int64_t* __restrict__ m_dev, int pos_half) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m_dev) M = min(M, __ldg(m_dev));
+    if (M <= 0 || (m & ~31ll) >= M) return;   // whole warp beyond the packed samples
     const bool valid = m < M;
     const int64_t mm = valid ? m : (M - 1);
-    const float x = pos[3 * mm], y = pos[3 * mm + 1], z = pos[3 * mm + 2];
+    float x = pos[3 * mm], y = pos[3 * mm + 1], z = pos[3 * mm + 2];
+    if (pos_half) {
+        x = __half2float(__float2half_rn(x)); y = __half2float(__float2half_rn(y)); z = __half2float(__float2half_rn(z));
+    }
     const float2* grow = reinterpret_cast<const float2*>(gout + mm * (int64_t)(2 * L));
     float gp[3] = {0.f, 0.f, 0.f};
     for (int l = 0; l < L; ++l) {
@@ -183,9 +194,9 @@ __global__ void __launch_bounds__(128) hash_bwd_kernel(const float* __restrict__
 
 template <int FLAVOUR>
 static int launch_bwd(const float* pos, int64_t M, const float* table, int L, LevelDesc d, const float* gout,
-                      float* gtable, float* gpos, int n_agg, cudaStream_t st) {
-    if (gpos) hash_bwd_kernel<FLAVOUR, true><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg);
-    else hash_bwd_kernel<FLAVOUR, false><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg);
+                      float* gtable, float* gpos, int n_agg, cudaStream_t st, const int64_t* m_dev = nullptr, int pos_half = 0) {
+    if (gpos) hash_bwd_kernel<FLAVOUR, true><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg, m_dev, pos_half);
+    else hash_bwd_kernel<FLAVOUR, false><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg, m_dev, pos_half);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -202,8 +213,8 @@ int pag_hash_fwd(int flavour, const float* pos, int64_t M, const float* table, i
     if (M == 0) return PAG_OK;
     LevelDesc d{fparam, res, offset, size};
     cudaStream_t st = (cudaStream_t)stream;
-    if (flavour == 0) hash_fwd_kernel<0><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, out, round_half);
-    else hash_fwd_kernel<1><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, out, round_half);
+    if (flavour == 0) hash_fwd_kernel<0><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, out, round_half, nullptr, 0);
+    else hash_fwd_kernel<1><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, out, round_half, nullptr, 0);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -218,6 +229,32 @@ int pag_hash_bwd(int flavour, const float* pos, int64_t M, const float* table, i
     cudaStream_t st = (cudaStream_t)stream;
     return flavour == 0 ? launch_bwd<0>(pos, M, table, L, d, grad_out, grad_table, grad_pos, n_agg_levels, st)
                         : launch_bwd<1>(pos, M, table, L, d, grad_out, grad_table, grad_pos, n_agg_levels, st);
+}
+
+// variants for the sync-free fused trace: sample count read on the device (m_dev[0] <= M_max), optional fp16 rounding of pos
+int pag_hash_fwd_dyn(int flavour, const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table, int L,
+                     int F, const float* fparam, const uint32_t* res, const uint32_t* offset, const uint32_t* size, float* out,
+                     int round_half, void* stream) {
+    if (F != 2) return PAG_ERR_UNSUPPORTED;
+    if (L <= 0 || (flavour != 0 && flavour != 1)) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    LevelDesc d{fparam, res, offset, size};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (flavour == 0) hash_fwd_kernel<0><<<pag_grid(M_max, 128), 128, 0, st>>>(pos, M_max, table, L, d, out, round_half, m_dev, pos_half);
+    else hash_fwd_kernel<1><<<pag_grid(M_max, 128), 128, 0, st>>>(pos, M_max, table, L, d, out, round_half, m_dev, pos_half);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_hash_bwd_dyn(int flavour, const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table, int L,
+                     int F, const float* fparam, const uint32_t* res, const uint32_t* offset, const uint32_t* size,
+                     const float* grad_out, float* grad_table, float* grad_pos, int n_agg_levels, void* stream) {
+    if (F != 2) return PAG_ERR_UNSUPPORTED;
+    if (L <= 0 || (flavour != 0 && flavour != 1)) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    LevelDesc d{fparam, res, offset, size};
+    cudaStream_t st = (cudaStream_t)stream;
+    return flavour == 0 ? launch_bwd<0>(pos, M_max, table, L, d, grad_out, grad_table, grad_pos, n_agg_levels, st, m_dev, pos_half)
+                        : launch_bwd<1>(pos, M_max, table, L, d, grad_out, grad_table, grad_pos, n_agg_levels, st, m_dev, pos_half);
 }
 
 int pag_hash_indices(int flavour, const float* pos, int64_t M, int L, const float* fparam, const uint32_t* res,

@@ -609,6 +609,38 @@ GRAD_SYNC_CHUNKS = int(__import__('os').environ.get('PAGNERF_GRAD_SYNC_CHUNKS', 
 IMG16 = True   # fp16 operand-image interchange between encoders and tensor-core decoders inside FusedTraceFn
 
 
+def _enc_levels(kind, spec):
+    return int(spec[4]) if kind == 'permuto' else int(spec[5])
+
+
+def _enc_fwd(kind, spec, samples, Mmax, m_dev, ph, table, out, img):
+    """Grid encode of the fused trace.  permuto spec: (scale_factor, shift, anneal, capacity, L, n_agg);
+    hash spec: (flavour, fparam, res, offset, size, L, round_half, n_agg, cast_half)."""
+    if kind == 'permuto':
+        sf, sh, an, cap, L, _ = spec
+        call("pag_permuto_fwd_img16_dyn" if img else "pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(table), cap, L, 2,
+             ptr(sf), ptr(sh), ptr(an), ptr(out))
+    else:
+        fl, fparam, res, offset, size, L, round_half, _, cast_half = spec
+        call("pag_hash_fwd_dyn", int(fl), ptr(samples), Mmax, ptr(m_dev), int(bool(ph and cast_half)), ptr(table), L, 2, ptr(fparam),
+             ptr(res), ptr(offset), ptr(size), ptr(out), int(bool(round_half)))
+
+
+def _enc_bwd(kind, spec, samples, Mmax, m_dev, ph, table, g, scale, g_table, g_pos, img, l0=0, l1=None):
+    if kind == 'permuto':
+        sf, sh, an, cap, L, n_agg = spec
+        if img:
+            call("pag_permuto_bwd_img16_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(table), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
+                 ptr(g), ptr(scale), ptr(g_table), ptr(g_pos), int(n_agg), int(l0), int(L if l1 is None else l1))
+        else:
+            call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(table), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
+                 ptr(g), ptr(g_table), ptr(g_pos), int(n_agg))
+    else:
+        fl, fparam, res, offset, size, L, _, n_agg, cast_half = spec
+        call("pag_hash_bwd_dyn", int(fl), ptr(samples), Mmax, ptr(m_dev), int(bool(ph and cast_half)), ptr(table), L, 2, ptr(fparam),
+             ptr(res), ptr(offset), ptr(size), ptr(g), ptr(g_table), ptr(g_pos), int(n_agg))
+
+
 class FusedTraceFn(Function):
     """PanopticPackedRFTracer.trace for ('ray' marching, permutohedral grids, tensor-core decoders) as ONE autograd
     node: ~10 kernel launches forward / ~10 backward, no host synchronisation (the packed-sample count stays on the
@@ -654,13 +686,15 @@ class FusedTraceFn(Function):
         m_dev = offsets[N:]                      # device-side packed-sample count M
         if seed_dev is not None:
             seed_dev.add_(1)                     # next replay / step draws the next jitter stream
-        sf, sh, an, cap, L, n_agg = cfg['grid']
+        kind = cfg.get('grid_kind', 'permuto')
+        L = _enc_levels(kind, cfg['grid'])
         IN = L * 2
         tb = table.detach().contiguous()
         ph = int(bool(cfg['pos_half']))
         # fp16 operand-image interchange between the encoders and the tensor-core decoders (one bulk copy per 128-sample tile
         # on the decoder side, coalesced 16-byte accesses on the encoder side); the f32 [M, 2L] layout stays for compaction
-        img = bool(cfg.get('img16', IMG16)) and not cfg.get('compact', COMPACT_LIVE) and IN % 8 == 0
+        # and for the hash grids
+        img = (bool(cfg.get('img16', IMG16)) and not cfg.get('compact', COMPACT_LIVE) and IN % 8 == 0 and kind == 'permuto')
         Tmax = (Mmax + 127) // 128
 
         def feat_buffer():
@@ -668,8 +702,7 @@ class FusedTraceFn(Function):
                     else torch.empty(Mmax, IN, dtype=f32, device=dev))
 
         feats = feat_buffer()
-        call("pag_permuto_fwd_img16_dyn" if img else "pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2,
-             ptr(sf), ptr(sh), ptr(an), ptr(feats))
+        _enc_fwd(kind, cfg['grid'], samples, Mmax, m_dev, ph, tb, feats, img)
         w = [_f32(x) for x in weights]
         lodw = _f32(cfg['lodw'])
         want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
@@ -701,14 +734,12 @@ class FusedTraceFn(Function):
         if src in ('delta', 'separate'):
             # the delta-grid encode only needs the samples: run it on a side stream, concurrently with the colour
             # decode + scalar compositing (both kernels leave most of the L1 / LSU bandwidth idle)
-            dsf, dsh, dan, dcap, dL, dn_agg = cfg['dgrid']
             dtb = dtable.detach().contiguous()
             dfeats = feat_buffer()
             side = _side_stream(dev)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                call("pag_permuto_fwd_img16_dyn" if img else "pag_permuto_fwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2,
-                     ptr(dsf), ptr(dsh), ptr(dan), ptr(dfeats))
+                _enc_fwd(kind, cfg['dgrid'], samples, Mmax, m_dev, ph, dtb, dfeats, img)
         sigma = torch.empty(Mmax, dtype=f32, device=dev)
         rgb = torch.empty(Mmax, 3, dtype=f32, device=dev) if want_rgb else None
         pe16 = None
@@ -765,7 +796,8 @@ class FusedTraceFn(Function):
                     else torch.empty(Mmax, IN, dtype=torch.float32, device=dev))
 
         f32 = torch.float32
-        sf, sh, an, cap, L, n_agg = cfg['grid']
+        kind = cfg.get('grid_kind', 'permuto')
+        L = _enc_levels(kind, cfg['grid'])
         ph = int(bool(cfg['pos_half']))
         Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
         sync, works = _GRAD_SYNC["enabled"], []
@@ -786,7 +818,6 @@ class FusedTraceFn(Function):
             need_gp = src in ('delta', 'separate')          # 'appearance': features are detached -> nothing upstream
             g_panop = grad_buffer() if need_gp else None
             if need_gp:
-                dsf, dsh, dan, dcap, dL, dn_agg = cfg['dgrid']
                 g_dtable = torch.zeros_like(dtb)
             side = _side_stream(dev)
             side.wait_stream(main)
@@ -796,12 +827,8 @@ class FusedTraceFn(Function):
                      Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
                      ptr(wgt), ptr(alpha), ptr(ridx), int(alpha.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev),
                      *_pan_bwd_workspace(Mmax, IN, Cs, Ci, dev), int(img))
-                if need_gp and img:
-                    call("pag_permuto_bwd_img16_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
-                         ptr(g_panop), ptr(scale_p), ptr(g_dtable), None, int(dn_agg), 0, int(dL))
-                elif need_gp:
-                    call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(dtb), dcap, dL, 2, ptr(dsf), ptr(dsh), ptr(dan),
-                         ptr(g_panop), ptr(g_dtable), None, int(dn_agg))
+                if need_gp:
+                    _enc_bwd(kind, cfg['dgrid'], samples, Mmax, m_dev, ph, dtb, g_panop, scale_p, g_dtable, None, img)
                     if sync:
                         works.append(_allreduce_async(g_dtable))   # overlaps the colour-branch backward
         # scalar compositing backward -> per-sample sigma / rgb gradients
@@ -825,20 +852,15 @@ class FusedTraceFn(Function):
                  ptr_array(grads[:10]), HIDDEN, VIEW_DIM, ptr(g_sigma), ptr(g_rgb_s), ptr(scale), ptr(g_feats), ptr(g_dir),
                  ptr(ctx.pe16), *_ws("pag_decode_dc_bwd_workspace", dev, Mmax, IN), int(img))
             g_pos = torch.empty(Mmax, 3, dtype=f32, device=dev) if need_rays else None
-            if img:
-                # multi-GPU: the colour table is the LAST gradient produced, so its all-reduce cannot hide behind other work --
-                # scatter it in level ranges and all-reduce every finished range while the next one is being scattered
-                nchunk = GRAD_SYNC_CHUNKS if (sync and L % GRAD_SYNC_CHUNKS == 0) else 1
-                step_l = L // nchunk
-                for c in range(nchunk):
-                    call("pag_permuto_bwd_img16_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
-                         ptr(g_feats), ptr(scale), ptr(g_table), ptr(g_pos), int(n_agg), c * step_l, (c + 1) * step_l)
-                    if sync and nchunk > 1:
-                        works.append(_allreduce_async(g_table[c * step_l:(c + 1) * step_l]))
-                table_reduced = sync and nchunk > 1
-            else:
-                call("pag_permuto_bwd_dyn", ptr(samples), Mmax, ptr(m_dev), ph, ptr(tb), cap, L, 2, ptr(sf), ptr(sh), ptr(an),
-                     ptr(g_feats), ptr(g_table), ptr(g_pos), int(n_agg))
+            # multi-GPU (opt-in, PAGNERF_GRAD_SYNC_CHUNKS > 1): scatter the colour table in level ranges and all-reduce every
+            # finished range while the next one is being scattered (measured slower at 2 GPUs)
+            nchunk = GRAD_SYNC_CHUNKS if (sync and img and GRAD_SYNC_CHUNKS > 1 and L % GRAD_SYNC_CHUNKS == 0) else 1
+            step_l = L // nchunk
+            for c in range(nchunk):
+                _enc_bwd(kind, cfg['grid'], samples, Mmax, m_dev, ph, tb, g_feats, scale, g_table, g_pos, img, c * step_l, (c + 1) * step_l)
+                if nchunk > 1:
+                    works.append(_allreduce_async(g_table[c * step_l:(c + 1) * step_l]))
+            table_reduced = nchunk > 1
             if need_rays:   # d samples / d (origin, dir): segment sums over each ray's packed range
                 g_o = torch.empty(N, 3, dtype=f32, device=dev)
                 g_d = torch.empty(N, 3, dtype=f32, device=dev)

@@ -231,9 +231,15 @@ class PanopticNeF(BaseNeuralField):
     def fused_trace_cfg(self, channels, rays, num_steps, bg_color):
         """Configuration for ops.FusedTraceFn (sync-free training trace), or None when this field / request is not
         covered by it ('ray' marching on PermutoGrid fields with the reference decoder shapes, tensor-core mode)."""
-        from ..grids import PermutoGrid
+        from ..grids import PermutoGrid, HashGridTinyCudaNN, HashGridTorch
         pan = [c for c in ('semantics', 'inst_embedding') if c in channels]
-        if not self._use_tc() or not isinstance(self.grid, PermutoGrid) or not hasattr(self.grid, 'embedder'):
+        if not self._use_tc() or not hasattr(self.grid, 'embedder'):
+            return None
+        if isinstance(self.grid, PermutoGrid):
+            kind = 'permuto'
+        elif isinstance(self.grid, (HashGridTinyCudaNN, HashGridTorch)):
+            kind = 'hash'
+        else:
             return None
         if pan and not self.fused_panoptic_ok(channels):
             return None
@@ -246,7 +252,11 @@ class PanopticNeF(BaseNeuralField):
         blas = self.grid.blas.to(dev)
 
         def enc(e):
-            return (e.scale_factor, e.random_shift_per_level, e.anneal_window, e.capacity, e.nr_levels, e.n_agg_levels)
+            if kind == 'permuto':
+                return (e.scale_factor, e.random_shift_per_level, e.anneal_window, e.capacity, e.nr_levels, e.n_agg_levels)
+            if isinstance(self.grid, HashGridTinyCudaNN):      # flavour 0; autocast casts the coordinates to half (:36)
+                return (0, e.level_scale, e.level_res, e.level_offset, e.level_size, e.n_levels, e.round_half, e.n_agg_levels, True)
+            return (1, e.level_res, None, e.level_offset, e.level_size, e.n_levels, False, e.n_agg_levels, False)
 
         seed = blas.jitter_seed
         if not blas.fixed_jitter:
@@ -256,7 +266,7 @@ class PanopticNeF(BaseNeuralField):
         return dict(octree=blas.octree, prefix=blas.prefix, level=self.grid.blas_level, S=int(num_steps), near=dmin, far=dmax,
                     bits=blas.level_bits(self.grid.blas_level) if self.grid.blas_level >= 2 else None,
                     seed=seed, seed_dev=getattr(blas, 'seed_tensor', None), bg_white=(bg_color == 'white'), pos_half=torch.is_autocast_enabled(),
-                    lodw=self._lodw(dev), grid=enc(self.grid.embedder),
+                    lodw=self._lodw(dev), grid_kind=kind, grid=enc(self.grid.embedder),
                     dgrid=enc(self.delta_grid.embedder) if src in ('delta', 'separate') else None, pan_src=src,
                     want_rgb='rgb' in channels, want_depth='depth' in channels,
                     Cs=self.num_classes if 'semantics' in channels else 0,
@@ -268,8 +278,13 @@ class PanopticNeF(BaseNeuralField):
         """(color table, delta table | None, 20 decoder tensors) in the order ops.FusedTraceFn expects."""
         wts = (_decoder_tensors(self.decoder_density, 1) + _decoder_tensors(self.decoder_color, 2)
                + _decoder_tensors(self.decoder_semantics, 1) + _decoder_tensors(self.decoder_inst, 2))
-        dt = self.delta_grid.embedder.lattice_values if hasattr(self, 'delta_grid') else None
-        return self.grid.embedder.lattice_values, dt, wts
+        def table(e):
+            for name in ('lattice_values', 'params', 'embeddings_weight'):      # permutohedral / tcnn / HashNeRF
+                if hasattr(e, name):
+                    return getattr(e, name)
+            raise AttributeError("unknown grid embedder")
+        dt = table(self.delta_grid.embedder) if hasattr(self, 'delta_grid') else None
+        return table(self.grid.embedder), dt, wts
 
     def trace_composited(self, coords, ray_d, ridx_rows, deltas, depths, offsets, num_rays, channels, bg_white, lod_idx=None):
         """Decode + composite in one pass: per-ray dict(alpha, hit, rgb, depth, semantics, inst_embedding).

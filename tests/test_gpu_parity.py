@@ -516,11 +516,13 @@ def test_fused_panoptic_composite_equals_modular(cuda_lib, name, mode):
 
 
 @pytest.mark.parametrize("with_pose_grad", [False, True])
-def test_sync_free_fused_trace_equals_stepwise(cuda_lib, with_pose_grad):
-    """ops.FusedTraceFn (device-side sample count, worst-case buffers, no host sync) vs the step-by-step plugin path."""
+@pytest.mark.parametrize("name", ["trace_delta_permuto_ray", "trace_nef_tcnn_ray"])
+def test_sync_free_fused_trace_equals_stepwise(cuda_lib, with_pose_grad, name):
+    """ops.FusedTraceFn (device-side sample count, worst-case buffers, no host sync) vs the step-by-step plugin path, for a
+    permutohedral delta field and for a PanopticNeF on the tcnn-style hash grid (heads on the detached colour features)."""
     from pagnerf_b200.tracers import PanopticPackedRFTracer
     from pagnerf_b200.wisp_compat import Rays
-    g = load_golden("trace_delta_permuto_ray")
+    g = load_golden(name)
     chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
     res = []
     for fused in (True, False):
