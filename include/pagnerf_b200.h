@@ -164,6 +164,19 @@ int pag_linear_head_fwd(const float* feats, const float* dfeats, const float* lo
                         const float* b, float* y, void* stream);
 int pag_linear_head_bwd(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN, const float* w,
                         const float* g, float* g_x, float* g_w, float* g_b, void* stream);
+/* fused-trace variants (device-side sample count): y = post * relu?(pre + head(x)) -- the DD field's tau_p =
+ * relu(y0.detach() + delta_density) * delta in one pass; the backward gates g with the forward output `gate` (ReLU), multiplies
+ * it by post and can accumulate into g_x. */
+int pag_linear_head_fwd_dyn(const float* feats, const float* dfeats, const float* lodw, int64_t M_max, const int64_t* m_dev, int IN,
+                            const float* w, const float* b, const float* pre, int relu, const float* post, float* y, void* stream);
+int pag_linear_head_bwd_dyn(const float* feats, const float* dfeats, const float* lodw, int64_t M_max, const int64_t* m_dev, int IN,
+                            const float* w, const float* g, const float* gate, const float* post, float* g_x, int accumulate_x,
+                            float* g_w, float* g_b, void* stream);
+/* DD tracer backward glue (tracers/panoptic_dd_packed_rf_tracer.py:128-162): gw[s] = alpha_p[ray] * (gw_sem + gw_inst)[s]
+ * + sum_c g[ray][c] out[ray][c] / alpha_p[ray], the gradient of the loss w.r.t. the panoptic integration weights. */
+int pag_dd_weight_grads(const float* g_sem, const float* out_sem, int Cs, const float* g_inst, const float* out_inst, int Ci,
+                        const float* alpha_p, const float* gw_sem, const float* gw_inst, const int64_t* offsets, int64_t R,
+                        float* gw, void* stream);
 
 /* tensor-core (tcgen05, fp16 operands / fp32 accumulate) variants of the four decoder entry points: the numerics of
  * the reference's autocast training step (pc_nerf/trainer.py:429).  grad_scale: device pointer to one power-of-two
@@ -177,7 +190,8 @@ int pag_decode_dc_bwd_tc(const float* feats, const float* lodw, const float* ray
                          void* stream);
 int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, int hidden, int view_dim,
-                             int want_rgb, float* sigma, float* rgb, const void* view_pe16, int feats_img16, void* stream);
+                             int want_rgb, float* sigma, float* rgb, float* y0_raw /* nullable: density pre-activation */,
+                             const void* view_pe16, int feats_img16, void* stream);
 int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, float* const* grads, int hidden,
                              int view_dim, const float* g_sigma, const float* g_rgb, const float* grad_scale, float* g_feats,
@@ -211,7 +225,9 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
                              const int64_t* ridx, int64_t R, const float* g_sem, const float* g_inst, const float* inst_lse,
                              const float* grad_scale, float* g_panop, const int64_t* m_dev, float* workspace,
-                             int64_t workspace_bytes, int x_img16, void* stream);
+                             int64_t workspace_bytes, int x_img16, float* gw_sem, float* gw_inst, void* stream);
+/* gw_sem / gw_inst f32[M] (nullable, softmax heads only): <p_s, g_ray> per sample = d out / d weight_s / alpha -- what a
+ * tracer whose panoptic weights carry gradient (PanopticDDensityPackedRFTracer) needs to continue the chain rule. */
 /* x_img16 != 0: feats / dfeats (and g_panop, then still multiplied by *grad_scale) are fp16 operand images, see
  * pag_permuto_fwd_img16_dyn; IN % 8 == 0. */
 /* workspace (nullable, device): *bytes of pag_pan_composite_bwd_workspace(M, IN, Cs, Ci, &bytes), 16-byte aligned.  With it every CTA stores its

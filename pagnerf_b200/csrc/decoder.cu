@@ -684,10 +684,14 @@ static int pan_bwd_launch(const float* feats, const float* dfeats, const float* 
 // (Identity): feat -> 64 -> 1 without a nonlinearity is ONE linear map, w = W2 W1, b = W2 b1 + b2 (collapsed on the host,
 // where autograd carries the gradient back to W1 / b1 / W2 / b2).  Thread per sample, float4 rows.
 // ---------------------------------------------------------------------------------------------
+// pre (nullable): added before the optional ReLU; post (nullable): per-sample factor applied after it -- the DD field's
+// tau_p = relu(y0.detach() + delta_density) * delta in one pass.  m_dev (nullable): device-side sample count.
 __global__ void linear_head_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ dfeats,
                                        const float* __restrict__ lodw, int64_t M, int IN, const float* __restrict__ w,
-                                       const float* __restrict__ b, float* __restrict__ y) {
+                                       const float* __restrict__ b, float* __restrict__ y, const float* __restrict__ pre,
+                                       int relu, const float* __restrict__ post, const int64_t* __restrict__ m_dev) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m_dev) M = min(M, __ldg(m_dev));
     if (m >= M) return;
     float acc = __ldg(b);
     for (int k = 0; k < IN; ++k) {
@@ -696,16 +700,26 @@ __global__ void linear_head_fwd_kernel(const float* __restrict__ feats, const fl
         if (lodw) x *= __ldg(lodw + k);
         acc = fmaf(x, __ldg(w + k), acc);
     }
+    if (pre) acc += pre[m];
+    if (relu) acc = fmaxf(acc, 0.f);
+    if (post) acc *= post[m];
     y[m] = acc;
 }
-// g_x[m,k] = g[m] * lodw[k] * w[k] (same for feats and dfeats); g_w[k] += sum_m g[m] * x[m,k]; g_b += sum_m g[m]
+// g_x[m,k] (+)= g[m] * lodw[k] * w[k] (same for feats and dfeats); g_w[k] += sum_m g[m] * x[m,k]; g_b += sum_m g[m].
+// gate (nullable): the forward output; g is zeroed where gate <= 0 (ReLU) ; post as in the forward.
 __global__ void __launch_bounds__(256) linear_head_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dfeats,
                                                               const float* __restrict__ lodw, int64_t M, int IN,
                                                               const float* __restrict__ w, const float* __restrict__ g,
-                                                              float* __restrict__ g_x, float* __restrict__ g_w, float* __restrict__ g_b) {
+                                                              float* __restrict__ g_x, float* __restrict__ g_w, float* __restrict__ g_b,
+                                                              const float* __restrict__ gate, const float* __restrict__ post,
+                                                              int accumulate_x, const int64_t* __restrict__ m_dev) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m_dev) M = min(M, __ldg(m_dev));
+    if ((m & ~31ll) >= M) return;
     const bool valid = m < M;
-    const float gm = valid ? g[m] : 0.f;
+    float gm = valid ? g[m] : 0.f;
+    if (valid && post) gm *= post[m];
+    if (valid && gate && !(gate[m] > 0.f)) gm = 0.f;
     const int lane = threadIdx.x & 31;
     for (int k = 0; k < IN; ++k) {
         const float lw = lodw ? __ldg(lodw + k) : 1.f;
@@ -713,7 +727,10 @@ __global__ void __launch_bounds__(256) linear_head_bwd_kernel(const float* __res
         if (valid) {
             x = feats[m * IN + k];
             if (dfeats) x += dfeats[m * IN + k];
-            if (g_x) g_x[m * IN + k] = gm * lw * __ldg(w + k);
+            if (g_x) {
+                const float v = gm * lw * __ldg(w + k);
+                if (accumulate_x) g_x[m * IN + k] += v; else g_x[m * IN + k] = v;
+            }
         }
         float s = gm * x * lw;
 #pragma unroll
@@ -724,6 +741,30 @@ __global__ void __launch_bounds__(256) linear_head_bwd_kernel(const float* __res
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
     if (lane == 0 && sb != 0.f) red_add_f32(g_b, sb);
+}
+// DD tracer backward glue: the panoptic outputs are out[ray] = alpha_p * sum_s w_p[s] f[s] with alpha_p = sum_s w_p[s] and the
+// weights NOT detached (tracers/panoptic_dd_packed_rf_tracer.py:128-162).  Given the per-sample <f_s, g_ray> from the fused heads
+// backward: d L / d w_p[s] = alpha_p * (gw_sem + gw_inst)[s] + d L / d alpha_p[ray],
+//           d L / d alpha_p[ray] = sum_c g[ray][c] * out[ray][c] / alpha_p[ray].     One warp per ray.
+__global__ void dd_weight_grads_kernel(const float* __restrict__ g_sem, const float* __restrict__ out_sem, int Cs,
+                                       const float* __restrict__ g_inst, const float* __restrict__ out_inst, int Ci,
+                                       const float* __restrict__ alpha_p, const float* __restrict__ gw_sem,
+                                       const float* __restrict__ gw_inst, const int64_t* __restrict__ offsets, int64_t R,
+                                       float* __restrict__ gw) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const int64_t s0 = offsets[r], s1 = offsets[r + 1];
+    if (s0 == s1) return;
+    float acc = 0.f;
+    if (g_sem) for (int c = lane; c < Cs; c += 32) acc = fmaf(g_sem[r * Cs + c], out_sem[r * Cs + c], acc);
+    if (g_inst) for (int c = lane; c < Ci; c += 32) acc = fmaf(g_inst[r * Ci + c], out_inst[r * Ci + c], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float a = alpha_p[r];
+    const float ga = a != 0.f ? acc / a : 0.f;
+    for (int64_t i = s0 + lane; i < s1; i += 32)
+        gw[i] = a * ((gw_sem ? gw_sem[i] : 0.f) + (gw_inst ? gw_inst[i] : 0.f)) + ga;
 }
 
 extern "C" {
@@ -815,7 +856,7 @@ int pag_linear_head_fwd(const float* feats, const float* dfeats, const float* lo
                         const float* b, float* y, void* stream) {
     if (IN <= 0) return PAG_ERR_ARG;
     if (M == 0) return PAG_OK;
-    linear_head_fwd_kernel<<<pag_grid(M, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M, IN, w, b, y);
+    linear_head_fwd_kernel<<<pag_grid(M, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M, IN, w, b, y, nullptr, 0, nullptr, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -823,7 +864,38 @@ int pag_linear_head_bwd(const float* feats, const float* dfeats, const float* lo
                         const float* g, float* g_x, float* g_w, float* g_b, void* stream) {
     if (IN <= 0) return PAG_ERR_ARG;
     if (M == 0) return PAG_OK;
-    linear_head_bwd_kernel<<<pag_grid(M, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M, IN, w, g, g_x, g_w, g_b);
+    linear_head_bwd_kernel<<<pag_grid(M, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M, IN, w, g, g_x, g_w, g_b,
+                                                                               nullptr, nullptr, 0, nullptr);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+// fused-trace variants: y = post * relu?(pre + head(x)) with the sample count on the device; the backward gates g with the
+// forward output (ReLU), multiplies it by post, and can accumulate into g_x (the heads' dX is already there)
+int pag_linear_head_fwd_dyn(const float* feats, const float* dfeats, const float* lodw, int64_t M_max, const int64_t* m_dev, int IN,
+                            const float* w, const float* b, const float* pre, int relu, const float* post, float* y, void* stream) {
+    if (IN <= 0) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    linear_head_fwd_kernel<<<pag_grid(M_max, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M_max, IN, w, b, y, pre, relu, post, m_dev);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_linear_head_bwd_dyn(const float* feats, const float* dfeats, const float* lodw, int64_t M_max, const int64_t* m_dev, int IN,
+                            const float* w, const float* g, const float* gate, const float* post, float* g_x, int accumulate_x,
+                            float* g_w, float* g_b, void* stream) {
+    if (IN <= 0) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    linear_head_bwd_kernel<<<pag_grid(M_max, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M_max, IN, w, g, g_x, g_w, g_b,
+                                                                                   gate, post, accumulate_x, m_dev);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+// see dd_weight_grads_kernel; gw f32[M] out
+int pag_dd_weight_grads(const float* g_sem, const float* out_sem, int Cs, const float* g_inst, const float* out_inst, int Ci,
+                        const float* alpha_p, const float* gw_sem, const float* gw_inst, const int64_t* offsets, int64_t R,
+                        float* gw, void* stream) {
+    if (R == 0) return PAG_OK;
+    dd_weight_grads_kernel<<<pag_grid(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(g_sem, out_sem, Cs, g_inst, out_inst, Ci, alpha_p,
+                                                                                    gw_sem, gw_inst, offsets, R, gw);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

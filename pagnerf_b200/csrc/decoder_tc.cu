@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
                                                                const float* __restrict__ ray_d, int S, int64_t M, int IN,
                                                                DcParams p, int want_rgb, float* __restrict__ sigma,
                                                                float* __restrict__ rgb, const int64_t* __restrict__ m_dev,
-                                                               const int64_t* __restrict__ ridx, const uint4* __restrict__ pe16) {
+                                                               const int64_t* __restrict__ ridx, const uint4* __restrict__ pe16,
+                                                               float* __restrict__ y0_raw) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(DC_THREADS) dc_tc_fwd_kernel(const float* __re
             tmem_ld16(tl + 64, y);
 #pragma unroll
             for (int i = 0; i < 16; ++i) y[i] += bias[64 + i];
-            if (valid) sigma[m] = fmaxf(y[0], 0.f);
+            if (valid) { sigma[m] = fmaxf(y[0], 0.f); if (y0_raw) y0_raw[m] = y[0]; }   // y0_raw: pre-activation (DD field)
             if (want_rgb) { tile_store8(T0, 0, row, y); tile_store8(T0, 1, row, y + 8); }
         } else if (want_rgb && cg <= 2) {
             if (pe16) stage_cin_pe16(T0, row, cg, pa, pb);
@@ -905,7 +906,7 @@ int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray
     if (rc) return rc;
     const int64_t tiles = (M + 127) / 128;
     const int64_t cap = 2 * (int64_t)tc_num_sms();
-    dc_tc_fwd_kernel<false><<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb, nullptr, nullptr, nullptr);
+    dc_tc_fwd_kernel<false><<<(int)(tiles < cap ? tiles : cap), DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, S, M, IN, p, want_rgb, sigma, rgb, nullptr, nullptr, nullptr, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -913,7 +914,8 @@ int pag_decode_dc_fwd_tc(const float* feats, const float* lodw, const float* ray
 // device-side sample count (m_dev[0] <= M_max) and per-sample ray index: sample m uses ray_d[ridx[m]]
 int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float* ray_d, const int64_t* ridx, int64_t M_max,
                              const int64_t* m_dev, int IN, const float* const* weights, int hidden, int view_dim,
-                             int want_rgb, float* sigma, float* rgb, const void* view_pe16, int feats_img16, void* stream) {
+                             int want_rgb, float* sigma, float* rgb, float* y0_raw, const void* view_pe16, int feats_img16,
+                             void* stream) {
     if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
     if (feats_img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
@@ -927,11 +929,11 @@ int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float*
     if (feats_img16) {
         int rc = tc_set_smem(dc_tc_fwd_kernel<true>, l.total);
         if (rc) return rc;
-        dc_tc_fwd_kernel<true><<<grid, DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx, pe);
+        dc_tc_fwd_kernel<true><<<grid, DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx, pe, y0_raw);
     } else {
         int rc = tc_set_smem(dc_tc_fwd_kernel<false>, l.total);
         if (rc) return rc;
-        dc_tc_fwd_kernel<false><<<grid, DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx, pe);
+        dc_tc_fwd_kernel<false><<<grid, DC_THREADS, l.total, (cudaStream_t)stream>>>(feats, lodw, ray_d, 1, M_max, IN, p, want_rgb, sigma, rgb, m_dev, ridx, pe, y0_raw);
     }
     PAG_LAUNCH_CHECK();
     return PAG_OK;

@@ -417,7 +417,8 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
     PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inst_inv_temp,
     const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
     const float* __restrict__ g_sem, const float* __restrict__ g_inst, int64_t R, const float* __restrict__ inst_lse,
-    const float* __restrict__ scale_ptr, float* __restrict__ g_panop, const int64_t* __restrict__ m_dev, float* __restrict__ ws) {
+    const float* __restrict__ scale_ptr, float* __restrict__ g_panop, const int64_t* __restrict__ m_dev, float* __restrict__ ws,
+    float* __restrict__ gw_sem, float* __restrict__ gw_inst) {
     if (m_dev) M = min(M, __ldg(m_dev));
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint64_t bar_s;
@@ -631,6 +632,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                 Z += e; E = fmaf(e, (j < Cs) ? g[j] : 0.f, E);
             }
             const float iz = 1.f / Z, dot = E * iz, css = cs * scale;
+            if (gw_sem && valid) gw_sem[m] = dot;      // <p_s, g_ray>: d out / d weight of this sample (DD tracer: weights carry gradient)
 #pragma unroll
             for (int j = 0; j < 16; ++j) g[j] = (j < Cs) ? (sem_softmax ? css * zs[j] * iz * (g[j] - dot) : css * g[j]) : 0.f;
             grad16_store(g, Gs, row, lane, db_s2);
@@ -668,6 +670,7 @@ __global__ void __launch_bounds__(PCB_THREADS) pan_comp_bwd_kernel(
                 part_s[cg][row] = dot;
                 __syncthreads(); PAG_PHASE(8);
                 dot = (part_s[0][row] + part_s[1][row]) + (part_s[2][row] + part_s[3][row]);
+                if (gw_inst && cg == 0 && valid) gw_inst[m] = dot * inv_scale;      // the cached gradients carry the loss scale
             }
             const float c2 = cs * inst_inv_temp;
 #pragma unroll
@@ -879,7 +882,7 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
                              int sem_softmax, int inst_softmax, float inst_temperature, const float* w, const float* alpha,
                              const int64_t* ridx, int64_t R, const float* g_sem, const float* g_inst, const float* inst_lse,
                              const float* grad_scale, float* g_panop, const int64_t* m_dev, float* workspace,
-                             int64_t workspace_bytes, int x_img16, void* stream) {
+                             int64_t workspace_bytes, int x_img16, float* gw_sem, float* gw_inst, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
     if (Ci > 0 && g_inst && inst_softmax && !inst_lse) return PAG_ERR_ARG;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
@@ -898,12 +901,12 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
         cudaError_t e2 = cudaFuncSetAttribute(pan_comp_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
         if (e2 != cudaSuccess) return (int)e2;
         pan_comp_bwd_kernel<true><<<nblocks, PCB_THREADS, l.total, (cudaStream_t)stream>>>(
-            feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev, ws);
+            feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev, ws, gw_sem, gw_inst);
     } else {
         cudaError_t e2 = cudaFuncSetAttribute(pan_comp_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, l.total);
         if (e2 != cudaSuccess) return (int)e2;
         pan_comp_bwd_kernel<false><<<nblocks, PCB_THREADS, l.total, (cudaStream_t)stream>>>(
-            feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev, ws);
+            feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax, inst_softmax, it, w, alpha, ridx, g_sem, g_inst, R, inst_lse, grad_scale, g_panop, m_dev, ws, gw_sem, gw_inst);
     }
     PAG_LAUNCH_CHECK();
     if (ws) {

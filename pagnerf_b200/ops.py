@@ -496,7 +496,7 @@ class PanCompositeFn(Function):
         if gs is not None or gi is not None:
             call("pag_pan_composite_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), ptr_array(grads), HIDDEN, Cs, Ci,
                  ss, is_, it, ptr(w_), ptr(a_), ptr(r_), int(a_.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(grad_scale(gs, gi)), ptr(gp), None,
-                 *_pan_bwd_workspace(M, IN, Cs, Ci, f.device), 0)
+                 *_pan_bwd_workspace(M, IN, Cs, Ci, f.device), 0, None, None)
         elif gp is not None:
             gp.zero_()
         return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
@@ -694,7 +694,9 @@ class FusedTraceFn(Function):
         # fp16 operand-image interchange between the encoders and the tensor-core decoders (one bulk copy per 128-sample tile
         # on the decoder side, coalesced 16-byte accesses on the encoder side); the f32 [M, 2L] layout stays for compaction
         # and for the hash grids
-        img = (bool(cfg.get('img16', IMG16)) and not cfg.get('compact', COMPACT_LIVE) and IN % 8 == 0 and kind == 'permuto')
+        dd = bool(cfg.get('dd'))      # PanopticDDensity field + tracer: own panoptic density stream, weights carry gradient
+        img = (bool(cfg.get('img16', IMG16)) and not cfg.get('compact', COMPACT_LIVE) and IN % 8 == 0 and kind == 'permuto'
+               and not dd)
         Tmax = (Mmax + 127) // 128
 
         def feat_buffer():
@@ -715,7 +717,7 @@ class FusedTraceFn(Function):
             # the survivors.  The list stays ray-sorted; offsets_c / its last entry replace offsets / the sample count.
             sigma0 = torch.empty(Mmax, dtype=f32, device=dev)
             call("pag_decode_dc_fwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
-                 HIDDEN, VIEW_DIM, 0, ptr(sigma0), None, None, 0)
+                 HIDDEN, VIEW_DIM, 0, ptr(sigma0), None, None, None, 0)
             offsets_c = torch.empty(N + 1, dtype=i64, device=dev)
             call("pag_compact_count", ptr(sigma0), ptr(offsets), N, ptr(counts), ptr(offsets_c))
             ridx_c = torch.empty(Mmax, dtype=i64, device=dev)
@@ -747,8 +749,9 @@ class FusedTraceFn(Function):
             pe16 = torch.empty(N, 32, dtype=torch.float16, device=dev)
             call("pag_view_pe16", ptr(d), N, ptr(pe16))
         ctx.pe16 = pe16
+        y0_raw = torch.empty(Mmax, dtype=f32, device=dev) if (dd and (Cs or Ci)) else None
         call("pag_decode_dc_fwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
-             HIDDEN, VIEW_DIM, int(want_rgb), ptr(sigma), ptr(rgb), ptr(pe16), int(img))
+             HIDDEN, VIEW_DIM, int(want_rgb), ptr(sigma), ptr(rgb), ptr(y0_raw), ptr(pe16), int(img))
         wgt = torch.empty(Mmax, dtype=f32, device=dev)
         T = torch.empty(Mmax, dtype=f32, device=dev)
         alpha = torch.empty(N, 1, dtype=f32, device=dev)
@@ -761,6 +764,7 @@ class FusedTraceFn(Function):
              ptr(offsets), N, bgw, ptr(wgt), ptr(T), ptr(alpha), ptr(hit), ptr(rgb_o), ptr(rgbsum), ptr(dep_o), None, None)
         sem_o = inst_o = None
         ctx.lse = None
+        dd_saved = (None,) * 6
         if Cs or Ci:
             sem_o = torch.zeros(N, Cs, dtype=f32, device=dev) if Cs else None
             inst_o = torch.zeros(N, Ci, dtype=f32, device=dev) if Ci else None
@@ -768,13 +772,26 @@ class FusedTraceFn(Function):
                 main.wait_stream(side)
             a, b = {'delta': (feats, dfeats), 'separate': (dfeats, None), 'appearance': (feats, None)}[src]
             lse = torch.empty(Mmax, dtype=f32, device=dev) if (Ci and cfg['inst_softmax']) else None
-            call("pag_pan_composite_fwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), HIDDEN, Cs, Ci,
+            pw, pa = wgt, alpha
+            if dd:
+                # panoptic density stream (pc_nerf/panoptic_dd_nef.py:236-245, tracers/panoptic_dd_packed_rf_tracer.py:128-137):
+                # tau_p = relu(y0.detach() + delta_density(panop)) * delta -> integration weights that carry gradient
+                tau_p = torch.empty(Mmax, dtype=f32, device=dev)
+                call("pag_linear_head_fwd_dyn", ptr(a), ptr(b), ptr(lodw), Mmax, ptr(m_dev), IN, ptr(w[20]), ptr(w[21]), ptr(y0_raw), 1,
+                     ptr(deltas), ptr(tau_p))
+                pw = torch.empty(Mmax, dtype=f32, device=dev)
+                T_p = torch.empty(Mmax, dtype=f32, device=dev)
+                call("pag_expint_fwd", ptr(tau_p), ptr(offsets), N, ptr(pw), ptr(T_p))
+                pa = torch.empty(N, 1, dtype=f32, device=dev)
+                call("pag_sum_reduce_fwd", ptr(pw), 1, ptr(offsets), N, ptr(pa))
+                dd_saved = (tau_p, pw, T_p, pa, sem_o, inst_o)
+            call("pag_pan_composite_fwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:20]), HIDDEN, Cs, Ci,
                  int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
-                 ptr(wgt), ptr(alpha), ptr(ridx), ptr(sem_o), ptr(inst_o), ptr(lse), ptr(m_dev), int(img))
+                 ptr(pw), ptr(pa), ptr(ridx), ptr(sem_o), ptr(inst_o), ptr(lse), ptr(m_dev), int(img))
             ctx.lse = lse
         ctx.cfg, ctx.img, ctx.IN = cfg, img, IN
         ctx.save_for_backward(o, d, offsets, ridx, samples, depths, deltas, feats, dfeats, sigma, rgb, wgt, T, alpha, rgbsum,
-                              tb, dtb, lodw, *w)
+                              tb, dtb, lodw, *dd_saved, *w)
         ctx.mark_non_differentiable(hit)
         ctx.last_m_dev = m_all
         return alpha, hit, rgb_o, dep_o, sem_o, inst_o, m_all
@@ -783,7 +800,7 @@ class FusedTraceFn(Function):
     @once_differentiable
     def backward(ctx, g_alpha, g_hit, g_rgb, g_depth, g_sem, g_inst, g_m):
         (o, d, offsets, ridx, samples, depths, deltas, feats, dfeats, sigma, rgb, wgt, T, alpha, rgbsum, tb, dtb, lodw,
-         *w) = ctx.saved_tensors
+         dd_tau, dd_w, dd_T, dd_alpha, dd_sem, dd_inst, *w) = ctx.saved_tensors
         cfg = ctx.cfg
         N, dev = o.shape[0], o.device
         img, IN = ctx.img, ctx.IN
@@ -823,10 +840,24 @@ class FusedTraceFn(Function):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 scale_p = grad_scale_dyn(gs if gs is not None else gi, gi if gs is not None else None, None)
-                call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:]), ptr_array(grads[10:]), HIDDEN,
+                dds = (dd_tau, dd_w, dd_T, dd_alpha, dd_sem, dd_inst) if dd_tau is not None else None
+                pw, pa = (dd_w, dd_alpha) if dds is not None else (wgt, alpha)
+                gw_sem = torch.empty(Mmax, dtype=f32, device=dev) if (dds is not None and gs is not None) else None
+                gw_inst = torch.empty(Mmax, dtype=f32, device=dev) if (dds is not None and gi is not None) else None
+                call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:20]), ptr_array(grads[10:20]), HIDDEN,
                      Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
-                     ptr(wgt), ptr(alpha), ptr(ridx), int(alpha.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev),
-                     *_pan_bwd_workspace(Mmax, IN, Cs, Ci, dev), int(img))
+                     ptr(pw), ptr(pa), ptr(ridx), int(alpha.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev),
+                     *_pan_bwd_workspace(Mmax, IN, Cs, Ci, dev), int(img), ptr(gw_sem), ptr(gw_inst))
+                if dds is not None:
+                    # the panoptic weights carry gradient: d L / d w_p -> reverse scan -> tau_p -> ReLU gate -> delta-density head
+                    tau_p, _, T_p, _, sem_o, inst_o = dds
+                    gwt = torch.empty(Mmax, dtype=f32, device=dev)
+                    call("pag_dd_weight_grads", ptr(gs), ptr(sem_o) if gs is not None else None, Cs, ptr(gi),
+                         ptr(inst_o) if gi is not None else None, Ci, ptr(pa), ptr(gw_sem), ptr(gw_inst), ptr(offsets), N, ptr(gwt))
+                    gtau = torch.empty(Mmax, dtype=f32, device=dev)
+                    call("pag_expint_bwd", ptr(gwt), ptr(pw), ptr(T_p), ptr(offsets), N, ptr(gtau))
+                    call("pag_linear_head_bwd_dyn", ptr(a), ptr(b), ptr(lodw), Mmax, ptr(m_dev), IN, ptr(w[20]), ptr(gtau), ptr(tau_p),
+                         ptr(deltas), ptr(g_panop), 1, ptr(grads[20]), ptr(grads[21]))
                 if need_gp:
                     _enc_bwd(kind, cfg['dgrid'], samples, Mmax, m_dev, ph, dtb, g_panop, scale_p, g_dtable, None, img)
                     if sync:

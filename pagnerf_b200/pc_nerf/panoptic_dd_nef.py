@@ -53,11 +53,38 @@ class PanopticDDensityNeF(PanopticNeF):
         self._register_forward_function(self.rgb_semantics, ["density", "rgb", "delta_density", "panoptic_density",
                                                              "semantics", "inst_embedding"])
 
-    def fused_panoptic_ok(self, channels):     # the fused kernels composite with the detached colour density: not this model
+    def fused_panoptic_ok(self, channels):     # the modular fused kernels composite with the detached colour density: not this model
         return False
 
-    def fused_trace_cfg(self, channels, rays, num_steps, bg_color):
-        return None
+    def fused_trace_cfg(self, channels, rays, num_steps, bg_color, dd=False):
+        """Sync-free fused trace with the panoptic density stream (ops.FusedTraceFn, cfg['dd']).  Only for the DD tracer (dd=True):
+        PanopticPackedRFTracer would composite the panoptic channels with the detached colour density."""
+        if not dd or self.separate_sem_grid or not (self.sem_softmax and self.inst_softmax):
+            return None
+        if self.sem_sigmoid or self.sem_normalize or self.inst_sigmoid or self.inst_normalize:
+            return None
+        fused_ok, self.fused_panoptic_ok = self.fused_panoptic_ok, lambda channels: True    # shapes are checked by the base method
+        try:
+            ok_shapes = (self.effective_feature_dim <= 48 and self.effective_feature_dim % 4 == 0 and self.num_classes <= 16
+                         and self.num_instances <= 208)
+            cfg = super().fused_trace_cfg(channels, rays, num_steps, bg_color) if ok_shapes else None
+        finally:
+            del self.fused_panoptic_ok
+        if cfg is not None:
+            cfg['dd'] = True
+        return cfg
+
+    def _pan_src(self):
+        return 'delta'
+
+    def fused_trace_tensors(self):
+        table, dtable, wts = super().fused_trace_tensors()
+        dec = self.decoder_delta_density          # Linear(+Identity) layers collapsed into one map (autograd reaches both layers)
+        w, bias = dec.lout.weight, dec.lout.bias
+        for l in reversed(list(dec.layers)):
+            bias = bias + w @ l.bias
+            w = w @ l.weight
+        return table, dtable, list(wts) + [w, bias]
 
     def _density_pre(self, feats):
         """density_feats[..., 0:1] BEFORE the ReLU, detached (:243): the semantic-head kernel on the density decoder's weights."""

@@ -12,7 +12,6 @@ from .panoptic_packed_rf_tracer import PanopticPackedRFTracer, sigma_sparsity_lo
 
 
 class PanopticDDensityPackedRFTracer(PanopticPackedRFTracer):
-    allow_fused = False      # the fused trace composites with the detached colour density
 
     def trace(self, nef, channels, extra_channels, rays, lod_idx=None, raymarch_type='voxel', num_steps=64, step_size=1.0,
               bg_color='white', stage=None):
@@ -24,6 +23,22 @@ class PanopticDDensityPackedRFTracer(PanopticPackedRFTracer):
             depth = None
         if lod_idx is None:
             lod_idx = nef.grid.num_lods - 1
+        plain = not extra_channels and not (self.ray_sparcity_reg > 0.0 and stage == 'train')
+        if plain and raymarch_type == 'ray' and self.allow_fused and hasattr(nef, 'fused_trace_cfg'):
+            try:
+                cfg = nef.fused_trace_cfg(channels, rays, num_steps, bg_color, dd=True)
+            except TypeError:          # a field without the panoptic density stream
+                cfg = None
+            if cfg is not None and cfg.get('dd'):
+                # training mode, sync-free: march -> encode -> decode -> two compositing streams as one autograd node
+                table, dtable, wts = nef.fused_trace_tensors()
+                alpha, hit, rgb, depth_o, sem, inst, m_dev = ops.FusedTraceFn.apply(rays.origins, rays.dirs, cfg, table, dtable, *wts)
+                self.last_num_samples = m_dev
+                outputs = {'alpha': alpha, 'hit': hit}
+                for name, val in (('rgb', rgb), ('depth', depth_o), ('semantics', sem), ('inst_embedding', inst)):
+                    if name in channels:
+                        outputs[name] = val
+                return RenderBuffer(**outputs)
         raymarch_results = nef.grid.raymarch(rays, level=nef.grid.active_lods[lod_idx], num_samples=num_steps,
                                              raymarch_type=raymarch_type)
         ridx, pidx, samples, depths, deltas = raymarch_results[:5]

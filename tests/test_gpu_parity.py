@@ -700,3 +700,35 @@ def test_fused_trace_img16_interchange_equals_f32_rows(cuda_lib):
     for a, b in zip(g1, g0):
         assert torch.isfinite(a).all()
         assert_close_norm(a, b, rel_l2=5e-2, max_frac=0.3, msg="img16 vs f32-row grad")
+
+
+def test_fused_dd_trace_equals_stepwise(cuda_lib):
+    """PanopticDDensityNeF + PanopticDDensityPackedRFTracer: the sync-free fused trace with the panoptic density stream
+    (weights carrying gradient: heads backward -> <p, g> per sample -> reverse scan -> ReLU gate -> delta-density head) vs the
+    step-by-step path that is pinned by the reference-made golden."""
+    from pagnerf_b200.tracers import PanopticDDensityPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_dd_permuto_ray")
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    res = []
+    for fused in (True, False):
+        nef = build_cuda_nef(g, DEV)
+        nef.decoder_precision = 'fp16'
+        tracer = PanopticDDensityPackedRFTracer(raymarch_type='ray', num_steps=int(g["num_steps"]), bg_color='white')
+        tracer.allow_fused = fused
+        o = torch.from_numpy(g["o"]).to(DEV).requires_grad_(True)
+        d = torch.from_numpy(g["d"]).to(DEV).requires_grad_(True)
+        rb = tracer(nef, channels=chans, rays=Rays(origins=o, dirs=d, dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+        if fused:
+            assert torch.is_tensor(tracer.last_num_samples), "the DD tracer must take the fused path"
+        loss = sum((getattr(rb, c) * torch.from_numpy(g["gw_" + c]).to(DEV)).sum() for c in chans)
+        loss.backward()
+        res.append(({c: getattr(rb, c).detach() for c in chans + ['alpha', 'hit']},
+                    {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in nef.named_parameters()}, o.grad, d.grad))
+    assert torch.equal(res[0][0]['hit'], res[1][0]['hit'])
+    for c in chans + ['alpha']:
+        assert_close(res[0][0][c], res[1][0][c], rtol=2e-3, atol_scale=2e-3, msg=c)
+    for k in res[0][1]:
+        assert_close_norm(res[0][1][k], res[1][1][k], rel_l2=2e-2, max_frac=5e-2, msg="grad " + k)
+    assert_close_norm(res[0][2], res[1][2], rel_l2=2e-2, max_frac=5e-2, msg="grad origins")
+    assert_close_norm(res[0][3], res[1][3], rel_l2=2e-2, max_frac=5e-2, msg="grad dirs")
