@@ -100,14 +100,15 @@ def loss_fn(rb_rgb, rb_sem, rb_inst, t_rgb, t_sem, t_inst):
 class Workload:
     """The training-step hot path on one GPU through the plugin classes."""
 
-    def __init__(self, device, n_rays=N_RAYS, seed=0, n_batches=4, amp=True):
+    def __init__(self, device, n_rays=N_RAYS, seed=0, n_batches=4, amp=True, dd=False):
+        """dd: the PanopticDDensity field + tracer pair (7 of the reference's 13 bup20 configs) instead of the delta field."""
         self.amp = amp
-        from pagnerf_b200.pc_nerf import PanopticDeltaNeF
-        from pagnerf_b200.tracers import PanopticPackedRFTracer
+        from pagnerf_b200.pc_nerf import PanopticDeltaNeF, PanopticDDensityNeF
+        from pagnerf_b200.tracers import PanopticPackedRFTracer, PanopticDDensityPackedRFTracer
         from pagnerf_b200 import spc
         torch.manual_seed(seed)
         self.device, self.n_rays = device, n_rays
-        self.nef = PanopticDeltaNeF(**NEF_KW)
+        self.nef = (PanopticDDensityNeF if dd else PanopticDeltaNeF)(**NEF_KW)
         pts = torch.from_numpy(make_scene(LEVEL, seed))
         octree = spc.unbatched_points_to_octree(pts, LEVEL)
         for g in (self.nef.grid, self.nef.delta_grid):
@@ -117,7 +118,8 @@ class Workload:
             self.nef.grid.embedder.lattice_values.mul_(1e3)
             self.nef.delta_grid.embedder.lattice_values.mul_(1e3)
         self.nef = self.nef.to(device)
-        self.tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=NUM_STEPS, bg_color='white', ray_max_travel=2.0)
+        self.tracer = (PanopticDDensityPackedRFTracer if dd else PanopticPackedRFTracer)(
+            raymarch_type='ray', num_steps=NUM_STEPS, bg_color='white', ray_max_travel=2.0)
         self.params = [p for p in self.nef.parameters()]
         self.channels = ['rgb', 'depth', 'semantics', 'inst_embedding']
         # pool of host (pinned) batches; step i uses batch i % n_batches
@@ -326,11 +328,13 @@ def main():
     ap.add_argument("--cpu-sample-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--dd", action="store_true", help="PanopticDDensity field + tracer (own panoptic density stream) instead of the "
+                                                      "BASELINE config-2 delta field; informational, not the headline workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    config = {"workload": "PanopticDeltaNeF + permutohedral grid (L=24,F=2,T=2^18 x2), BUP20-shaped 1MP frame, "
+    config = {"workload": ("PanopticDDensityNeF + DD tracer" if args.dd else "PanopticDeltaNeF") + " + permutohedral grid (L=24,F=2,T=2^18 x2), BUP20-shaped 1MP frame, "
                           f"{args.rays} rays/step/GPU, occtree 'ray' march {NUM_STEPS} steps, level-7 pruned octree; "
                           "rgb+depth+semantics(6)+inst(200); fwd+bwd",
               "rays_per_gpu": args.rays, "parallelism": f"ray-sharded dp{world}" if world > 1 else "single"}
@@ -364,7 +368,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
         trace("process group up")
-    wl = Workload(device, args.rays, seed=rank)
+    wl = Workload(device, args.rays, seed=rank, dd=args.dd)
     trace("workload built")
     if world > 1:
         from pagnerf_b200 import ops

@@ -168,10 +168,12 @@ int pag_linear_head_bwd(const float* feats, const float* dfeats, const float* lo
  * relu(y0.detach() + delta_density) * delta in one pass; the backward gates g with the forward output `gate` (ReLU), multiplies
  * it by post and can accumulate into g_x. */
 int pag_linear_head_fwd_dyn(const float* feats, const float* dfeats, const float* lodw, int64_t M_max, const int64_t* m_dev, int IN,
-                            const float* w, const float* b, const float* pre, int relu, const float* post, float* y, void* stream);
+                            const float* w, const float* b, const float* pre, int relu, const float* post, float* y, int x_img16,
+                            void* stream);
 int pag_linear_head_bwd_dyn(const float* feats, const float* dfeats, const float* lodw, int64_t M_max, const int64_t* m_dev, int IN,
                             const float* w, const float* g, const float* gate, const float* post, float* g_x, int accumulate_x,
-                            float* g_w, float* g_b, void* stream);
+                            float* g_w, float* g_b, int x_img16, const float* img_scale, void* stream);
+/* x_img16 != 0: feats / dfeats / g_x are fp16 operand images (g_x accumulated, multiplied by *img_scale like the heads' dX). */
 /* DD tracer backward glue (tracers/panoptic_dd_packed_rf_tracer.py:128-162): gw[s] = alpha_p[ray] * (gw_sem + gw_inst)[s]
  * + sum_c g[ray][c] out[ray][c] / alpha_p[ray], the gradient of the loss w.r.t. the panoptic integration weights. */
 int pag_dd_weight_grads(const float* g_sem, const float* out_sem, int Cs, const float* g_inst, const float* out_inst, int Ci,

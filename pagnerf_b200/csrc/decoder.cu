@@ -14,6 +14,7 @@
 // weights (no transpose), and accumulates dW with a cooperative register-tiled (4x4) product
 // over the CTA's 128-sample tile straight out of the staging columns.
 #include "decoder_common.cuh"
+#include <cuda_fp16.h>
 
 // cooperative copy of W[rows][cols] (global) into smem [pad4(rows)][colsp], zero padded
 __device__ __forceinline__ void stage_weights(float* dst, const float* __restrict__ W, int rows, int cols, int colsp) {
@@ -742,6 +743,122 @@ __global__ void __launch_bounds__(256) linear_head_bwd_kernel(const float* __res
     for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
     if (lane == 0 && sb != 0.f) red_add_f32(g_b, sb);
 }
+// the same head on the fp16 operand images of the fused trace (tile t = m / 128: [IN/8 chunks][128 rows][8 halfs], see
+// pag_permuto_fwd_img16_dyn): coalesced 16-byte accesses; x = half(feats) + half(dfeats) exactly as the heads kernels form it.
+// The backward adds its input gradient, multiplied by the loss scale *img_scale the heads' dX image carries, into that image.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&x)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 hadd8(const uint4& a, const uint4& b) {
+    uint4 r;
+    const __half2 *x = reinterpret_cast<const __half2*>(&a), *y = reinterpret_cast<const __half2*>(&b);
+    __half2* o = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __hadd2(x[i], y[i]);
+    return r;
+}
+__global__ void linear_head_fwd_img_kernel(const uint4* __restrict__ fimg, const uint4* __restrict__ dimg,
+                                           const float* __restrict__ lodw, int64_t M, int IN, const float* __restrict__ w,
+                                           const float* __restrict__ b, float* __restrict__ y, const float* __restrict__ pre,
+                                           int relu, const float* __restrict__ post, const int64_t* __restrict__ m_dev) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m_dev) M = min(M, __ldg(m_dev));
+    if (m >= M) return;
+    const int C = IN >> 3;
+    const int64_t base = (m >> 7) * C * 128 + (m & 127);
+    float acc = __ldg(b);
+    for (int c = 0; c < C; ++c) {
+        uint4 u = __ldg(fimg + base + c * 128);
+        if (dimg) u = hadd8(u, __ldg(dimg + base + c * 128));
+        float x[8];
+        unpack8(u, x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(x[k] * (lodw ? __ldg(lodw + 8 * c + k) : 1.f), __ldg(w + 8 * c + k), acc);
+    }
+    if (pre) acc += pre[m];
+    if (relu) acc = fmaxf(acc, 0.f);
+    if (post) acc *= post[m];
+    y[m] = acc;
+}
+// Persistent grid: every thread walks samples with a grid stride and keeps the weight-gradient partials of all (<= 64) input
+// features in registers; one shuffle / shared-memory reduction and IN atomics per CTA at the end (a per-warp, per-feature
+// reduction with an atomic each made 590 k atomics on 48 addresses: 0.52 ms for 392 k samples).
+#define LH_MAXC 8
+__global__ void __launch_bounds__(256) linear_head_bwd_img_kernel(const uint4* __restrict__ fimg, const uint4* __restrict__ dimg,
+                                                                  const float* __restrict__ lodw, int64_t M, int IN,
+                                                                  const float* __restrict__ w, const float* __restrict__ g,
+                                                                  uint4* __restrict__ gx_img, const float* __restrict__ img_scale,
+                                                                  float* __restrict__ g_w, float* __restrict__ g_b,
+                                                                  const float* __restrict__ gate, const float* __restrict__ post,
+                                                                  const int64_t* __restrict__ m_dev) {
+    __shared__ float red_s[8][8 * LH_MAXC + 1];
+    if (m_dev) M = min(M, __ldg(m_dev));
+    const int C = IN >> 3;
+    const float scale = img_scale ? __ldg(img_scale) : 1.f;
+    float acc[LH_MAXC][8];
+#pragma unroll
+    for (int c = 0; c < LH_MAXC; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
+    float accb = 0.f;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+        float gm = g[m];
+        if (post) gm *= post[m];
+        if (gate && !(gate[m] > 0.f)) gm = 0.f;
+        if (gm == 0.f) continue;
+        const int64_t base = (m >> 7) * C * 128 + (m & 127);
+        const float gs = gm * scale;
+        accb += gm;
+#pragma unroll
+        for (int c = 0; c < LH_MAXC; ++c) {
+            if (c < C) {
+                uint4 u = __ldg(fimg + base + c * 128);
+                if (dimg) u = hadd8(u, __ldg(dimg + base + c * 128));
+                float x[8];
+                unpack8(u, x);
+                if (gx_img) {      // accumulate into the heads' dX image (scaled)
+                    uint4 gi = gx_img[base + c * 128];
+                    __half2* gh = reinterpret_cast<__half2*>(&gi);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float l0 = lodw ? __ldg(lodw + 8 * c + 2 * k) : 1.f, l1 = lodw ? __ldg(lodw + 8 * c + 2 * k + 1) : 1.f;
+                        const float2 f = __half22float2(gh[k]);
+                        gh[k] = __floats2half2_rn(fmaf(gs * l0, __ldg(w + 8 * c + 2 * k), f.x), fmaf(gs * l1, __ldg(w + 8 * c + 2 * k + 1), f.y));
+                    }
+                    gx_img[base + c * 128] = gi;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[c][k] = fmaf(gm * x[k], lodw ? __ldg(lodw + 8 * c + k) : 1.f, acc[c][k]);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < LH_MAXC; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = acc[c][k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red_s[wid][8 * c + k] = v;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accb += __shfl_xor_sync(0xffffffffu, accb, o);
+    if (lane == 0) red_s[wid][8 * LH_MAXC] = accb;
+    __syncthreads();
+    for (int i = threadIdx.x; i <= 8 * LH_MAXC; i += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += red_s[k][i];
+        if (v != 0.f) {
+            if (i < IN) red_add_f32(g_w + i, v);
+            else if (i == 8 * LH_MAXC) red_add_f32(g_b, v);
+        }
+    }
+}
+
 // DD tracer backward glue: the panoptic outputs are out[ray] = alpha_p * sum_s w_p[s] f[s] with alpha_p = sum_s w_p[s] and the
 // weights NOT detached (tracers/panoptic_dd_packed_rf_tracer.py:128-162).  Given the per-sample <f_s, g_ray> from the fused heads
 // backward: d L / d w_p[s] = alpha_p * (gw_sem + gw_inst)[s] + d L / d alpha_p[ray],
@@ -872,18 +989,33 @@ int pag_linear_head_bwd(const float* feats, const float* dfeats, const float* lo
 // fused-trace variants: y = post * relu?(pre + head(x)) with the sample count on the device; the backward gates g with the
 // forward output (ReLU), multiplies it by post, and can accumulate into g_x (the heads' dX is already there)
 int pag_linear_head_fwd_dyn(const float* feats, const float* dfeats, const float* lodw, int64_t M_max, const int64_t* m_dev, int IN,
-                            const float* w, const float* b, const float* pre, int relu, const float* post, float* y, void* stream) {
-    if (IN <= 0) return PAG_ERR_ARG;
+                            const float* w, const float* b, const float* pre, int relu, const float* post, float* y, int x_img16,
+                            void* stream) {
+    if (IN <= 0 || (x_img16 && (IN & 7))) return PAG_ERR_ARG;
     if (M_max == 0) return PAG_OK;
+    if (x_img16) {
+        linear_head_fwd_img_kernel<<<pag_grid(M_max, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint4*>(feats), reinterpret_cast<const uint4*>(dfeats), lodw, M_max, IN, w, b, y, pre, relu, post, m_dev);
+        PAG_LAUNCH_CHECK();
+        return PAG_OK;
+    }
     linear_head_fwd_kernel<<<pag_grid(M_max, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M_max, IN, w, b, y, pre, relu, post, m_dev);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
 int pag_linear_head_bwd_dyn(const float* feats, const float* dfeats, const float* lodw, int64_t M_max, const int64_t* m_dev, int IN,
                             const float* w, const float* g, const float* gate, const float* post, float* g_x, int accumulate_x,
-                            float* g_w, float* g_b, void* stream) {
-    if (IN <= 0) return PAG_ERR_ARG;
+                            float* g_w, float* g_b, int x_img16, const float* img_scale, void* stream) {
+    if (IN <= 0 || (x_img16 && ((IN & 7) || !accumulate_x))) return PAG_ERR_ARG;
     if (M_max == 0) return PAG_OK;
+    if (x_img16) {
+        const int gridp = pag_grid(M_max, 256) < 592 ? pag_grid(M_max, 256) : 592;     // persistent: ~2 resident CTAs per SM, 2 waves
+        linear_head_bwd_img_kernel<<<gridp, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint4*>(feats), reinterpret_cast<const uint4*>(dfeats), lodw, M_max, IN, w, g,
+            reinterpret_cast<uint4*>(g_x), img_scale, g_w, g_b, gate, post, m_dev);
+        PAG_LAUNCH_CHECK();
+        return PAG_OK;
+    }
     linear_head_bwd_kernel<<<pag_grid(M_max, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M_max, IN, w, g, g_x, g_w, g_b,
                                                                                    gate, post, accumulate_x, m_dev);
     PAG_LAUNCH_CHECK();

@@ -696,7 +696,7 @@ class FusedTraceFn(Function):
         # and for the hash grids
         dd = bool(cfg.get('dd'))      # PanopticDDensity field + tracer: own panoptic density stream, weights carry gradient
         img = (bool(cfg.get('img16', IMG16)) and not cfg.get('compact', COMPACT_LIVE) and IN % 8 == 0 and kind == 'permuto'
-               and not dd)
+               )
         Tmax = (Mmax + 127) // 128
 
         def feat_buffer():
@@ -778,7 +778,7 @@ class FusedTraceFn(Function):
                 # tau_p = relu(y0.detach() + delta_density(panop)) * delta -> integration weights that carry gradient
                 tau_p = torch.empty(Mmax, dtype=f32, device=dev)
                 call("pag_linear_head_fwd_dyn", ptr(a), ptr(b), ptr(lodw), Mmax, ptr(m_dev), IN, ptr(w[20]), ptr(w[21]), ptr(y0_raw), 1,
-                     ptr(deltas), ptr(tau_p))
+                     ptr(deltas), ptr(tau_p), int(img))
                 pw = torch.empty(Mmax, dtype=f32, device=dev)
                 T_p = torch.empty(Mmax, dtype=f32, device=dev)
                 call("pag_expint_fwd", ptr(tau_p), ptr(offsets), N, ptr(pw), ptr(T_p))
@@ -857,7 +857,7 @@ class FusedTraceFn(Function):
                     gtau = torch.empty(Mmax, dtype=f32, device=dev)
                     call("pag_expint_bwd", ptr(gwt), ptr(pw), ptr(T_p), ptr(offsets), N, ptr(gtau))
                     call("pag_linear_head_bwd_dyn", ptr(a), ptr(b), ptr(lodw), Mmax, ptr(m_dev), IN, ptr(w[20]), ptr(gtau), ptr(tau_p),
-                         ptr(deltas), ptr(g_panop), 1, ptr(grads[20]), ptr(grads[21]))
+                         ptr(deltas), ptr(g_panop), 1, ptr(grads[20]), ptr(grads[21]), int(img), ptr(scale_p))
                 if need_gp:
                     _enc_bwd(kind, cfg['dgrid'], samples, Mmax, m_dev, ph, dtb, g_panop, scale_p, g_dtable, None, img)
                     if sync:

@@ -669,7 +669,8 @@ def test_fused_trace_live_compaction_is_exact(cuda_lib):
         assert_close(g1[n], g0[n], rtol=1e-4, atol_scale=2e-5, msg=n)   # summation order (atomics, tile grouping) differs
 
 
-def test_fused_trace_img16_interchange_equals_f32_rows(cuda_lib):
+@pytest.mark.parametrize("dd", [False, True])
+def test_fused_trace_img16_interchange_equals_f32_rows(cuda_lib, dd):
     """fp16 operand-image interchange between encoders and tensor-core decoders (ops.IMG16: coalesced encoder stores, bulk
     tile copies, fp16 dX images) vs the f32 [M, 2L] row interchange, on the bench field (L = 24, 200 instances): same
     step, same jitter -> outputs at the fp16 tolerance, gradients norm-wise."""
@@ -680,7 +681,7 @@ def test_fused_trace_img16_interchange_equals_f32_rows(cuda_lib):
     try:
         for img in (True, False):
             ops.IMG16 = img
-            wl = bench.Workload(dev, n_rays=2048, seed=0, n_batches=2)
+            wl = bench.Workload(dev, n_rays=2048, seed=0, n_batches=2, dd=dd)      # dd: DD field + tracer (panoptic density stream)
             wl.keep_rb = True
             blas = wl.nef.grid.blas
             blas.fixed_jitter, blas.jitter_seed = True, 11
