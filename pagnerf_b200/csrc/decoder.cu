@@ -708,40 +708,60 @@ __global__ void linear_head_fwd_kernel(const float* __restrict__ feats, const fl
 }
 // g_x[m,k] (+)= g[m] * lodw[k] * w[k] (same for feats and dfeats); g_w[k] += sum_m g[m] * x[m,k]; g_b += sum_m g[m].
 // gate (nullable): the forward output; g is zeroed where gate <= 0 (ReLU) ; post as in the forward.
+// Persistent grid, weight-gradient partials of all (<= 64) input features in registers, one reduction + IN atomics per CTA.
+#define LHR_MAXIN 64
 __global__ void __launch_bounds__(256) linear_head_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ dfeats,
                                                               const float* __restrict__ lodw, int64_t M, int IN,
                                                               const float* __restrict__ w, const float* __restrict__ g,
                                                               float* __restrict__ g_x, float* __restrict__ g_w, float* __restrict__ g_b,
                                                               const float* __restrict__ gate, const float* __restrict__ post,
                                                               int accumulate_x, const int64_t* __restrict__ m_dev) {
-    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float red_s[8][LHR_MAXIN + 1];
     if (m_dev) M = min(M, __ldg(m_dev));
-    if ((m & ~31ll) >= M) return;
-    const bool valid = m < M;
-    float gm = valid ? g[m] : 0.f;
-    if (valid && post) gm *= post[m];
-    if (valid && gate && !(gate[m] > 0.f)) gm = 0.f;
-    const int lane = threadIdx.x & 31;
-    for (int k = 0; k < IN; ++k) {
-        const float lw = lodw ? __ldg(lodw + k) : 1.f;
-        float x = 0.f;
-        if (valid) {
-            x = feats[m * IN + k];
-            if (dfeats) x += dfeats[m * IN + k];
-            if (g_x) {
-                const float v = gm * lw * __ldg(w + k);
-                if (accumulate_x) g_x[m * IN + k] += v; else g_x[m * IN + k] = v;
+    float acc[LHR_MAXIN];
+#pragma unroll
+    for (int k = 0; k < LHR_MAXIN; ++k) acc[k] = 0.f;
+    float accb = 0.f;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+        float gm = g[m];
+        if (post) gm *= post[m];
+        if (gate && !(gate[m] > 0.f)) gm = 0.f;
+        accb += gm;
+#pragma unroll
+        for (int k = 0; k < LHR_MAXIN; ++k) {
+            if (k < IN) {
+                const float lw = lodw ? __ldg(lodw + k) : 1.f;
+                float x = feats[m * IN + k];
+                if (dfeats) x += dfeats[m * IN + k];
+                if (g_x) {
+                    const float v = gm * lw * __ldg(w + k);
+                    if (accumulate_x) g_x[m * IN + k] += v; else g_x[m * IN + k] = v;
+                }
+                acc[k] = fmaf(gm * x, lw, acc[k]);
             }
         }
-        float s = gm * x * lw;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && s != 0.f) red_add_f32(g_w + k, s);
     }
-    float sb = gm;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
-    if (lane == 0 && sb != 0.f) red_add_f32(g_b, sb);
+    for (int k = 0; k < LHR_MAXIN; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red_s[wid][k] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accb += __shfl_xor_sync(0xffffffffu, accb, o);
+    if (lane == 0) red_s[wid][LHR_MAXIN] = accb;
+    __syncthreads();
+    for (int i = threadIdx.x; i <= LHR_MAXIN; i += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += red_s[k][i];
+        if (v != 0.f) {
+            if (i < IN) red_add_f32(g_w + i, v);
+            else if (i == LHR_MAXIN) red_add_f32(g_b, v);
+        }
+    }
 }
 // the same head on the fp16 operand images of the fused trace (tile t = m / 128: [IN/8 chunks][128 rows][8 halfs], see
 // pag_permuto_fwd_img16_dyn): coalesced 16-byte accesses; x = half(feats) + half(dfeats) exactly as the heads kernels form it.
@@ -981,8 +1001,9 @@ int pag_linear_head_bwd(const float* feats, const float* dfeats, const float* lo
                         const float* g, float* g_x, float* g_w, float* g_b, void* stream) {
     if (IN <= 0) return PAG_ERR_ARG;
     if (M == 0) return PAG_OK;
-    linear_head_bwd_kernel<<<pag_grid(M, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M, IN, w, g, g_x, g_w, g_b,
-                                                                               nullptr, nullptr, 0, nullptr);
+    if (IN > LHR_MAXIN) return PAG_ERR_UNSUPPORTED;
+    linear_head_bwd_kernel<<<pag_grid(M, 256) < 592 ? pag_grid(M, 256) : 592, 256, 0, (cudaStream_t)stream>>>(
+        feats, dfeats, lodw, M, IN, w, g, g_x, g_w, g_b, nullptr, nullptr, 0, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -1016,8 +1037,9 @@ int pag_linear_head_bwd_dyn(const float* feats, const float* dfeats, const float
         PAG_LAUNCH_CHECK();
         return PAG_OK;
     }
-    linear_head_bwd_kernel<<<pag_grid(M_max, 256), 256, 0, (cudaStream_t)stream>>>(feats, dfeats, lodw, M_max, IN, w, g, g_x, g_w, g_b,
-                                                                                   gate, post, accumulate_x, m_dev);
+    if (IN > LHR_MAXIN) return PAG_ERR_UNSUPPORTED;
+    linear_head_bwd_kernel<<<pag_grid(M_max, 256) < 592 ? pag_grid(M_max, 256) : 592, 256, 0, (cudaStream_t)stream>>>(
+        feats, dfeats, lodw, M_max, IN, w, g, g_x, g_w, g_b, gate, post, accumulate_x, m_dev);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
