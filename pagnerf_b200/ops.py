@@ -4,6 +4,8 @@ PyTorch is plumbing here: it owns device memory, streams and the autograd graph;
 step of the hot path is one of our sm_100a kernels.  All functions require CUDA tensors and raise
 otherwise -- there is deliberately no CPU or library fallback.
 """
+import os
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -605,7 +607,8 @@ def _allreduce_async(t):
 # freshly initialised field (bench.py's synthetic weights: every sample has sigma > 0) the extra pass is pure overhead
 # (+0.12 ms on 392 k samples), so it is opt-in: cfg['compact'] / ops.COMPACT_LIVE.
 COMPACT_LIVE = False
-GRAD_SYNC_CHUNKS = int(__import__('os').environ.get('PAGNERF_GRAD_SYNC_CHUNKS', '1'))   # level ranges the colour-table scatter is split into when its all-reduce is pipelined (multi-GPU)
+# level ranges the colour-table scatter is split into when its all-reduce is pipelined (multi-GPU; measured slower: default 1)
+GRAD_SYNC_CHUNKS = int(os.environ.get('PAGNERF_GRAD_SYNC_CHUNKS', '1'))
 IMG16 = True   # fp16 operand-image interchange between encoders and tensor-core decoders inside FusedTraceFn
 
 
