@@ -277,29 +277,7 @@ __device__ __forceinline__ void stage_x(uint8_t* tile, int row, const float* __r
         tile_store8(tile, c, row, v);
     }
 }
-// column-split variant: chunk c of the row is written by column group c % ncg
-__device__ __forceinline__ void stage_x_cg(uint8_t* tile, int row, int cg, int ncg, const float* __restrict__ a,
-                                           const float* __restrict__ b, const float* __restrict__ lodw, int IN, int nchunks, int64_t m) {
-    const float4* a4 = reinterpret_cast<const float4*>(a + m * IN);
-    const float4* b4 = b ? reinterpret_cast<const float4*>(b + m * IN) : nullptr;
-    const float4* w4 = lodw ? reinterpret_cast<const float4*>(lodw) : nullptr;
-    for (int c = cg; c < nchunks; c += ncg) {
-        float v[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int q = 2 * c + h;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * q < IN) {
-                x = __ldg(a4 + q);
-                if (b4) { const float4 y = __ldg(b4 + q); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-                if (w4) { const float4 w = __ldg(w4 + q); x.x *= w.x; x.y *= w.y; x.z *= w.z; x.w *= w.w; }
-            }
-            v[4 * h] = x.x; v[4 * h + 1] = x.y; v[4 * h + 2] = x.z; v[4 * h + 3] = x.w;
-        }
-        tile_store8(tile, c, row, v);
-    }
-}
-// L2 prefetch of the chunks stage_x_cg will read for row m of a later tile (kernels without spare shared memory)
+// L2 prefetch of the chunks of row m of a later tile (f32-row kernels without spare shared memory)
 __device__ __forceinline__ void prefetch_x_l2(const float* __restrict__ a, const float* __restrict__ b, int IN, int nchunks, int64_t m,
                                               int cg, int ncg) {
     for (int c = cg; c < nchunks; c += ncg) {
@@ -428,22 +406,6 @@ __device__ __forceinline__ void dx_copy_out(const float* __restrict__ stage, flo
     }
 }
 
-// 16 dX columns [c16, c16+16) of this thread's row -> global (float4 stores)
-__device__ __forceinline__ void store_dx16(uint32_t taddr, float* __restrict__ dst, const float* __restrict__ lodw, int IN,
-                                           int c16, float inv_scale, bool valid) {
-    float v[16];
-    tmem_ld16(taddr + c16, v);
-    if (valid) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (c16 + 4 * q < IN) {
-                const float4 w = lodw ? __ldg(reinterpret_cast<const float4*>(lodw + c16) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
-                reinterpret_cast<float4*>(dst + c16)[q] = make_float4(v[4 * q] * inv_scale * w.x, v[4 * q + 1] * inv_scale * w.y,
-                                                                     v[4 * q + 2] * inv_scale * w.z, v[4 * q + 3] * inv_scale * w.w);
-            }
-        }
-    }
-}
 // dX row (TMEM) -> global, float4 stores
 __device__ __forceinline__ void store_dx(uint32_t taddr, float* __restrict__ dst, const float* __restrict__ lodw, int IN,
                                          int INP, float inv_scale, bool valid) {

@@ -375,16 +375,6 @@ __device__ __forceinline__ void stage_w16_part(__half* img, const float* __restr
     }
 }
 
-// transposed accumulator [lanes = input features k][cols = classes j] -> gW[j][k]
-__device__ __forceinline__ void flush_dw_T(uint32_t taddr, float* __restrict__ gW, int k, int K, int C, float inv_scale) {
-    float v[16];
-    tmem_ld16(taddr, v);
-    if (k < K) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j < C) red_add_f32(gW + (size_t)j * K + k, v[j] * inv_scale);
-    }
-}
 // 16 consecutive (pre-scaled) per-ray output gradients: from the tile's fp16 cache when the ray is one of the first
 // PCB_NGC of the tile, else straight from global memory
 __device__ __forceinline__ void load_g16(const __half* __restrict__ gc_row, const float* __restrict__ grow, int c0, int C, bool vec4,
