@@ -6,19 +6,28 @@
 // ncu on the FP32-FMA kernels showed them issue/occupancy bound (profiles/r01_*): 85 GFLOP per
 // 410 k-sample step cost 8.6 ms on the FMA pipe, i.e. the contraction, not memory, bounds the step.
 //
-// Mapping: one CTA = 128 threads = one 128-sample tile; thread t owns sample row t == TMEM lane t.
+// Mapping (density/colour kernels; the modular semantic/instance kernels further down keep the simpler 128-thread form):
+//   * persistent CTAs (one per SM in the backward, two in the forward), one 128-sample tile at a time, 512 threads =
+//     4 column groups x 128 rows: warps w, w+4, w+8, w+12 share TMEM lane quadrant w % 4 and split a row's columns,
+//     which quadruples the warps that hide epilogue latency without more TMEM or shared memory;
 //   * activations / gradients live in shared memory as fp16 "tile images" [F/8][128 rows][8 halfs]
 //     (UMMA SWIZZLE_NONE canonical layout; a thread writes its row with conflict-free 16-byte stores);
-//   * weights are staged once per persistent CTA as fp16 images [IN/8][OUT rows][8 halfs];
+//   * weights are staged once per CTA as fp16 images [IN/8][OUT rows][8 halfs]; the LOD weights of the feature vector are
+//     folded into the first-layer image;
 //   * ONE image serves every operand role:  Y = X W^T (tile K-major x weight K-major),
 //     dX = G W (tile K-major x the same weight image read MN-major), dW += G^T X (tile MN-major x
 //     tile MN-major, K = the tile's 128 samples);
-//   * the layer epilogue (bias, ReLU / sigmoid / softmax, fp16 repack) is thread-per-row on the
-//     accumulator row read back with tcgen05.ld;
-//   * weight gradients never leave TMEM until the CTA has swept all its tiles (accumulate flag),
-//     bias gradients are warp reduce-scattered in registers; both are flushed once per CTA.
+//   * tcgen05.mma is issued from warp-uniform control flow (warp_id_uniform() == 0 && elect_one()): under a divergent
+//     `threadIdx.x == 0` the compiler wraps every MMA in a per-lane loop (tools/mma_bench.py: 105 -> 77 cycles per MMA);
+//   * the input tile arrives either as f32 rows (coalesced cp.async into rotation-swizzled slots, converted by the
+//     threads) or, in the fused trace, as the encoder's fp16 operand image by ONE bulk (TMA) copy per tile into a
+//     ping-pong buffer; dX leaves the same way (padded f32 staging + coalesced copy-out, or an fp16 image tile + bulk store);
+//   * weight gradients never leave TMEM until the CTA has swept all its tiles (accumulate flag); a constant "ones" tile next
+//     to each B operand adds 16 accumulator columns whose first column is the bias gradient; the CTA's partial sums go to
+//     a private workspace slice (plain stores) and ws_reduce_kernel adds the slices (red.add without a workspace).
 // Upstream gradients are multiplied by a power-of-two `grad_scale` before the fp16 repack and every
-// result is unscaled in fp32 (the GradScaler trick, applied inside the kernel).
+// result is unscaled in fp32 (the GradScaler trick, applied inside the kernel); dX images keep the scale and the encoder
+// backward removes it.
 #include "decoder_tc_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
