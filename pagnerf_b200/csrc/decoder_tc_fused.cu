@@ -5,14 +5,18 @@
 // per ray (tracers/panoptic_packed_rf_tracer.py:178-205).  At 380 k samples the [M,200] fp32 tensor alone is
 // 304 MB written + read in forward and twice that in backward -- more traffic than everything else in the step.
 // Here the probabilities never leave the SM:
-//   forward : logits (tcgen05, TMEM) -> softmax (thread per sample) -> per-warp transpose -> lanes = classes walk
-//             the warp's 32 samples, accumulate c_s * p[s][j] (c_s = alpha_ray * w_s, both detached) and flush one
-//             coalesced red.add per ray segment into out[N, C];
-//   backward: logits recomputed (tcgen05), per-ray gradients g_out[N, C] (13 MB, L2 resident) gathered per
-//             sample -- the lanes of a warp mostly share the ray, so the gathers are broadcasts --,
-//             d logits = c_s * p * (g - <p, g>) / T, then the usual dX / dW chain of decoder_tc.cu.
-// Output convention: out[ray] = alpha_p * sum_s w_p[s] * f[s]  (alpha_p, w_p detached): only the decoders and the
-// delta grid receive gradient, exactly as in the reference.
+//   forward : logits (tcgen05, TMEM) -> block-wise online softmax, ONE ex2 per logit, exponentials parked back in TMEM
+//             (tcgen05.st) -> per-warp fp16 transpose -> lanes = classes walk the warp's 32 samples, accumulate
+//             c_s * p[s][j] (c_s = alpha_ray * w_s) and flush one coalesced red.add per ray segment into out[N, C];
+//             the log2-domain log-sum-exp of every sample is kept for the backward; two CTAs per SM;
+//   backward: logits recomputed (tcgen05), p = 2^(z - lse) (one ex2 per logit), per-ray gradients g_out[N, C] read through a
+//             per-tile fp16 shared-memory cache of the tile's first 16 rays, d logits = c_s * p * (g - <p, g>) / T, then the
+//             dX / dW chain with joint first-layer MMAs (semantic | instance) and tensor-core bias gradients (ones tile).
+// 512 threads = 4 column groups x 128 rows as in decoder_tc.cu; inputs as f32 rows or as the encoders' fp16 operand images
+// (bulk copies), see decoder_tc.cu's header.
+// Output convention: out[ray] = alpha_p * sum_s w_p[s] * f[s].  For PanopticPackedRFTracer alpha_p, w_p are the detached
+// colour weights: only the decoders and the delta grid receive gradient, exactly as in the reference.  For the DD tracer they
+// come from the panoptic density and carry gradient: the backward additionally emits <p_s, g_ray> per sample (gw_sem, gw_inst).
 #include "decoder_tc_common.cuh"
 
 // ---------------------------------------------------------------------------------------------

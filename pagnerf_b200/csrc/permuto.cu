@@ -7,10 +7,12 @@
 // B200 design: one thread per sample walks ALL levels with the 4L float2 gathers of a sample
 // issued from one thread (unrolled by 4 levels -> 16 independent 8-byte gathers in flight); the
 // whole 50 MB table stays L2 resident (126 MB L2) so the gathers are L2-sector bound, not HBM
-// bound; each thread writes its own contiguous 8L-byte output row.  Backward re-derives the
+// bound; each thread writes its own contiguous 8L-byte output row, or -- in the fused trace -- the fp16
+// operand image of the tensor-core decoders (coalesced 16-byte stores, see permuto_fwd_kernel).  Backward re-derives the
 // lattice (cheaper than storing 32 B/level/sample) and scatters with red.global.add.v2.f32;
 // the coarse levels, where a warp hits a handful of vertices, are first aggregated inside the
-// warp (match-any leader reduction) so contention at L2 drops by up to 32x.
+// warp (match-any leader reduction) so contention at L2 drops by up to 32x; rows with an exactly-zero
+// gradient issue no atomics at all.
 // Lattice integers (rem0, rank, key, idx) are bit-exact against oracle/permuto.py.
 #include "common.cuh"
 #include <cuda_fp16.h>
