@@ -167,3 +167,28 @@ def test_grad_allreduce_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK {r}" in o, o
+
+
+def test_lattice_hash_linear_form_is_the_loop_form():
+    """csrc/permuto.cu evaluates the lattice-vertex hash as base + r*(m+m^2+m^3) - 4*sum [rank_i > 3-r] m^(3-i) (three multiplies
+    per level); the oracle / the published algorithm iterate k = (k + key_i) * m per vertex.  Same uint32 wrap-around result."""
+    import numpy as np
+    M1 = 2531011
+    M2 = (M1 * M1) & 0xFFFFFFFF
+    M3 = (M2 * M1) & 0xFFFFFFFF
+    MS = (M1 + M2 + M3) & 0xFFFFFFFF
+    rng = np.random.default_rng(0)
+    for _ in range(5000):
+        rem = [int(x) for x in rng.integers(-50000, 50000, 3)]
+        rank = [int(x) for x in rng.integers(0, 4, 3)]
+        base = ((rem[0] & 0xFFFFFFFF) * M3 + (rem[1] & 0xFFFFFFFF) * M2 + (rem[2] & 0xFFFFFFFF) * M1) & 0xFFFFFFFF
+        for r in range(4):
+            k = 0
+            for i in range(3):
+                key = rem[i] + r - (4 if rank[i] > 3 - r else 0)
+                k = ((k + key) * M1) & 0xFFFFFFFF
+            lin = (base + r * MS) & 0xFFFFFFFF
+            for i, P in enumerate((M3, M2, M1)):
+                if rank[i] > 3 - r:
+                    lin = (lin - 4 * P) & 0xFFFFFFFF
+            assert k == lin
