@@ -383,6 +383,10 @@ class DecodePanFn(Function):
         else:
             call("pag_decode_pan_bwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), ptr_array(grads), HIDDEN, Cs, Ci, ss, is_, it,
                  ptr(sem), ptr(inst), ptr(gs), ptr(gi), ptr(gp))
+        if gs is None:      # a head that was not requested leaves its parameters without gradient (None), like autograd would
+            grads[0:4] = [None] * 4
+        if gi is None:
+            grads[4:10] = [None] * 6
         return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
                 None, None, None, None, None, None, None, *grads)
 
@@ -658,6 +662,7 @@ class FusedTraceFn(Function):
     @staticmethod
     def forward(ctx, origins, dirs, cfg, table, dtable, *weights):
         _chk(origins, dirs, table, *weights)
+        ctx.set_materialize_grads(False)      # outputs the loss does not use arrive as None: their backward chain is skipped
         o, d = _f32(origins), _f32(dirs)
         N, S, dev = o.shape[0], int(cfg['S']), o.device
         Mmax = max(N * S, 1)
@@ -909,5 +914,19 @@ class FusedTraceFn(Function):
             works.append(_allreduce_async(flat))
             for wk in works:
                 wk.wait()
+        # parameters of heads that were not requested (or got no upstream gradient) receive None, like the reference's autograd
+        colour_ran = ga is not None or gr is not None or gd is not None
+        gout = list(grads)
+        if not colour_ran:
+            gout[0:4] = [None] * 4
+            g_table = None
+        if not (colour_ran and gr is not None):
+            gout[4:10] = [None] * 6
+        if gs is None:
+            gout[10:14] = [None] * 4
+        if gi is None:
+            gout[14:20] = [None] * 6
+        if len(gout) > 20 and gs is None and gi is None:
+            gout[20:] = [None] * (len(gout) - 20)
         return (g_o if ctx.needs_input_grad[0] else None, g_d if ctx.needs_input_grad[1] else None, None,
-                g_table, g_dtable, *grads)
+                g_table, g_dtable, *gout)

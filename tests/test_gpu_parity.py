@@ -733,3 +733,34 @@ def test_fused_dd_trace_equals_stepwise(cuda_lib):
         assert_close_norm(res[0][1][k], res[1][1][k], rel_l2=2e-2, max_frac=5e-2, msg="grad " + k)
     assert_close_norm(res[0][2], res[1][2], rel_l2=2e-2, max_frac=5e-2, msg="grad origins")
     assert_close_norm(res[0][3], res[1][3], rel_l2=2e-2, max_frac=5e-2, msg="grad dirs")
+
+
+@pytest.mark.parametrize("chans", [['rgb'], ['rgb', 'depth'], ['semantics'], ['rgb', 'inst_embedding'], ['depth', 'semantics', 'inst_embedding']])
+def test_fused_trace_channel_subsets(cuda_lib, chans):
+    """Channel gating of the fused training trace (only the requested heads / outputs are computed) vs the step-by-step path."""
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_ray")
+    res = []
+    for fused in (True, False):
+        nef = build_cuda_nef(g, DEV)
+        nef.decoder_precision = 'fp16'
+        tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=int(g["num_steps"]), bg_color='white')
+        tracer.allow_fused = fused
+        o, d = torch.from_numpy(g["o"]).to(DEV), torch.from_numpy(g["d"]).to(DEV)
+        rb = tracer(nef, channels=chans, rays=Rays(origins=o, dirs=d, dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+        if fused:
+            assert torch.is_tensor(tracer.last_num_samples)
+        sum((getattr(rb, c).float() * torch.from_numpy(g["gw_" + c]).to(DEV)).sum() for c in chans).backward()
+        # a parameter "receives gradient" if its .grad is a non-zero tensor (unused heads: None or exact zeros)
+        res.append(({c: getattr(rb, c).detach() for c in chans + ['alpha']},
+                    {k: p.grad.clone() for k, p in nef.named_parameters() if p.grad is not None and bool((p.grad != 0).any())}))
+        assert all(torch.isfinite(v).all() for v in res[-1][1].values())
+        for c in ('rgb', 'depth', 'semantics', 'inst_embedding'):
+            if c not in chans:
+                assert getattr(rb, c, None) is None, f"{c} was not requested"
+    for c in chans + ['alpha']:
+        assert_close(res[0][0][c], res[1][0][c], rtol=1e-3, atol_scale=1e-3, msg=c)
+    assert set(res[0][1]) == set(res[1][1]), "the same parameters receive gradient on both paths"
+    for k in res[0][1]:
+        assert_close_norm(res[0][1][k], res[1][1][k], rel_l2=5e-3, max_frac=2e-2, msg="grad " + k)
