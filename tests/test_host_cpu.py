@@ -101,6 +101,33 @@ def test_plugin_surface_and_state_dict_keys():
     assert torch.equal(nef2.grid.blas.octree.cpu(), oc) and nef2.grid.blas.max_level == 3
 
 
+def test_dd_plugin_surface():
+    """PanopticDDensityNeF / PanopticDDensityPackedRFTracer: reference names, channels and state_dict keys
+    (pc_nerf/panoptic_dd_nef.py:41-58,121-128; tracers/panoptic_dd_packed_rf_tracer.py)."""
+    import bench
+    from pagnerf_b200.pc_nerf import PanopticDDensityNeF
+    from pagnerf_b200.tracers import PanopticDDensityPackedRFTracer, PanopticPackedRFTracer
+    kw = dict(bench.NEF_KW, blas_level=3, capacity_log_2=8, delta_capacity_log_2=7)
+    nef = PanopticDDensityNeF(**kw)
+    nef.grid.init_from_scales(); nef.delta_grid.init_from_scales()
+    assert nef.delta_grid.capacity == 128
+    keys = set(nef.state_dict().keys())
+    for k in ("decoder_delta_density.layers.0.weight", "decoder_delta_density.layers.0.bias",
+              "decoder_delta_density.lout.weight", "decoder_delta_density.lout.bias", "delta_grid.embedder.lattice_values"):
+        assert k in keys
+    assert nef.decoder_delta_density.lout.weight.shape == (1, 64) and nef.decoder_delta_density.layers[0].weight.shape == (64, 48)
+    assert nef.get_supported_channels() == {"density", "rgb", "delta_density", "panoptic_density", "semantics", "inst_embedding"}
+    assert nef.get_nef_type() == 'delta_panoptic_nef'
+    tr = PanopticDDensityPackedRFTracer(raymarch_type='ray', num_steps=512, ray_max_travel=2.0)
+    assert isinstance(tr, PanopticPackedRFTracer) and tr.panoptic_channels == {'semantics', 'inst_embedding'}
+    # the collapsed delta-density head (two Linear layers, activation 'none') is the same linear map
+    table, dtable, wts = nef.fused_trace_tensors()
+    assert len(wts) == 22 and wts[20].shape == (1, 48) and wts[21].shape == (1,)
+    x = torch.randn(5, 48)
+    ref = nef.decoder_delta_density(x)
+    assert torch.allclose(x @ wts[20].T + wts[21], ref, atol=1e-5)
+
+
 def test_unsupported_configs_fail_loudly():
     import bench
     from pagnerf_b200.pc_nerf import PanopticNeF
