@@ -1,11 +1,17 @@
 #!/usr/bin/env python
-"""bench.py -- PAg-NeRF hot path on B200: rays/s of a training step (march + encode + decode +
-composite + backward), BASELINE.json config[1]:
+"""bench.py -- PAg-NeRF hot path on B200.  Default = BASELINE.json config[1] ("config 2" in BASELINE.md's 1-based table):
+rays/s of a training step (march + encode + decode + composite + backward) of
   PanopticDeltaNeF + permutohedral grid (L=24, F=2, T=2^18, colour + delta grid), BUP20-shaped 1 MP
   camera, 16 384 rays / step / GPU, occupancy-octree 'ray' march with 128 steps on a pruned level-7 octree.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4|5] [--march ray|voxel]
+Prints ONE JSON line (rank 0).  The other BASELINE configs (1-based):
+  1  PanopticDeltaNeF + hash_grid_torch (L=16, T=2^19), 4 096 rays x 64 samples (the reference's CPU-runnable case)
+  3  PanopticNeF + tcnn-style hash grid (L=14, T=2^19, base 16), 65 536 rays x 128 samples dense
+  4  config 2's model + pose gradients (BAPipeline) + Adam + gradient all-reduce, 65 536 rays / GPU
+  5  inference: one 1 048 576-ray frame, rgb + depth + semantics(6) + instances(200), forward only -> frames/s
+`--impl reference` times the reference's own torch CPU path (north_star: grids/hash_grid_torch.py + torch MLPs + torch
+compositing; restated in oracle/, pinned to the verbatim reference file by tests/golden/hash_torch.npz) on the host cores.
 """
 import argparse
 import json
@@ -29,6 +35,23 @@ C_SEM, C_INST = 6, 200
 RAYS_PER_IMG = 4096
 NEAR, FAR = 0.0, 2.0
 
+# BASELINE.json configs (1-based like BASELINE.md).  scene: 'pruned' = slab + blobs (a few % of the level-7 cells), 'dense' =
+# the pre-prune 128^3 occupancy (grids/occtree.py:60) with rays confined to the cube so that every ray keeps all S samples
+CONFIGS = {
+    1: dict(field='delta', grid='hashtorch', levels=16, rays=4096, S=64, scene='dense', mode='train', far=1.7,
+            workload="PanopticDeltaNeF + hash_grid_torch (L=16,F=2,T=2^19 x2, 16..2048), 4096 rays x 64 samples dense packing"),
+    2: dict(field='delta', grid='permuto', levels=24, rays=16384, S=128, scene='pruned', mode='train', far=FAR,
+            workload="PanopticDeltaNeF + permutohedral grid (L=24,F=2,T=2^18 x2), BUP20-shaped 1MP frame, 16384 rays/step/GPU, "
+                     "occtree 'ray' march 128 steps, level-7 pruned octree"),
+    3: dict(field='nef', grid='tcnn', levels=14, rays=65536, S=128, scene='dense', mode='train', far=1.7,
+            workload="PanopticNeF (no delta grid) + tcnn-style hash grid (L=14,F=2,T=2^19, base 16 x2/level), 65536 rays x 128 samples dense"),
+    4: dict(field='delta', grid='permuto', levels=24, rays=65536, S=128, scene='pruned', mode='train', far=FAR, pose=True, adam=True,
+            workload="config 2 model + pose optimisation (6-DoF per image) + Adam + gradient all-reduce, 65536 rays/GPU"),
+    5: dict(field='delta', grid='permuto', levels=24, rays=1048576, S=128, scene='pruned', mode='infer', far=FAR,
+            workload="inference render of one 1024x1024 frame (1 048 576 rays): rgb+depth+semantics(6)+inst(200), forward only, "
+                     "random-init PanopticDeltaNeF + permutohedral grid, level-7 pruned octree, 128 march steps"),
+}
+
 
 # ------------------------------------------------------------------------------------------------
 # synthetic BUP20-shaped workload: scene, cameras, rays, targets
@@ -50,18 +73,26 @@ def make_scene(level=LEVEL, seed=0):
     return np.argwhere(occ).astype(np.int16)
 
 
-def make_rays(n_rays, step, seed=0, res=1024):
+def make_rays(n_rays, step, seed=0, res=1024, confined=False):
     """`n_rays/4096` images x 4096 random pixels; pinhole res x res, focal 0.9*res; cameras on the line
-    x in [-0.8, 0.8] at z = +0.9 looking down -z with 2 degrees of seeded jitter."""
+    x in [-0.8, 0.8] at z = +0.9 looking down -z with 2 degrees of seeded jitter.
+    confined: narrower frustum (focal 2*res) from x, y in [-0.4, 0.4] so that every sample up to t = 1.7 stays inside
+    the unit cube -- the dense N x S packing of BASELINE configs 1 and 3 (every ray keeps all its samples)."""
     rng = np.random.default_rng(seed * 100003 + step)
     n_img = max(1, n_rays // RAYS_PER_IMG)
     per = n_rays // n_img
     os_, ds_ = [], []
     for _ in range(n_img):
         cam = np.array([rng.uniform(-0.8, 0.8), rng.uniform(-0.05, 0.05), 0.9])
+        focal = 0.9 * res
+        if confined:
+            cam = np.array([rng.uniform(-0.4, 0.4), rng.uniform(-0.4, 0.4), 0.9])
+            focal = 2.0 * res
         pix = rng.integers(0, res, size=(per, 2)).astype(np.float64) + 0.5
-        d = np.stack([(pix[:, 0] - res / 2) / (0.9 * res), (pix[:, 1] - res / 2) / (0.9 * res), -np.ones(per)], 1)
+        d = np.stack([(pix[:, 0] - res / 2) / focal, (pix[:, 1] - res / 2) / focal, -np.ones(per)], 1)
         ang = np.deg2rad(rng.normal(0, 2.0, 2))
+        if confined:
+            ang = np.clip(ang, -np.deg2rad(3.0), np.deg2rad(3.0))
         cx, sx, cy, sy = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1])
         Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
         Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
@@ -86,6 +117,18 @@ NEF_KW = dict(grid_type="PermutoGrid", interpolation_type='linear', multiscale_t
               coarsest_scale=1.0, finest_scale=1e-4, capacity_log_2=CAP_LOG2, delta_capacity_log_2=CAP_LOG2)
 
 
+def nef_kwargs(cfg):
+    """Constructor arguments of the field of a BASELINE config (configs/bup20/best.yaml shapes)."""
+    kw = dict(NEF_KW)
+    if cfg['grid'] == 'hashtorch':      # BASELINE.md section 2: L=16, F=2, T=2^19, base 16, finest 2048
+        kw.update(grid_type="HashGridTorch", num_lods=16, codebook_bitwidth=19)
+    elif cfg['grid'] == 'tcnn':         # BASELINE.md section 3 row 3: L=14, F=2, T=2^19, base 16, x2 per level
+        kw.update(grid_type="HashGridTinyCudaNN", num_lods=14, codebook_bitwidth=19)
+    if cfg['field'] == 'nef':
+        kw.update(panoptic_features_type=None)
+    return kw
+
+
 def loss_fn(rb_rgb, rb_sem, rb_inst, t_rgb, t_sem, t_inst):
     """rgb L1 x10 + semantic NLL x0.1 + instance NLL (reference pc_nerf/trainer.py:442-480, log(x + 1e-27) :459)."""
     l = 10.0 * torch.abs(rb_rgb - t_rgb).mean()
@@ -98,34 +141,45 @@ def loss_fn(rb_rgb, rb_sem, rb_inst, t_rgb, t_sem, t_inst):
 
 
 class Workload:
-    """The training-step hot path on one GPU through the plugin classes."""
+    """The hot path of one BASELINE config on one GPU through the plugin classes."""
 
-    def __init__(self, device, n_rays=N_RAYS, seed=0, n_batches=4, amp=True, dd=False):
+    def __init__(self, device, n_rays=None, seed=0, n_batches=4, amp=True, dd=False, config=2, march='ray'):
         """dd: the PanopticDDensity field + tracer pair (7 of the reference's 13 bup20 configs) instead of the delta field."""
         self.amp = amp
-        from pagnerf_b200.pc_nerf import PanopticDeltaNeF, PanopticDDensityNeF
+        from pagnerf_b200.pc_nerf import PanopticDeltaNeF, PanopticDDensityNeF, PanopticNeF
         from pagnerf_b200.tracers import PanopticPackedRFTracer, PanopticDDensityPackedRFTracer
         from pagnerf_b200 import spc
+        cfg = self.cfg = CONFIGS[config]
+        n_rays = int(n_rays or cfg['rays'])
         torch.manual_seed(seed)
-        self.device, self.n_rays = device, n_rays
-        self.nef = (PanopticDDensityNeF if dd else PanopticDeltaNeF)(**NEF_KW)
-        pts = torch.from_numpy(make_scene(LEVEL, seed))
-        octree = spc.unbatched_points_to_octree(pts, LEVEL)
-        for g in (self.nef.grid, self.nef.delta_grid):
-            g.init_from_scales()
-            g.blas_init(octree)
+        self.device, self.n_rays, self.S, self.far = device, n_rays, cfg['S'], cfg['far']
+        cls = PanopticNeF if cfg['field'] == 'nef' else (PanopticDDensityNeF if dd else PanopticDeltaNeF)
+        self.nef = cls(**nef_kwargs(cfg))
+        grids = [self.nef.grid] + ([self.nef.delta_grid] if hasattr(self.nef, 'delta_grid') else [])
+        octree = spc.unbatched_points_to_octree(torch.from_numpy(make_scene(LEVEL, seed)), LEVEL) if cfg['scene'] == 'pruned' else None
+        for g in grids:
+            if cfg['grid'] == 'permuto':
+                g.init_from_scales()
+            elif cfg['grid'] == 'hashtorch':
+                g.init_from_geometric(16, 2048, 16)          # config_parser.py:733 (tree_type geometric)
+            else:
+                g.init_from_resolutions([16 * 2 ** i for i in range(14)])
+            if octree is not None:
+                g.blas_init(octree)
         with torch.no_grad():  # random-init field, but opaque enough that compositing terminates like a trained one
-            self.nef.grid.embedder.lattice_values.mul_(1e3)
-            self.nef.delta_grid.embedder.lattice_values.mul_(1e3)
+            for g in grids:
+                for name in ('lattice_values', 'params', 'embeddings_weight'):
+                    if hasattr(g.embedder, name):
+                        getattr(g.embedder, name).mul_(1e3)
         self.nef = self.nef.to(device)
         self.tracer = (PanopticDDensityPackedRFTracer if dd else PanopticPackedRFTracer)(
-            raymarch_type='ray', num_steps=NUM_STEPS, bg_color='white', ray_max_travel=2.0)
+            raymarch_type=march, num_steps=(cfg['S'] if march == 'ray' else 2), bg_color='white', ray_max_travel=2.0)
         self.params = [p for p in self.nef.parameters()]
         self.channels = ['rgb', 'depth', 'semantics', 'inst_embedding']
         # pool of host (pinned) batches; step i uses batch i % n_batches
         self.host = []
         for b in range(n_batches):
-            o, d = make_rays(n_rays, b, seed)
+            o, d = make_rays(n_rays, b, seed, confined=(cfg['scene'] == 'dense'))
             tr, ts, ti = make_targets(n_rays, b, seed)
             hb = [torch.from_numpy(x) for x in (o, d, tr, ts, ti)]
             if device.type == 'cuda':
@@ -138,14 +192,17 @@ class Workload:
     def h2d_bytes(self):
         return sum(x.numel() * x.element_size() for x in self.host[0])
 
+    def render(self, o, d):
+        from pagnerf_b200.wisp_compat import Rays
+        rays = Rays(origins=o, dirs=d, dist_min=NEAR, dist_max=self.far)
+        return self.tracer(self.nef, channels=self.channels, rays=rays, lod_idx=None, stage='train')
+
     def loss_of(self, o, d, tr, ts, ti):
         """forward + loss of one step (what a trainer's step() does between zero_grad and backward)."""
-        from pagnerf_b200.wisp_compat import Rays
-        rays = Rays(origins=o, dirs=d, dist_min=NEAR, dist_max=FAR)
         # the reference's training step runs under autocast (pc_nerf/trainer.py:429): fp16-rounded coords,
         # fp16-operand / fp32-accumulate decoders; the loss scaling of its GradScaler happens inside our kernels
         with torch.autocast('cuda', dtype=torch.float16, enabled=self.amp):
-            rb = self.tracer(self.nef, channels=self.channels, rays=rays, lod_idx=None, stage='train')
+            rb = self.render(o, d)
             loss = loss_fn(rb.rgb.float(), rb.semantics.float(), rb.inst_embedding.float(), tr, ts, ti)
         # NB: keeping `rb` alive keeps its autograd graph -- and the parameters' AccumulateGrad nodes, which remember the
         # stream they were created on -- alive; CUDA-graph capture needs them re-created on the capture stream.
@@ -175,51 +232,77 @@ def build_workload(device, n_rays=N_RAYS, seed=0):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU reference arm: oracle port of the same path (numpy/torch CPU), bounded sample
+# CPU reference arm: the reference's own torch CPU path (north_star / BASELINE.md section 2), bounded sample
 # ------------------------------------------------------------------------------------------------
 class CpuReference:
-    def __init__(self, n_rays, seed=0):
-        from oracle.field import FieldOracle
-        from oracle.permuto import PermutoEncodingOracle
-        from oracle import spc as ospc
-        torch.manual_seed(seed)
-        scales = np.geomspace(1.0, 1e-4, L)
-        grid = PermutoEncodingOracle(2 ** CAP_LOG2, L, F, scales, seed=seed)
-        delta = PermutoEncodingOracle(2 ** CAP_LOG2, L, F, scales, seed=seed + 1)
-        with torch.no_grad():
-            grid.lattice_values.mul_(1e3); delta.lattice_values.mul_(1e3)
-        self.field = FieldOracle(grid, delta, feat_dim=L * F, num_classes=C_SEM, num_instances=C_INST)
-        self.octree = ospc.points_to_octree(make_scene(LEVEL, seed), LEVEL)
-        _, _, self.prefix = ospc.scan_octree(self.octree, LEVEL)
-        self.n_rays, self.seed, self.i = n_rays, seed, 0
+    """grids/hash_grid_torch.HashEmbedder (x2: colour + delta grid; L=16, F=2, T=2^19, base 16, finest 2048) + torch nn.Linear
+    decoders (density 32-64-16, colour 43-64-64-3, semantics 32-64-6, instances 32-64-64-200; stop-gradient and fusion as
+    pc_nerf/panoptic_delta_nef.py:170-257) + torch compositing (exponential_integration / sum_reduce restated with cumsum, two
+    integrations, alpha on top, white background, tracers/panoptic_packed_rf_tracer.py:134-205), fixed dense packing (every ray
+    keeps S jittered samples: the reference has no CPU marcher), L1 rgb + NLL semantics + NLL instances, loss.backward(); fp32,
+    no autocast, no optimiser step.  The hash grid is oracle/hashgrid.HashEmbedderOracle: same torch ops as the reference file,
+    pinned to it bit-exactly (indices) / 1e-6 (features) by tests/golden/hash_torch.npz -- /root/reference itself does not exist
+    on the GPU box.  This is the only CPU-runnable path the reference has (its permutohedral / tcnn grids are CUDA extensions)."""
 
-    def step(self):
-        from oracle import raymarch as orm
+    def __init__(self, n_rays, S, delta=True, seed=0):
+        from oracle.field import FieldOracle
+        from oracle.hashgrid import HashEmbedderOracle
+        torch.manual_seed(seed)
+        grid = HashEmbedderOracle(16, 2, 19, 16, 2048, seed=seed)
+        dgrid = HashEmbedderOracle(16, 2, 19, 16, 2048, seed=seed + 1) if delta else None
+        with torch.no_grad():
+            grid.embeddings.mul_(1e3)
+            if dgrid is not None:
+                dgrid.embeddings.mul_(1e3)
+        self.field = FieldOracle(grid, dgrid, feat_dim=32, num_classes=C_SEM, num_instances=C_INST)
+        self.n_rays, self.S, self.seed, self.i = n_rays, S, seed, 0
+
+    def step(self, train=True):
         from oracle.field import trace_oracle
-        o, d = make_rays(self.n_rays, self.i, self.seed)
-        tr, ts, ti = [torch.from_numpy(x) for x in make_targets(self.n_rays, self.i, self.seed)]
+        N, S = self.n_rays, self.S
+        o, d = [torch.from_numpy(x) for x in make_rays(N, self.i, self.seed, confined=True)]
+        tr, ts, ti = [torch.from_numpy(x) for x in make_targets(N, self.i, self.seed)]
+        g = torch.Generator().manual_seed(self.i)
         self.i += 1
-        ridx, pidx, s, dp, dl, b = orm.raymarch_ray(self.octree, self.prefix, o, d, LEVEL, NUM_STEPS, NEAR, FAR, seed=self.i)
+        t = (torch.arange(S, dtype=torch.float32)[None, :] + torch.rand(N, S, generator=g)) * (1.7 / S)      # near 0, far 1.7
+        samples = (o[:, None, :] + d[:, None, :] * t[:, :, None]).reshape(N * S, 1, 3)
+        deltas = torch.diff(t, dim=1, prepend=torch.zeros(N, 1)).reshape(N * S, 1)
+        boundary = torch.zeros(N * S, dtype=torch.bool)
+        boundary[::S] = True
+        ridx = torch.arange(N).repeat_interleave(S)
         for p in self.field.parameters():
             p.grad = None
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
-        out = trace_oracle(self.field, t(o), t(d), t(ridx).long(), t(s), t(dp), t(dl), t(b),
-                           ['rgb', 'depth', 'semantics', 'inst_embedding'])
-        loss = loss_fn(out['rgb'], out['semantics'], out['inst_embedding'], tr, ts, ti)
+        chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+        with torch.set_grad_enabled(train):
+            out = trace_oracle(self.field, o, d, ridx, samples, t.reshape(N * S, 1), deltas, boundary, chans)
+            if not train:
+                return 0.0
+            loss = loss_fn(out['rgb'], out['semantics'], out['inst_embedding'], tr, ts, ti)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
 
-def time_cpu_reference(n_rays, steps, warmup):
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def time_cpu_reference(n_rays, S, steps, warmup, delta=True, train=True):
+    """-> (rays/s, s/step, threads) of the reference's torch CPU path on all host cores."""
     torch.set_num_threads(os.cpu_count())
-    ref = CpuReference(n_rays)
+    ref = CpuReference(n_rays, S, delta=delta)
     for _ in range(warmup):
-        ref.step()
+        ref.step(train)
     t0 = time.perf_counter()
     for _ in range(steps):
-        ref.step()
+        ref.step(train)
     dt = (time.perf_counter() - t0) / steps
-    return n_rays / dt, dt
+    return n_rays / dt, dt, torch.get_num_threads()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -264,32 +347,6 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # main
 # ------------------------------------------------------------------------------------------------
-# algorithmic bytes / flops per packed sample (DESIGN.md "Kernels")
-ALGO = {
-    "pag_permuto_fwd_dyn": ("hbm", 12 + L * 4 * 8 + L * 2 * 4),
-    "pag_permuto_bwd_dyn": ("hbm", 12 + L * 2 * 4 + 2 * L * 4 * 8),
-    # fp16 operand-image interchange: features / feature gradients move as halfs (SURVEY 8d figures minus 2 B per feature)
-    "pag_permuto_fwd_img16_dyn": ("hbm", 12 + L * 4 * 8 + L * 2 * 2),
-    "pag_permuto_bwd_img16_dyn": ("hbm", 12 + L * 2 * 2 + 2 * L * 4 * 8),
-    "pag_decode_dc_fwd_tc_dyn": ("tensor", 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
-    "pag_decode_dc_bwd_tc_dyn": ("tensor", 3 * 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
-    "pag_pan_composite_fwd_tc": ("tensor", 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
-    "pag_pan_composite_bwd_tc": ("tensor", 4 * 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
-    "pag_permuto_fwd": ("hbm", 12 + L * 4 * 8 + L * 2 * 4),
-    "pag_permuto_bwd": ("hbm", 12 + L * 2 * 4 + 2 * L * 4 * 8),
-    "pag_decode_dc_fwd_tc": ("tensor", 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
-    "pag_decode_dc_bwd_tc": ("tensor", 3 * 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
-    "pag_decode_pan_fwd_tc": ("tensor", 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
-    "pag_decode_pan_bwd_tc": ("tensor", 3 * 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
-    "pag_decode_dc_fwd": ("tensor", 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
-    "pag_decode_dc_bwd": ("tensor", 3 * 2 * (48 * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)),
-    "pag_decode_pan_fwd": ("tensor", 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
-    "pag_decode_pan_bwd": ("tensor", 3 * 2 * (48 * 64 + 64 * C_SEM + 48 * 64 + 64 * 64 + 64 * C_INST)),
-    "pag_composite_fwd": ("hbm", 4 + 4 + 4 + 12 + 4 * C_SEM + 4 * C_INST + 8),
-    "pag_composite_bwd": ("hbm", 2 * (4 + 4 + 4 + 12 + 4 * C_SEM + 4 * C_INST) + 8),
-}
-
-
 def measured_traffic(kernel):
     """dram bytes per launch of `kernel` from the committed ncu --set full capture of this same command
     (profiles/r01_traffic.json: {entry point: {"dram_bytes": .., "samples": ..}}), rescaled to this run's sample count."""
@@ -307,50 +364,126 @@ def peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def _leave(world):
-    """Multi-rank exit.  No collective follows the max-over-ranks all-reduce, so every rank may leave on its own; the NCCL
-    communicator teardown (destroy_process_group with captured graphs still holding NCCL kernels) can block on a peer that has
-    already gone, so flush and exit the process directly."""
-    if world > 1:
-        sys.stdout.flush()
-        sys.stderr.flush()
-        torch.cuda.synchronize()
+def _leave(world, dist=None):
+    """Multi-rank exit: barrier (every rank still alive), then tear the NCCL communicator down properly.  A watchdog turns a
+    teardown that hangs (captured graphs still holding NCCL kernels have done that) into a loud message instead of a stuck job."""
+    if world <= 1:
+        return
+    sys.stdout.flush()
+    sys.stderr.flush()
+    torch.cuda.synchronize()
+
+    def _watchdog():
+        time.sleep(30.0)
+        print("[bench] WARNING: NCCL teardown did not finish within 30 s; exiting the process directly", file=sys.stderr, flush=True)
         os._exit(0)
+
+    threading.Thread(target=_watchdog, daemon=True).start()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def algo_table(levels):
+    """ALGORITHMIC bytes / flops per packed sample of every entry point (DESIGN.md "Kernels"); `levels` = grid levels.
+    Encoders: 12 B position + vertex reads/RMW (4 x 8 B per level permutohedral, 8 x 8 B hash: the tables are f32) + features
+    (f32 rows, or halfs in the fp16 operand-image interchange)."""
+    Lv = levels
+    IN = 2 * Lv
+    dc = 2 * (IN * 64 + 64 * 16 + 43 * 64 + 64 * 64 + 64 * 3)
+    pan = 2 * (IN * 64 + 64 * C_SEM + IN * 64 + 64 * 64 + 64 * C_INST)
+    t = {
+        "pag_permuto_fwd_dyn": ("l2", 12 + Lv * 4 * 8 + Lv * 2 * 4), "pag_permuto_bwd_dyn": ("l2", 12 + Lv * 2 * 4 + 2 * Lv * 4 * 8),
+        "pag_permuto_fwd_img16_dyn": ("l2", 12 + Lv * 4 * 8 + Lv * 2 * 2), "pag_permuto_bwd_img16_dyn": ("l2", 12 + Lv * 2 * 2 + 2 * Lv * 4 * 8),
+        "pag_permuto_fwd": ("l2", 12 + Lv * 4 * 8 + Lv * 2 * 4), "pag_permuto_bwd": ("l2", 12 + Lv * 2 * 4 + 2 * Lv * 4 * 8),
+        "pag_hash_fwd_dyn": ("l2", 12 + Lv * 8 * 8 + Lv * 2 * 4), "pag_hash_bwd_dyn": ("l2", 12 + Lv * 2 * 4 + 2 * Lv * 8 * 8),
+        "pag_hash_fwd_img16_dyn": ("l2", 12 + Lv * 8 * 8 + Lv * 2 * 2), "pag_hash_bwd_img16_dyn": ("l2", 12 + Lv * 2 * 2 + 2 * Lv * 8 * 8),
+        "pag_composite_fwd": ("hbm", 4 + 4 + 4 + 12 + 8), "pag_composite_bwd": ("hbm", 2 * (4 + 4 + 4 + 12) + 8),
+    }
+    for k in ("pag_decode_dc_fwd_tc_dyn", "pag_decode_dc_fwd_tc", "pag_decode_dc_fwd"):
+        t[k] = ("tensor", dc)
+    for k in ("pag_decode_dc_bwd_tc_dyn", "pag_decode_dc_bwd_tc", "pag_decode_dc_bwd"):
+        t[k] = ("tensor", 3 * dc)
+    for k in ("pag_pan_composite_fwd_tc", "pag_decode_pan_fwd_tc", "pag_decode_pan_fwd"):
+        t[k] = ("tensor", pan)
+    for k in ("pag_decode_pan_bwd_tc", "pag_decode_pan_bwd"):
+        t[k] = ("tensor", 3 * pan)
+    t["pag_pan_composite_bwd_tc"] = ("tensor", 4 * pan)      # forward recomputed inside the backward
+    return t
+
+
+def l2_probe(device):
+    """Measured L2 read bandwidth (GB/s): pag_l2_stream_probe streams a 64 MB buffer (resident in the 126 MB L2 after the
+    first pass) with coalesced 16-byte loads."""
+    from pagnerf_b200 import _lib
+    buf = torch.zeros(64 << 20, dtype=torch.uint8, device=device)
+    sink = torch.zeros(148 * 8 * 256, dtype=torch.float32, device=device)
+    iters = 8
+    for _ in range(2):
+        _lib.call("pag_l2_stream_probe", _lib.ptr(buf), buf.numel(), iters, _lib.ptr(sink))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        _lib.call("pag_l2_stream_probe", _lib.ptr(buf), buf.numel(), iters, _lib.ptr(sink))
+    e1.record()
+    torch.cuda.synchronize()
+    return buf.numel() * iters * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rays", type=int, default=N_RAYS)
-    ap.add_argument("--cpu-sample-rays", type=int, default=1024)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE config, 1-based (default 2 = the headline)")
+    ap.add_argument("--march", default="ray", choices=["ray", "voxel"], help="octree marching mode of the training trace (config 2)")
+    ap.add_argument("--rays", type=int, default=None, help="rays per step per GPU (default: the config's)")
+    ap.add_argument("--cpu-sample-rays", type=int, default=1024, help="rays per step of the CPU reference leg (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--infer-precision", default="fp32", choices=["fp32", "tc"],
+                    help="config 5: decoders in exact fp32 (the reference validates without autocast, pc_nerf/trainer.py:683) or on the "
+                         "tensor cores (fp16 operands); fp32 is the reported value, tc is reported beside it")
     ap.add_argument("--dd", action="store_true", help="PanopticDDensity field + tracer (own panoptic density stream) instead of the "
                                                       "BASELINE config-2 delta field; informational, not the headline workload")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    infer = cfg['mode'] == 'infer'
+    if args.steps is None:
+        args.steps = 10 if infer else (50 if cfg['rays'] > 16384 else 200)
+    if args.warmup is None:
+        args.warmup = 3 if infer else 10
+    rays = int(args.rays or cfg['rays'])
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    config = {"workload": ("PanopticDDensityNeF + DD tracer" if args.dd else "PanopticDeltaNeF") + " + permutohedral grid (L=24,F=2,T=2^18 x2), BUP20-shaped 1MP frame, "
-                          f"{args.rays} rays/step/GPU, occtree 'ray' march {NUM_STEPS} steps, level-7 pruned octree; "
-                          "rgb+depth+semantics(6)+inst(200); fwd+bwd",
-              "rays_per_gpu": args.rays, "parallelism": f"ray-sharded dp{world}" if world > 1 else "single"}
+    workload = cfg['workload'].replace("PanopticDeltaNeF", "PanopticDDensityNeF + DD tracer") if args.dd else cfg['workload']
+    if args.march == 'voxel':
+        workload = workload.replace("occtree 'ray' march 128 steps", "occtree 'voxel' march, 2 samples per voxel, ray_max_travel 2.0")
+    config = {"workload": workload + ("; rgb+depth+semantics(6)+inst(200); fwd+bwd" if not infer else ""),
+              "baseline_config": args.config, "rays_per_gpu": rays if not infer else rays // world,
+              "parallelism": (f"ray-sharded dp{world}" if world > 1 else "single")}
+    metric = ("inference frames/s (1 MP rgb+depth+semantic+instance maps)" if infer
+              else "train rays/s (march+encode+decode+composite+backward)")
+    unit = "frames/s" if infer else "rays/s"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-        value, dt = time_cpu_reference(args.cpu_sample_rays, steps, warm)
-        out = {"impl": "reference", "metric": "train rays/s (march+encode+decode+composite+backward)", "value": value,
-               "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": config,
-               "cpu_baseline": {"value": value, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{args.cpu_sample_rays} rays/step of the same workload, oracle (numpy+torch CPU) fwd+bwd"},
-               "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        # the reference's torch CPU path on a bounded sample of the workload: cpu_sample_rays rays x 64 samples per step
+        # (BASELINE.md section 2 packing); config 1 IS that path at its full 4 096 rays.  K steps after W warm-ups, as asked.
+        n_cpu = rays if args.config == 1 else min(rays, args.cpu_sample_rays)
+        rps, dt, threads = time_cpu_reference(n_cpu, 64, args.steps, args.warmup, delta=(cfg['field'] != 'nef'), train=not infer)
+        value = rps / (1024 * 1024) if infer else rps
+        out = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "cpu": cpu_model(),
+                                "sample": f"{n_cpu} rays x 64 samples per step (dense packing), the reference's torch CPU path: HashEmbedder x"
+                                          f"{1 if cfg['field'] == 'nef' else 2} (L=16,T=2^19) + nn.Linear decoders + torch compositing, "
+                                          + ("forward only" if infer else "fwd + loss + backward") + ", fp32, all host threads"},
+               "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out))
         return 0
 
@@ -368,11 +501,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
         trace("process group up")
-    wl = Workload(device, args.rays, seed=rank, dd=args.dd)
+    if infer:
+        return bench_inference(args, cfg, config, metric, unit, rank, world, device, dist)
+    if cfg.get('pose'):
+        return bench_pose_adam(args, cfg, config, metric, unit, rank, world, device, dist)
+    wl = Workload(device, rays, seed=rank, dd=args.dd, config=args.config, march=args.march)
     trace("workload built")
     if world > 1:
         from pagnerf_b200 import ops
-        # gradient all-reduce (NCCL, AVG) issued from inside the fused backward (reserving SMs for NCCL measured slower: 0)
+        # gradient all-reduce (NCCL) issued from inside the fused backward (reserving SMs for NCCL measured slower: 0)
         ops.set_grad_sync(True, reserved_sms=int(os.environ.get("BENCH_RESERVED_SMS", 0)))
 
     def step(from_host):
@@ -388,19 +525,17 @@ def main():
         trace(f"warm-up step {i} enqueued")
     sync()
     trace("warm-up done")
-    # ---- CUDA-graph capture of the whole step (single GPU; the fused path has static launch geometry) --------------
-    graphed, graph_note = None, "eager"
+    fused = torch.is_tensor(getattr(wl.tracer, 'last_num_samples', None))     # device-side sample count <=> sync-free fused trace
+    # ---- CUDA-graph capture of the whole step (the fused path has static launch geometry) ---------------------------
+    graphed, graph_note = None, "eager (--no-graph)" if args.no_graph else "eager (step-by-step plugin path: one host sync per march)"
     # multi-rank: NCCL all-reduces issued inside the backward are captured with the step (every rank captures the same sequence)
-    if (world == 1 or os.environ.get("BENCH_GRAPH_MULTI", "1") == "1") and not args.no_graph:
-        try:
-            from pagnerf_b200.graph import GraphedStep
-            wl.keep_rb, wl.last_rb = False, None
-            graphed = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef)
-            graph_note = "whole step (fwd + loss + bwd%s) replayed as one CUDA graph" % (" + NCCL gradient all-reduce" if world > 1 else "")
-            trace("graph captured")
-        except Exception as e:   # keep the eager number rather than fail the bench
-            graphed, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {e})"
-            torch.cuda.synchronize()
+    if fused and not args.no_graph:
+        # a failing capture fails the bench: an eager number must never be reported under the graph-replay label
+        from pagnerf_b200.graph import GraphedStep
+        wl.keep_rb, wl.last_rb = False, None
+        graphed = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef)
+        graph_note = "whole step (fwd + loss + bwd%s) replayed as one CUDA graph" % (" + NCCL gradient all-reduce" if world > 1 else "")
+        trace("graph captured")
 
     def run(from_host):
         if graphed is None:
@@ -436,6 +571,25 @@ def main():
     t1.record()
     sync()
     ms_e2e = t0.elapsed_time(t1) / args.steps
+    # ---- multi-GPU: the same graph with the gradient all-reduces switched off = compute only; the difference is the exposed
+    #      all-reduce time (SURVEY 8e "allreduce exposed ms") ------------------------------------------------------------
+    ms_nosync = None
+    if world > 1 and graphed is not None:
+        from pagnerf_b200 import ops as _o
+        _o.set_grad_sync(False)
+        g2 = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef)
+        for _ in range(3):
+            g2(*wl.batch(False))
+        sync()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(args.steps):
+            g2(*wl.batch(False))
+        n1.record()
+        sync()
+        ms_nosync = n0.elapsed_time(n1) / args.steps
+        del g2
+        _o.set_grad_sync(True, reserved_sms=int(os.environ.get("BENCH_RESERVED_SMS", 0)))
     # ---- per-entry-point CUDA-event timing of the same step, eager (events cannot be read back from a graph) ---------
     ksteps = min(args.steps, 20)
     sync()
@@ -454,15 +608,16 @@ def main():
     _lib.timing_reset(False)
     _ops.BRANCH_OVERLAP = True
     clk = clocks.stop() if clocks else None
-    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, ms_nosync or 0.0], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, ms_nosync = float(t[0]), float(t[1]), (float(t[2]) if ms_nosync is not None else None)
     if rank != 0:
-        _leave(world)
+        _leave(world, dist)
         return 0
 
     hbm, tf, how = peaks()
+    ALGO = algo_table(cfg['levels'])
     top = max(per_kernel.items(), key=lambda kv: kv[1]["ms_per_step"]) if per_kernel else None
     roof = None
     n_samples = wl.tracer.last_num_samples if hasattr(wl.tracer, "last_num_samples") else None
@@ -471,20 +626,20 @@ def main():
     # zero-density samples are dropped after the density pass (exact): the kernels downstream of the compaction process
     # the live samples only; kernels launched twice per step (main + delta grid / density-only + full decode) see both counts
     live = getattr(_ops.FusedTraceFn, "last_live_dev", None)
-    n_live = int(live.item()) if torch.is_tensor(live) else n_samples
+    n_live = int(live.item()) if (fused and torch.is_tensor(live)) else n_samples
     n_all = n_samples
-    if top and n_samples:
-        if top[0] in ("pag_pan_composite_fwd_tc", "pag_pan_composite_bwd_tc", "pag_decode_dc_bwd_tc_dyn", "pag_permuto_bwd_dyn",
-                      "pag_permuto_bwd_img16_dyn"):
-            n_samples = n_live
-        elif top[0] in ("pag_permuto_fwd_dyn", "pag_permuto_fwd_img16_dyn", "pag_decode_dc_fwd_tc_dyn"):
-            n_samples = (n_all + n_live) // 2
+    l2_gbs = l2_probe(device)
     if top and top[0] in ALGO and n_samples:
         bound, per = ALGO[top[0]]
         dur = top[1]["ms_per_launch"] * 1e-3
-        if bound == "hbm":
+        if bound in ("hbm", "l2"):
             ach = per * n_samples / dur / 1e9
-            roof = {"kernel": top[0], "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None}
+            peak = l2_gbs if bound == "l2" else hbm
+            roof = {"kernel": top[0], "bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "frac_of_hbm_peak": ach / hbm, "hbm_peak": hbm,
+                    "note": "gather/scatter over tables that stay L2 resident (DRAM traffic is ~0.1x the algorithmic bytes): the bound is the "
+                            "L2 -> SM path, peak = L2 read bandwidth measured live by pag_l2_stream_probe (64 MB buffer, coalesced 16-byte "
+                            "loads); the same figure against the measured HBM copy peak is kept as frac_of_hbm_peak" if bound == "l2" else None}
         else:
             ach = per * n_samples / dur / 1e12
             roof = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "traffic": None,
@@ -492,62 +647,239 @@ def main():
         tr = measured_traffic(top[0])
         if tr:
             roof["traffic"] = tr["dram_bytes"] * n_samples / tr["samples"]
-            roof["traffic_source"] = "ncu --set full dram__bytes_read+write per launch (profiles/r01_ncu_full_final.md), scaled by packed samples"
+            roof["traffic_source"] = "ncu --set full dram__bytes_read+write per launch (profiles/), scaled by packed samples"
         roof["peak_source"] = how
         roof["share_of_step"] = top[1]["ms_per_step"] / ms
         roof["samples_per_launch"] = n_samples
     # ---- encoder vs the memory system (BASELINE metric "encoder GB/s vs peak") -------------------------------
-    encoder = None
-    enc_name = "pag_permuto_fwd_img16_dyn" if "pag_permuto_fwd_img16_dyn" in per_kernel else "pag_permuto_fwd_dyn"
-    enc = per_kernel.get(enc_name)
-    enc_bytes = ALGO[enc_name][1]
-    if enc and n_all:
-        table = wl.nef.grid.embedder.lattice_values.detach()
-        entries = table.numel() // 2
-        sink = torch.empty(n_all, device=device)
-        for _ in range(3):
-            _lib.call("pag_gather_probe", _lib.ptr(table), entries, n_all, 96, _lib.ptr(sink))
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(10):
-            _lib.call("pag_gather_probe", _lib.ptr(table), entries, n_all, 96, _lib.ptr(sink))
-        g1.record()
-        torch.cuda.synchronize()      # rank 0 only from here on: no barrier
-        probe_gbs = n_all * 96 * 8 / (g0.elapsed_time(g1) / 10 * 1e-3) / 1e9
-        t_enc = enc["ms_per_launch"] * 1e-3
-        n_enc = (n_all + n_live) / 2          # two launches per step: colour grid (all samples) and delta grid (live samples)
-        encoder = {"kernel": enc_name, "ms_per_launch": round(enc["ms_per_launch"], 4), "samples_per_launch": n_enc,
-                   "algorithmic_bytes_per_sample": enc_bytes,
-                   "algorithmic_GBps": enc_bytes * n_enc / t_enc / 1e9, "hbm_peak_GBps": hbm, "frac_of_hbm_peak": enc_bytes * n_enc / t_enc / 1e9 / hbm,
-                   "vertex_gather_GBps": 768 * n_enc / t_enc / 1e9, "achievable_gather_GBps": probe_gbs,
-                   "frac_of_achievable_gather": 768 * n_enc / t_enc / 1e9 / probe_gbs,
-                   "note": "algorithmic bytes = 12 pos + 768 vertex reads + features out (192 f32 / 96 fp16 image); achievable = pag_gather_probe: uniformly "
-                           "random 8-byte loads, 16 in flight per thread, from the same 50 MB table (32-byte sectors: 4x the bytes move)"}
+    encoder = encoder_report(wl, per_kernel, ALGO, n_all, n_live, hbm, l2_gbs, device) if cfg['grid'] == 'permuto' and fused else None
     cpu = None
     if not args.no_cpu_baseline:
-        v, dt = time_cpu_reference(args.cpu_sample_rays, 3, 1)
-        cpu = {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{args.cpu_sample_rays} rays/step x 3 steps of the same workload, oracle (numpy+torch CPU) fwd+bwd"}
-    total_rays = args.rays * world
-    result = {"metric": "train rays/s (march+encode+decode+composite+backward)", "value": total_rays / (ms * 1e-3),
+        n_cpu = min(rays, args.cpu_sample_rays)
+        v, dt, threads = time_cpu_reference(n_cpu, 64, 3, 1, delta=(cfg['field'] != 'nef'))
+        cpu = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port", "cpu": cpu_model(),
+               "sample": f"{n_cpu} rays x 64 samples per step x 3 steps (dense packing), the reference's torch CPU path: HashEmbedder x"
+                         f"{1 if cfg['field'] == 'nef' else 2} (L=16,T=2^19) + nn.Linear decoders + torch compositing, fwd + loss + backward, fp32"}
+    total_rays = rays * world
+    result = {"metric": metric, "value": total_rays / (ms * 1e-3),
               "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
               "dtype": "fp16 operands / f32 accumulate (decoders, tcgen05) + f32 (encoders, compositing) = the reference's autocast",
               "data": "synthetic",
-              "config": dict(config, l2="no explicit flush: ray batches cycle and the per-step working set (2x50 MB tables + their "
-                                        "gradients + per-sample features and feature gradients, > 400 MB) exceeds the 126 MB L2",
-                             packed_samples_per_step=n_all, live_samples_per_step=n_live,
-                             compaction="samples with density exactly 0 (integration weight 0, gradient 0) are dropped after the "
-                                        "density pass; results are unchanged",
-                             execution=graph_note,
-                             kernel_breakdown="per-entry-point CUDA events over %d eager steps of the same workload" % ksteps),
+              "config": config,
+              "details": dict(l2="no explicit flush: ray batches cycle and the per-step working set (tables + their gradients + per-sample "
+                                 "features and feature gradients, > 400 MB) exceeds the 126 MB L2",
+                              packed_samples_per_step=n_all, live_samples_per_step=n_live, execution=graph_note,
+                              kernel_breakdown="per-entry-point CUDA events over %d eager steps of the same workload" % ksteps),
               "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": wl.h2d_bytes(),
                       "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
               "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roof, "encoder": encoder, "cpu_baseline": cpu,
               "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
+    if ms_nosync is not None:
+        result["allreduce"] = {"ms_per_step_without_allreduce": ms_nosync, "exposed_ms": ms - ms_nosync,
+                               "note": "same CUDA graph captured with the gradient all-reduces switched off, max over ranks"}
     print(json.dumps(result))
-    _leave(world)
+    _leave(world, dist)
     return 0
+
+
+def make_frame_rays(res=1024, seed=0):
+    """All res x res pixel rays of one pinhole camera of the synthetic pass (same intrinsics / pose family as make_rays)."""
+    rng = np.random.default_rng(seed * 100003 + 77)
+    cam = np.array([rng.uniform(-0.8, 0.8), rng.uniform(-0.05, 0.05), 0.9])
+    ys, xs = np.meshgrid(np.arange(res) + 0.5, np.arange(res) + 0.5, indexing="ij")
+    d = np.stack([(xs - res / 2) / (0.9 * res), (ys - res / 2) / (0.9 * res), -np.ones_like(xs)], -1).reshape(-1, 3)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.tile(cam, (res * res, 1)).astype(np.float32), d.astype(np.float32)
+
+
+def bench_inference(args, cfg, config, metric, unit, rank, world, device, dist):
+    """BASELINE config 5: full-frame render (pc_nerf/trainer.py:637-649 batch_render + :683 no autocast), frames/s.  One frame is
+    split into row blocks across the ranks (strong scaling; the only exchange is the gather of the finished map tiles), every
+    rank renders its block in chunks of `render_batch` rays under torch.no_grad()."""
+    from pagnerf_b200 import _lib
+    from pagnerf_b200.wisp_compat import Rays
+    total = int(args.rays or cfg['rays'])
+    res = int(round(total ** 0.5))
+    assert res * res == total, "config 5 renders a square frame"
+    per = total // world
+    chunk = min(per, int(os.environ.get("BENCH_RENDER_BATCH", 131072)))
+    wl = Workload(device, n_rays=4096, seed=0, n_batches=1, config=5)
+    o_np, d_np = make_frame_rays(res)
+    lo = rank * per
+    host_o = torch.from_numpy(o_np[lo:lo + per]).pin_memory()
+    host_d = torch.from_numpy(d_np[lo:lo + per]).pin_memory()
+    dev_o, dev_d = host_o.to(device), host_d.to(device)
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    host_out = [torch.empty(per, 3).pin_memory(), torch.empty(per, 1).pin_memory(),
+                torch.empty(per, dtype=torch.uint8).pin_memory(), torch.empty(per, dtype=torch.uint8).pin_memory()]
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def render_frame(o, d, precision):
+        """-> rgb [per,3], depth [per,1], semantic labels u8 [per], instance labels u8 [per] (argmax maps, as evaluate_metrics)."""
+        wl.nef.decoder_precision = 'fp16' if precision == 'tc' else 'fp32'
+        outs = []
+        with torch.no_grad():
+            for c0 in range(0, per, chunk):
+                rb = wl.tracer(wl.nef, channels=chans, rays=Rays(origins=o[c0:c0 + chunk], dirs=d[c0:c0 + chunk], dist_min=NEAR, dist_max=FAR),
+                               lod_idx=None, stage='val')
+                outs.append((rb.rgb, rb.depth, rb.semantics.argmax(-1).to(torch.uint8), rb.inst_embedding.argmax(-1).to(torch.uint8)))
+        return [torch.cat([x[i] for x in outs]) for i in range(4)]
+
+    def gather(maps):
+        if world == 1:
+            return maps
+        out = []
+        for m in maps:
+            full = torch.empty((per * world,) + tuple(m.shape[1:]), dtype=m.dtype, device=device)
+            dist.all_gather_into_tensor(full, m.contiguous())
+            out.append(full)
+        return out
+
+    def time_frames(precision, steps, warmup, e2e):
+        for _ in range(max(warmup, 1)):
+            gather(render_frame(dev_o, dev_d, precision))
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            if e2e:
+                o, d = host_o.to(device, non_blocking=True), host_d.to(device, non_blocking=True)
+                maps = render_frame(o, d, precision)
+                for dst, src in zip(host_out, maps):
+                    dst.copy_(src, non_blocking=True)
+                torch.cuda.current_stream().synchronize()      # the frame is on the host
+            else:
+                gather(render_frame(dev_o, dev_d, precision))
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    prec = args.infer_precision
+    clocks = ClockSampler(device.index or 0) if rank == 0 else None
+    ms = time_frames(prec, args.steps, max(args.warmup, 3), False)
+    ms_e2e = time_frames(prec, args.steps, 1, True)
+    other = 'tc' if prec == 'fp32' else 'fp32'
+    ms_other = time_frames(other, max(2, args.steps // 3), 2, False)
+    clk = clocks.stop() if clocks else None
+    # per-entry-point breakdown of one frame (selected precision)
+    wl.nef.decoder_precision = 'fp16' if prec == 'tc' else 'fp32'
+    sync()
+    _lib.timing_reset(True)
+    l0 = _lib.launch_count
+    render_frame(dev_o, dev_d, prec)
+    per_kernel = _lib.timing_report()
+    launches = _lib.launch_count - l0
+    _lib.timing_reset(False)
+    if rank != 0:
+        _leave(world, dist)
+        return 0
+    hbm, tf, how = peaks()
+    ALGO = algo_table(cfg['levels'])
+    n_samples = 0
+    with torch.no_grad():
+        from pagnerf_b200 import ops
+        blas = wl.nef.grid.blas
+        for c0 in range(0, per, chunk):
+            n_samples += int(ops.raymarch_ray(blas.octree, blas.prefix, dev_o[c0:c0 + chunk], dev_d[c0:c0 + chunk], LEVEL, wl.S, NEAR, FAR, seed=0)[6][-1])
+    top = max(per_kernel.items(), key=lambda kv: kv[1]["ms_total"]) if per_kernel else None
+    roof = None
+    if top and top[0] in ALGO:
+        bound, b = ALGO[top[0]]
+        dur = top[1]["ms_total"] * 1e-3
+        l2_gbs = l2_probe(device)
+        if bound == "tensor":
+            ach = b * n_samples / dur / 1e12
+            roof = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "traffic": None}
+        else:
+            ach = b * n_samples / dur / 1e9
+            peak = l2_gbs if bound == "l2" else hbm
+            roof = {"kernel": top[0], "bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
+        roof.update(peak_source=how, share_of_step=top[1]["ms_total"] / ms, samples_per_launch=n_samples / max(top[1]["launches"], 1))
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, dt, threads = time_cpu_reference(args.cpu_sample_rays, 64, 3, 1, train=False)
+        cpu = {"value": v / total, "unit": unit, "cores": threads, "kind": "port", "cpu": cpu_model(),
+               "sample": f"{args.cpu_sample_rays} rays x 64 samples x 3 steps, forward only, the reference's torch CPU path, scaled to {total} rays per frame"}
+    dt_note = {"fp32": "f32 (exact FMA decoders; the reference validates without autocast)", "tc": "fp16 operands / f32 accumulate (tcgen05 decoders) + f32"}
+    result = {"metric": metric, "value": 1e3 / ms, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dt_note[prec], "data": "synthetic", "config": config,
+              "details": dict(render_batch=chunk, packed_samples_per_frame_rank0=n_samples, rays_per_rank=per,
+                              other_precision={"dtype": dt_note[other], "frames_per_s": 1e3 / ms_other, "ms_per_frame": ms_other}),
+              "e2e": {"value": 1e3 / ms_e2e, "unit": unit, "h2d_bytes_per_step": per * 24, "d2h_bytes_per_step": per * (12 + 4 + 1 + 1), "ms_per_step": ms_e2e,
+                      "note": "pinned host rays -> H2D -> render -> argmax label maps -> D2H of rgb, depth, semantic and instance label maps (this rank's block)"},
+              "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+              "kernels_ms_per_frame": {k: round(v["ms_total"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_total"])}}
+    print(json.dumps(result))
+    _leave(world, dist)
+    return 0
+
+
+def bench_pose_adam(args, cfg, config, metric, unit, rank, world, device, dist):
+    raise NotImplementedError("config 4 (pose optimisation + Adam) is wired up in pagnerf_b200/ba_pipeline.py")
+
+
+def encoder_report(wl, per_kernel, ALGO, n_all, n_live, hbm, l2_gbs, device):
+    """Permutohedral forward against the memory system: algorithmic GB/s vs HBM peak, vertex gathers vs the random-gather probe, and
+    the L2-sector roofline: 32-byte sectors a warp instruction really touches (computed from this batch's lattice indices: lanes of
+    a warp that hit the same sector share it) x 32 B / time, against the measured L2 read bandwidth."""
+    from pagnerf_b200 import _lib, ops
+    enc_name = "pag_permuto_fwd_img16_dyn" if "pag_permuto_fwd_img16_dyn" in per_kernel else "pag_permuto_fwd_dyn"
+    enc = per_kernel.get(enc_name)
+    if not enc or not n_all:
+        return None
+    enc_bytes = ALGO[enc_name][1]
+    emb = wl.nef.grid.embedder
+    table = emb.lattice_values.detach()
+    entries = table.numel() // 2
+    sink = torch.empty(n_all, device=device)
+    for _ in range(3):
+        _lib.call("pag_gather_probe", _lib.ptr(table), entries, n_all, 96, _lib.ptr(sink))
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(10):
+        _lib.call("pag_gather_probe", _lib.ptr(table), entries, n_all, 96, _lib.ptr(sink))
+    g1.record()
+    torch.cuda.synchronize()      # rank 0 only from here on: no barrier
+    probe_gbs = n_all * 96 * 8 / (g0.elapsed_time(g1) / 10 * 1e-3) / 1e9
+    t_enc = enc["ms_per_launch"] * 1e-3
+    n_enc = (n_all + n_live) / 2          # two launches per step: colour grid (all samples) and delta grid (live samples)
+    # sectors per warp instruction on a sample of the batch: one marched ray batch, first 32k packed samples
+    sectors = None
+    try:
+        o, d = wl.dev[0][0], wl.dev[0][1]
+        blas = wl.nef.grid.blas
+        r = ops.raymarch_ray(blas.octree, blas.prefix, o, d, LEVEL, wl.S, NEAR, wl.far, seed=1)
+        pos = r[2].reshape(-1, 3)[:32768].half().float().contiguous()
+        m = (pos.shape[0] // 32) * 32
+        idx, _, _ = ops.permuto_indices(pos[:m], emb.capacity, emb.scale_factor, emb.random_shift_per_level)      # [L, m, 4]
+        sec = (idx.to(torch.int64) >> 2).view(idx.shape[0], m // 32, 32, 4).permute(0, 1, 3, 2)      # 8-byte entries: 4 per sector
+        srt = torch.sort(sec, dim=-1).values
+        distinct = 1 + (srt[..., 1:] != srt[..., :-1]).sum(-1)          # [L, warps, 4] sectors per warp-wide gather
+        sectors = float(distinct.sum()) / m                                  # sectors per sample (<= 4 L)
+    except Exception as e:      # diagnostic only
+        sectors = None
+    rep = {"kernel": enc_name, "ms_per_launch": round(enc["ms_per_launch"], 4), "samples_per_launch": n_enc,
+           "algorithmic_bytes_per_sample": enc_bytes,
+           "algorithmic_GBps": enc_bytes * n_enc / t_enc / 1e9, "hbm_peak_GBps": hbm, "frac_of_hbm_peak": enc_bytes * n_enc / t_enc / 1e9 / hbm,
+           "vertex_gather_GBps": 768 * n_enc / t_enc / 1e9, "achievable_gather_GBps": probe_gbs,
+           "frac_of_achievable_gather": 768 * n_enc / t_enc / 1e9 / probe_gbs,
+           "l2_read_peak_GBps": l2_gbs,
+           "note": "algorithmic bytes = 12 pos + 768 vertex reads + features out (192 f32 / 96 fp16 image); achievable = pag_gather_probe: uniformly "
+                   "random 8-byte loads, 16 in flight per thread, from the same 50 MB table (a lower bound of the achievable rate: neighbouring "
+                   "samples share coarse-level vertices, the probe's addresses do not); l2_sector_*: distinct 32-byte sectors per warp-wide "
+                   "gather (from this batch's lattice indices) x 32 B against the measured L2 read bandwidth"}
+    if sectors is not None:
+        sec_gbs = sectors * 32 * n_enc / t_enc / 1e9
+        rep.update(l2_sectors_per_sample=sectors, l2_sector_GBps=sec_gbs, l2_sector_frac=sec_gbs / l2_gbs)
+    return rep
 
 
 if __name__ == "__main__":

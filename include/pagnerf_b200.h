@@ -84,6 +84,16 @@ int pag_voxel_samples(const float* origins, const float* dirs, const int64_t* ri
 int pag_max_travel_mask(const int64_t* ridx, const float* depths, int64_t K, int S, const int64_t* ray_first,
                         float max_travel, uint8_t* keep, void* stream);
 /* kaolin.render.spc.mark_pack_boundaries, tracers/panoptic_packed_rf_tracer.py:114. */
+/* Sync-free 'voxel' marching for the fused training trace (configs/bup20/best.yaml:34 switches the trainer to voxel marching at
+ * epoch 201, pc_nerf/trainer.py:362-366): after pag_raytrace_count / pag_raytrace_emit into worst-case nugget buffers, the max-travel
+ * filter of tracers/panoptic_packed_rf_tracer.py:88-108 is folded into the kept-nugget count (rel i32[K_max]: rank among the ray's kept
+ * nuggets or -1; offsets i64[N+1]: packed SAMPLE offsets, offsets[N] = M stays on the device) and the emit pass writes the S samples
+ * of every kept nugget into the packed list.  Jitter index = k*S + s with k the unfiltered nugget index (== pag_voxel_samples). */
+int pag_voxel_filter_count(const float* nug_depth, const int64_t* nug_offsets, int64_t N, int S, uint32_t seed, const uint32_t* seed_dev,
+                           float max_travel, int apply_filter, int32_t* rel, int32_t* counts, int64_t* offsets, void* stream);
+int pag_voxel_emit_dyn(const float* origins, const float* dirs, const int64_t* nug_ridx, const float* nug_depth, const int32_t* rel,
+                       const int64_t* nug_offsets, const int64_t* offsets, int64_t N, int64_t K_max, int S, uint32_t seed,
+                       const uint32_t* seed_dev, int64_t* ridx, float* samples, float* depths, float* deltas, void* stream);
 int pag_mark_pack_boundaries(const int64_t* ids, int64_t M, uint8_t* boundary, void* stream);
 
 /* ---- permutohedral encoding: grids/permuto_grid.py:57-62,71 -> PermutoEncoding fwd / bwd ------------- */
@@ -136,6 +146,17 @@ int pag_hash_fwd_dyn(int flavour, const float* pos, int64_t M_max, const int64_t
 int pag_hash_bwd_dyn(int flavour, const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table, int L,
                      int F, const float* fparam, const uint32_t* res, const uint32_t* offset, const uint32_t* size,
                      const float* grad_out, float* grad_table, float* grad_pos, int n_agg_levels, void* stream);
+/* fp16 operand-image interchange with the tensor-core decoders inside the fused trace (same layout as
+ * pag_permuto_fwd_img16_dyn: tiles of 128 samples, ceil(2L/16)*2 chunks [128 rows][8 halfs], zero padded); the gradient image is
+ * scaled by *img_scale (device float, nullable = 1).  Replaces grids/hash_grid_tinycudann.py:41 / grids/hash_grid_torch.py:95-108
+ * on the training path (the reference's autocast hands the decoders half features as well). */
+int pag_hash_fwd_img16_dyn(int flavour, const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table, int L,
+                           int F, const float* fparam, const uint32_t* res, const uint32_t* offset, const uint32_t* size, void* img16,
+                           void* stream);
+int pag_hash_bwd_img16_dyn(int flavour, const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table, int L,
+                           int F, const float* fparam, const uint32_t* res, const uint32_t* offset, const uint32_t* size,
+                           const void* grad_img16, const float* img_scale, float* grad_table, float* grad_pos, int n_agg_levels,
+                           void* stream);
 int pag_hash_indices(int flavour, const float* pos, int64_t M, int L, const float* fparam, const uint32_t* res,
                      const uint32_t* offset, const uint32_t* size, uint32_t* idx, void* stream);
 
@@ -269,6 +290,9 @@ int pag_set_reserved_sms(int n, int* previous /* host */);
 /* ---- achievable-gather-bandwidth probe (bench.py: denominator of the encoder's roofline fraction) ----
  * threads x loads_per_thread (multiple of 16, 16 in flight per thread) uniformly random 8-byte loads from table[entries] float2; sink f32[threads]. */
 int pag_gather_probe(const float* table, int64_t entries, int64_t threads, int loads_per_thread, float* sink, void* stream);
+/* L2 read bandwidth: all CTAs together stream buf[bytes] (multiple of 16; <= the 126 MB L2 to stay resident) iters times with
+ * coalesced 16-byte loads; sink f32[148 * 8 * 256].  Peak of the "l2" roofline of the gather-bound encoders. */
+int pag_l2_stream_probe(const void* buf, int64_t bytes, int iters, float* sink, void* stream);
 
 /* ---- tcgen05 building-block probe (tests only): one 128-row tile through the tensor-core operand images ---- */
 int pag_tc_gemm_test(int mode, const float* A, const float* B, float* D, int N, int K, int FA, int reps, void* stream);

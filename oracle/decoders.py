@@ -7,6 +7,8 @@ pc_nerf/panoptic_nef.py:75,114-164 and configs/bup20/best.yaml:66-97).
 import torch
 from torch import nn
 
+from . import autocast
+
 
 class BasicDecoderOracle(nn.Module):
     """num_layers hidden Linear+activation (first in->hidden; ReLU, or none for wisp's 'none' = Identity), then `lout`
@@ -21,6 +23,11 @@ class BasicDecoderOracle(nn.Module):
 
     def forward(self, x):
         h = x
+        if autocast.enabled():      # the reference's fp16 autocast numerics (oracle/autocast.py); output fp16
+            for l in self.layers:
+                h = autocast.linear(h, l.weight, l.bias)
+                h = torch.relu(h) if self.activation == 'relu' else h
+            return autocast.linear(h, self.lout.weight, self.lout.bias)
         for l in self.layers:
             h = l(h)
             h = torch.relu(h) if self.activation == 'relu' else h

@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import spc
+from . import autocast, spc
 from .decoders import BasicDecoderOracle, PositionalEmbedderOracle
 
 
@@ -42,6 +42,10 @@ class FieldOracle(nn.Module):
         semantics [M*S,C], inst_embedding [M*S,C])."""
         out = {}
         batch, S, _ = coords.shape
+        amp = autocast.enabled()      # the reference's autocast step (oracle/autocast.py): fp16-rounded coordinates into the
+        ph = getattr(self, 'pos_half', None)      # permutohedral encoders (grids/permuto_grid.py:65), fp16 Linear layers, fp32 softmax
+        if amp if ph is None else ph:             # pos_half=True alone: exact fp32 arithmetic on the fp16-rounded coordinates
+            coords = coords.half().to(coords.dtype)
         feats = self.grid(coords.reshape(-1, 3)) * self.lod_weights.to(coords.dtype)
         density_feats = self.decoder_density(feats)
         density = torch.relu(density_feats[..., 0:1]).reshape(batch, S, 1)
@@ -64,12 +68,12 @@ class FieldOracle(nn.Module):
                 out['panoptic_density'] = torch.relu(density_feats[..., 0:1].reshape(batch, S, 1).detach() + dd)
         if 'semantics' in channels:
             s = self.decoder_semantics(panop)
-            out['semantics'] = F.softmax(s, -1) if self.sem_softmax else s
+            out['semantics'] = F.softmax(s.float() if amp else s, -1) if self.sem_softmax else s
         if 'inst_embedding' in channels:
             e = self.decoder_inst(panop)
             if self.inst_soft_temperature > 0.0:
                 e = e / self.inst_soft_temperature
-            out['inst_embedding'] = F.softmax(e, -1) if self.inst_softmax else e
+            out['inst_embedding'] = F.softmax(e.float() if amp else e, -1) if self.inst_softmax else e
         return out
 
 

@@ -92,15 +92,23 @@ class PermutoEncodingOracle(nn.Module):
         self.register_buffer("scale_factor", torch.from_numpy(scale_factor_table(scales)))
         self.register_buffer("anneal_window", torch.ones(nr_levels))
 
-    def indices(self, pos):
-        """(rem0, rank, idx) for every level: int32/int32/uint32 arrays [L,M,4]."""
+    def indices(self, pos, pos_half=False):
+        """(rem0, rank, idx) for every level: int32/int32/uint32 arrays [L,M,4].
+        pos_half: the reference's autocast step (grids/permuto_grid.py:65 `custom_fwd(cast_inputs=torch.half)`, :71
+        `.type(torch.float)`): coordinates rounded to fp16 (round-to-nearest-even) and widened again BEFORE the lattice
+        arithmetic -- identical already-rounded positions on both sides, indices stay bit-exact targets."""
         p = pos.detach().cpu().numpy().astype(np.float32)
+        if pos_half:
+            p = p.astype(np.float16).astype(np.float32)
         sf = self.scale_factor.numpy(); sh = self.random_shift_per_level.numpy()
         out = [lattice_level(p, sf[l], sh[l], self.capacity) for l in range(self.nr_levels)]
         return (np.stack([o[1] for o in out]), np.stack([o[2] for o in out]), np.stack([o[3] for o in out]))
 
-    def forward(self, pos):
-        """pos [M,3] (float32 or float64 leaf) -> [M, L*F], level-major / feature-minor."""
+    def forward(self, pos, pos_half=False):
+        """pos [M,3] (float32 or float64 leaf) -> [M, L*F], level-major / feature-minor.
+        pos_half: round the coordinates to fp16 first (see `indices`); the cast is an autograd op, d/d pos passes through."""
+        if pos_half:
+            pos = pos.half().to(pos.dtype)
         dt = pos.dtype
         ft = np.float64 if dt == torch.float64 else np.float32
         p32 = pos.detach().cpu().numpy().astype(ft)

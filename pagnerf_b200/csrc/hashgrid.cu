@@ -86,14 +86,28 @@ __device__ __forceinline__ void make_cell(float x, float y, float z, const Level
     else hashnerf_cell(x, y, z, __ldg(d.fparam + l), __ldg(d.size + l) - 1u, c);
 }
 
-template <int FLAVOUR>
+// IMG16: features go out as the tensor-core decoders' fp16 operand image (see permuto_fwd_kernel in permuto.cu): tile m / 128
+// holds [nXc chunks][128 rows][8 halfs], nXc = ceil(2L / 16) * 2 chunks of four levels each; levels >= L and rows between M and
+// the end of the last tile are zero (the tensor core reads whole, 16-feature-padded tiles).
+template <int FLAVOUR, bool IMG16>
 __global__ void __launch_bounds__(128) hash_fwd_kernel(const float* __restrict__ pos, int64_t M,
                                                        const float* __restrict__ table, int L, LevelDesc d,
                                                        float* __restrict__ out, int round_half,
                                                        const int64_t* __restrict__ m_dev, int pos_half) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m_dev) M = min(M, __ldg(m_dev));   // packed-sample count produced on the device by the marcher (fused trace)
-    if (m >= M) return;
+    uint4* img = nullptr;
+    const int nXc = ((2 * L + 15) & ~15) >> 3;
+    if (IMG16) {
+        const int64_t Mpad = (M + 127) & ~(int64_t)127;
+        if (m >= Mpad) return;
+        img = reinterpret_cast<uint4*>(out) + ((m >> 7) * nXc) * 128 + (m & 127);    // chunk c at img[c * 128]
+        if (m >= M) {
+            for (int c = 0; c < nXc; ++c) img[c * 128] = make_uint4(0u, 0u, 0u, 0u);
+            return;
+        }
+    } else if (m >= M) return;
+    uint32_t pk[4] = {0u, 0u, 0u, 0u};
     float x = pos[3 * m], y = pos[3 * m + 1], z = pos[3 * m + 2];
     if (pos_half) {   // autocast: custom_fwd(cast_inputs=torch.half), grids/hash_grid_tinycudann.py:36
         x = __half2float(__float2half_rn(x)); y = __half2float(__float2half_rn(y)); z = __half2float(__float2half_rn(z));
@@ -114,11 +128,22 @@ __global__ void __launch_bounds__(128) hash_fwd_kernel(const float* __restrict__
             acc.x = fmaf(w, v[k].x, acc.x);
             acc.y = fmaf(w, v[k].y, acc.y);
         }
-        if (round_half) {  // tcnn returns __half, the wrapper casts back to float (:41)
-            acc.x = __half2float(__float2half_rn(acc.x));
-            acc.y = __half2float(__float2half_rn(acc.y));
+        if (IMG16) {
+            const __half2 h = __floats2half2_rn(acc.x, acc.y);
+            pk[l & 3] = *reinterpret_cast<const uint32_t*>(&h);
+            if ((l & 3) == 3) { img[(l >> 2) * 128] = make_uint4(pk[0], pk[1], pk[2], pk[3]); pk[0] = pk[1] = pk[2] = pk[3] = 0u; }
+        } else {
+            if (round_half) {  // tcnn returns __half, the wrapper casts back to float (:41)
+                acc.x = __half2float(__float2half_rn(acc.x));
+                acc.y = __half2float(__float2half_rn(acc.y));
+            }
+            orow[l] = acc;
         }
-        orow[l] = acc;
+    }
+    if (IMG16) {      // partially filled chunk (L % 4 != 0) and the all-zero padding chunks up to nXc
+        int c = L >> 2;
+        if (L & 3) { img[c * 128] = make_uint4(pk[0], pk[1], pk[2], pk[3]); ++c; }
+        for (; c < nXc; ++c) img[c * 128] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
@@ -135,12 +160,15 @@ __global__ void hash_indices_kernel(const float* __restrict__ pos, int64_t M, in
     }
 }
 
-template <int FLAVOUR, bool POS_GRAD>
+// GIMG: the upstream gradient arrives as the decoders' fp16 tile image, still multiplied by the power-of-two loss scale
+// *img_scale of the tensor-core backward (see permuto_bwd_kernel)
+template <int FLAVOUR, bool POS_GRAD, bool GIMG>
 __global__ void __launch_bounds__(128) hash_bwd_kernel(const float* __restrict__ pos, int64_t M,
                                                        const float* __restrict__ table, int L, LevelDesc d,
                                                        const float* __restrict__ gout, float* __restrict__ gtable,
                                                        float* __restrict__ gpos, int n_agg_levels,
-                                                       const int64_t* __restrict__ m_dev, int pos_half) {
+                                                       const int64_t* __restrict__ m_dev, int pos_half,
+                                                       const float* __restrict__ img_scale) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m_dev) M = min(M, __ldg(m_dev));
     if (M <= 0 || (m & ~31ll) >= M) return;   // whole warp beyond the packed samples
@@ -151,11 +179,23 @@ __global__ void __launch_bounds__(128) hash_bwd_kernel(const float* __restrict__
         x = __half2float(__float2half_rn(x)); y = __half2float(__float2half_rn(y)); z = __half2float(__float2half_rn(z));
     }
     const float2* grow = reinterpret_cast<const float2*>(gout + mm * (int64_t)(2 * L));
+    const int nXc = ((2 * L + 15) & ~15) >> 3;
+    const uint4* gimg = reinterpret_cast<const uint4*>(gout) + ((mm >> 7) * nXc) * 128 + (mm & 127);   // chunk c at gimg[c * 128]
+    const float inv_scale = (GIMG && img_scale) ? 1.f / __ldg(img_scale) : 1.f;
+    uint4 gq = make_uint4(0u, 0u, 0u, 0u);
     float gp[3] = {0.f, 0.f, 0.f};
     for (int l = 0; l < L; ++l) {
         Cell c;
         make_cell<FLAVOUR>(x, y, z, d, l, c);
-        float2 g = __ldg(grow + l);
+        float2 g;
+        if (GIMG) {
+            if ((l & 3) == 0) gq = __ldg(gimg + (l >> 2) * 128);
+            const uint32_t u = (l & 3) == 0 ? gq.x : ((l & 3) == 1 ? gq.y : ((l & 3) == 2 ? gq.z : gq.w));
+            g = __half22float2(*reinterpret_cast<const __half2*>(&u));
+            g.x *= inv_scale; g.y *= inv_scale;
+        } else {
+            g = __ldg(grow + l);
+        }
         if (!valid) { g.x = 0.f; g.y = 0.f; }
         const size_t off = 2 * (size_t)__ldg(d.offset + l);
         float* gl = gtable + off;
@@ -194,9 +234,16 @@ __global__ void __launch_bounds__(128) hash_bwd_kernel(const float* __restrict__
 
 template <int FLAVOUR>
 static int launch_bwd(const float* pos, int64_t M, const float* table, int L, LevelDesc d, const float* gout,
-                      float* gtable, float* gpos, int n_agg, cudaStream_t st, const int64_t* m_dev = nullptr, int pos_half = 0) {
-    if (gpos) hash_bwd_kernel<FLAVOUR, true><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg, m_dev, pos_half);
-    else hash_bwd_kernel<FLAVOUR, false><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg, m_dev, pos_half);
+                      float* gtable, float* gpos, int n_agg, cudaStream_t st, const int64_t* m_dev = nullptr, int pos_half = 0,
+                      bool gimg = false, const float* img_scale = nullptr) {
+    const dim3 g = pag_grid(M, 128);
+    if (gimg) {
+        if (gpos) hash_bwd_kernel<FLAVOUR, true, true><<<g, 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg, m_dev, pos_half, img_scale);
+        else hash_bwd_kernel<FLAVOUR, false, true><<<g, 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg, m_dev, pos_half, img_scale);
+    } else {
+        if (gpos) hash_bwd_kernel<FLAVOUR, true, false><<<g, 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg, m_dev, pos_half, nullptr);
+        else hash_bwd_kernel<FLAVOUR, false, false><<<g, 128, 0, st>>>(pos, M, table, L, d, gout, gtable, gpos, n_agg, m_dev, pos_half, nullptr);
+    }
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -213,8 +260,8 @@ int pag_hash_fwd(int flavour, const float* pos, int64_t M, const float* table, i
     if (M == 0) return PAG_OK;
     LevelDesc d{fparam, res, offset, size};
     cudaStream_t st = (cudaStream_t)stream;
-    if (flavour == 0) hash_fwd_kernel<0><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, out, round_half, nullptr, 0);
-    else hash_fwd_kernel<1><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, out, round_half, nullptr, 0);
+    if (flavour == 0) hash_fwd_kernel<0, false><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, out, round_half, nullptr, 0);
+    else hash_fwd_kernel<1, false><<<pag_grid(M, 128), 128, 0, st>>>(pos, M, table, L, d, out, round_half, nullptr, 0);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -240,8 +287,8 @@ int pag_hash_fwd_dyn(int flavour, const float* pos, int64_t M_max, const int64_t
     if (M_max == 0) return PAG_OK;
     LevelDesc d{fparam, res, offset, size};
     cudaStream_t st = (cudaStream_t)stream;
-    if (flavour == 0) hash_fwd_kernel<0><<<pag_grid(M_max, 128), 128, 0, st>>>(pos, M_max, table, L, d, out, round_half, m_dev, pos_half);
-    else hash_fwd_kernel<1><<<pag_grid(M_max, 128), 128, 0, st>>>(pos, M_max, table, L, d, out, round_half, m_dev, pos_half);
+    if (flavour == 0) hash_fwd_kernel<0, false><<<pag_grid(M_max, 128), 128, 0, st>>>(pos, M_max, table, L, d, out, round_half, m_dev, pos_half);
+    else hash_fwd_kernel<1, false><<<pag_grid(M_max, 128), 128, 0, st>>>(pos, M_max, table, L, d, out, round_half, m_dev, pos_half);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -255,6 +302,37 @@ int pag_hash_bwd_dyn(int flavour, const float* pos, int64_t M_max, const int64_t
     cudaStream_t st = (cudaStream_t)stream;
     return flavour == 0 ? launch_bwd<0>(pos, M_max, table, L, d, grad_out, grad_table, grad_pos, n_agg_levels, st, m_dev, pos_half)
                         : launch_bwd<1>(pos, M_max, table, L, d, grad_out, grad_table, grad_pos, n_agg_levels, st, m_dev, pos_half);
+}
+
+// fp16 operand-image interchange with the tensor-core decoders (fused trace): img16 holds ceil(M_max / 128) tiles of
+// ceil(2L / 16) * 2 chunks of 2048 bytes; grad_img16 likewise, scaled by *img_scale (device float, nullable = 1)
+int pag_hash_fwd_img16_dyn(int flavour, const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table, int L,
+                           int F, const float* fparam, const uint32_t* res, const uint32_t* offset, const uint32_t* size, void* img16,
+                           void* stream) {
+    if (F != 2) return PAG_ERR_UNSUPPORTED;
+    if (L <= 0 || (flavour != 0 && flavour != 1)) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    LevelDesc d{fparam, res, offset, size};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t Mpad = (M_max + 127) & ~(int64_t)127;
+    float* out = reinterpret_cast<float*>(img16);
+    if (flavour == 0) hash_fwd_kernel<0, true><<<pag_grid(Mpad, 128), 128, 0, st>>>(pos, M_max, table, L, d, out, 0, m_dev, pos_half);
+    else hash_fwd_kernel<1, true><<<pag_grid(Mpad, 128), 128, 0, st>>>(pos, M_max, table, L, d, out, 0, m_dev, pos_half);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_hash_bwd_img16_dyn(int flavour, const float* pos, int64_t M_max, const int64_t* m_dev, int pos_half, const float* table, int L,
+                           int F, const float* fparam, const uint32_t* res, const uint32_t* offset, const uint32_t* size,
+                           const void* grad_img16, const float* img_scale, float* grad_table, float* grad_pos, int n_agg_levels,
+                           void* stream) {
+    if (F != 2) return PAG_ERR_UNSUPPORTED;
+    if (L <= 0 || (flavour != 0 && flavour != 1)) return PAG_ERR_ARG;
+    if (M_max == 0) return PAG_OK;
+    LevelDesc d{fparam, res, offset, size};
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* g = reinterpret_cast<const float*>(grad_img16);
+    return flavour == 0 ? launch_bwd<0>(pos, M_max, table, L, d, g, grad_table, grad_pos, n_agg_levels, st, m_dev, pos_half, true, img_scale)
+                        : launch_bwd<1>(pos, M_max, table, L, d, g, grad_table, grad_pos, n_agg_levels, st, m_dev, pos_half, true, img_scale);
 }
 
 int pag_hash_indices(int flavour, const float* pos, int64_t M, int L, const float* fparam, const uint32_t* res,

@@ -481,6 +481,65 @@ __global__ void max_travel_mask_kernel(const int64_t* __restrict__ ridx, const f
     keep[k] = (__fsub_rn(depths[k * S], depths[f * S]) < max_travel) ? 1 : 0;
 }
 
+// ---- sync-free 'voxel' marching (fused training trace) -------------------------------------------------------------------
+// The nuggets of the raytrace pass stay on the device (worst-case buffers, count = nug_off[N]); the max-travel filter of
+// tracers/panoptic_packed_rf_tracer.py:88-108 is folded into the per-ray count of the kept nuggets, and the emit pass writes the
+// S samples of every kept nugget straight into the packed (ray-sorted) sample list the encoders / decoders read.  The jitter
+// index stays k * S + s with k the UNFILTERED nugget index, so positions are bit-identical to pag_voxel_samples + filter.
+// warp per ray: rel[k] = rank of nugget k among the ray's kept nuggets (-1 = dropped); counts[ray] = kept * S
+__global__ void voxel_filter_kernel(const float* __restrict__ depth, const int64_t* __restrict__ nug_off, int64_t N, int S,
+                                    uint32_t seed, const uint32_t* __restrict__ seed_dev, float max_travel, int apply_filter,
+                                    int* __restrict__ rel, int* __restrict__ counts) {
+    if (seed_dev) seed = __ldg(seed_dev);
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= N) return;
+    const int64_t k0 = nug_off[ray], k1 = nug_off[ray + 1];
+    int kept = 0;
+    if (k1 > k0) {
+        const float first = voxel_sample_depth(k0, 0, S, depth[2 * k0], depth[2 * k0 + 1], nullptr, seed);
+        for (int64_t kb = k0; kb < k1; kb += 32) {
+            const int64_t k = kb + lane;
+            bool keep = false;
+            if (k < k1) {
+                const float d0 = voxel_sample_depth(k, 0, S, depth[2 * k], depth[2 * k + 1], nullptr, seed);
+                keep = !apply_filter || (__fsub_rn(d0, first) < max_travel);
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            if (k < k1) rel[k] = keep ? kept + __popc(b & ((1u << lane) - 1u)) : -1;
+            kept += __popc(b);
+        }
+    }
+    if (lane == 0) counts[ray] = kept * S;
+}
+
+// thread per (unfiltered nugget, sample): offsets = per-ray packed SAMPLE offsets of the kept nuggets
+__global__ void voxel_emit_kernel(const float* __restrict__ org, const float* __restrict__ dir, const int64_t* __restrict__ nug_ridx,
+                                  const float* __restrict__ depth, const int* __restrict__ rel, const int64_t* __restrict__ nug_off,
+                                  const int64_t* __restrict__ offsets, int64_t N, int64_t K_max, int S, uint32_t seed,
+                                  const uint32_t* __restrict__ seed_dev, int64_t* __restrict__ ridx, float* __restrict__ samples,
+                                  float* __restrict__ depths, float* __restrict__ deltas) {
+    if (seed_dev) seed = __ldg(seed_dev);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t K = min(K_max, nug_off[N]);
+    const int64_t k = t / S;
+    if (k >= K) return;
+    const int r = rel[k];
+    if (r < 0) return;
+    const int s = (int)(t - k * S);
+    const int64_t ray = nug_ridx[k];
+    const float t0 = depth[2 * k], t1 = depth[2 * k + 1];
+    const float ds = voxel_sample_depth(k, s, S, t0, t1, nullptr, seed);
+    const float prev = (s == 0) ? t0 : voxel_sample_depth(k, s - 1, S, t0, t1, nullptr, seed);
+    const int64_t dst = offsets[ray] + (int64_t)r * S + s;
+    ridx[dst] = ray;
+    depths[dst] = ds;
+    deltas[dst] = __fsub_rn(ds, prev);
+    samples[3 * dst + 0] = __fadd_rn(org[3 * ray + 0], __fmul_rn(dir[3 * ray + 0], ds));
+    samples[3 * dst + 1] = __fadd_rn(org[3 * ray + 1], __fmul_rn(dir[3 * ray + 1], ds));
+    samples[3 * dst + 2] = __fadd_rn(org[3 * ray + 2], __fmul_rn(dir[3 * ray + 2], ds));
+}
+
 __global__ void mark_pack_boundaries_kernel(const int64_t* __restrict__ ids, int64_t M, uint8_t* __restrict__ b) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
@@ -636,6 +695,32 @@ int pag_max_travel_mask(const int64_t* ridx, const float* depths, int64_t K, int
     if (K == 0) return PAG_OK;
     max_travel_mask_kernel<<<pag_grid(K, 256), 256, 0, (cudaStream_t)stream>>>(ridx, depths, K, S, ray_first,
                                                                               max_travel, keep);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// Sync-free voxel marching, after pag_raytrace_count / pag_raytrace_emit (nuggets in worst-case device buffers):
+// max-travel filter + kept count per ray + scan -> offsets[N+1] = packed SAMPLE offsets (offsets[N] = M on the device)
+int pag_voxel_filter_count(const float* nug_depth, const int64_t* nug_offsets, int64_t N, int S, uint32_t seed, const uint32_t* seed_dev,
+                           float max_travel, int apply_filter, int32_t* rel, int32_t* counts, int64_t* offsets, void* stream) {
+    if (S <= 0) return PAG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 0) {
+        voxel_filter_kernel<<<pag_grid(N * 32, 256), 256, 0, st>>>(nug_depth, nug_offsets, N, S, seed, seed_dev, max_travel, apply_filter, rel, counts);
+        PAG_LAUNCH_CHECK();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, offsets);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+// ... and the samples of the kept nuggets into the packed list (ridx i64, samples f32[.,3], depths, deltas; K_max = nugget capacity)
+int pag_voxel_emit_dyn(const float* origins, const float* dirs, const int64_t* nug_ridx, const float* nug_depth, const int32_t* rel,
+                       const int64_t* nug_offsets, const int64_t* offsets, int64_t N, int64_t K_max, int S, uint32_t seed,
+                       const uint32_t* seed_dev, int64_t* ridx, float* samples, float* depths, float* deltas, void* stream) {
+    if (S <= 0) return PAG_ERR_ARG;
+    if (N == 0 || K_max == 0) return PAG_OK;
+    voxel_emit_kernel<<<pag_grid(K_max * S, 256), 256, 0, (cudaStream_t)stream>>>(origins, dirs, nug_ridx, nug_depth, rel, nug_offsets, offsets,
+                                                                                 N, K_max, S, seed, seed_dev, ridx, samples, depths, deltas);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

@@ -282,6 +282,32 @@ __global__ void __launch_bounds__(128) gather_probe_kernel(const float* __restri
     sink[t] = acc;
 }
 
+// L2 read-bandwidth probe: every CTA streams the whole buffer `iters` times with coalesced 16-byte loads, each CTA starting at
+// its own offset so that the L2 slices are loaded evenly; the buffer (<= 64 MB) stays resident in the 126 MB L2 after the first pass
+__global__ void __launch_bounds__(256) l2_stream_probe_kernel(const uint4* __restrict__ buf, int64_t n16, int iters, float* __restrict__ sink) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        const int64_t start = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x + (int64_t)it * 4099 * blockDim.x) % n16;
+        int64_t i = start;
+        for (int64_t k = 0; k < n16; k += stride * 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int64_t j = i + u * stride;
+                if (j >= n16) j -= n16;
+                if (j >= n16) j %= n16;
+                asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(buf + j));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+            i += 4 * stride;
+            if (i >= n16) i %= n16;
+        }
+    }
+    sink[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float(acc & 0x007fffffu);
+}
+
 extern "C" {
 
 // forward: out[M, 2L] (level-major, feature-minor)
@@ -408,6 +434,16 @@ int pag_permuto_indices(const float* pos, int64_t M, int64_t capacity, int L, co
 int pag_gather_probe(const float* table, int64_t entries, int64_t threads, int loads_per_thread, float* sink, void* stream) {
     if (entries <= 0 || entries > 0xFFFFFFFFll || threads <= 0 || loads_per_thread <= 0 || (loads_per_thread & 15)) return PAG_ERR_ARG;
     gather_probe_kernel<<<pag_grid(threads, 128), 128, 0, (cudaStream_t)stream>>>(table, (uint32_t)entries, threads, loads_per_thread, sink);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// ---- L2 read-bandwidth probe (the denominator of the encoders' "l2" roofline) -----------------------------------------------
+// All CTAs together read `bytes` (multiple of 16, <= L2 size) `iters` times: bytes * iters / time = L2 -> SM read bandwidth once
+// the buffer is L2 resident.  sink: 148 * 8 * 256 floats.
+int pag_l2_stream_probe(const void* buf, int64_t bytes, int iters, float* sink, void* stream) {
+    if (bytes <= 0 || (bytes & 15) || iters <= 0) return PAG_ERR_ARG;
+    l2_stream_probe_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(buf), bytes / 16, iters, sink);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

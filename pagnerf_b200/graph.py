@@ -15,15 +15,44 @@ class GraphedStep:
         loss = g(*new_inputs)        # copies inputs into the static buffers, replays, returns the static loss tensor
     `.grad` of `params` are static tensors refreshed by every replay.  step_fn must not keep references to tensors
     that carry a grad_fn between calls (they would pin AccumulateGrad nodes created on another stream).
+
+    Device pointers baked into the graph: parameters / static inputs (stable), the occupancy bit field and the LOD weights
+    (both refreshed IN PLACE by OctreeAS.init / PanopticNeF._lodw, so prune() and LOD annealing need no action), and -- for
+    octree levels < 2, where the fused trace marches against the octree itself -- blas.octree / blas.prefix, which prune()
+    replaces.  `__call__` compares those addresses with the live ones and re-captures when any changed.
     """
 
     def __init__(self, step_fn, example_inputs, params, nef, warmup=3):
         self.params = list(params)
+        self.step_fn, self.nef, self.warmup = step_fn, nef, warmup
         self.static_inputs = [x.clone() for x in example_inputs]
+        self._capture()
+
+    def _signature(self):
+        nef = self.nef
+        blas = nef.grid.blas
+        lvl = nef.grid.blas_level
+        bits = blas._bits.get(int(lvl)) if lvl >= 2 else None
+        lodw = getattr(nef, '_lodw_dev', None)
+        return (bits.data_ptr() if bits is not None else (blas.octree.data_ptr(), blas.prefix.data_ptr()),
+                lodw.data_ptr() if lodw is not None else None)
+
+    def _capture(self):
+        nef, step_fn, warmup = self.nef, self.step_fn, self.warmup
         dev = self.static_inputs[0].device
         blas = nef.grid.blas.to(dev)
         if getattr(blas, 'seed_tensor', None) is None:
             blas.seed_tensor = torch.full((1,), int(blas.jitter_seed), dtype=torch.int32, device=dev)
+        blas.graph_seed_active = True      # fused traces read (and advance) the device-resident jitter seed from here on ...
+        try:
+            self._capture_inner(step_fn, warmup)
+        finally:
+            blas.graph_seed_active = False  # ... until capture is over: eager traces keep following blas.jitter_seed
+        blas.jitter_seed = int(blas.seed_tensor.item())
+        self.blas = blas
+        self.sig = self._signature()
+
+    def _capture_inner(self, step_fn, warmup):
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -43,6 +72,11 @@ class GraphedStep:
             self.loss.backward()
 
     def __call__(self, *inputs):
+        if self._signature() != self.sig:      # prune() on a coarse octree / a re-allocated weight vector: stale addresses
+            self.graph = None
+            self._capture()
+        if not self.blas.fixed_jitter:         # host mirror of the device-side seed the replay advances
+            self.blas.jitter_seed = (self.blas.jitter_seed + 1) & 0x7FFFFFFF
         for dst, src in zip(self.static_inputs, inputs):
             dst.copy_(src, non_blocking=True)
         self.graph.replay()

@@ -629,8 +629,12 @@ def _enc_fwd(kind, spec, samples, Mmax, m_dev, ph, table, out, img):
              ptr(sf), ptr(sh), ptr(an), ptr(out))
     else:
         fl, fparam, res, offset, size, L, round_half, _, cast_half = spec
-        call("pag_hash_fwd_dyn", int(fl), ptr(samples), Mmax, ptr(m_dev), int(bool(ph and cast_half)), ptr(table), L, 2, ptr(fparam),
-             ptr(res), ptr(offset), ptr(size), ptr(out), int(bool(round_half)))
+        if img:
+            call("pag_hash_fwd_img16_dyn", int(fl), ptr(samples), Mmax, ptr(m_dev), int(bool(ph and cast_half)), ptr(table), L, 2, ptr(fparam),
+                 ptr(res), ptr(offset), ptr(size), ptr(out))
+        else:
+            call("pag_hash_fwd_dyn", int(fl), ptr(samples), Mmax, ptr(m_dev), int(bool(ph and cast_half)), ptr(table), L, 2, ptr(fparam),
+                 ptr(res), ptr(offset), ptr(size), ptr(out), int(bool(round_half)))
 
 
 def _enc_bwd(kind, spec, samples, Mmax, m_dev, ph, table, g, scale, g_table, g_pos, img, l0=0, l1=None):
@@ -644,8 +648,12 @@ def _enc_bwd(kind, spec, samples, Mmax, m_dev, ph, table, g, scale, g_table, g_p
                  ptr(g), ptr(g_table), ptr(g_pos), int(n_agg))
     else:
         fl, fparam, res, offset, size, L, _, n_agg, cast_half = spec
-        call("pag_hash_bwd_dyn", int(fl), ptr(samples), Mmax, ptr(m_dev), int(bool(ph and cast_half)), ptr(table), L, 2, ptr(fparam),
-             ptr(res), ptr(offset), ptr(size), ptr(g), ptr(g_table), ptr(g_pos), int(n_agg))
+        if img:
+            call("pag_hash_bwd_img16_dyn", int(fl), ptr(samples), Mmax, ptr(m_dev), int(bool(ph and cast_half)), ptr(table), L, 2, ptr(fparam),
+                 ptr(res), ptr(offset), ptr(size), ptr(g), ptr(scale), ptr(g_table), ptr(g_pos), int(n_agg))
+        else:
+            call("pag_hash_bwd_dyn", int(fl), ptr(samples), Mmax, ptr(m_dev), int(bool(ph and cast_half)), ptr(table), L, 2, ptr(fparam),
+                 ptr(res), ptr(offset), ptr(size), ptr(g), ptr(g_table), ptr(g_pos), int(n_agg))
 
 
 class FusedTraceFn(Function):
@@ -665,34 +673,60 @@ class FusedTraceFn(Function):
         ctx.set_materialize_grads(False)      # outputs the loss does not use arrive as None: their backward chain is skipped
         o, d = _f32(origins), _f32(dirs)
         N, S, dev = o.shape[0], int(cfg['S']), o.device
-        Mmax = max(N * S, 1)
-        lin = _linspace(S, dev)
+        voxel = cfg.get('march', 'ray') == 'voxel'
         f32, i64 = torch.float32, torch.int64
         counts = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
         offsets = torch.empty(N + 1, dtype=i64, device=dev)
-        near = float(cfg['near'])
-        rng = float(torch.tensor(float(cfg['far']) - near, dtype=f32))
         seed_dev = cfg.get('seed_dev')
-        ridx = torch.empty(Mmax, dtype=i64, device=dev)
-        samples = torch.empty(Mmax, 3, dtype=f32, device=dev)
-        depths = torch.empty(Mmax, dtype=f32, device=dev)
-        deltas = torch.empty(Mmax, dtype=f32, device=dev)
-        bits = cfg.get('bits')
-        if bits is not None:
-            # occupancy bit field instead of the octree descent, 128-bit step masks instead of N*S point indices
-            masks = torch.empty(max(N, 1) * ((S + 31) // 32), dtype=torch.int32, device=dev)
-            call("pag_march_ray_bits_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(bits),
-                 int(cfg['level']), ptr(masks), ptr(counts), ptr(offsets), ptr(seed_dev))
-            call("pag_march_ray_bits_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(masks),
-                 ptr(offsets), ptr(ridx), ptr(samples), ptr(depths), ptr(deltas), ptr(seed_dev))
+        if voxel:
+            # 'voxel' marching (kaolin raytrace nuggets, S samples per nugget) without a host sync: the nuggets live in buffers
+            # sized for the DDA worst case (a ray crosses at most 3 * 2^level - 2 cells of the level's grid); only the first
+            # K = nug_off[N] entries are ever touched.  The max-travel filter is folded into the kept-nugget count.
+            level = int(cfg['level'])
+            Kmax = max(N * min(3 * (1 << level) - 2, int(cfg.get('max_nuggets_per_ray') or (1 << 30))), 1)
+            Mmax = Kmax * S
+            nug_off = torch.empty(N + 1, dtype=i64, device=dev)
+            call("pag_raytrace_count", ptr(cfg['octree']), ptr(cfg['prefix']), ptr(o), ptr(d), N, level, ptr(counts), ptr(nug_off))
+            nug_ridx = torch.empty(Kmax, dtype=i64, device=dev)
+            nug_pidx = torch.empty(Kmax, dtype=i64, device=dev)
+            nug_depth = torch.empty(Kmax, 2, dtype=f32, device=dev)
+            call("pag_raytrace_emit", ptr(cfg['octree']), ptr(cfg['prefix']), ptr(o), ptr(d), N, level, ptr(nug_off), ptr(nug_ridx),
+                 ptr(nug_pidx), ptr(nug_depth))
+            rel = torch.empty(Kmax, dtype=torch.int32, device=dev)
+            mt = cfg.get('max_travel')
+            call("pag_voxel_filter_count", ptr(nug_depth), ptr(nug_off), N, S, int(cfg['seed']), ptr(seed_dev),
+                 float(mt if mt is not None else 0.0), int(mt is not None), ptr(rel), ptr(counts), ptr(offsets))
+            ridx = torch.empty(Mmax, dtype=i64, device=dev)
+            samples = torch.empty(Mmax, 3, dtype=f32, device=dev)
+            depths = torch.empty(Mmax, dtype=f32, device=dev)
+            deltas = torch.empty(Mmax, dtype=f32, device=dev)
+            call("pag_voxel_emit_dyn", ptr(o), ptr(d), ptr(nug_ridx), ptr(nug_depth), ptr(rel), ptr(nug_off), ptr(offsets), N, Kmax, S,
+                 int(cfg['seed']), ptr(seed_dev), ptr(ridx), ptr(samples), ptr(depths), ptr(deltas))
         else:
-            pidx_tmp = torch.empty(Mmax, dtype=torch.int32, device=dev)
-            call("pag_march_ray_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng,
-                 ptr(cfg['octree']), ptr(cfg['prefix']), int(cfg['level']), ptr(pidx_tmp), ptr(counts), ptr(offsets), ptr(seed_dev))
-            call("pag_march_ray_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(pidx_tmp),
-                 ptr(offsets), ptr(ridx), None, ptr(samples), ptr(depths), ptr(deltas), None, ptr(seed_dev))
+            Mmax = max(N * S, 1)
+            lin = _linspace(S, dev)
+            near = float(cfg['near'])
+            rng = float(torch.tensor(float(cfg['far']) - near, dtype=f32))
+            ridx = torch.empty(Mmax, dtype=i64, device=dev)
+            samples = torch.empty(Mmax, 3, dtype=f32, device=dev)
+            depths = torch.empty(Mmax, dtype=f32, device=dev)
+            deltas = torch.empty(Mmax, dtype=f32, device=dev)
+            bits = cfg.get('bits')
+            if bits is not None:
+                # occupancy bit field instead of the octree descent, 128-bit step masks instead of N*S point indices
+                masks = torch.empty(max(N, 1) * ((S + 31) // 32), dtype=torch.int32, device=dev)
+                call("pag_march_ray_bits_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(bits),
+                     int(cfg['level']), ptr(masks), ptr(counts), ptr(offsets), ptr(seed_dev))
+                call("pag_march_ray_bits_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(masks),
+                     ptr(offsets), ptr(ridx), ptr(samples), ptr(depths), ptr(deltas), ptr(seed_dev))
+            else:
+                pidx_tmp = torch.empty(Mmax, dtype=torch.int32, device=dev)
+                call("pag_march_ray_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng,
+                     ptr(cfg['octree']), ptr(cfg['prefix']), int(cfg['level']), ptr(pidx_tmp), ptr(counts), ptr(offsets), ptr(seed_dev))
+                call("pag_march_ray_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(cfg['seed']), near, rng, ptr(pidx_tmp),
+                     ptr(offsets), ptr(ridx), None, ptr(samples), ptr(depths), ptr(deltas), None, ptr(seed_dev))
         m_dev = offsets[N:]                      # device-side packed-sample count M
-        if seed_dev is not None:
+        if seed_dev is not None and not cfg.get('fixed_jitter'):
             seed_dev.add_(1)                     # next replay / step draws the next jitter stream
         kind = cfg.get('grid_kind', 'permuto')
         L = _enc_levels(kind, cfg['grid'])
@@ -703,12 +737,15 @@ class FusedTraceFn(Function):
         # on the decoder side, coalesced 16-byte accesses on the encoder side); the f32 [M, 2L] layout stays for compaction
         # and for the hash grids
         dd = bool(cfg.get('dd'))      # PanopticDDensity field + tracer: own panoptic density stream, weights carry gradient
-        img = (bool(cfg.get('img16', IMG16)) and not cfg.get('compact', COMPACT_LIVE) and IN % 8 == 0 and kind == 'permuto'
-               )
+        # live-sample compaction drops samples whose COLOUR density is 0; with the DD field the panoptic density
+        # relu(y0.detach() + delta_density) can be positive there, so the two are never combined
+        compact = bool(cfg.get('compact', COMPACT_LIVE)) and not dd
+        img = bool(cfg.get('img16', IMG16)) and not compact and IN % 4 == 0 and (kind == 'hash' or IN % 8 == 0) and (not dd or IN % 16 == 0)
         Tmax = (Mmax + 127) // 128
+        nXc = ((IN + 15) // 16) * 2      # 16-byte chunks per row of an operand-image tile (features padded to a multiple of 16)
 
         def feat_buffer():
-            return (torch.empty(Tmax, IN // 8, 128, 8, dtype=torch.float16, device=dev) if img
+            return (torch.empty(Tmax, nXc, 128, 8, dtype=torch.float16, device=dev) if img
                     else torch.empty(Mmax, IN, dtype=f32, device=dev))
 
         feats = feat_buffer()
@@ -719,7 +756,7 @@ class FusedTraceFn(Function):
         Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
         src = cfg['pan_src'] if (Cs or Ci) else 'none'
         m_all = m_dev
-        if cfg.get('compact', COMPACT_LIVE):
+        if compact:
             # density-only pass over every packed sample, then drop the ones with sigma == 0 (weight 0, gradient 0: exact)
             # from the list; everything below -- colour / panoptic decoders, delta-grid encode, the whole backward -- runs on
             # the survivors.  The list stays ray-sorted; offsets_c / its last entry replace offsets / the sample count.
@@ -816,8 +853,10 @@ class FusedTraceFn(Function):
         Tmax = (Mmax + 127) // 128
         m_dev = offsets[N:]
 
+        nXc = ((IN + 15) // 16) * 2
+
         def grad_buffer():      # feature gradients: fp16 operand images (still carrying the loss scale) or f32 rows
-            return (torch.empty(Tmax, IN // 8, 128, 8, dtype=torch.float16, device=dev) if img
+            return (torch.empty(Tmax, nXc, 128, 8, dtype=torch.float16, device=dev) if img
                     else torch.empty(Mmax, IN, dtype=torch.float32, device=dev))
 
         f32 = torch.float32

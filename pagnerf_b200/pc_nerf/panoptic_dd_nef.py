@@ -56,7 +56,7 @@ class PanopticDDensityNeF(PanopticNeF):
     def fused_panoptic_ok(self, channels):     # the modular fused kernels composite with the detached colour density: not this model
         return False
 
-    def fused_trace_cfg(self, channels, rays, num_steps, bg_color, dd=False):
+    def fused_trace_cfg(self, channels, rays, num_steps, bg_color, raymarch_type='ray', max_travel=None, dd=False):
         """Sync-free fused trace with the panoptic density stream (ops.FusedTraceFn, cfg['dd']).  Only for the DD tracer (dd=True):
         PanopticPackedRFTracer would composite the panoptic channels with the detached colour density."""
         if not dd or self.separate_sem_grid or not (self.sem_softmax and self.inst_softmax):
@@ -67,7 +67,7 @@ class PanopticDDensityNeF(PanopticNeF):
         try:
             ok_shapes = (self.effective_feature_dim <= 48 and self.effective_feature_dim % 4 == 0 and self.num_classes <= 16
                          and self.num_instances <= 208)
-            cfg = super().fused_trace_cfg(channels, rays, num_steps, bg_color) if ok_shapes else None
+            cfg = super().fused_trace_cfg(channels, rays, num_steps, bg_color, raymarch_type, max_travel) if ok_shapes else None
         finally:
             del self.fused_panoptic_ok
         if cfg is not None:

@@ -32,6 +32,9 @@ class PanopticDeltaNeF(PanopticNeF):
     def get_nef_type(self):
         return 'delta_panoptic_nef'
 
+    def _prune_supported(self):
+        return True      # the delta field prunes every grid type (pc_nerf/panoptic_delta_nef.py:63-104)
+
     def _prune_grids(self):
         return [self.grid] + ([self.delta_grid] if 'delta_grid' in dir(self) else [])
 

@@ -123,9 +123,15 @@ class PanopticNeF(BaseNeuralField):
     def _prune_grids(self):
         return [self.grid]
 
+    def _prune_supported(self):
+        # the base field prunes the hash grids only and raises for anything else (pc_nerf/panoptic_nef.py:211,235)
+        return self.grid_type in ["HashGrid", "HashGridTorch", "HashGridTinyCudaNN", "TriplanarGrid"]
+
     def prune(self):
         if self.grid is None:
             return
+        if not self._prune_supported():
+            raise NotImplementedError
         density_decay = 0.6
         min_density = ((0.01 * 512) / np.sqrt(3))
         dev = self.device
@@ -142,7 +148,12 @@ class PanopticNeF(BaseNeuralField):
         _points = points[mask]
         for grid in self._prune_grids():
             octree = spc.unbatched_points_to_octree(_points, grid.blas_level, sorted=True)
-            grid.blas_init(octree)
+            # PermutoGrid re-registers its checkpoint buffers (blas_octree / points / prefix / pyramid); the hash grids keep
+            # the state_dict keys they were built with (pc_nerf/panoptic_delta_nef.py:98-104, pc_nerf/panoptic_nef.py:233)
+            if self.grid_type == "PermutoGrid":
+                grid.blas_init(octree)
+            else:
+                grid.blas.init(octree)
 
     # ---- forward ---------------------------------------------------------------------------------
     def forward(self, channels=None, **kwargs):
@@ -170,7 +181,13 @@ class PanopticNeF(BaseNeuralField):
         t = self.lod_weights
         key = (id(t), t._version, str(device))
         if getattr(self, '_lodw_key', None) != key:
-            self._lodw_key, self._lodw_dev = key, t.detach().to(device=device, dtype=torch.float32).contiguous()
+            new = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            old = getattr(self, '_lodw_dev', None)
+            if old is not None and old.shape == new.shape and old.device == new.device:
+                old.copy_(new)      # in place: a captured CUDA graph (graph.GraphedStep) keeps reading the live weights
+            else:
+                self._lodw_dev = new
+            self._lodw_key = key
         return self._lodw_dev
 
     def _use_tc(self):
@@ -228,7 +245,7 @@ class PanopticNeF(BaseNeuralField):
             return 'appearance'
         return {None: 'delta', 'delta': 'delta', 'separate': 'separate', 'appearance': 'appearance'}.get(self.panoptic_features_type)
 
-    def fused_trace_cfg(self, channels, rays, num_steps, bg_color):
+    def fused_trace_cfg(self, channels, rays, num_steps, bg_color, raymarch_type='ray', max_travel=None):
         """Configuration for ops.FusedTraceFn (sync-free training trace), or None when this field / request is not
         covered by it ('ray' marching on PermutoGrid fields with the reference decoder shapes, tensor-core mode)."""
         from ..grids import PermutoGrid, HashGridTinyCudaNN, HashGridTorch
@@ -264,8 +281,13 @@ class PanopticNeF(BaseNeuralField):
         dmin = float(rays.dist_min) if not torch.is_tensor(rays.dist_min) else float(rays.dist_min.flatten()[0])
         dmax = float(rays.dist_max) if not torch.is_tensor(rays.dist_max) else float(rays.dist_max.flatten()[0])
         return dict(octree=blas.octree, prefix=blas.prefix, level=self.grid.blas_level, S=int(num_steps), near=dmin, far=dmax,
+                    march=raymarch_type, max_travel=max_travel,
                     bits=blas.level_bits(self.grid.blas_level) if self.grid.blas_level >= 2 else None,
-                    seed=seed, seed_dev=getattr(blas, 'seed_tensor', None), bg_white=(bg_color == 'white'), pos_half=torch.is_autocast_enabled(),
+                    seed=seed, fixed_jitter=bool(blas.fixed_jitter),
+                    # the device-resident seed is for CUDA-graph capture / replay only (graph.GraphedStep); eager traces follow
+                    # blas.jitter_seed like the step-by-step path
+                    seed_dev=getattr(blas, 'seed_tensor', None) if getattr(blas, 'graph_seed_active', False) else None,
+                    bg_white=(bg_color == 'white'), pos_half=torch.is_autocast_enabled(),
                     lodw=self._lodw(dev), grid_kind=kind, grid=enc(self.grid.embedder),
                     dgrid=enc(self.delta_grid.embedder) if src in ('delta', 'separate') else None, pan_src=src,
                     want_rgb='rgb' in channels, want_depth='depth' in channels,

@@ -110,20 +110,31 @@ class OctreeAS:
         self.jitter_seed = 0       # seed of the counter-based jitter stream; bumped per raymarch call
         self.fixed_jitter = False  # tests pin the stream
         self._bits = {}            # level -> occupancy bit field (see level_bits)
+        self.version = 0           # bumped by every init(): consumers that cache device pointers (graph.GraphedStep) compare it
 
     def init(self, octree):
-        octree = octree.to(self.device).to(torch.uint8).contiguous()
+        # the scan is ~40 small integer ops per level: on the tensor's own device (an octree that arrives on the host -- a
+        # checkpoint, a golden -- is scanned there and moved once, instead of ~900 tiny launches on the GPU)
+        octree = octree.to(torch.uint8).contiguous()
         level = octree_max_level(octree)
-        self.points, self.pyramid, self.prefix = scan_octree(octree, level)
-        self.points = self.points.contiguous()
-        self.prefix = self.prefix.contiguous()
+        points, self.pyramid, prefix = scan_octree(octree, level)
+        self.points = points.contiguous().to(self.device)
+        self.prefix = prefix.contiguous().to(self.device)
+        octree = octree.to(self.device)
         self.octree = octree
         self.max_level = level
-        self._bits = {}
+        self.version += 1
+        # occupancy bit fields have a fixed size per level: refresh the cached ones IN PLACE, so that a CUDA graph that
+        # captured their address (the fused training trace marches against them) sees the pruned octree on its next replay
+        for lvl, b in list(self._bits.items()):
+            if b.device == octree.device and b.is_cuda and lvl <= level:
+                ops.call("pag_octree_level_bits", ops.ptr(self.octree), ops.ptr(self.prefix), lvl, ops.ptr(b))
+            else:
+                del self._bits[lvl]
 
     def init_dense(self, level):
         n_nodes = (8 ** level - 1) // 7
-        self.init(torch.full((n_nodes,), 0xFF, dtype=torch.uint8, device=self.device))
+        self.init(torch.full((n_nodes,), 0xFF, dtype=torch.uint8))      # scanned on the host, moved once
 
     def to(self, device):
         device = torch.device(device)

@@ -24,9 +24,10 @@ class PanopticDDensityPackedRFTracer(PanopticPackedRFTracer):
         if lod_idx is None:
             lod_idx = nef.grid.num_lods - 1
         plain = not extra_channels and not (self.ray_sparcity_reg > 0.0 and stage == 'train')
-        if plain and raymarch_type == 'ray' and self.allow_fused and hasattr(nef, 'fused_trace_cfg'):
+        if plain and raymarch_type in ('ray', 'voxel') and self.allow_fused and hasattr(nef, 'fused_trace_cfg'):
             try:
-                cfg = nef.fused_trace_cfg(channels, rays, num_steps, bg_color, dd=True)
+                cfg = nef.fused_trace_cfg(channels, rays, num_steps, bg_color, raymarch_type,
+                                          self.ray_max_travel if raymarch_type == 'voxel' else None, dd=True)
             except TypeError:          # a field without the panoptic density stream
                 cfg = None
             if cfg is not None and cfg.get('dd'):

@@ -25,7 +25,7 @@ class PanopticPackedRFTracer(PackedRFTracer):
         self.panoptic_channels = {'semantics', 'inst_embedding'}
         self.ray_sparcity_reg = ray_sparcity_reg
         self.ray_max_travel = ray_max_travel
-        self.allow_fused = True     # sync-free fused trace in training mode ('ray' marching, PermutoGrid fields)
+        self.allow_fused = True     # sync-free fused trace in training mode ('ray' and 'voxel' marching)
 
     def get_supported_channels(self):
         return {'depth', 'hit', 'rgb', 'alpha', 'semantics', 'inst_embedding'}
@@ -42,8 +42,11 @@ class PanopticPackedRFTracer(PackedRFTracer):
             lod_idx = nef.grid.num_lods - 1
 
         plain = not extra_channels and not (self.ray_sparcity_reg > 0.0 and stage == 'train')
-        if plain and raymarch_type == 'ray' and self.allow_fused and hasattr(nef, 'fused_trace_cfg'):
-            cfg = nef.fused_trace_cfg(channels, rays, num_steps, bg_color)
+        if plain and raymarch_type in ('ray', 'voxel') and self.allow_fused and hasattr(nef, 'fused_trace_cfg'):
+            # 'voxel' (the trainer's mode from epoch 201 on, configs/bup20/best.yaml:34): nuggets + max-travel filter (:88-108)
+            # stay on the device as well
+            cfg = nef.fused_trace_cfg(channels, rays, num_steps, bg_color, raymarch_type,
+                                      self.ray_max_travel if raymarch_type == 'voxel' else None)
             if cfg is not None:
                 # training mode, sync-free: march -> encode -> decode -> composite as one autograd node
                 table, dtable, wts = nef.fused_trace_tensors()

@@ -764,3 +764,91 @@ def test_fused_trace_channel_subsets(cuda_lib, chans):
     assert set(res[0][1]) == set(res[1][1]), "the same parameters receive gradient on both paths"
     for k in res[0][1]:
         assert_close_norm(res[0][1][k], res[1][1][k], rel_l2=5e-3, max_frac=2e-2, msg="grad " + k)
+
+
+# ------------------------------------------------------------------------------------------------
+# sync-free 'voxel' marching (the trainer's mode from epoch 201 on: configs/bup20/best.yaml:34, pc_nerf/trainer.py:362-366)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("max_travel", [None, 0.35])
+def test_voxel_device_side_march_bit_exact(cuda_lib, max_travel):
+    """Device-side nugget filter + sample emit (no host sync, worst-case buffers) == raytrace -> voxel samples -> max-travel
+    filter of the step-by-step path and of the oracle, bit for bit (packed order, ray ids, positions, depths, deltas)."""
+    from oracle import spc as ospc, raymarch as orm
+    from pagnerf_b200 import ops, spc
+    from pagnerf_b200._lib import call, ptr
+    level, S, N, seed = 5, 3, 700, 11
+    pts = _scene(level, seed=4, frac=0.2)
+    octree = spc.unbatched_points_to_octree(torch.from_numpy(pts), level)
+    blas = spc.OctreeAS(DEV)
+    blas.init(octree)
+    o_np, d_np = _rays(N, seed=5)
+    o, d = torch.from_numpy(o_np).to(DEV), torch.from_numpy(d_np).to(DEV)
+    # reference: step-by-step ops (each bit-exact vs the oracle in test_raymarch_voxel_bit_exact_and_filter)
+    ridx, pidx, samples, depths, deltas, boundary, off = ops.raymarch_voxel(blas.octree, blas.prefix, o, d, level, S, seed=seed)
+    if max_travel is not None:
+        keep = ops.max_travel_mask(ridx, depths, ops.ray_offsets(ridx, N), max_travel)
+        assert 0 < int(keep.sum()) < keep.numel(), "the filter must drop something for this test to mean anything"
+        deltas = deltas.reshape(depths.shape)[keep].reshape(-1)
+        ridx, samples, depths = ridx[keep], samples[keep], depths[keep]
+    ref_ridx = ridx.repeat_interleave(S)
+    # device-side chain
+    Kmax = N * (3 * (1 << level) - 2)
+    counts = torch.empty(N, dtype=torch.int32, device=DEV)
+    nug_off = torch.empty(N + 1, dtype=torch.int64, device=DEV)
+    call("pag_raytrace_count", ptr(blas.octree), ptr(blas.prefix), ptr(o), ptr(d), N, level, ptr(counts), ptr(nug_off))
+    assert int(nug_off[-1]) <= Kmax
+    nr = torch.empty(Kmax, dtype=torch.int64, device=DEV); npx = torch.empty(Kmax, dtype=torch.int64, device=DEV)
+    nd = torch.empty(Kmax, 2, device=DEV)
+    call("pag_raytrace_emit", ptr(blas.octree), ptr(blas.prefix), ptr(o), ptr(d), N, level, ptr(nug_off), ptr(nr), ptr(npx), ptr(nd))
+    rel = torch.empty(Kmax, dtype=torch.int32, device=DEV)
+    offsets = torch.empty(N + 1, dtype=torch.int64, device=DEV)
+    call("pag_voxel_filter_count", ptr(nd), ptr(nug_off), N, S, seed, None, float(max_travel or 0.0), int(max_travel is not None),
+         ptr(rel), ptr(counts), ptr(offsets))
+    M = int(offsets[-1])
+    assert M == ref_ridx.shape[0]
+    r2 = torch.full((Kmax * S,), -1, dtype=torch.int64, device=DEV)
+    s2 = torch.zeros(Kmax * S, 3, device=DEV); dp2 = torch.zeros(Kmax * S, device=DEV); dl2 = torch.zeros(Kmax * S, device=DEV)
+    call("pag_voxel_emit_dyn", ptr(o), ptr(d), ptr(nr), ptr(nd), ptr(rel), ptr(nug_off), ptr(offsets), N, Kmax, S, seed, None,
+         ptr(r2), ptr(s2), ptr(dp2), ptr(dl2))
+    assert torch.equal(r2[:M], ref_ridx)
+    assert torch.equal(s2[:M], samples.reshape(-1, 3)), "sample positions bit-exact"
+    assert torch.equal(dp2[:M], depths.reshape(-1)) and torch.equal(dl2[:M], deltas.reshape(-1))
+    assert torch.equal(offsets, ops.ray_offsets(ridx, N) * S)
+
+
+@pytest.mark.parametrize("with_pose_grad", [False, True])
+def test_sync_free_fused_trace_equals_stepwise_voxel(cuda_lib, with_pose_grad):
+    """ops.FusedTraceFn with 'voxel' marching (nuggets, max-travel filter and samples on the device) vs the step-by-step plugin
+    path on the reference-made voxel golden's field, rays and filter threshold; tensor-core decoders on both sides."""
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_voxel")
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    res = []
+    for fused in (True, False):
+        nef = build_cuda_nef(g, DEV)
+        nef.decoder_precision = 'fp16'
+        tracer = PanopticPackedRFTracer(raymarch_type='voxel', num_steps=int(g["num_steps"]), bg_color='white',
+                                        ray_max_travel=float(g["ray_max_travel"]))
+        tracer.allow_fused = fused
+        o = torch.from_numpy(g["o"]).to(DEV).requires_grad_(with_pose_grad)
+        d = torch.from_numpy(g["d"]).to(DEV).requires_grad_(with_pose_grad)
+        rb = tracer(nef, channels=chans, rays=Rays(origins=o, dirs=d, dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+        assert torch.is_tensor(tracer.last_num_samples) == fused, "fused path keeps the sample count on the device"
+        n = int(tracer.last_num_samples)
+        loss = sum((getattr(rb, c) * torch.from_numpy(g["gw_" + c]).to(DEV)).sum() for c in chans)
+        loss.backward()
+        res.append(({c: getattr(rb, c).detach() for c in chans + ['alpha', 'hit']}, {k: p.grad.clone() for k, p in nef.named_parameters()},
+                    o.grad if with_pose_grad else None, d.grad if with_pose_grad else None, n))
+    assert res[0][4] == res[1][4] > 0, "same packed-sample count"
+    assert torch.equal(res[0][0]['hit'], res[1][0]['hit'])
+    for c in chans + ['alpha']:
+        assert_close(res[0][0][c], res[1][0][c], rtol=1e-3, atol_scale=1e-3, msg=c)
+    for k in res[0][1]:
+        assert_close_norm(res[0][1][k], res[1][1][k], rel_l2=5e-3, max_frac=2e-2, msg="grad " + k)
+    if with_pose_grad:
+        assert_close_norm(res[0][2], res[1][2], rel_l2=5e-3, max_frac=2e-2, msg="grad origins")
+        assert_close_norm(res[0][3], res[1][3], rel_l2=5e-3, max_frac=2e-2, msg="grad dirs")
+    # and against the reference-made golden outputs at the fp16 tolerance
+    for c in chans + ['alpha']:
+        assert_close(res[0][0][c], g["out_" + c], msg="golden " + c, rtol=3e-3, atol_scale=3e-3)
