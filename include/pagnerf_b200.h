@@ -287,6 +287,16 @@ int pag_expint_bwd(const float* gw, const float* w, const float* T, const int64_
  * the backward in multi-GPU training -- can make progress.  previous (host, nullable) receives the old value. */
 int pag_set_reserved_sms(int n, int* previous /* host */);
 
+/* ---- camera-pose transform of the base rays (bundle adjustment) ----
+ * Replaces BAPipeline.transform_rays (pc_nerf/ba_pipeline.py:85-92; kaolin Camera.extrinsics 'matrix_6dof_rotation' backend :44,
+ * inv_transform_rays + renormalised directions :88-89) and its autograd backward into the 9 pose parameters per camera
+ * (a1, a2: 6-D rotation, Gram-Schmidt rows of the view rotation; t: view translation).  Rays are grouped by camera, B per group;
+ * cam_idx (nullable = identity) maps group -> parameter row; g_params is accumulated into. */
+int pag_pose_transform_fwd(const float* params, const int64_t* cam_idx, const float* base_o, const float* base_d, int64_t C, int64_t B,
+                           float* out_o, float* out_d, void* stream);
+int pag_pose_transform_bwd(const float* params, const int64_t* cam_idx, const float* base_o, const float* base_d, const float* g_o,
+                           const float* g_d, int64_t C, int64_t B, float* g_params, void* stream);
+
 /* ---- achievable-gather-bandwidth probe (bench.py: denominator of the encoder's roofline fraction) ----
  * threads x loads_per_thread (multiple of 16, 16 in flight per thread) uniformly random 8-byte loads from table[entries] float2; sink f32[threads]. */
 int pag_gather_probe(const float* table, int64_t entries, int64_t threads, int loads_per_thread, float* sink, void* stream);

@@ -162,6 +162,44 @@ class RaySamplesFn(Function):
         return go, gd, None, None, None
 
 
+class PoseTransformFn(Function):
+    """BAPipeline.transform_rays (pc_nerf/ba_pipeline.py:85-92): camera-space base rays -> world-space rays through the 9
+    pose parameters per camera (6-D rotation + translation), directions renormalised; backward reduces d/d(o, d) to the
+    parameter rows, one CTA per camera (csrc/pose.cu)."""
+
+    @staticmethod
+    def forward(ctx, params, cam_idx, base_o, base_d):
+        _chk(params, cam_idx, base_o, base_d)
+        p = _f32(params)
+        ci = cam_idx.to(torch.int64).contiguous()
+        bo, bd = _f32(base_o).reshape(-1, 3), _f32(base_d).reshape(-1, 3)
+        C = ci.shape[0]
+        if C == 0 or bo.shape[0] % C:
+            raise ValueError("base rays must be grouped by camera with the same number of rays per camera")
+        B = bo.shape[0] // C
+        o, d = torch.empty_like(bo), torch.empty_like(bd)
+        call("pag_pose_transform_fwd", ptr(p), ptr(ci), ptr(bo), ptr(bd), C, B, ptr(o), ptr(d))
+        ctx.save_for_backward(p, ci, bo, bd)
+        ctx.shape = params.shape
+        return o, d
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_o, g_d):
+        p, ci, bo, bd = ctx.saved_tensors
+        C = ci.shape[0]
+        gp = torch.zeros_like(p)
+        go = _f32(g_o) if g_o is not None else None
+        gd = _f32(g_d) if g_d is not None else None
+        if go is not None or gd is not None:
+            call("pag_pose_transform_bwd", ptr(p), ptr(ci), ptr(bo), ptr(bd), ptr(go), ptr(gd), C, bo.shape[0] // C, ptr(gp))
+        return gp.reshape(ctx.shape), None, None, None
+
+
+def pose_transform(params, cam_idx, base_o, base_d):
+    return PoseTransformFn.apply(params, cam_idx, base_o, base_d)
+
+
 # ------------------------------------------------------------------------------------------------
 # encoders
 # ------------------------------------------------------------------------------------------------

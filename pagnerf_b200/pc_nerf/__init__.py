@@ -4,3 +4,4 @@ from .panoptic_delta_nef import PanopticDeltaNeF
 from .panoptic_dd_nef import PanopticDDensityNeF
 
 __all__ = ["PanopticNeF", "PanopticDeltaNeF", "PanopticDDensityNeF"]
+from .ba_pipeline import BAPipeline  # noqa: F401,E402

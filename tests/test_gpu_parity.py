@@ -852,3 +852,85 @@ def test_sync_free_fused_trace_equals_stepwise_voxel(cuda_lib, with_pose_grad):
     # and against the reference-made golden outputs at the fp16 tolerance
     for c in chans + ['alpha']:
         assert_close(res[0][0][c], g["out_" + c], msg="golden " + c, rtol=3e-3, atol_scale=3e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# camera-pose transform (BAPipeline.transform_rays, pc_nerf/ba_pipeline.py:85-92) forward + backward
+# ------------------------------------------------------------------------------------------------
+def _random_poses(n, gen):
+    """n view matrices: random rotations (QR) + translations."""
+    q, _ = torch.linalg.qr(torch.randn(n, 3, 3, generator=gen))
+    q = q * torch.sign(torch.linalg.det(q))[:, None, None]
+    V = torch.eye(4).repeat(n, 1, 1)
+    V[:, :3, :3] = q
+    V[:, :3, 3] = torch.randn(n, 3, generator=gen) * 0.5
+    return V
+
+
+@pytest.mark.parametrize("B", [1, 37, 4096])
+def test_pose_transform_forward_backward(cuda_lib, B):
+    from oracle import pose as opose
+    from pagnerf_b200 import ops
+    gen = torch.Generator().manual_seed(B)
+    n_cam, C = 7, 5
+    V = _random_poses(n_cam, gen)
+    params = opose.params_from_view_matrix(V)
+    params = params + 0.05 * torch.randn(n_cam, 9, generator=gen)      # off the orthonormal manifold: Gram-Schmidt must do work
+    cam_idx = torch.tensor([3, 0, 6, 3, 1])                              # a camera may repeat inside a batch
+    bo = torch.randn(C * B, 3, generator=gen) * 0.1
+    bd = torch.nn.functional.normalize(torch.randn(C * B, 3, generator=gen), dim=-1)
+    go, gd = torch.randn(C * B, 3, generator=gen), torch.randn(C * B, 3, generator=gen)
+    p_ref = params.clone().double().requires_grad_(True)
+    o_ref, d_ref = opose.transform_rays(p_ref, cam_idx, bo.double(), bd.double())
+    ((o_ref * go.double()).sum() + (d_ref * gd.double()).sum()).backward()
+    p = params.clone().to(DEV).requires_grad_(True)
+    o, d = ops.pose_transform(p, cam_idx.to(DEV), bo.to(DEV), bd.to(DEV))
+    assert_close(o, o_ref.float(), rtol=1e-5, atol_scale=1e-6, msg="world origins")
+    assert_close(d, d_ref.float(), rtol=1e-5, atol_scale=1e-6, msg="world dirs")
+    ((o * go.to(DEV)).sum() + (d * gd.to(DEV)).sum()).backward()
+    assert_close(p.grad, p_ref.grad.float(), rtol=1e-4, atol_scale=1e-5, msg="pose parameter gradient")
+    assert float(p.grad[[2, 4, 5]].abs().max()) == 0.0, "cameras that are not in the batch receive no gradient"
+
+
+def test_ba_pipeline_pose_gradients_through_fused_trace(cuda_lib):
+    """BAPipeline (pose table + nef + tracer): d loss / d camera_extrinsics through the fused training trace equals the chain
+    rule applied by the oracle to the trace's own d/d origins, d/d dirs; anchor frames keep a zero gradient (:53-62)."""
+    from oracle import pose as opose
+    from pagnerf_b200.pc_nerf.ba_pipeline import BAPipeline
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_ray")
+    nef = build_cuda_nef(g, DEV)
+    nef.decoder_precision = 'fp16'
+    tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=int(g["num_steps"]), bg_color='white')
+    gen = torch.Generator().manual_seed(0)
+    N = g["o"].shape[0]
+    C = 4
+    B = N // C
+    V = torch.eye(4).repeat(3, 1, 1)
+    V[:, :3, 3] = torch.randn(3, 3, generator=gen) * 0.02
+    # camera-space base rays chosen so that the identity-ish poses reproduce the golden's world rays approximately
+    bo = torch.from_numpy(g["o"][:C * B]).clone()
+    bd = torch.from_numpy(g["d"][:C * B]).clone()
+    pipe = BAPipeline(nef, V, tracer, anchor_frame_idxs=[1], near=0.0, far=2.0).to(DEV)
+    cam_ids = torch.tensor([0, 1, 2, 0])
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    rb = pipe(channels=chans, rays=Rays(origins=bo.to(DEV), dirs=bd.to(DEV)), cam_ids=cam_ids, lod_idx=None, stage='train')
+    loss = sum((getattr(rb, c) * torch.from_numpy(g["gw_" + c][:C * B]).to(DEV)).sum() for c in chans)
+    loss.backward()
+    gp = pipe.camera_extrinsics.grad
+    assert gp is not None and torch.isfinite(gp).all() and float(gp.abs().max()) > 0
+    assert float(gp[1].abs().max()) == 0.0, "anchor frame"
+    # chain rule check: the same trace on detached world rays gives d/d(o, d); the oracle maps them to the parameters
+    rays_w = pipe.transform_rays(Rays(origins=bo.to(DEV), dirs=bd.to(DEV)), cam_ids)
+    o = rays_w.origins.detach().requires_grad_(True)
+    d = rays_w.dirs.detach().requires_grad_(True)
+    nef.zero_grad(set_to_none=True)
+    rb2 = tracer(nef, channels=chans, rays=Rays(origins=o, dirs=d, dist_min=0.0, dist_max=2.0), lod_idx=None, stage='train')
+    sum((getattr(rb2, c) * torch.from_numpy(g["gw_" + c][:C * B]).to(DEV)).sum() for c in chans).backward()
+    p_ref = pipe.camera_extrinsics.detach().cpu().double().requires_grad_(True)
+    o_ref, d_ref = opose.transform_rays(p_ref, cam_ids, bo.double(), bd.double())
+    ((o_ref * o.grad.cpu().double()).sum() + (d_ref * d.grad.cpu().double()).sum()).backward()
+    ref = p_ref.grad.float()
+    ref[1] = 0.0
+    assert_close(gp, ref, rtol=1e-3, atol_scale=1e-4, msg="pose gradient through the trace")

@@ -219,3 +219,25 @@ def test_lattice_hash_linear_form_is_the_loop_form():
                 if rank[i] > 3 - r:
                     lin = (lin - 4 * P) & 0xFFFFFFFF
             assert k == lin
+
+
+def test_pose_oracle_properties():
+    """oracle/pose.py (the checker of csrc/pose.cu): Gram-Schmidt rows are a proper rotation, view matrices round-trip through
+    the 9-parameter layout, and inv_transform_rays inverts the view transform; autograd matches finite differences."""
+    import torch
+    from oracle import pose
+    gen = torch.Generator().manual_seed(0)
+    p = torch.randn(5, 9, generator=gen, dtype=torch.float64)
+    R = pose.rot6d_to_matrix(p[:, :6])
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3, dtype=torch.float64).expand(5, 3, 3), atol=1e-12)
+    assert torch.allclose(torch.linalg.det(R), torch.ones(5, dtype=torch.float64), atol=1e-12)
+    V = torch.eye(4, dtype=torch.float64).repeat(5, 1, 1)
+    V[:, :3, :3], V[:, :3, 3] = R, p[:, 6:]
+    assert torch.allclose(pose.params_from_view_matrix(V)[:, :6], torch.cat([R[:, 0], R[:, 1]], 1))
+    xw = torch.randn(5 * 3, 3, generator=gen, dtype=torch.float64)                       # world points
+    xc = (torch.einsum('cij,cbj->cbi', R, xw.reshape(5, 3, 3)) + p[:, None, 6:]).reshape(-1, 3)   # view transform
+    back, _ = pose.transform_rays(pose.params_from_view_matrix(V), torch.arange(5), xc, xc)
+    assert torch.allclose(back, xw, atol=1e-10)
+    q = p.clone().requires_grad_(True)
+    bo, bd = torch.randn(10, 3, generator=gen, dtype=torch.float64), torch.randn(10, 3, generator=gen, dtype=torch.float64)
+    assert torch.autograd.gradcheck(lambda z: pose.transform_rays(z, torch.tensor([1, 4]), bo, bd), (q,), atol=1e-6)
