@@ -103,6 +103,36 @@ def make_rays(n_rays, step, seed=0, res=1024, confined=False):
     return np.concatenate(os_).astype(np.float32), np.concatenate(ds_).astype(np.float32)
 
 
+def make_cameras(seed=0, n_cam=42):
+    """The synthetic robot pass as view matrices [n_cam, 4, 4] (world -> camera): 42 poses on the line x in [-0.8, 0.8] at z = +0.9
+    looking down -z with 2 degrees of seeded jitter (agrobot_base.py:110-113: 42 train frames)."""
+    rng = np.random.default_rng(seed * 100003 + 4242)
+    V = np.tile(np.eye(4), (n_cam, 1, 1))
+    for i in range(n_cam):
+        cam = np.array([-0.8 + 1.6 * i / (n_cam - 1), rng.uniform(-0.05, 0.05), 0.9])
+        ang = np.deg2rad(rng.normal(0, 2.0, 2))
+        cx, sx, cy, sy = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1])
+        Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rcw = Ry @ Rx                      # camera -> world
+        V[i, :3, :3] = Rcw.T
+        V[i, :3, 3] = -Rcw.T @ cam
+    return V.astype(np.float32)
+
+
+def make_base_rays(n_rays, step, seed=0, res=1024, n_cam=42):
+    """Camera-space base rays (origin 0, unit pixel directions) of n_rays/4096 images + the camera index of each image: what
+    BAPipeline.transform_rays consumes (data['base_rays'], pc_nerf/trainer.py:421)."""
+    rng = np.random.default_rng(seed * 100003 + step + 99)
+    n_img = max(1, n_rays // RAYS_PER_IMG)
+    per = n_rays // n_img
+    pix = rng.integers(0, res, size=(n_img * per, 2)).astype(np.float64) + 0.5
+    d = np.stack([(pix[:, 0] - res / 2) / (0.9 * res), (pix[:, 1] - res / 2) / (0.9 * res), -np.ones(n_img * per)], 1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    cams = rng.integers(0, n_cam, size=n_img).astype(np.int64)
+    return np.zeros((n_img * per, 3), np.float32), d.astype(np.float32), cams
+
+
 def make_targets(n_rays, step, seed=0):
     rng = np.random.default_rng(seed * 7919 + step + 1)
     return (rng.uniform(0, 1, (n_rays, 3)).astype(np.float32), rng.integers(0, C_SEM, n_rays).astype(np.int64),
@@ -176,12 +206,32 @@ class Workload:
             raymarch_type=march, num_steps=(cfg['S'] if march == 'ray' else 2), bg_color='white', ray_max_travel=2.0)
         self.params = [p for p in self.nef.parameters()]
         self.channels = ['rgb', 'depth', 'semantics', 'inst_embedding']
+        self.pipe = self.optimizer = None
+        if cfg.get('pose'):
+            # bundle adjustment (pc_nerf/ba_pipeline.py): 42 trainable camera poses, frame 0 anchored
+            from pagnerf_b200.pc_nerf import BAPipeline
+            self.pipe = BAPipeline(self.nef, torch.from_numpy(make_cameras(0)), self.tracer, anchor_frame_idxs=[0], near=NEAR, far=self.far).to(device)
+            self.params.append(self.pipe.camera_extrinsics)
+        if cfg.get('adam'):
+            # the reference's parameter groups (pc_nerf/trainer.py:229-300; best.yaml: lr 1e-3, grid / delta-grid lr x 100,
+            # extrinsics lr 1e-4, wisp's Adam eps 1e-15)
+            from pagnerf_b200.optim import FusedAdam
+            named = dict(self.nef.named_parameters())
+            groups = [dict(params=[p for n, p in named.items() if 'decoder' in n], lr=1e-3, name='decoder'),
+                      dict(params=[p for n, p in named.items() if 'decoder' not in n and 'delta_grid' in n], lr=1e-1, name='delta_grid'),
+                      dict(params=[p for n, p in named.items() if 'decoder' not in n and 'delta_grid' not in n], lr=1e-1, name='grid')]
+            if self.pipe is not None:
+                groups.append(dict(params=[self.pipe.camera_extrinsics], lr=1e-4, name='extrinsics'))
+            self.optimizer = FusedAdam(groups, eps=1e-15)
         # pool of host (pinned) batches; step i uses batch i % n_batches
         self.host = []
         for b in range(n_batches):
-            o, d = make_rays(n_rays, b, seed, confined=(cfg['scene'] == 'dense'))
+            if self.pipe is not None:
+                o, d, cams = make_base_rays(n_rays, b, seed)
+            else:
+                o, d = make_rays(n_rays, b, seed, confined=(cfg['scene'] == 'dense'))
             tr, ts, ti = make_targets(n_rays, b, seed)
-            hb = [torch.from_numpy(x) for x in (o, d, tr, ts, ti)]
+            hb = [torch.from_numpy(x) for x in ((o, d, tr, ts, ti) + ((cams,) if self.pipe is not None else ()))]
             if device.type == 'cuda':
                 hb = [x.pin_memory() for x in hb]
             self.host.append(hb)
@@ -192,17 +242,30 @@ class Workload:
     def h2d_bytes(self):
         return sum(x.numel() * x.element_size() for x in self.host[0])
 
-    def render(self, o, d):
+    def render(self, o, d, cams=None):
         from pagnerf_b200.wisp_compat import Rays
         rays = Rays(origins=o, dirs=d, dist_min=NEAR, dist_max=self.far)
+        if self.pipe is not None:      # camera-space base rays -> world rays through the trainable poses, then the trace
+            return self.pipe(channels=self.channels, rays=rays, cam_ids=cams, lod_idx=None, stage='train')
         return self.tracer(self.nef, channels=self.channels, rays=rays, lod_idx=None, stage='train')
 
-    def loss_of(self, o, d, tr, ts, ti):
+    def after_backward(self):
+        """What follows loss.backward() in the reference's step: (multi-GPU) the all-reduce of the gradients produced outside the
+        fused trace -- the pose table --, then optimizer.step() (pc_nerf/trainer.py:582-590)."""
+        import torch.distributed as dist
+        if self.pipe is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            g = self.pipe.camera_extrinsics.grad
+            if g is not None:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)
+        if self.optimizer is not None:
+            self.optimizer.step()
+
+    def loss_of(self, o, d, tr, ts, ti, cams=None):
         """forward + loss of one step (what a trainer's step() does between zero_grad and backward)."""
         # the reference's training step runs under autocast (pc_nerf/trainer.py:429): fp16-rounded coords,
         # fp16-operand / fp32-accumulate decoders; the loss scaling of its GradScaler happens inside our kernels
         with torch.autocast('cuda', dtype=torch.float16, enabled=self.amp):
-            rb = self.render(o, d)
+            rb = self.render(o, d, cams)
             loss = loss_fn(rb.rgb.float(), rb.semantics.float(), rb.inst_embedding.float(), tr, ts, ti)
         # NB: keeping `rb` alive keeps its autograd graph -- and the parameters' AccumulateGrad nodes, which remember the
         # stream they were created on -- alive; CUDA-graph capture needs them re-created on the capture stream.
@@ -224,6 +287,7 @@ class Workload:
             p.grad = None
         loss = self.loss_of(*b)
         loss.backward()
+        self.after_backward()
         return {"rb": self.last_rb, "loss": loss, "ridx": getattr(self.tracer, "_last_ridx", torch.zeros(1, device=self.device))}
 
 
@@ -503,8 +567,6 @@ def main():
         trace("process group up")
     if infer:
         return bench_inference(args, cfg, config, metric, unit, rank, world, device, dist)
-    if cfg.get('pose'):
-        return bench_pose_adam(args, cfg, config, metric, unit, rank, world, device, dist)
     wl = Workload(device, rays, seed=rank, dd=args.dd, config=args.config, march=args.march)
     trace("workload built")
     if world > 1:
@@ -533,7 +595,7 @@ def main():
         # a failing capture fails the bench: an eager number must never be reported under the graph-replay label
         from pagnerf_b200.graph import GraphedStep
         wl.keep_rb, wl.last_rb = False, None
-        graphed = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef)
+        graphed = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef, post_backward=wl.after_backward)
         graph_note = "whole step (fwd + loss + bwd%s) replayed as one CUDA graph" % (" + NCCL gradient all-reduce" if world > 1 else "")
         trace("graph captured")
 
@@ -577,7 +639,7 @@ def main():
     if world > 1 and graphed is not None:
         from pagnerf_b200 import ops as _o
         _o.set_grad_sync(False)
-        g2 = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef)
+        g2 = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef, post_backward=wl.after_backward)
         for _ in range(3):
             g2(*wl.batch(False))
         sync()
@@ -820,10 +882,6 @@ def bench_inference(args, cfg, config, metric, unit, rank, world, device, dist):
     print(json.dumps(result))
     _leave(world, dist)
     return 0
-
-
-def bench_pose_adam(args, cfg, config, metric, unit, rank, world, device, dist):
-    raise NotImplementedError("config 4 (pose optimisation + Adam) is wired up in pagnerf_b200/ba_pipeline.py")
 
 
 def encoder_report(wl, per_kernel, ALGO, n_all, n_live, hbm, l2_gbs, device):

@@ -272,7 +272,8 @@ int pag_composite_bwd(const float* sigma, const float* deltas, const float* dept
                       float* g_rgb_s, float* g_sem_s, float* g_inst_s, void* stream);
 /* debugging aid: cudaStreamCaptureStatus of `stream` (0 none, 1 active, 2 invalidated), negative on error. */
 int pag_capture_status(void* stream);
-/* power-of-two loss scale for the fp16 tensor-core backward (the GradScaler of pc_nerf/trainer.py:582, on the device). */
+/* power-of-two loss scale for the fp16 tensor-core backward (the GradScaler of pc_nerf/trainer.py:582, on the device).
+ * scratch: two uint32, zero on entry, left zero by the kernel (one launch: the last block finalises and resets). */
 int pag_grad_scale(const float* a, int64_t na, int wa, const float* b, int64_t nb, int wb, const int64_t* m_dev,
                    float target, uint32_t* scratch, float* out_scale, void* stream);
 /* kaolin.render.spc.sum_reduce / exponential_integration (weights only), packs given by offsets[R+1]. */
@@ -296,6 +297,14 @@ int pag_pose_transform_fwd(const float* params, const int64_t* cam_idx, const fl
                            float* out_o, float* out_d, void* stream);
 int pag_pose_transform_bwd(const float* params, const int64_t* cam_idx, const float* base_o, const float* base_d, const float* g_o,
                            const float* g_d, int64_t C, int64_t B, float* g_params, void* stream);
+
+/* ---- fused multi-tensor Adam (BASELINE config 4: "+ Adam"; SURVEY 8e "a single fused unscale + Adam kernel") ----
+ * Replaces torch.optim.Adam.step() as the reference's trainer runs it (pc_nerf/trainer.py:229-300 parameter groups, :590 step;
+ * configs/bup20/best.yaml:114 optimizer_type adam): n_tensors <= 48 fp32 tensors in one launch, host arrays of device pointers,
+ * step count and optional inverse loss scale in device memory (graph capturable).  amsgrad off, L2 weight decay. */
+int pag_adam_step(float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* numel, const float* lr,
+                  const float* weight_decay, int n_tensors, float beta1, float beta2, float eps, int* step, const float* inv_scale,
+                  void* stream);
 
 /* ---- achievable-gather-bandwidth probe (bench.py: denominator of the encoder's roofline fraction) ----
  * threads x loads_per_thread (multiple of 16, 16 in flight per thread) uniformly random 8-byte loads from table[entries] float2; sink f32[threads]. */

@@ -262,43 +262,78 @@ __global__ void expint_bwd_kernel(const float* __restrict__ gw, const float* __r
 }
 
 // ---- loss-scale for the fp16 tensor-core backward: scale = 2^floor(log2(target / max|g|)) (one launch + finalize) ----
-__global__ void absmax_kernel(const float* __restrict__ a, int64_t na, const float* __restrict__ b, int64_t nb,
-                              const int64_t* __restrict__ m_dev, int wa, int wb, unsigned* __restrict__ scratch) {
+// One launch: vectorised abs-max over a (and b), atomicMax into scratch[0]; the LAST block to finish (ticket in scratch[1]) turns
+// the maximum into the power-of-two scale and resets both words, so the scratch stays zero between calls (no memset launch).
+__global__ void __launch_bounds__(256) absmax_scale_kernel(const float* __restrict__ a, int64_t na, const float* __restrict__ b, int64_t nb,
+                                                           const int64_t* __restrict__ m_dev, int wa, int wb, float target,
+                                                           unsigned* __restrict__ scratch, float* __restrict__ out) {
     if (m_dev) { const int64_t mv = __ldg(m_dev); na = min(na, mv * wa); nb = min(nb, mv * wb); }
     float mx = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = (i < na) ? a[i] : b[i - na];
-        mx = fmaxf(mx, fabsf(v));     // NaN is dropped by fmaxf
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const float* p = t ? b : a;
+        const int64_t n = t ? nb : na;
+        if (!p || n <= 0) continue;
+        if (!(reinterpret_cast<uintptr_t>(p) & 15)) {
+            const int64_t n4 = n >> 2;
+            const float4* p4 = reinterpret_cast<const float4*>(p);
+            int64_t i = tid;
+            for (; i + 3 * nth < n4; i += 4 * nth) {      // four independent 16-byte loads in flight
+                const float4 v0 = __ldg(p4 + i), v1 = __ldg(p4 + i + nth), v2 = __ldg(p4 + i + 2 * nth), v3 = __ldg(p4 + i + 3 * nth);
+                mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))),
+                                     fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w)))));
+                mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w))),
+                                     fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w)))));
+            }
+            for (; i < n4; i += nth) {
+                const float4 v = __ldg(p4 + i);
+                mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));     // NaN is dropped by fmaxf
+            }
+            for (int64_t j = (n4 << 2) + tid; j < n; j += nth) mx = fmaxf(mx, fabsf(p[j]));
+        } else {
+            for (int64_t j = tid; j < n; j += nth) mx = fmaxf(mx, fabsf(p[j]));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(scratch, __float_as_uint(mx));
-}
-__global__ void scale_finalize_kernel(const unsigned* __restrict__ scratch, float target, float* __restrict__ out) {
-    const float amax = fmaxf(__uint_as_float(*scratch), 1e-30f);
-    float s = exp2f(floorf(log2f(target / amax)));
-    s = fminf(fmaxf(s, 5.9604645e-08f), 1.1529215e18f);   // [2^-24, 2^60]
-    *out = s;
+    __shared__ float wmax[8];
+    __shared__ bool last;
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = wmax[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, wmax[w]);
+        if (m > 0.f) atomicMax(scratch, __float_as_uint(m));
+        __threadfence();
+        last = atomicAdd(scratch + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const float amax = fmaxf(__uint_as_float(atomicExch(scratch, 0u)), 1e-30f);
+        float s = exp2f(floorf(log2f(target / amax)));
+        s = fminf(fmaxf(s, 5.9604645e-08f), 1.1529215e18f);   // [2^-24, 2^60]
+        *out = s;
+        scratch[1] = 0u;
+    }
 }
 
 extern "C" {
 
-// out_scale[0] = power-of-two loss scale for the gradients a[na] (and b[nb], nullable); scratch: one uint32 on the device.
+// out_scale[0] = power-of-two loss scale 2^floor(log2(target / max|.|)) for the gradients a[na] (and b[nb], nullable).
+// scratch: TWO uint32 on the device, zero on entry; the kernel leaves them zero again (one launch, no memset).
 // With m_dev the element counts are min(na, m_dev[0]*wa) / min(nb, m_dev[0]*wb) (packed-sample tensors of width wa / wb).
 int pag_grad_scale(const float* a, int64_t na, int wa, const float* b, int64_t nb, int wb, const int64_t* m_dev,
                    float target, uint32_t* scratch, float* out_scale, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return (int)e;
     if (!b) nb = 0;
     const int64_t n = na + nb;
-    if (n > 0) {
-        int grid = (int)((n + 1023) / 1024);
-        if (grid > 1184) grid = 1184;
-        absmax_kernel<<<grid, 256, 0, st>>>(a, na, b, nb, m_dev, wa, wb, scratch);
-        PAG_LAUNCH_CHECK();
-    }
-    scale_finalize_kernel<<<1, 1, 0, st>>>(scratch, target, out_scale);
+    int grid = (int)((n / 4 + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    absmax_scale_kernel<<<grid, 256, 0, st>>>(a, na, b, nb, m_dev, wa, wb, target, scratch, out_scale);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

@@ -22,9 +22,11 @@ class GraphedStep:
     replaces.  `__call__` compares those addresses with the live ones and re-captures when any changed.
     """
 
-    def __init__(self, step_fn, example_inputs, params, nef, warmup=3):
+    def __init__(self, step_fn, example_inputs, params, nef, warmup=3, post_backward=None):
+        """post_backward(): work captured right after loss.backward() -- gradient all-reduces of parameters outside the fused trace,
+        the optimizer step (pagnerf_b200.optim.FusedAdam is capturable: step count and moments live on the device)."""
         self.params = list(params)
-        self.step_fn, self.nef, self.warmup = step_fn, nef, warmup
+        self.step_fn, self.nef, self.warmup, self.post_backward = step_fn, nef, warmup, post_backward
         self.static_inputs = [x.clone() for x in example_inputs]
         self._capture()
 
@@ -61,6 +63,8 @@ class GraphedStep:
                     p.grad = None
                 loss = step_fn(*self.static_inputs)
                 loss.backward()
+                if self.post_backward is not None:
+                    self.post_backward()
                 del loss     # drop the autograd graph: the parameters' AccumulateGrad nodes must be re-created on the capture stream
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
@@ -70,6 +74,8 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.loss = step_fn(*self.static_inputs)
             self.loss.backward()
+            if self.post_backward is not None:
+                self.post_backward()
 
     def __call__(self, *inputs):
         if self._signature() != self.sig:      # prune() on a coarse octree / a re-allocated weight vector: stale addresses

@@ -302,10 +302,17 @@ def grad_scale(*grads):
     return grad_scale_dyn(gs[0], gs[1] if len(gs) > 1 else None, None)
 
 
+_SCALE_SCRATCH = {}
+
+
 def grad_scale_dyn(a, b, m_dev, wa=1, wb=1):
     """One-launch device-side loss scale; with m_dev only the first m_dev[0]*w elements of a / b are scanned."""
     dev = a.device
-    scratch = torch.empty(1, dtype=torch.int32, device=dev)
+    # two zeroed words per (device, stream): the kernel's last block resets them, so they are zeroed exactly once
+    key = (str(dev), torch.cuda.current_stream().cuda_stream)
+    scratch = _SCALE_SCRATCH.get(key)
+    if scratch is None:
+        scratch = _SCALE_SCRATCH[key] = torch.zeros(2, dtype=torch.int32, device=dev)
     out = torch.empty(1, dtype=torch.float32, device=dev)
     call("pag_grad_scale", ptr(a), a.numel(), int(wa), ptr(b), b.numel() if b is not None else 0, int(wb), ptr(m_dev),
          GRAD_TARGET, ptr(scratch), ptr(out))

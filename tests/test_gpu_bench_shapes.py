@@ -8,7 +8,7 @@ Three computations of the same step on the same rays and the same jitter stream:
   C  oracle, amp     the same oracle with oracle/autocast.py: the reference's own autocast numerics (fp16 nn.Linear with
                      fp32 accumulation, fp16 ReLU / sigmoid, fp32 softmax, loss scale 2^16) restated on the CPU
 Tolerances: outputs A vs B at north_star's fp16 tolerance 2e-3; every gradient A vs B in relative l2 at
-max(2e-3, 2 x the error C makes against B) -- i.e. the tensor-core path may be no worse than twice the reference's own
+max(2e-3, 1.5 x the error C makes against B) -- i.e. the tensor-core path may be no worse than 1.5 x the reference's own
 autocast step, measured here rather than assumed; plus an elementwise check with a floor of the same size.
 """
 import numpy as np
@@ -122,7 +122,7 @@ def test_bench_field_fused_trace_vs_oracle(cuda_lib, dd):
         e_ours, e_amp = _rel_l2(a, r), _rel_l2(amp[c], r)
         report.append(f"out {c}: ours {e_ours:.2e} reference-autocast {e_amp:.2e}")
         assert not bad.any(), f"{c}: {int(bad.sum())}/{bad.numel()} beyond 2e-3 (max err {float((a - r).abs().max()):.3e}, ref max {float(r.abs().max()):.3e})"
-        assert e_ours <= max(2e-3, 2.0 * e_amp), f"{c}: rel l2 {e_ours:.3e} vs reference autocast {e_amp:.3e}"
+        assert e_ours <= max(2e-3, 1.5 * e_amp), f"{c}: rel l2 {e_ours:.3e} vs reference autocast {e_amp:.3e}"
     # ---- every gradient: tolerance set from the reference's own autocast error ---------------------------------------
     checked = 0
     for k, g in ours_g.items():
@@ -132,7 +132,7 @@ def test_bench_field_fused_trace_vs_oracle(cuda_lib, dd):
         r, am = ref_g[ko].float(), amp_g[ko].float()
         e_ours, e_amp = _rel_l2(g, r), _rel_l2(am, r)
         report.append(f"grad {k}: ours {e_ours:.2e} reference-autocast {e_amp:.2e}")
-        lim = max(2e-3, 2.0 * e_amp)
+        lim = max(2e-3, 1.5 * e_amp)
         assert torch.isfinite(g).all(), k
         assert e_ours <= lim, f"grad {k}: rel l2 {e_ours:.3e} > {lim:.3e} (reference autocast {e_amp:.3e})"
         # elementwise, with a floor of the same relative size on the tensor's scale
@@ -144,7 +144,7 @@ def test_bench_field_fused_trace_vs_oracle(cuda_lib, dd):
     for name, g, r, am in (("origins", o.grad.cpu(), ref_go, amp_go), ("dirs", d.grad.cpu(), ref_gd, amp_gd)):
         e_ours, e_amp = _rel_l2(g, r), _rel_l2(am, r)
         report.append(f"grad {name}: ours {e_ours:.2e} reference-autocast {e_amp:.2e}")
-        assert e_ours <= max(2e-3, 2.0 * e_amp), f"grad {name}: rel l2 {e_ours:.3e} vs reference autocast {e_amp:.3e}"
+        assert e_ours <= max(2e-3, 1.5 * e_amp), f"grad {name}: rel l2 {e_ours:.3e} vs reference autocast {e_amp:.3e}"
     print("\n".join(report))
 
 
