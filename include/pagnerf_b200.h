@@ -94,6 +94,12 @@ int pag_voxel_filter_count(const float* nug_depth, const int64_t* nug_offsets, i
 int pag_voxel_emit_dyn(const float* origins, const float* dirs, const int64_t* nug_ridx, const float* nug_depth, const int32_t* rel,
                        const int64_t* nug_offsets, const int64_t* offsets, int64_t N, int64_t K_max, int S, uint32_t seed,
                        const uint32_t* seed_dev, int64_t* ridx, float* samples, float* depths, float* deltas, void* stream);
+/* Octree rebuild on the device (prune(): pc_nerf/panoptic_delta_nef.py:63-104, pc_nerf/panoptic_nef.py:207-237 -> kaolin
+ * unbatched_points_to_octree + wisp OctreeAS.init): from the dense leaf-occupancy mask u8[8^level] in Morton
+ * order to the SPC layout the marcher consumes.  Workspaces and outputs hold F = (8^(level+1)-1)/7 entries (see csrc/octree.cu);
+ * pyramid i32[2, level+2] stays on the device: n_nodes = pyramid[1][level], n_points = pyramid[1][level+1]. */
+int pag_octree_from_mask(const uint8_t* mask, int level, int32_t* exists, uint8_t* bytes, int64_t* pos, int32_t* popc, int64_t* prefix64,
+                         uint8_t* octree, int16_t* points, int32_t* prefix, int32_t* pyramid, void* stream);
 int pag_mark_pack_boundaries(const int64_t* ids, int64_t M, uint8_t* boundary, void* stream);
 
 /* ---- permutohedral encoding: grids/permuto_grid.py:57-62,71 -> PermutoEncoding fwd / bwd ------------- */
@@ -270,6 +276,11 @@ int pag_composite_bwd(const float* sigma, const float* deltas, const float* dept
                       const float* alpha, const float* rgbsum, const float* g_alpha, const float* g_rgb,
                       const float* g_depth, const float* g_sem, int Cs, const float* g_inst, int Ci, float* g_sigma,
                       float* g_rgb_s, float* g_sem_s, float* g_inst_s, void* stream);
+/* Gradient tables on the wire as halfs for the multi-GPU all-reduce (the reference reduces its grid gradients through
+ * DistributedDataParallel-style fp32 all-reduce -- here the two 50 MB tables can travel as fp16 under a shared power-of-two scale):
+ * out16[n] = half(x[n] * scale[0]);  x[n] = float(in16[n]) * mult / scale[0].  n % 4 == 0, 16-byte aligned. */
+int pag_pack_f16(const float* x, int64_t n, const float* scale, void* out16, void* stream);
+int pag_unpack_f16(const void* in16, int64_t n, const float* scale, float mult, float* x, void* stream);
 /* debugging aid: cudaStreamCaptureStatus of `stream` (0 none, 1 active, 2 invalidated), negative on error. */
 int pag_capture_status(void* stream);
 /* power-of-two loss scale for the fp16 tensor-core backward (the GradScaler of pc_nerf/trainer.py:582, on the device).

@@ -15,6 +15,7 @@
 // lanes = channels so the [M,C] rows are read exactly once, fully coalesced (800 B/sample).
 // Everything is HBM-stream bound: algorithmic bytes per sample fwd = 4+4+4+12+4C_sem+4C_inst (+1).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 __device__ __forceinline__ float warp_excl_scan(float v, float& total) {
     const int lane = threadIdx.x & 31;
@@ -320,7 +321,47 @@ __global__ void __launch_bounds__(256) absmax_scale_kernel(const float* __restri
     }
 }
 
+// fp16 transport of a gradient table through the all-reduce: out16 = half(x * scale), x = float(in16) * mult / scale
+__global__ void __launch_bounds__(256) pack_f16_kernel(const float4* __restrict__ x, int64_t n4, const float* __restrict__ scale, uint2* __restrict__ out) {
+    const float s = __ldg(scale);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        const __half2 a = __floats2half2_rn(v.x * s, v.y * s), b = __floats2half2_rn(v.z * s, v.w * s);
+        out[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+}
+__global__ void __launch_bounds__(256) unpack_f16_kernel(const uint2* __restrict__ in, int64_t n4, const float* __restrict__ scale, float mult,
+                                                         float4* __restrict__ x) {
+    const float s = mult / __ldg(scale);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 u = __ldg(in + i);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        x[i] = make_float4(a.x * s, a.y * s, b.x * s, b.y * s);
+    }
+}
+
 extern "C" {
+
+// Gradient tables on the wire as halfs (multi-GPU all-reduce): out16[n] = half(x[n] * scale[0]) and back,
+// x[n] = float(in16[n]) * mult / scale[0]; n a multiple of 4, 16-byte aligned buffers; scale on the device (pag_grad_scale).
+int pag_pack_f16(const float* x, int64_t n, const float* scale, void* out16, void* stream) {
+    if (n < 0 || (n & 3)) return PAG_ERR_ARG;
+    if (n == 0) return PAG_OK;
+    int grid = (int)((n / 4 + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    pack_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), n / 4, scale, reinterpret_cast<uint2*>(out16));
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_unpack_f16(const void* in16, int64_t n, const float* scale, float mult, float* x, void* stream) {
+    if (n < 0 || (n & 3)) return PAG_ERR_ARG;
+    if (n == 0) return PAG_OK;
+    int grid = (int)((n / 4 + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    unpack_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(in16), n / 4, scale, mult, reinterpret_cast<float4*>(x));
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
 
 // out_scale[0] = power-of-two loss scale 2^floor(log2(target / max|.|)) for the gradients a[na] (and b[nb], nullable).
 // scratch: TWO uint32 on the device, zero on entry; the kernel leaves them zero again (one launch, no memset).

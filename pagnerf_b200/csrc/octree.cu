@@ -540,6 +540,65 @@ __global__ void voxel_emit_kernel(const float* __restrict__ org, const float* __
     samples[3 * dst + 2] = __fadd_rn(org[3 * ray + 2], __fmul_rn(dir[3 * ray + 2], ds));
 }
 
+// ---------------------------------------------------------------------------------------------
+// octree rebuild from a dense leaf-occupancy mask (prune(): pc_nerf/panoptic_delta_nef.py:63-104 -> kaolin
+// unbatched_points_to_octree + wisp OctreeAS.init).  All nodes of all levels live in ONE flat index space
+// f = base_l + morton (base_l = (8^l - 1) / 7): a bottom-up OR pass per level gives every node its child byte and existence flag,
+// ONE exclusive scan over the flags gives every existing node its point index (points are listed level by level in Morton order,
+// and the byte of a non-leaf node sits at the same index in `octree`), a second scan over the popcounts gives `prefix`.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t level_base(int l) { return ((1ll << (3 * l)) - 1) / 7; }
+
+__global__ void octree_build_leaf_kernel(const uint8_t* __restrict__ mask, int L, int* __restrict__ exists) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ll << (3 * L))) return;
+    exists[level_base(L) + i] = mask[i] ? 1 : 0;
+}
+__global__ void octree_build_level_kernel(int l, int* __restrict__ exists, uint8_t* __restrict__ bytes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1ll << (3 * l))) return;
+    const int* ch = exists + level_base(l + 1) + 8 * i;
+    uint32_t b = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b |= ch[j] ? (1u << j) : 0u;
+    bytes[level_base(l) + i] = (uint8_t)b;
+    exists[level_base(l) + i] = b ? 1 : 0;
+}
+__global__ void octree_build_emit_kernel(int L, const int* __restrict__ exists, const uint8_t* __restrict__ bytes,
+                                         const int64_t* __restrict__ pos, uint8_t* __restrict__ octree, int16_t* __restrict__ points,
+                                         int* __restrict__ popc) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= level_base(L + 1) || !exists[f]) return;
+    int l = 0;
+    while (l < L && f >= level_base(l + 1)) ++l;
+    const int64_t code = f - level_base(l), p = pos[f];
+    int x = 0, y = 0, z = 0;
+    for (int b = 0; b < l; ++b) {
+        x |= (int)((code >> (3 * b + 2)) & 1) << b;
+        y |= (int)((code >> (3 * b + 1)) & 1) << b;
+        z |= (int)((code >> (3 * b)) & 1) << b;
+    }
+    points[3 * p] = (int16_t)x; points[3 * p + 1] = (int16_t)y; points[3 * p + 2] = (int16_t)z;
+    if (l < L) { octree[p] = bytes[f]; popc[p] = __popc((uint32_t)bytes[f]); }
+}
+__global__ void octree_build_finish_kernel(int L, const int64_t* __restrict__ pos, const int64_t* __restrict__ prefix64, int* __restrict__ prefix,
+                                           int* __restrict__ pyramid) {
+    const int64_t n_nodes = pos[level_base(L)];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_nodes) prefix[i] = (int)prefix64[i];
+    if (i == 0) {
+        int acc = 0;
+        for (int l = 0; l <= L; ++l) {
+            const int cnt = (int)(pos[level_base(l + 1)] - pos[level_base(l)]);
+            pyramid[l] = cnt;
+            pyramid[(L + 2) + l] = acc;
+            acc += cnt;
+        }
+        pyramid[L + 1] = 0;
+        pyramid[(L + 2) + L + 1] = acc;
+    }
+}
+
 __global__ void mark_pack_boundaries_kernel(const int64_t* __restrict__ ids, int64_t M, uint8_t* __restrict__ b) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
@@ -721,6 +780,34 @@ int pag_voxel_emit_dyn(const float* origins, const float* dirs, const int64_t* n
     if (N == 0 || K_max == 0) return PAG_OK;
     voxel_emit_kernel<<<pag_grid(K_max * S, 256), 256, 0, (cudaStream_t)stream>>>(origins, dirs, nug_ridx, nug_depth, rel, nug_offsets, offsets,
                                                                                  N, K_max, S, seed, seed_dev, ridx, samples, depths, deltas);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// Octree (kaolin SPC layout: octree bytes, points, prefix, pyramid) from the dense leaf-occupancy mask u8[8^level] in Morton order
+// (= the order of grid.dense_points).  Workspaces / outputs sized for F = (8^(level+1) - 1) / 7 nodes: exists i32[F], bytes u8[F],
+// pos i64[F+1], popc i32[F], prefix64 i64[F+1]; outputs octree u8[F], points i16[F,3], prefix i32[F+1], pyramid i32[2, level+2]
+// (device).  Valid lengths: n_nodes = pyramid[1][level], n_points = pyramid[1][level+1].  An empty mask yields n_points = 0.
+int pag_octree_from_mask(const uint8_t* mask, int level, int32_t* exists, uint8_t* bytes, int64_t* pos, int32_t* popc, int64_t* prefix64,
+                         uint8_t* octree, int16_t* points, int32_t* prefix, int32_t* pyramid, void* stream) {
+    if (level < 1 || level > PAG_MAX_LEVEL) return PAG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t F = ((1ll << (3 * (level + 1))) - 1) / 7, leaves = 1ll << (3 * level), inner = ((1ll << (3 * level)) - 1) / 7;
+    octree_build_leaf_kernel<<<pag_grid(leaves, 256), 256, 0, st>>>(mask, level, exists);
+    PAG_LAUNCH_CHECK();
+    for (int l = level - 1; l >= 0; --l) {
+        octree_build_level_kernel<<<pag_grid(1ll << (3 * l), 256), 256, 0, st>>>(l, exists, bytes);
+        PAG_LAUNCH_CHECK();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(exists, F, pos);
+    PAG_LAUNCH_CHECK();
+    cudaError_t e = cudaMemsetAsync(popc, 0, sizeof(int32_t) * inner, st);
+    if (e != cudaSuccess) return (int)e;
+    octree_build_emit_kernel<<<pag_grid(F, 256), 256, 0, st>>>(level, exists, bytes, pos, octree, points, popc);
+    PAG_LAUNCH_CHECK();
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(popc, inner, prefix64);      // entries beyond n_nodes are zero: harmless
+    PAG_LAUNCH_CHECK();
+    octree_build_finish_kernel<<<pag_grid(inner + 1, 256), 256, 0, st>>>(level, pos, prefix64, prefix, pyramid);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

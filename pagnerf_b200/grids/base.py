@@ -33,6 +33,13 @@ class BLASGrid(nn.Module):
         self.blas.init(octree)
         self._register_blas_buffers()
 
+    def blas_init_from_mask(self, mask, register=True):
+        """prune(): rebuild the accel-struct from the dense occupancy mask (Morton order = `dense_points` order) with the
+        device-side builder; `register` re-registers the checkpoint buffers (PermutoGrid) or leaves the state_dict keys alone."""
+        self.blas.init_from_mask(mask, self.blas_level)
+        if register:
+            self._register_blas_buffers()
+
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         # octree size changes with pruning: adopt the checkpoint's accel-struct before the strict shape check
         key = prefix + 'blas_octree'

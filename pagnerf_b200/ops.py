@@ -619,36 +619,91 @@ def exponential_integration(feats, tau, boundary, exclusive=True):
 # ------------------------------------------------------------------------------------------------
 # sync-free fused trace (training mode): march -> encode -> decode -> composite in one autograd node
 # ------------------------------------------------------------------------------------------------
-_GRAD_SYNC = {"group": None, "enabled": False}
+_GRAD_SYNC = {"group": None, "enabled": False, "transport": os.environ.get("PAGNERF_GRAD_TRANSPORT", "fp32"),
+              "colour_first": os.environ.get("PAGNERF_COLOUR_FIRST", "0") == "1"}
 _SIDE_STREAMS = {}
 BRANCH_OVERLAP = True    # run the independent branches of the fused trace on two streams (bench.py disables it for its
                          # per-kernel CUDA-event pass so that kernel durations do not overlap)
 
 
-def _side_stream(device):
-    """One auxiliary stream per device for the branch-level concurrency inside the fused trace."""
+def _side_stream(device, which=0):
+    """Auxiliary streams per device for the branch-level concurrency inside the fused trace (0: panoptic branch, 1: colour-table
+    all-reduce, 2: gradient-table zero fill)."""
     if not BRANCH_OVERLAP:
         return torch.cuda.current_stream()
-    key = str(device)
+    key = (str(device), which)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
 
 
-def set_grad_sync(enabled, group=None, reserved_sms=0):
-    """Ray-sharded data parallelism: when enabled, FusedTraceFn.backward all-reduces (AVG) the gradients it
-    produces itself -- the delta-grid table as soon as its scatter kernel is queued, so that the NCCL transfer over
-    NVLink overlaps the remaining colour-branch backward; the colour table and the flattened decoder gradients at the
-    end -- and returns already-reduced gradients.  One process per GPU, torch.distributed initialised by the caller."""
+def set_grad_sync(enabled, group=None, reserved_sms=0, transport=None, colour_first=None):
+    """Ray-sharded data parallelism: when enabled, FusedTraceFn.backward all-reduces (mean) the gradients it
+    produces itself -- each grid table as soon as its scatter kernel is queued, on its own stream, so that the NCCL transfer over
+    NVLink overlaps the rest of the backward; the flattened decoder gradients (one small bucket) at the end -- and returns
+    already-reduced gradients.  One process per GPU, torch.distributed initialised by the caller.
+      transport    'fp32' (exact mean) or 'fp16': the two 50 MB tables travel as halfs under a power-of-two scale shared by all
+                   ranks (a 4-byte MIN all-reduce of the per-rank scales first); halves the bytes on the wire, 2^-11 relative
+                   rounding per element -- inside north_star's 2e-3 for fp16 features.  Default: PAGNERF_GRAD_TRANSPORT or 'fp32'.
+      colour_first issue the colour chain (and the all-reduce of its table) before the panoptic chain instead of after it."""
     _GRAD_SYNC["enabled"], _GRAD_SYNC["group"] = bool(enabled), group
+    if transport is not None:
+        if transport not in ('fp32', 'fp16'):
+            raise ValueError("transport must be 'fp32' or 'fp16'")
+        _GRAD_SYNC["transport"] = transport
+    if colour_first is not None:
+        _GRAD_SYNC["colour_first"] = bool(colour_first)
     # leave a few SMs to the NCCL kernels: the persistent decoder kernels would otherwise hold every SM until they finish
     # and the "overlapped" all-reduce would start only then
     _lib.load().pag_set_reserved_sms(int(reserved_sms) if enabled else 0, None)
 
 
-def _allreduce_async(t):
+def _dist_world():
     import torch.distributed as dist
-    return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=_GRAD_SYNC["group"], async_op=True)
+    return dist.get_world_size(_GRAD_SYNC["group"])
+
+
+def _allreduce_mean_async(t):
+    """async mean all-reduce; NCCL has a native AVG, other backends (gloo in the tests) sum and divide on wait."""
+    import torch.distributed as dist
+    g = _GRAD_SYNC["group"]
+    if dist.get_backend(g) == 'nccl':
+        wk = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=g, async_op=True)
+        return lambda: wk.wait()
+    wk = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=g, async_op=True)
+
+    def fin():
+        wk.wait()
+        t.mul_(1.0 / dist.get_world_size(g))
+    return fin
+
+
+def _table_reduce_async(t):
+    """Mean all-reduce of a grid-table gradient on the CURRENT stream's timeline; returns fin() to call before the result is used.
+    fp16 transport: |t|_max -> power-of-two scale (target 2^14 / world: the sum over the ranks stays below the fp16 maximum) ->
+    MIN over the ranks (every rank must use the same scale) -> halfs -> SUM all-reduce -> floats / (scale * world)."""
+    import torch.distributed as dist
+    if _GRAD_SYNC.get("transport", "fp32") != 'fp16':
+        return _allreduce_mean_async(t)
+    g = _GRAD_SYNC["group"]
+    world = dist.get_world_size(g)
+    flat = t.reshape(-1)
+    n = flat.numel()
+    scr_key = (str(t.device), torch.cuda.current_stream().cuda_stream)
+    scratch = _SCALE_SCRATCH.get(scr_key)
+    if scratch is None:
+        scratch = _SCALE_SCRATCH[scr_key] = torch.zeros(2, dtype=torch.int32, device=t.device)
+    scale = torch.empty(1, dtype=torch.float32, device=t.device)
+    call("pag_grad_scale", ptr(flat), n, 1, None, 0, 1, None, float(2.0 ** 14 / world), ptr(scratch), ptr(scale))
+    dist.all_reduce(scale, op=dist.ReduceOp.MIN, group=g)
+    h = torch.empty(n, dtype=torch.float16, device=t.device)
+    call("pag_pack_f16", ptr(flat), n, ptr(scale), ptr(h))
+    wk = dist.all_reduce(h, op=dist.ReduceOp.SUM, group=g, async_op=True)
+
+    def fin():
+        wk.wait()
+        call("pag_unpack_f16", ptr(h), n, ptr(scale), 1.0 / world, ptr(flat))
+    return fin
 
 
 # FusedTraceFn can drop zero-density samples after a density-only pass (exact; see pag_compact_count).  It pays when a
@@ -656,8 +711,6 @@ def _allreduce_async(t):
 # freshly initialised field (bench.py's synthetic weights: every sample has sigma > 0) the extra pass is pure overhead
 # (+0.12 ms on 392 k samples), so it is opt-in: cfg['compact'] / ops.COMPACT_LIVE.
 COMPACT_LIVE = False
-# level ranges the colour-table scatter is split into when its all-reduce is pipelined (multi-GPU; measured slower: default 1)
-GRAD_SYNC_CHUNKS = int(os.environ.get('PAGNERF_GRAD_SYNC_CHUNKS', '1'))
 IMG16 = True   # fp16 operand-image interchange between encoders and tensor-core decoders inside FusedTraceFn
 
 
@@ -778,6 +831,19 @@ class FusedTraceFn(Function):
         IN = L * 2
         tb = table.detach().contiguous()
         ph = int(bool(cfg['pos_half']))
+        # the two 50 MB gradient tables of the backward are zero-filled NOW, on their own stream, under the forward's latency-bound
+        # decoder kernels (the fill is pure HBM write bandwidth the forward leaves idle) instead of at the head of the backward
+        ctx.prezero = None
+        if BRANCH_OVERLAP and ctx.needs_input_grad[3] and cfg.get('prezero', True):
+            zs = _side_stream(dev, 2)
+            g_table0 = torch.empty_like(tb)
+            g_dtable0 = torch.empty_like(dtable) if (dtable is not None and ctx.needs_input_grad[4]) else None
+            zs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(zs):
+                g_table0.zero_()
+                if g_dtable0 is not None:
+                    g_dtable0.zero_()
+            ctx.prezero = (g_table0, g_dtable0, zs)
         # fp16 operand-image interchange between the encoders and the tensor-core decoders (one bulk copy per 128-sample tile
         # on the decoder side, coalesced 16-byte accesses on the encoder side); the f32 [M, 2L] layout stays for compaction
         # and for the hash grids
@@ -909,28 +975,38 @@ class FusedTraceFn(Function):
         L = _enc_levels(kind, cfg['grid'])
         ph = int(bool(cfg['pos_half']))
         Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
-        sync, works = _GRAD_SYNC["enabled"], []
+        sync, fins = _GRAD_SYNC["enabled"], []
         sizes = [x.numel() for x in w]
         flat = torch.zeros(sum(sizes), dtype=f32, device=dev)          # all 20 decoder gradients: one memset
         grads = [t.view_as(x) for t, x in zip(flat.split(sizes), w)]
-        g_dtable = None
         gs = _f32(g_sem) if (g_sem is not None and Cs) else None
         gi = _f32(g_inst) if (g_inst is not None and Ci) else None
         main = torch.cuda.current_stream()
-        side = None
-        table_reduced = False
-        if gs is not None or gi is not None:
+        # gradient tables: zero-filled during the forward on their own stream when the forward could tell they would be needed
+        g_table0, g_dtable0, zs = ctx.prezero if ctx.prezero is not None else (None, None, None)
+        ctx.prezero = None
+        if zs is not None:
+            main.wait_stream(zs)
+        st = {'g_dtable': None, 'g_table': None, 'g_o': None, 'g_d': None, 'side': None, 'comm': None}
+        want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
+        ga = _f32(g_alpha) if g_alpha is not None else None
+        gr = _f32(g_rgb) if (g_rgb is not None and want_rgb) else None
+        gd = _f32(g_depth) if (g_depth is not None and want_depth) else None
+        need_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        colour_ran = ga is not None or gr is not None or gd is not None
+
+        def run_pan():
             # panoptic chain (heads backward -> delta-grid scatter [-> all-reduce]) on a side stream; it shares nothing
-            # with the colour chain below except read-only inputs, and the two sets of kernels overlap on the SMs
+            # with the colour chain except read-only inputs, and the two sets of kernels overlap on the SMs
             src = cfg['pan_src']
             a, b = {'delta': (feats, dfeats), 'separate': (dfeats, None), 'appearance': (feats, None)}[src]
             need_gp = src in ('delta', 'separate')          # 'appearance': features are detached -> nothing upstream
             g_panop = grad_buffer() if need_gp else None
-            if need_gp:
-                g_dtable = torch.zeros_like(dtb)
-            side = _side_stream(dev)
+            side = st['side'] = _side_stream(dev)
             side.wait_stream(main)
             with torch.cuda.stream(side):
+                if need_gp:
+                    st['g_dtable'] = g_dtable0 if g_dtable0 is not None else torch.zeros_like(dtb)
                 scale_p = grad_scale_dyn(gs if gs is not None else gi, gi if gs is not None else None, None)
                 dds = (dd_tau, dd_w, dd_T, dd_alpha, dd_sem, dd_inst) if dd_tau is not None else None
                 pw, pa = (dd_w, dd_alpha) if dds is not None else (wgt, alpha)
@@ -951,18 +1027,13 @@ class FusedTraceFn(Function):
                     call("pag_linear_head_bwd_dyn", ptr(a), ptr(b), ptr(lodw), Mmax, ptr(m_dev), IN, ptr(w[20]), ptr(gtau), ptr(tau_p),
                          ptr(deltas), ptr(g_panop), 1, ptr(grads[20]), ptr(grads[21]), int(img), ptr(scale_p))
                 if need_gp:
-                    _enc_bwd(kind, cfg['dgrid'], samples, Mmax, m_dev, ph, dtb, g_panop, scale_p, g_dtable, None, img)
+                    _enc_bwd(kind, cfg['dgrid'], samples, Mmax, m_dev, ph, dtb, g_panop, scale_p, st['g_dtable'], None, img)
                     if sync:
-                        works.append(_allreduce_async(g_dtable))   # overlaps the colour-branch backward
-        # scalar compositing backward -> per-sample sigma / rgb gradients
-        want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
-        ga = _f32(g_alpha) if g_alpha is not None else None
-        gr = _f32(g_rgb) if (g_rgb is not None and want_rgb) else None
-        gd = _f32(g_depth) if (g_depth is not None and want_depth) else None
-        g_table = torch.zeros_like(tb)
-        need_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        g_o = g_d = None
-        if ga is not None or gr is not None or gd is not None:
+                        fins.append((side, _table_reduce_async(st['g_dtable'])))   # overlaps whatever of the backward is still queued
+
+        def run_colour():
+            # scalar compositing backward -> per-sample sigma / rgb gradients -> density / colour decoders -> colour-grid scatter
+            g_table = st['g_table'] = g_table0 if g_table0 is not None else torch.zeros_like(tb)
             g_sigma = torch.empty(Mmax, dtype=f32, device=dev)
             g_rgb_s = torch.empty(Mmax, 3, dtype=f32, device=dev) if gr is not None else None
             call("pag_composite_bwd", ptr(sigma), ptr(deltas), ptr(depths) if gd is not None else None, ptr(rgb), ptr(offsets), N,
@@ -975,31 +1046,34 @@ class FusedTraceFn(Function):
                  ptr_array(grads[:10]), HIDDEN, VIEW_DIM, ptr(g_sigma), ptr(g_rgb_s), ptr(scale), ptr(g_feats), ptr(g_dir),
                  ptr(ctx.pe16), *_ws("pag_decode_dc_bwd_workspace", dev, Mmax, IN), int(img))
             g_pos = torch.empty(Mmax, 3, dtype=f32, device=dev) if need_rays else None
-            # multi-GPU (opt-in, PAGNERF_GRAD_SYNC_CHUNKS > 1): scatter the colour table in level ranges and all-reduce every
-            # finished range while the next one is being scattered (measured slower at 2 GPUs)
-            nchunk = GRAD_SYNC_CHUNKS if (sync and img and GRAD_SYNC_CHUNKS > 1 and L % GRAD_SYNC_CHUNKS == 0) else 1
-            step_l = L // nchunk
-            for c in range(nchunk):
-                _enc_bwd(kind, cfg['grid'], samples, Mmax, m_dev, ph, tb, g_feats, scale, g_table, g_pos, img, c * step_l, (c + 1) * step_l)
-                if nchunk > 1:
-                    works.append(_allreduce_async(g_table[c * step_l:(c + 1) * step_l]))
-            table_reduced = nchunk > 1
+            _enc_bwd(kind, cfg['grid'], samples, Mmax, m_dev, ph, tb, g_feats, scale, g_table, g_pos, img)
+            if sync:      # the table's all-reduce leaves from its own stream: the rest of the backward keeps flowing on main
+                comm = st['comm'] = _side_stream(dev, 1)
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    fins.append((comm, _table_reduce_async(g_table)))
             if need_rays:   # d samples / d (origin, dir): segment sums over each ray's packed range
-                g_o = torch.empty(N, 3, dtype=f32, device=dev)
-                g_d = torch.empty(N, 3, dtype=f32, device=dev)
+                st['g_o'] = torch.empty(N, 3, dtype=f32, device=dev)
+                st['g_d'] = torch.empty(N, 3, dtype=f32, device=dev)
                 gpt = torch.addcmul(g_dir, g_pos, depths.unsqueeze(1)) if g_dir is not None else (g_pos * depths.unsqueeze(1))
-                call("pag_sum_reduce_fwd", ptr(g_pos), 3, ptr(offsets), N, ptr(g_o))
-                call("pag_sum_reduce_fwd", ptr(gpt.contiguous()), 3, ptr(offsets), N, ptr(g_d))
-        if side is not None:
-            main.wait_stream(side)
+                call("pag_sum_reduce_fwd", ptr(g_pos), 3, ptr(offsets), N, ptr(st['g_o']))
+                call("pag_sum_reduce_fwd", ptr(gpt.contiguous()), 3, ptr(offsets), N, ptr(st['g_d']))
+
+        pan_ran = gs is not None or gi is not None
+        order = (run_colour, run_pan) if _GRAD_SYNC.get("colour_first") else (run_pan, run_colour)
+        for fn in order:
+            if (fn is run_pan and pan_ran) or (fn is run_colour and colour_ran):
+                fn()
+        for strm, fin in fins:      # finish each table's reduction on the stream that issued it (unpack kernels overlap too)
+            with torch.cuda.stream(strm):
+                fin()
+        for strm in (st['side'], st['comm']):
+            if strm is not None:
+                main.wait_stream(strm)
         if sync:
-            if not table_reduced:
-                works.append(_allreduce_async(g_table))
-            works.append(_allreduce_async(flat))
-            for wk in works:
-                wk.wait()
+            _allreduce_mean_async(flat)()
+        g_table, g_dtable, g_o, g_d = st['g_table'], st['g_dtable'], st['g_o'], st['g_d']
         # parameters of heads that were not requested (or got no upstream gradient) receive None, like the reference's autograd
-        colour_ran = ga is not None or gr is not None or gd is not None
         gout = list(grads)
         if not colour_ran:
             gout[0:4] = [None] * 4

@@ -147,6 +147,11 @@ class PanopticNeF(BaseNeuralField):
         mask = self.grid.occupancy > min_density
         _points = points[mask]
         for grid in self._prune_grids():
+            if mask.is_cuda and mask.numel() == 8 ** grid.blas_level:
+                # device-side rebuild straight from the dense mask (csrc/octree.cu pag_octree_from_mask): same octree bytes as
+                # unbatched_points_to_octree(points[mask]) -- `dense_points` is in Morton order
+                grid.blas_init_from_mask(mask, register=self.grid_type == "PermutoGrid")
+                continue
             octree = spc.unbatched_points_to_octree(_points, grid.blas_level, sorted=True)
             # PermutoGrid re-registers its checkpoint buffers (blas_octree / points / prefix / pyramid); the hash grids keep
             # the state_dict keys they were built with (pc_nerf/panoptic_delta_nef.py:98-104, pc_nerf/panoptic_nef.py:233)

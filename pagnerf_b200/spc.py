@@ -82,6 +82,32 @@ def scan_octree(octree, level):
     return points, pyramid, prefix
 
 
+def octree_from_mask(mask, level):
+    """Dense leaf-occupancy mask bool[8^level] in Morton order (the order of `dense_points`) on a CUDA device ->
+    (octree u8[n_nodes], points i16[P,3], pyramid i32[2,level+2] (CPU), prefix i32[n_nodes+1]) with one kernel chain
+    (csrc/octree.cu pag_octree_from_mask) instead of unique / searchsorted / ~900 small integer ops; one 4 * (level+2)-word
+    D2H read for the sizes (cold path: runs once per prune)."""
+    dev = mask.device
+    F = (8 ** (level + 1) - 1) // 7
+    m = mask.to(torch.uint8).contiguous()
+    assert m.numel() == 8 ** level
+    i32, i64, u8 = torch.int32, torch.int64, torch.uint8
+    exists = torch.empty(F, dtype=i32, device=dev)
+    byts = torch.empty(F, dtype=u8, device=dev)
+    pos = torch.empty(F + 1, dtype=i64, device=dev)
+    popc = torch.empty(F, dtype=i32, device=dev)
+    prefix64 = torch.empty(F + 1, dtype=i64, device=dev)
+    octree = torch.empty(F, dtype=u8, device=dev)
+    points = torch.empty(F, 3, dtype=torch.int16, device=dev)
+    prefix = torch.empty(F + 1, dtype=i32, device=dev)
+    pyramid = torch.empty(2, level + 2, dtype=i32, device=dev)
+    ops.call("pag_octree_from_mask", ops.ptr(m), int(level), ops.ptr(exists), ops.ptr(byts), ops.ptr(pos), ops.ptr(popc), ops.ptr(prefix64),
+             ops.ptr(octree), ops.ptr(points), ops.ptr(prefix), ops.ptr(pyramid))
+    pyr = pyramid.cpu()
+    n_nodes, n_points = int(pyr[1, level]), int(pyr[1, level + 1])
+    return octree[:n_nodes].clone(), points[:n_points].clone(), pyr, prefix[:n_nodes + 1].clone()
+
+
 def unbatched_get_level_points(points, pyramid, level):
     s = int(pyramid[1, level])
     return points[s:s + int(pyramid[0, level])]
@@ -124,13 +150,25 @@ class OctreeAS:
         self.octree = octree
         self.max_level = level
         self.version += 1
+        self._refresh_bits()
+
+    def _refresh_bits(self):
         # occupancy bit fields have a fixed size per level: refresh the cached ones IN PLACE, so that a CUDA graph that
         # captured their address (the fused training trace marches against them) sees the pruned octree on its next replay
+        octree, level = self.octree, self.max_level
         for lvl, b in list(self._bits.items()):
             if b.device == octree.device and b.is_cuda and lvl <= level:
                 ops.call("pag_octree_level_bits", ops.ptr(self.octree), ops.ptr(self.prefix), lvl, ops.ptr(b))
             else:
                 del self._bits[lvl]
+
+    def init_from_mask(self, mask, level):
+        """Rebuild from the dense leaf-occupancy mask (Morton order) on the device -- the prune() path."""
+        self.device = mask.device
+        self.octree, self.points, self.pyramid, self.prefix = octree_from_mask(mask, level)
+        self.max_level = level
+        self.version += 1
+        self._refresh_bits()
 
     def init_dense(self, level):
         n_nodes = (8 ** level - 1) // 7

@@ -965,3 +965,82 @@ def test_fused_adam_matches_torch_adam(cuda_lib):
         assert_close(b, a.detach(), rtol=2e-6, atol_scale=1e-6, msg=f"param {k}")
     st = ours.state[our_p[0]]
     assert set(st) == {'exp_avg', 'exp_avg_sq', 'step'} and int(st['step']) == 5
+
+
+# ------------------------------------------------------------------------------------------------
+# prune(): device-side octree rebuild, checkpoint keys, graph-safe occupancy refresh
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("level,frac", [(1, 0.5), (3, 0.3), (5, 0.05), (7, 0.02), (4, 0.0), (4, 1.0)])
+def test_octree_from_mask_matches_oracle(cuda_lib, level, frac):
+    """pag_octree_from_mask (dense Morton-ordered mask -> SPC octree / points / prefix / pyramid) == oracle points_to_octree + scan."""
+    from oracle import spc as ospc
+    from pagnerf_b200 import spc
+    n = 8 ** level
+    gen = torch.Generator().manual_seed(level)
+    mask = torch.rand(n, generator=gen) < frac if 0.0 < frac < 1.0 else torch.full((n,), frac >= 1.0)
+    octree, points, pyramid, prefix = spc.octree_from_mask(mask.to(DEV), level)
+    codes = torch.nonzero(mask).flatten()
+    if codes.numel() == 0:
+        assert octree.numel() == 0 and points.numel() == 0 and int(pyramid[1, level + 1]) == 0
+        return
+    pts = spc.morton_decode(codes, level).numpy()
+    ref_oct = ospc.points_to_octree(pts, level)
+    ref_pts, ref_pyr, ref_pre = ospc.scan_octree(ref_oct, level)
+    assert np.array_equal(octree.cpu().numpy(), ref_oct)
+    assert np.array_equal(points.cpu().numpy(), ref_pts)
+    assert np.array_equal(prefix.cpu().numpy(), ref_pre)
+    assert np.array_equal(pyramid.numpy(), ref_pyr)
+
+
+def test_prune_rebuilds_octree_and_keeps_checkpoint_keys(cuda_lib):
+    """PanopticDeltaNeF.prune() on the GPU (pc_nerf/panoptic_delta_nef.py:63-104): the pruned octree equals the oracle's build
+    from the surviving cells, both grids share it, marching works against it, state_dict keys are unchanged and the checkpoint
+    round-trips; a cached occupancy bit field is refreshed in place (same address: CUDA graphs stay valid)."""
+    from oracle import spc as ospc
+    from pagnerf_b200 import spc
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_ray")
+    nef = build_cuda_nef(g, DEV)
+    level = nef.grid.blas_level
+    for gr in (nef.grid, nef.delta_grid):
+        gr.blas.init_dense(level)
+        gr.blas.to(DEV)
+        gr._register_blas_buffers()
+    keys0 = set(nef.state_dict().keys())
+    bits = nef.grid.blas.level_bits(level)
+    addr0 = bits.data_ptr()
+    assert int(bits.view(torch.uint8).sum()) == 255 * bits.numel() * 4, "dense octree: every occupancy bit set"
+    # a running occupancy that survives the 0.6 decay in about half of the cells (threshold 0.01*512/sqrt(3) = 2.96); the
+    # field's own density (~1 at the golden's init) is maxed in by prune() like in the reference
+    torch.manual_seed(0)
+    nef.grid.occupancy = torch.rand(8 ** level) * 10.0
+    nef.prune()
+    occ = nef.grid.occupancy
+    mask = (occ > (0.01 * 512) / np.sqrt(3)).cpu()
+    assert 0 < int(mask.sum()) < mask.numel(), f"prune kept {int(mask.sum())} of {mask.numel()} cells: the test needs a partial octree"
+    pts = nef.grid.dense_points.cpu()[mask].numpy()
+    ref_oct = ospc.points_to_octree(pts, level)
+    ref_pts, ref_pyr, ref_pre = ospc.scan_octree(ref_oct, level)
+    for gr in (nef.grid, nef.delta_grid):
+        assert np.array_equal(gr.blas.octree.cpu().numpy(), ref_oct)
+        assert np.array_equal(gr.blas.points.cpu().numpy(), ref_pts)
+        assert np.array_equal(gr.blas.prefix.cpu().numpy(), ref_pre)
+        assert np.array_equal(gr.blas.pyramid.numpy(), ref_pyr)
+    assert set(nef.state_dict().keys()) == keys0, "prune must not change the checkpoint keys"
+    bits2 = nef.grid.blas.level_bits(level)
+    assert bits2.data_ptr() == addr0, "occupancy bit field refreshed in place"
+    assert int(torch.tensor([bin(int(x) & 0xFFFFFFFF).count('1') for x in bits2.cpu().tolist()]).sum()) == int(mask.sum())
+    # the pruned field still traces, and the checkpoint round-trips into a fresh model (octree adopted from the state_dict)
+    tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=int(g["num_steps"]), bg_color='white')
+    rays = Rays(origins=torch.from_numpy(g["o"]).to(DEV), dirs=torch.from_numpy(g["d"]).to(DEV), dist_min=0.0, dist_max=2.0)
+    rb = tracer(nef, channels=['rgb', 'depth', 'semantics', 'inst_embedding'], rays=rays, lod_idx=None, stage='val')
+    assert torch.isfinite(rb.rgb).all()
+    nef2 = build_cuda_nef(g, DEV)
+    nef2.load_state_dict(nef.state_dict())
+    assert torch.equal(nef2.grid.blas.octree.cpu(), nef.grid.blas.octree.cpu())
+    for gr in (nef.grid, nef.delta_grid, nef2.grid, nef2.delta_grid):
+        gr.blas.fixed_jitter, gr.blas.jitter_seed = True, 3
+    rb2 = tracer(nef2, channels=['rgb', 'depth', 'semantics', 'inst_embedding'], rays=rays, lod_idx=None, stage='val')
+    rb1 = tracer(nef, channels=['rgb', 'depth', 'semantics', 'inst_embedding'], rays=rays, lod_idx=None, stage='val')
+    assert torch.equal(rb1.rgb, rb2.rgb) and torch.equal(rb1.inst_embedding, rb2.inst_embedding)
