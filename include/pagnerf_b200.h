@@ -317,6 +317,13 @@ int pag_adam_step(float* const* p, const float* const* g, float* const* m, float
                   const float* weight_decay, int n_tensors, float beta1, float beta2, float eps, int* step, const float* inv_scale,
                   void* stream);
 
+/* ---- L2 persisting window for a grid table (north_star: "per-level tables staged in shared memory or L2-persisting windows";
+ * the tables of grids/permuto_grid.py:57-62 are 50 MB each, the B200 L2 126 MB) ----
+ * Kernels launched on `stream` afterwards treat [base, base+bytes) as persisting with probability hit_ratio, everything else as
+ * streaming; bytes = 0 clears.  pag_l2_limits: the device's maximum persisting carve-out and window size. */
+int pag_set_l2_window(const void* base, int64_t bytes, float hit_ratio, void* stream);
+int pag_l2_limits(int64_t* max_persisting /* host */, int64_t* max_window /* host */);
+
 /* ---- achievable-gather-bandwidth probe (bench.py: denominator of the encoder's roofline fraction) ----
  * threads x loads_per_thread (multiple of 16, 16 in flight per thread) uniformly random 8-byte loads from table[entries] float2; sink f32[threads]. */
 int pag_gather_probe(const float* table, int64_t entries, int64_t threads, int loads_per_thread, float* sink, void* stream);

@@ -926,7 +926,7 @@ int pag_decode_dc_fwd_tc_dyn(const float* feats, const float* lodw, const float*
                              int want_rgb, float* sigma, float* rgb, float* y0_raw, const void* view_pe16, int feats_img16,
                              void* stream) {
     if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
-    if (feats_img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
+    if (feats_img16 && (IN & 3)) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     DcParams p{};
     fill_dc(p, weights, nullptr);
@@ -974,7 +974,7 @@ int pag_decode_dc_bwd_tc_dyn(const float* feats, const float* lodw, const float*
                              float* g_dir, const void* view_pe16, float* workspace, int64_t workspace_bytes, int img16,
                              void* stream) {
     if (hidden != H || view_dim != PE_DIM || IN < 1 || IN > 64 || (IN & 3)) return PAG_ERR_UNSUPPORTED;
-    if (img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
+    if (img16 && (IN & 3)) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     DcParams p{};
     fill_dc(p, weights, grads);

@@ -845,7 +845,7 @@ int pag_pan_composite_fwd_tc(const float* feats, const float* dfeats, const floa
                              float inst_temperature, const float* w, const float* alpha, const int64_t* ridx,
                              float* out_sem, float* out_inst, float* inst_lse, const int64_t* m_dev, int x_img16, void* stream) {
     if (!fused_shape_ok(IN, hidden, Cs, Ci)) return PAG_ERR_UNSUPPORTED;
-    if (x_img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
+    if (x_img16 && (IN & 3)) return PAG_ERR_UNSUPPORTED;
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
     PanParams p{};
     fill_pan_f(p, weights, nullptr);
@@ -882,7 +882,7 @@ int pag_pan_composite_bwd_tc(const float* feats, const float* dfeats, const floa
     if (M == 0 || (Cs == 0 && Ci == 0)) return PAG_OK;
     PanParams p{};
     fill_pan_f(p, weights, grads);
-    if (x_img16 && (IN & 7)) return PAG_ERR_UNSUPPORTED;
+    if (x_img16 && (IN & 3)) return PAG_ERR_UNSUPPORTED;
     const PanCompBwdLayout l = pan_comp_bwd_layout(IN, Cs, Ci, x_img16 != 0);
     if (l.total > 227 * 1024) return PAG_ERR_UNSUPPORTED;
     const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;

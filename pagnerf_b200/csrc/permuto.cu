@@ -15,6 +15,7 @@
 // gradient issue no atomics at all.
 // Lattice integers (rem0, rank, key, idx) are bit-exact against oracle/permuto.py.
 #include "common.cuh"
+#include <string.h>
 #include <cuda_fp16.h>
 
 #define PERMUTO_HASH_MUL 2531011u
@@ -435,6 +436,52 @@ int pag_gather_probe(const float* table, int64_t entries, int64_t threads, int l
     if (entries <= 0 || entries > 0xFFFFFFFFll || threads <= 0 || loads_per_thread <= 0 || (loads_per_thread & 15)) return PAG_ERR_ARG;
     gather_probe_kernel<<<pag_grid(threads, 128), 128, 0, (cudaStream_t)stream>>>(table, (uint32_t)entries, threads, loads_per_thread, sink);
     PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// ---- L2 persisting window (north_star: "per-level tables ... in L2-persisting windows") ------------------------------------
+// Marks [base, base + bytes) as persisting for every kernel launched on `stream` afterwards (captured into CUDA-graph kernel
+// nodes as well); bytes == 0 clears the window.  The persisting carve-out of the L2 is raised to the device maximum on first
+// use.  hit_ratio: fraction of the window's lines that get the persisting property (set < 1 when the window is larger than the
+// carve-out, so that the persisting lines do not thrash each other).
+int pag_set_l2_window(const void* base, int64_t bytes, float hit_ratio, void* stream) {
+    static bool carved = false;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_persist <= 0 || max_window <= 0) return PAG_ERR_UNSUPPORTED;
+    if (!carved) {
+        e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+        if (e != cudaSuccess) return (int)e;
+        carved = true;
+    }
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    if (bytes > 0) {
+        v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+        v.accessPolicyWindow.num_bytes = (size_t)(bytes < (int64_t)max_window ? bytes : (int64_t)max_window);
+        v.accessPolicyWindow.hitRatio = hit_ratio;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        v.accessPolicyWindow.num_bytes = 0;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    e = cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    return e == cudaSuccess ? PAG_OK : (int)e;
+}
+// max persisting carve-out / max window size of the current device (bytes)
+int pag_l2_limits(int64_t* max_persisting, int64_t* max_window) {
+    int dev = 0, a = 0, b = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PAG_ERR_ARG;
+    cudaDeviceGetAttribute(&a, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&b, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_persisting) *max_persisting = a;
+    if (max_window) *max_window = b;
     return PAG_OK;
 }
 

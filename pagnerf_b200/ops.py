@@ -350,8 +350,9 @@ class DecodeDCFn(Function):
         gf = torch.empty_like(f) if need_f else None
         gd = torch.empty(M, 3, dtype=torch.float32, device=f.device) if need_d else None
         if ctx.use_tc:
+            sc = grad_scale(gs, gr)      # held in a local: the tensor must outlive the enqueue of the kernel that reads it
             call("pag_decode_dc_bwd_tc", ptr(f), ptr(lw), ptr(rd), ctx.S, M, IN, ptr_array(w), ptr_array(grads), HIDDEN,
-                 VIEW_DIM, ptr(gs), ptr(gr), ptr(grad_scale(gs, gr)), ptr(gf), ptr(gd))
+                 VIEW_DIM, ptr(gs), ptr(gr), ptr(sc), ptr(gf), ptr(gd))
         else:
             call("pag_decode_dc_bwd", ptr(f), ptr(lw), ptr(rd), ctx.S, M, IN, ptr_array(w), ptr_array(grads), HIDDEN,
                  VIEW_DIM, ptr(gs), ptr(gr), ptr(gf), ptr(gd))
@@ -423,8 +424,9 @@ class DecodePanFn(Function):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         gp = torch.empty_like(f) if need else None
         if ctx.use_tc:
+            sc = grad_scale(gs, gi)
             call("pag_decode_pan_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), ptr_array(grads), HIDDEN, Cs, Ci, ss, is_, it,
-                 ptr(sem), ptr(inst), ptr(gs), ptr(gi), ptr(grad_scale(gs, gi)), ptr(gp))
+                 ptr(sem), ptr(inst), ptr(gs), ptr(gi), ptr(sc), ptr(gp))
         else:
             call("pag_decode_pan_bwd", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(w), ptr_array(grads), HIDDEN, Cs, Ci, ss, is_, it,
                  ptr(sem), ptr(inst), ptr(gs), ptr(gi), ptr(gp))
@@ -500,13 +502,19 @@ def _pan_bwd_workspace(M, IN, Cs, Ci, device):
     return _ws("pag_pan_composite_bwd_workspace", device, M, IN, Cs, Ci)
 
 
+class _Workspace:
+    """Partial weight-gradient workspace of a backward entry point (torch-allocated: graph safe).  The tensor must outlive the
+    ENQUEUE of the kernel that uses it -- hold the object in a local until after the call; once the kernel is queued the caching
+    allocator's stream-ordered reuse makes dropping it safe."""
+
+    def __init__(self, query, device, *args):
+        nbytes = query_i64(query, *[int(a) for a in args])
+        self.t = torch.empty(nbytes // 4, dtype=torch.float32, device=device) if nbytes else None
+        self.args = (ptr(self.t), nbytes) if nbytes else (None, 0)
+
+
 def _ws(query, device, *args):
-    """(pointer, bytes) of the partial weight-gradient workspace a backward entry point can use (torch-allocated: graph safe)."""
-    nbytes = query_i64(query, *[int(a) for a in args])
-    if nbytes == 0:
-        return None, 0
-    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=device)   # the caching allocator is stream ordered: safe to drop after enqueue
-    return ptr(ws), nbytes
+    return _Workspace(query, device, *args)
 
 
 class PanCompositeFn(Function):
@@ -545,9 +553,11 @@ class PanCompositeFn(Function):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         gp = torch.empty_like(f) if need else None
         if gs is not None or gi is not None:
+            wsp = _pan_bwd_workspace(M, IN, Cs, Ci, f.device)
+            sc = grad_scale(gs, gi)
             call("pag_pan_composite_bwd_tc", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), ptr_array(grads), HIDDEN, Cs, Ci,
-                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), int(a_.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(grad_scale(gs, gi)), ptr(gp), None,
-                 *_pan_bwd_workspace(M, IN, Cs, Ci, f.device), 0, None, None)
+                 ss, is_, it, ptr(w_), ptr(a_), ptr(r_), int(a_.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(sc), ptr(gp), None,
+                 *wsp.args, 0, None, None)
         elif gp is not None:
             gp.zero_()
         return (gp if ctx.needs_input_grad[0] else None, gp if ctx.needs_input_grad[1] else None,
@@ -711,6 +721,21 @@ def _table_reduce_async(t):
 # freshly initialised field (bench.py's synthetic weights: every sample has sigma > 0) the extra pass is pure overhead
 # (+0.12 ms on 392 k samples), so it is opt-in: cfg['compact'] / ops.COMPACT_LIVE.
 COMPACT_LIVE = False
+# L2 persisting windows (north_star design constraint; opt-in, see DESIGN 4.1 for the measurement): during the forward each encoder's
+# stream marks ITS table as persisting, during the backward its gradient table; everything else streams through the L2
+L2_WINDOW = os.environ.get('PAGNERF_L2_WINDOW', '0') == '1'
+
+
+def _l2_window(t, hit_ratio=1.0):
+    if L2_WINDOW:
+        lib = _lib.load()
+        rc = lib.pag_set_l2_window(ptr(t) if t is not None else None, int(t.numel() * t.element_size()) if t is not None else 0,
+                                   float(hit_ratio), _lib.stream())
+        if rc != 0:
+            raise RuntimeError(f"pagnerf_b200.pag_set_l2_window failed: {rc}")
+
+
+PREZERO = os.environ.get('PAGNERF_PREZERO', '1') == '1'
 IMG16 = True   # fp16 operand-image interchange between encoders and tensor-core decoders inside FusedTraceFn
 
 
@@ -834,7 +859,7 @@ class FusedTraceFn(Function):
         # the two 50 MB gradient tables of the backward are zero-filled NOW, on their own stream, under the forward's latency-bound
         # decoder kernels (the fill is pure HBM write bandwidth the forward leaves idle) instead of at the head of the backward
         ctx.prezero = None
-        if BRANCH_OVERLAP and ctx.needs_input_grad[3] and cfg.get('prezero', True):
+        if BRANCH_OVERLAP and PREZERO and ctx.needs_input_grad[3] and cfg.get('prezero', True):
             zs = _side_stream(dev, 2)
             g_table0 = torch.empty_like(tb)
             g_dtable0 = torch.empty_like(dtable) if (dtable is not None and ctx.needs_input_grad[4]) else None
@@ -860,6 +885,7 @@ class FusedTraceFn(Function):
                     else torch.empty(Mmax, IN, dtype=f32, device=dev))
 
         feats = feat_buffer()
+        _l2_window(tb)
         _enc_fwd(kind, cfg['grid'], samples, Mmax, m_dev, ph, tb, feats, img)
         w = [_f32(x) for x in weights]
         lodw = _f32(cfg['lodw'])
@@ -897,6 +923,7 @@ class FusedTraceFn(Function):
             side = _side_stream(dev)
             side.wait_stream(main)
             with torch.cuda.stream(side):
+                _l2_window(dtb)
                 _enc_fwd(kind, cfg['dgrid'], samples, Mmax, m_dev, ph, dtb, dfeats, img)
         sigma = torch.empty(Mmax, dtype=f32, device=dev)
         rgb = torch.empty(Mmax, 3, dtype=f32, device=dev) if want_rgb else None
@@ -987,7 +1014,11 @@ class FusedTraceFn(Function):
         ctx.prezero = None
         if zs is not None:
             main.wait_stream(zs)
-        st = {'g_dtable': None, 'g_table': None, 'g_o': None, 'g_d': None, 'side': None, 'comm': None}
+        # 'keep': every temporary that a kernel on ANOTHER stream than its allocation stream touches stays referenced until the
+        # streams have been joined at the end of this function -- a tensor that dies earlier goes back to its allocation
+        # stream's pool and the next allocation there (e.g. the colour chain's gradient image) would alias it while the side
+        # stream is still reading
+        st = {'g_dtable': None, 'g_table': None, 'g_o': None, 'g_d': None, 'side': None, 'comm': None, 'keep': []}
         want_rgb, want_depth = bool(cfg['want_rgb']), bool(cfg['want_depth'])
         ga = _f32(g_alpha) if g_alpha is not None else None
         gr = _f32(g_rgb) if (g_rgb is not None and want_rgb) else None
@@ -1012,10 +1043,11 @@ class FusedTraceFn(Function):
                 pw, pa = (dd_w, dd_alpha) if dds is not None else (wgt, alpha)
                 gw_sem = torch.empty(Mmax, dtype=f32, device=dev) if (dds is not None and gs is not None) else None
                 gw_inst = torch.empty(Mmax, dtype=f32, device=dev) if (dds is not None and gi is not None) else None
+                wsp = _pan_bwd_workspace(Mmax, IN, Cs, Ci, dev)
                 call("pag_pan_composite_bwd_tc", ptr(a), ptr(b), ptr(lodw), Mmax, IN, ptr_array(w[10:20]), ptr_array(grads[10:20]), HIDDEN,
                      Cs, Ci, int(bool(cfg['sem_softmax'])), int(bool(cfg['inst_softmax'])), float(cfg['inst_temperature']),
                      ptr(pw), ptr(pa), ptr(ridx), int(alpha.shape[0]), ptr(gs), ptr(gi), ptr(ctx.lse), ptr(scale_p), ptr(g_panop), ptr(m_dev),
-                     *_pan_bwd_workspace(Mmax, IN, Cs, Ci, dev), int(img), ptr(gw_sem), ptr(gw_inst))
+                     *wsp.args, int(img), ptr(gw_sem), ptr(gw_inst))
                 if dds is not None:
                     # the panoptic weights carry gradient: d L / d w_p -> reverse scan -> tau_p -> ReLU gate -> delta-density head
                     tau_p, _, T_p, _, sem_o, inst_o = dds
@@ -1026,7 +1058,10 @@ class FusedTraceFn(Function):
                     call("pag_expint_bwd", ptr(gwt), ptr(pw), ptr(T_p), ptr(offsets), N, ptr(gtau))
                     call("pag_linear_head_bwd_dyn", ptr(a), ptr(b), ptr(lodw), Mmax, ptr(m_dev), IN, ptr(w[20]), ptr(gtau), ptr(tau_p),
                          ptr(deltas), ptr(g_panop), 1, ptr(grads[20]), ptr(grads[21]), int(img), ptr(scale_p))
+                    st['keep'] += [gwt, gtau]
+                st['keep'] += [g_panop, scale_p, gw_sem, gw_inst, wsp]
                 if need_gp:
+                    _l2_window(st['g_dtable'])
                     _enc_bwd(kind, cfg['dgrid'], samples, Mmax, m_dev, ph, dtb, g_panop, scale_p, st['g_dtable'], None, img)
                     if sync:
                         fins.append((side, _table_reduce_async(st['g_dtable'])))   # overlaps whatever of the backward is still queued
@@ -1042,10 +1077,13 @@ class FusedTraceFn(Function):
             scale = grad_scale_dyn(g_sigma, g_rgb_s, m_dev, 1, 3)
             g_feats = grad_buffer()
             g_dir = torch.empty(Mmax, 3, dtype=f32, device=dev) if ctx.needs_input_grad[1] else None
+            wsd = _ws("pag_decode_dc_bwd_workspace", dev, Mmax, IN)
             call("pag_decode_dc_bwd_tc_dyn", ptr(feats), ptr(lodw), ptr(d), ptr(ridx), Mmax, ptr(m_dev), IN, ptr_array(w[:10]),
                  ptr_array(grads[:10]), HIDDEN, VIEW_DIM, ptr(g_sigma), ptr(g_rgb_s), ptr(scale), ptr(g_feats), ptr(g_dir),
-                 ptr(ctx.pe16), *_ws("pag_decode_dc_bwd_workspace", dev, Mmax, IN), int(img))
+                 ptr(ctx.pe16), *wsd.args, int(img))
             g_pos = torch.empty(Mmax, 3, dtype=f32, device=dev) if need_rays else None
+            st['keep'] += [g_sigma, g_rgb_s, g_feats, g_dir, g_pos, scale, wsd]
+            _l2_window(g_table)
             _enc_bwd(kind, cfg['grid'], samples, Mmax, m_dev, ph, tb, g_feats, scale, g_table, g_pos, img)
             if sync:      # the table's all-reduce leaves from its own stream: the rest of the backward keeps flowing on main
                 comm = st['comm'] = _side_stream(dev, 1)

@@ -558,14 +558,15 @@ def test_cuda_graph_replay_matches_eager(cuda_lib):
     wl = bench.Workload(dev, n_rays=2048, seed=0, n_batches=2)
     wl.keep_rb = False
     blas = wl.nef.grid.blas
-    blas.fixed_jitter, blas.jitter_seed = True, 5
+    blas.jitter_seed = 5
     g = GraphedStep(wl.loss_of, wl.dev[0], wl.params, wl.nef)
     seed_before = int(blas.seed_tensor.item())
+    assert blas.jitter_seed == seed_before, "host mirror of the device-side jitter seed"
     loss_g = float(g(*wl.dev[1]))
     grads_g = [p.grad.clone() for p in wl.params]
-    assert int(blas.seed_tensor.item()) == seed_before + 1
-    # eager step with the same batch and the same jitter seed
-    blas.seed_tensor.fill_(seed_before)
+    assert int(blas.seed_tensor.item()) == seed_before + 1 == blas.jitter_seed
+    # eager step with the same batch and the same jitter seed (eager traces follow blas.jitter_seed, not the device-side seed)
+    blas.jitter_seed = seed_before
     for p in wl.params:
         p.grad = None
     loss_e = wl.loss_of(*wl.dev[1])
@@ -828,8 +829,8 @@ def test_sync_free_fused_trace_equals_stepwise_voxel(cuda_lib, with_pose_grad):
     for fused in (True, False):
         nef = build_cuda_nef(g, DEV)
         nef.decoder_precision = 'fp16'
-        tracer = PanopticPackedRFTracer(raymarch_type='voxel', num_steps=int(g["num_steps"]), bg_color='white',
-                                        ray_max_travel=float(g["ray_max_travel"]))
+        tracer = PanopticPackedRFTracer(raymarch_type='voxel', num_steps=int(g["num_steps"]),
+                                        bg_color='white' if bool(g["bg_white"]) else 'black', ray_max_travel=float(g["ray_max_travel"]))
         tracer.allow_fused = fused
         o = torch.from_numpy(g["o"]).to(DEV).requires_grad_(with_pose_grad)
         d = torch.from_numpy(g["d"]).to(DEV).requires_grad_(with_pose_grad)
@@ -1011,10 +1012,12 @@ def test_prune_rebuilds_octree_and_keeps_checkpoint_keys(cuda_lib):
     bits = nef.grid.blas.level_bits(level)
     addr0 = bits.data_ptr()
     assert int(bits.view(torch.uint8).sum()) == 255 * bits.numel() * 4, "dense octree: every occupancy bit set"
-    # a running occupancy that survives the 0.6 decay in about half of the cells (threshold 0.01*512/sqrt(3) = 2.96); the
-    # field's own density (~1 at the golden's init) is maxed in by prune() like in the reference
+    # a running occupancy that survives the 0.6 decay in about half of the cells (threshold 0.01*512/sqrt(3) = 2.96)
     torch.manual_seed(0)
     nef.grid.occupancy = torch.rand(8 ** level) * 10.0
+    with torch.no_grad():      # the field itself contributes no density here: the running occupancy alone decides
+        nef.decoder_density.lout.weight[0].zero_()
+        nef.decoder_density.lout.bias[0] = -1.0
     nef.prune()
     occ = nef.grid.occupancy
     mask = (occ > (0.01 * 512) / np.sqrt(3)).cpu()
@@ -1044,3 +1047,27 @@ def test_prune_rebuilds_octree_and_keeps_checkpoint_keys(cuda_lib):
     rb2 = tracer(nef2, channels=['rgb', 'depth', 'semantics', 'inst_embedding'], rays=rays, lod_idx=None, stage='val')
     rb1 = tracer(nef, channels=['rgb', 'depth', 'semantics', 'inst_embedding'], rays=rays, lod_idx=None, stage='val')
     assert torch.equal(rb1.rgb, rb2.rgb) and torch.equal(rb1.inst_embedding, rb2.inst_embedding)
+
+
+def test_full_size_step_on_a_dirty_allocator(cuda_lib):
+    """Every torch.empty() of the fused step is served from NaN-filled memory: a read of a buffer nobody wrote, or of a tensor that
+    went back to the caching allocator while another stream was still using it, turns into non-finite gradients.  (Regression:
+    a gradient image freed by the panoptic chain was re-used by the colour chain while the delta-grid scatter was still reading.)"""
+    import bench
+    dev = torch.device(DEV)
+    x = torch.full((3_000_000_000 // 4,), float('nan'), device=dev)
+    del x
+    ref = None
+    for rep in range(3):
+        wl = bench.Workload(dev, n_rays=16384, seed=0, n_batches=1)
+        r = wl.forward_backward()
+        torch.cuda.synchronize()
+        grads = {n: p.grad for n, p in wl.nef.named_parameters()}
+        for n, g in grads.items():
+            assert g is not None and torch.isfinite(g).all(), f"rep {rep}: {n}"
+        if ref is None:
+            ref = {n: g.clone() for n, g in grads.items()}
+        else:      # same rays, same parameters, same jitter stream: only the order of the atomics may differ
+            for n, g in grads.items():
+                assert_close_norm(g, ref[n], rel_l2=1e-4, max_frac=1e-3, msg=f"rep {rep} vs rep 0: {n}")
+    torch.cuda.empty_cache()
