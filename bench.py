@@ -567,12 +567,16 @@ def main():
         trace("process group up")
     if infer:
         return bench_inference(args, cfg, config, metric, unit, rank, world, device, dist)
-    wl = Workload(device, rays, seed=rank, dd=args.dd, config=args.config, march=args.march)
+    # BENCH_SAME_SEED=1 (diagnostic): every rank traces the same rays -> no load imbalance between the ranks
+    wl = Workload(device, rays, seed=0 if os.environ.get('BENCH_SAME_SEED') == '1' else rank, dd=args.dd, config=args.config, march=args.march)
     trace("workload built")
+    transport = None
     if world > 1:
         from pagnerf_b200 import ops
-        # gradient all-reduce (NCCL) issued from inside the fused backward (reserving SMs for NCCL measured slower: 0)
-        ops.set_grad_sync(True, reserved_sms=int(os.environ.get("BENCH_RESERVED_SMS", 0)))
+        # gradient exchange issued from inside the fused backward.  Default: the tables live in symmetric memory and are reduced in
+        # place by csrc/allreduce.cu over NVLink / NVSwitch peer memory (exact fp32); PAGNERF_GRAD_TRANSPORT=fp32|fp16 selects NCCL.
+        transport = os.environ.get("PAGNERF_GRAD_TRANSPORT", "symm")
+        ops.set_grad_sync(True, reserved_sms=int(os.environ.get("BENCH_RESERVED_SMS", 0)), transport=transport)
 
     def step(from_host):
         return wl.forward_backward(from_host=from_host)
@@ -651,7 +655,7 @@ def main():
         sync()
         ms_nosync = n0.elapsed_time(n1) / args.steps
         del g2
-        _o.set_grad_sync(True, reserved_sms=int(os.environ.get("BENCH_RESERVED_SMS", 0)))
+        _o.set_grad_sync(True, reserved_sms=int(os.environ.get("BENCH_RESERVED_SMS", 0)), transport=transport)
     # ---- per-entry-point CUDA-event timing of the same step, eager (events cannot be read back from a graph) ---------
     ksteps = min(args.steps, 20)
     sync()
@@ -738,7 +742,10 @@ def main():
               "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roof, "encoder": encoder, "cpu_baseline": cpu,
               "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
     if ms_nosync is not None:
-        result["allreduce"] = {"ms_per_step_without_allreduce": ms_nosync, "exposed_ms": ms - ms_nosync,
+        result["allreduce"] = {"transport": {"symm": "own kernel over NVLink/NVSwitch peer memory (symmetric buffers; multimem.ld_reduce/st through the "
+                                                     "switch multicast address at > 2 ranks, peer loads/stores at 2), exact fp32",
+                                             "fp32": "NCCL all-reduce, fp32", "fp16": "NCCL all-reduce, tables as fp16 under a shared scale"}[transport],
+                               "ms_per_step_without_allreduce": ms_nosync, "exposed_ms": ms - ms_nosync,
                                "note": "same CUDA graph captured with the gradient all-reduces switched off, max over ranks"}
     print(json.dumps(result))
     _leave(world, dist)

@@ -309,6 +309,16 @@ int pag_pose_transform_fwd(const float* params, const int64_t* cam_idx, const fl
 int pag_pose_transform_bwd(const float* params, const int64_t* cam_idx, const float* base_o, const float* base_d, const float* g_o,
                            const float* g_d, int64_t C, int64_t B, float* g_params, void* stream);
 
+/* ---- gradient all-reduce over NVLink / NVSwitch peer memory (ray-sharded data parallelism; no reference counterpart:
+ * the reference is single-GPU, its DDP equivalent would all-reduce the grid tables of grids/permuto_grid.py:57-62 with NCCL) ----
+ * In-place x <- mult * sum_ranks x on elements [offset, offset+n) of a SYMMETRIC float buffer: through the NVSwitch multicast
+ * address (multimem.ld_reduce / multimem.st: the sum is formed inside the switch) or, when multicast is NULL, with explicit loads
+ * from / stores to the `world` peer copies.  Rank r reduces the r-th slice.  The cross-rank ordering is pag_symm_barrier on the same
+ * stream before and after: one CTA exchanging epochs through int32 flags [channels][16] kept at flag_offset of the same buffer. */
+int pag_symm_barrier(float* const* peers, int64_t flag_offset, int* epoch, int rank, int world, int channel, void* stream);
+int pag_allreduce_symm(float* multicast, float* const* peers, int rank, int world, int64_t offset, int64_t n, float mult, int max_ctas,
+                       void* stream);
+
 /* ---- fused multi-tensor Adam (BASELINE config 4: "+ Adam"; SURVEY 8e "a single fused unscale + Adam kernel") ----
  * Replaces torch.optim.Adam.step() as the reference's trainer runs it (pc_nerf/trainer.py:229-300 parameter groups, :590 step;
  * configs/bup20/best.yaml:114 optimizer_type adam): n_tensors <= 48 fp32 tensors in one launch, host arrays of device pointers,

@@ -655,17 +655,38 @@ def set_grad_sync(enabled, group=None, reserved_sms=0, transport=None, colour_fi
       transport    'fp32' (exact mean) or 'fp16': the two 50 MB tables travel as halfs under a power-of-two scale shared by all
                    ranks (a 4-byte MIN all-reduce of the per-rank scales first); halves the bytes on the wire, 2^-11 relative
                    rounding per element -- inside north_star's 2e-3 for fp16 features.  Default: PAGNERF_GRAD_TRANSPORT or 'fp32'.
+                   'symm': the gradient tables live in symmetric memory (parallel.SymmetricGradBuffers) and are reduced IN PLACE by
+                   our own kernel over NVLink / NVSwitch peer memory (csrc/allreduce.cu: multimem.ld_reduce + multimem.st through the
+                   switch's multicast address, exact fp32) instead of NCCL; the returned table gradients are views of those
+                   persistent buffers -- valid until the next backward overwrites them (NCCL backend, one node).
       colour_first issue the colour chain (and the all-reduce of its table) before the panoptic chain instead of after it."""
     _GRAD_SYNC["enabled"], _GRAD_SYNC["group"] = bool(enabled), group
     if transport is not None:
-        if transport not in ('fp32', 'fp16'):
-            raise ValueError("transport must be 'fp32' or 'fp16'")
+        if transport not in ('fp32', 'fp16', 'symm'):
+            raise ValueError("transport must be 'fp32', 'fp16' or 'symm'")
         _GRAD_SYNC["transport"] = transport
     if colour_first is not None:
         _GRAD_SYNC["colour_first"] = bool(colour_first)
     # leave a few SMs to the NCCL kernels: the persistent decoder kernels would otherwise hold every SM until they finish
     # and the "overlapped" all-reduce would start only then
     _lib.load().pag_set_reserved_sms(int(reserved_sms) if enabled else 0, None)
+
+
+_SYMM = {}
+
+
+def _symm_grads(device, n_table, n_dtable, n_flat):
+    """Per-process symmetric gradient buffers for the 'symm' transport (created collectively at the first backward)."""
+    key = (str(device), int(n_table), int(n_dtable), int(n_flat))
+    sg = _SYMM.get(key)
+    if sg is None:
+        from .parallel import SymmetricGradBuffers
+        sg = _SYMM[key] = SymmetricGradBuffers({'dtable': n_dtable, 'table': n_table, 'flat': n_flat}, device, _GRAD_SYNC["group"])
+    return sg
+
+
+def _use_symm():
+    return _GRAD_SYNC["enabled"] and _GRAD_SYNC.get("transport") == 'symm'
 
 
 def _dist_world():
@@ -724,6 +745,7 @@ COMPACT_LIVE = False
 # L2 persisting windows (north_star design constraint; opt-in, see DESIGN 4.1 for the measurement): during the forward each encoder's
 # stream marks ITS table as persisting, during the backward its gradient table; everything else streams through the L2
 L2_WINDOW = os.environ.get('PAGNERF_L2_WINDOW', '0') == '1'
+SYMM_CHUNKS = int(os.environ.get('PAGNERF_SYMM_CHUNKS', '1'))      # level ranges of the colour-table scatter / exchange pipeline ('symm' transport)
 
 
 def _l2_window(t, hit_ratio=1.0):
@@ -861,8 +883,13 @@ class FusedTraceFn(Function):
         ctx.prezero = None
         if BRANCH_OVERLAP and PREZERO and ctx.needs_input_grad[3] and cfg.get('prezero', True):
             zs = _side_stream(dev, 2)
-            g_table0 = torch.empty_like(tb)
-            g_dtable0 = torch.empty_like(dtable) if (dtable is not None and ctx.needs_input_grad[4]) else None
+            if _use_symm():      # gradient tables in symmetric memory: reduced in place by csrc/allreduce.cu
+                sg = _symm_grads(dev, tb.numel(), dtable.numel() if dtable is not None else 0, sum(x.numel() for x in weights))
+                g_table0 = sg.view('table').view_as(tb)
+                g_dtable0 = sg.view('dtable').view_as(dtable) if (dtable is not None and ctx.needs_input_grad[4]) else None
+            else:
+                g_table0 = torch.empty_like(tb)
+                g_dtable0 = torch.empty_like(dtable) if (dtable is not None and ctx.needs_input_grad[4]) else None
             zs.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(zs):
                 g_table0.zero_()
@@ -1003,8 +1030,14 @@ class FusedTraceFn(Function):
         ph = int(bool(cfg['pos_half']))
         Cs, Ci = int(cfg['Cs']), int(cfg['Ci'])
         sync, fins = _GRAD_SYNC["enabled"], []
+        smask = int(os.environ.get('PAGNERF_SYNC_MASK', '7'))      # debugging: bit 0 delta table, bit 1 colour table, bit 2 decoders
         sizes = [x.numel() for x in w]
-        flat = torch.zeros(sum(sizes), dtype=f32, device=dev)          # all 20 decoder gradients: one memset
+        symm = _symm_grads(dev, tb.numel(), dtb.numel() if dtb is not None else 0, sum(sizes)) if (sync and _use_symm()) else None
+        if symm is not None:
+            flat = symm.view('flat')
+            flat.zero_()
+        else:
+            flat = torch.zeros(sum(sizes), dtype=f32, device=dev)          # all 20 decoder gradients: one memset
         grads = [t.view_as(x) for t, x in zip(flat.split(sizes), w)]
         gs = _f32(g_sem) if (g_sem is not None and Cs) else None
         gi = _f32(g_inst) if (g_inst is not None and Ci) else None
@@ -1037,7 +1070,13 @@ class FusedTraceFn(Function):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 if need_gp:
-                    st['g_dtable'] = g_dtable0 if g_dtable0 is not None else torch.zeros_like(dtb)
+                    if g_dtable0 is not None:
+                        st['g_dtable'] = g_dtable0
+                    elif symm is not None:
+                        st['g_dtable'] = symm.view('dtable').view_as(dtb)
+                        st['g_dtable'].zero_()
+                    else:
+                        st['g_dtable'] = torch.zeros_like(dtb)
                 scale_p = grad_scale_dyn(gs if gs is not None else gi, gi if gs is not None else None, None)
                 dds = (dd_tau, dd_w, dd_T, dd_alpha, dd_sem, dd_inst) if dd_tau is not None else None
                 pw, pa = (dd_w, dd_alpha) if dds is not None else (wgt, alpha)
@@ -1063,12 +1102,21 @@ class FusedTraceFn(Function):
                 if need_gp:
                     _l2_window(st['g_dtable'])
                     _enc_bwd(kind, cfg['dgrid'], samples, Mmax, m_dev, ph, dtb, g_panop, scale_p, st['g_dtable'], None, img)
-                    if sync:
+                    if sync and symm is not None and (smask & 1):
+                        symm.allreduce('dtable', channel=0)      # on the side stream: overlaps whatever of the backward is still queued
+                    elif sync and (smask & 1):
                         fins.append((side, _table_reduce_async(st['g_dtable'])))   # overlaps whatever of the backward is still queued
 
         def run_colour():
             # scalar compositing backward -> per-sample sigma / rgb gradients -> density / colour decoders -> colour-grid scatter
-            g_table = st['g_table'] = g_table0 if g_table0 is not None else torch.zeros_like(tb)
+            if g_table0 is not None:
+                g_table = g_table0
+            elif symm is not None:
+                g_table = symm.view('table').view_as(tb)
+                g_table.zero_()
+            else:
+                g_table = torch.zeros_like(tb)
+            st['g_table'] = g_table
             g_sigma = torch.empty(Mmax, dtype=f32, device=dev)
             g_rgb_s = torch.empty(Mmax, 3, dtype=f32, device=dev) if gr is not None else None
             call("pag_composite_bwd", ptr(sigma), ptr(deltas), ptr(depths) if gd is not None else None, ptr(rgb), ptr(offsets), N,
@@ -1084,12 +1132,24 @@ class FusedTraceFn(Function):
             g_pos = torch.empty(Mmax, 3, dtype=f32, device=dev) if need_rays else None
             st['keep'] += [g_sigma, g_rgb_s, g_feats, g_dir, g_pos, scale, wsd]
             _l2_window(g_table)
-            _enc_bwd(kind, cfg['grid'], samples, Mmax, m_dev, ph, tb, g_feats, scale, g_table, g_pos, img)
-            if sync:      # the table's all-reduce leaves from its own stream: the rest of the backward keeps flowing on main
-                comm = st['comm'] = _side_stream(dev, 1)
-                comm.wait_stream(main)
-                with torch.cuda.stream(comm):
-                    fins.append((comm, _table_reduce_async(g_table)))
+            # 'symm' transport, opt-in (PAGNERF_SYMM_CHUNKS > 1): the colour table is the last gradient of the step, nothing is left
+            # to hide its exchange behind -- scatter it in level ranges and let every finished range leave on the exchange stream
+            # while the next one is being scattered.  Measured at 2 GPUs: 1 / 2 / 3 ranges = 1.53 / 1.51 / 1.55 ms (the extra passes
+            # over the samples eat the overlap), so the default stays 1.
+            nchunk = SYMM_CHUNKS if (sync and symm is not None and (smask & 2) and img and kind == 'permuto' and L % SYMM_CHUNKS == 0) else 1
+            step_l = L // nchunk
+            per_level = tb.numel() // L
+            for c in range(nchunk):
+                l0, l1 = c * step_l, (c + 1) * step_l
+                _enc_bwd(kind, cfg['grid'], samples, Mmax, m_dev, ph, tb, g_feats, scale, g_table, g_pos, img, l0, l1 if nchunk > 1 else None)
+                if sync and (symm is not None or (smask & 2)):
+                    comm = st['comm'] = _side_stream(dev, 1)
+                    comm.wait_stream(main)
+                    with torch.cuda.stream(comm):
+                        if symm is not None and (smask & 2):
+                            symm.allreduce('table', channel=1, sub=(l0 * per_level, (l1 - l0) * per_level))
+                        elif symm is None and (smask & 2):
+                            fins.append((comm, _table_reduce_async(g_table)))
             if need_rays:   # d samples / d (origin, dir): segment sums over each ray's packed range
                 st['g_o'] = torch.empty(N, 3, dtype=f32, device=dev)
                 st['g_d'] = torch.empty(N, 3, dtype=f32, device=dev)
@@ -1108,7 +1168,9 @@ class FusedTraceFn(Function):
         for strm in (st['side'], st['comm']):
             if strm is not None:
                 main.wait_stream(strm)
-        if sync:
+        if sync and symm is not None and (smask & 4):
+            symm.allreduce('flat', channel=2, max_ctas=16)
+        elif sync and symm is None and (smask & 4):
             _allreduce_mean_async(flat)()
         g_table, g_dtable, g_o, g_d = st['g_table'], st['g_dtable'], st['g_o'], st['g_d']
         # parameters of heads that were not requested (or got no upstream gradient) receive None, like the reference's autograd
