@@ -107,8 +107,12 @@ def build_cuda_nef(g, device):
     return nef.to(device)
 
 
-def assert_close(a, b, rtol=1e-4, atol_scale=1e-4, msg=""):
-    """|a-b| <= rtol*|b| + atol_scale*max|b|  (north_star: 1e-4 relative in fp32)."""
+def assert_close(a, b, rtol=1e-4, atol_scale=2e-5, msg=""):
+    """Elementwise |a-b| <= rtol*|b| + atol_scale*max|b|  (north_star: 1e-4 relative in fp32).  The floor (default 2e-5 of the
+    tensor's scale, ~170 fp32 ulps of the largest element) covers the elements that are differences / sums of much larger terms
+    -- table gradients accumulated from thousands of atomics in arbitrary order, softmax tails -- whose absolute error is set by
+    the large terms, not by their own magnitude; a fifth of the relative tolerance, so it cannot hide a wrong small element
+    behind the relative term of a large one."""
     a = torch.as_tensor(a).double().cpu()
     b = torch.as_tensor(b).double().cpu()
     assert a.shape == b.shape, f"{msg}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
@@ -118,12 +122,14 @@ def assert_close(a, b, rtol=1e-4, atol_scale=1e-4, msg=""):
                            f"{float((a - b).abs().max()):.3e}, ref max {float(b.abs().max()):.3e}")
 
 
-def assert_close_norm(a, b, rel_l2=5e-2, max_frac=0.3, msg=""):
-    """Reduced-precision comparison: ||a-b||_2 <= rel_l2*||b||_2 and max|a-b| <= max_frac*max|b|
-    Gradients of a ReLU MLP evaluated with fp16-rounded activations differ from the fp32 ones by the few hidden
-    units whose pre-activation sign flips under the rounding (measured: ~1e-2 relative l2, independent of the
-    sample count, while the last-layer gradients -- no mask involved -- agree to 3e-4); the reference's own
-    autocast training step has the same property."""
+def assert_close_norm(a, b, rel_l2=1.5e-2, max_frac=0.1, msg=""):
+    """Reduced-precision comparison: ||a-b||_2 <= rel_l2*||b||_2 and max|a-b| <= max_frac*max|b|.
+    Gradients of a ReLU MLP evaluated with fp16-rounded activations differ from the fp32 ones by the few hidden units whose
+    pre-activation sign flips under the rounding.  The size of that effect is MEASURED, not assumed: tests/test_gpu_bench_shapes.py
+    runs the reference's own autocast numerics (oracle/autocast.py) beside the tensor-core path at the benchmarked shapes -- the
+    reference's autocast step is 2e-4 .. 8e-3 relative l2 away from exact fp32 per tensor, the tensor-core kernels 2e-5 .. 6e-3
+    (profiles/r02_parity_bench_shapes.md).  The default here (1.5e-2 l2, 10 % max) is for the small goldens (48 rays, a few
+    hundred samples), where one flipped unit is a visibly larger share of the total."""
     a = torch.as_tensor(a).double().cpu()
     b = torch.as_tensor(b).double().cpu()
     assert a.shape == b.shape, f"{msg}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
