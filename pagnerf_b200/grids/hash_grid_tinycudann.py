@@ -29,7 +29,7 @@ def tcnn_levels(n_levels, log2_T, base_resolution, per_level_scale=2.0):
 class TcnnEncoding(nn.Module):
     """tcnn.Encoding(n_input_dims=3, {otype: HashGrid, ...}) container: flat `params` like upstream."""
 
-    def __init__(self, n_input_dims, encoding_config, agg_resolution_threshold=64):
+    def __init__(self, n_input_dims, encoding_config, agg_resolution_threshold=16):
         super().__init__()
         c = encoding_config
         if n_input_dims != 3 or c.get("otype", "HashGrid") != "HashGrid" or c["n_features_per_level"] != 2:
@@ -43,6 +43,8 @@ class TcnnEncoding(nn.Module):
         self.register_buffer('level_size', torch.from_numpy(sz).to(torch.int32), persistent=False)
         self.params = nn.Parameter((torch.rand(total * self.F) * 2 - 1) * 1e-4)
         self.n_output_dims = self.n_levels * self.F
+        # warp-aggregated scatter only on the coarsest level: measured on BASELINE configs 1 / 3 (tools/hash_tune.py, B200):
+        # 0 / 1 / 3 / 5 aggregated levels = 0.31 / 0.28 / 0.29 / 0.41 ms and 1.51 / 1.19 / 1.79 / 3.31 ms per launch
         self.n_agg_levels = int((rs <= agg_resolution_threshold).sum())
         self.round_half = True  # upstream returns __half; the wrapper casts to float (:41)
 
