@@ -413,11 +413,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def measured_traffic(kernel):
     """dram bytes per launch of `kernel` from the committed ncu --set full capture of this same command
-    (profiles/r01_traffic.json: {entry point: {"dram_bytes": .., "samples": ..}}), rescaled to this run's sample count."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not os.path.exists(p):
-        return None
-    return json.load(open(p)).get(kernel)
+    (profiles/r02_traffic.json: {entry point: {"dram_bytes": .., "samples": ..}}), rescaled to this run's sample count."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            hit = json.load(open(p)).get(kernel)
+            if hit:
+                return hit
+    return None
 
 
 def peaks():
