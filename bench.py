@@ -932,6 +932,8 @@ def encoder_report(wl, per_kernel, ALGO, n_all, n_live, hbm, l2_gbs, device):
         srt = torch.sort(sec, dim=-1).values
         distinct = 1 + (srt[..., 1:] != srt[..., :-1]).sum(-1)          # [L, warps, 4] sectors per warp-wide gather
         sectors = float(distinct.sum()) / m                                  # sectors per sample (<= 4 L)
+        ln = torch.sort(sec >> 2, dim=-1).values                              # 128-byte lines: 16 entries each
+        lines = float((1 + (ln[..., 1:] != ln[..., :-1]).sum(-1)).sum()) / m     # L1 wavefronts per sample (<= 4 L)
     except Exception as e:      # diagnostic only
         sectors = None
     rep = {"kernel": enc_name, "ms_per_launch": round(enc["ms_per_launch"], 4), "samples_per_launch": n_enc,
@@ -947,6 +949,15 @@ def encoder_report(wl, per_kernel, ALGO, n_all, n_live, hbm, l2_gbs, device):
     if sectors is not None:
         sec_gbs = sectors * 32 * n_enc / t_enc / 1e9
         rep.update(l2_sectors_per_sample=sectors, l2_sector_GBps=sec_gbs, l2_sector_frac=sec_gbs / l2_gbs)
+        # the tighter bound of a scattered gather: the L1/LSU processes ONE 128-byte line (wavefront) per cycle per SM whatever
+        # the bytes used from it (B300_MICROARCH.md: rt_L1tex_wf ~ 1.0 cyc/wf); a warp-wide 8-byte gather that touches k distinct
+        # lines costs k cycles of that pipe.  peak = 148 SMs x SM clock.
+        clk = 1.965e9
+        wf_rate = lines * n_enc / t_enc
+        rep.update(l1_wavefronts_per_sample=lines, l1_wavefront_rate_G_per_s=wf_rate / 1e9, l1_wavefront_peak_G_per_s=148 * clk / 1e9,
+                   l1_wavefront_frac=wf_rate / (148 * clk),
+                   l1_note="distinct 128-byte lines per warp-wide vertex gather (this batch's lattice indices), one L1/LSU wavefront per "
+                           "cycle per SM at 1965 MHz: the bound the kernel actually runs against (ncu: l1tex 69 %, lts 49 %, dram 4 %)")
     return rep
 
 

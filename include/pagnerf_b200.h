@@ -94,6 +94,19 @@ int pag_voxel_filter_count(const float* nug_depth, const int64_t* nug_offsets, i
 int pag_voxel_emit_dyn(const float* origins, const float* dirs, const int64_t* nug_ridx, const float* nug_depth, const int32_t* rel,
                        const int64_t* nug_offsets, const int64_t* offsets, int64_t N, int64_t K_max, int S, uint32_t seed,
                        const uint32_t* seed_dev, int64_t* ridx, float* samples, float* depths, float* deltas, void* stream);
+/* One-traversal variant of the sync-free voxel chain: the raytrace stages every ray's nuggets in its own row of
+ * stage_depth f32[N, stage_cap, 2] (stage_cap >= 3 * 2^level - 2) while counting; filter and emit read the rows (rel i32[N, stage_cap]).
+ * With slot_counts (and level >= 2) the traversal is split 64 ways per ray: thread (ray, i1, i2) walks the i2-th child of the i1-th
+ * child of the root in the ray's own visiting order; a count pass and a write pass, both 64x wider than the per-ray DFS. */
+int pag_raytrace_stage(const uint8_t* octree, const int32_t* prefix, const float* origins, const float* dirs, int64_t N, int level,
+                       int64_t stage_cap, int32_t* counts, int64_t* nug_offsets, float* stage_depth, int32_t* slot_counts /* i32[N*64], nullable */,
+                       void* stream);
+int pag_voxel_filter_count_staged(const float* stage_depth, const int64_t* nug_offsets, int64_t N, int64_t stage_cap, int S, uint32_t seed,
+                                  const uint32_t* seed_dev, float max_travel, int apply_filter, int32_t* rel, int32_t* counts,
+                                  int64_t* offsets, void* stream);
+int pag_voxel_emit_staged(const float* origins, const float* dirs, const float* stage_depth, const int32_t* rel, const int64_t* nug_offsets,
+                          const int64_t* offsets, int64_t N, int64_t stage_cap, int S, uint32_t seed, const uint32_t* seed_dev,
+                          int64_t* ridx, float* samples, float* depths, float* deltas, void* stream);
 /* Octree rebuild on the device (prune(): pc_nerf/panoptic_delta_nef.py:63-104, pc_nerf/panoptic_nef.py:207-237 -> kaolin
  * unbatched_points_to_octree + wisp OctreeAS.init): from the dense leaf-occupancy mask u8[8^level] in Morton
  * order to the SPC layout the marcher consumes.  Workspaces and outputs hold F = (8^(level+1)-1)/7 entries (see csrc/octree.cu);

@@ -373,12 +373,24 @@ __device__ __forceinline__ float ray_aabb(const RayCtx& r, float vcx, float vcy,
     return entry;
 }
 
-template <bool EMIT>
+// MODE 0: count nuggets per ray; 1: emit (ridx, pidx, depth) at the packed offsets of a previous count + scan; 2: ONE pass for the
+// sync-free fused trace -- depth pairs go to the ray's own staging row depth[ray * stage_cap + n] and the count is written too
+// (no second traversal; the filter / emit kernels read the staged rows)
+// SPLIT (staged modes, level >= 2): 64 threads per ray.  Thread (ray, i1, i2) walks only the i1-th child of the root and the i2-th
+// child of that node in the ray's own visiting order (children j = code ^ i) and everything below; the 64 partial traversals in
+// (i1, i2) order ARE the ray's DFS order, so per-thread counts + a prefix over the ray's 64 slots give every nugget its place in
+// the ray's staging row.  The sequential per-ray DFS is latency bound (dependent octree-byte / prefix loads, two warps per SM at
+// 16 k rays): 64-way splitting turns 0.42 ms into two short passes.
+template <int MODE, bool SPLIT>
 __global__ void raytrace_kernel(const uint8_t* __restrict__ octree, const int* __restrict__ prefix,
                                 const float* __restrict__ org, const float* __restrict__ dir, int64_t N, int level,
                                 int* __restrict__ counts, const int64_t* __restrict__ offsets,
-                                int64_t* __restrict__ ridx, int64_t* __restrict__ pidx, float* __restrict__ depth) {
-    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                int64_t* __restrict__ ridx, int64_t* __restrict__ pidx, float* __restrict__ depth, int64_t stage_cap,
+                                int* __restrict__ counts64) {
+    constexpr bool EMIT = MODE != 0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ray = SPLIT ? (tid >> 6) : tid;
+    const int sub = SPLIT ? (int)(tid & 63) : 0;
     if (ray >= N) return;
     RayCtx r;
     r.ox = org[3 * ray]; r.oy = org[3 * ray + 1]; r.oz = org[3 * ray + 2];
@@ -389,26 +401,31 @@ __global__ void raytrace_kernel(const uint8_t* __restrict__ octree, const int* _
     r.sz = (__float_as_uint(r.dz) >> 31) ? 1.f : -1.f;
     const float ax = __fmaf_rn(0.5f, r.ox, 0.5f), ay = __fmaf_rn(0.5f, r.oy, 0.5f), az = __fmaf_rn(0.5f, r.oz, 0.5f);
 
-    int64_t out = EMIT ? offsets[ray] : 0;
+    int64_t out = MODE == 1 ? offsets[ray] : (MODE == 2 ? ray * stage_cap : 0);
+    if (SPLIT && MODE == 2) {      // this thread's place in the ray's row: nuggets of the slots visited before it
+        const int* c = counts64 + ray * 64;
+        for (int k = 0; k < sub; ++k) out += __ldg(c + k);
+    }
     int n = 0;
     int node[PAG_MAX_LEVEL + 1], px[PAG_MAX_LEVEL + 1], py[PAG_MAX_LEVEL + 1], pz[PAG_MAX_LEVEL + 1];
-    uint8_t byte[PAG_MAX_LEVEL + 1], code[PAG_MAX_LEVEL + 1], iter[PAG_MAX_LEVEL + 1];
+    uint8_t byte[PAG_MAX_LEVEL + 1], code[PAG_MAX_LEVEL + 1], iter[PAG_MAX_LEVEL + 1], lim[PAG_MAX_LEVEL + 1];
     int l = -1;
     {   // root
         float ex;
         const float entry = ray_aabb(r, 0.f, 0.f, 0.f, 1.f, &ex);
         if (level == 0) {
             if (entry > 0.f) {
-                if (EMIT) { ridx[out] = ray; pidx[out] = 0; depth[2 * out] = entry; depth[2 * out + 1] = ex; ++out; }
+                if (EMIT) { if (MODE == 1) { ridx[out] = ray; pidx[out] = 0; } depth[2 * out] = entry; depth[2 * out + 1] = ex; ++out; }
                 ++n;
             }
         } else if (entry != 0.f) {
-            l = 0; node[0] = 0; px[0] = py[0] = pz[0] = 0; byte[0] = __ldg(octree); iter[0] = 0;
+            l = 0; node[0] = 0; px[0] = py[0] = pz[0] = 0; byte[0] = __ldg(octree);
+            iter[0] = SPLIT ? (uint8_t)(sub >> 3) : 0; lim[0] = SPLIT ? (uint8_t)((sub >> 3) + 1) : 8;
             code[0] = (uint8_t)(((ax > 0.5f) ? 4 : 0) | ((ay > 0.5f) ? 2 : 0) | ((az > 0.5f) ? 1 : 0));
         }
     }
     while (l >= 0) {
-        if (iter[l] == 8) { --l; continue; }
+        if (iter[l] == lim[l]) { --l; continue; }
         const uint32_t i = iter[l]++;
         const uint32_t j = code[l] ^ i;
         const uint32_t b = byte[l];
@@ -424,14 +441,15 @@ __global__ void raytrace_kernel(const uint8_t* __restrict__ octree, const int* _
             float ex;
             const float entry = ray_aabb(r, vcx, vcy, vcz, rad, &ex);
             if (entry > 0.f) {
-                if (EMIT) { ridx[out] = ray; pidx[out] = child; depth[2 * out] = entry; depth[2 * out + 1] = ex; ++out; }
+                if (EMIT) { if (MODE == 1) { ridx[out] = ray; pidx[out] = child; } depth[2 * out] = entry; depth[2 * out + 1] = ex; ++out; }
                 ++n;
             }
         } else {
             const float entry = ray_aabb(r, vcx, vcy, vcz, rad, nullptr);
             if (entry != 0.f) {
                 l = cl; node[l] = child; px[l] = cx; py[l] = cy; pz[l] = cz;
-                byte[l] = __ldg(octree + child); iter[l] = 0;
+                byte[l] = __ldg(octree + child);
+                iter[l] = (SPLIT && l == 1) ? (uint8_t)(sub & 7) : 0; lim[l] = (SPLIT && l == 1) ? (uint8_t)((sub & 7) + 1) : 8;
                 const float bx = __fmul_rn(rad, (float)cx + 0.5f), by = __fmul_rn(rad, (float)cy + 0.5f),
                             bz = __fmul_rn(rad, (float)cz + 0.5f);
                 code[l] = (uint8_t)(((__fsub_rn(ax, bx) > 0.f) ? 4 : 0) | ((__fsub_rn(ay, by) > 0.f) ? 2 : 0) |
@@ -439,7 +457,19 @@ __global__ void raytrace_kernel(const uint8_t* __restrict__ octree, const int* _
             }
         }
     }
-    if (!EMIT) counts[ray] = n;
+    if (SPLIT) { if (MODE == 0) counts64[tid] = n; }
+    else if (MODE != 1) counts[ray] = n;
+}
+
+// per-ray totals of the 64 slot counts
+__global__ void raytrace_totals_kernel(const int* __restrict__ counts64, int64_t N, int* __restrict__ counts) {
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= N) return;
+    const int4* c = reinterpret_cast<const int4*>(counts64 + ray * 64);
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const int4 v = __ldg(c + k); s += v.x + v.y + v.z + v.w; }
+    counts[ray] = s;
 }
 
 __device__ __forceinline__ float voxel_sample_depth(int64_t k, int s, int S, float t0, float t1,
@@ -487,30 +517,66 @@ __global__ void max_travel_mask_kernel(const int64_t* __restrict__ ridx, const f
 // S samples of every kept nugget straight into the packed (ray-sorted) sample list the encoders / decoders read.  The jitter
 // index stays k * S + s with k the UNFILTERED nugget index, so positions are bit-identical to pag_voxel_samples + filter.
 // warp per ray: rel[k] = rank of nugget k among the ray's kept nuggets (-1 = dropped); counts[ray] = kept * S
+// stage_cap > 0: depth / rel are per-ray staging rows (entry j of ray r at r * stage_cap + j) instead of packed arrays
 __global__ void voxel_filter_kernel(const float* __restrict__ depth, const int64_t* __restrict__ nug_off, int64_t N, int S,
                                     uint32_t seed, const uint32_t* __restrict__ seed_dev, float max_travel, int apply_filter,
-                                    int* __restrict__ rel, int* __restrict__ counts) {
+                                    int* __restrict__ rel, int* __restrict__ counts, int64_t stage_cap) {
     if (seed_dev) seed = __ldg(seed_dev);
     const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (ray >= N) return;
     const int64_t k0 = nug_off[ray], k1 = nug_off[ray + 1];
+    const int64_t shift = stage_cap > 0 ? ray * stage_cap - k0 : 0;      // storage index = k + shift
     int kept = 0;
     if (k1 > k0) {
-        const float first = voxel_sample_depth(k0, 0, S, depth[2 * k0], depth[2 * k0 + 1], nullptr, seed);
+        const float first = voxel_sample_depth(k0, 0, S, depth[2 * (k0 + shift)], depth[2 * (k0 + shift) + 1], nullptr, seed);
         for (int64_t kb = k0; kb < k1; kb += 32) {
             const int64_t k = kb + lane;
             bool keep = false;
             if (k < k1) {
-                const float d0 = voxel_sample_depth(k, 0, S, depth[2 * k], depth[2 * k + 1], nullptr, seed);
+                const float d0 = voxel_sample_depth(k, 0, S, depth[2 * (k + shift)], depth[2 * (k + shift) + 1], nullptr, seed);
                 keep = !apply_filter || (__fsub_rn(d0, first) < max_travel);
             }
             const unsigned b = __ballot_sync(0xffffffffu, keep);
-            if (k < k1) rel[k] = keep ? kept + __popc(b & ((1u << lane) - 1u)) : -1;
+            if (k < k1) rel[k + shift] = keep ? kept + __popc(b & ((1u << lane) - 1u)) : -1;
             kept += __popc(b);
         }
     }
     if (lane == 0) counts[ray] = kept * S;
+}
+
+// warp per ray over the staged rows: lanes = (nugget, sample) pairs of the ray; the ray's kept samples are contiguous in the packed
+// output, so the stores coalesce
+__global__ void voxel_emit_staged_kernel(const float* __restrict__ org, const float* __restrict__ dir, const float* __restrict__ depth,
+                                         const int* __restrict__ rel, const int64_t* __restrict__ nug_off, const int64_t* __restrict__ offsets,
+                                         int64_t N, int64_t stage_cap, int S, uint32_t seed, const uint32_t* __restrict__ seed_dev,
+                                         int64_t* __restrict__ ridx, float* __restrict__ samples, float* __restrict__ depths,
+                                         float* __restrict__ deltas) {
+    if (seed_dev) seed = __ldg(seed_dev);
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= N) return;
+    const int64_t k0 = nug_off[ray];
+    const int n = (int)(nug_off[ray + 1] - k0);
+    if (n == 0 || offsets[ray + 1] == offsets[ray]) return;
+    const float ox = org[3 * ray], oy = org[3 * ray + 1], oz = org[3 * ray + 2];
+    const float dx = dir[3 * ray], dy = dir[3 * ray + 1], dz = dir[3 * ray + 2];
+    const int64_t base = offsets[ray], row = ray * stage_cap;
+    for (int i = lane; i < n * S; i += 32) {
+        const int j = i / S, s = i - j * S;
+        const int r = rel[row + j];
+        if (r < 0) continue;
+        const float t0 = depth[2 * (row + j)], t1 = depth[2 * (row + j) + 1];
+        const float ds = voxel_sample_depth(k0 + j, s, S, t0, t1, nullptr, seed);
+        const float prev = (s == 0) ? t0 : voxel_sample_depth(k0 + j, s - 1, S, t0, t1, nullptr, seed);
+        const int64_t dst = base + (int64_t)r * S + s;
+        ridx[dst] = ray;
+        depths[dst] = ds;
+        deltas[dst] = __fsub_rn(ds, prev);
+        samples[3 * dst + 0] = __fadd_rn(ox, __fmul_rn(dx, ds));
+        samples[3 * dst + 1] = __fadd_rn(oy, __fmul_rn(dy, ds));
+        samples[3 * dst + 2] = __fadd_rn(oz, __fmul_rn(dz, ds));
+    }
 }
 
 // thread per (unfiltered nugget, sample): offsets = per-ray packed SAMPLE offsets of the kept nuggets
@@ -717,8 +783,8 @@ int pag_raytrace_count(const uint8_t* octree, const int32_t* prefix, const float
     if (level < 0 || level > PAG_MAX_LEVEL) return PAG_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (N > 0) {
-        raytrace_kernel<false><<<pag_grid(N, 128), 128, 0, st>>>(octree, prefix, origins, dirs, N, level, counts,
-                                                                nullptr, nullptr, nullptr, nullptr);
+        raytrace_kernel<0, false><<<pag_grid(N, 128), 128, 0, st>>>(octree, prefix, origins, dirs, N, level, counts,
+                                                                   nullptr, nullptr, nullptr, nullptr, 0, nullptr);
         PAG_LAUNCH_CHECK();
     }
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, offsets);
@@ -731,8 +797,8 @@ int pag_raytrace_emit(const uint8_t* octree, const int32_t* prefix, const float*
                       void* stream) {
     if (level < 0 || level > PAG_MAX_LEVEL) return PAG_ERR_ARG;
     if (N == 0) return PAG_OK;
-    raytrace_kernel<true><<<pag_grid(N, 128), 128, 0, (cudaStream_t)stream>>>(octree, prefix, origins, dirs, N, level,
-                                                                             nullptr, offsets, ridx, pidx, depth);
+    raytrace_kernel<1, false><<<pag_grid(N, 128), 128, 0, (cudaStream_t)stream>>>(octree, prefix, origins, dirs, N, level,
+                                                                                 nullptr, offsets, ridx, pidx, depth, 0, nullptr);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
@@ -765,7 +831,7 @@ int pag_voxel_filter_count(const float* nug_depth, const int64_t* nug_offsets, i
     if (S <= 0) return PAG_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (N > 0) {
-        voxel_filter_kernel<<<pag_grid(N * 32, 256), 256, 0, st>>>(nug_depth, nug_offsets, N, S, seed, seed_dev, max_travel, apply_filter, rel, counts);
+        voxel_filter_kernel<<<pag_grid(N * 32, 256), 256, 0, st>>>(nug_depth, nug_offsets, N, S, seed, seed_dev, max_travel, apply_filter, rel, counts, 0);
         PAG_LAUNCH_CHECK();
     }
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, offsets);
@@ -808,6 +874,58 @@ int pag_octree_from_mask(const uint8_t* mask, int level, int32_t* exists, uint8_
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(popc, inner, prefix64);      // entries beyond n_nodes are zero: harmless
     PAG_LAUNCH_CHECK();
     octree_build_finish_kernel<<<pag_grid(inner + 1, 256), 256, 0, st>>>(level, pos, prefix64, prefix, pyramid);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+
+// One-traversal variant for the fused trace: nuggets of ray r are staged in row r of stage_depth f32[N, stage_cap, 2] (stage_cap >= the
+// DDA worst case 3 * 2^level - 2), counts / nug_offsets as pag_raytrace_count; pag_voxel_filter_count_staged / pag_voxel_emit_staged
+// then read the rows (rel i32[N, stage_cap]).  Same nuggets, same order, same samples as the two-pass chain, one DFS per ray instead of two.
+int pag_raytrace_stage(const uint8_t* octree, const int32_t* prefix, const float* origins, const float* dirs, int64_t N, int level,
+                       int64_t stage_cap, int32_t* counts, int64_t* nug_offsets, float* stage_depth, int32_t* slot_counts, void* stream) {
+    if (level < 0 || level > PAG_MAX_LEVEL || stage_cap < 1) return PAG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 0 && level >= 2 && slot_counts) {
+        // 64 threads per ray (see raytrace_kernel<., true>): count per slot, per-ray totals, then the same walk again writing each
+        // slot's nuggets at its prefix inside the ray's row -- two short, wide passes instead of one long, narrow one
+        raytrace_kernel<0, true><<<pag_grid(N * 64, 128), 128, 0, st>>>(octree, prefix, origins, dirs, N, level, nullptr, nullptr, nullptr,
+                                                                       nullptr, nullptr, 0, slot_counts);
+        PAG_LAUNCH_CHECK();
+        raytrace_totals_kernel<<<pag_grid(N, 128), 128, 0, st>>>(slot_counts, N, counts);
+        PAG_LAUNCH_CHECK();
+        raytrace_kernel<2, true><<<pag_grid(N * 64, 128), 128, 0, st>>>(octree, prefix, origins, dirs, N, level, nullptr, nullptr, nullptr,
+                                                                       nullptr, stage_depth, stage_cap, slot_counts);
+        PAG_LAUNCH_CHECK();
+    } else if (N > 0) {
+        raytrace_kernel<2, false><<<pag_grid(N, 64), 64, 0, st>>>(octree, prefix, origins, dirs, N, level, counts, nullptr, nullptr, nullptr,
+                                                                 stage_depth, stage_cap, nullptr);
+        PAG_LAUNCH_CHECK();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, nug_offsets);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_voxel_filter_count_staged(const float* stage_depth, const int64_t* nug_offsets, int64_t N, int64_t stage_cap, int S, uint32_t seed,
+                                  const uint32_t* seed_dev, float max_travel, int apply_filter, int32_t* rel, int32_t* counts,
+                                  int64_t* offsets, void* stream) {
+    if (S <= 0 || stage_cap < 1) return PAG_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 0) {
+        voxel_filter_kernel<<<pag_grid(N * 32, 256), 256, 0, st>>>(stage_depth, nug_offsets, N, S, seed, seed_dev, max_travel, apply_filter, rel,
+                                                                  counts, stage_cap);
+        PAG_LAUNCH_CHECK();
+    }
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts, N, offsets);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_voxel_emit_staged(const float* origins, const float* dirs, const float* stage_depth, const int32_t* rel, const int64_t* nug_offsets,
+                          const int64_t* offsets, int64_t N, int64_t stage_cap, int S, uint32_t seed, const uint32_t* seed_dev,
+                          int64_t* ridx, float* samples, float* depths, float* deltas, void* stream) {
+    if (S <= 0 || stage_cap < 1) return PAG_ERR_ARG;
+    if (N == 0) return PAG_OK;
+    voxel_emit_staged_kernel<<<pag_grid(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(origins, dirs, stage_depth, rel, nug_offsets, offsets, N,
+                                                                                     stage_cap, S, seed, seed_dev, ridx, samples, depths, deltas);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }

@@ -817,6 +817,30 @@ def test_voxel_device_side_march_bit_exact(cuda_lib, max_travel):
     assert torch.equal(s2[:M], samples.reshape(-1, 3)), "sample positions bit-exact"
     assert torch.equal(dp2[:M], depths.reshape(-1)) and torch.equal(dl2[:M], deltas.reshape(-1))
     assert torch.equal(offsets, ops.ray_offsets(ridx, N) * S)
+    # the one-traversal staged chain the fused trace uses: same counts, same packed samples
+    cap = 3 * (1 << level) - 2
+    counts3 = torch.empty(N, dtype=torch.int32, device=DEV)
+    nug_off3 = torch.empty(N + 1, dtype=torch.int64, device=DEV)
+    stage = torch.full((N * cap, 2), float('nan'), device=DEV)
+    call("pag_raytrace_stage", ptr(blas.octree), ptr(blas.prefix), ptr(o), ptr(d), N, level, cap, ptr(counts3), ptr(nug_off3), ptr(stage), None)
+    assert torch.equal(nug_off3, nug_off)
+    # ... and its 64-way split (thread per (ray, child of root, grandchild)): identical rows
+    stage64 = torch.full((N * cap, 2), float('nan'), device=DEV)
+    slots = torch.empty(N * 64, dtype=torch.int32, device=DEV)
+    nug_off4 = torch.empty(N + 1, dtype=torch.int64, device=DEV)
+    call("pag_raytrace_stage", ptr(blas.octree), ptr(blas.prefix), ptr(o), ptr(d), N, level, cap, ptr(counts3), ptr(nug_off4), ptr(stage64), ptr(slots))
+    assert torch.equal(nug_off4, nug_off)
+    assert torch.equal(torch.nan_to_num(stage64, nan=-7.0), torch.nan_to_num(stage, nan=-7.0)), "split traversal == per-ray DFS, bit for bit"
+    rel3 = torch.empty(N * cap, dtype=torch.int32, device=DEV)
+    offsets3 = torch.empty(N + 1, dtype=torch.int64, device=DEV)
+    call("pag_voxel_filter_count_staged", ptr(stage), ptr(nug_off3), N, cap, S, seed, None, float(max_travel or 0.0), int(max_travel is not None),
+         ptr(rel3), ptr(counts3), ptr(offsets3))
+    assert torch.equal(offsets3, offsets)
+    r3 = torch.full((Kmax * S,), -1, dtype=torch.int64, device=DEV)
+    s3 = torch.zeros(Kmax * S, 3, device=DEV); dp3 = torch.zeros(Kmax * S, device=DEV); dl3 = torch.zeros(Kmax * S, device=DEV)
+    call("pag_voxel_emit_staged", ptr(o), ptr(d), ptr(stage), ptr(rel3), ptr(nug_off3), ptr(offsets3), N, cap, S, seed, None,
+         ptr(r3), ptr(s3), ptr(dp3), ptr(dl3))
+    assert torch.equal(r3[:M], r2[:M]) and torch.equal(s3[:M], s2[:M]) and torch.equal(dp3[:M], dp2[:M]) and torch.equal(dl3[:M], dl2[:M])
 
 
 @pytest.mark.parametrize("with_pose_grad", [False, True])
