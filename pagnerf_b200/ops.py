@@ -358,6 +358,8 @@ class DecodeDCFn(Function):
                  VIEW_DIM, ptr(gs), ptr(gr), ptr(gf), ptr(gd))
         if need_d:
             gd = gd.view(-1, ctx.S, 3).sum(1) if ctx.S > 1 else gd
+        if gr is None:      # the colour decoder was not evaluated / got no gradient: its parameters receive None, like autograd's
+            grads[4:10] = [None] * 6
         return (gf, None, gd, None, None, None, *grads)
 
 
