@@ -332,6 +332,17 @@ int pag_symm_barrier(float* const* peers, int64_t flag_offset, int* epoch, int r
 int pag_allreduce_symm(float* multicast, float* const* peers, int rank, int world, int64_t offset, int64_t n, float mult, int max_ctas,
                        void* stream);
 
+/* ---- instance loss with linear assignment, on the device ----
+ * Replaces LinAssignmentThingsLoss (loss/lin_assignment_things.py:13-89, called at pc_nerf/trainer.py:484-520: Python loops over the
+ * labels with a .cpu() each, scipy.optimize.linear_sum_assignment on the host, utils/outlier_rejection.py:8-52 id-range rejection):
+ * sorted unique labels + per-ray ranks, label x id cost matrix, shortest-augmenting-path assignment (one CTA per image), virtual
+ * labels, arg-max check and the NLL -- five launches, no host synchronisation.  Workspace shapes in csrc/loss.cu. */
+int pag_inst_assignment_loss_fwd(const float* p, const int64_t* gt, const uint8_t* stuff, const float* points, int64_t B, int64_t R, int C,
+                                 float frame_min_length, int max_num_inst_at_x, int id_margin, int32_t* labels, int32_t* n_labels, int32_t* rank,
+                                 float* csum, float* cnt, float* xsum, int32_t* assign, int32_t* virt, int32_t* flag, float* loss, void* stream);
+int pag_inst_assignment_loss_bwd(const float* p, const int32_t* virt, const int32_t* flag, const float* g_loss, int64_t B, int64_t R, int C,
+                                 float* gp, void* stream);
+
 /* ---- fused multi-tensor Adam (BASELINE config 4: "+ Adam"; SURVEY 8e "a single fused unscale + Adam kernel") ----
  * Replaces torch.optim.Adam.step() as the reference's trainer runs it (pc_nerf/trainer.py:229-300 parameter groups, :590 step;
  * configs/bup20/best.yaml:114 optimizer_type adam): n_tensors <= 48 fp32 tensors in one launch, host arrays of device pointers,

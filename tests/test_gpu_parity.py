@@ -1097,3 +1097,50 @@ def test_full_size_step_on_a_dirty_allocator(cuda_lib):
             for n, g in grads.items():
                 assert_close_norm(g, ref[n], rel_l2=1e-4, max_frac=1e-3, msg=f"rep {rep} vs rep 0: {n}")
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------
+# device-side instance loss with linear assignment (loss/lin_assignment_things.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,R,outlier", [(20, 257, False), (200, 1024, False), (200, 4096, True), (8, 64, False)])
+def test_lin_assignment_things_loss_matches_oracle(cuda_lib, C, R, outlier):
+    from oracle.losses import lin_assignment_things_loss
+    from pagnerf_b200.loss import LinAssignmentThingsLoss
+    gen = torch.Generator().manual_seed(C + R)
+    B = 3
+    p = torch.softmax(torch.randn(B, R, C, generator=gen) * 2.0, -1)
+    n_inst = [min(C + 5, 30), 5, 1]                                       # more labels than ids in image 0 when C is small
+    gt = torch.stack([torch.randint(0, n + 1, (R,), generator=gen) * 7 for n in n_inst])      # ids 0, 7, 14, ... (0 = no instance)
+    gt[2, : R // 2] = 0
+    stuff = torch.rand(B, R, generator=gen) < 0.3
+    pts = torch.rand(B, R, 3, generator=gen) * 2 - 1 if outlier else None
+    pr = p.clone().requires_grad_(True)
+    ref, virt_ref = lin_assignment_things_loss(pr, gt, stuff, pts)
+    w = torch.rand(B, R, generator=gen)
+    (ref * w).sum().backward()
+    loss_fn = LinAssignmentThingsLoss(outlier_rejection=outlier)
+    pd = p.clone().to(DEV).requires_grad_(True)
+    out = loss_fn(pd, gt.to(DEV), stuff.to(DEV), pts.to(DEV) if outlier else None)
+    assert torch.equal(loss_fn.last_virtual_labels.cpu().long(), virt_ref), "virtual labels == scipy's assignment"
+    assert_close(out, ref.detach(), rtol=1e-5, atol_scale=1e-6, msg="loss")
+    (out * w.to(DEV)).sum().backward()
+    assert_close(pd.grad, pr.grad, rtol=1e-5, atol_scale=1e-6, msg="grad probabilities")
+
+
+def test_lin_assignment_no_wrong_pixel_gives_zero_loss(cuda_lib):
+    """An image whose arg-max prediction already equals the virtual labels contributes no loss (:84)."""
+    from pagnerf_b200.loss import LinAssignmentThingsLoss
+    B, R, C = 2, 128, 10
+    gt = torch.zeros(B, R, dtype=torch.int64)
+    gt[0, :40], gt[0, 40:90] = 3, 9            # two instances in image 0; image 1 is all stuff
+    stuff = gt == 0
+    p = torch.full((B, R, C), 0.01)
+    p[0, :40, 5], p[0, 40:90, 2] = 0.9, 0.9    # confident, consistent ids: the assignment maps 3 -> id 5, 9 -> id 2
+    p[0, 90:, 0], p[1, :, 0] = 0.9, 0.9
+    p = p / p.sum(-1, keepdim=True)
+    out = LinAssignmentThingsLoss()(p.to(DEV), gt.to(DEV), stuff.to(DEV))
+    assert float(out.abs().max()) == 0.0
+    p[0, 0, 5], p[0, 0, 7] = 0.01, 0.9         # one wrong pixel: the whole image 0 is trained, image 1 still is not
+    p = p / p.sum(-1, keepdim=True)
+    out = LinAssignmentThingsLoss()(p.to(DEV), gt.to(DEV), stuff.to(DEV))
+    assert float(out[0].min()) > 0.0 and float(out[1].abs().max()) == 0.0

@@ -241,3 +241,24 @@ def test_pose_oracle_properties():
     q = p.clone().requires_grad_(True)
     bo, bd = torch.randn(10, 3, generator=gen, dtype=torch.float64), torch.randn(10, 3, generator=gen, dtype=torch.float64)
     assert torch.autograd.gradcheck(lambda z: pose.transform_rays(z, torch.tensor([1, 4]), bo, bd), (q,), atol=1e-6)
+
+
+def test_loss_oracle_basics():
+    """oracle/losses.py (the checker of csrc/loss.cu): consistent predictions give zero loss, one wrong pixel trains the whole image,
+    labels beyond the id table fall back to id 1 (loss/lin_assignment_things.py:31,48-55,84)."""
+    import torch
+    from oracle.losses import lin_assignment_things_loss, virtual_labels
+    R, C = 64, 6
+    gt = torch.zeros(1, R, dtype=torch.int64)
+    gt[0, :20], gt[0, 20:40] = 4, 11
+    p = torch.full((1, R, C), 0.02)
+    p[0, :20, 3], p[0, 20:40, 1], p[0, 40:, 0] = 0.9, 0.9, 0.9
+    p = p / p.sum(-1, keepdim=True)
+    loss, virt = lin_assignment_things_loss(p, gt, gt == 0)
+    assert float(loss.abs().max()) == 0.0 and virt[0, 0] == 3 and virt[0, 25] == 1 and virt[0, 50] == 0
+    p[0, 0, 3], p[0, 0, 5] = 0.02, 0.9
+    loss, _ = lin_assignment_things_loss(p / p.sum(-1, keepdim=True), gt, gt == 0)
+    assert float(loss.min()) > 0.0
+    many = torch.arange(1, 9)                      # 8 labels, 5 ids: the 3 largest labels are not assigned
+    v = virtual_labels(torch.softmax(torch.randn(8, C), -1), many)
+    assert (v[5:] == 1).all() and sorted(v[:5].tolist()) == [1, 2, 3, 4, 5]
