@@ -160,7 +160,12 @@ def nef_kwargs(cfg):
 
 
 def loss_fn(rb_rgb, rb_sem, rb_inst, t_rgb, t_sem, t_inst):
-    """rgb L1 x10 + semantic NLL x0.1 + instance NLL (reference pc_nerf/trainer.py:442-480, log(x + 1e-27) :459)."""
+    """rgb L1 x10 + semantic NLL x0.1 + instance NLL (reference pc_nerf/trainer.py:442-480, log(x + 1e-27) :459).  On CUDA tensors
+    the three terms and their gradients are one kernel each way (pagnerf_b200.loss.panoptic_loss); the torch formulation below is
+    what it is checked against (tests/test_gpu_parity.py::test_fused_panoptic_loss) and what the CPU reference arm runs."""
+    if rb_rgb.is_cuda and os.environ.get("BENCH_TORCH_LOSS") != "1":
+        from pagnerf_b200.loss import panoptic_loss
+        return panoptic_loss(rb_rgb, rb_sem, rb_inst, t_rgb, t_sem, t_inst, 10.0, 0.1, 1.0, 1e-27)
     l = 10.0 * torch.abs(rb_rgb - t_rgb).mean()
     # nll_loss(log(p + eps), t) == -mean(log(p[i, t_i] + eps)): same value and gradient, but the log / its backward touch N
     # entries instead of N x C, and torch's single-block nll_loss reduction kernels (20 us each at N = 16384) are avoided --

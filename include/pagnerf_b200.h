@@ -343,6 +343,16 @@ int pag_inst_assignment_loss_fwd(const float* p, const int64_t* gt, const uint8_
 int pag_inst_assignment_loss_bwd(const float* p, const int32_t* virt, const int32_t* flag, const float* g_loss, int64_t B, int64_t R, int C,
                                  float* gp, void* stream);
 
+/* Photometric + panoptic NLL loss of a training step (pc_nerf/trainer.py:442-480: L1 rgb, NLL of log(p + 1e-27) on the composited
+ * semantic / instance probabilities) as one forward and one backward launch instead of ~20 torch kernels.
+ * partials f32[>= 592], ticket u32[1] zero on entry (left zero), loss f32[1]; g_loss f32[1] on the device. */
+int pag_panoptic_loss_fwd(const float* rgb, const float* sem, const float* inst, const float* t_rgb, const int64_t* t_sem, const int64_t* t_inst,
+                          int64_t N, int Cs, int Ci, float w_rgb, float w_sem, float w_inst, float eps, float* partials, uint32_t* ticket,
+                          float* loss, void* stream);
+int pag_panoptic_loss_bwd(const float* rgb, const float* sem, const float* inst, const float* t_rgb, const int64_t* t_sem, const int64_t* t_inst,
+                          int64_t N, int Cs, int Ci, float w_rgb, float w_sem, float w_inst, float eps, const float* g_loss, float* g_rgb,
+                          float* g_sem, float* g_inst, void* stream);
+
 /* ---- fused multi-tensor Adam (BASELINE config 4: "+ Adam"; SURVEY 8e "a single fused unscale + Adam kernel") ----
  * Replaces torch.optim.Adam.step() as the reference's trainer runs it (pc_nerf/trainer.py:229-300 parameter groups, :590 step;
  * configs/bup20/best.yaml:114 optimizer_type adam): n_tensors <= 48 fp32 tensors in one launch, host arrays of device pointers,

@@ -221,7 +221,93 @@ __global__ void inst_nll_bwd_kernel(const float* __restrict__ p, const int* __re
     if (vl >= 0 && flag[w / R]) gp[w * C + vl] = -g[w] / (p[w * C + vl] + 1e-27f);
 }
 
+// ---------------------------------------------------------------------------------------------
+// photometric + panoptic NLL loss of a training step in one launch (and one for its gradients)
+// ---------------------------------------------------------------------------------------------
+// loss = w_rgb * mean |rgb - t_rgb| + w_sem * mean -log(sem[n, t_sem[n]] + eps) + w_inst * mean -log(inst[n, t_inst[n]] + eps)
+// (pc_nerf/trainer.py:442-480: L1 rgb, NLL of log(p + 1e-27) for the composited semantic / instance probabilities).  As torch ops
+// this is ~20 launches of a few microseconds each between the forward and the backward of a 1.2 ms step.
+__global__ void __launch_bounds__(256) panoptic_loss_fwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sem, const float* __restrict__ inst,
+                                                                const float* __restrict__ t_rgb, const int64_t* __restrict__ t_sem,
+                                                                const int64_t* __restrict__ t_inst, int64_t N, int Cs, int Ci, float w_rgb, float w_sem,
+                                                                float w_inst, float eps, float* __restrict__ partials, unsigned* __restrict__ ticket,
+                                                                float* __restrict__ loss) {
+    float acc = 0.f;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        if (rgb) acc += w_rgb * (fabsf(rgb[3 * n] - t_rgb[3 * n]) + fabsf(rgb[3 * n + 1] - t_rgb[3 * n + 1]) + fabsf(rgb[3 * n + 2] - t_rgb[3 * n + 2])) * (1.f / 3.f);
+        if (sem) acc -= w_sem * logf(sem[n * Cs + t_sem[n]] + eps);
+        if (inst) acc -= w_inst * logf(inst[n * Ci + t_inst[n]] + eps);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ float ws[8];
+    __shared__ bool last;
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += ws[k];
+        partials[blockIdx.x] = t;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {      // deterministic: the last block adds the partial sums in block order
+        __threadfence();
+        float t = 0.f;
+        for (unsigned k = 0; k < gridDim.x; ++k) t += *reinterpret_cast<volatile float*>(partials + k);
+        *loss = t / (float)N;
+        *ticket = 0u;
+    }
+}
+// warp per ray: the wide rows are written coalesced (zeros + the one non-zero of the NLL)
+__global__ void __launch_bounds__(256) panoptic_loss_bwd_kernel(const float* __restrict__ rgb, const float* __restrict__ sem, const float* __restrict__ inst,
+                                                                const float* __restrict__ t_rgb, const int64_t* __restrict__ t_sem,
+                                                                const int64_t* __restrict__ t_inst, int64_t N, int Cs, int Ci, float w_rgb, float w_sem,
+                                                                float w_inst, float eps, const float* __restrict__ g_loss, float* __restrict__ g_rgb,
+                                                                float* __restrict__ g_sem, float* __restrict__ g_inst) {
+    const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const float g = __ldg(g_loss) / (float)N;
+    if (g_rgb && lane < 3) {
+        const float d = rgb[3 * n + lane] - t_rgb[3 * n + lane];
+        g_rgb[3 * n + lane] = g * w_rgb * (1.f / 3.f) * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+    }
+    if (g_sem) {
+        const int t = (int)t_sem[n];
+        for (int c = lane; c < Cs; c += 32) g_sem[n * Cs + c] = (c == t) ? -g * w_sem / (sem[n * Cs + t] + eps) : 0.f;
+    }
+    if (g_inst) {
+        const int t = (int)t_inst[n];
+        for (int c = lane; c < Ci; c += 32) g_inst[n * Ci + c] = (c == t) ? -g * w_inst / (inst[n * Ci + t] + eps) : 0.f;
+    }
+}
+
 extern "C" {
+
+// rgb f32[N,3] / sem f32[N,Cs] / inst f32[N,Ci] (each nullable with its target); partials f32[>= 148*4], ticket u32[1] zero on entry
+// (left zero); loss f32[1].  Backward: g_loss f32[1] on the device; gradient tensors fully written (nullable per channel).
+int pag_panoptic_loss_fwd(const float* rgb, const float* sem, const float* inst, const float* t_rgb, const int64_t* t_sem, const int64_t* t_inst,
+                          int64_t N, int Cs, int Ci, float w_rgb, float w_sem, float w_inst, float eps, float* partials, uint32_t* ticket,
+                          float* loss, void* stream) {
+    if (N <= 0) return PAG_ERR_ARG;
+    int grid = (int)((N + 255) / 256);
+    if (grid > 148 * 4) grid = 148 * 4;
+    panoptic_loss_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rgb, sem, inst, t_rgb, t_sem, t_inst, N, Cs, Ci, w_rgb, w_sem, w_inst, eps,
+                                                                    partials, ticket, loss);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
+int pag_panoptic_loss_bwd(const float* rgb, const float* sem, const float* inst, const float* t_rgb, const int64_t* t_sem, const int64_t* t_inst,
+                          int64_t N, int Cs, int Ci, float w_rgb, float w_sem, float w_inst, float eps, const float* g_loss, float* g_rgb,
+                          float* g_sem, float* g_inst, void* stream) {
+    if (N <= 0) return PAG_ERR_ARG;
+    panoptic_loss_bwd_kernel<<<pag_grid(N * 32, 256), 256, 0, (cudaStream_t)stream>>>(rgb, sem, inst, t_rgb, t_sem, t_inst, N, Cs, Ci, w_rgb, w_sem,
+                                                                                     w_inst, eps, g_loss, g_rgb, g_sem, g_inst);
+    PAG_LAUNCH_CHECK();
+    return PAG_OK;
+}
 
 // p f32[B, R, C] probabilities, gt i64[B, R], stuff u8[B, R], points f32[B, R, 3] (nullable: no outlier rejection).
 // Workspaces (caller allocates; csum / cnt / xsum / flag zeroed): labels i32[B, C-1], n_labels i32[B], rank i32[B, R],

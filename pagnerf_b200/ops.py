@@ -747,7 +747,8 @@ COMPACT_LIVE = False
 # L2 persisting windows (north_star design constraint; opt-in, see DESIGN 4.1 for the measurement): during the forward each encoder's
 # stream marks ITS table as persisting, during the backward its gradient table; everything else streams through the L2
 L2_WINDOW = os.environ.get('PAGNERF_L2_WINDOW', '0') == '1'
-SYMM_CHUNKS = int(os.environ.get('PAGNERF_SYMM_CHUNKS', '1'))      # level ranges of the colour-table scatter / exchange pipeline ('symm' transport)
+SYMM_CHUNKS = int(os.environ.get('PAGNERF_SYMM_CHUNKS', '1'))
+SYMM_SPLIT_LEVEL = int(os.environ.get('PAGNERF_SYMM_SPLIT_LEVEL', '0'))      # level ranges of the colour-table scatter / exchange pipeline ('symm' transport)
 
 
 def _l2_window(t, hit_ratio=1.0):
@@ -1144,10 +1145,14 @@ class FusedTraceFn(Function):
             # while the next one is being scattered.  Measured at 2 GPUs: 1 / 2 / 3 ranges = 1.53 / 1.51 / 1.55 ms (the extra passes
             # over the samples eat the overlap), so the default stays 1.
             nchunk = SYMM_CHUNKS if (sync and symm is not None and (smask & 2) and img and kind == 'permuto' and L % SYMM_CHUNKS == 0) else 1
-            step_l = L // nchunk
+            bounds = [(c * (L // nchunk), (c + 1) * (L // nchunk)) for c in range(nchunk)]
+            if sync and symm is not None and (smask & 2) and img and kind == 'permuto' and 0 < SYMM_SPLIT_LEVEL < L:
+                # uneven two-way split: the big first range leaves while the small last one is scattered, so that only a small
+                # exchange is left exposed at the end of the step
+                bounds, nchunk = [(0, SYMM_SPLIT_LEVEL), (SYMM_SPLIT_LEVEL, L)], 2
             per_level = tb.numel() // L
             for c in range(nchunk):
-                l0, l1 = c * step_l, (c + 1) * step_l
+                l0, l1 = bounds[c]
                 _enc_bwd(kind, cfg['grid'], samples, Mmax, m_dev, ph, tb, g_feats, scale, g_table, g_pos, img, l0, l1 if nchunk > 1 else None)
                 if sync and (symm is not None or (smask & 2)):
                     comm = st['comm'] = _side_stream(dev, 1)

@@ -1144,3 +1144,33 @@ def test_lin_assignment_no_wrong_pixel_gives_zero_loss(cuda_lib):
     p = p / p.sum(-1, keepdim=True)
     out = LinAssignmentThingsLoss()(p.to(DEV), gt.to(DEV), stuff.to(DEV))
     assert float(out[0].min()) > 0.0 and float(out[1].abs().max()) == 0.0
+
+
+def test_fused_panoptic_loss(cuda_lib):
+    """pagnerf_b200.loss.panoptic_loss (one launch each way) == the torch formulation of the step's loss (bench.loss_fn), value and
+    gradients; channels may be absent; the self-resetting scratch survives repeated calls."""
+    import bench, os
+    from pagnerf_b200.loss import panoptic_loss
+    gen = torch.Generator().manual_seed(0)
+    N, Cs, Ci = 3001, 6, 200
+    rgb = torch.rand(N, 3, generator=gen); sem = torch.softmax(torch.randn(N, Cs, generator=gen), -1) * torch.rand(N, 1, generator=gen)
+    inst = torch.softmax(torch.randn(N, Ci, generator=gen), -1) * torch.rand(N, 1, generator=gen)
+    inst[5] = 0.0                                       # a ray without samples: log(0 + 1e-27)
+    tr, ts, ti = torch.rand(N, 3, generator=gen), torch.randint(0, Cs, (N,), generator=gen), torch.randint(0, Ci, (N,), generator=gen)
+    os.environ["BENCH_TORCH_LOSS"] = "1"
+    try:
+        a = [t.clone().requires_grad_(True) for t in (rgb, sem, inst)]
+        ref = bench.loss_fn(*a, tr, ts, ti)
+        (ref * 3.0).backward()
+    finally:
+        del os.environ["BENCH_TORCH_LOSS"]
+    for rep in range(2):
+        b = [t.clone().to(DEV).requires_grad_(True) for t in (rgb, sem, inst)]
+        out = panoptic_loss(*b, tr.to(DEV), ts.to(DEV), ti.to(DEV), 10.0, 0.1, 1.0, 1e-27)
+        (out * 3.0).backward()
+        assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
+        for x, y, name in zip(b, a, ("rgb", "sem", "inst")):
+            assert_close(x.grad, y.grad, rtol=1e-5, atol_scale=1e-7, msg="grad " + name)
+    only = panoptic_loss(None, b[1].detach().requires_grad_(True), None, None, ts.to(DEV), None, 0.0, 1.0, 0.0)
+    exp = -torch.log(sem.gather(1, ts[:, None]) + 1e-27).mean()
+    assert abs(float(only) - float(exp)) <= 1e-5 * abs(float(exp))

@@ -1,6 +1,5 @@
 N=${1:-2}
-PAGNERF_SYMM_CHUNKS=2 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/mg_check.py 2>&1 | grep -E "transport|MG_CHECK|rank|Error|error" | head -20
-for v in ${SWEEP:-"PAGNERF_SYMM_CHUNKS=1" "PAGNERF_SYMM_CHUNKS=2" "PAGNERF_SYMM_CHUNKS=3"}; do
+for v in ${SWEEP:-"PAGNERF_SYMM_SPLIT_LEVEL=18" "PAGNERF_SYMM_SPLIT_LEVEL=21"}; do
 echo "== $v"
 env $v PAGNERF_GRAD_TRANSPORT=symm timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 50 --warmup 5 --no-cpu-baseline 2> gpurun_out/mg.err | python -c "
 import sys, json
