@@ -23,10 +23,14 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+LAST_BUILD = None
+
+
 def build(force=False, verbose=False, extra_flags=(), tag=""):
     """tag / extra_flags: an instrumented variant (e.g. tag='_dbg', extra_flags=['-DPAG_PHASE_TIMING']) built beside the
     product library as libpagnerf_b200<tag>.so; select it at load time with PAGNERF_B200_LIB=<path>."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    force = force or os.environ.get("PAGNERF_FORCE_BUILD") == "1"
     lib = LIB.replace(".so", f"{tag}.so")
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "pagnerf_b200.h"))
@@ -48,8 +52,22 @@ def build(force=False, verbose=False, extra_flags=(), tag=""):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or _stale(lib, objs):
+    linked = bool(force or procs or _stale(lib, objs))
+    if linked:
         subprocess.check_call([nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    # what this call did, for the record (the driver's GPU box reuses the .so that travelled with the snapshot unless a source is
+    # newer; PAGNERF_FORCE_BUILD=1 or build(force=True) compiles everything from source there)
+    global LAST_BUILD
+    LAST_BUILD = {"library": lib, "compiled": [src for src, _ in procs], "reused": [s_ for s_ in SOURCES if s_ not in [x for x, _ in procs]],
+                  "linked": linked, "forced": bool(force)}
+    try:
+        import json
+        import time
+        LAST_BUILD["when"] = time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())
+        with open(os.path.join(CSRC, "build_info.json"), "w") as f:
+            json.dump(LAST_BUILD, f, indent=1)
+    except OSError:
+        pass
     return lib
 
 

@@ -262,3 +262,66 @@ def test_loss_oracle_basics():
     many = torch.arange(1, 9)                      # 8 labels, 5 ids: the 3 largest labels are not assigned
     v = virtual_labels(torch.softmax(torch.randn(8, C), -1), many)
     assert (v[5:] == 1).all() and sorted(v[:5].tolist()) == [1, 2, 3, 4, 5]
+
+
+def test_ba_pipeline_surface_and_pose_layout():
+    """BAPipeline (pc_nerf/ba_pipeline.py:10-92): constructor forms, the 9-parameter `camera_extrinsics` layout (first two rows of
+    the view rotation + translation), cam-id mapping, anchor mask registration; the transform itself refuses CPU tensors."""
+    import torch
+    from oracle import pose as opose
+    from pagnerf_b200.pc_nerf import BAPipeline
+    V = torch.eye(4).repeat(3, 1, 1)
+    V[:, :3, 3] = torch.tensor([[0.1, 0.2, 0.3], [0.0, 0.0, 1.0], [-1.0, 0.5, 0.0]])
+    pipe = BAPipeline(None, V, None, anchor_frame_idxs=[0])
+    assert tuple(pipe.camera_extrinsics.shape) == (3, 9)
+    assert torch.equal(pipe.camera_extrinsics.detach(), opose.params_from_view_matrix(V))
+    assert 'camera_extrinsics' in dict(pipe.named_parameters())
+    assert pipe.cameras.extrinsics.parameters() is pipe.camera_extrinsics and len(pipe.cameras) == 3
+
+    class Cam:      # kaolin-like duck type
+        def __init__(self, v): self.extrinsics, self.near, self.far = self, 0.0, 2.0; self._v = v
+        def view_matrix(self): return self._v[None]
+    pipe2 = BAPipeline(None, {"a": Cam(V[0]), "b": Cam(V[1])}, None)
+    assert pipe2.cam_id_to_idx == {"a": 0, "b": 1} and pipe2.cameras.far == 2.0
+    assert pipe2.get_camera_indices(["b", "a"]).tolist() == [1, 0]
+    from pagnerf_b200.wisp_compat import Rays
+    with pytest.raises(RuntimeError):
+        pipe.transform_rays(Rays(origins=torch.zeros(6, 3), dirs=torch.ones(6, 3)), torch.tensor([0, 1, 2]))
+
+
+def test_fused_adam_refuses_cpu_and_amsgrad():
+    import torch
+    from pagnerf_b200.optim import FusedAdam
+    p = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(NotImplementedError):
+        FusedAdam([p], amsgrad=True)
+    opt = FusedAdam([dict(params=[p], lr=0.1)], eps=1e-15)
+    assert opt.param_groups[0]['lr'] == 0.1 and opt.param_groups[0]['betas'] == (0.9, 0.999)
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        opt.step()
+
+
+def test_bench_configs_build_and_reference_arm_line():
+    """bench.py plumbing on the CPU: every BASELINE config's field constructs with the documented shapes, the confined rays of the
+    dense configs stay inside the cube, and `--impl reference` prints one JSON line with the same `config` object our arm prints."""
+    import json
+    import numpy as np
+    import torch
+    import bench
+    shapes = {1: ("HashGridTorch", 16, True), 2: ("PermutoGrid", 24, True), 3: ("HashGridTinyCudaNN", 14, False)}
+    for cid, (gtype, levels, delta) in shapes.items():
+        wl = bench.Workload(torch.device('cpu'), n_rays=64, n_batches=1, config=cid)
+        assert type(wl.nef.grid).__name__ == gtype and wl.nef.grid.num_lods == levels and hasattr(wl.nef, 'delta_grid') == delta
+    o, d = bench.make_rays(4096, 0, 0, confined=True)
+    pts = o[:, None, :] + d[:, None, :] * np.linspace(0, 1.7, 33)[None, :, None]
+    assert np.abs(pts).max() < 1.0, "dense N x S packing: every sample inside the unit cube"
+    V = bench.make_cameras(0)
+    assert V.shape == (42, 4, 4) and np.allclose(V[:, :3, :3] @ np.transpose(V[:, :3, :3], (0, 2, 1)), np.eye(3), atol=1e-6)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-rays", "64"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["steps"] == 1 and line["unit"] == "rays/s" and line["cpu_baseline"]["kind"] == "port"
+    assert line["config"]["baseline_config"] == 2 and line["config"]["rays_per_gpu"] == 16384
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
