@@ -20,6 +20,17 @@
 
 #define PERMUTO_HASH_MUL 2531011u
 
+#define PERMUTO_MAX_LEVELS 64
+// per-level parameters into shared memory: lv[2l] = (sf.x, sf.y, sf.z, anneal), lv[2l+1] = (shift.x, shift.y, shift.z, 0)
+__device__ __forceinline__ void permuto_stage_levels(float4* lv, int L, const float* __restrict__ sf, const float* __restrict__ sh,
+                                                     const float* __restrict__ anneal) {
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        lv[2 * l] = make_float4(__ldg(sf + 3 * l), __ldg(sf + 3 * l + 1), __ldg(sf + 3 * l + 2), anneal ? __ldg(anneal + l) : 1.f);
+        lv[2 * l + 1] = make_float4(__ldg(sh + 3 * l), __ldg(sh + 3 * l + 1), __ldg(sh + 3 * l + 2), 0.f);
+    }
+    __syncthreads();
+}
+
 struct PermutoVertex {
     uint32_t idx[4];
     float bary[4];
@@ -27,12 +38,13 @@ struct PermutoVertex {
 };
 
 // one level of the lattice for one point; `cap_mask` != 0 means capacity is a power of two
-__device__ __forceinline__ void permuto_lattice(float p0, float p1, float p2, const float* __restrict__ sf,
-                                                const float* __restrict__ sh, uint32_t cap, uint32_t cap_mask,
-                                                PermutoVertex& v) {
-    const float cf0 = __fmul_rn(__fadd_rn(p0, __ldg(sh + 0)), __ldg(sf + 0));
-    const float cf1 = __fmul_rn(__fadd_rn(p1, __ldg(sh + 1)), __ldg(sf + 1));
-    const float cf2 = __fmul_rn(__fadd_rn(p2, __ldg(sh + 2)), __ldg(sf + 2));
+// sfv / shv: the level's scale factors / random shift (xyz).  The encode kernels keep all levels' parameters in shared memory
+// (two broadcast LDS.128 per level instead of seven uniform LDG: the uniform loads were 12 % of the kernel's L1 wavefronts).
+__device__ __forceinline__ void permuto_lattice(float p0, float p1, float p2, const float4 sfv, const float4 shv, uint32_t cap,
+                                                uint32_t cap_mask, PermutoVertex& v) {
+    const float cf0 = __fmul_rn(__fadd_rn(p0, shv.x), sfv.x);
+    const float cf1 = __fmul_rn(__fadd_rn(p1, shv.y), sfv.y);
+    const float cf2 = __fmul_rn(__fadd_rn(p2, shv.z), sfv.z);
     float e[4];
     float sm = 0.f;
     e[3] = __fmaf_rn(-3.f, cf2, sm); sm = __fadd_rn(sm, cf2);
@@ -104,6 +116,8 @@ __global__ void __launch_bounds__(128) permuto_fwd_kernel(
     const float* __restrict__ pos, int64_t M, const float* __restrict__ table, uint32_t cap, uint32_t cap_mask, int L,
     const float* __restrict__ sf, const float* __restrict__ sh, const float* __restrict__ anneal,
     float* __restrict__ out, const int64_t* __restrict__ m_dev, int pos_half) {
+    __shared__ float4 lv[2 * PERMUTO_MAX_LEVELS];
+    permuto_stage_levels(lv, L, sf, sh, anneal);
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m_dev) M = min(M, __ldg(m_dev));   // packed-sample count produced on the device by the marcher
     uint4* img = nullptr;
@@ -125,13 +139,14 @@ __global__ void __launch_bounds__(128) permuto_fwd_kernel(
 #pragma unroll 4
     for (int l = 0; l < L; ++l) {
         PermutoVertex v;
-        permuto_lattice(p0, p1, p2, sf + 3 * l, sh + 3 * l, cap, cap_mask, v);
+        const float4 sfv = lv[2 * l];
+        permuto_lattice(p0, p1, p2, sfv, lv[2 * l + 1], cap, cap_mask, v);
         const float* tl = table + (size_t)l * cap * 2;
         const float2 a = ldg2(tl + 2 * (size_t)v.idx[0]);
         const float2 b = ldg2(tl + 2 * (size_t)v.idx[1]);
         const float2 c = ldg2(tl + 2 * (size_t)v.idx[2]);
         const float2 d = ldg2(tl + 2 * (size_t)v.idx[3]);
-        const float w = __ldg(anneal + l);
+        const float w = sfv.w;
         float2 acc;
         acc.x = (a.x * v.bary[0] + b.x * v.bary[1] + c.x * v.bary[2] + d.x * v.bary[3]) * w;
         acc.y = (a.y * v.bary[0] + b.y * v.bary[1] + c.y * v.bary[2] + d.y * v.bary[3]) * w;
@@ -154,7 +169,8 @@ __global__ void permuto_indices_kernel(const float* __restrict__ pos, int64_t M,
     const float p0 = pos[3 * m], p1 = pos[3 * m + 1], p2 = pos[3 * m + 2];
     for (int l = 0; l < L; ++l) {
         PermutoVertex v;
-        permuto_lattice(p0, p1, p2, sf + 3 * l, sh + 3 * l, cap, cap_mask, v);
+        permuto_lattice(p0, p1, p2, make_float4(__ldg(sf + 3 * l), __ldg(sf + 3 * l + 1), __ldg(sf + 3 * l + 2), 1.f),
+                        make_float4(__ldg(sh + 3 * l), __ldg(sh + 3 * l + 1), __ldg(sh + 3 * l + 2), 0.f), cap, cap_mask, v);
         for (int r = 0; r < 4; ++r) {
             idx[((size_t)l * M + m) * 4 + r] = v.idx[r];
             rank[((size_t)l * M + m) * 4 + r] = v.rank[r];
@@ -171,6 +187,8 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
     const float* __restrict__ sf, const float* __restrict__ sh, const float* __restrict__ anneal,
     const float* __restrict__ gout, float* __restrict__ gtable, float* __restrict__ gpos, int n_agg_levels,
     const int64_t* __restrict__ m_dev, int pos_half, const float* __restrict__ img_scale, int l0, int l1) {
+    __shared__ float4 lv[2 * PERMUTO_MAX_LEVELS];
+    permuto_stage_levels(lv, L, sf, sh, anneal);
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m_dev) M = min(M, __ldg(m_dev));
     if (M <= 0 || (m & ~31ll) >= M) return;   // whole warp beyond the packed samples
@@ -205,8 +223,9 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
     uint4 gq = make_uint4(0u, 0u, 0u, 0u);
     for (int l = l0; l < l1; ++l) {
         PermutoVertex v;
-        permuto_lattice(p0, p1, p2, sf + 3 * l, sh + 3 * l, cap, cap_mask, v);
-        const float w = __ldg(anneal + l);
+        const float4 sfv = lv[2 * l];
+        permuto_lattice(p0, p1, p2, sfv, lv[2 * l + 1], cap, cap_mask, v);
+        const float w = sfv.w;
         float2 g;
         if (GIMG) {
             if ((l & 3) == 0 || l == l0) gq = __ldg(gimg + (l >> 2) * 128);
@@ -248,9 +267,9 @@ __global__ void __launch_bounds__(128) permuto_bwd_kernel(
                 de[i] = 0.25f * t;
             }
             // e0 = c0+c1+c2, e1 = c2+c1-c0, e2 = c2-2c1, e3 = -3c2
-            gp0 += (de[0] - de[1]) * __ldg(sf + 3 * l + 0);
-            gp1 += (de[0] + de[1] - 2.f * de[2]) * __ldg(sf + 3 * l + 1);
-            gp2 += (de[0] + de[1] + de[2] - 3.f * de[3]) * __ldg(sf + 3 * l + 2);
+            gp0 += (de[0] - de[1]) * sfv.x;
+            gp1 += (de[0] + de[1] - 2.f * de[2]) * sfv.y;
+            gp2 += (de[0] + de[1] + de[2] - 3.f * de[3]) * sfv.z;
         }
     }
     if (POS_GRAD && valid) {
@@ -316,6 +335,7 @@ int pag_permuto_fwd(const float* pos, int64_t M, const float* table, int64_t cap
                     const float* scale_factor, const float* shift, const float* anneal, float* out, void* stream) {
     if (F != 2) return PAG_ERR_UNSUPPORTED;
     if (capacity <= 0 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (L > PERMUTO_MAX_LEVELS) return PAG_ERR_UNSUPPORTED;
     if (M == 0) return PAG_OK;
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
@@ -332,6 +352,7 @@ int pag_permuto_fwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, i
                         float* out, void* stream) {
     if (F != 2) return PAG_ERR_UNSUPPORTED;
     if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (L > PERMUTO_MAX_LEVELS) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
@@ -347,6 +368,7 @@ int pag_permuto_fwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_
                               void* img16, void* stream) {
     if (F != 2 || (L & 3)) return PAG_ERR_UNSUPPORTED;
     if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (L > PERMUTO_MAX_LEVELS) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
@@ -363,6 +385,7 @@ int pag_permuto_bwd(const float* pos, int64_t M, const float* table, int64_t cap
                     float* grad_table, float* grad_pos, int n_agg_levels, void* stream) {
     if (F != 2) return PAG_ERR_UNSUPPORTED;
     if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (L > PERMUTO_MAX_LEVELS) return PAG_ERR_UNSUPPORTED;
     if (M == 0) return PAG_OK;
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
@@ -381,6 +404,7 @@ int pag_permuto_bwd_dyn(const float* pos, int64_t M_max, const int64_t* m_dev, i
                         const float* grad_out, float* grad_table, float* grad_pos, int n_agg_levels, void* stream) {
     if (F != 2) return PAG_ERR_UNSUPPORTED;
     if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (L > PERMUTO_MAX_LEVELS) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
@@ -402,6 +426,7 @@ int pag_permuto_bwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_
     if (F != 2 || (L & 3)) return PAG_ERR_UNSUPPORTED;
     if (level_begin < 0 || level_end > L || level_begin >= level_end) return PAG_ERR_ARG;
     if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (L > PERMUTO_MAX_LEVELS) return PAG_ERR_UNSUPPORTED;
     if (M_max == 0) return PAG_OK;
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
@@ -419,6 +444,7 @@ int pag_permuto_bwd_img16_dyn(const float* pos, int64_t M_max, const int64_t* m_
 int pag_permuto_indices(const float* pos, int64_t M, int64_t capacity, int L, const float* scale_factor,
                         const float* shift, uint32_t* idx, int32_t* rank, float* bary, void* stream) {
     if (capacity <= 1 || capacity > 0xFFFFFFFFll || L <= 0) return PAG_ERR_ARG;
+    if (L > PERMUTO_MAX_LEVELS) return PAG_ERR_UNSUPPORTED;
     if (M == 0) return PAG_OK;
     const uint32_t cap = (uint32_t)capacity;
     const uint32_t mask = ((cap & (cap - 1)) == 0) ? (cap - 1) : 0;
