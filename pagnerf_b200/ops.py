@@ -893,6 +893,11 @@ class FusedTraceFn(Function):
             zs = _side_stream(dev, 2)
             if _use_symm():      # gradient tables in symmetric memory: reduced in place by csrc/allreduce.cu
                 sg = _symm_grads(dev, tb.numel(), dtable.numel() if dtable is not None else 0, sum(x.numel() for x in weights))
+                if getattr(sg, 'in_flight', False):
+                    raise RuntimeError("pagnerf_b200: transport='symm' keeps ONE set of persistent gradient buffers per process -- a second "
+                                       "fused trace was started before the backward of the previous one (gradient accumulation over "
+                                       "several forwards needs transport='fp32')")
+                sg.in_flight = True
                 g_table0 = sg.view('table').view_as(tb)
                 g_dtable0 = sg.view('dtable').view_as(dtable) if (dtable is not None and ctx.needs_input_grad[4]) else None
             else:
@@ -1042,6 +1047,7 @@ class FusedTraceFn(Function):
         sizes = [x.numel() for x in w]
         symm = _symm_grads(dev, tb.numel(), dtb.numel() if dtb is not None else 0, sum(sizes)) if (sync and _use_symm()) else None
         if symm is not None:
+            symm.in_flight = False
             flat = symm.view('flat')
             flat.zero_()
         else:
