@@ -832,7 +832,7 @@ class FusedTraceFn(Function):
             # sized for the DDA worst case (a ray crosses at most 3 * 2^level - 2 cells of the level's grid); only the first
             # K = nug_off[N] entries are ever touched.  The max-travel filter is folded into the kept-nugget count.
             level = int(cfg['level'])
-            Kmax = max(N * min(3 * (1 << level) - 2, int(cfg.get('max_nuggets_per_ray') or (1 << 30))), 1)
+            Kmax = max(N * (3 * (1 << level) - 2), 1)      # always the worst case: the staging rows are never clamped
             Mmax = Kmax * S
             cap = Kmax // max(N, 1)
             nug_off = torch.empty(N + 1, dtype=i64, device=dev)

@@ -44,9 +44,10 @@ class FusedAdam(torch.optim.Optimizer):
                     raise RuntimeError("FusedAdam: CUDA fp32 contiguous parameters only (no CPU fallback)")
                 buckets.setdefault((key, p.device), []).append((p, float(group['lr']), float(group['weight_decay'])))
         for ((betas, eps), dev), items in buckets.items():
-            step = self._step_dev.get(dev)
+            skey = (dev, betas, eps)      # one device-side step counter per launch bucket
+            step = self._step_dev.get(skey)
             if step is None:
-                step = self._step_dev[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+                step = self._step_dev[skey] = torch.zeros(1, dtype=torch.int32, device=dev)
             for c0 in range(0, len(items), 48):
                 chunk = items[c0:c0 + 48]
                 n = len(chunk)
