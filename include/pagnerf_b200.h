@@ -252,6 +252,18 @@ int pag_decode_pan_bwd_tc(const float* feats, const float* dfeats, const float* 
                           int inst_softmax, float inst_temperature, const float* sem, const float* inst,
                           const float* g_sem, const float* g_inst, const float* grad_scale, float* g_panop, void* stream);
 
+/* exact-FP32 decoders for inference, register-tiled (csrc/decoder_tiled.cu; forward only).  pag_decode_dc_fwd_tiled has the
+ * contract of pag_decode_dc_fwd (pc_nerf/panoptic_nef.py:274-300); pag_pan_composite_fwd_f32 has the contract of
+ * pag_pan_composite_fwd_tc without the saved log-sum-exp (pc_nerf/panoptic_nef.py:302-363 fused with
+ * tracers/panoptic_packed_rf_tracer.py:148-178): out_sem[N,Cs] / out_inst[N,Ci] zeroed by the caller, ridx i64[M] ascending. */
+int pag_decode_dc_fwd_tiled(const float* feats, const float* lodw, const float* ray_d, int samples_per_ray, int64_t M, int IN,
+                            const float* const* weights, int hidden, int view_dim, int want_rgb, float* sigma, float* rgb,
+                            void* stream);
+int pag_pan_composite_fwd_f32(const float* feats, const float* dfeats, const float* lodw, int64_t M, int IN,
+                              const float* const* weights, int hidden, int Cs, int Ci, int sem_softmax, int inst_softmax,
+                              float inst_temperature, const float* w, const float* alpha, const int64_t* ridx,
+                              float* out_sem, float* out_inst, void* stream);
+
 /* panoptic heads fused with their compositing (training mode): out[ray] = alpha_ray * sum_s w_s * head(panop_s) with
  * alpha, w detached (tracers/panoptic_packed_rf_tracer.py:148-155,178-205); the [M,C] probabilities never reach HBM.
  * out_sem[N,Cs] / out_inst[N,Ci] must be zeroed by the caller (accumulated with red.add). ridx i64[M] ascending.

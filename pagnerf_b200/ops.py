@@ -291,6 +291,7 @@ def hash_indices(pos, flavour, fparam, res, offset, size):
 # ------------------------------------------------------------------------------------------------
 HIDDEN = 64
 VIEW_DIM = 27
+TILED_F32 = os.environ.get('PAGNERF_TILED_F32', '1') == '1'     # 0: the one-sample-per-thread FP32 forward also for inference
 GRAD_TARGET = 1024.0   # upstream gradients are rescaled so that their max magnitude sits near 2^10 in fp16
 
 
@@ -319,8 +320,17 @@ def grad_scale_dyn(a, b, m_dev, wa=1, wb=1):
     return out
 
 
+def dc_mode(use_tc, IN):
+    """Kernel family for DecodeDCFn: tensor cores / register-tiled FP32 (inference, torch.no_grad()) / per-thread FP32."""
+    if use_tc:
+        return True
+    return 'tiled' if (TILED_F32 and IN % 4 == 0 and not torch.is_grad_enabled()) else False
+
+
 class DecodeDCFn(Function):
-    """density + color decoders.  feats [M,IN], ray_d [M//S, 3] -> sigma [M], rgb [M,3] (or None)."""
+    """density + color decoders.  feats [M,IN], ray_d [M//S, 3] -> sigma [M], rgb [M,3] (or None).
+    use_tc: True (tensor cores), False (exact FP32, differentiable) or 'tiled' (exact FP32, forward only: the caller promises
+    that nothing is differentiated -- see dc_mode())."""
 
     @staticmethod
     def forward(ctx, feats, lodw, ray_d, S, want_rgb, use_tc, *weights):
@@ -332,8 +342,11 @@ class DecodeDCFn(Function):
         sigma = torch.empty(M, dtype=torch.float32, device=f.device)
         rgb = torch.empty(M, 3, dtype=torch.float32, device=f.device) if want_rgb else None
         lw = _f32(lodw)
-        call("pag_decode_dc_fwd_tc" if use_tc else "pag_decode_dc_fwd", ptr(f), ptr(lw), ptr(rd), int(S), M, IN,
-             ptr_array(w), HIDDEN, VIEW_DIM, int(bool(want_rgb)), ptr(sigma), ptr(rgb))
+        # exact-FP32 inference (nothing to differentiate): the register-tiled forward (csrc/decoder_tiled.cu)
+        tiled = use_tc == 'tiled'
+        use_tc = use_tc is True
+        entry = "pag_decode_dc_fwd_tc" if use_tc else ("pag_decode_dc_fwd_tiled" if tiled else "pag_decode_dc_fwd")
+        call(entry, ptr(f), ptr(lw), ptr(rd), int(S), M, IN, ptr_array(w), HIDDEN, VIEW_DIM, int(bool(want_rgb)), ptr(sigma), ptr(rgb))
         ctx.save_for_backward(f, lw, rd, *w)
         ctx.S, ctx.want_rgb, ctx.use_tc = int(S), bool(want_rgb), bool(use_tc)
         return sigma, rgb
@@ -517,6 +530,24 @@ class _Workspace:
 
 def _ws(query, device, *args):
     return _Workspace(query, device, *args)
+
+
+def pan_composite_f32(feats, dfeats, lodw, w, alpha, ridx, N, Cs, Ci, sem_softmax, inst_softmax, inst_temperature, *weights):
+    """Exact-FP32 semantic + instance heads fused with their compositing, forward only (inference; csrc/decoder_tiled.cu):
+    per-ray maps [N,Cs], [N,Ci] -- the [M,C] probabilities never reach HBM."""
+    _chk(feats, dfeats, w, alpha, ridx, *weights)
+    with torch.no_grad():
+        f, df = _f32(feats), _f32(dfeats)
+        M, IN = f.shape
+        wt = [_f32(x) for x in weights]
+        lw = _f32(lodw)
+        w_, a_ = _f32(w).reshape(-1), _f32(alpha).reshape(-1)
+        r_ = ridx.to(torch.int64).contiguous()
+        sem = torch.zeros(N, Cs, dtype=torch.float32, device=f.device) if Cs else None
+        inst = torch.zeros(N, Ci, dtype=torch.float32, device=f.device) if Ci else None
+        call("pag_pan_composite_fwd_f32", ptr(f), ptr(df), ptr(lw), M, IN, ptr_array(wt), HIDDEN, int(Cs), int(Ci),
+             int(bool(sem_softmax)), int(bool(inst_softmax)), float(inst_temperature), ptr(w_), ptr(a_), ptr(r_), ptr(sem), ptr(inst))
+    return sem, inst
 
 
 class PanCompositeFn(Function):

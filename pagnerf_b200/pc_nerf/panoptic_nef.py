@@ -203,7 +203,7 @@ class PanopticNeF(BaseNeuralField):
     def _dc(self, feats, ray_d, num_samples, want_rgb):
         w = _decoder_tensors(self.decoder_density, 1) + _decoder_tensors(self.decoder_color, 2)
         lodw = self._lodw(feats.device)
-        return ops.DecodeDCFn.apply(feats, lodw, ray_d, num_samples, want_rgb, self._use_tc(), *w)
+        return ops.DecodeDCFn.apply(feats, lodw, ray_d, num_samples, want_rgb, ops.dc_mode(self._use_tc(), feats.shape[-1]), *w)
 
     def _pan(self, feats, dfeats, want_sem, want_inst, inst_temperature=0.0):
         """semantic / instance heads on (feats + dfeats) * lod_weights; non-default sigmoid / normalize
@@ -234,9 +234,12 @@ class PanopticNeF(BaseNeuralField):
         return (feats.detach() if (self.sem_detach and self.inst_detach) else feats), None
 
     def fused_panoptic_ok(self, channels):
-        """Can the semantic / instance heads be fused with their compositing (csrc/decoder_tc_fused.cu)?"""
+        """Can the semantic / instance heads be fused with their compositing?  Tensor-core mode: csrc/decoder_tc_fused.cu
+        (forward + backward).  Exact-FP32 mode: only when nothing is differentiated (inference; csrc/decoder_tiled.cu)."""
         want = [c for c in ('semantics', 'inst_embedding') if c in channels]
-        if not want or not self._use_tc():
+        if not want:
+            return False
+        if not self._use_tc() and (torch.is_grad_enabled() or not ops.TILED_F32):
             return False
         plain = not (self.sem_sigmoid or self.sem_normalize or self.inst_sigmoid or self.inst_normalize or self.inst_direct_pos)
         det = self.sem_detach and self.inst_detach
@@ -333,7 +336,8 @@ class PanopticNeF(BaseNeuralField):
             a, b = self._panoptic_inputs(feats, coords, lod_idx)
             wts = _decoder_tensors(self.decoder_semantics, 1) + _decoder_tensors(self.decoder_inst, 2)
             lodw = self._lodw(feats.device)
-            sem_o, inst_o = ops.PanCompositeFn.apply(
+            fused = ops.PanCompositeFn.apply if self._use_tc() else ops.pan_composite_f32
+            sem_o, inst_o = fused(
                 a, b, lodw, w, alpha.detach(), ridx_rows, num_rays, self.num_classes if want_sem else 0,
                 self.num_instances if want_inst else 0, bool(self.sem_softmax), bool(self.inst_softmax),
                 float(getattr(self, 'inst_soft_temperature', 0.0)), *wts)

@@ -1174,3 +1174,96 @@ def test_fused_panoptic_loss(cuda_lib):
     only = panoptic_loss(None, b[1].detach().requires_grad_(True), None, None, ts.to(DEV), None, 0.0, 1.0, 0.0)
     exp = -torch.log(sem.gather(1, ts[:, None]) + 1e-27).mean()
     assert abs(float(only) - float(exp)) <= 1e-5 * abs(float(exp))
+
+
+# ------------------------------------------------------------------------------------------------
+# register-tiled exact-FP32 inference decoders (csrc/decoder_tiled.cu)
+# ------------------------------------------------------------------------------------------------
+def _rand_linear(out_f, in_f, gen, scale=1.0):
+    w = (torch.rand(out_f, in_f, generator=gen) * 2 - 1) * (scale / in_f ** 0.5)
+    b = (torch.rand(out_f, generator=gen) * 2 - 1) * 0.1
+    return [w.to(DEV), b.to(DEV)]
+
+
+@pytest.mark.parametrize("M,IN,S", [(1, 48, 1), (127, 48, 1), (128, 12, 1), (1000, 48, 8), (40000, 28, 1)])
+def test_tiled_dc_forward_equals_one_sample_per_thread(cuda_lib, M, IN, S):
+    """Same op order per output (bias, k ascending, fmaf): sigma / rgb of the tiled forward equal the per-thread kernel's."""
+    from pagnerf_b200 import ops
+    from pagnerf_b200._lib import call, ptr, ptr_array
+    gen = torch.Generator().manual_seed(M + IN)
+    w = _rand_linear(64, IN, gen) + _rand_linear(16, 64, gen) + _rand_linear(64, 43, gen) + _rand_linear(64, 64, gen) + _rand_linear(3, 64, gen)
+    M = (M + S - 1) // S * S
+    feats = torch.randn(M, IN, generator=gen).to(DEV)
+    lodw = (torch.rand(IN, generator=gen) + 0.5).to(DEV)
+    ray_d = torch.nn.functional.normalize(torch.randn(M // S, 3, generator=gen), dim=-1).to(DEV)
+    res = []
+    for entry in ("pag_decode_dc_fwd", "pag_decode_dc_fwd_tiled"):
+        sigma, rgb = torch.full((M,), -7.0, device=DEV), torch.full((M, 3), -7.0, device=DEV)
+        call(entry, ptr(feats), ptr(lodw), ptr(ray_d), S, M, IN, ptr_array(w), 64, 27, 1, ptr(sigma), ptr(rgb))
+        res.append((sigma, rgb))
+    assert torch.equal(res[0][0], res[1][0])
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 2e-7
+    sigma_only = torch.full((M,), -7.0, device=DEV)
+    call("pag_decode_dc_fwd_tiled", ptr(feats), None, None, S, M, IN, ptr_array(w), 64, 27, 0, ptr(sigma_only), None)
+    call("pag_decode_dc_fwd", ptr(feats), None, ptr(ray_d), S, M, IN, ptr_array(w), 64, 27, 0, ptr(res[0][0]), None)
+    assert torch.equal(sigma_only, res[0][0])
+
+
+@pytest.mark.parametrize("M,IN,Cs,Ci,delta,softmax,temp", [
+    (1, 48, 7, 200, True, True, 0.0), (129, 48, 7, 200, True, True, 0.5), (5000, 48, 7, 200, False, True, 0.0),
+    (3000, 12, 3, 50, True, False, 2.0), (777, 48, 0, 200, True, True, 0.0), (777, 28, 16, 0, False, True, 0.0),
+    (60000, 48, 7, 208, True, True, 0.0)])
+def test_tiled_panoptic_composite_f32(cuda_lib, M, IN, Cs, Ci, delta, softmax, temp):
+    """Heads + compositing in one exact-FP32 kernel vs the per-thread FP32 heads ([M,C] probabilities) composited in float64:
+    ragged tile tails, rays crossing tile / thread-group boundaries, empty rays, a missing head, no softmax, temperature."""
+    from pagnerf_b200 import ops
+    gen = torch.Generator().manual_seed(M + Cs + Ci)
+    w = (_rand_linear(64, IN, gen) + _rand_linear(max(Cs, 1), 64, gen, 4.0)
+         + _rand_linear(64, IN, gen) + _rand_linear(64, 64, gen) + _rand_linear(max(Ci, 1), 64, gen, 4.0))
+    feats = torch.randn(M, IN, generator=gen).to(DEV)
+    dfeats = torch.randn(M, IN, generator=gen).to(DEV) * 0.3 if delta else None
+    lodw = (torch.rand(IN, generator=gen) + 0.5).to(DEV)
+    N = max(2, M // 9)
+    ridx = torch.sort(torch.randint(0, N, (M,), generator=gen)).values.to(DEV)       # some rays stay empty
+    wgt = torch.rand(M, generator=gen).to(DEV)
+    alpha = torch.rand(N, 1, generator=gen).to(DEV)
+    with torch.no_grad():
+        sem, inst = ops.pan_composite_f32(feats, dfeats, lodw, wgt, alpha, ridx, N, Cs, Ci, softmax, softmax, temp, *w)
+        ps, pi = ops.DecodePanFn.apply(feats, dfeats, lodw, Cs, Ci, softmax, softmax, temp, False, *w)
+    coef = (alpha.reshape(-1)[ridx] * wgt).double()
+    for got, p, C in ((sem, ps, Cs), (inst, pi, Ci)):
+        if C == 0:
+            assert got is None
+            continue
+        want = torch.zeros(N, C, dtype=torch.float64, device=DEV).index_add_(0, ridx, p.double() * coef[:, None])
+        assert_close(got, want.float(), rtol=1e-5, atol_scale=1e-5, msg=f"C={C}")
+
+
+@pytest.mark.parametrize("name,mode", [("trace_delta_permuto_ray", "ray"), ("trace_delta_permuto_voxel", "voxel"), ("trace_nef_tcnn_ray", "ray")])
+def test_tiled_f32_inference_trace_matches_golden(cuda_lib, name, mode):
+    """torch.no_grad() + exact-FP32 decoders (the validation / render path, pc_nerf/trainer.py:637-683): the tracer takes the tiled
+    kernels; outputs vs the reference-made golden at 1e-4 and vs the stepwise per-thread kernels at 1e-5."""
+    from pagnerf_b200 import ops
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden(name)
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    nef = build_cuda_nef(g, DEV)
+    nef.decoder_precision = 'fp32'
+    tracer = PanopticPackedRFTracer(raymarch_type=mode, num_steps=int(g["num_steps"]),
+                                    bg_color='white' if bool(g["bg_white"]) else 'black', ray_max_travel=float(g["ray_max_travel"]))
+    rays = Rays(origins=torch.from_numpy(g["o"]).to(DEV), dirs=torch.from_numpy(g["d"]).to(DEV), dist_min=0.0, dist_max=2.0)
+    assert not nef.fused_panoptic_ok(set(chans))           # differentiable FP32: the modular kernels (they have a backward)
+    res = []
+    try:
+        for tiled in (True, False):
+            ops.TILED_F32 = tiled
+            with torch.no_grad():
+                assert nef.fused_panoptic_ok(set(chans)) == tiled
+                rb = tracer(nef, channels=chans, rays=rays, lod_idx=None, stage='val')
+            res.append({c: getattr(rb, c) for c in chans + ['alpha']})
+    finally:
+        ops.TILED_F32 = True
+    for c in chans + ['alpha']:
+        assert_close(res[0][c], g["out_" + c], msg=c + " vs golden")
+        assert_close(res[0][c], res[1][c], rtol=1e-5, atol_scale=1e-5, msg=c + " vs stepwise")
