@@ -13,10 +13,16 @@
 // (semantics / instance maps = alpha * sum_s w_s p_s with detached weights).
 #include "decoder_common.cuh"
 
-#define TL_NT 256
-#define TL_ROWS 128
-#define TL_LDA (TL_ROWS + 4)
-#define TL_BUF (H * TL_LDA)  // one activation buffer [64][132]; also holds a raw [128][IN <= 64] row block
+// ROWS = samples per tile; a tile is worked by a GROUP of 2 * ROWS threads with its own named barrier; a CTA holds NG groups that
+// walk their own tiles and share the staged weights (one group's staging / epilogue / barrier wait is filled by the others' FMA
+// phases).  Measured on the 1 MP frame: density + colour 21.0 ms with 1 x 128 rows, 18.7 ms with 3 x 64; the panoptic heads (whose
+// weights leave room for two 64-row groups only) 35.9 ms with 1 x 128, 38.0 ms with 2 x 64.
+#define TL_LDA(ROWS) ((ROWS) + 4)
+#define TL_BUF(ROWS) (H * TL_LDA(ROWS))   // one activation buffer [64][ROWS+4]; also holds a raw [ROWS][IN <= 64] row block
+#define PAN_ROWS 128
+#define PAN_MAXG 1
+#define DC_ROWS 64
+#define DC_MAXG 3
 #define TL_CIP 208          // instance classes padded: 16 lanes x 13
 
 // packed FP32 FMA (sm_100: FFMA2) -- c.x = a.x * w + c.x, c.y = a.y * w + c.y, each rounded like fmaf.  One issue slot per two
@@ -38,9 +44,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int ROWS>
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(2 * ROWS) : "memory"); }
 
-// D[o][s] = relu(b[o] + sum_k WT[k][o] A[k][s]) for o < 64, s < 128; A, D k-major with stride TL_LDA; WT [K][64].
+// D[o][s] = relu(b[o] + sum_k WT[k][o] A[k][s]) for o < 64, s < ROWS; A, D k-major with stride TL_LDA(ROWS); WT [K][64].
 // thread = 8 samples x 4 outputs: 16 FFMA2 per 3 LDS.128
+template <int ROWS>
 __device__ __forceinline__ void tl_layer64(const float* __restrict__ A, int K, const float* __restrict__ WT,
                                            const float* __restrict__ b, float* __restrict__ D, int tid) {
     const int og = tid & 15, sg = tid >> 4;
@@ -57,8 +66,8 @@ __device__ __forceinline__ void tl_layer64(const float* __restrict__ A, int K, c
     const float* w = WT + og * 4;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(a + k * TL_LDA);
-        const float4 a1 = *reinterpret_cast<const float4*>(a + k * TL_LDA + 4);
+        const float4 a0 = *reinterpret_cast<const float4*>(a + k * TL_LDA(ROWS));
+        const float4 a1 = *reinterpret_cast<const float4*>(a + k * TL_LDA(ROWS) + 4);
         const float4 ww = *reinterpret_cast<const float4*>(w + k * 64);
         const float2 av[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
         const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
@@ -69,7 +78,7 @@ __device__ __forceinline__ void tl_layer64(const float* __restrict__ A, int K, c
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float* d = D + (og * 4 + i) * TL_LDA + sg * 8;
+        float* d = D + (og * 4 + i) * TL_LDA(ROWS) + sg * 8;
         *reinterpret_cast<float4*>(d) = make_float4(fmaxf(acc[0][i].x, 0.f), fmaxf(acc[0][i].y, 0.f), fmaxf(acc[1][i].x, 0.f), fmaxf(acc[1][i].y, 0.f));
         *reinterpret_cast<float4*>(d + 4) = make_float4(fmaxf(acc[2][i].x, 0.f), fmaxf(acc[2][i].y, 0.f), fmaxf(acc[3][i].x, 0.f), fmaxf(acc[3][i].y, 0.f));
     }
@@ -78,7 +87,7 @@ __device__ __forceinline__ void tl_layer64(const float* __restrict__ A, int K, c
 // Output head fused with its compositing.  thread = 8 consecutive samples (sg) x NC classes {i*16 + cg}:
 //   logits z = b + WT^T h (WT [64][16*NC]);  p = softmax ? softmax(z * scale) : z * scale;  out[ray][c] += coef_s * p_s[c]
 // summed over the thread's samples with one red per (ray run, class).
-template <int NC>
+template <int NC, int ROWS>
 __device__ __forceinline__ void tl_head(const float* __restrict__ A, const float* __restrict__ WT, const float* __restrict__ b, int C,
                                         bool softmax, float scale, const float* __restrict__ coef, const int* __restrict__ rr,
                                         float* __restrict__ out, int tid) {
@@ -95,8 +104,8 @@ __device__ __forceinline__ void tl_head(const float* __restrict__ A, const float
         const float* wt = WT + cg;
 #pragma unroll 2
         for (int k = 0; k < H; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(a + k * TL_LDA);
-            const float4 a1 = *reinterpret_cast<const float4*>(a + k * TL_LDA + 4);
+            const float4 a0 = *reinterpret_cast<const float4*>(a + k * TL_LDA(ROWS));
+            const float4 a1 = *reinterpret_cast<const float4*>(a + k * TL_LDA(ROWS) + 4);
             const float2 av[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
@@ -181,18 +190,20 @@ __device__ __forceinline__ void tl_stage_b(float* __restrict__ dst, const float*
     for (int i = threadIdx.x; i < np; i += blockDim.x) dst[i] = i < n ? __ldg(b + i) : 0.f;
 }
 
-// asynchronous copy of rows [row0, row0 + 128) x IN (one contiguous span) into a raw shared-memory block [128][IN]
-__device__ __forceinline__ void tl_fetch_rows(float* __restrict__ raw, const float* __restrict__ src, int IN, int64_t row0, int64_t M) {
+// asynchronous copy of rows [row0, row0 + ROWS) x IN (one contiguous span) into a raw shared-memory block [ROWS][IN]
+template <int ROWS>
+__device__ __forceinline__ void tl_fetch_rows(float* __restrict__ raw, const float* __restrict__ src, int IN, int64_t row0, int64_t M, int gt) {
     const int64_t left = M - row0;
-    const int nch = (int)(left >= TL_ROWS ? TL_ROWS : (left > 0 ? left : 0)) * (IN >> 2);
+    const int nch = (int)(left >= ROWS ? ROWS : (left > 0 ? left : 0)) * (IN >> 2);
     const float* g = src + row0 * IN;
-    for (int c = threadIdx.x; c < nch; c += TL_NT) cp_async16(raw + 4 * c, g + 4 * c);
+    for (int c = gt; c < nch; c += (2 * ROWS)) cp_async16(raw + 4 * c, g + 4 * c);
 }
 // XT[k][r] = (rawA[r][k] + rawB[r][k]) * lodw[k], rows past M zero
+template <int ROWS>
 __device__ __forceinline__ void tl_transpose_x(float* __restrict__ XT, const float* __restrict__ rawA, const float* __restrict__ rawB,
-                                               const float* __restrict__ lodw, int IN, int64_t row0, int64_t M) {
+                                               const float* __restrict__ lodw, int IN, int64_t row0, int64_t M, int gt) {
     const int nq = IN >> 2;
-    for (int g = threadIdx.x; g < TL_ROWS * nq; g += TL_NT) {
+    for (int g = gt; g < ROWS * nq; g += (2 * ROWS)) {
         const int r = g / nq, q = g - r * nq;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row0 + r < M) {
@@ -200,52 +211,54 @@ __device__ __forceinline__ void tl_transpose_x(float* __restrict__ XT, const flo
             if (rawB) { const float4 u = *reinterpret_cast<const float4*>(rawB + 4 * g); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
             if (lodw) { const float4 l = ldg4(lodw + 4 * q); v.x *= l.x; v.y *= l.y; v.z *= l.z; v.w *= l.w; }
         }
-        float* d = XT + (4 * q) * TL_LDA + r;
-        d[0] = v.x; d[TL_LDA] = v.y; d[2 * TL_LDA] = v.z; d[3 * TL_LDA] = v.w;
+        float* d = XT + (4 * q) * TL_LDA(ROWS) + r;
+        d[0] = v.x; d[TL_LDA(ROWS)] = v.y; d[2 * TL_LDA(ROWS)] = v.z; d[3 * TL_LDA(ROWS)] = v.w;
     }
 }
 
-struct TlPanLayout { int P, Q, R, Ws1T, bs1, Ws2T, bs2, Wi1T, bi1, Wi2T, bi2, Wi3T, bi3, coef, ray, total; };
-__host__ __device__ inline TlPanLayout tl_pan_layout(int IN) {
+struct TlPanLayout { int Ws1T, bs1, Ws2T, bs2, Wi1T, bi1, Wi2T, bi2, Wi3T, bi3, groups, gstride, total; };
+// per group: P, Q, R activation buffers + coef[PAN_ROWS] + ray[PAN_ROWS]
+__host__ __device__ inline TlPanLayout tl_pan_layout(int IN, int NG) {
     TlPanLayout l; int o = 0;
-    l.P = o; o += TL_BUF; l.Q = o; o += TL_BUF; l.R = o; o += TL_BUF;
     l.Ws1T = o; o += IN * H; l.bs1 = o; o += H; l.Ws2T = o; o += H * 16; l.bs2 = o; o += 16;
     l.Wi1T = o; o += IN * H; l.bi1 = o; o += H; l.Wi2T = o; o += H * H; l.bi2 = o; o += H;
     l.Wi3T = o; o += H * TL_CIP; l.bi3 = o; o += TL_CIP;
-    l.coef = o; o += TL_ROWS; l.ray = o; o += TL_ROWS;
-    l.total = o;
+    l.groups = o; l.gstride = 3 * TL_BUF(PAN_ROWS) + 2 * PAN_ROWS;
+    l.total = o + NG * l.gstride;
     return l;
 }
 
-// Per tile (4 block barriers):  raw rows (cp.async, issued one tile ahead) in P, Q -> X k-major in R | first layers R -> P (semantic
-// hidden), R -> Q (instance hidden 1) | semantic head from P, instance layer 2 Q -> R | next tile's raw rows -> P, Q in flight while
-// the instance head (55 % of the arithmetic) runs from R.
-__global__ void __launch_bounds__(TL_NT, 1)
+// Per tile and group (4 group barriers):  raw rows (cp.async, issued one tile ahead) in P, Q -> X k-major in R | first layers R -> P
+// (semantic hidden), R -> Q (instance hidden 1) | semantic head from P, instance layer 2 Q -> R | next tile's raw rows -> P, Q in
+// flight while the instance head (55 % of the arithmetic) runs from R.
+__global__ void __launch_bounds__(PAN_MAXG * (2 * PAN_ROWS), 1)
 pan_comp_fwd_tiled_kernel(const float* __restrict__ feats, const float* __restrict__ dfeats, const float* __restrict__ lodw,
                           int64_t M, int IN, PanParams p, int Cs, int Ci, int sem_softmax, int inst_softmax, float inv_temp,
                           const float* __restrict__ w, const float* __restrict__ alpha, const int64_t* __restrict__ ridx,
                           float* __restrict__ out_sem, float* __restrict__ out_inst) {
     extern __shared__ __align__(16) float smem[];
-    const TlPanLayout l = tl_pan_layout(IN);
-    float *P = smem + l.P, *Q = smem + l.Q, *R = smem + l.R, *coef = smem + l.coef;
-    int* rr = reinterpret_cast<int*>(smem + l.ray);
-    const int tid = threadIdx.x;
-    const int64_t ntiles = (M + TL_ROWS - 1) / TL_ROWS;
+    const int NG = blockDim.x / (2 * PAN_ROWS), grp = threadIdx.x / (2 * PAN_ROWS), gt = threadIdx.x - grp * (2 * PAN_ROWS);
+    const TlPanLayout l = tl_pan_layout(IN, NG);
+    float* P = smem + l.groups + grp * l.gstride;
+    float *Q = P + TL_BUF(PAN_ROWS), *R = Q + TL_BUF(PAN_ROWS), *coef = R + TL_BUF(PAN_ROWS);
+    int* rr = reinterpret_cast<int*>(coef + PAN_ROWS);
+    const int64_t ntiles = (M + PAN_ROWS - 1) / PAN_ROWS;
+    const int64_t tile0 = (int64_t)blockIdx.x * NG + grp, tstride = (int64_t)gridDim.x * NG;
     int ray_n = 0;
     float coef_n = 0.f;
     auto fetch = [&](int64_t tile) {      // raw rows + this thread's compositing coefficient of `tile`
-        tl_fetch_rows(P, feats, IN, tile * TL_ROWS, M);
-        if (dfeats) tl_fetch_rows(Q, dfeats, IN, tile * TL_ROWS, M);
+        tl_fetch_rows<PAN_ROWS>(P, feats, IN, tile * PAN_ROWS, M, gt);
+        if (dfeats) tl_fetch_rows<PAN_ROWS>(Q, dfeats, IN, tile * PAN_ROWS, M, gt);
         cp_async_commit();
-        if (tid < TL_ROWS) {
-            const int64_t m = tile * TL_ROWS + tid;
+        if (gt < PAN_ROWS) {
+            const int64_t m = tile * PAN_ROWS + gt;
             const bool valid = m < M;
             const int64_t ray = ridx[valid ? m : M - 1];
             ray_n = (int)ray;
             coef_n = valid ? __ldg(alpha + ray) * __ldg(w + m) : 0.f;
         }
     };
-    if ((int64_t)blockIdx.x < ntiles) fetch(blockIdx.x);
+    if (tile0 < ntiles) fetch(tile0);
     if (Cs > 0) {
         tl_stage_wt(smem + l.Ws1T, p.Ws1, H, H, IN, IN); tl_stage_b(smem + l.bs1, p.bs1, H, H);
         tl_stage_wt(smem + l.Ws2T, p.Ws2, Cs, 16, H, H); tl_stage_b(smem + l.bs2, p.bs2, Cs, 16);
@@ -255,68 +268,72 @@ pan_comp_fwd_tiled_kernel(const float* __restrict__ feats, const float* __restri
         tl_stage_wt(smem + l.Wi2T, p.Wi2, H, H, H, H); tl_stage_b(smem + l.bi2, p.bi2, H, H);
         tl_stage_wt(smem + l.Wi3T, p.Wi3, Ci, TL_CIP, H, H); tl_stage_b(smem + l.bi3, p.bi3, Ci, TL_CIP);
     }
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t row0 = tile * TL_ROWS;
+    __syncthreads();                       // weights staged (the only block-wide barrier)
+    for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
+        const int64_t row0 = tile * PAN_ROWS;
         cp_async_wait_all();
-        __syncthreads();                       // raw rows landed; the previous tile's instance head is done with R / coef / rr
-        if (tid < TL_ROWS) { rr[tid] = ray_n; coef[tid] = coef_n; }
-        tl_transpose_x(R, P, dfeats ? Q : nullptr, lodw, IN, row0, M);
-        __syncthreads();
-        if (Cs > 0) tl_layer64(R, IN, smem + l.Ws1T, smem + l.bs1, P, tid);
-        if (Ci > 0) tl_layer64(R, IN, smem + l.Wi1T, smem + l.bi1, Q, tid);
-        __syncthreads();
-        if (Cs > 0) tl_head<1>(P, smem + l.Ws2T, smem + l.bs2, Cs, sem_softmax != 0, 1.f, coef, rr, out_sem, tid);
-        if (Ci > 0) tl_layer64(Q, H, smem + l.Wi2T, smem + l.bi2, R, tid);
-        __syncthreads();
-        if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
-        if (Ci > 0) tl_head<13>(R, smem + l.Wi3T, smem + l.bi3, Ci, inst_softmax != 0, inv_temp, coef, rr, out_inst, tid);
+        group_sync<PAN_ROWS>(grp);                   // raw rows landed; the previous tile's instance head is done with R / coef / rr
+        if (gt < PAN_ROWS) { rr[gt] = ray_n; coef[gt] = coef_n; }
+        tl_transpose_x<PAN_ROWS>(R, P, dfeats ? Q : nullptr, lodw, IN, row0, M, gt);
+        group_sync<PAN_ROWS>(grp);
+        if (Cs > 0) tl_layer64<PAN_ROWS>(R, IN, smem + l.Ws1T, smem + l.bs1, P, gt);
+        if (Ci > 0) tl_layer64<PAN_ROWS>(R, IN, smem + l.Wi1T, smem + l.bi1, Q, gt);
+        group_sync<PAN_ROWS>(grp);
+        if (Cs > 0) tl_head<1, PAN_ROWS>(P, smem + l.Ws2T, smem + l.bs2, Cs, sem_softmax != 0, 1.f, coef, rr, out_sem, gt);
+        if (Ci > 0) tl_layer64<PAN_ROWS>(Q, H, smem + l.Wi2T, smem + l.bi2, R, gt);
+        group_sync<PAN_ROWS>(grp);
+        if (tile + tstride < ntiles) fetch(tile + tstride);
+        if (Ci > 0) tl_head<13, PAN_ROWS>(R, smem + l.Wi3T, smem + l.bi3, Ci, inst_softmax != 0, inv_temp, coef, rr, out_inst, gt);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // density + colour
 // ---------------------------------------------------------------------------------------------
-struct TlDcLayout { int RAW, X, A, B, Wd1T, bd1, Wd2T, bd2, Wc1T, bc1, Wc2T, bc2, Wc3, bc3, total; };
-__host__ __device__ inline TlDcLayout tl_dc_layout(int IN) {
+struct TlDcLayout { int Wd1T, bd1, Wd2T, bd2, Wc1T, bc1, Wc2T, bc2, Wc3, bc3, groups, oX, oA, oB, gstride, total; };
+// per group: RAW [DC_ROWS][IN] (next tile's rows, cp.async) | X [max(IN, CINP)][LDA] (features k-major, then the colour decoder's input) | A | B
+__host__ __device__ inline TlDcLayout tl_dc_layout(int IN, int NG) {
     TlDcLayout l; int o = 0;
-    l.RAW = o; o += TL_ROWS * IN;                          // next tile's raw rows (cp.async)
-    l.X = o; o += (IN > CINP ? IN : CINP) * TL_LDA;        // features k-major, then the colour decoder's input [CINP][LDA]
-    l.A = o; o += TL_BUF; l.B = o; o += TL_BUF;
     l.Wd1T = o; o += IN * H; l.bd1 = o; o += H; l.Wd2T = o; o += H * DOUT; l.bd2 = o; o += DOUT;
     l.Wc1T = o; o += CINP * H; l.bc1 = o; o += H; l.Wc2T = o; o += H * H; l.bc2 = o; o += H;
     l.Wc3 = o; o += 4 * H; l.bc3 = o; o += 4;
-    l.total = o;
+    l.groups = o;
+    l.oX = DC_ROWS * IN; l.oA = l.oX + (IN > CINP ? IN : CINP) * TL_LDA(DC_ROWS); l.oB = l.oA + TL_BUF(DC_ROWS); l.gstride = l.oB + TL_BUF(DC_ROWS);
+    l.total = o + NG * l.gstride;
     return l;
 }
 
-__global__ void __launch_bounds__(TL_NT, 1)
+__global__ void __launch_bounds__(DC_MAXG * (2 * DC_ROWS), 1)
 dc_fwd_tiled_kernel(const float* __restrict__ feats, const float* __restrict__ lodw, const float* __restrict__ ray_d, int S,
                     int64_t M, int IN, DcParams p, int want_rgb, float* __restrict__ sigma, float* __restrict__ rgb) {
     extern __shared__ __align__(16) float smem[];
-    const TlDcLayout l = tl_dc_layout(IN);
-    float *RAW = smem + l.RAW, *XT = smem + l.X, *A = smem + l.A, *B = smem + l.B;
-    const int tid = threadIdx.x;
-    const int64_t ntiles = (M + TL_ROWS - 1) / TL_ROWS;
-    if ((int64_t)blockIdx.x < ntiles) { tl_fetch_rows(RAW, feats, IN, (int64_t)blockIdx.x * TL_ROWS, M); cp_async_commit(); }
+    const int NG = blockDim.x / (2 * DC_ROWS), grp = threadIdx.x / (2 * DC_ROWS), gt = threadIdx.x - grp * (2 * DC_ROWS);
+    const TlDcLayout l = tl_dc_layout(IN, NG);
+    float* RAW = smem + l.groups + grp * l.gstride;
+    float *XT = RAW + l.oX, *A = RAW + l.oA, *B = RAW + l.oB;
+    const int64_t ntiles = (M + DC_ROWS - 1) / DC_ROWS;
+    const int64_t tile0 = (int64_t)blockIdx.x * NG + grp, tstride = (int64_t)gridDim.x * NG;
+    if (tile0 < ntiles) { tl_fetch_rows<DC_ROWS>(RAW, feats, IN, tile0 * DC_ROWS, M, gt); cp_async_commit(); }
     tl_stage_wt(smem + l.Wd1T, p.Wd1, H, H, IN, IN); tl_stage_b(smem + l.bd1, p.bd1, H, H);
     tl_stage_wt(smem + l.Wd2T, p.Wd2, DOUT, DOUT, H, H); tl_stage_b(smem + l.bd2, p.bd2, DOUT, DOUT);
     if (want_rgb) {
         tl_stage_wt(smem + l.Wc1T, p.Wc1, H, H, CIN, CINP); tl_stage_b(smem + l.bc1, p.bc1, H, H);
         tl_stage_wt(smem + l.Wc2T, p.Wc2, H, H, H, H); tl_stage_b(smem + l.bc2, p.bc2, H, H);
-        for (int i = tid; i < 3 * H; i += TL_NT) smem[l.Wc3 + i] = __ldg(p.Wc3 + i);
+        for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) smem[l.Wc3 + i] = __ldg(p.Wc3 + i);
         tl_stage_b(smem + l.bc3, p.bc3, 3, 4);
     }
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t row0 = tile * TL_ROWS;
+    __syncthreads();                       // weights staged (the only block-wide barrier)
+    for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
+        const int64_t row0 = tile * DC_ROWS;
         cp_async_wait_all();
-        __syncthreads();                       // raw rows landed; the previous tile's readers of X / A are done
-        tl_transpose_x(XT, RAW, nullptr, lodw, IN, row0, M);
-        __syncthreads();
-        if (tile + gridDim.x < ntiles) { tl_fetch_rows(RAW, feats, IN, (tile + gridDim.x) * TL_ROWS, M); cp_async_commit(); }
-        tl_layer64(XT, IN, smem + l.Wd1T, smem + l.bd1, A, tid);
-        __syncthreads();
+        group_sync<DC_ROWS>(grp);                   // raw rows landed; the previous tile's readers of X / A are done
+        tl_transpose_x<DC_ROWS>(XT, RAW, nullptr, lodw, IN, row0, M, gt);
+        group_sync<DC_ROWS>(grp);
+        if (tile + tstride < ntiles) { tl_fetch_rows<DC_ROWS>(RAW, feats, IN, (tile + tstride) * DC_ROWS, M, gt); cp_async_commit(); }
+        tl_layer64<DC_ROWS>(XT, IN, smem + l.Wd1T, smem + l.bd1, A, gt);
+        group_sync<DC_ROWS>(grp);
         {   // density head 64 -> 16 (no activation) into rows 0..15 of the colour input: thread = 4 samples x 2 outputs
-            const int og = tid & 7, sg = tid >> 3;
+            const int og = gt & 7, sg = gt >> 3;
             float2 acc[2][2];
             const float b0 = smem[l.bd2 + 2 * og], b1 = smem[l.bd2 + 2 * og + 1];
 #pragma unroll
@@ -325,14 +342,14 @@ dc_fwd_tiled_kernel(const float* __restrict__ feats, const float* __restrict__ l
             const float* wt = smem + l.Wd2T + 2 * og;
 #pragma unroll 8
             for (int k = 0; k < H; ++k) {
-                const float4 av = *reinterpret_cast<const float4*>(a + k * TL_LDA);
+                const float4 av = *reinterpret_cast<const float4*>(a + k * TL_LDA(DC_ROWS));
                 const float2 wv = *reinterpret_cast<const float2*>(wt + k * DOUT);
                 ffma2(acc[0][0], make_float2(av.x, av.y), wv.x); ffma2(acc[1][0], make_float2(av.z, av.w), wv.x);
                 ffma2(acc[0][1], make_float2(av.x, av.y), wv.y); ffma2(acc[1][1], make_float2(av.z, av.w), wv.y);
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i)
-                *reinterpret_cast<float4*>(XT + (2 * og + i) * TL_LDA + sg * 4) = make_float4(acc[0][i].x, acc[0][i].y, acc[1][i].x, acc[1][i].y);
+                *reinterpret_cast<float4*>(XT + (2 * og + i) * TL_LDA(DC_ROWS) + sg * 4) = make_float4(acc[0][i].x, acc[0][i].y, acc[1][i].x, acc[1][i].y);
             if (og == 0) {
                 const float sg4[4] = {acc[0][0].x, acc[0][0].y, acc[1][0].x, acc[1][0].y};
 #pragma unroll
@@ -343,28 +360,29 @@ dc_fwd_tiled_kernel(const float* __restrict__ feats, const float* __restrict__ l
             }
         }
         if (!want_rgb) continue;
-        if (tid < TL_ROWS) {   // view-direction embedding into rows 16..42, row 43 zero
-            const int64_t m = row0 + tid;
+        if (gt >= (2 * DC_ROWS) - DC_ROWS) {   // view-direction embedding into rows 16..42, row 43 zero (the group's upper warps)
+            const int s = gt - ((2 * DC_ROWS) - DC_ROWS);
+            const int64_t m = row0 + s;
             const int64_t r = (m < M ? m : M - 1) / S;
             float pe[PE_DIM];
             view_embed(__ldg(ray_d + 3 * r), __ldg(ray_d + 3 * r + 1), __ldg(ray_d + 3 * r + 2), pe);
 #pragma unroll
-            for (int k = 0; k < PE_DIM; ++k) XT[(DOUT + k) * TL_LDA + tid] = pe[k];
-            XT[CIN * TL_LDA + tid] = 0.f;
+            for (int k = 0; k < PE_DIM; ++k) XT[(DOUT + k) * TL_LDA(DC_ROWS) + s] = pe[k];
+            XT[CIN * TL_LDA(DC_ROWS) + s] = 0.f;
         }
-        __syncthreads();
-        tl_layer64(XT, CINP, smem + l.Wc1T, smem + l.bc1, B, tid);
-        __syncthreads();
-        tl_layer64(B, H, smem + l.Wc2T, smem + l.bc2, A, tid);
-        __syncthreads();
-        if (tid < TL_ROWS) {
-            const int64_t m = row0 + tid;
-            const float* hcol = A + tid;
+        group_sync<DC_ROWS>(grp);
+        tl_layer64<DC_ROWS>(XT, CINP, smem + l.Wc1T, smem + l.bc1, B, gt);
+        group_sync<DC_ROWS>(grp);
+        tl_layer64<DC_ROWS>(B, H, smem + l.Wc2T, smem + l.bc2, A, gt);
+        group_sync<DC_ROWS>(grp);
+        if (gt < DC_ROWS) {
+            const int64_t m = row0 + gt;
+            const float* hcol = A + gt;
             const float* w3 = smem + l.Wc3;
             float a0 = smem[l.bc3], a1 = smem[l.bc3 + 1], a2 = smem[l.bc3 + 2];
 #pragma unroll 8
             for (int k = 0; k < H; ++k) {
-                const float h = hcol[k * TL_LDA];
+                const float h = hcol[k * TL_LDA(DC_ROWS)];
                 a0 = fmaf(w3[k], h, a0); a1 = fmaf(w3[H + k], h, a1); a2 = fmaf(w3[2 * H + k], h, a2);
             }
             if (m < M) {
@@ -401,14 +419,16 @@ int pag_pan_composite_fwd_f32(const float* feats, const float* dfeats, const flo
     PanParams p{};
     p.Ws1 = weights[0]; p.bs1 = weights[1]; p.Ws2 = weights[2]; p.bs2 = weights[3]; p.Wi1 = weights[4]; p.bi1 = weights[5];
     p.Wi2 = weights[6]; p.bi2 = weights[7]; p.Wi3 = weights[8]; p.bi3 = weights[9];
-    const size_t bytes = (size_t)tl_pan_layout(IN).total * sizeof(float);
+    int NG = PAN_MAXG;                      // as many tile groups as the shared memory holds next to the weights
+    while (NG > 1 && (size_t)tl_pan_layout(IN, NG).total * sizeof(float) > 227 * 1024) --NG;
+    const size_t bytes = (size_t)tl_pan_layout(IN, NG).total * sizeof(float);
     if (bytes > 227 * 1024) return PAG_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(pan_comp_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    const int64_t tiles = (M + TL_ROWS - 1) / TL_ROWS;
+    const int64_t tiles = ((M + PAN_ROWS - 1) / PAN_ROWS + NG - 1) / NG;
     const int grid = (int)(tiles < tl_num_sms() ? tiles : tl_num_sms());
     const float it = inst_temperature > 0.f ? 1.f / inst_temperature : 1.f;
-    pan_comp_fwd_tiled_kernel<<<grid, TL_NT, bytes, (cudaStream_t)stream>>>(feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax,
+    pan_comp_fwd_tiled_kernel<<<grid, NG * (2 * PAN_ROWS), bytes, (cudaStream_t)stream>>>(feats, dfeats, lodw, M, IN, p, Cs, Ci, sem_softmax,
                                                                             inst_softmax, it, w, alpha, ridx, out_sem, out_inst);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
@@ -424,13 +444,15 @@ int pag_decode_dc_fwd_tiled(const float* feats, const float* lodw, const float* 
     DcParams p{};
     p.Wd1 = weights[0]; p.bd1 = weights[1]; p.Wd2 = weights[2]; p.bd2 = weights[3]; p.Wc1 = weights[4]; p.bc1 = weights[5];
     p.Wc2 = weights[6]; p.bc2 = weights[7]; p.Wc3 = weights[8]; p.bc3 = weights[9];
-    const size_t bytes = (size_t)tl_dc_layout(IN).total * sizeof(float);
+    int NG = DC_MAXG;
+    while (NG > 1 && (size_t)tl_dc_layout(IN, NG).total * sizeof(float) > 227 * 1024) --NG;
+    const size_t bytes = (size_t)tl_dc_layout(IN, NG).total * sizeof(float);
     if (bytes > 227 * 1024) return PAG_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(dc_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    const int64_t tiles = (M + TL_ROWS - 1) / TL_ROWS;
+    const int64_t tiles = ((M + DC_ROWS - 1) / DC_ROWS + NG - 1) / NG;
     const int grid = (int)(tiles < tl_num_sms() ? tiles : tl_num_sms());
-    dc_fwd_tiled_kernel<<<grid, TL_NT, bytes, (cudaStream_t)stream>>>(feats, lodw, ray_d, samples_per_ray, M, IN, p, want_rgb, sigma, rgb);
+    dc_fwd_tiled_kernel<<<grid, NG * (2 * DC_ROWS), bytes, (cudaStream_t)stream>>>(feats, lodw, ray_d, samples_per_ray, M, IN, p, want_rgb, sigma, rgb);
     PAG_LAUNCH_CHECK();
     return PAG_OK;
 }
