@@ -4,7 +4,7 @@
 // 200 logits per sample go through global memory twice (logits -> softmax -> composite kernel).  ncu on the 1 MP frame
 // (profiles/r02_ncu_full.md): pan_fwd 120 ms, dc_fwd 36 ms of a 186 ms frame, FFMA pipe 23 % busy.  Here a CTA owns a
 // 128-sample tile held k-major in shared memory ([k][128+4] floats) and every thread accumulates an 8-sample x 4-output
-// (8 x 13 for the instance logits) register block -- 32 (104) FFMA per 3 (15) LDS -- and the instance / semantic
+// (8 x 13 for the instance logits) register block -- 16 (52) packed FFMA2 per 3 (9) LDS -- and the instance / semantic
 // probabilities are composited straight from registers into the per-ray maps (red.add), never written per sample.
 // Arithmetic order per output is the same as decoder.cu (bias, then k ascending, fmaf), so hidden activations are
 // bit-identical to that path; the composited sums differ in association only.
@@ -84,34 +84,62 @@ __device__ __forceinline__ void tl_layer64(const float* __restrict__ A, int K, c
     }
 }
 
-// Output head fused with its compositing.  thread = 8 consecutive samples (sg) x NC classes {i*16 + cg}:
-//   logits z = b + WT^T h (WT [64][16*NC]);  p = softmax ? softmax(z * scale) : z * scale;  out[ray][c] += coef_s * p_s[c]
-// summed over the thread's samples with one red per (ray run, class).
+// Output head fused with its compositing.  thread = 8 consecutive samples (sg) x NC classes: NC/2 adjacent pairs
+// {32 ip + 2 cg, + 1} (weights by LDS.64: a 16-lane group reads one 128-byte line; composited with red.v2) and, for odd NC, the
+// single class 32 (NC/2) + cg.  logits z = b + WT^T h (WT [64][16*NC]);  p = softmax ? softmax(z * scale) : z * scale;
+// out[ray][c] += coef_s * p_s[c], summed over the thread's samples with one red per (ray run, class pair).
+template <int NC>
+__device__ __forceinline__ int tl_class(int i, int cg) {
+    constexpr int NP = NC / 2;
+    return i < 2 * NP ? (i >> 1) * 32 + 2 * cg + (i & 1) : NP * 32 + cg;
+}
+template <int NC>
+__device__ __forceinline__ void tl_flush(float* __restrict__ row, int C, int cg, const float (&run)[NC]) {
+    constexpr int NP = NC / 2;
+    if ((C & 1) == 0) {                    // even class count: rows stay 8-byte aligned
+#pragma unroll
+        for (int ip = 0; ip < NP; ++ip)
+            if (ip * 32 + 2 * cg < C) red_add_f32x2(row + ip * 32 + 2 * cg, run[2 * ip], run[2 * ip + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 2 * NP; ++i)
+            if (tl_class<NC>(i, cg) < C) red_add_f32(row + tl_class<NC>(i, cg), run[i]);
+    }
+    if (NC & 1)
+        if (NP * 32 + cg < C) red_add_f32(row + NP * 32 + cg, run[NC - 1]);
+}
 template <int NC, int ROWS>
 __device__ __forceinline__ void tl_head(const float* __restrict__ A, const float* __restrict__ WT, const float* __restrict__ b, int C,
                                         bool softmax, float scale, const float* __restrict__ coef, const int* __restrict__ rr,
                                         float* __restrict__ out, int tid) {
+    constexpr int NP = NC / 2;
     const int cg = tid & 15, sg = tid >> 4;
     float2 acc[4][NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        const float bv = b[i * 16 + cg];
+        const float bv = b[tl_class<NC>(i, cg)];
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j][i] = make_float2(bv, bv);
     }
     {
         const float* a = A + sg * 8;
-        const float* wt = WT + cg;
+        const float* wt = WT + 2 * cg;
+        const float* wl = WT + NP * 32 + cg;
 #pragma unroll 2
         for (int k = 0; k < H; ++k) {
             const float4 a0 = *reinterpret_cast<const float4*>(a + k * TL_LDA(ROWS));
             const float4 a1 = *reinterpret_cast<const float4*>(a + k * TL_LDA(ROWS) + 4);
             const float2 av[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                const float wv = wt[k * (16 * NC) + i * 16];
+            for (int ip = 0; ip < NP; ++ip) {
+                const float2 wv = *reinterpret_cast<const float2*>(wt + k * (16 * NC) + ip * 32);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) ffma2(acc[j][i], av[j], wv);
+                for (int j = 0; j < 4; ++j) { ffma2(acc[j][2 * ip], av[j], wv.x); ffma2(acc[j][2 * ip + 1], av[j], wv.y); }
+            }
+            if (NC & 1) {
+                const float wv = wl[k * (16 * NC)];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ffma2(acc[j][NC - 1], av[j], wv);
             }
         }
     }
@@ -124,7 +152,7 @@ __device__ __forceinline__ void tl_head(const float* __restrict__ A, const float
         for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
 #pragma unroll
         for (int i = 0; i < NC; ++i)
-            if (i * 16 + cg < C) {
+            if (tl_class<NC>(i, cg) < C) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { mx[2 * j] = fmaxf(mx[2 * j], acc[j][i].x); mx[2 * j + 1] = fmaxf(mx[2 * j + 1], acc[j][i].y); }
             }
@@ -136,7 +164,7 @@ __device__ __forceinline__ void tl_head(const float* __restrict__ A, const float
         }
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            const bool on = i * 16 + cg < C;
+            const bool on = tl_class<NC>(i, cg) < C;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 acc[j][i].x = on ? ex2_approx((acc[j][i].x - mx[2 * j]) * sc2) : 0.f;
@@ -164,19 +192,15 @@ __device__ __forceinline__ void tl_head(const float* __restrict__ A, const float
 #pragma unroll
     for (int j = 1; j < 8; ++j) {
         if (rv[j] != rprev) {              // uniform over the 16 lanes of this sample group
+            tl_flush<NC>(out + (size_t)rprev * C, C, cg, run);
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                if (i * 16 + cg < C) red_add_f32(out + (size_t)rprev * C + i * 16 + cg, run[i]);
-                run[i] = 0.f;
-            }
+            for (int i = 0; i < NC; ++i) run[i] = 0.f;
             rprev = rv[j];
         }
 #pragma unroll
         for (int i = 0; i < NC; ++i) run[i] = fmaf((j & 1) ? acc[j >> 1][i].y : acc[j >> 1][i].x, cf[j], run[i]);
     }
-#pragma unroll
-    for (int i = 0; i < NC; ++i)
-        if (i * 16 + cg < C) red_add_f32(out + (size_t)rprev * C + i * 16 + cg, run[i]);
+    tl_flush<NC>(out + (size_t)rprev * C, C, cg, run);
 }
 
 // WT[k][o] = k < IN ? W[o][k] : 0 for o < OUT, zero for OUT <= o < OUTP  (W: torch Linear [OUT][IN])

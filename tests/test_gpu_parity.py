@@ -1211,7 +1211,7 @@ def test_tiled_dc_forward_equals_one_sample_per_thread(cuda_lib, M, IN, S):
 
 @pytest.mark.parametrize("M,IN,Cs,Ci,delta,softmax,temp", [
     (1, 48, 7, 200, True, True, 0.0), (129, 48, 7, 200, True, True, 0.5), (5000, 48, 7, 200, False, True, 0.0),
-    (3000, 12, 3, 50, True, False, 2.0), (777, 48, 0, 200, True, True, 0.0), (777, 28, 16, 0, False, True, 0.0),
+    (3000, 12, 3, 50, True, False, 2.0), (3000, 12, 3, 51, True, True, 0.0), (777, 48, 0, 200, True, True, 0.0), (777, 28, 16, 0, False, True, 0.0),
     (60000, 48, 7, 208, True, True, 0.0)])
 def test_tiled_panoptic_composite_f32(cuda_lib, M, IN, Cs, Ci, delta, softmax, temp):
     """Heads + compositing in one exact-FP32 kernel vs the per-thread FP32 heads ([M,C] probabilities) composited in float64:
