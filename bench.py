@@ -578,12 +578,26 @@ def main():
     # BENCH_SAME_SEED=1 (diagnostic): every rank traces the same rays -> no load imbalance between the ranks
     wl = Workload(device, rays, seed=0 if os.environ.get('BENCH_SAME_SEED') == '1' else rank, dd=args.dd, config=args.config, march=args.march)
     trace("workload built")
-    transport = None
+    transport, transport_fallback = None, None
     if world > 1:
         from pagnerf_b200 import ops
         # gradient exchange issued from inside the fused backward.  Default: the tables live in symmetric memory and are reduced in
         # place by csrc/allreduce.cu over NVLink / NVSwitch peer memory (exact fp32); PAGNERF_GRAD_TRANSPORT=fp32|fp16 selects NCCL.
         transport = os.environ.get("PAGNERF_GRAD_TRANSPORT", "symm")
+        if transport == "symm":
+            # symmetric memory needs P2P / multicast capable peers: probe it once (collectively); without it the exchange falls
+            # back to NCCL (exact fp32) and the JSON line says so -- never silently
+            ok = 1
+            try:
+                from pagnerf_b200.parallel import SymmetricGradBuffers
+                SymmetricGradBuffers({"probe": 1024}, device)
+            except Exception as e:      # noqa: BLE001 -- any failure of the symmetric allocation / rendezvous
+                ok = 0
+                print(f"[bench] rank {rank}: symmetric memory unavailable ({e!r}); falling back to NCCL fp32", file=sys.stderr, flush=True)
+            flag = torch.tensor([ok], device=device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                transport, transport_fallback = "fp32", "symmetric memory unavailable on this box -> NCCL fp32"
         ops.set_grad_sync(True, reserved_sms=int(os.environ.get("BENCH_RESERVED_SMS", 0)), transport=transport)
 
     def step(from_host):
@@ -755,6 +769,8 @@ def main():
                                              "fp32": "NCCL all-reduce, fp32", "fp16": "NCCL all-reduce, tables as fp16 under a shared scale"}[transport],
                                "ms_per_step_without_allreduce": ms_nosync, "exposed_ms": ms - ms_nosync,
                                "note": "same CUDA graph captured with the gradient all-reduces switched off, max over ranks"}
+        if transport_fallback:
+            result["allreduce"]["fallback"] = transport_fallback
     print(json.dumps(result))
     _leave(world, dist)
     return 0
