@@ -291,6 +291,10 @@ def hash_indices(pos, flavour, fparam, res, offset, size):
 # ------------------------------------------------------------------------------------------------
 HIDDEN = 64
 VIEW_DIM = 27
+# Rendering under torch.no_grad(): samples whose integration weight is exactly 0 (transmittance underflowed behind an opaque
+# surface, or sigma == 0) add exactly nothing to any map, so the colour decoder, the delta-grid lookup and the panoptic heads
+# run on the other samples only when those are fewer than this share of the packed samples (0 disables, > 1 forces).
+LIVE_COMPACT_FRAC = float(os.environ.get('PAGNERF_LIVE_COMPACT_FRAC', '0.7'))
 TILED_F32 = os.environ.get('PAGNERF_TILED_F32', '1') == '1'     # 0: the one-sample-per-thread FP32 forward also for inference
 GRAD_TARGET = 1024.0   # upstream gradients are rescaled so that their max magnitude sits near 2^10 in fp16
 

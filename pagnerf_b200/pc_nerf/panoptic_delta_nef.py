@@ -41,9 +41,13 @@ class PanopticDeltaNeF(PanopticNeF):
     def register_forward_functions(self):
         self._register_forward_function(self.rgb_semantics, ["density", "rgb", "semantics", "inst_embedding"])
 
-    def _panoptic_inputs(self, feats, coords, lod_idx):
+    def _panoptic_inputs(self, feats, coords, lod_idx, rows=None):
+        """rows (int64 [K], inference only): packed samples to evaluate -- the delta grid is looked up for those only."""
         pft = self.panoptic_features_type
         feats_detached = feats.detach()          # :214
+        if rows is not None:
+            feats_detached = feats_detached.index_select(0, rows)
+            coords = coords.reshape(-1, 1, 3).index_select(0, rows)
         if pft in ['delta', 'separate'] or pft is None:
             delta_feats = self._encode(self.delta_grid, coords.detach(), lod_idx)   # coords.detach(): :215
         if pft == 'delta' or pft is None:

@@ -229,9 +229,11 @@ class PanopticNeF(BaseNeuralField):
         return sem, inst
 
     # ---- fused decode + composite (used by PanopticPackedRFTracer.trace in training mode) --------------------
-    def _panoptic_inputs(self, feats, coords, lod_idx):
-        """(a, b): the panoptic heads read (a + b) * lod_weights.  Base field: the (detached) colour features."""
-        return (feats.detach() if (self.sem_detach and self.inst_detach) else feats), None
+    def _panoptic_inputs(self, feats, coords, lod_idx, rows=None):
+        """(a, b): the panoptic heads read (a + b) * lod_weights.  Base field: the (detached) colour features.
+        rows (int64 [K], inference only): evaluate packed samples `rows` only -> [K, F] tensors."""
+        a = feats.detach() if (self.sem_detach and self.inst_detach) else feats
+        return (a if rows is None else a.index_select(0, rows)), None
 
     def fused_panoptic_ok(self, channels):
         """Can the semantic / instance heads be fused with their compositing?  Tensor-core mode: csrc/decoder_tc_fused.cu
@@ -318,22 +320,51 @@ class PanopticNeF(BaseNeuralField):
 
     def trace_composited(self, coords, ray_d, ridx_rows, deltas, depths, offsets, num_rays, channels, bg_white, lod_idx=None):
         """Decode + composite in one pass: per-ray dict(alpha, hit, rgb, depth, semantics, inst_embedding).
-        The panoptic probabilities are composited inside the decoder kernel and never materialised."""
+        The panoptic probabilities are composited inside the decoder kernel and never materialised.
+        Under torch.no_grad() (rendering / validation) the density pass runs first and everything downstream of the integration
+        weights -- colour decoder, delta-grid lookup, panoptic heads -- runs on the samples with a non-zero weight only
+        (ops.LIVE_COMPACT_FRAC; exact: a zero weight multiplies whatever the skipped decoders would have produced)."""
         if lod_idx is None:
             lod_idx = len(self.grid.active_lods) - 1
         batch, num_samples, _ = coords.shape
         feats = self._encode(self.grid, coords, lod_idx)
-        sigma, rgb = self._dc(feats, ray_d, num_samples, 'rgb' in channels)
-        alpha, hit, rgb_o, dep_o, _, _, w = ops.composite(sigma, deltas, depths if 'depth' in channels else None, rgb,
+        want_rgb = 'rgb' in channels
+        want_sem, want_inst = 'semantics' in channels, 'inst_embedding' in channels
+        rows = None
+        probe = not torch.is_grad_enabled() and ops.LIVE_COMPACT_FRAC > 0.0 and feats.shape[0] > 0 and (want_rgb or want_sem or want_inst)
+        if probe and getattr(self, '_dense_chunks_left', 0) > 0:
+            self._dense_chunks_left -= 1          # the last probe found (almost) every sample live: skip the density-first pass for a while
+            probe = False
+        if probe:
+            sigma, _ = self._dc(feats, ray_d, num_samples, False)
+            alpha, hit, _, dep_o, _, _, w = ops.composite(sigma, deltas, depths if 'depth' in channels else None, None,
                                                            None, None, offsets, bg_white)
+            wf = w.reshape(-1)
+            live = torch.nonzero(wf).reshape(-1)          # host sync on its size (this path already has one per march)
+            if live.numel() < ops.LIVE_COMPACT_FRAC * wf.numel():
+                rows = live
+            else:
+                self._dense_chunks_left = 63
+        if rows is not None:
+            w = wf.index_select(0, rows)
+            ridx_rows = ridx_rows.index_select(0, rows)
+            rgb_o = None
+            if want_rgb:
+                rd = ray_d.index_select(0, rows // num_samples) if num_samples > 1 else ray_d.index_select(0, rows)
+                _, rgb = self._dc(feats.index_select(0, rows), rd, 1, True)
+                acc = ops.SumReduceFn.apply(rgb * w.unsqueeze(-1), ops.ray_offsets(ridx_rows, num_rays))
+                rgb_o = (1.0 - alpha) + alpha * acc if bg_white else alpha * acc          # alpha on top, like ops.composite
+        else:
+            sigma, rgb = self._dc(feats, ray_d, num_samples, want_rgb)
+            alpha, hit, rgb_o, dep_o, _, _, w = ops.composite(sigma, deltas, depths if 'depth' in channels else None, rgb,
+                                                               None, None, offsets, bg_white)
         out = {'alpha': alpha, 'hit': hit, 'density': sigma}
-        if 'rgb' in channels:
+        if want_rgb:
             out['rgb'] = rgb_o
         if 'depth' in channels:
             out['depth'] = dep_o
-        want_sem, want_inst = 'semantics' in channels, 'inst_embedding' in channels
         if want_sem or want_inst:
-            a, b = self._panoptic_inputs(feats, coords, lod_idx)
+            a, b = self._panoptic_inputs(feats, coords, lod_idx, rows) if rows is not None else self._panoptic_inputs(feats, coords, lod_idx)
             wts = _decoder_tensors(self.decoder_semantics, 1) + _decoder_tensors(self.decoder_inst, 2)
             lodw = self._lodw(feats.device)
             fused = ops.PanCompositeFn.apply if self._use_tc() else ops.pan_composite_f32

@@ -1255,15 +1255,58 @@ def test_tiled_f32_inference_trace_matches_golden(cuda_lib, name, mode):
     rays = Rays(origins=torch.from_numpy(g["o"]).to(DEV), dirs=torch.from_numpy(g["d"]).to(DEV), dist_min=0.0, dist_max=2.0)
     assert not nef.fused_panoptic_ok(set(chans))           # differentiable FP32: the modular kernels (they have a backward)
     res = []
+    frac0 = ops.LIVE_COMPACT_FRAC
     try:
-        for tiled in (True, False):
-            ops.TILED_F32 = tiled
+        # tiled kernels without / with the live-sample compaction forced on (density pass first, the rest on w != 0 rows), stepwise kernels
+        for tiled, frac in ((True, 0.0), (True, 2.0), (False, 0.0)):
+            ops.TILED_F32, ops.LIVE_COMPACT_FRAC = tiled, frac
             with torch.no_grad():
                 assert nef.fused_panoptic_ok(set(chans)) == tiled
                 rb = tracer(nef, channels=chans, rays=rays, lod_idx=None, stage='val')
             res.append({c: getattr(rb, c) for c in chans + ['alpha']})
     finally:
-        ops.TILED_F32 = True
+        ops.TILED_F32, ops.LIVE_COMPACT_FRAC = True, frac0
     for c in chans + ['alpha']:
         assert_close(res[0][c], g["out_" + c], msg=c + " vs golden")
-        assert_close(res[0][c], res[1][c], rtol=1e-5, atol_scale=1e-5, msg=c + " vs stepwise")
+        assert_close(res[1][c], g["out_" + c], msg=c + " (compacted) vs golden")
+        assert_close(res[0][c], res[2][c], rtol=1e-5, atol_scale=1e-5, msg=c + " vs stepwise")
+        assert_close(res[1][c], res[2][c], rtol=1e-5, atol_scale=1e-5, msg=c + " (compacted) vs stepwise")
+
+
+def test_live_compaction_skips_zero_weight_samples_exactly(cuda_lib):
+    """An opaque field (density scaled up until the transmittance underflows to exactly 0 behind the first hits): the no-grad
+    render with the zero-weight samples dropped before the colour decoder / delta-grid lookup / heads equals the full render,
+    in both decoder precisions, and really runs on fewer samples."""
+    from pagnerf_b200 import ops
+    from pagnerf_b200.tracers import PanopticPackedRFTracer
+    from pagnerf_b200.wisp_compat import Rays
+    g = load_golden("trace_delta_permuto_ray")
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    nef = build_cuda_nef(g, DEV)
+    with torch.no_grad():
+        nef.decoder_density.lout.bias[0] = 3000.0
+    tracer = PanopticPackedRFTracer(raymarch_type='ray', num_steps=int(g["num_steps"]), bg_color='white')
+    rays = Rays(origins=torch.from_numpy(g["o"]).to(DEV), dirs=torch.from_numpy(g["d"]).to(DEV), dist_min=0.0, dist_max=2.0)
+    frac0 = ops.LIVE_COMPACT_FRAC
+    seen = []
+    orig = ops.pan_composite_f32
+
+    def spy(feats, *a, **k):
+        seen.append(feats.shape[0])
+        return orig(feats, *a, **k)
+    try:
+        for prec in ('fp32', 'fp16'):
+            nef.decoder_precision = prec
+            res = []
+            for frac in (0.0, 0.7):
+                ops.LIVE_COMPACT_FRAC = frac
+                ops.pan_composite_f32 = spy
+                with torch.no_grad():
+                    rb = tracer(nef, channels=chans, rays=rays, lod_idx=None, stage='val')
+                res.append({c: getattr(rb, c) for c in chans + ['alpha']})
+            for c in chans + ['alpha']:
+                assert_close(res[1][c], res[0][c], rtol=1e-5, atol_scale=1e-5, msg=f"{prec} {c}")
+            if prec == 'fp32':
+                assert len(seen) == 2 and 0 < seen[1] < 0.5 * seen[0], seen
+    finally:
+        ops.LIVE_COMPACT_FRAC, ops.pan_composite_f32 = frac0, orig
