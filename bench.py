@@ -905,6 +905,9 @@ def bench_inference(args, cfg, config, metric, unit, rank, world, device, dist):
     result = {"metric": metric, "value": 1e3 / ms, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dt_note[prec], "data": "synthetic", "config": config,
               "details": dict(render_batch=chunk, packed_samples_per_frame_rank0=n_samples, rays_per_rank=per,
+                              live_fraction_last_chunk=getattr(wl.nef, 'last_live_fraction', None),
+                              live_note="share of the packed samples whose integration weight exceeds ops.LIVE_WEIGHT_EPS (2^-30); when below "
+                                        "ops.LIVE_COMPACT_FRAC the colour decoder, the delta-grid lookup and the heads run on those samples only",
                               other_precision={"dtype": dt_note[other], "frames_per_s": 1e3 / ms_other, "ms_per_frame": ms_other}),
               "e2e": {"value": 1e3 / ms_e2e, "unit": unit, "h2d_bytes_per_step": per * 24, "d2h_bytes_per_step": per * (12 + 4 + 1 + 1), "ms_per_step": ms_e2e,
                       "note": "pinned host rays -> H2D -> render -> argmax label maps -> D2H of rgb, depth, semantic and instance label maps (this rank's block)"},

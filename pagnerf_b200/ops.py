@@ -295,6 +295,11 @@ VIEW_DIM = 27
 # surface, or sigma == 0) add exactly nothing to any map, so the colour decoder, the delta-grid lookup and the panoptic heads
 # run on the other samples only when those are fewer than this share of the packed samples (0 disables, > 1 forces).
 LIVE_COMPACT_FRAC = float(os.environ.get('PAGNERF_LIVE_COMPACT_FRAC', '0.7'))
+# A sample counts as live when its weight exceeds this.  0 keeps every non-zero weight (bit-exact skipping).  The default 2^-30
+# also drops the samples behind an opaque surface whose weight is positive but below the fp32 resolution of the composited sums
+# (the weights of a ray sum to <= 1; <= 128 dropped terms of <= 2^-30 each move a map by <= 1.2e-7, the size of the fp32 rounding of
+# the sum itself and 1000x below the 1e-4 parity tolerance; renderers usually stop rays at a transmittance of 1e-4).
+LIVE_WEIGHT_EPS = float(os.environ.get('PAGNERF_LIVE_WEIGHT_EPS', str(2.0 ** -30)))
 TILED_F32 = os.environ.get('PAGNERF_TILED_F32', '1') == '1'     # 0: the one-sample-per-thread FP32 forward also for inference
 GRAD_TARGET = 1024.0   # upstream gradients are rescaled so that their max magnitude sits near 2^10 in fp16
 

@@ -340,7 +340,8 @@ class PanopticNeF(BaseNeuralField):
             alpha, hit, _, dep_o, _, _, w = ops.composite(sigma, deltas, depths if 'depth' in channels else None, None,
                                                            None, None, offsets, bg_white)
             wf = w.reshape(-1)
-            live = torch.nonzero(wf).reshape(-1)          # host sync on its size (this path already has one per march)
+            live = torch.nonzero(wf > ops.LIVE_WEIGHT_EPS).reshape(-1)      # host sync on its size (this path already has one per march)
+            self.last_live_fraction = live.numel() / wf.numel()
             if live.numel() < ops.LIVE_COMPACT_FRAC * wf.numel():
                 rows = live
             else:
