@@ -181,3 +181,40 @@ def test_permuto_half_coords_bit_exact(cuda_lib):
     ref = enc(x, pos_half=True).detach()
     err = (out_h.cpu() - ref).abs()
     assert float((err / (1e-4 * ref.abs() + 1e-4 * ref.abs().max())).max()) <= 1.0, "features on rounded coordinates vs oracle"
+
+
+def test_bench_field_fp32_inference_vs_oracle(cuda_lib):
+    """BASELINE config 5's path at its shapes (L = 24, C_inst = 200): torch.no_grad(), no autocast -> fp32 coordinates, the
+    register-tiled exact-FP32 decoders with the heads composited in-kernel (csrc/decoder_tiled.cu), against the exact oracle on
+    the same marched samples.  Tolerance: north_star's fp32 1e-4."""
+    import bench
+    from oracle import spc as ospc, raymarch as orm
+    from oracle.field import trace_oracle
+    from pagnerf_b200.wisp_compat import Rays
+    dev = torch.device(DEV)
+    wl = bench.Workload(dev, n_rays=N_RAYS, seed=0, n_batches=1, config=5)
+    for g in (wl.nef.grid, wl.nef.delta_grid):
+        g.blas.fixed_jitter, g.blas.jitter_seed = True, SEED_JITTER
+    chans = ['rgb', 'depth', 'semantics', 'inst_embedding']
+    o_np, d_np = bench.make_rays(N_RAYS, 0, 0)
+    wl.nef.decoder_precision = 'auto'
+    with torch.no_grad():
+        assert wl.nef.fused_panoptic_ok(set(chans)) and not wl.nef._use_tc(), "exact-FP32 tiled kernels must be the path taken"
+        rb = wl.tracer(wl.nef, channels=chans, rays=Rays(origins=torch.from_numpy(o_np).to(dev), dirs=torch.from_numpy(d_np).to(dev),
+                                                          dist_min=bench.NEAR, dist_max=bench.FAR), lod_idx=None, stage='val')
+    ours = {c: getattr(rb, c).float().cpu() for c in chans + ['alpha']}
+    octree = ospc.points_to_octree(bench.make_scene(bench.LEVEL, 0), bench.LEVEL)
+    _, _, prefix = ospc.scan_octree(octree, bench.LEVEL)
+    ridx, pidx, s, dp, dl, b = orm.raymarch_ray(octree, prefix, o_np, d_np, bench.LEVEL, bench.NUM_STEPS, bench.NEAR, bench.FAR, seed=SEED_JITTER)
+    assert int(wl.tracer.last_num_samples) == ridx.shape[0], "packed-sample count: marcher == oracle marcher"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    field = _oracle_field(wl.nef)
+    field.pos_half = False
+    with torch.no_grad():
+        ref = trace_oracle(field, torch.from_numpy(o_np), torch.from_numpy(d_np), t(ridx).long(), t(s), t(dp), t(dl), t(b), chans)
+    assert np.array_equal(rb.hit.cpu().numpy(), ref['hit'].numpy().astype(bool))
+    for c in chans + ['alpha']:
+        a, r = ours[c], ref[c].float()
+        bad = (a - r).abs() > 1e-4 * r.abs() + 1e-4 * float(r.abs().max())
+        print(f"out {c}: rel l2 {_rel_l2(a, r):.2e}, max abs err {float((a - r).abs().max()):.2e}")
+        assert not bad.any(), f"{c}: {int(bad.sum())}/{bad.numel()} beyond 1e-4 (max err {float((a - r).abs().max()):.3e}, ref max {float(r.abs().max()):.3e})"
