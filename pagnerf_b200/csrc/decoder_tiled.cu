@@ -6,8 +6,9 @@
 // 128-sample tile held k-major in shared memory ([k][128+4] floats) and every thread accumulates an 8-sample x 4-output
 // (8 x 13 for the instance logits) register block -- 16 (52) packed FFMA2 per 3 (9) LDS -- and the instance / semantic
 // probabilities are composited straight from registers into the per-ray maps (red.add), never written per sample.
-// Arithmetic order per output is the same as decoder.cu (bias, then k ascending, fmaf), so hidden activations are
-// bit-identical to that path; the composited sums differ in association only.
+// Arithmetic order per output is the same as decoder.cu (bias, then k ascending, fmaf), so hidden activations (and the density) are
+// bit-identical to that path; the composited sums differ in association only, the colour through the view embedding's
+// double-angle recurrence (<= 1e-6).
 //
 // Reference semantics: pc_nerf/panoptic_nef.py:253-363 (decoders), tracers/panoptic_packed_rf_tracer.py:148-178
 // (semantics / instance maps = alpha * sum_s w_s p_s with detached weights).
@@ -314,6 +315,25 @@ pan_comp_fwd_tiled_kernel(const float* __restrict__ feats, const float* __restri
 // ---------------------------------------------------------------------------------------------
 // density + colour
 // ---------------------------------------------------------------------------------------------
+// view_embed (decoder_common.cuh) with one sincosf per component and the double-angle recurrence for the octaves 2, 4, 8 (|v| <= 1:
+// the recurrence doubles the absolute error per octave, <= 1e-6 at the last one) instead of 24 sinf / cosf calls per sample
+__device__ __forceinline__ void view_embed_doubling(float dx, float dy, float dz, float* pe /*27*/) {
+    const float v[3] = {-dx, -dy, -dz};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        pe[c] = v[c];
+        float sn, cs;
+        sincosf(v[c], &sn, &cs);
+#pragma unroll
+        for (int f = 0; f < PE_F; ++f) {
+            pe[3 + 3 * f + c] = sn;
+            pe[3 + 3 * PE_F + 3 * f + c] = cs;
+            const float s2 = 2.f * sn * cs, c2 = fmaf(-2.f * sn, sn, 1.f);
+            sn = s2; cs = c2;
+        }
+    }
+}
+
 struct TlDcLayout { int Wd1T, bd1, Wd2T, bd2, Wc1T, bc1, Wc2T, bc2, Wc3, bc3, groups, oX, oA, oB, gstride, total; };
 // per group: RAW [DC_ROWS][IN] (next tile's rows, cp.async) | X [max(IN, CINP)][LDA] (features k-major, then the colour decoder's input) | A | B
 __host__ __device__ inline TlDcLayout tl_dc_layout(int IN, int NG) {
@@ -389,7 +409,7 @@ dc_fwd_tiled_kernel(const float* __restrict__ feats, const float* __restrict__ l
             const int64_t m = row0 + s;
             const int64_t r = (m < M ? m : M - 1) / S;
             float pe[PE_DIM];
-            view_embed(__ldg(ray_d + 3 * r), __ldg(ray_d + 3 * r + 1), __ldg(ray_d + 3 * r + 2), pe);
+            view_embed_doubling(__ldg(ray_d + 3 * r), __ldg(ray_d + 3 * r + 1), __ldg(ray_d + 3 * r + 2), pe);
 #pragma unroll
             for (int k = 0; k < PE_DIM; ++k) XT[(DOUT + k) * TL_LDA(DC_ROWS) + s] = pe[k];
             XT[CIN * TL_LDA(DC_ROWS) + s] = 0.f;

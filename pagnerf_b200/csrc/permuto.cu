@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(128) permuto_fwd_kernel(
         p0 = __half2float(__float2half_rn(p0)); p1 = __half2float(__float2half_rn(p1)); p2 = __half2float(__float2half_rn(p2));
     }
     float2* orow = reinterpret_cast<float2*>(out + m * (int64_t)(2 * L));
+    const bool row16 = !IMG16 && !(L & 1);   // f32 rows of an even level count are 16-byte aligned: two levels per store (every lane's
+    float2 prev = make_float2(0.f, 0.f);     // store is its own L1 wavefront at this 8L-byte stride -- half as many of them)
     uint32_t pk[4];
 #pragma unroll 4
     for (int l = 0; l < L; ++l) {
@@ -154,6 +156,9 @@ __global__ void __launch_bounds__(128) permuto_fwd_kernel(
             const __half2 h = __floats2half2_rn(acc.x, acc.y);
             pk[l & 3] = *reinterpret_cast<const uint32_t*>(&h);
             if ((l & 3) == 3) img[(l >> 2) * 128] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else if (row16) {
+            if (l & 1) reinterpret_cast<float4*>(orow)[l >> 1] = make_float4(prev.x, prev.y, acc.x, acc.y);
+            else prev = acc;
         } else {
             orow[l] = acc;
         }

@@ -1187,7 +1187,7 @@ def _rand_linear(out_f, in_f, gen, scale=1.0):
 
 @pytest.mark.parametrize("M,IN,S", [(1, 48, 1), (127, 48, 1), (128, 12, 1), (1000, 48, 8), (40000, 28, 1)])
 def test_tiled_dc_forward_equals_one_sample_per_thread(cuda_lib, M, IN, S):
-    """Same op order per output (bias, k ascending, fmaf): sigma / rgb of the tiled forward equal the per-thread kernel's."""
+    """Same op order per output (bias, k ascending, fmaf): sigma of the tiled forward equals the per-thread kernel's bit for bit, rgb to 1e-5."""
     from pagnerf_b200 import ops
     from pagnerf_b200._lib import call, ptr, ptr_array
     gen = torch.Generator().manual_seed(M + IN)
@@ -1202,7 +1202,7 @@ def test_tiled_dc_forward_equals_one_sample_per_thread(cuda_lib, M, IN, S):
         call(entry, ptr(feats), ptr(lodw), ptr(ray_d), S, M, IN, ptr_array(w), 64, 27, 1, ptr(sigma), ptr(rgb))
         res.append((sigma, rgb))
     assert torch.equal(res[0][0], res[1][0])
-    assert float((res[0][1] - res[1][1]).abs().max()) <= 2e-7
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-5      # colour: the tiled kernel builds the view embedding's octaves by angle doubling
     sigma_only = torch.full((M,), -7.0, device=DEV)
     call("pag_decode_dc_fwd_tiled", ptr(feats), None, None, S, M, IN, ptr_array(w), 64, 27, 0, ptr(sigma_only), None)
     call("pag_decode_dc_fwd", ptr(feats), None, ptr(ray_d), S, M, IN, ptr_array(w), 64, 27, 0, ptr(res[0][0]), None)
