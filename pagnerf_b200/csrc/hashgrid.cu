@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(128) hash_fwd_kernel(const float* __restrict__
         x = __half2float(__float2half_rn(x)); y = __half2float(__float2half_rn(y)); z = __half2float(__float2half_rn(z));
     }
     float2* orow = reinterpret_cast<float2*>(out + m * (int64_t)(2 * L));
+    const bool row16 = !IMG16 && !(L & 1);   // 16-byte aligned f32 rows: two levels per store (see permuto_fwd_kernel)
+    float2 prev = make_float2(0.f, 0.f);
 #pragma unroll 2
     for (int l = 0; l < L; ++l) {
         Cell c;
@@ -137,7 +139,9 @@ __global__ void __launch_bounds__(128) hash_fwd_kernel(const float* __restrict__
                 acc.x = __half2float(__float2half_rn(acc.x));
                 acc.y = __half2float(__float2half_rn(acc.y));
             }
-            orow[l] = acc;
+            if (!row16) orow[l] = acc;
+            else if (l & 1) reinterpret_cast<float4*>(orow)[l >> 1] = make_float4(prev.x, prev.y, acc.x, acc.y);
+            else prev = acc;
         }
     }
     if (IMG16) {      // partially filled chunk (L % 4 != 0) and the all-zero padding chunks up to nXc

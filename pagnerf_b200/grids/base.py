@@ -47,9 +47,14 @@ class BLASGrid(nn.Module):
             self.blas_init(state_dict[key])
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
-    def raymarch(self, rays, level=None, num_samples=64, raymarch_type='voxel'):
+    # interpolate() of the grids built on this base looks features up by position only: tracers may ask the marcher to skip the
+    # octree point indices (need_pidx=False)
+    interpolate_needs_pidx = False
+
+    def raymarch(self, rays, level=None, num_samples=64, raymarch_type='voxel', need_pidx=True):
         """Wrapper over OctreeAS.raymarch at blas_level (reference grids/occtree.py:85-91)."""
-        return self.blas.raymarch(rays, level=self.blas_level, num_samples=num_samples, raymarch_type=raymarch_type)
+        return self.blas.raymarch(rays, level=self.blas_level, num_samples=num_samples, raymarch_type=raymarch_type,
+                                  need_pidx=need_pidx)
 
     def raytrace(self, rays, level=None, with_exit=False):
         return self.blas.raytrace(rays, level=self.blas_level, with_exit=with_exit)

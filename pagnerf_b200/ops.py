@@ -75,6 +75,35 @@ def raymarch_ray(octree, prefix, origins, dirs, level, num_samples, dist_min, di
     return ridx, pidx, samples, depths, deltas, boundary, offsets
 
 
+def raymarch_ray_bits(bits, origins, dirs, level, num_samples, dist_min, dist_max, seed=0):
+    """'ray' mode against the occupancy bit field of `level` (OctreeAS.level_bits): one cached word per step instead of an octree
+    descent, no point indices.  Same samples, bit for bit, as raymarch_ray.  Returns ridx i64[M], None, samples f32[M,1,3],
+    depths f32[M,1], deltas f32[M,1], boundary bool[M], offsets i64[N+1]."""
+    _chk(bits, origins, dirs)
+    o, d = _f32(origins), _f32(dirs)
+    N, S, dev = o.shape[0], int(num_samples), o.device
+    lin = _linspace(S, dev)
+    masks = torch.empty(max(N, 1) * ((S + 31) // 32), dtype=torch.int32, device=dev)
+    counts = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+    offsets = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    near, rng = float(dist_min), float(torch.tensor(float(dist_max) - float(dist_min), dtype=torch.float32))
+    call("pag_march_ray_bits_count", ptr(o), ptr(d), N, S, ptr(lin), None, int(seed), near, rng, ptr(bits), int(level),
+         ptr(masks), ptr(counts), ptr(offsets), None)
+    M = int(offsets[-1].item())  # the one host sync the tensor-shaped plugin API needs
+    ridx = torch.empty(M, dtype=torch.int64, device=dev)
+    samples = torch.empty(M, 1, 3, dtype=torch.float32, device=dev)
+    depths = torch.empty(M, 1, dtype=torch.float32, device=dev)
+    deltas = torch.empty(M, 1, dtype=torch.float32, device=dev)
+    if M:
+        call("pag_march_ray_bits_emit", ptr(o), ptr(d), N, S, ptr(lin), None, int(seed), near, rng, ptr(masks), ptr(offsets),
+             ptr(ridx), ptr(samples), ptr(depths), ptr(deltas), None)
+    # pack boundaries without a second host sync: rays with samples mark their first packed row (empty rays add 0 at the next ray's row)
+    first = torch.zeros(M + 1, dtype=torch.int32, device=dev)
+    first.scatter_add_(0, offsets[:-1], (counts[:N] > 0).to(torch.int32))
+    boundary = first[:M] > 0
+    return ridx, None, samples, depths, deltas, boundary, offsets
+
+
 def raytrace(octree, prefix, origins, dirs, level):
     """kaolin unbatched_raytrace(return_depth=True, with_exit=True) -> ridx i64[K], pidx i64[K], depth f32[K,2], offsets."""
     _chk(octree, prefix, origins, dirs)

@@ -203,10 +203,12 @@ class OctreeAS:
         ridx, pidx, depth, _ = ops.raytrace(self.octree, self.prefix, rays.origins, rays.dirs, lvl)
         return ridx, pidx, (depth if with_exit else depth[:, :1])
 
-    def raymarch(self, rays, level=None, num_samples=64, raymarch_type='voxel'):
+    def raymarch(self, rays, level=None, num_samples=64, raymarch_type='voxel', need_pidx=True):
         """-> (ridx, pidx, samples, depths, deltas, boundary) with the shapes of wisp v0.1.1
         (SURVEY Appendix A.4).  Sample positions stay attached to rays.origins / rays.dirs for
-        pose optimisation (pc_nerf/ba_pipeline.py:49-51)."""
+        pose optimisation (pc_nerf/ba_pipeline.py:49-51).
+        need_pidx=False ('ray' mode; callers whose grid does not index features by octree point): pidx is None and the march
+        runs against the occupancy bit field -- the same samples from a 4-5x cheaper kernel pair."""
         self.to(rays.origins.device)
         lvl = self.max_level if level is None else level
         seed = self.jitter_seed
@@ -219,8 +221,12 @@ class OctreeAS:
                 self.octree, self.prefix, rays.origins, rays.dirs, lvl, num_samples, seed=seed)
             row_offsets = offsets * int(num_samples)
         elif raymarch_type == 'ray':
-            ridx, pidx, samples, depths, deltas, boundary, offsets = ops.raymarch_ray(
-                self.octree, self.prefix, rays.origins, rays.dirs, lvl, num_samples, dmin, dmax, seed=seed)
+            if not need_pidx and 2 <= lvl <= 8:          # bit field of level 8: 2 MB
+                ridx, pidx, samples, depths, deltas, boundary, offsets = ops.raymarch_ray_bits(
+                    self.level_bits(lvl), rays.origins, rays.dirs, lvl, num_samples, dmin, dmax, seed=seed)
+            else:
+                ridx, pidx, samples, depths, deltas, boundary, offsets = ops.raymarch_ray(
+                    self.octree, self.prefix, rays.origins, rays.dirs, lvl, num_samples, dmin, dmax, seed=seed)
             row_offsets = offsets
         else:
             raise TypeError(f"raymarch type {raymarch_type} is wrong, use 'voxel' or 'ray'")

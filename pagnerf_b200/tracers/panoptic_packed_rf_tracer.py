@@ -58,8 +58,9 @@ class PanopticPackedRFTracer(PackedRFTracer):
                         outputs[name] = val
                 return RenderBuffer(**outputs)
 
+        kw = {} if getattr(nef.grid, 'interpolate_needs_pidx', True) else {'need_pidx': False}
         ridx, pidx, samples, depths, deltas, boundary = nef.grid.raymarch(
-            rays, level=nef.grid.active_lods[lod_idx], num_samples=num_steps, raymarch_type=raymarch_type)
+            rays, level=nef.grid.active_lods[lod_idx], num_samples=num_steps, raymarch_type=raymarch_type, **kw)
         S = samples.shape[1]
 
         if raymarch_type == 'voxel' and depths.numel() != 0:
@@ -67,7 +68,7 @@ class PanopticPackedRFTracer(PackedRFTracer):
             first = ops.ray_offsets(ridx, N)
             valid_mask = ops.max_travel_mask(ridx, depths, first, self.ray_max_travel)
             deltas = deltas.reshape(depths.shape)[valid_mask].reshape(-1, 1)
-            ridx, pidx, samples, depths = ridx[valid_mask], pidx[valid_mask], samples[valid_mask], depths[valid_mask]
+            ridx, pidx, samples, depths = ridx[valid_mask], (pidx[valid_mask] if pidx is not None else None), samples[valid_mask], depths[valid_mask]
 
         offsets = ops.ray_offsets(ridx, N) * S        # packed sample range of every ray (empty rays: lo == hi)
         self.last_num_samples, self._last_ridx = int(ridx.shape[0]) * S, ridx

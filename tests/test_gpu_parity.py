@@ -115,6 +115,11 @@ def test_raymarch_ray_bit_exact(cuda_lib, S):
     got2 = ops.raymarch_ray(blas.octree, blas.prefix, torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), level, S, 0.0, 2.5,
                             jitter=torch.from_numpy(jit).to(DEV))
     assert torch.equal(got2[2], got[2]) and torch.equal(got2[0], got[0])
+    # the occupancy-bit-field marcher behind raymarch(need_pidx=False): same packed samples, bit for bit, no point indices
+    got3 = ops.raymarch_ray_bits(blas.level_bits(level), torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), level, S, 0.0, 2.5, seed=5)
+    assert got3[1] is None
+    for i in (0, 2, 3, 4, 5, 6):
+        assert torch.equal(got3[i], got[i]), names[i] if i < 6 else "offsets"
 
 
 def test_raymarch_voxel_bit_exact_and_filter(cuda_lib):
