@@ -2,9 +2,9 @@
 //
 // decoder.cu keeps one sample per thread: every FFMA needs its own shared-memory weight operand and the instance head's
 // 200 logits per sample go through global memory twice (logits -> softmax -> composite kernel).  ncu on the 1 MP frame
-// (profiles/r02_ncu_full.md): pan_fwd 120 ms, dc_fwd 36 ms of a 186 ms frame, FFMA pipe 23 % busy.  Here a CTA owns a
-// 128-sample tile held k-major in shared memory ([k][128+4] floats) and every thread accumulates an 8-sample x 4-output
-// (8 x 13 for the instance logits) register block -- 16 (52) packed FFMA2 per 3 (9) LDS -- and the instance / semantic
+// (profiles/r02_ncu_tiled.md): pan_fwd 120 ms, dc_fwd 36 ms of a 186 ms frame, FFMA pipe 16-23 % busy.  Here a group of threads
+// owns a 64- or 128-sample tile held k-major in shared memory ([k][ROWS+4] floats) and every thread accumulates an 8-sample x
+// 4-output (8 x 13 for the instance logits) register block -- 16 (52) packed FFMA2 per 3 (9) LDS -- and the instance / semantic
 // probabilities are composited straight from registers into the per-ray maps (red.add), never written per sample.
 // Arithmetic order per output is the same as decoder.cu (bias, then k ascending, fmaf), so hidden activations (and the density) are
 // bit-identical to that path; the composited sums differ in association only, the colour through the view embedding's
