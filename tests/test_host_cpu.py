@@ -101,6 +101,34 @@ def test_plugin_surface_and_state_dict_keys():
     assert torch.equal(nef2.grid.blas.octree.cpu(), oc) and nef2.grid.blas.max_level == 3
 
 
+def test_decoder_kernel_family_selection():
+    """Which decoder kernels a call gets (host logic only): tensor cores under autocast; exact FP32 otherwise -- the register-tiled
+    forward kernels only when nothing is differentiated, the one-sample-per-thread kernels (they have a backward) under grad."""
+    import bench
+    from pagnerf_b200 import ops
+    from pagnerf_b200.pc_nerf import PanopticDeltaNeF
+    assert ops.dc_mode(True, 48) is True
+    assert ops.dc_mode(False, 48) is False
+    with torch.no_grad():
+        assert ops.dc_mode(False, 48) == 'tiled' and ops.dc_mode(False, 30) is False and ops.dc_mode(True, 48) is True
+    nef = PanopticDeltaNeF(**dict(bench.NEF_KW, blas_level=3, capacity_log_2=8, delta_capacity_log_2=7))
+    chans = {'rgb', 'semantics', 'inst_embedding'}
+    nef.decoder_precision = 'fp32'
+    assert not nef.fused_panoptic_ok(chans)
+    with torch.no_grad():
+        assert nef.fused_panoptic_ok(chans) and not nef.fused_panoptic_ok({'rgb'})
+        tiled0, ops.TILED_F32 = ops.TILED_F32, False
+        try:
+            assert not nef.fused_panoptic_ok(chans)
+        finally:
+            ops.TILED_F32 = tiled0
+    nef.decoder_precision = 'fp16'
+    assert nef.fused_panoptic_ok(chans)
+    nef.decoder_precision = 'auto'
+    assert not nef._use_tc()
+    assert nef.grid.interpolate_needs_pidx is False          # the tracer may march without octree point indices
+
+
 def test_dd_plugin_surface():
     """PanopticDDensityNeF / PanopticDDensityPackedRFTracer: reference names, channels and state_dict keys
     (pc_nerf/panoptic_dd_nef.py:41-58,121-128; tracers/panoptic_dd_packed_rf_tracer.py)."""
