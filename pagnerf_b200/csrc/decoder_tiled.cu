@@ -17,7 +17,8 @@
 // ROWS = samples per tile; a tile is worked by a GROUP of 2 * ROWS threads with its own named barrier; a CTA holds NG groups that
 // walk their own tiles and share the staged weights (one group's staging / epilogue / barrier wait is filled by the others' FMA
 // phases).  Measured on the 1 MP frame: density + colour 21.0 ms with 1 x 128 rows, 18.7 ms with 3 x 64; the panoptic heads (whose
-// weights leave room for two 64-row groups only) 35.9 ms with 1 x 128, 38.0 ms with 2 x 64.
+// weights leave room for two 64-row groups only) 35.9 ms with 1 x 128, 38.0 ms with 2 x 64 (36.6 vs 36.7 ms after the class-pair
+// loads: decoupling the phases is not what the heads kernel lacks).
 #define TL_LDA(ROWS) ((ROWS) + 4)
 #define TL_BUF(ROWS) (H * TL_LDA(ROWS))   // one activation buffer [64][ROWS+4]; also holds a raw [ROWS][IN <= 64] row block
 #define PAN_ROWS 128
