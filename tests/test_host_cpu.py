@@ -129,6 +129,22 @@ def test_decoder_kernel_family_selection():
     assert nef.grid.interpolate_needs_pidx is False          # the tracer may march without octree point indices
 
 
+def test_view_embedding_double_angle_recurrence_error_bound():
+    """csrc/decoder_tiled.cu builds the octaves sin / cos(2^f v), f = 1..3, from one sincos per component by angle doubling in
+    fp32; the comment there promises <= 1e-6 absolute against the directly evaluated embedding for |v| <= 1 (unit directions)."""
+    import numpy as np
+    v = np.linspace(-1.0, 1.0, 200001).astype(np.float32)
+    sn, cs = np.sin(v.astype(np.float64)).astype(np.float32), np.cos(v.astype(np.float64)).astype(np.float32)
+    worst = 0.0
+    for f in range(4):
+        a = v.astype(np.float64) * (1 << f)
+        worst = max(worst, float(np.abs(sn - np.sin(a)).max()), float(np.abs(cs - np.cos(a)).max()))
+        s2 = (np.float32(2.0) * sn) * cs
+        c2 = (np.float32(-2.0) * sn).astype(np.float64) * sn.astype(np.float64) + 1.0      # fmaf(-2 sn, sn, 1): one rounding
+        sn, cs = s2.astype(np.float32), c2.astype(np.float32)
+    assert worst <= 1e-6, worst
+
+
 def test_dd_plugin_surface():
     """PanopticDDensityNeF / PanopticDDensityPackedRFTracer: reference names, channels and state_dict keys
     (pc_nerf/panoptic_dd_nef.py:41-58,121-128; tracers/panoptic_dd_packed_rf_tracer.py)."""
